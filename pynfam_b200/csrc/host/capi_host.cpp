@@ -1,0 +1,149 @@
+// C ABI of the host set-up library (libpnfam_host.so): declared in include/pnfam_b200.h.
+#include <cstring>
+#include <map>
+#include <string>
+
+#include "../../../include/pnfam_b200.h"
+#include "problem.hpp"
+
+using namespace pnfam;
+
+struct pnfam_problem {
+  std::unique_ptr<Problem> p;
+  std::map<std::string, std::vector<double>> f64_cache;
+  std::map<std::string, std::vector<int32_t>> i32_cache;
+};
+
+static void set_err(char* err, int errlen, const std::string& s) {
+  if (err && errlen > 0) {
+    std::strncpy(err, s.c_str(), (size_t)errlen - 1);
+    err[errlen - 1] = 0;
+  }
+}
+
+extern "C" {
+
+int pnfam_problem_create(const char* rundir, const char* namelist_file, pnfam_problem** out, char* err, int errlen) {
+  try {
+    auto h = new pnfam_problem;
+    h->p = Problem::load(rundir ? rundir : ".", namelist_file ? namelist_file : "pnfam_NAMELIST.dat");
+    *out = h;
+    return 0;
+  } catch (const std::exception& e) {
+    set_err(err, errlen, e.what());
+    return 1;
+  }
+}
+
+int pnfam_problem_create_shared(const pnfam_problem* nucleus_of, const char* rundir, const char* namelist_file,
+                                pnfam_problem** out, char* err, int errlen) {
+  try {
+    auto h = new pnfam_problem;
+    h->p = Problem::load(rundir ? rundir : ".", namelist_file, nucleus_of->p->nuc);
+    *out = h;
+    return 0;
+  } catch (const std::exception& e) {
+    set_err(err, errlen, e.what());
+    return 1;
+  }
+}
+
+void pnfam_problem_destroy(pnfam_problem* p) { delete p; }
+
+int pnfam_problem_scalar(const pnfam_problem* h, const char* name, double* out) {
+  const Problem& p = *h->p;
+  const FamBasis& b = p.nuc->basis;
+  const Interaction& x = p.inter;
+  const FamInput& in = p.in;
+  const std::string n(name);
+  std::map<std::string, double> m = {
+      {"nb", b.nb}, {"dqp", b.dqp}, {"nghl", b.nghl}, {"n_shells", b.n_shells}, {"dmat", (double)b.dmat},
+      {"npr_n", b.npr[0]}, {"npr_p", b.npr[1]}, {"nxy", (double)p.f.mat.elem.size()}, {"nxterms", (double)p.g.size()},
+      {"beta_minus", p.f.beta_minus}, {"blo_active", b.blo_active},
+      {"blo_qp_n", b.blo_qp[0]}, {"blo_qp_p", b.blo_qp[1]},
+      {"skip_residual", x.skip_residual},
+      {"cdrho", x.cdrho}, {"ctau", x.ctau}, {"ctj0", x.ctj0}, {"ctj1", x.ctj1}, {"ctj2", x.ctj2}, {"crdj", x.crdj},
+      {"cds", x.cds}, {"ct", x.ct}, {"cj", x.cj}, {"cgs", x.cgs}, {"cf", x.cf}, {"csdj", x.csdj},
+      {"cr0", x.cr0}, {"crr", x.crr}, {"cs0", x.cs0}, {"csr", x.csr}, {"sigma_r", x.sigma_r},
+      {"cpair0", x.cpair0}, {"cpairr", x.cpairr}, {"cspair0", x.cspair0}, {"cspairr", x.cspairr},
+      {"real_eqrpa", in.real_eqrpa}, {"imag_eqrpa", in.imag_eqrpa}, {"max_iter", in.max_iter},
+      {"broyden_history_size", in.broyden_history_size}, {"convergence_epsilon", in.convergence_epsilon},
+      {"quench_residual_int", x.skip_residual ? 0.0 : in.quench_residual_int},
+      {"energy_shift_prot", in.energy_shift_prot}, {"energy_shift_neut", in.energy_shift_neut},
+      {"ala_n", p.nuc->hfb.ala[0]}, {"ala_p", p.nuc->hfb.ala[1]},
+      {"inner_n", p.nuc->hfb.inner[0]}, {"inner_p", p.nuc->hfb.inner[1]},
+      {"setup_seconds", p.setup_seconds},
+  };
+  auto it = m.find(n);
+  if (it == m.end()) return 1;
+  *out = it->second;
+  return 0;
+}
+
+int pnfam_problem_array_f64(pnfam_problem* h, const char* name, const double** ptr, int64_t* n) {
+  const Problem& p = *h->p;
+  const FamBasis& b = p.nuc->basis;
+  const HfbSolution& s = p.nuc->hfb;
+  const Interaction& x = p.inter;
+  const std::string nm(name);
+  const std::vector<double>* v = nullptr;
+  std::map<std::string, const std::vector<double>*> m = {
+      {"wf", &b.wf}, {"wfdr", &b.wfdr}, {"wfdz", &b.wfdz}, {"wfd2", &b.wfd2}, {"wfdp", &b.wfdp}, {"wfd2_all", &b.wfd2_all},
+      {"y", &b.y}, {"z", &b.z}, {"wdcori", &b.wdcori}, {"Ep", &b.Ep}, {"En", &b.En},
+      {"Up", &b.Up}, {"Vp", &b.Vp}, {"Un", &b.Un}, {"Vn", &b.Vn}, {"rho_n", &b.rho_n}, {"rho_p", &b.rho_p},
+      {"qp_fn", &b.qp_fn}, {"qp_fp", &b.qp_fp},
+      {"crho", &x.crho}, {"cs", &x.cs}, {"cpair", &x.cpair}, {"cspair", &x.cspair},
+      {"f_elem", &p.f.mat.elem},
+      {"hfb_hmat_n", &s.hmat[0]}, {"hfb_hmat_p", &s.hmat[1]}, {"hfb_dmat_n", &s.dmat[0]}, {"hfb_dmat_p", &s.dmat[1]},
+      {"hfb_E_n", &s.E[0]}, {"hfb_E_p", &s.E[1]}, {"hfb_U_n", &s.U[0]}, {"hfb_V_n", &s.V[0]},
+      {"hfb_U_p", &s.U[1]}, {"hfb_V_p", &s.V[1]}, {"hel_ro", &p.nuc->hel.ro},
+  };
+  auto it = m.find(nm);
+  if (it != m.end()) v = it->second;
+  if (!v && nm.rfind("g_elem_", 0) == 0) {
+    size_t i = (size_t)std::stoi(nm.substr(7));
+    if (i < p.g.size()) v = &p.g[i].mat.elem;
+  }
+  if (!v) return 1;
+  *ptr = v->data();
+  *n = (int64_t)v->size();
+  return 0;
+}
+
+int pnfam_problem_array_i32(pnfam_problem* h, const char* name, const int32_t** ptr, int64_t* n) {
+  const Problem& p = *h->p;
+  const FamBasis& b = p.nuc->basis;
+  const std::string nm(name);
+  const std::vector<int>* v = nullptr;
+  std::map<std::string, const std::vector<int>*> m = {
+      {"db", &b.db}, {"isstart", &b.isstart}, {"nr", &b.nr}, {"nz", &b.nz}, {"nl", &b.nl}, {"ns", &b.ns},
+      {"npar", &b.npar}, {"num_spin_up", &b.num_spin_up},
+      {"f_ir2c", &p.f.mat.ir2c}, {"f_ic2r", &p.f.mat.ic2r}, {"f_ir2m", &p.f.mat.ir2m}, {"f_ic2m", &p.f.mat.ic2m},
+      {"hfb_id", &p.nuc->hfb.id},
+  };
+  auto it = m.find(nm);
+  if (it != m.end()) v = it->second;
+  if (!v && nm.rfind("g_ir2c_", 0) == 0) {
+    size_t i = (size_t)std::stoi(nm.substr(7));
+    if (i < p.g.size()) v = &p.g[i].mat.ir2c;
+  }
+  if (!v) return 1;
+  static_assert(sizeof(int) == sizeof(int32_t), "int must be 32-bit");
+  *ptr = reinterpret_cast<const int32_t*>(v->data());
+  *n = (int64_t)v->size();
+  return 0;
+}
+
+int pnfam_problem_label(const pnfam_problem* h, int which, char* out, int outlen) {
+  const Problem& p = *h->p;
+  std::string s;
+  if (which == 0) s = p.f.label;
+  else if (which >= 1 && (size_t)which <= p.g.size()) s = p.g[which - 1].label;
+  else if (which == -1) s = p.inter.name;
+  else if (which == -2) s = p.in.fam_output_filename;
+  else return 1;
+  set_err(out, outlen, s);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,106 @@
+// Host-side FAM set-up: everything pnfam_main.x prepares before entering the iteration
+// (exes/pnfam/pnfam_solver.f90:44-62): the time-reversal-doubled, spin-sorted basis
+// (hfbtho_solution.f90:137-459), the residual-interaction couplings (pnfam_interaction.f90:90-260),
+// the external-field matrices and their block maps (pnfam_extfield.f90:37-108,110-622,763-840,
+// 882-949) and the pnFAM namelist (pnfam_setup.f90:98-108,178-250).
+#pragma once
+#include <array>
+#include <string>
+#include <vector>
+
+#include "hfb_front.hpp"
+
+namespace pnfam {
+
+// Block-sparse matrix with at most one non-zero block per block row/column
+// (pnfam_type_blockmatrix.f90:15-26).  Blocks are stored in increasing block-row order,
+// column-major inside a block; ir2c/ic2r are 1-based partner indices (0 = none), ir2m/ic2m are
+// 1-based offsets into elem.
+struct BlockMatrix {
+  std::vector<int> ir2c, ic2r, ir2m, ic2m;
+  std::vector<double> elem;
+  void init(int nb, size_t n) {
+    ir2c.assign(nb, 0); ic2r.assign(nb, 0); ir2m.assign(nb, 0); ic2m.assign(nb, 0);
+    elem.assign(n, 0.0);
+  }
+};
+
+// The pnFAM namelist (&general &ext_field &interaction &solver), defaults of pnfam_setup.f90:178-210.
+struct FamInput {
+  std::string namelist_path = "pnfam_NAMELIST.dat";
+  // general
+  std::string fam_output_filename;
+  bool print_stdout = true;
+  int use_fam_storage = 0;
+  double real_eqrpa = 0.0, imag_eqrpa = 0.5;
+  // ext_field
+  std::string beta_type = "-", operator_name = "F";
+  int operator_k = 0;
+  bool compute_crossterms = false;
+  int two_body_current_mode = 0;
+  bool two_body_current_usep = false;
+  double two_body_current_lecs[3] = {-3.4, 5.4, 0.0};
+  // solver
+  int max_iter = 200, broyden_history_size = 50;
+  double convergence_epsilon = 1e-7, energy_shift_prot = 0, energy_shift_neut = 0, quench_residual_int = 1.0;
+  // interaction
+  std::string interaction_name = "NONE";
+  bool require_self_consistency = true, require_gauge_invariance = false, force_j2_terms = false;
+  bool has_vpair0 = false, has_vpair1 = false, has_vpair_t0 = false, has_vpair_t1 = false;
+  double vpair0 = 0, vpair1 = 0, vpair_t0 = 0, vpair_t1 = 0;
+  // overrides: cs0 csr cds ct cf cgs cj csdj
+  bool has_override[8] = {false, false, false, false, false, false, false, false};
+  double override_val[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+
+  static FamInput read(const std::string& path);
+};
+
+// Doubled (explicit time-reversed partners), spin-sorted single-particle basis + HFB solution.
+struct FamBasis {
+  int nb = 0, dqp = 0, nghl = 0, n_shells = 0;
+  size_t dmat = 0;
+  int npr[3] = {0, 0, 0};
+  std::vector<int> db, isstart;          // isstart 1-based like the reference
+  std::vector<int> nr, nz, nl, ns, npar, num_spin_up;
+  std::vector<double> wf, wfdr, wfdz, wfd2, wfdp, wfd2_all;  // (nghl, dqp) column-major
+  std::vector<double> y, z, wdcori;
+  std::vector<double> Ep, En, Up, Vp, Un, Vn;
+  std::vector<double> rho_n, rho_p;      // coordinate-space densities (normalised)
+  bool blo_active = false;
+  int blo_qp[2] = {0, 0};                // 1-based overall qp index of the blocked level (n, p)
+  int blo_ib[2] = {0, 0}, blo_is[2] = {0, 0};
+  std::vector<double> qp_fn, qp_fp;      // equal-filling occupations (only if blo_active)
+  // functional data handed over from HFBTHO
+  double hfb_cpair[2] = {0, 0}, hfb_alpha_pair[2] = {0, 0}, rho_nm = 0.16, hbzero = 0;
+  double hfb_cr0 = 0, hfb_crr = 0, hfb_cdrho = 0, hfb_ctau = 0, hfb_ctj = 0, hfb_crdj = 0;
+  bool hfb_use_j2terms = false;
+
+  static FamBasis build(const HfbSolution& s);
+};
+
+// Residual interaction couplings (pnfam_interaction.f90).
+struct Interaction {
+  bool skip_residual = false;
+  std::string name;
+  double cr0 = 0, crr = 0, cs0 = 0, csr = 0, sigma_r = 0, sigma_s = 0;
+  double cpair0 = 0, cpairr = 0, cspair0 = 0, cspairr = 0, sigma_pair = 1;
+  double cdrho = 0, ctau = 0, ctj0 = 0, ctj1 = 0, ctj2 = 0, crdj = 0, cds = 0, ct = 0, cj = 0, cgs = 0, cf = 0, csdj = 0;
+  std::vector<double> crho, cs, cpair, cspair;  // (nghl)
+  std::vector<std::string> notes;               // "[!] ..." lines for the log
+
+  static Interaction build(const FamInput& in, const FamBasis& b);
+};
+
+struct ExtField {
+  std::string label;
+  bool beta_minus = true, parity_even = true;
+  int k = 0, rank = 0;
+  BlockMatrix mat;
+};
+
+ExtField make_external_field(const FamBasis& b, const std::string& beta_type, const std::string& label, int k);
+std::vector<ExtField> make_crossterms(const FamBasis& b, const ExtField& op);
+// Read the Yukawa part of a two-body-current field from <name>.tbc (pnfam_storage.f90:562-727).
+bool read_tbc(const std::string& path, const FamBasis& b, const FamInput& in, ExtField& f, std::string& why);
+
+}  // namespace pnfam

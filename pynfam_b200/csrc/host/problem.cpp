@@ -1,0 +1,59 @@
+#include "problem.hpp"
+
+#include <chrono>
+#include <stdexcept>
+
+namespace pnfam {
+
+std::shared_ptr<Nucleus> Nucleus::load(const std::string& rundir) {
+  auto n = std::make_shared<Nucleus>();
+  const std::string d = rundir.empty() ? std::string(".") : rundir;
+  // file names are hard-coded in the reference (hfbtho_interface.f90:33, hfbtho_io.f90:209)
+  n->hfb_in = HfbInput::read(d + "/hfbtho_NAMELIST.dat");
+  n->hel = HelData::read(d + "/hfbtho_output.hel");
+  n->hfb = HfbSolution::build(n->hfb_in, n->hel);
+  n->basis = FamBasis::build(n->hfb);
+  return n;
+}
+
+static int digit(int v, int p) {
+  for (int i = 0; i < p; i++) v /= 10;
+  return v % 10;
+}
+
+std::unique_ptr<Problem> Problem::load(const std::string& rundir, const std::string& namelist,
+                                       std::shared_ptr<Nucleus> nuc) {
+  auto t0 = std::chrono::steady_clock::now();
+  auto p = std::make_unique<Problem>();
+  const std::string d = rundir.empty() ? std::string(".") : rundir;
+  std::string nml = namelist;
+  if (!nml.empty() && nml[0] != '/') nml = d + "/" + nml;
+  p->in = FamInput::read(nml);
+  p->nuc = nuc ? nuc : Nucleus::load(d);
+  FamBasis& b = p->nuc->basis;
+  p->inter = Interaction::build(p->in, b);
+  const FamInput& in = p->in;
+  // external field (pnfam_solver.f90:556-654)
+  const int mode = in.two_body_current_mode;
+  int u[7] = {0, 0, 0, 0, 0, 0, 0};
+  if (mode != 0) {
+    u[1] = digit(mode, 5); u[2] = digit(mode, 4); u[3] = digit(mode, 3);
+    u[4] = digit(mode, 2); u[5] = digit(mode, 1); u[6] = digit(mode, 0);
+    if (u[1] < 1 || u[1] > 2 || u[2] < 1 || u[2] > 5 || u[3] < 1 || u[3] > 3 || (u[1] != 1 && u[3] != 1))
+      throw std::runtime_error("Invalid value supplied for two_body_current_mode.");
+    if (u[3] != 1) throw std::runtime_error("This two_body_current_mode is not yet operational.");
+    if (u[5] != 0 || u[6] != 0 || u[4] >= 2)
+      throw std::runtime_error("two-body-current corrections to P / PS0 / RS* operators are not supported yet");
+  }
+  p->f = make_external_field(b, in.beta_type, in.operator_name, in.operator_k);
+  if (in.compute_crossterms) p->g = make_crossterms(b, p->f);
+  if (mode != 0 && p->f.label == "GT" && u[4] != 0) {
+    std::string why;
+    if (!read_tbc(d + "/" + in.fam_output_filename + ".tbc", b, in, p->f, why))
+      throw std::runtime_error("two_body_current_mode=" + std::to_string(mode) + ": " + why);
+  }
+  p->setup_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return p;
+}
+
+}  // namespace pnfam

@@ -1,0 +1,31 @@
+// One pnFAM problem as pnfam_main.x sees it: a working directory holding hfbtho_NAMELIST.dat +
+// hfbtho_output.hel and one pnFAM namelist -> basis, HFB solution, interaction, external field(s).
+#pragma once
+#include <map>
+#include <memory>
+#include <string>
+
+#include "fam_setup.hpp"
+
+namespace pnfam {
+
+struct Nucleus {  // everything that depends only on the HFB files (shared by all operators / omegas)
+  HfbInput hfb_in;
+  HelData hel;
+  HfbSolution hfb;
+  FamBasis basis;
+  static std::shared_ptr<Nucleus> load(const std::string& rundir);
+};
+
+struct Problem {
+  std::shared_ptr<Nucleus> nuc;
+  FamInput in;
+  Interaction inter;
+  ExtField f;
+  std::vector<ExtField> g;
+  double setup_seconds = 0;
+  static std::unique_ptr<Problem> load(const std::string& rundir, const std::string& namelist,
+                                       std::shared_ptr<Nucleus> nuc = nullptr);
+};
+
+}  // namespace pnfam

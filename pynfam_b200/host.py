@@ -1,0 +1,101 @@
+"""ctypes view of libpnfam_host.so (section 1 of include/pnfam_b200.h): the host set-up that the
+reference performs in Fortran before entering the FAM iteration (pnfam_solver.f90:44-62)."""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "lib", "libpnfam_host.so")
+        if not os.path.isfile(path):
+            raise RuntimeError("libpnfam_host.so is not built: run `python -c 'import __graft_entry__ as g; g.build()'`"
+                               " or `make -C pynfam_b200/csrc`")
+        L = ctypes.CDLL(path)
+        vp, cp, ci = ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int
+        L.pnfam_problem_create.argtypes = [cp, cp, ctypes.POINTER(vp), cp, ci]
+        L.pnfam_problem_create_shared.argtypes = [vp, cp, cp, ctypes.POINTER(vp), cp, ci]
+        L.pnfam_problem_destroy.argtypes = [vp]
+        L.pnfam_problem_destroy.restype = None
+        L.pnfam_problem_scalar.argtypes = [vp, cp, ctypes.POINTER(ctypes.c_double)]
+        L.pnfam_problem_array_f64.argtypes = [vp, cp, ctypes.POINTER(ctypes.POINTER(ctypes.c_double)),
+                                              ctypes.POINTER(ctypes.c_int64)]
+        L.pnfam_problem_array_i32.argtypes = [vp, cp, ctypes.POINTER(ctypes.POINTER(ctypes.c_int32)),
+                                              ctypes.POINTER(ctypes.c_int64)]
+        L.pnfam_problem_label.argtypes = [vp, ci, cp, ci]
+        _LIB = L
+    return _LIB
+
+
+class PnfamError(RuntimeError):
+    pass
+
+
+class Problem:
+    """One (nucleus, operator, K, omega) problem: what `pnfam_main.x <namelist>` sets up in `rundir`."""
+
+    def __init__(self, rundir, namelist, share_nucleus_with=None):
+        L = lib()
+        self._h = ctypes.c_void_p()
+        err = ctypes.create_string_buffer(1024)
+        if share_nucleus_with is None:
+            rc = L.pnfam_problem_create(os.fsencode(rundir), os.fsencode(namelist), ctypes.byref(self._h), err, 1024)
+        else:
+            rc = L.pnfam_problem_create_shared(share_nucleus_with._h, os.fsencode(rundir), os.fsencode(namelist),
+                                               ctypes.byref(self._h), err, 1024)
+        if rc != 0:
+            self._h = None
+            raise PnfamError(err.value.decode())
+        self.rundir = rundir
+        self.namelist = namelist
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().pnfam_problem_destroy(self._h)
+            self._h = None
+
+    @property
+    def handle(self):
+        return self._h
+
+    def scalar(self, name):
+        v = ctypes.c_double()
+        if lib().pnfam_problem_scalar(self._h, name.encode(), ctypes.byref(v)) != 0:
+            raise KeyError(name)
+        return v.value
+
+    def iscalar(self, name):
+        return int(round(self.scalar(name)))
+
+    def f64(self, name):
+        p = ctypes.POINTER(ctypes.c_double)()
+        n = ctypes.c_int64()
+        if lib().pnfam_problem_array_f64(self._h, name.encode(), ctypes.byref(p), ctypes.byref(n)) != 0:
+            raise KeyError(name)
+        if n.value == 0:
+            return np.zeros(0)
+        return np.ctypeslib.as_array(p, shape=(n.value,)).copy()
+
+    def i32(self, name):
+        p = ctypes.POINTER(ctypes.c_int32)()
+        n = ctypes.c_int64()
+        if lib().pnfam_problem_array_i32(self._h, name.encode(), ctypes.byref(p), ctypes.byref(n)) != 0:
+            raise KeyError(name)
+        if n.value == 0:
+            return np.zeros(0, np.int32)
+        return np.ctypeslib.as_array(p, shape=(n.value,)).copy()
+
+    def label(self, which=0):
+        buf = ctypes.create_string_buffer(256)
+        if lib().pnfam_problem_label(self._h, which, buf, 256) != 0:
+            raise KeyError(which)
+        return buf.value.decode()
+
+    def table(self, name):
+        """(nghl, dqp) wave-function table as a Fortran-ordered 2-D array."""
+        return self.f64(name).reshape(self.iscalar("dqp"), self.iscalar("nghl")).T
