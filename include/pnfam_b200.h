@@ -42,6 +42,90 @@ int pnfam_problem_array_i32(pnfam_problem* p, const char* name, const int32_t** 
 /* which: 0 operator label, 1..nxterms cross-term labels, -1 interaction name, -2 output base name */
 int pnfam_problem_label(const pnfam_problem* p, int which, char* out, int outlen);
 
+/* ------------------------------------------------------------------------------------------------
+ * 2. The FAM iteration on the GPU (libpnfam_b200.so, CUDA sm_100a) -- THE HOT PATH
+ *    replaces: ifam                    exes/pnfam/pnfam_solver.f90:93-221   (whole loop, batched over omega)
+ *              init_pnfam_solver       exes/pnfam/pnfam_solver.f90:226-460  (F -> qp basis, Greens, T)
+ *              calc_hamiltonian (ptr)  exes/pnfam/pnfam_setup.f90:56-71, pnfam_hamiltonian_blas.f90:51-74
+ *              triprod_bbm             exes/pnfam/pnfam_type_bbm.f90:557-576
+ *              qrpa_broyden            exes/pnfam/pnfam_broyden.f90:96-216
+ *    There is NO CPU fallback: every entry point fails with an error if no CUDA device is usable.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct pnfam_b200_ctx pnfam_b200_ctx;
+
+/* Nucleus + residual interaction: the module variables of hfb_solution / pnfam_interaction /
+ * type_blockmatrix that the reference's iteration reads.  Tables are (nghl, dqp) column-major with the
+ * rows of every block sorted spin-up first (hfbtho_solution.f90:309-351). */
+typedef struct {
+  int32_t nb, dqp, nghl;
+  const int32_t* db;            /* [nb]  block dimensions                                   */
+  const int32_t* num_spin_up;   /* [nb]                                                     */
+  const double *wf, *wfdr, *wfdp, *wfdz, *wfd2_all;  /* [nghl*dqp]                          */
+  const double *wdcori, *crho, *cs, *cpair, *cspair; /* [nghl]                              */
+  double cdrho, ctau, ctj0, ctj1, ctj2, crdj, cds, ct, cj, cgs, cf, csdj;
+  const double *Ep, *En;        /* [dqp]  quasiparticle energies (0 above the pairing window) */
+  const double *Up, *Vp, *Un, *Vn; /* [sum db^2] block-diagonal storage (pnfam_setup.f90:292-321) */
+  const double *qp_fp, *qp_fn;  /* [dqp] equal-filling / thermal occupations, or NULL        */
+} pnfam_b200_model;
+
+int pnfam_b200_ctx_create(const pnfam_b200_model* model, int device, pnfam_b200_ctx** out, char* err, int errlen);
+void pnfam_b200_ctx_destroy(pnfam_b200_ctx* ctx);
+
+/* External field f (+ cross-term fields g_k sharing f's block structure), single-particle basis,
+ * as produced by init_external_field / setup_crossterms (pnfam_extfield.f90:37-108, 882-949). */
+typedef struct {
+  int32_t beta_minus;           /* 1: beta-, 0: beta+                                        */
+  int32_t nxterms;
+  const int32_t* f_ir2c;        /* [nb] 1-based partner column block, 0 = none               */
+  const double* f_elem;         /* [nxy]                                                     */
+  const double* const* g_elem;  /* [nxterms][nxy]                                            */
+} pnfam_b200_operator;
+
+typedef struct {
+  int32_t max_iter;             /* &solver max_iter                                          */
+  int32_t broyden_history_size; /* &solver broyden_history_size                              */
+  double convergence_epsilon, quench_residual_int, energy_shift_prot, energy_shift_neut;
+} pnfam_b200_solver_params;
+
+typedef struct {
+  double seconds_total;         /* wall time of the call                                     */
+  double seconds_device;        /* CUDA-event time of the iteration loop                     */
+  int64_t iterations;           /* sum over points of FAM iterations performed               */
+  int64_t kernel_launches;      /* kernels launched by this call                             */
+  int64_t h2d_bytes, d2h_bytes;
+  double seconds_density, seconds_projection; /* CUDA-event time spent in the two dominant kernels */
+  int64_t launches_density, launches_projection;
+} pnfam_b200_stats;
+
+/* Solve npoints complex frequencies of one operator.  Outputs (host buffers):
+ *   strength [npoints][1+nxterms][2]  S and cross-terms (re,im), as the "Result" table of the .dat
+ *   iters    [npoints]                iteration count at exit (iter_conv of ifam), or max_iter
+ *   conv     [npoints]                1 converged, 0 interrupted
+ *   si       [npoints]                last max|dX|
+ *   trace    [npoints][max_iter+1][4] optional (may be NULL): si, Re S, Im S, seconds per iteration */
+int pnfam_b200_solve(pnfam_b200_ctx* ctx, const pnfam_b200_operator* op, const pnfam_b200_solver_params* prm,
+                     int32_t npoints, const double* omega_re, const double* omega_im, double* strength,
+                     int32_t* iters, int32_t* conv, double* si, double* trace, pnfam_b200_stats* stats, char* err,
+                     int errlen);
+
+/* The reference's plug-in point `calc_hamiltonian` (pnfam_setup.f90:56-71): 8 input and 8 output
+ * block matrices in the reference's argument order
+ *   in : rerho_pn imrho_pn rekp imkp rerho_np imrho_np rekm imkm
+ *   out: reh_pn imh_pn redp imdp reh_np imh_np redm imdm
+ * The caller presets ir2c/ir2m of the outputs, exactly as pnfam_solver.f90:402-413 does. */
+typedef struct {
+  double* elem;                 /* [nelem]                                                   */
+  const int32_t* ir2c;          /* [nb] 1-based, 0 = none                                    */
+  const int32_t* ir2m;          /* [nb] 1-based offsets                                      */
+  int64_t nelem;
+} pnfam_b200_blockmatrix;
+int pnfam_b200_calc_hamiltonian(pnfam_b200_ctx* ctx, const pnfam_b200_blockmatrix in[8], pnfam_b200_blockmatrix out[8],
+                                char* err, int errlen);
+
+/* FP64 DMMA (mma.sync m8n8k4) peak probe used for the roofline denominator of the tensor-bound
+ * kernels: returns achieved TFLOP/s of a register-resident DMMA loop on all SMs. */
+int pnfam_b200_dmma_peak(int device, double* tflops, char* err, int errlen);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,78 @@
+// Shared device-side definitions of the B200 FAM iteration (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+
+#define PNFAM_CUDA_CHECK(x)                                                                          \
+  do {                                                                                               \
+    cudaError_t e_ = (x);                                                                            \
+    if (e_ != cudaSuccess)                                                                           \
+      throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " + __FILE__ + ":" + \
+                               std::to_string(__LINE__));                                            \
+  } while (0)
+
+namespace pnfam {
+
+// ---- tiling constants -------------------------------------------------------------------------
+constexpr int RT = 16;        // grid points per r-tile (2 DMMA m-tiles)
+constexpr int RS = 20;        // padded r-stride of a wave-function row in shared memory (bank-conflict free)
+constexpr int NTYPE = 5;      // wf, d/dr, (Lambda/r), d/dz, laplacian_all
+
+// FP64 tensor-core MMA: D(8x8) += A(8x4, row) * B(4x8, col).
+// Fragment layout (PTX ISA, mma.m8n8k4 .f64): lane l holds A[l/4][l%4], B[l%4][l/4],
+// C[l/4][2*(l%4)] and C[l/4][2*(l%4)+1].
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+struct cplx {
+  double re, im;
+};
+__host__ __device__ __forceinline__ cplx operator+(cplx a, cplx b) { return {a.re + b.re, a.im + b.im}; }
+__host__ __device__ __forceinline__ cplx operator-(cplx a, cplx b) { return {a.re - b.re, a.im - b.im}; }
+__host__ __device__ __forceinline__ cplx operator-(cplx a) { return {-a.re, -a.im}; }
+__host__ __device__ __forceinline__ cplx operator*(double s, cplx a) { return {s * a.re, s * a.im}; }
+__host__ __device__ __forceinline__ cplx operator*(cplx a, cplx b) { return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
+__host__ __device__ __forceinline__ cplx mul_i(cplx a) { return {-a.im, a.re}; }     // i * a
+__host__ __device__ __forceinline__ cplx mul_mi(cplx a) { return {a.im, -a.re}; }    // -i * a
+
+// ---- block structures on the device ---------------------------------------------------------------
+struct DevBlockStruct {
+  const int* r2c;   // [nb] partner column block or -1
+  const int* r2m;   // [nb] element offset of the block
+};
+
+struct DevBasis {
+  int nb, dqp, nghl, ntiles;
+  const int* db;        // [nb]
+  const int* isstart;   // [nb] 0-based first state of block
+  const int* nsu;       // [nb] number of spin-up states (they come first inside a block)
+  const double* phi;    // [ntiles][NTYPE][dqp][RT] tile-major wave-function tables
+  const double* wdcori; // [nghl]
+  const double* crho;   // [nghl]
+  const double* cs;
+  const double* cpair;
+  const double* cspair;
+  double cdrho, ctau, ctj0, ctj1, ctj2, crdj, cds, ct, cj, cgs, cf, csdj;
+};
+
+// transform tasks (host/symbolic.hpp flattened)
+struct DevTerm {
+  int a_mat, a_off, a_trans;
+  int b_quad, b_off, b_trans;
+  int c_mat, c_off, c_trans;
+  int t_off;                 // offset of the intermediate op(A)op(B) block in the scratch array
+  double alpha_re, alpha_im;
+};
+struct DevTask {
+  int out_quad, out_off, m, n, nterms;
+  DevTerm t[4];
+};
+
+}  // namespace pnfam

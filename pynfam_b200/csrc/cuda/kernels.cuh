@@ -1,0 +1,103 @@
+// Host-callable launchers of the FAM iteration kernels.
+#pragma once
+#include "device_common.cuh"
+
+namespace pnfam {
+
+// ---- (a)/(d) transforms ---------------------------------------------------------------------------
+struct DevicePlan {
+  const DevTask* tasks = nullptr;
+  const void* entries = nullptr;  // Phase1Entry[nentries]
+  int ntasks = 0, nentries = 0, max_dim = 0;
+  size_t scratch_elems = 0;       // doubles of scratch per (point, re/im)
+};
+
+struct TransformArgs {
+  const double* W[4];             // Ua, Va, Ub, Vb block arrays
+  const double* in;               // middle operand, per point
+  size_t in_pstride;
+  int in_pack;                    // 1: Broyden pack layout, 0: [c][quad][nxy]
+  double* out;
+  size_t out_pstride;
+  int out_pack;
+  double* scratch;                // [nactive][2][scratch_stride]
+  size_t scratch_stride;
+  size_t nxy;
+  const int* active;              // [nactive] point indices
+};
+
+void launch_transform(const DevicePlan& plan, const TransformArgs& args, int nactive, cudaStream_t stream);
+
+// ---- (b)/(c) hamiltonian --------------------------------------------------------------------------
+// Bilinear grid densities D[t][t'][s][s'] = sum_{a in s, b in s'} phi^t_a(r) rho_ab phi^t'_b(r)
+constexpr int NDD_RHO = 4 * 4 * 2 * 2 * 2;  // doubles per grid point (complex)
+constexpr int NDD_KAP = 2 * 2 * 2;
+constexpr int NMF = 5 * 5 * 2 * 2 * 2;       // field tensor mf(ta,tb,sa,sb) complex, doubles per grid point
+constexpr int NPF = 2 * 2 * 2;               // pairing field (sa,sb) complex
+
+struct HamArgs {
+  DevBasis basis;
+  // per pass q=0 (pn,+) / q=1 (np,-): input structures (dRsp quadrants) and output structures (dHsp quadrants)
+  DevBlockStruct rho_in[2], kap_in[2], h_out[2], d_out[2];
+  int rho_quad[2], kap_quad[2];   // storage quadrant of rho / kappa (and of h / Delta) for each pass
+  const double* rsp;              // [P][2 c][4][nxy]
+  double* hsp;                    // [P][2 c][4][nxy]
+  size_t nxy;
+  double* dd_rho;                 // [nactive][2 q][NDD_RHO][nghl]
+  double* dd_kap;                 // [nactive][2 q][NDD_KAP][nghl]
+  double* mf;                     // [nactive][2 q][NMF][nghl]
+  double* pf;                     // [nactive][2 q][NPF][nghl]
+  double* hpart;                  // split-K partials of the projection
+  const int* active;
+  int nactive;
+};
+
+struct ProjPlan {                 // output tiles of the grid->HO projection
+  const int4* tiles_h = nullptr;  // (block row, a-chunk start (padded index space), b-chunk start, spin bits)
+  const int4* tiles_d = nullptr;
+  int ntiles_h[2] = {0, 0}, ntiles_d[2] = {0, 0};
+  int tile_off_h[2] = {0, 0}, tile_off_d[2] = {0, 0};
+  int ksplit = 1;
+};
+
+void launch_density(const HamArgs& a, cudaStream_t stream);
+void launch_fields(const HamArgs& a, cudaStream_t stream);
+void launch_projection(const HamArgs& a, const ProjPlan& pp, cudaStream_t stream);
+size_t projection_partial_elems(const ProjPlan& pp, size_t nxy);
+
+// ---- (d) Greens function update, Broyden mixer, strength -----------------------------------------
+struct MixArgs {
+  int nvec;                       // 4 (X,Y re/im) or 8 (+P,Q)
+  size_t nxy, n;                  // n = nvec*nxy
+  int M;                          // allocated history slots (stride of df/dv/gram), >= 1
+  int Mmode;                      // the namelist's broyden_history_size: <0 no mixing, 0 linear, >0 Broyden
+  double alpha;                   // mixing factor
+  double w0;
+  const double* hqp;              // [P][2][4][nxy]
+  const double* fqp;              // [4][nxy]
+  const double* esum;             // [4][nxy]  b*f1_i + c*f2_j of matrix_2qp for each qp quadrant
+  const double* tfac;             // [4][nxy] or nullptr
+  const double* omega;            // [P][2]
+  double quench;
+  double* vin;                    // [P][n]
+  double* vout;                   // [P][n]
+  double* df;                     // [P][M][n]
+  double* dv;                     // [P][M][n]
+  double* gram;                   // [P][M][M]
+  double* work;                   // [P][M]   df_i . vout
+  double* gamma;                  // [P][M]
+  double* red;                    // [P][nred][2] partial (max, sumsq)
+  int nred;
+  double* si;                     // [P]
+  double* normi;                  // [P]
+  const double* gqp;              // [1+nx][4][nxy] (F first, then cross-terms)
+  int nstr;                       // 1 + nxterms
+  double* strength;               // [P][nstr][2]
+  const int* active;
+  int nactive;
+};
+void launch_greens(const MixArgs& a, cudaStream_t stream);
+void launch_broyden(const MixArgs& a, int iter, cudaStream_t stream);
+void launch_strength(const MixArgs& a, cudaStream_t stream);
+
+}  // namespace pnfam

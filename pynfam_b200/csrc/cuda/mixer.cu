@@ -1,0 +1,265 @@
+// Block (d) of the FAM iteration, device-resident:
+//   * H20/F20 assembly + energy-denominator update   dR = G(omega) o (quench*dH + F) [o T]
+//       (pnfam_solver.f90:169-183, matrix_2qp :510-544, complex_emult_bbm pnfam_type_bbm.f90:288-327)
+//   * modified Broyden mixing (Johnson 1988) with history M, w0 = 0.01
+//       (pnfam_broyden.f90:117-216).  The reference rebuilds the M x M Gram matrix every iteration
+//       (O(M^2) dots); only the row of the newest difference vector changes, so it is updated
+//       incrementally here: 2*iter_used dots + one fused axpy sweep per iteration, all HBM-streaming.
+//   * strength and cross-term contraction  S = -(1/pi) F.dR   (pnfam_solver.f90:190-203)
+#include "device_common.cuh"
+#include "kernels.cuh"
+
+namespace pnfam {
+
+__device__ __forceinline__ size_t pack_offset(int c, int k, size_t nxy) {
+  return (k < 2) ? ((size_t)c * 2 + k) * nxy : (4 + (size_t)c * 2 + (k - 2)) * nxy;
+}
+
+// ---- Greens function update ---------------------------------------------------------------------
+__global__ void greens_kernel(MixArgs a) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = blockIdx.y, za = blockIdx.z;
+  if (i >= a.nxy) return;
+  const int p = a.active[za];
+  double hre = a.fqp[(size_t)k * a.nxy + i], him = 0.0;
+  if (a.quench != 0.0) {
+    hre += a.quench * a.hqp[(((size_t)p * 2 + 0) * 4 + k) * a.nxy + i];
+    him = a.quench * a.hqp[(((size_t)p * 2 + 1) * 4 + k) * a.nxy + i];
+  }
+  const double wre = a.omega[2 * p], wim = a.omega[2 * p + 1];
+  const double sgn = (k & 1) ? 1.0 : -1.0;            // X,P: E - omega ; Y,Q: E + omega
+  const double dre = a.esum[(size_t)k * a.nxy + i] + sgn * wre, dim = sgn * wim;
+  const double inv = -1.0 / (dre * dre + dim * dim);  // G = -1/(d) = -conj(d)/|d|^2
+  const double gre = dre * inv, gim = -dim * inv;
+  double zre = gre * hre - gim * him, zim = gim * hre + gre * him;
+  if (a.tfac) {
+    const double t = a.tfac[(size_t)k * a.nxy + i];
+    zre *= t; zim *= t;
+  }
+  double* vo = a.vout + (size_t)p * a.n;
+  vo[pack_offset(0, k, a.nxy) + i] = zre;
+  vo[pack_offset(1, k, a.nxy) + i] = zim;
+}
+
+void launch_greens(const MixArgs& a, cudaStream_t stream) {
+  if (a.nactive <= 0) return;
+  dim3 grid((unsigned)((a.nxy + 255) / 256), a.nvec / 2, a.nactive);
+  greens_kernel<<<grid, 256, 0, stream>>>(a);
+}
+
+// ---- block reductions ---------------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  double s = 0.0;
+  for (int i = 0; i < nw; i++) s += sh[i];   // fixed order
+  return s;
+}
+__device__ __forceinline__ double block_max(double v, double* sh) {
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  double s = 0.0;
+  for (int i = 0; i < nw; i++) s = fmax(s, sh[i]);
+  return s;
+}
+
+// vout <- vout - vin ; si partial ; (iter>=2) raw difference vectors into slot ipos + partial |df|^2
+__global__ void __launch_bounds__(256) bro_diff_kernel(MixArgs a, int ipos) {
+  __shared__ double sh[8];
+  const int za = blockIdx.y, p = a.active[za];
+  double* vo = a.vout + (size_t)p * a.n;
+  const double* vi = a.vin + (size_t)p * a.n;
+  double* dfp = ipos >= 0 ? a.df + ((size_t)p * a.M + ipos) * a.n : nullptr;
+  double* dvp = ipos >= 0 ? a.dv + ((size_t)p * a.M + ipos) * a.n : nullptr;
+  double mx = 0.0, ss = 0.0;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < a.n; e += (size_t)gridDim.x * blockDim.x) {
+    const double d = vo[e] - vi[e];
+    vo[e] = d;
+    mx = fmax(mx, fabs(d));
+    if (dfp) {
+      const double f = d - dfp[e];
+      dfp[e] = f;
+      dvp[e] = vi[e] - dvp[e];
+      ss += f * f;
+    }
+  }
+  mx = block_max(mx, sh);
+  ss = block_sum(ss, sh);
+  if (threadIdx.x == 0) {
+    a.red[((size_t)p * a.nred + blockIdx.x) * 2] = mx;
+    a.red[((size_t)p * a.nred + blockIdx.x) * 2 + 1] = ss;
+  }
+}
+
+__global__ void bro_finalize_kernel(MixArgs a) {
+  const int p = a.active[blockIdx.x];
+  if (threadIdx.x == 0) {
+    double mx = 0.0, ss = 0.0;
+    for (int i = 0; i < a.nred; i++) {
+      mx = fmax(mx, a.red[((size_t)p * a.nred + i) * 2]);
+      ss += a.red[((size_t)p * a.nred + i) * 2 + 1];
+    }
+    a.si[p] = mx;
+    a.normi[p] = ss > 0.0 ? 1.0 / sqrt(ss) : 0.0;
+  }
+}
+
+// no mixing (M<0): vin = vout_new ; linear: vin += alpha*(vout_new - vin).  vout holds the difference.
+__global__ void bro_linear_kernel(MixArgs a, double alpha) {
+  const int za = blockIdx.y, p = a.active[za];
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= a.n) return;
+  a.vin[(size_t)p * a.n + e] += alpha * a.vout[(size_t)p * a.n + e];
+}
+
+// dots of the (raw) newest difference vector and of vout with every stored df_i
+__global__ void __launch_bounds__(256) bro_dots_kernel(MixArgs a, int ipos, int iter_used) {
+  __shared__ double sh[8];
+  const int i = blockIdx.x, za = blockIdx.y, p = a.active[za];
+  const double* dfi = a.df + ((size_t)p * a.M + i) * a.n;
+  const double* dfn = a.df + ((size_t)p * a.M + ipos) * a.n;
+  const double* vo = a.vout + (size_t)p * a.n;
+  double s1 = 0.0, s2 = 0.0;
+  for (size_t e = threadIdx.x; e < a.n; e += blockDim.x) {
+    const double f = dfi[e];
+    s1 += f * dfn[e];
+    s2 += f * vo[e];
+  }
+  s1 = block_sum(s1, sh);
+  s2 = block_sum(s2, sh);
+  if (threadIdx.x == 0) {
+    const double nm = a.normi[p];
+    // df_ipos is still un-normalised in memory: scale the dots instead
+    double* G = a.gram + (size_t)p * a.M * a.M;
+    if (i == ipos) {
+      G[(size_t)i * a.M + i] = 1.0 + a.w0 * a.w0;
+      a.work[(size_t)p * a.M + i] = s2 * nm;
+    } else {
+      G[(size_t)i * a.M + ipos] = G[(size_t)ipos * a.M + i] = s1 * nm;
+      a.work[(size_t)p * a.M + i] = s2;
+    }
+  }
+}
+
+// gamma = B^{-1} work, B = Gram + w0^2 on the diagonal (SPD): Cholesky in one thread (M <= ~50)
+__global__ void bro_solve_kernel(MixArgs a, int iter_used) {
+  extern __shared__ double L[];
+  const int p = a.active[blockIdx.x];
+  if (threadIdx.x != 0) return;
+  const int n = iter_used, M = a.M;
+  const double* G = a.gram + (size_t)p * M * M;
+  double* y = L + (size_t)n * n;
+  for (int j = 0; j < n; j++) {
+    for (int i = j; i < n; i++) {
+      double s = (i == j) ? (1.0 + a.w0 * a.w0) : G[(size_t)i * M + j];
+      for (int k = 0; k < j; k++) s -= L[i * n + k] * L[j * n + k];
+      if (i == j) L[j * n + j] = sqrt(s);
+      else L[i * n + j] = s / L[j * n + j];
+    }
+  }
+  const double* w = a.work + (size_t)p * M;
+  for (int i = 0; i < n; i++) {
+    double s = w[i];
+    for (int k = 0; k < i; k++) s -= L[i * n + k] * y[k];
+    y[i] = s / L[i * n + i];
+  }
+  double* gm = a.gamma + (size_t)p * M;
+  for (int i = n - 1; i >= 0; i--) {
+    double s = y[i];
+    for (int k = i + 1; k < n; k++) s -= L[k * n + i] * gm[k];
+    gm[i] = s / L[i * n + i];
+  }
+}
+
+// curv = alpha*vout - sum_i gamma_i (dv_i + alpha df_i); store (vout, vin) in slot inext; vin += curv
+__global__ void __launch_bounds__(256) bro_update_kernel(MixArgs a, int ipos, int inext, int iter_used) {
+  const int za = blockIdx.y, p = a.active[za];
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= a.n) return;
+  const double alpha = a.alpha;
+  const double vo = a.vout[(size_t)p * a.n + e];
+  const double vi = a.vin[(size_t)p * a.n + e];
+  double* df = a.df + (size_t)p * a.M * a.n + e;
+  double* dv = a.dv + (size_t)p * a.M * a.n + e;
+  const double nm = a.normi[p];
+  const double* gm = a.gamma + (size_t)p * a.M;
+  double curv = alpha * vo;
+  for (int i = 0; i < iter_used; i++) {
+    double f = df[(size_t)i * a.n], v = dv[(size_t)i * a.n];
+    if (i == ipos) {
+      f *= nm; v *= nm;
+      if (ipos != inext) { df[(size_t)i * a.n] = f; dv[(size_t)i * a.n] = v; }
+    }
+    curv = curv - gm[i] * (v + alpha * f);
+  }
+  df[(size_t)inext * a.n] = vo;
+  dv[(size_t)inext * a.n] = vi;
+  a.vin[(size_t)p * a.n + e] = vi + curv;
+}
+
+void launch_broyden(const MixArgs& a, int iter, cudaStream_t stream) {
+  if (a.nactive <= 0) return;
+  const int M = a.Mmode;
+  const unsigned nblk = (unsigned)((a.n + 255) / 256);
+  int iter_used = 0, ipos = -1, inext = 0;
+  const bool broyden = !(M < 0 || M == 0 || iter == 0);
+  if (broyden) {
+    iter_used = iter - 1 < M ? iter - 1 : M;
+    ipos = iter - 1 - ((iter - 2) / M) * M;   // 1-based slot, Fortran integer arithmetic (truncation toward zero)
+    inext = iter - ((iter - 1) / M) * M;
+    ipos -= 1; inext -= 1;                    // 0-based
+  }
+  bro_diff_kernel<<<dim3(a.nred, a.nactive), 256, 0, stream>>>(a, (broyden && iter >= 2) ? ipos : -1);
+  bro_finalize_kernel<<<a.nactive, 32, 0, stream>>>(a);
+  if (!broyden) {
+    const double alpha = (M < 0) ? 1.0 : a.alpha;
+    bro_linear_kernel<<<dim3(nblk, a.nactive), 256, 0, stream>>>(a, alpha);
+    return;
+  }
+  if (iter_used > 0) {
+    bro_dots_kernel<<<dim3(iter_used, a.nactive), 256, 0, stream>>>(a, ipos, iter_used);
+    const size_t sh = ((size_t)iter_used * iter_used + iter_used) * sizeof(double);
+    bro_solve_kernel<<<a.nactive, 32, sh, stream>>>(a, iter_used);
+  }
+  bro_update_kernel<<<dim3(nblk, a.nactive), 256, 0, stream>>>(a, ipos, inext, iter_used);
+}
+
+// ---- strength function ----------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) strength_kernel(MixArgs a) {
+  __shared__ double sh[8];
+  const int k = blockIdx.x, za = blockIdx.y, p = a.active[za];
+  const double* g = a.gqp + (size_t)k * 4 * a.nxy;
+  const double* v = a.vin + (size_t)p * a.n;
+  const int nq = a.nvec / 2;
+  double sre = 0.0, sim = 0.0;
+  for (int q = 0; q < nq; q++) {
+    const double* gq = g + (size_t)q * a.nxy;
+    const double* vr = v + pack_offset(0, q, a.nxy);
+    const double* vi = v + pack_offset(1, q, a.nxy);
+    for (size_t e = threadIdx.x; e < a.nxy; e += blockDim.x) {
+      const double gg = gq[e];
+      sre += gg * vr[e];
+      sim += gg * vi[e];
+    }
+  }
+  sre = block_sum(sre, sh);
+  sim = block_sum(sim, sh);
+  if (threadIdx.x == 0) {
+    const double pi = 3.14159265358979323846264338327950288;
+    a.strength[((size_t)p * a.nstr + k) * 2] = -sre / pi;
+    a.strength[((size_t)p * a.nstr + k) * 2 + 1] = -sim / pi;
+  }
+}
+
+void launch_strength(const MixArgs& a, cudaStream_t stream) {
+  if (a.nactive <= 0) return;
+  strength_kernel<<<dim3(a.nstr, a.nactive), 256, 0, stream>>>(a);
+}
+
+}  // namespace pnfam

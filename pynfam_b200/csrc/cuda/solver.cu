@@ -1,0 +1,576 @@
+// Device context, batched FAM solve loop and the C ABI of libpnfam_b200.so (include/pnfam_b200.h, section 2).
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include "../../../include/pnfam_b200.h"
+#include "../host/symbolic.hpp"
+#include "device_common.cuh"
+#include "kernels.cuh"
+
+namespace pnfam {
+
+// ---- small RAII device buffer -------------------------------------------------------------------------
+template <class T>
+struct DBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DBuf() = default;
+  DBuf(const DBuf&) = delete;
+  DBuf& operator=(const DBuf&) = delete;
+  ~DBuf() { release(); }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  void alloc(size_t count) {
+    release();
+    n = count;
+    if (count) PNFAM_CUDA_CHECK(cudaMalloc(&p, count * sizeof(T)));
+  }
+  void upload(const std::vector<T>& h) {
+    alloc(h.size());
+    if (!h.empty()) PNFAM_CUDA_CHECK(cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  }
+  void zero() { if (p) PNFAM_CUDA_CHECK(cudaMemset(p, 0, n * sizeof(T))); }
+};
+
+struct DevStructBuf {
+  DBuf<int> r2c, r2m;
+  void upload(const BlockStruct& s) { r2c.upload(s.r2c); r2m.upload(s.r2m); }
+  void upload(const std::vector<int>& c, const std::vector<int>& m) { r2c.upload(c); r2m.upload(m); }
+  DevBlockStruct view() const { return {r2c.p, r2m.p}; }
+};
+
+}  // namespace pnfam
+
+using namespace pnfam;
+
+struct pnfam_b200_ctx {
+  int device = 0;
+  int nb = 0, dqp = 0, nghl = 0, ntiles = 0;
+  size_t dmat = 0;
+  std::vector<int> db, isstart, nsu;
+  std::vector<double> Ep, En, qp_fp, qp_fn;
+  bool use_diag = false;
+  DBuf<int> d_db, d_isstart, d_nsu;
+  DBuf<double> d_phi, d_wdcori, d_crho, d_cs, d_cpair, d_cspair;
+  DBuf<double> d_Up, d_Vp, d_Un, d_Vn;
+  DevBasis basis{};
+  cudaStream_t stream = nullptr;
+  int64_t launches = 0;
+};
+
+static void set_err(char* err, int errlen, const std::string& s) {
+  if (err && errlen > 0) {
+    std::strncpy(err, s.c_str(), (size_t)errlen - 1);
+    err[errlen - 1] = 0;
+  }
+}
+
+static void require_device(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0)
+    throw std::runtime_error(std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                             "): the pnFAM iteration has no CPU fallback");
+  if (device < 0 || device >= n) throw std::runtime_error("invalid CUDA device index");
+  PNFAM_CUDA_CHECK(cudaSetDevice(device));
+}
+
+extern "C" int pnfam_b200_ctx_create(const pnfam_b200_model* m, int device, pnfam_b200_ctx** out, char* err, int errlen) {
+  try {
+    require_device(device);
+    auto c = std::make_unique<pnfam_b200_ctx>();
+    c->device = device;
+    c->nb = m->nb; c->dqp = m->dqp; c->nghl = m->nghl;
+    c->ntiles = (m->nghl + RT - 1) / RT;
+    c->db.assign(m->db, m->db + m->nb);
+    c->nsu.assign(m->num_spin_up, m->num_spin_up + m->nb);
+    c->isstart.resize(m->nb);
+    int a = 0;
+    c->dmat = 0;
+    for (int i = 0; i < m->nb; i++) { c->isstart[i] = a; a += c->db[i]; c->dmat += (size_t)c->db[i] * c->db[i]; }
+    if (a != m->dqp) throw std::runtime_error("model: sum(db) != dqp");
+    c->Ep.assign(m->Ep, m->Ep + m->dqp);
+    c->En.assign(m->En, m->En + m->dqp);
+    c->use_diag = m->qp_fp != nullptr && m->qp_fn != nullptr;
+    if (c->use_diag) { c->qp_fp.assign(m->qp_fp, m->qp_fp + m->dqp); c->qp_fn.assign(m->qp_fn, m->qp_fn + m->dqp); }
+    c->d_db.upload(c->db); c->d_isstart.upload(c->isstart); c->d_nsu.upload(c->nsu);
+    // tile-major wave-function tables: phi[tile][type][state][RT]
+    {
+      const double* tab[NTYPE] = {m->wf, m->wfdr, m->wfdp, m->wfdz, m->wfd2_all};
+      std::vector<double> h((size_t)c->ntiles * NTYPE * c->dqp * RT, 0.0);
+      for (int t = 0; t < NTYPE; t++)
+        for (int s = 0; s < c->dqp; s++)
+          for (int r = 0; r < c->nghl; r++)
+            h[(((size_t)(r / RT) * NTYPE + t) * c->dqp + s) * RT + (r % RT)] = tab[t][(size_t)s * c->nghl + r];
+      c->d_phi.upload(h);
+    }
+    auto up = [&](DBuf<double>& d, const double* p, size_t n) { d.upload(std::vector<double>(p, p + n)); };
+    up(c->d_wdcori, m->wdcori, m->nghl); up(c->d_crho, m->crho, m->nghl); up(c->d_cs, m->cs, m->nghl);
+    up(c->d_cpair, m->cpair, m->nghl); up(c->d_cspair, m->cspair, m->nghl);
+    up(c->d_Up, m->Up, c->dmat); up(c->d_Vp, m->Vp, c->dmat); up(c->d_Un, m->Un, c->dmat); up(c->d_Vn, m->Vn, c->dmat);
+    DevBasis& B = c->basis;
+    B.nb = c->nb; B.dqp = c->dqp; B.nghl = c->nghl; B.ntiles = c->ntiles;
+    B.db = c->d_db.p; B.isstart = c->d_isstart.p; B.nsu = c->d_nsu.p; B.phi = c->d_phi.p;
+    B.wdcori = c->d_wdcori.p; B.crho = c->d_crho.p; B.cs = c->d_cs.p; B.cpair = c->d_cpair.p; B.cspair = c->d_cspair.p;
+    B.cdrho = m->cdrho; B.ctau = m->ctau; B.ctj0 = m->ctj0; B.ctj1 = m->ctj1; B.ctj2 = m->ctj2; B.crdj = m->crdj;
+    B.cds = m->cds; B.ct = m->ct; B.cj = m->cj; B.cgs = m->cgs; B.cf = m->cf; B.csdj = m->csdj;
+    PNFAM_CUDA_CHECK(cudaStreamCreate(&c->stream));
+    *out = c.release();
+    return 0;
+  } catch (const std::exception& e) {
+    set_err(err, errlen, e.what());
+    return 1;
+  }
+}
+
+extern "C" void pnfam_b200_ctx_destroy(pnfam_b200_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+// ---- per-operator device data ----------------------------------------------------------------------
+namespace {
+
+struct OperatorDev {
+  OperatorPlan plan;
+  DBuf<DevTask> fwd_tasks, bwd_tasks;
+  DBuf<int2> fwd_entries, bwd_entries;
+  DevicePlan fwd, bwd;
+  DevStructBuf sp[4], hsp[4];
+  DBuf<int4> tiles_h, tiles_d;
+  ProjPlan proj;
+  DBuf<double> gqp, esum, tfac;
+  size_t scratch_elems = 0;
+};
+
+void flatten(const TransformPlan& tp, DBuf<DevTask>& dt, DBuf<int2>& de, DevicePlan& out) {
+  std::vector<DevTask> tasks;
+  std::vector<int2> entries;
+  int toff = 0, maxd = 0;
+  for (const BlockTask& b : tp.tasks) {
+    DevTask d{};
+    d.out_quad = b.out_quad; d.out_off = b.out_off; d.m = b.m; d.n = b.n; d.nterms = b.nterms;
+    maxd = std::max(maxd, std::max(b.m, b.n));
+    for (int t = 0; t < b.nterms; t++) {
+      const TripleTerm& s = b.t[t];
+      DevTerm& x = d.t[t];
+      x.a_mat = s.a_mat; x.a_off = s.a_off; x.a_trans = s.a_trans;
+      x.b_quad = s.b_quad; x.b_off = s.b_off; x.b_trans = s.b_trans;
+      x.c_mat = s.c_mat; x.c_off = s.c_off; x.c_trans = s.c_trans;
+      x.alpha_re = s.alpha_re; x.alpha_im = s.alpha_im;
+      x.t_off = toff;
+      toff += b.m * b.n;
+      entries.push_back(make_int2((int)tasks.size(), t));
+    }
+    tasks.push_back(d);
+  }
+  dt.upload(tasks); de.upload(entries);
+  out.tasks = dt.p; out.entries = de.p; out.ntasks = (int)tasks.size(); out.nentries = (int)entries.size();
+  out.max_dim = maxd; out.scratch_elems = (size_t)toff;
+}
+
+// 2-quasiparticle tables of matrix_2qp (pnfam_solver.f90:510-544): v[e] = b*f1_i + c*f2_j on a structure
+std::vector<double> table_2qp(const pnfam_b200_ctx& c, const BlockStruct& st, size_t nxy, double b, double cc,
+                              const std::vector<double>& f1, const std::vector<double>& f2, double e0) {
+  std::vector<double> v(nxy, 0.0);
+  if (!st.allocated) return v;
+  for (int ibr = 0; ibr < c.nb; ibr++) {
+    const int ibc = st.r2c[ibr];
+    if (ibc < 0) continue;
+    size_t ipt = st.r2m[ibr];
+    for (int i2 = 0; i2 < c.db[ibc]; i2++)
+      for (int i1 = 0; i1 < c.db[ibr]; i1++) v[ipt++] = b * f1[c.isstart[ibr] + i1] + cc * f2[c.isstart[ibc] + i2] + e0;
+  }
+  return v;
+}
+
+void build_proj_tiles(const pnfam_b200_ctx& c, const BlockStruct st[2], std::vector<int4>& tiles, int ntiles[2], int off[2]) {
+  for (int q = 0; q < 2; q++) {
+    off[q] = (int)tiles.size();
+    for (int ix = 0; ix < c.nb; ix++) {
+      const int iy = st[q].r2c[ix];
+      if (iy < 0) continue;
+      const int di = c.db[ix], dj = c.db[iy], nu = c.nsu[ix];
+      for (int s = 0; s < 2; s++) {
+        const int lo = s == 0 ? 0 : nu, hi = s == 0 ? nu : di;
+        for (int a0 = lo; a0 < hi; a0 += 64)
+          for (int b0 = 0; b0 < dj; b0 += 32) tiles.push_back(make_int4(ix, a0, b0, 0));
+      }
+    }
+    ntiles[q] = (int)tiles.size() - off[q];
+  }
+}
+
+std::unique_ptr<OperatorDev> make_operator(pnfam_b200_ctx& c, const pnfam_b200_operator& op, int npoints) {
+  auto od = std::make_unique<OperatorDev>();
+  std::vector<int> ir2c(op.f_ir2c, op.f_ir2c + c.nb);
+  od->plan = make_operator_plan(c.db, ir2c, c.use_diag, op.beta_minus != 0);
+  flatten(od->plan.forward, od->fwd_tasks, od->fwd_entries, od->fwd);
+  flatten(od->plan.backward, od->bwd_tasks, od->bwd_entries, od->bwd);
+  od->scratch_elems = std::max(od->fwd.scratch_elems, od->bwd.scratch_elems);
+  for (int k = 0; k < 4; k++) { od->sp[k].upload(od->plan.sp[k]); od->hsp[k].upload(od->plan.hsp[k]); }
+  // projection output tiles: pass 0 -> (h_pn = hsp[0], Delta+ = hsp[1]); pass 1 -> (h_np = hsp[3], Delta- = hsp[2])
+  {
+    std::vector<int4> th, td;
+    BlockStruct sh[2] = {od->plan.hsp[0], od->plan.hsp[3]}, sd[2] = {od->plan.hsp[1], od->plan.hsp[2]};
+    build_proj_tiles(c, sh, th, od->proj.ntiles_h, od->proj.tile_off_h);
+    build_proj_tiles(c, sd, td, od->proj.ntiles_d, od->proj.tile_off_d);
+    od->tiles_h.upload(th); od->tiles_d.upload(td);
+    od->proj.tiles_h = od->tiles_h.p; od->proj.tiles_d = od->tiles_d.p;
+    const int per = std::max(1, od->proj.ntiles_h[0] * std::max(1, npoints));
+    od->proj.ksplit = std::min(std::min(c.ntiles, 32), std::max(1, (2 * 148 + per - 1) / per));
+  }
+  return od;
+}
+
+struct Timer {
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  double s() const { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+};
+
+HamArgs make_ham_args(const pnfam_b200_ctx& c, const OperatorDev& od) {
+  HamArgs h{};
+  h.basis = c.basis;
+  h.rho_in[0] = od.sp[0].view(); h.kap_in[0] = od.sp[1].view(); h.rho_in[1] = od.sp[3].view(); h.kap_in[1] = od.sp[2].view();
+  h.h_out[0] = od.hsp[0].view(); h.d_out[0] = od.hsp[1].view(); h.h_out[1] = od.hsp[3].view(); h.d_out[1] = od.hsp[2].view();
+  h.rho_quad[0] = 0; h.kap_quad[0] = 1; h.rho_quad[1] = 3; h.kap_quad[1] = 2;
+  h.nxy = od.plan.nxy;
+  return h;
+}
+
+}  // namespace
+
+extern "C" int pnfam_b200_solve(pnfam_b200_ctx* c, const pnfam_b200_operator* op, const pnfam_b200_solver_params* prm,
+                                int32_t npoints, const double* omega_re, const double* omega_im, double* strength,
+                                int32_t* iters, int32_t* conv, double* si_out, double* trace, pnfam_b200_stats* stats,
+                                char* err, int errlen) {
+  try {
+    Timer wall;
+    require_device(c->device);
+    cudaStream_t st = c->stream;
+    const int P = npoints;
+    if (P <= 0) return 0;
+    int64_t launches = 0, h2d = 0, d2h = 0;
+    auto od = make_operator(*c, *op, P);
+    const size_t nxy = od->plan.nxy;
+    const int nvec = c->use_diag ? 8 : 4, nq = nvec / 2;
+    const size_t n = (size_t)nvec * nxy;
+    const int nstr = 1 + op->nxterms;
+    const double quench = prm->quench_residual_int;
+    const bool no_residual = std::fabs(quench) < 1e-10;
+    const int M = no_residual ? -1 : prm->broyden_history_size;
+    const int Malloc = std::max(M, 1);
+    const bool bminus = op->beta_minus != 0;
+
+    // ---- static per-operator tables ---------------------------------------------------------------
+    std::vector<double> Ea = bminus ? c->Ep : c->En, Eb = bminus ? c->En : c->Ep;
+    {
+      const double sa = bminus ? prm->energy_shift_prot : prm->energy_shift_neut;
+      const double sb = bminus ? prm->energy_shift_neut : prm->energy_shift_prot;
+      for (auto& e : Ea) e += sa;
+      for (auto& e : Eb) e += sb;
+    }
+    {
+      std::vector<double> es(4 * nxy, 0.0), tf;
+      for (int k = 0; k < nq; k++) {
+        auto v = table_2qp(*c, od->plan.qp[k], nxy, 1.0, k < 2 ? 1.0 : -1.0, Ea, Eb, 0.0);
+        std::copy(v.begin(), v.end(), es.begin() + (size_t)k * nxy);
+      }
+      od->esum.upload(es);
+      if (c->use_diag) {
+        const std::vector<double>& fa = bminus ? c->qp_fp : c->qp_fn;
+        const std::vector<double>& fb = bminus ? c->qp_fn : c->qp_fp;
+        tf.assign(4 * nxy, 0.0);
+        for (int k = 0; k < 4; k++) {
+          auto v = k < 2 ? table_2qp(*c, od->plan.qp[k], nxy, -1.0, -1.0, fa, fb, 1.0)
+                         : table_2qp(*c, od->plan.qp[k], nxy, -1.0, +1.0, fa, fb, 0.0);
+          std::copy(v.begin(), v.end(), tf.begin() + (size_t)k * nxy);
+        }
+        od->tfac.upload(tf);
+      }
+      h2d += (int64_t)(es.size() + tf.size()) * 8;
+    }
+
+    // ---- per-point state ---------------------------------------------------------------------------------
+    DBuf<double> vin, vout, df, dv, gram, work, gamma, red, d_si, d_normi, d_omega, d_str;
+    DBuf<double> rsp, hsp, hqp, scratch, dd_rho, dd_kap, mf, pf, hpart;
+    DBuf<int> d_active;
+    const int nred = 64;
+    vin.alloc((size_t)P * n); vout.alloc((size_t)P * n);
+    vin.zero(); vout.zero();
+    if (M > 0) { df.alloc((size_t)P * Malloc * n); dv.alloc((size_t)P * Malloc * n); df.zero(); dv.zero(); }
+    gram.alloc((size_t)P * Malloc * Malloc); work.alloc((size_t)P * Malloc); gamma.alloc((size_t)P * Malloc);
+    gram.zero(); work.zero(); gamma.zero();
+    red.alloc((size_t)P * nred * 2); d_si.alloc(P); d_normi.alloc(P); d_omega.alloc((size_t)P * 2);
+    d_str.alloc((size_t)P * nstr * 2);
+    rsp.alloc((size_t)P * 8 * nxy); hsp.alloc((size_t)P * 8 * nxy); hqp.alloc((size_t)P * 8 * nxy);
+    rsp.zero(); hsp.zero(); hqp.zero();
+    scratch.alloc((size_t)P * 2 * std::max<size_t>(od->scratch_elems, 1));
+    dd_rho.alloc((size_t)P * 2 * NDD_RHO * c->nghl); dd_kap.alloc((size_t)P * 2 * NDD_KAP * c->nghl);
+    mf.alloc((size_t)P * 2 * NMF * c->nghl); pf.alloc((size_t)P * 2 * NPF * c->nghl);
+    hpart.alloc((size_t)P * projection_partial_elems(od->proj, nxy));
+    d_active.alloc(P);
+    {
+      std::vector<double> w(2 * (size_t)P);
+      for (int p = 0; p < P; p++) { w[2 * p] = omega_re[p]; w[2 * p + 1] = omega_im[p]; }
+      PNFAM_CUDA_CHECK(cudaMemcpy(d_omega.p, w.data(), w.size() * 8, cudaMemcpyHostToDevice));
+      h2d += (int64_t)w.size() * 8;
+    }
+    std::vector<int> active(P);
+    for (int p = 0; p < P; p++) active[p] = p;
+    PNFAM_CUDA_CHECK(cudaMemcpy(d_active.p, active.data(), P * sizeof(int), cudaMemcpyHostToDevice));
+
+    TransformArgs ta{};
+    if (bminus) { ta.W[0] = c->d_Up.p; ta.W[1] = c->d_Vp.p; ta.W[2] = c->d_Un.p; ta.W[3] = c->d_Vn.p; }
+    else { ta.W[0] = c->d_Un.p; ta.W[1] = c->d_Vn.p; ta.W[2] = c->d_Up.p; ta.W[3] = c->d_Vp.p; }
+    ta.scratch = scratch.p; ta.scratch_stride = std::max<size_t>(od->scratch_elems, 1);
+    ta.nxy = nxy; ta.active = d_active.p;
+
+    // ---- F and cross-term fields -> quasiparticle basis (pnfam_solver.f90:368-382): backward transform of
+    //      dHsp = [f 0; 0 0] (real flavour), one field at a time through point slot 0.
+    od->gqp.alloc((size_t)nstr * 4 * nxy);
+    od->gqp.zero();
+    for (int k = 0; k < nstr; k++) {
+      const double* src = k == 0 ? op->f_elem : op->g_elem[k - 1];
+      PNFAM_CUDA_CHECK(cudaMemsetAsync(hsp.p, 0, 8 * nxy * sizeof(double), st));
+      PNFAM_CUDA_CHECK(cudaMemcpyAsync(hsp.p, src, nxy * sizeof(double), cudaMemcpyHostToDevice, st));
+      h2d += (int64_t)nxy * 8;
+      TransformArgs b = ta;
+      b.in = hsp.p; b.in_pstride = 8 * nxy; b.in_pack = 0;
+      b.out = hqp.p; b.out_pstride = 8 * nxy; b.out_pack = 0;
+      launch_transform(od->bwd, b, 1, st);
+      launches += 2;
+      PNFAM_CUDA_CHECK(cudaMemcpyAsync(od->gqp.p + (size_t)k * 4 * nxy, hqp.p, 4 * nxy * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    }
+    PNFAM_CUDA_CHECK(cudaMemsetAsync(hsp.p, 0, 8 * nxy * sizeof(double), st));
+    PNFAM_CUDA_CHECK(cudaMemsetAsync(hqp.p, 0, 8 * nxy * sizeof(double), st));
+
+    HamArgs ha = make_ham_args(*c, *od);
+    ha.rsp = rsp.p; ha.hsp = hsp.p; ha.dd_rho = dd_rho.p; ha.dd_kap = dd_kap.p; ha.mf = mf.p; ha.pf = pf.p;
+    ha.hpart = hpart.p; ha.active = d_active.p;
+
+    MixArgs ma{};
+    ma.nvec = nvec; ma.nxy = nxy; ma.n = n; ma.M = Malloc; ma.Mmode = M; ma.alpha = (double)0.7f; ma.w0 = 0.01;
+    ma.hqp = hqp.p; ma.fqp = od->gqp.p; ma.esum = od->esum.p; ma.tfac = c->use_diag ? od->tfac.p : nullptr;
+    ma.omega = d_omega.p; ma.quench = no_residual ? 0.0 : quench;
+    ma.vin = vin.p; ma.vout = vout.p; ma.df = df.p; ma.dv = dv.p; ma.gram = gram.p; ma.work = work.p; ma.gamma = gamma.p;
+    ma.red = red.p; ma.nred = nred; ma.si = d_si.p; ma.normi = d_normi.p; ma.gqp = od->gqp.p; ma.nstr = nstr;
+    ma.strength = d_str.p; ma.active = d_active.p;
+
+    std::vector<double> h_si(P, 1.0), h_str((size_t)P * nstr * 2, 0.0);
+    for (int p = 0; p < P; p++) { iters[p] = 0; conv[p] = 0; si_out[p] = 1.0; }
+    for (size_t i = 0; i < (size_t)P * nstr * 2; i++) strength[i] = 0.0;
+    const int tstride = (prm->max_iter + 1) * 4;
+    if (trace) {
+      std::fill(trace, trace + (size_t)P * tstride, 0.0);
+      for (int p = 0; p < P; p++) trace[(size_t)p * tstride] = 1.0;
+    }
+
+    cudaEvent_t ev0, ev1, evd0, evd1, evp0, evp1;
+    PNFAM_CUDA_CHECK(cudaEventCreate(&ev0)); PNFAM_CUDA_CHECK(cudaEventCreate(&ev1));
+    PNFAM_CUDA_CHECK(cudaEventCreate(&evd0)); PNFAM_CUDA_CHECK(cudaEventCreate(&evd1));
+    PNFAM_CUDA_CHECK(cudaEventCreate(&evp0)); PNFAM_CUDA_CHECK(cudaEventCreate(&evp1));
+    PNFAM_CUDA_CHECK(cudaEventRecord(ev0, st));
+    double t_dens = 0, t_proj = 0;
+    int64_t n_dens = 0, n_proj = 0, total_iters = 0;
+    int nactive = P;
+    // the loop of ifam (pnfam_solver.f90:114-209) for all still-active points in lock step
+    for (int it = 0; it < prm->max_iter && nactive > 0; it++) {
+      Timer titer;
+      ha.nactive = nactive; ma.nactive = nactive;
+      if (!no_residual) {
+        TransformArgs f = ta;
+        f.in = vin.p; f.in_pstride = n; f.in_pack = 1;
+        f.out = rsp.p; f.out_pstride = 8 * nxy; f.out_pack = 0;
+        launch_transform(od->fwd, f, nactive, st);
+        PNFAM_CUDA_CHECK(cudaEventRecord(evd0, st));
+        launch_density(ha, st);
+        PNFAM_CUDA_CHECK(cudaEventRecord(evd1, st));
+        launch_fields(ha, st);
+        PNFAM_CUDA_CHECK(cudaEventRecord(evp0, st));
+        launch_projection(ha, od->proj, st);
+        PNFAM_CUDA_CHECK(cudaEventRecord(evp1, st));
+        TransformArgs b = ta;
+        b.in = hsp.p; b.in_pstride = 8 * nxy; b.in_pack = 0;
+        b.out = hqp.p; b.out_pstride = 8 * nxy; b.out_pack = 0;
+        launch_transform(od->bwd, b, nactive, st);
+        launches += 2 + 2 + 1 + 5 + 2;
+        n_dens += 2; n_proj += 4;
+      }
+      launch_greens(ma, st);
+      launch_broyden(ma, it, st);
+      launch_strength(ma, st);
+      launches += 1 + 5 + 1;
+      PNFAM_CUDA_CHECK(cudaMemcpyAsync(h_si.data(), d_si.p, P * sizeof(double), cudaMemcpyDeviceToHost, st));
+      PNFAM_CUDA_CHECK(cudaMemcpyAsync(h_str.data(), d_str.p, (size_t)P * nstr * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+      PNFAM_CUDA_CHECK(cudaStreamSynchronize(st));
+      d2h += (int64_t)P * 8 + (int64_t)P * nstr * 16;
+      if (!no_residual) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, evd0, evd1); t_dens += ms * 1e-3;
+        cudaEventElapsedTime(&ms, evp0, evp1); t_proj += ms * 1e-3;
+      }
+      const double dt = titer.s();
+      std::vector<int> next;
+      for (int za = 0; za < nactive; za++) {
+        const int p = active[za];
+        total_iters++;
+        iters[p] = it + 1;
+        si_out[p] = h_si[p];
+        for (int k = 0; k < nstr * 2; k++) strength[(size_t)p * nstr * 2 + k] = h_str[(size_t)p * nstr * 2 + k];
+        if (trace) {
+          double* t = trace + (size_t)p * tstride + (size_t)(it + 1) * 4;
+          t[0] = h_si[p]; t[1] = h_str[(size_t)p * nstr * 2]; t[2] = h_str[(size_t)p * nstr * 2 + 1]; t[3] = dt;
+        }
+        if (h_si[p] < prm->convergence_epsilon) conv[p] = 1;
+        else next.push_back(p);
+      }
+      if (next.size() != (size_t)nactive) {
+        active = next;
+        nactive = (int)active.size();
+        if (nactive > 0) {
+          PNFAM_CUDA_CHECK(cudaMemcpyAsync(d_active.p, active.data(), nactive * sizeof(int), cudaMemcpyHostToDevice, st));
+          h2d += nactive * 4;
+        }
+      }
+    }
+    PNFAM_CUDA_CHECK(cudaEventRecord(ev1, st));
+    PNFAM_CUDA_CHECK(cudaStreamSynchronize(st));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ev0, ev1);
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(evd0); cudaEventDestroy(evd1);
+    cudaEventDestroy(evp0); cudaEventDestroy(evp1);
+    if (stats) {
+      stats->seconds_total = wall.s(); stats->seconds_device = ms * 1e-3; stats->iterations = total_iters;
+      stats->kernel_launches = launches; stats->h2d_bytes = h2d; stats->d2h_bytes = d2h;
+      stats->seconds_density = t_dens; stats->seconds_projection = t_proj;
+      stats->launches_density = n_dens; stats->launches_projection = n_proj;
+    }
+    c->launches += launches;
+    return 0;
+  } catch (const std::exception& e) {
+    set_err(err, errlen, e.what());
+    return 1;
+  }
+}
+
+// ---- calc_hamiltonian-shaped entry -----------------------------------------------------------------------
+extern "C" int pnfam_b200_calc_hamiltonian(pnfam_b200_ctx* c, const pnfam_b200_blockmatrix in[8], pnfam_b200_blockmatrix out[8],
+                                           char* err, int errlen) {
+  try {
+    require_device(c->device);
+    cudaStream_t st = c->stream;
+    size_t nxy = 0;
+    for (int i = 0; i < 8; i++) nxy = std::max(nxy, (size_t)std::max(in[i].nelem, out[i].nelem));
+    auto mk = [&](const pnfam_b200_blockmatrix& b, DevStructBuf& d, BlockStruct& hs) {
+      hs.r2c.assign(c->nb, -1); hs.r2m.assign(c->nb, -1); hs.allocated = true;
+      for (int i = 0; i < c->nb; i++) if (b.ir2c[i] > 0) { hs.r2c[i] = b.ir2c[i] - 1; hs.r2m[i] = b.ir2m[i] - 1; }
+      d.upload(hs);
+    };
+    // argument order -> (pass, kind): in: rho_pn(0,1) k+(2,3) rho_np(4,5) k-(6,7); storage quads 0,1,3,2
+    DevStructBuf sin[4], sout[4];
+    BlockStruct hin[4], hout[4];
+    const int quad_of_pair[4] = {0, 1, 3, 2};
+    DBuf<double> rsp, hsp, dd_rho, dd_kap, mf, pf, hpart;
+    DBuf<int> d_active;
+    rsp.alloc(8 * nxy); hsp.alloc(8 * nxy); rsp.zero(); hsp.zero();
+    for (int pr = 0; pr < 4; pr++) {
+      mk(in[2 * pr], sin[pr], hin[pr]);
+      mk(out[2 * pr], sout[pr], hout[pr]);
+      for (int cc = 0; cc < 2; cc++)
+        PNFAM_CUDA_CHECK(cudaMemcpy(rsp.p + ((size_t)cc * 4 + quad_of_pair[pr]) * nxy, in[2 * pr + cc].elem,
+                                    in[2 * pr + cc].nelem * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    HamArgs h{};
+    h.basis = c->basis;
+    h.rho_in[0] = sin[0].view(); h.kap_in[0] = sin[1].view(); h.rho_in[1] = sin[2].view(); h.kap_in[1] = sin[3].view();
+    h.h_out[0] = sout[0].view(); h.d_out[0] = sout[1].view(); h.h_out[1] = sout[2].view(); h.d_out[1] = sout[3].view();
+    h.rho_quad[0] = 0; h.kap_quad[0] = 1; h.rho_quad[1] = 3; h.kap_quad[1] = 2;
+    h.nxy = nxy;
+    ProjPlan pp;
+    DBuf<int4> th, td;
+    {
+      std::vector<int4> vh, vd;
+      BlockStruct shh[2] = {hout[0], hout[2]}, sdd[2] = {hout[1], hout[3]};
+      build_proj_tiles(*c, shh, vh, pp.ntiles_h, pp.tile_off_h);
+      build_proj_tiles(*c, sdd, vd, pp.ntiles_d, pp.tile_off_d);
+      th.upload(vh); td.upload(vd);
+      pp.tiles_h = th.p; pp.tiles_d = td.p;
+      const int per = std::max(1, pp.ntiles_h[0]);
+      pp.ksplit = std::min(std::min(c->ntiles, 32), std::max(1, (2 * 148 + per - 1) / per));
+    }
+    dd_rho.alloc((size_t)2 * NDD_RHO * c->nghl); dd_kap.alloc((size_t)2 * NDD_KAP * c->nghl);
+    mf.alloc((size_t)2 * NMF * c->nghl); pf.alloc((size_t)2 * NPF * c->nghl);
+    hpart.alloc(projection_partial_elems(pp, nxy));
+    std::vector<int> act = {0};
+    d_active.upload(act);
+    h.rsp = rsp.p; h.hsp = hsp.p; h.dd_rho = dd_rho.p; h.dd_kap = dd_kap.p; h.mf = mf.p; h.pf = pf.p; h.hpart = hpart.p;
+    h.active = d_active.p; h.nactive = 1;
+    launch_density(h, st);
+    launch_fields(h, st);
+    launch_projection(h, pp, st);
+    PNFAM_CUDA_CHECK(cudaStreamSynchronize(st));
+    PNFAM_CUDA_CHECK(cudaGetLastError());
+    for (int pr = 0; pr < 4; pr++)
+      for (int cc = 0; cc < 2; cc++)
+        PNFAM_CUDA_CHECK(cudaMemcpy(out[2 * pr + cc].elem, hsp.p + ((size_t)cc * 4 + quad_of_pair[pr]) * nxy,
+                                    out[2 * pr + cc].nelem * sizeof(double), cudaMemcpyDeviceToHost));
+    c->launches += 2 + 1 + 5;
+    return 0;
+  } catch (const std::exception& e) {
+    set_err(err, errlen, e.what());
+    return 1;
+  }
+}
+
+// ---- DMMA peak probe ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters) {
+  double c[8][2];
+#pragma unroll
+  for (int j = 0; j < 8; j++) { c[j][0] = 0.0; c[j][1] = 0.0; }
+  double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) dmma884(c[j][0], c[j][1], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int j = 0; j < 8; j++) s += c[j][0] + c[j][1];
+  if (s == 12345.678) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+extern "C" int pnfam_b200_dmma_peak(int device, double* tflops, char* err, int errlen) {
+  try {
+    require_device(device);
+    cudaDeviceProp prop;
+    PNFAM_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    DBuf<double> out;
+    const int blocks = prop.multiProcessorCount * 4, iters = 20000;
+    out.alloc((size_t)blocks * 256);
+    cudaEvent_t e0, e1;
+    PNFAM_CUDA_CHECK(cudaEventCreate(&e0)); PNFAM_CUDA_CHECK(cudaEventCreate(&e1));
+    dmma_peak_kernel<<<blocks, 256>>>(out.p, 1000);
+    double best = 0;
+    for (int rep = 0; rep < 3; rep++) {
+      PNFAM_CUDA_CHECK(cudaEventRecord(e0));
+      dmma_peak_kernel<<<blocks, 256>>>(out.p, iters);
+      PNFAM_CUDA_CHECK(cudaEventRecord(e1));
+      PNFAM_CUDA_CHECK(cudaEventSynchronize(e1));
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e0, e1);
+      const double flop = (double)blocks * 8 /*warps*/ * iters * 8 * 512.0;
+      best = std::max(best, flop / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *tflops = best;
+    return 0;
+  } catch (const std::exception& e) {
+    set_err(err, errlen, e.what());
+    return 1;
+  }
+}
