@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""bench.py -- pnFAM throughput on B200: FAM iterations/s and omega-points/s.
+
+Workload (config.workload): 162Gd, SkO', 16 HO shells, 40x40 Gauss grid (N=1958, nghl=1600, nxy=103926),
+Gamow-Teller K=0, synthetic CIRCLE contour sweep (pynfam/strength/contour.py:212-283 restated) with
+`--points` Gauss-Legendre nodes PER GPU, every point solved to convergence (eps=1e-7, M=50, max_iter=300).
+Inputs: tests/golden/Gd162_SKOP_16sh/ (made with the reference's own hfbtho_main).
+
+One "step" = one full batched contour solve on each rank (all FAM iterations of all its points).
+  value   = FAM iterations/s, whole job, device-resident (CUDA events around the iteration loop)
+  e2e     = same metric through the C ABI from HOST buffers: context creation (H2D of all tables) +
+            operator upload + solve + D2H of the strengths, wall clock, every step
+  impl=reference : the reference's unmodified pnfam_main.x (oracle/_ref) on the host cores, a bounded
+            sample of the same workload (one omega point, `--ref-iters` iterations), iterations/s from its
+            own per-iteration timer.
+"""
+import argparse
+import json
+import os
+import re
+import shutil
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+CASE = os.path.join(ROOT, "tests", "golden", "Gd162_SKOP_16sh")
+WORKLOAD = "Gd162 SkO' 16 shells 40x40 grid, GT- K=0, synthetic CIRCLE contour sweep"
+
+FAM_NML = """&general
+    fam_output_filename = 'GT-K0'
+    print_stdout = .true.
+    use_fam_storage = 0
+    real_eqrpa = {re}
+    imag_eqrpa = {im}
+/
+&ext_field
+    beta_type = '-'
+    operator_name = 'GT'
+    operator_k = 0
+    compute_crossterms = .true.
+    two_body_current_mode = 0
+/
+&interaction
+    interaction_name = 'SKOP'
+    require_self_consistency = .true.
+    require_gauge_invariance = .true.
+    force_j2_terms = .false.
+    vpair_t0 = -346.352
+    vpair_t1 = ,
+    override_cs0 = 128.279
+    override_csr = 0.0
+    override_cds = 0.0
+/
+&solver
+    max_iter = {max_iter}
+    convergence_epsilon = 1e-07
+    broyden_history_size = 50
+/
+"""
+
+
+def circle_contour(npts, emin=0.0, emax=10.0):
+    """CIRCLE contour of pynfam (strength/contour.py:212-283): omega_k = r0 + r exp(i theta_k), theta on
+    Gauss-Legendre nodes over [pi, 3pi].  All npts nodes are returned (no symmetry shortcut)."""
+    import numpy as np
+    x, _ = np.polynomial.legendre.leggauss(npts)
+    theta = np.pi + (x + 1.0) * np.pi
+    r0, r = 0.5 * (emin + emax), 0.5 * (emax - emin)
+    return r0 + r * np.exp(1j * theta)
+
+
+def stage(wd, omega, max_iter):
+    os.makedirs(wd, exist_ok=True)
+    for f in ("hfbtho_NAMELIST.dat", "hfbtho_output.hel"):
+        shutil.copy(os.path.join(CASE, f), wd)
+    with open(os.path.join(wd, "GT-K0.in"), "w") as f:
+        f.write(FAM_NML.format(re=repr(float(omega.real)), im=repr(float(omega.imag)), max_iter=max_iter))
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons during the timed region (NVML)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.sm, self.reasons, self.sm_max = index, False, [], set(), None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.sm_max = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                     nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+            while not self.stop_flag:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+                time.sleep(0.1)
+        except Exception as e:  # noqa: BLE001
+            self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
+
+    def summary(self):
+        s = sorted(self.sm)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons)}
+
+
+def run_reference(args, rank):
+    """Reference arm: the unmodified prebuilt pnfam_main.x on the host cores (kind 'reference')."""
+    if rank != 0:
+        return
+    from oracle import refrun
+    cores = os.cpu_count()
+    if not refrun.ensure_built():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/pnfam_main.x or the OpenBLAS wheel is missing"}))
+        return
+    om = circle_contour(args.points)[args.points // 3]
+    wd = tempfile.mkdtemp()
+    stage(wd, om, args.ref_iters)
+    per_iter = []
+    setup = []
+    for step in range(args.warmup + args.steps):
+        dat, wall, out = refrun.run_pnfam(wd, "GT-K0.in", threads=cores)
+        times = [float(m.group(1)) for m in re.finditer(r"^#\s+\d+[LB]\s+\S+\s+\S+\s+\S+\s+(\S+)\s*$", out, re.M)]
+        if not times:
+            print(json.dumps({"impl": "reference", "unavailable": "reference run produced no iteration table"}))
+            return
+        if step >= args.warmup:
+            per_iter += times
+            setup.append(wall - sum(times))
+    ips = len(per_iter) / sum(per_iter)
+    line = {
+        "impl": "reference", "metric": "FAM iterations/s (omega-points/s in omega_points_per_s)", "value": ips,
+        "unit": "iterations/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * sum(per_iter) / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "points_per_gpu": args.points, "shells": 16, "nghl": 1600},
+        "omega_points_per_s": ips / args.assumed_iters_per_point,
+        "cpu_baseline": {"value": ips, "unit": "iterations/s", "cores": cores, "kind": "reference",
+                         "sample": "1 omega point x %d FAM iterations per step, OMP=OPENBLAS threads=%d; per-iteration "
+                                   "time from pnfam_main.x's own timer; setup (HFB reconstruction, %.1f s/launch) excluded"
+                                   % (args.ref_iters, cores, sum(setup) / len(setup))},
+        "e2e": {"value": ips, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--points", type=int, default=32, help="omega points per GPU (weak scaling)")
+    ap.add_argument("--ref-iters", type=int, default=4)
+    ap.add_argument("--assumed-iters-per-point", type=float, default=25.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from pynfam_b200 import gpu, host
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the FAM iteration has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    # ---- this rank's shard of the contour (independent omega points: no data-path collective) --------
+    npts = args.points * world
+    omegas = circle_contour(npts)
+    mine = omegas[rank::world]
+    wd = tempfile.mkdtemp()
+    stage(wd, mine[0], 300)
+    t0 = time.time()
+    prob = host.Problem(wd, "GT-K0.in")
+    setup_s = time.time() - t0
+    ctx = gpu.Context(prob, device=local)
+    nghl, nxy, dqp = prob.iscalar("nghl"), prob.iscalar("nxy"), prob.iscalar("dqp")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    dmma_peak = gpu.dmma_peak_tflops(local)
+    for _ in range(args.warmup):
+        ctx.solve(prob, omegas=mine)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    dev_s, iters, launches = 0.0, 0, 0
+    dens_s = proj_s = dens_fl = proj_fl = 0.0
+    dens_n = proj_n = 0
+    last = None
+    for _ in range(args.steps):
+        r = ctx.solve(prob, omegas=mine)
+        st = r["stats"]
+        dev_s += st["seconds_device"]; iters += st["iterations"]; launches += st["kernel_launches"]
+        dens_s += st["seconds_density"]; proj_s += st["seconds_projection"]
+        dens_fl += st["flops_density"]; proj_fl += st["flops_projection"]
+        dens_n += st["launches_density"]; proj_n += st["launches_projection"]
+        last = r
+    barrier()
+    # ---- e2e: host buffers -> context + operator upload -> solve -> strengths back, wall clock ------
+    e2e_s, e2e_iters, h2d, d2h = 0.0, 0, 0, 0
+    model_bytes = 8 * (5 * nghl * dqp + 5 * nghl + 2 * dqp + 4 * int(prob.scalar("dmat")))
+    for _ in range(args.steps):
+        barrier()
+        t0 = time.perf_counter()
+        c2 = gpu.Context(prob, device=local)
+        r2 = c2.solve(prob, omegas=mine)
+        torch.cuda.synchronize()
+        e2e_s += time.perf_counter() - t0
+        e2e_iters += r2["stats"]["iterations"]
+        h2d += model_bytes + r2["stats"]["h2d_bytes"]
+        d2h += r2["stats"]["d2h_bytes"]
+        del c2
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    # ---- aggregate over ranks: time = max over ranks, work = sum -------------------------------------
+    vals = torch.tensor([dev_s, e2e_s], dtype=torch.float64, device="cuda")
+    sums = torch.tensor([iters, e2e_iters, launches, len(mine) * args.steps, h2d, d2h], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+        # gather the strengths (the only exchange the path has): [npts_rank][1+nx] complex
+        s_loc = torch.view_as_real(torch.from_numpy(np.ascontiguousarray(last["strength"])).cuda())
+        s_all = [torch.empty_like(s_loc) for _ in range(world)]
+        dist.all_gather(s_all, s_loc)
+    vals, sums = vals.cpu().numpy(), sums.cpu().numpy()
+    if rank == 0:
+        value = sums[0] / vals[0]
+        pts_per_s = sums[3] / vals[0]
+        # roofline of the dominant kernels (tensor-bound, FP64 DMMA): algorithmic flops / CUDA-event time
+        top = ("density", dens_fl, dens_s, dens_n) if dens_s >= proj_s else ("projection", proj_fl, proj_s, proj_n)
+        ach = top[1] / top[2] / 1e12 if top[2] > 0 else 0.0
+        line = {
+            "metric": "FAM iterations/s (omega-points/s in omega_points_per_s)", "value": value, "unit": "iterations/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * vals[0] / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "points_per_gpu": args.points, "shells": 16, "basis_states": dqp,
+                       "nghl": nghl, "nxy": nxy, "eps": 1e-7, "broyden_history": 50,
+                       "l2": "per-step working set (Broyden history 2*50*4*nxy*8 B per point = %.1f GB) >> 126 MB L2; "
+                             "no flush needed" % (len(mine) * 2 * 50 * 4 * nxy * 8 / 1e9)},
+            "omega_points_per_s": pts_per_s,
+            "iterations_per_point": sums[0] / sums[3],
+            "iterations_per_s_per_gpu": value / world,
+            "host_setup_s": setup_s,
+            "e2e": {"value": sums[1] / vals[1], "unit": "iterations/s", "h2d_bytes_per_step": int(sums[4] / args.steps / world),
+                    "d2h_bytes_per_step": int(sums[5] / args.steps / world), "omega_points_per_s": sums[3] / vals[1]},
+            "gpu_launches": int(sums[2]),
+            "roofline": {"bound": "tensor", "kernel": top[0], "achieved": ach, "peak": dmma_peak, "unit": "TFLOP/s",
+                         "frac": ach / dmma_peak if dmma_peak else None, "traffic": None,
+                         "peak_source": "FP64 DMMA (mma.sync m8n8k4) measured live by pnfam_b200_dmma_peak; "
+                                        "MEASURED_PEAKS.json carries no FP64 figure",
+                         "density": {"tflops": dens_fl / dens_s / 1e12 if dens_s else None, "share_of_step": dens_s / dev_s,
+                                     "ms_per_launch": 1e3 * dens_s / max(1, dens_n)},
+                         "projection": {"tflops": proj_fl / proj_s / 1e12 if proj_s else None, "share_of_step": proj_s / dev_s,
+                                        "ms_per_launch": 1e3 * proj_s / max(1, proj_n)}},
+            "clocks": sampler.summary(),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(args):
+    """Rank 0, N=1: the reference binary (kind 'reference') or, if it did not travel, the numpy oracle port, on a
+    bounded sample of the same workload."""
+    from oracle import refrun
+    cores = os.cpu_count()
+    om = circle_contour(args.points)[args.points // 3]
+    wd = tempfile.mkdtemp()
+    stage(wd, om, args.ref_iters)
+    if refrun.ensure_built():
+        dat, wall, out = refrun.run_pnfam(wd, "GT-K0.in", threads=cores)
+        times = [float(m.group(1)) for m in re.finditer(r"^#\s+\d+[LB]\s+\S+\s+\S+\s+\S+\s+(\S+)\s*$", out, re.M)]
+        if times:
+            return {"value": len(times) / sum(times), "unit": "iterations/s", "cores": cores, "kind": "reference",
+                    "sample": "oracle/_ref/pnfam_main.x, 1 omega point x %d iterations, %d threads; wall %.1f s incl. %.1f s setup"
+                              % (len(times), cores, wall, wall - sum(times))}
+    from oracle import fam_oracle as fo
+    from pynfam_b200 import host
+    p = host.Problem(wd, "GT-K0.in")
+    s = fo.solver_from_problem(p)
+    t0 = time.time()
+    s.solve(2, 1e-7)
+    return {"value": 2 / (time.time() - t0), "unit": "iterations/s", "cores": 1, "kind": "port",
+            "sample": "numpy oracle, 1 omega point x 2 iterations"}
+
+
+if __name__ == "__main__":
+    main()

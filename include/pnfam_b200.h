@@ -95,6 +95,8 @@ typedef struct {
   int64_t h2d_bytes, d2h_bytes;
   double seconds_density, seconds_projection; /* CUDA-event time spent in the two dominant kernels */
   int64_t launches_density, launches_projection;
+  double flops_density, flops_projection;     /* algorithmic FP64 flops of those launches: (16+4) and (20+4) x nghl x nxy
+                                                 per (point, pass), SURVEY.md section 8d */
 } pnfam_b200_stats;
 
 /* Solve npoints complex frequencies of one operator.  Outputs (host buffers):

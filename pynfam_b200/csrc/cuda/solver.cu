@@ -378,6 +378,7 @@ extern "C" int pnfam_b200_solve(pnfam_b200_ctx* c, const pnfam_b200_operator* op
     PNFAM_CUDA_CHECK(cudaEventRecord(ev0, st));
     double t_dens = 0, t_proj = 0;
     int64_t n_dens = 0, n_proj = 0, total_iters = 0;
+    double fl_dens = 0, fl_proj = 0;
     int nactive = P;
     // the loop of ifam (pnfam_solver.f90:114-209) for all still-active points in lock step
     for (int it = 0; it < prm->max_iter && nactive > 0; it++) {
@@ -401,6 +402,8 @@ extern "C" int pnfam_b200_solve(pnfam_b200_ctx* c, const pnfam_b200_operator* op
         launch_transform(od->bwd, b, nactive, st);
         launches += 2 + 2 + 1 + 5 + 2;
         n_dens += 2; n_proj += 4;
+        fl_dens += (double)nactive * 2.0 * 20.0 * c->nghl * (double)nxy;
+        fl_proj += (double)nactive * 2.0 * 24.0 * c->nghl * (double)nxy;
       }
       launch_greens(ma, st);
       launch_broyden(ma, it, st);
@@ -450,6 +453,7 @@ extern "C" int pnfam_b200_solve(pnfam_b200_ctx* c, const pnfam_b200_operator* op
       stats->kernel_launches = launches; stats->h2d_bytes = h2d; stats->d2h_bytes = d2h;
       stats->seconds_density = t_dens; stats->seconds_projection = t_proj;
       stats->launches_density = n_dens; stats->launches_projection = n_proj;
+      stats->flops_density = fl_dens; stats->flops_projection = fl_proj;
     }
     c->launches += launches;
     return 0;

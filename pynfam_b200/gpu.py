@@ -40,7 +40,8 @@ class Stats(ctypes.Structure):
                 ("iterations", ctypes.c_int64), ("kernel_launches", ctypes.c_int64),
                 ("h2d_bytes", ctypes.c_int64), ("d2h_bytes", ctypes.c_int64),
                 ("seconds_density", ctypes.c_double), ("seconds_projection", ctypes.c_double),
-                ("launches_density", ctypes.c_int64), ("launches_projection", ctypes.c_int64)]
+                ("launches_density", ctypes.c_int64), ("launches_projection", ctypes.c_int64),
+                ("flops_density", ctypes.c_double), ("flops_projection", ctypes.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -1,0 +1,176 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Everything goes through the C ABI of
+libpnfam_b200.so (pynfam_b200.gpu is a thin ctypes view).  The checker is the CPU oracle (oracle/) and the
+reference's golden vectors (tests/golden/); tolerance 1e-9 relative on the complex strength and cross-terms
+as stated by BASELINE.json's north_star (observed agreement is ~1e-14)."""
+import numpy as np
+import pytest
+
+from conftest import gold_rows, load_points, stage_point
+from oracle import fam_oracle as fo
+from pynfam_b200 import host
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from pynfam_b200 import gpu as g
+    return g
+
+
+def _rel(a, b):
+    return abs(a - b) / abs(b)
+
+
+CASES = [
+    ("S40_SKOP_6sh", "GT-K0", 10),
+    ("S40_GT_All", "RS0-K0", 5),
+    ("S40_GT_All", "P-K1", 3),
+    ("S40_GT_All", "RS2-K2", 7),
+    ("S40_GT_All", "R-K0", 1),
+    ("S40_GT_All", "F-K0", 2),
+    ("Gd162_GT_open_6sh", "GT-K1", 40),
+    ("Gd162_1-_closed_6sh", "RS1-K1", 4),
+    ("Gd162_0-_closed_6sh", "PS0-K0", 8),
+]
+
+
+@pytest.mark.parametrize("case,op,idx", CASES)
+def test_trajectory_matches_oracle_and_golden(gpu, case, op, idx, tmp_path):
+    pt = stage_point(case, op, idx, str(tmp_path))
+    p = host.Problem(str(tmp_path), "x.in")
+    ctx = gpu.Context(p)
+    model = fo.model_from_problem(p)
+    for mi in (1, 2, 4):
+        so = fo.solver_from_problem(p, model)
+        _, si, st = so.solve(mi, 1e-7)
+        r = ctx.solve(p, max_iter=mi)
+        assert abs(r["si"][0] - si) <= 1e-9 * si
+        for k in range(len(st)):
+            assert _rel(r["strength"][0, k], st[k]) < TOL, (mi, k)
+    r = ctx.solve(p, want_trace=True)
+    gold = gold_rows(pt)
+    assert int(r["iters"][0]) == pt["iters"] and int(r["conv"][0]) == 1
+    for k, lab in enumerate(["Strength"] + r["labels"][1:]):
+        if lab in gold:
+            assert _rel(r["strength"][0, k], gold[lab]) < TOL, lab
+    for (i, _, si_g, re_g, im_g) in pt["trace"]:
+        t = r["trace"][0, i]
+        assert abs(t[0] - si_g) < 6e-11 and abs(t[1] - re_g) < 6e-11 and abs(t[2] - im_g) < 6e-11
+
+
+@pytest.mark.parametrize("case,op", [("S40_SKOP_6sh", "GT-K0"), ("S40_GT_All", "RS1-K1"), ("Gd162_GT_open_6sh", "GT-K0")])
+def test_whole_contour_batched_against_golden(gpu, case, op, tmp_path):
+    """All omega points of one operator in ONE batched call (how the product is meant to be driven)."""
+    pts = load_points(case)[op]
+    stage_point(case, op, 0, str(tmp_path))
+    p = host.Problem(str(tmp_path), "x.in")
+    ctx = gpu.Context(p)
+    import re
+    om = []
+    for pt in pts:
+        om.append(complex(float(re.search(r"real_eqrpa\s*=\s*(\S+)", pt["namelist"]).group(1)),
+                          float(re.search(r"imag_eqrpa\s*=\s*(\S+)", pt["namelist"]).group(1))))
+    r = ctx.solve(p, omegas=om)
+    for i, pt in enumerate(pts):
+        gold = gold_rows(pt)
+        assert int(r["iters"][i]) == pt["iters"], i
+        for k, lab in enumerate(["Strength"] + r["labels"][1:]):
+            if lab in gold:
+                assert _rel(r["strength"][i, k], gold[lab]) < TOL, (i, lab)
+
+
+def test_calc_hamiltonian_entry_matches_oracle(gpu, tmp_path):
+    stage_point("Gd162_GT_open_6sh", "GT-K1", 40, str(tmp_path))
+    p = host.Problem(str(tmp_path), "x.in")
+    ctx = gpu.Context(p)
+    s = fo.solver_from_problem(p)
+    s.iterate(0)
+    s.iterate(1)
+    order = [(11, 0), (11, 1), (12, 0), (12, 1), (22, 0), (22, 1), (21, 0), (21, 1)]
+    ins = [(s.dRsp_im if c else s.dRsp_re).m[q].copy() for q, c in order]
+    ref = [(s.dHsp_im if c else s.dHsp_re).m[q].copy() for q, c in order]
+    outs = [r.copy() for r in ref]
+    for o in outs:
+        o.elem = np.zeros_like(o.elem)
+    ctx.calc_hamiltonian(ins, outs)
+    scale = max(np.abs(r.elem).max() for r in ref)
+    for o, r in zip(outs, ref):
+        assert np.abs(o.elem - r.elem).max() < 1e-12 * scale
+    # linearity (size-independent property): H(2x - 3y) = 2 H(x) - 3 H(y)
+    rng = np.random.default_rng(7)
+    x = [b.copy() for b in ins]
+    y = [b.copy() for b in ins]
+    for b in y:
+        b.elem = rng.standard_normal(len(b.elem))
+    z = [b.copy() for b in ins]
+    for bz, bx, by in zip(z, x, y):
+        bz.elem = 2 * bx.elem - 3 * by.elem
+    hx, hy, hz = ([r.copy() for r in ref] for _ in range(3))
+    ctx.calc_hamiltonian(x, hx)
+    ctx.calc_hamiltonian(y, hy)
+    ctx.calc_hamiltonian(z, hz)
+    sc = max(np.abs(b.elem).max() for b in hy)
+    for a, b, c in zip(hx, hy, hz):
+        assert np.abs(c.elem - (2 * a.elem - 3 * b.elem)).max() < 1e-12 * sc
+
+
+def test_mixer_variants_match_oracle(gpu, tmp_path):
+    """Broyden ring-buffer wrap-around (M=3), linear mixing (M=0) and no residual interaction (M<0)."""
+    stage_point("S40_SKOP_6sh", "GT-K0", 10, str(tmp_path))
+    p = host.Problem(str(tmp_path), "x.in")
+    ctx = gpu.Context(p)
+    model = fo.model_from_problem(p)
+    for M, mi in ((3, 12), (1, 6), (0, 8)):
+        so = fo.FamSolver(model, p.i32("f_ir2c"), p.f64("f_elem"), [], True,
+                          complex(p.scalar("real_eqrpa"), p.scalar("imag_eqrpa")), 1.0, M)
+        _, si, st = so.solve(mi, 1e-7)
+        r = ctx.solve(p, max_iter=mi, history=M)
+        assert _rel(r["strength"][0, 0], st[0]) < TOL and abs(r["si"][0] - si) < 1e-9 * si, M
+    stage_point("S40_SKOP_6sh", "GT-K0", 10, str(tmp_path), name="none.in",
+                patch=lambda s: s.replace("interaction_name = 'SKOP'", "interaction_name = 'NONE'"))
+    pn = host.Problem(str(tmp_path), "none.in", share_nucleus_with=p)
+    r = gpu.Context(pn).solve(pn)
+    ref = complex(2.3502388218313224888E-01, -5.6592934893661954454E-02)   # live reference binary, SURVEY.md 8c
+    assert int(r["iters"][0]) == 2 and r["si"][0] == 0.0 and _rel(r["strength"][0, 0], ref) < TOL
+
+
+def test_symmetry_and_batch_independence(gpu, tmp_path):
+    """S(omega*) = S(omega)* (the symmetry pynfam uses to fill half of a closed contour,
+    pynfam/strength/fam_strength.py:292-338); a batched solve equals the same points solved one at a time."""
+    stage_point("S40_GT_All", "RS1-K0", 3, str(tmp_path))
+    p = host.Problem(str(tmp_path), "x.in")
+    ctx = gpu.Context(p)
+    w = complex(p.scalar("real_eqrpa"), p.scalar("imag_eqrpa"))
+    oms = [w, w.conjugate(), w + 1.5, w + 4.0 - 0.7j]
+    rb = ctx.solve(p, omegas=oms)
+    assert np.abs(rb["strength"][1] - rb["strength"][0].conj()).max() < 1e-12 * np.abs(rb["strength"][0]).max()
+    for i, o in enumerate(oms):
+        r1 = ctx.solve(p, omegas=[o])
+        assert int(r1["iters"][0]) == int(rb["iters"][i])
+        assert np.abs(r1["strength"][0] - rb["strength"][i]).max() <= 1e-13 * np.abs(rb["strength"][i]).max()
+
+
+def test_gd162_16_shells_against_reference_binary(gpu, tmp_path):
+    """Full production size (N=1958, nghl=1600, nxy=103926): known answers produced by the reference's own
+    pnfam_main.x (tests/golden/make_gd162_16sh.py)."""
+    pts = load_points("Gd162_SKOP_16sh")
+    ctx = None
+    base = None
+    for op, lst in pts.items():
+        for i, pt in enumerate(lst):
+            stage_point("Gd162_SKOP_16sh", op, i, str(tmp_path), name="%s_%d.in" % (op, i))
+            p = host.Problem(str(tmp_path), "%s_%d.in" % (op, i), share_nucleus_with=base)
+            if base is None:
+                base = p
+                ctx = gpu.Context(p)
+            r = ctx.solve(p)
+            gold = gold_rows(pt)
+            assert int(r["iters"][0]) == pt["iters"]
+            for k, lab in enumerate(["Strength"] + r["labels"][1:]):
+                if lab in gold:
+                    assert _rel(r["strength"][0, k], gold[lab]) < TOL, (op, i, lab)

@@ -1,0 +1,102 @@
+"""CPU tests of the host logic and of the C ABI surface (no GPU compute)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, stage_point
+from oracle import refrun
+from pynfam_b200 import host
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "pnfam_b200.h")).read()
+    return sorted(set(re.findall(r"\b(pnfam_(?:b200_|problem_)\w+)\s*\(", hdr)))
+
+
+def test_every_declared_symbol_is_exported():
+    syms = _declared_symbols()
+    assert len(syms) >= 12
+    libs = [ctypes.CDLL(os.path.join(ROOT, "pynfam_b200", "lib", n)) for n in ("libpnfam_host.so", "libpnfam_b200.so")]
+    for s in syms:
+        assert any(hasattr(l, s) for l in libs), s
+
+
+def test_gpu_library_fails_loudly_without_device():
+    """No CPU fallback: without a CUDA device the DMMA probe (and every other entry) must return an error."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from pynfam_b200 import gpu
+    with pytest.raises(gpu.GpuError, match="no CUDA device|CUDA"):
+        gpu.dmma_peak_tflops()
+
+
+def test_namelist_roundtrip(tmp_path):
+    g = {"general": {"fam_output_filename": "GT-K0", "print_stdout": True, "real_eqrpa": 0.5, "imag_eqrpa": -2.25},
+         "interaction": {"interaction_name": "SKOP", "vpair_t1": None, "override_cs0": 128.279}}
+    path = str(tmp_path / "a.in")
+    refrun.write_namelist(path, g)
+    back = refrun.read_namelist(path)
+    assert back["general"]["fam_output_filename"] == "GT-K0"
+    assert back["general"]["imag_eqrpa"] == -2.25
+    assert back["interaction"]["vpair_t1"] is None
+
+
+def test_front_end_basis_and_orthonormality(tmp_path):
+    stage_point("S40_SKOP_6sh", "GT-K0", 0, str(tmp_path))
+    p = host.Problem(str(tmp_path), "x.in")
+    assert (p.iscalar("dqp"), p.iscalar("nb"), p.iscalar("nghl"), p.iscalar("nxy")) == (168, 26, 400, 1640)
+    wf = p.table("wf")
+    ns, nl, nz = p.i32("ns"), p.i32("nl"), p.i32("nz")
+    g = wf.T @ wf
+    # quadrature-orthonormal within equal (Lambda, z-parity); the z mesh covers z>0 only (reflection symmetry)
+    # and the table carries sqrt(weights)
+    same = (nl[:, None] == nl[None, :]) & ((nz[:, None] % 2) == (nz[None, :] % 2)) & (ns[:, None] == ns[None, :])
+    assert np.abs((g - np.eye(168))[same]).max() < 1e-12
+    # spin-up states first inside every block
+    db, nsu = p.i32("db"), p.i32("num_spin_up")
+    o = 0
+    for d, u in zip(db, nsu):
+        assert (ns[o:o + u] == 1).all() and (ns[o + u:o + d] == -1).all()
+        o += d
+    # U^T U + V^T V = 1 on the active quasiparticles (columns above the pairing window are zeroed)
+    for t in "np":
+        U, V, E = p.f64("U" + t), p.f64("V" + t), p.f64("E" + t)
+        o = q = 0
+        for d in db:
+            u, v = U[o:o + d * d].reshape(d, d, order="F"), V[o:o + d * d].reshape(d, d, order="F")
+            nrm = (u * u).sum(0) + (v * v).sum(0)
+            act = E[q:q + d] != 0
+            assert np.abs(nrm[act] - 1).max() < 1e-12 and (nrm[~act] == 0).all()
+            o += d * d
+            q += d
+    # particle number from the normalised coordinate-space densities
+    w = 1.0 / p.f64("wdcori")
+    assert abs((p.f64("rho_n") * w).sum() - 24) < 1e-9 and abs((p.f64("rho_p") * w).sum() - 16) < 1e-9
+
+
+def test_couplings_match_reference_header(tmp_path):
+    """The .dat header of the golden point prints the couplings to 9 decimals."""
+    stage_point("S40_SKOP_6sh", "GT-K0", 10, str(tmp_path))
+    p = host.Problem(str(tmp_path), "x.in")
+    want = dict(cr0=246.942585311, crr=-198.724045856, cs0=128.279, csr=0.0, cdrho=-32.162034342, ctau=-4.156239521,
+                cj=4.156239521, crdj=41.4444, csdj=41.4444, ctj0=3.057291667, ctj1=4.5859375, ctj2=9.171875,
+                ct=-9.171875, cf=0.0, cpair0=-33.027032645, cpairr=103.100736927, cspair0=-43.294, cspairr=135.151206361)
+    for k, v in want.items():
+        assert abs(p.scalar(k) - v) < 6e-10, (k, p.scalar(k), v)
+
+
+def test_bad_inputs_fail_cleanly(tmp_path):
+    stage_point("S40_SKOP_6sh", "GT-K0", 10, str(tmp_path),
+                patch=lambda s: s.replace("operator_name = 'GT'", "operator_name = 'XYZ'"))
+    with pytest.raises(host.PnfamError, match="Unknown operator"):
+        host.Problem(str(tmp_path), "x.in")
+    stage_point("S40_SKOP_6sh", "GT-K0", 10, str(tmp_path),
+                patch=lambda s: s.replace("operator_k = 0", "operator_k = 2"))
+    with pytest.raises(host.PnfamError, match="K out of range"):
+        host.Problem(str(tmp_path), "x.in")
+    with pytest.raises(host.PnfamError):
+        host.Problem(str(tmp_path / "nowhere"), "x.in")
