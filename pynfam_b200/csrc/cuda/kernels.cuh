@@ -35,11 +35,24 @@ constexpr int NDD_KAP = 2 * 2 * 2;
 constexpr int NMF = 5 * 5 * 2 * 2 * 2;       // field tensor mf(ta,tb,sa,sb) complex, doubles per grid point
 constexpr int NPF = 2 * 2 * 2;               // pairing field (sa,sb) complex
 
+// One pipeline step of the density kernel: an (a-chunk x b-chunk) piece of one block of rho / kappa.
+struct DensStep {
+  int a_row0, nac;      // first basis state (global index) and count of the contraction chunk (one spin segment)
+  int b_row0, nbc;      // first column state (global index) and count
+  int rho_off, ld;      // element offset of (a chunk start, b chunk start) inside the block matrix, leading dim
+  int flags;            // bit0: new b-chunk (load phi_b into buffer bbuf); bit1: first a-chunk (zero C); bit2: last (epilogue)
+  int ssp;              // s*2 + sp  (spin of a-segment, spin of b-segment);  bit 4: bbuf
+};
+constexpr int DENS_AC = 48;   // contraction chunk
+constexpr int DENS_BC = 32;   // column chunk
+
 struct HamArgs {
   DevBasis basis;
   // per pass q=0 (pn,+) / q=1 (np,-): input structures (dRsp quadrants) and output structures (dHsp quadrants)
   DevBlockStruct rho_in[2], kap_in[2], h_out[2], d_out[2];
   int rho_quad[2], kap_quad[2];   // storage quadrant of rho / kappa (and of h / Delta) for each pass
+  const DensStep* steps_rho[2]; int nsteps_rho[2];   // pipeline step lists of the density kernel, per pass
+  const DensStep* steps_kap[2]; int nsteps_kap[2];
   const double* rsp;              // [P][2 c][4][nxy]
   double* hsp;                    // [P][2 c][4][nxy]
   size_t nxy;
@@ -61,6 +74,9 @@ struct ProjPlan {                 // output tiles of the grid->HO projection
 };
 
 void launch_density(const HamArgs& a, cudaStream_t stream);
+// host helper: flatten a block structure into density pipeline steps
+void build_density_steps(int nb, const int* db, const int* isstart, const int* nsu, const int* r2c, const int* r2m,
+                         DensStep* out, int* nout);  // out may be null to count
 void launch_fields(const HamArgs& a, cudaStream_t stream);
 void launch_projection(const HamArgs& a, const ProjPlan& pp, cudaStream_t stream);
 size_t projection_partial_elems(const ProjPlan& pp, size_t nxy);

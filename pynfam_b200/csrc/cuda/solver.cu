@@ -145,8 +145,17 @@ struct OperatorDev {
   DBuf<int4> tiles_h, tiles_d;
   ProjPlan proj;
   DBuf<double> gqp, esum, tfac;
+  DBuf<DensStep> dsteps[4];       // rho pass0, rho pass1, kappa pass0, kappa pass1
+  int ndsteps[4] = {0, 0, 0, 0};
   size_t scratch_elems = 0;
 };
+
+void upload_density_steps(const pnfam_b200_ctx& c, const BlockStruct& st, DBuf<DensStep>& buf, int& n) {
+  build_density_steps(c.nb, c.db.data(), c.isstart.data(), c.nsu.data(), st.r2c.data(), st.r2m.data(), nullptr, &n);
+  std::vector<DensStep> h(std::max(n, 1));
+  build_density_steps(c.nb, c.db.data(), c.isstart.data(), c.nsu.data(), st.r2c.data(), st.r2m.data(), h.data(), &n);
+  buf.upload(h);
+}
 
 void flatten(const TransformPlan& tp, DBuf<DevTask>& dt, DBuf<int2>& de, DevicePlan& out) {
   std::vector<DevTask> tasks;
@@ -198,7 +207,7 @@ void build_proj_tiles(const pnfam_b200_ctx& c, const BlockStruct st[2], std::vec
       const int di = c.db[ix], dj = c.db[iy], nu = c.nsu[ix];
       for (int s = 0; s < 2; s++) {
         const int lo = s == 0 ? 0 : nu, hi = s == 0 ? nu : di;
-        for (int a0 = lo; a0 < hi; a0 += 64)
+        for (int a0 = lo; a0 < hi; a0 += 48)
           for (int b0 = 0; b0 < dj; b0 += 32) tiles.push_back(make_int4(ix, a0, b0, 0));
       }
     }
@@ -214,6 +223,10 @@ std::unique_ptr<OperatorDev> make_operator(pnfam_b200_ctx& c, const pnfam_b200_o
   flatten(od->plan.backward, od->bwd_tasks, od->bwd_entries, od->bwd);
   od->scratch_elems = std::max(od->fwd.scratch_elems, od->bwd.scratch_elems);
   for (int k = 0; k < 4; k++) { od->sp[k].upload(od->plan.sp[k]); od->hsp[k].upload(od->plan.hsp[k]); }
+  upload_density_steps(c, od->plan.sp[0], od->dsteps[0], od->ndsteps[0]);
+  upload_density_steps(c, od->plan.sp[3], od->dsteps[1], od->ndsteps[1]);
+  upload_density_steps(c, od->plan.sp[1], od->dsteps[2], od->ndsteps[2]);
+  upload_density_steps(c, od->plan.sp[2], od->dsteps[3], od->ndsteps[3]);
   // projection output tiles: pass 0 -> (h_pn = hsp[0], Delta+ = hsp[1]); pass 1 -> (h_np = hsp[3], Delta- = hsp[2])
   {
     std::vector<int4> th, td;
@@ -240,6 +253,10 @@ HamArgs make_ham_args(const pnfam_b200_ctx& c, const OperatorDev& od) {
   h.h_out[0] = od.hsp[0].view(); h.d_out[0] = od.hsp[1].view(); h.h_out[1] = od.hsp[3].view(); h.d_out[1] = od.hsp[2].view();
   h.rho_quad[0] = 0; h.kap_quad[0] = 1; h.rho_quad[1] = 3; h.kap_quad[1] = 2;
   h.nxy = od.plan.nxy;
+  for (int q = 0; q < 2; q++) {
+    h.steps_rho[q] = od.dsteps[q].p; h.nsteps_rho[q] = od.ndsteps[q];
+    h.steps_kap[q] = od.dsteps[2 + q].p; h.nsteps_kap[q] = od.ndsteps[2 + q];
+  }
   return h;
 }
 
@@ -496,6 +513,16 @@ extern "C" int pnfam_b200_calc_hamiltonian(pnfam_b200_ctx* c, const pnfam_b200_b
     h.h_out[0] = sout[0].view(); h.d_out[0] = sout[1].view(); h.h_out[1] = sout[2].view(); h.d_out[1] = sout[3].view();
     h.rho_quad[0] = 0; h.kap_quad[0] = 1; h.rho_quad[1] = 3; h.kap_quad[1] = 2;
     h.nxy = nxy;
+    DBuf<DensStep> dsteps[4];
+    int ndsteps[4];
+    upload_density_steps(*c, hin[0], dsteps[0], ndsteps[0]);
+    upload_density_steps(*c, hin[2], dsteps[1], ndsteps[1]);
+    upload_density_steps(*c, hin[1], dsteps[2], ndsteps[2]);
+    upload_density_steps(*c, hin[3], dsteps[3], ndsteps[3]);
+    for (int q = 0; q < 2; q++) {
+      h.steps_rho[q] = dsteps[q].p; h.nsteps_rho[q] = ndsteps[q];
+      h.steps_kap[q] = dsteps[2 + q].p; h.nsteps_kap[q] = ndsteps[2 + q];
+    }
     ProjPlan pp;
     DBuf<int4> th, td;
     {

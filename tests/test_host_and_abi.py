@@ -100,3 +100,21 @@ def test_bad_inputs_fail_cleanly(tmp_path):
         host.Problem(str(tmp_path), "x.in")
     with pytest.raises(host.PnfamError):
         host.Problem(str(tmp_path / "nowhere"), "x.in")
+
+
+def test_drop_in_exe_without_gpu_reports_failure_the_reference_way(tmp_path):
+    """Without a CUDA device the drop-in must not fall back to a CPU path: like the reference on an error it
+    exits 0, keeps stderr silent and emits no result table, which is how pynfam detects a failed task
+    (pynfam/fortran/pnfam_run.py:155-164)."""
+    import subprocess
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    exe = os.path.join(ROOT, "pynfam_b200", "bin", "pnfam_main.x")
+    assert os.path.isfile(exe)
+    stage_point("S40_SKOP_6sh", "GT-K0", 10, str(tmp_path), name="GT-K0.in")
+    r = subprocess.run([exe, "GT-K0.in"], cwd=str(tmp_path), capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stderr.strip() == ""
+    assert "no CUDA device" in r.stdout
+    assert "Strength" not in refrun.parse_dat(r.stdout)["rows"]
+    assert not os.path.isfile(str(tmp_path / "GT-K0.dat"))
