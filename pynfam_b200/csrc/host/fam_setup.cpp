@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cctype>
 #include <cmath>
+#include <fstream>
 #include <stdexcept>
 
 namespace pnfam {
@@ -365,7 +366,8 @@ static std::vector<double> i1111(const FamBasis& b) {
   return I;
 }
 
-ExtField make_external_field(const FamBasis& b, const std::string& beta_type, const std::string& label_in, int K) {
+ExtField make_external_field(const FamBasis& b, const std::string& beta_type, const std::string& label_in, int K,
+                             const std::vector<double>* rho_fac) {
   ExtField op;
   op.label = upper(label_in);
   const std::string& L = op.label;
@@ -420,8 +422,14 @@ ExtField make_external_field(const FamBasis& b, const std::string& beta_type, co
         if (B == "F") {
           if (xl1 == xl2 && xs1 == xs2) me = dot(wf1, wf2);
         } else if (B == "GT") {
-          if (K == 0) { if (xl1 == xl2 && xs1 == xs2) me = xs1 * dot(wf1, wf2); }
-          else { if (xl1 == xl2 && xs1 == xs2 + 2 * K) me = -K * sq2 * dot(wf1, wf2); }
+          auto dotg = [&](const double* a, const double* cc) {
+            if (!rho_fac) return dot(a, cc);
+            double s = 0;
+            for (int i = 0; i < nghl; i++) s += a[i] * ((*rho_fac)[i] * cc[i]);
+            return s;
+          };
+          if (K == 0) { if (xl1 == xl2 && xs1 == xs2) me = xs1 * dotg(wf1, wf2); }
+          else { if (xl1 == xl2 && xs1 == xs2 + 2 * K) me = -K * sq2 * dotg(wf1, wf2); }
         } else if (B == "R") {
           if (K == 0) { if (xl1 == xl2 && xs1 == xs2) me = dotw(wf1, b.z, wf2); }
           else { if (xl1 == xl2 + K && xs1 == xs2) me = -K / sq2 * dotw(wf1, r, wf2); }
@@ -479,9 +487,68 @@ std::vector<ExtField> make_crossterms(const FamBasis& b, const ExtField& op) {
   return out;
 }
 
-bool read_tbc(const std::string&, const FamBasis&, const FamInput&, ExtField&, std::string& why) {
-  why = "two-body-current (.tbc) input is not wired in yet";
-  return false;
+bool read_tbc(const std::string& path, const FamBasis& b, const FamInput& in, ExtField& f, std::string& why) {
+  std::ifstream probe(path, std::ios::binary);
+  if (!probe) { why = "cannot open " + path + " (computing the two-body-current field from scratch is not supported)"; return false; }
+  probe.close();
+  FortUnformatted fu(path);
+  FortRecord r;
+  const size_t nxy = f.mat.elem.size();
+  const double c3new = in.two_body_current_lecs[0], c4new = in.two_body_current_lecs[1] + 0.25;
+  bool found = false;
+  while (fu.next(r)) {
+    if (r.size() != 8 || r.get_str(8) != "extf_2bc") continue;
+    auto need = [&]() { if (!fu.next(r)) throw std::runtime_error(".tbc: truncated file"); };
+    need(); const int use_hblas = r.get<int32_t>();
+    need(); /* mode */
+    need(); const int usep = r.get<int32_t>();
+    need(); /* lecs */
+    need();
+    const int nb_r = r.get<int32_t>(), dqp_r = r.get<int32_t>(), nxy_r = r.get<int32_t>(), nxy12_r = r.get<int32_t>();
+    need();
+    std::string label = r.get_str(std::min<size_t>(r.size(), 80));
+    while (!label.empty() && (label.back() == ' ' || label.back() == 0)) label.pop_back();
+    need(); const int k_r = r.get<int32_t>();
+    need(); /* rank */
+    need(); const int bm_r = r.get<int32_t>();
+    need(); const int pe_r = r.get<int32_t>();
+    need(); /* use_2bc */
+    if (use_hblas != 1 || (usep == 0 && in.two_body_current_usep) || nb_r != b.nb || dqp_r != b.dqp || (size_t)nxy_r != nxy ||
+        nxy12_r > 0 || label != f.label || k_r != f.k || bm_r != (f.beta_minus ? 1 : 0) || pe_r != (f.parity_even ? 1 : 0)) {
+      why = "the file '" + path + "' is incompatible with the current calculation";
+      return false;
+    }
+    std::vector<double> tot(nxy, 0.0);
+    const double fac[4] = {c3new, c3new, c4new, c4new};
+    for (int a = 0; a < 4 + (usep ? 2 : 0); a++) {
+      need();
+      if (r.size() != nxy * 8) throw std::runtime_error(".tbc: unexpected record size");
+      std::vector<double> v = r.get_vec<double>(nxy);
+      const double s = a < 4 ? fac[a] : 1.0;
+      for (size_t i = 0; i < nxy; i++) tot[i] += v[i] * s;
+    }
+    f.mat.elem = tot;
+    found = true;
+    break;
+  }
+  if (!found) why = "no extf_2bc record in " + path;
+  return found;
+}
+
+void apply_two_body_current_gt(const std::string& tbc_path, const FamBasis& b, const FamInput& in, int i1, ExtField& f) {
+  // constants of init_extfield_2bc_type (pnfam_type_extfield_2bc.f90:47-77, pnfam_constants.f90:44-67)
+  const double hbarc = 197.3269718, Fpi = 92.4, Mn = 939.0;
+  const double caux = (hbarc * hbarc * hbarc) / (2.0 * Mn * Fpi * Fpi);
+  const double cd = in.two_body_current_lecs[2] * (-0.25);
+  std::vector<double> tmp(f.mat.elem.size(), 0.0);
+  if (i1 == 1) for (size_t i = 0; i < tmp.size(); i++) tmp[i] = -f.mat.elem[i];   // Park sign convention: -sigma tau + 2BC
+  std::vector<double> rho_fac(b.nghl);
+  for (int r = 0; r < b.nghl; r++) rho_fac[r] = (caux * 2.0 * cd) * (b.rho_n[r] + b.rho_p[r]);
+  ExtField contact = make_external_field(b, f.beta_minus ? "-" : "+", f.label, f.k, &rho_fac);
+  for (size_t i = 0; i < tmp.size(); i++) tmp[i] += contact.mat.elem[i];
+  std::string why;
+  if (!read_tbc(tbc_path, b, in, f, why)) throw std::runtime_error(why);
+  for (size_t i = 0; i < tmp.size(); i++) f.mat.elem[i] += tmp[i];
 }
 
 }  // namespace pnfam

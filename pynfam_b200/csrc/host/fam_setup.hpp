@@ -98,9 +98,16 @@ struct ExtField {
   BlockMatrix mat;
 };
 
-ExtField make_external_field(const FamBasis& b, const std::string& beta_type, const std::string& label, int k);
+// rho_fac (optional, nghl): weight folded into the GT operator, sigma tau f(rho) -- the contact part of the
+// two-body current (pnfam_extfield.f90:167-190)
+ExtField make_external_field(const FamBasis& b, const std::string& beta_type, const std::string& label, int k,
+                             const std::vector<double>* rho_fac = nullptr);
 std::vector<ExtField> make_crossterms(const FamBasis& b, const ExtField& op);
 // Read the Yukawa part of a two-body-current field from <name>.tbc (pnfam_storage.f90:562-727).
+// On success f.mat.elem holds c3/c4-weighted gamma (direct + exchange) exactly as read_tbc leaves it.
 bool read_tbc(const std::string& path, const FamBasis& b, const FamInput& in, ExtField& f, std::string& why);
+// Full two-body-current GT field of mode i1 i2=1 i3=1 i4>0 (pnfam_solver.f90:596-652):
+//   F = [-GT_1body if i1==1] + GT[contact rho_fac] + Yukawa part from <name>.tbc
+void apply_two_body_current_gt(const std::string& tbc_path, const FamBasis& b, const FamInput& in, int i1, ExtField& f);
 
 }  // namespace pnfam

@@ -48,9 +48,8 @@ std::unique_ptr<Problem> Problem::load(const std::string& rundir, const std::str
   p->f = make_external_field(b, in.beta_type, in.operator_name, in.operator_k);
   if (in.compute_crossterms) p->g = make_crossterms(b, p->f);
   if (mode != 0 && p->f.label == "GT" && u[4] != 0) {
-    std::string why;
-    if (!read_tbc(d + "/" + in.fam_output_filename + ".tbc", b, in, p->f, why))
-      throw std::runtime_error("two_body_current_mode=" + std::to_string(mode) + ": " + why);
+    if (u[2] != 1) throw std::runtime_error("two_body_current_mode: only the full-FAM Yukawa field read from <name>.tbc (2nd digit = 1) is supported");
+    apply_two_body_current_gt(d + "/" + in.fam_output_filename + ".tbc", b, in, u[1], p->f);
   }
   p->setup_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   return p;

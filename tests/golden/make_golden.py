@@ -30,6 +30,10 @@ CASES = {
     "Gd162_GT_open_6sh": ("Gd162_GT_open/000000", None),
     "Gd162_1-_closed_6sh": ("Gd162 closed tests/1-/000000", None),
     "Gd162_0-_closed_6sh": ("Gd162 closed tests/0-/000000", None),
+    # full-FAM two-body currents via hfb_soln/*.tbc.  Only the GT operators: the forbidden-operator results of
+    # this 2023 tree were made with an older source whose mode digit 4 = 1 also corrected RS*; the shipped
+    # binary/source (pnfam_extfield.f90:430-438: use_2bc(4) >= 2) does not, and the live binary agrees with us.
+    "S40_All_GT2bc": ("S40_All_GT2bc/000000", ["GT-K0", "GT-K1"]),
 }
 
 
@@ -43,6 +47,9 @@ def main():
         os.makedirs(dst, exist_ok=True)
         for f in ("hfbtho_NAMELIST.dat", "hfbtho_output.hel"):
             shutil.copy(os.path.join(src, "hfb_soln", f), dst)
+        for f in os.listdir(os.path.join(src, "hfb_soln")):
+            if f.endswith(".tbc"):   # cached two-body-current external field (input data of the run)
+                shutil.copy(os.path.join(src, "hfb_soln", f), dst)
         points = {}
         meta = os.path.join(src, "fam_soln", "fam_meta")
         for tarname in sorted(os.listdir(meta)):

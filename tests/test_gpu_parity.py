@@ -36,6 +36,10 @@ CASES = [
     ("Gd162_GT_open_6sh", "GT-K1", 40),
     ("Gd162_1-_closed_6sh", "RS1-K1", 4),
     ("Gd162_0-_closed_6sh", "PS0-K0", 8),
+    ("S40_All_GT2bc", "GT-K1", 12),      # two-body currents via .tbc
+    ("Gd163_blocked_6sh", "GT-K0", 0),   # odd-A equal-filling: 8 amplitude vectors (X,Y,P,Q re/im)
+    ("Gd163_blocked_6sh", "GT-K1", 0),
+    ("Gd163_blocked_6sh", "RS1-K1", 0),
 ]
 
 

@@ -16,6 +16,8 @@ CASES = [
     ("S40_GT_All", "RS2-K2", 7),
     ("Gd162_GT_open_6sh", "GT-K1", 40),  # deformed, pairing active
     ("Gd162_0-_closed_6sh", "PS0-K0", 8),
+    ("S40_All_GT2bc", "GT-K0", 4),       # two-body currents: Yukawa part from GT-K0.tbc + contact + (-1-body)
+    ("Gd163_blocked_6sh", "GT-K0", 0),   # odd-A, blocked 5/2-[523] neutron: P,Q quadrants + statistical factors
 ]
 
 
