@@ -175,7 +175,7 @@ def main():
     import numpy as np
     import torch
     import torch.distributed as dist
-    from pynfam_b200 import gpu, host
+    from pynfam_b200 import gpu, host, shard
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the FAM iteration has no CPU fallback")
@@ -186,7 +186,8 @@ def main():
     # ---- this rank's shard of the contour (independent omega points: no data-path collective) --------
     npts = args.points * world
     omegas = circle_contour(npts)
-    mine = omegas[rank::world]
+    my_idx = shard.partition(omegas, world)[rank]
+    mine = omegas[my_idx]
     wd = tempfile.mkdtemp()
     stage(wd, mine[0], 300)
     t0 = time.time()
@@ -243,10 +244,9 @@ def main():
     if world > 1:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-        # gather the strengths (the only exchange the path has): [npts_rank][1+nx] complex
-        s_loc = torch.view_as_real(torch.from_numpy(np.ascontiguousarray(last["strength"])).cuda())
-        s_all = [torch.empty_like(s_loc) for _ in range(world)]
-        dist.all_gather(s_all, s_loc)
+    # the only exchange the path has: gather the strengths of all points (NCCL all_gather over NVLink)
+    all_strength = shard.gather_strengths(my_idx, last["strength"], npts, dist=dist if world > 1 else None, device="cuda")
+    assert np.isfinite(all_strength).all() and np.abs(all_strength[:, 0]).min() > 0
     vals, sums = vals.cpu().numpy(), sums.cpu().numpy()
     if rank == 0:
         value = sums[0] / vals[0]
