@@ -15,6 +15,9 @@
 //   h_ab = 2 sum_r sum_{t t'} phi^t_a(r) mf^{t t'}_{s_a s_b}(r) phi^t'_b(r)
 // builds G^t(r,b) = sum_t' mf^{t t'} phi^t'_b on the fly in shared memory and contracts over (r,t)
 // with DMMA, so the 20 Ng x N "hpsi" arrays of the reference never exist either.
+#include <algorithm>
+#include <vector>
+
 #include "device_common.cuh"
 #include "kernels.cuh"
 
@@ -49,14 +52,24 @@ __device__ __forceinline__ void load_phi_rows(double (*dst)[ROWS][RS], const dou
     for (int row = r0; row < n4; row += 16) dst[t][row][rr] = row < n ? src[(size_t)row * RT] : 0.0;
   }
 }
-template <int NT, int ROWS, int NTHREADS>
-__device__ __forceinline__ void load_phi_rows_async(double (*dst)[ROWS][RS], const double* __restrict__ phit, int dqp, int row0,
-                                                    int n, int n4) {
-  const int rr = (threadIdx.x & 7) * 2, r0 = threadIdx.x >> 3;   // 8 lanes x 16 bytes per 128-byte row
+// cooperative asynchronous copy of a spin-sorted run of rows (n_up spin-up rows followed by n_dn spin-down rows,
+// starting at global row row0) of 4 tables into dst[t][.][0..15]: up rows land at [0, n_up), down rows at
+// [pad4(n_up), ...); padding rows are zero-filled.  base(t) gives the table of slot t (nullptr: all padding).
+// 8 lanes x 16 bytes move one 128-byte row.
+template <int ROWS, int NTHREADS, class Base>
+__device__ __forceinline__ void load_phi_rows_async(double (*dst)[ROWS][RS], Base base, const double* safe, int row0, int n_up,
+                                                    int n_dn) {
+  const int rr = (threadIdx.x & 7) * 2, r0 = threadIdx.x >> 3;
+  const int up4 = (n_up + 3) & ~3, tot4 = up4 + ((n_dn + 3) & ~3);
 #pragma unroll
-  for (int t = 0; t < NT; t++) {
-    const double* __restrict__ src = phit + ((size_t)t * dqp + row0) * RT + rr;
-    for (int row = r0; row < n4; row += NTHREADS / 8) cp_async16(&dst[t][row][rr], row < n ? src + (size_t)row * RT : phit, row < n);
+  for (int t = 0; t < 4; t++) {
+    const double* __restrict__ tb = base(t);
+    const double* __restrict__ src = (tb ? tb : safe) + (size_t)row0 * RT + rr;
+    for (int sr = r0; sr < tot4; sr += NTHREADS / 8) {
+      const int gr = sr < up4 ? sr : n_up + (sr - up4);
+      const bool ok = tb != nullptr && (sr < up4 ? sr < n_up : gr < n_up + n_dn);
+      cp_async16(&dst[t][sr][rr], ok ? src + (size_t)gr * RT : safe, ok);
+    }
   }
 }
 
@@ -68,40 +81,64 @@ __device__ __forceinline__ void load_phi_rows_async(double (*dst)[ROWS][RS], con
 constexpr int DAC = DENS_AC, DBC = DENS_BC;
 constexpr int RHS = DAC + 4;  // padded row stride of the transposed rho chunk [n=(b,c)][k=a] (bank-conflict free)
 
-template <int NT>
+// Row slots of a density CTA: MODE 0 (rho): 4 derivative types of ONE 16-point tile;
+//                             MODE 1 (kappa): the wave function (type 0) of FOUR consecutive 16-point tiles.
 struct DensSmem {
-  double a[2][NT][DAC][RS];      // phi^t_a(r)   [stage][t][a][r]
+  double a[2][4][DAC][RS];       // phi_a(r)   [stage][slot][a][r]
   double rho[2][2 * DBC][RHS];   // rho chunk, transposed and interleaved: [stage][(b,c)][a]
-  double b[2][NT][DBC][RS];      // phi^t'_b(r)  [bbuf][t'][b][r]
+  double b[2][4][DBC][RS];       // phi_b(r)   [bbuf][slot][b][r]
 };
 
 void build_density_steps(int nb, const int* db, const int* isstart, const int* nsu, const int* r2c, const int* r2m,
                          DensStep* out, int* nout) {
+  auto pad4 = [](int x) { return (x + 3) & ~3; };
+  // split [0,d) with spin boundary nu into chunks of at most `cap` PADDED entries; a chunk holds (n_up, n_dn)
+  struct Chunk { int start, n_up, n_dn; };
+  auto chunks = [&](int d, int nu, int cap, std::vector<Chunk>& v) {
+    v.clear();
+    if (pad4(nu) + pad4(d - nu) <= cap) { v.push_back({0, nu, d - nu}); return; }
+    for (int c0 = 0; c0 < nu; c0 += cap) v.push_back({c0, std::min(cap, nu - c0), 0});
+    for (int c0 = nu; c0 < d; c0 += cap) v.push_back({c0, 0, std::min(cap, d - c0)});
+  };
   int n = 0, bbuf = 0;
+  std::vector<Chunk> ac, bc;
   for (int ix = 0; ix < nb; ix++) {
     const int iy = r2c[ix];
     if (iy < 0) continue;
-    const int di = db[ix], dj = db[iy], nui = nsu[ix], nuj = nsu[iy];
-    for (int sp = 0; sp < 2; sp++) {
-      const int b_lo = sp == 0 ? 0 : nuj, b_hi = sp == 0 ? nuj : dj;
-      for (int bc0 = b_lo; bc0 < b_hi; bc0 += DBC) {
-        bool newb = true;
-        for (int s = 0; s < 2; s++) {
-          const int a_lo = s == 0 ? 0 : nui, a_hi = s == 0 ? nui : di;
-          for (int ac0 = a_lo; ac0 < a_hi; ac0 += DAC) {
-            if (newb) bbuf ^= 1;
-            if (out) {
-              DensStep& d = out[n];
-              d.a_row0 = isstart[ix] + ac0; d.nac = (a_hi - ac0) < DAC ? (a_hi - ac0) : DAC;
-              d.b_row0 = isstart[iy] + bc0; d.nbc = (b_hi - bc0) < DBC ? (b_hi - bc0) : DBC;
-              d.rho_off = r2m[ix] + ac0 + bc0 * di; d.ld = di;
-              d.flags = (newb ? 1 : 0) | (ac0 == a_lo ? 2 : 0) | (ac0 + DAC >= a_hi ? 4 : 0);
-              d.ssp = (s * 2 + sp) | (bbuf << 4);
-            }
-            newb = false;
-            n++;
-          }
+    const int di = db[ix], dj = db[iy];
+    chunks(di, nsu[ix], DENS_AC, ac);
+    // a spin segment longer than one chunk accumulates C across steps: then the b-chunk must hold a single spin
+    const bool a_multi = nsu[ix] > DENS_AC || di - nsu[ix] > DENS_AC;
+    chunks(dj, nsu[iy], a_multi ? 0 : DENS_BC, bc);
+    if (a_multi) {
+      bc.clear();
+      for (int c0 = 0; c0 < nsu[iy]; c0 += DENS_BC) bc.push_back({c0, std::min(DENS_BC, nsu[iy] - c0), 0});
+      for (int c0 = nsu[iy]; c0 < dj; c0 += DENS_BC) bc.push_back({c0, 0, std::min(DENS_BC, dj - c0)});
+    }
+    for (const Chunk& b : bc) {
+      bool newb = true;
+      // a-chunks of one spin segment accumulate into the same C: they must be consecutive -> order: all chunks
+      // (merged chunks are complete on their own; split segments come up-chunks first, then down-chunks)
+      for (size_t ia = 0; ia < ac.size(); ia++) {
+        const Chunk& a = ac[ia];
+        if (newb) bbuf ^= 1;
+        const bool merged = a.n_up > 0 && a.n_dn > 0;
+        bool first = true, last = true;
+        if (!merged) {
+          const bool up = a.n_up > 0;
+          first = ia == 0 || (up ? ac[ia - 1].n_up == 0 : ac[ia - 1].n_dn == 0) || (ac[ia - 1].n_up > 0 && ac[ia - 1].n_dn > 0);
+          last = ia + 1 == ac.size() || (up ? ac[ia + 1].n_up == 0 : ac[ia + 1].n_dn == 0);
         }
+        if (out) {
+          DensStep& d = out[n];
+          d.a_row0 = isstart[ix] + a.start; d.na_up = a.n_up; d.na_dn = a.n_dn;
+          d.b_row0 = isstart[iy] + b.start; d.nb_up = b.n_up; d.nb_dn = b.n_dn;
+          d.rho_off = r2m[ix] + a.start + b.start * di; d.ld = di;
+          d.flags = (newb ? 1 : 0) | (first ? 2 : 0) | (last ? 4 : 0) | (bbuf << 3);
+          d.pad = 0;
+        }
+        newb = false;
+        n++;
       }
     }
   }
@@ -120,10 +157,13 @@ __device__ __forceinline__ void dens_mma(double (&C)[NTW][2], const double* __re
 }
 
 constexpr int DTHREADS = 512;   // 16 warps: (type t) x (r-half) x (column group)
-template <int NT>
-__global__ void __launch_bounds__(DTHREADS, 1) density_kernel(HamArgs g, int is_kappa) {
+template <int MODE>
+__global__ void __launch_bounds__(DTHREADS, 1) density_kernel(HamArgs g) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  DensSmem<NT>& sm = *reinterpret_cast<DensSmem<NT>*>(smem_raw);
+  DensSmem& sm = *reinterpret_cast<DensSmem*>(smem_raw);
+  constexpr int NT = 4;                       // row slots
+  constexpr int NTE = MODE == 0 ? 4 : 1;      // phi_b types contracted in the epilogue
+  constexpr int is_kappa = MODE;
   constexpr int NWARP = DTHREADS / 32;
   constexpr int CG = NWARP / (2 * NT);        // column groups: warps sharing a (type, r-half) split the 8 n-tiles
   constexpr int NTW = 8 / CG;                 // n-tiles per warp per chunk
@@ -139,31 +179,40 @@ __global__ void __launch_bounds__(DTHREADS, 1) density_kernel(HamArgs g, int is_
   const int quad = is_kappa ? g.kap_quad[q] : g.rho_quad[q];
   const double* __restrict__ rre = g.rsp + ((size_t)p * 2 + 0) * 4 * g.nxy + (size_t)quad * g.nxy;
   const double* __restrict__ rim = g.rsp + ((size_t)p * 2 + 1) * 4 * g.nxy + (size_t)quad * g.nxy;
-  const double* __restrict__ phit = B.phi + (size_t)tile * NTYPE * B.dqp * RT;
-  double acc[2][2][NT][2];
+  // table of row slot t for this CTA
+  auto slot_base = [&](int t) -> const double* {
+    if (MODE == 0) return B.phi + ((size_t)tile * NTYPE + t) * B.dqp * RT;
+    const int tl = tile * 4 + t;
+    return tl < B.ntiles ? B.phi + (size_t)tl * NTYPE * B.dqp * RT : nullptr;
+  };
+  double acc[2][2][NTE][2];
 #pragma unroll
   for (int s = 0; s < 2; s++)
 #pragma unroll
     for (int sp = 0; sp < 2; sp++)
 #pragma unroll
-      for (int t = 0; t < NT; t++) acc[s][sp][t][0] = acc[s][sp][t][1] = 0.0;
+      for (int t = 0; t < NTE; t++) acc[s][sp][t][0] = acc[s][sp][t][1] = 0.0;
   const int row_a = rh * 8 + lr;
 
   auto prefetch = [&](int k) {
     const DensStep d = steps[k];
     const int stage = k & 1;
-    const int nac4 = (d.nac + 3) & ~3, nbc4 = (d.nbc + 3) & ~3;
-    load_phi_rows_async<NT, DAC, DTHREADS>(sm.a[stage], phit, B.dqp, d.a_row0, d.nac, nac4);
-    if (d.flags & 1) load_phi_rows_async<NT, DBC, DTHREADS>(sm.b[(d.ssp >> 4) & 1], phit, B.dqp, d.b_row0, d.nbc, nbc4);
-    // rho chunk: threads sweep a (coalesced) for 4 columns at a time
-    const int al = threadIdx.x & 63;
-    if (al < nac4) {
-      const double* __restrict__ pr = rre + d.rho_off + al;
-      const double* __restrict__ pi = rim + d.rho_off + al;
-      for (int bl = threadIdx.x >> 6; bl < nbc4; bl += DTHREADS / 64) {
-        const bool ok = al < d.nac && bl < d.nbc;
-        cp_async8(&sm.rho[stage][2 * bl][al], ok ? pr + (size_t)bl * d.ld : rre, ok);
-        cp_async8(&sm.rho[stage][2 * bl + 1][al], ok ? pi + (size_t)bl * d.ld : rim, ok);
+    load_phi_rows_async<DAC, DTHREADS>(sm.a[stage], slot_base, B.phi, d.a_row0, d.na_up, d.na_dn);
+    if (d.flags & 1) load_phi_rows_async<DBC, DTHREADS>(sm.b[(d.flags >> 3) & 1], slot_base, B.phi, d.b_row0, d.nb_up, d.nb_dn);
+    // rho chunk: threads sweep a (coalesced) for 8 columns at a time; smem index = padded (spin-segmented) index
+    const int aup4 = (d.na_up + 3) & ~3, atot4 = aup4 + ((d.na_dn + 3) & ~3);
+    const int bup4 = (d.nb_up + 3) & ~3, btot4 = bup4 + ((d.nb_dn + 3) & ~3);
+    const int sa_ = threadIdx.x & 63;
+    if (sa_ < atot4) {
+      const int ga = sa_ < aup4 ? sa_ : d.na_up + (sa_ - aup4);
+      const bool aok = sa_ < aup4 ? sa_ < d.na_up : ga < d.na_up + d.na_dn;
+      const double* __restrict__ pr = rre + d.rho_off + ga;
+      const double* __restrict__ pi = rim + d.rho_off + ga;
+      for (int sb_ = threadIdx.x >> 6; sb_ < btot4; sb_ += DTHREADS / 64) {
+        const int gb = sb_ < bup4 ? sb_ : d.nb_up + (sb_ - bup4);
+        const bool ok = aok && (sb_ < bup4 ? sb_ < d.nb_up : gb < d.nb_up + d.nb_dn);
+        cp_async8(&sm.rho[stage][2 * sb_][sa_], ok ? pr + (size_t)gb * d.ld : rre, ok);
+        cp_async8(&sm.rho[stage][2 * sb_ + 1][sa_], ok ? pi + (size_t)gb * d.ld : rim, ok);
       }
     }
     cp_async_commit();
@@ -177,99 +226,90 @@ __global__ void __launch_bounds__(DTHREADS, 1) density_kernel(HamArgs g, int is_
     if (k + 1 < nsteps) { prefetch(k + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
     __syncthreads();
     const DensStep d = steps[k];
-    const int stage = k & 1, bbuf = (d.ssp >> 4) & 1, ssp = d.ssp & 3;
-    const int nac4 = (d.nac + 3) & ~3, nbc4 = (d.nbc + 3) & ~3;
-    if (d.flags & 2) {
+    const int stage = k & 1, bbuf = (d.flags >> 3) & 1;
+    const int aup4 = (d.na_up + 3) & ~3, adn4 = (d.na_dn + 3) & ~3;
+    const int bup4 = (d.nb_up + 3) & ~3, bdn4 = (d.nb_dn + 3) & ~3;
 #pragma unroll
-      for (int j = 0; j < NTW; j++) C[j][0] = C[j][1] = 0.0;
-    }
-    const int ksteps = nac4 >> 2;
-    {
-      // n-tiles owned by this warp: nt = cg + CG*j < nbc4/4  -> dispatch on the count so that the DMMA sequence
-      // is unpredicated straight-line code
-      const int ntn = ((nbc4 >> 2) - cg + CG - 1) / CG;
-      const double* __restrict__ pa = &sm.a[stage][tw][lc][row_a];
-      const double* __restrict__ pb = &sm.rho[stage][cg * 8 + lr][lc];
-      switch (ntn) {
-        case 8: dens_mma<8, CG>(C, pa, pb, ksteps); break;
-        case 7: dens_mma<7, CG>(C, pa, pb, ksteps); break;
-        case 6: dens_mma<6, CG>(C, pa, pb, ksteps); break;
-        case 5: dens_mma<5, CG>(C, pa, pb, ksteps); break;
-        case 4: dens_mma<4, CG>(C, pa, pb, ksteps); break;
-        case 3: dens_mma<3, CG>(C, pa, pb, ksteps); break;
-        case 2: dens_mma<2, CG>(C, pa, pb, ksteps); break;
-        case 1: dens_mma<1, CG>(C, pa, pb, ksteps); break;
-        default: break;
-      }
-    }
-    if (d.flags & 4) {
-      // epilogue: contract the product tile with phi^t'_b(r) for every t' into the (s, s') accumulators
-      double e[NT][2];
+    for (int s = 0; s < 2; s++) {
+      const int k0 = s == 0 ? 0 : aup4, ksteps = (s == 0 ? aup4 : adn4) >> 2;
+      if (ksteps == 0) continue;
 #pragma unroll
-      for (int t2 = 0; t2 < NT; t2++) e[t2][0] = e[t2][1] = 0.0;
+      for (int sp = 0; sp < 2; sp++) {
+        const int nt0 = (sp == 0 ? 0 : bup4) >> 2, ntiles_n = (sp == 0 ? bup4 : bdn4) >> 2;
+        if (ntiles_n == 0) continue;
+        if (d.flags & 2) {
 #pragma unroll
-      for (int j = 0; j < NTW; j++) {
-        const int nt = cg + CG * j;
-        if (nt * 4 < nbc4) {
-          const int bl = nt * 4 + lc;
+          for (int j = 0; j < NTW; j++) C[j][0] = C[j][1] = 0.0;
+        }
+        // n-tiles owned by this warp: local index cg + CG*j < ntiles_n -> dispatch on the count so that the DMMA
+        // sequence is unpredicated straight-line code
+        const int ntn = (ntiles_n - cg + CG - 1) / CG;
+        const double* __restrict__ pa = &sm.a[stage][tw][k0 + lc][row_a];
+        const double* __restrict__ pb = &sm.rho[stage][(nt0 + cg) * 8 + lr][k0 + lc];
+        switch (ntn) {
+          case 8: dens_mma<8, CG>(C, pa, pb, ksteps); break;
+          case 7: dens_mma<7, CG>(C, pa, pb, ksteps); break;
+          case 6: dens_mma<6, CG>(C, pa, pb, ksteps); break;
+          case 5: dens_mma<5, CG>(C, pa, pb, ksteps); break;
+          case 4: dens_mma<4, CG>(C, pa, pb, ksteps); break;
+          case 3: dens_mma<3, CG>(C, pa, pb, ksteps); break;
+          case 2: dens_mma<2, CG>(C, pa, pb, ksteps); break;
+          case 1: dens_mma<1, CG>(C, pa, pb, ksteps); break;
+          default: break;
+        }
+        if (d.flags & 4) {
+          // epilogue: contract the product tile with phi_b(r) into the (s, s') accumulators (static indices)
 #pragma unroll
-          for (int t2 = 0; t2 < NT; t2++) {
-            const double ph = sm.b[bbuf][t2][bl][row_a];
-            e[t2][0] += C[j][0] * ph;
-            e[t2][1] += C[j][1] * ph;
+          for (int j = 0; j < NTW; j++) {
+            if (j < ntn) {
+              const int bl = (nt0 + cg + CG * j) * 4 + lc;
+#pragma unroll
+              for (int t2 = 0; t2 < NTE; t2++) {
+                const double ph = sm.b[bbuf][MODE == 0 ? t2 : tw][bl][row_a];
+                acc[s][sp][t2][0] += C[j][0] * ph;
+                acc[s][sp][t2][1] += C[j][1] * ph;
+              }
+            }
           }
         }
-      }
-      switch (ssp) {   // keeps the accumulator indices static (registers)
-        case 0:
-#pragma unroll
-          for (int t2 = 0; t2 < NT; t2++) { acc[0][0][t2][0] += e[t2][0]; acc[0][0][t2][1] += e[t2][1]; }
-          break;
-        case 1:
-#pragma unroll
-          for (int t2 = 0; t2 < NT; t2++) { acc[0][1][t2][0] += e[t2][0]; acc[0][1][t2][1] += e[t2][1]; }
-          break;
-        case 2:
-#pragma unroll
-          for (int t2 = 0; t2 < NT; t2++) { acc[1][0][t2][0] += e[t2][0]; acc[1][0][t2][1] += e[t2][1]; }
-          break;
-        default:
-#pragma unroll
-          for (int t2 = 0; t2 < NT; t2++) { acc[1][1][t2][0] += e[t2][0]; acc[1][1][t2][1] += e[t2][1]; }
-          break;
       }
     }
     __syncthreads();   // stage k&1 is free for the prefetch of step k+2
   }
   // reduce over the 4 lanes of a row, then over column-group warps (fixed order: deterministic)
-  double* red = reinterpret_cast<double*>(smem_raw);  // [NWARP][8 rows][2*2*NT*2]
-  constexpr int NACC = 2 * 2 * NT * 2;
+  double* red = reinterpret_cast<double*>(smem_raw);  // [NWARP][8 rows][2*2*NTE*2]
+  constexpr int NACC = 2 * 2 * NTE * 2;
 #pragma unroll
   for (int s = 0; s < 2; s++)
 #pragma unroll
     for (int sp = 0; sp < 2; sp++)
 #pragma unroll
-      for (int t2 = 0; t2 < NT; t2++)
+      for (int t2 = 0; t2 < NTE; t2++)
 #pragma unroll
         for (int c = 0; c < 2; c++) {
           double v = acc[s][sp][t2][c];
           v += __shfl_xor_sync(0xffffffffu, v, 1);
           v += __shfl_xor_sync(0xffffffffu, v, 2);
-          if (lc == 0) red[((size_t)warp * 8 + lr) * NACC + ((s * 2 + sp) * NT + t2) * 2 + c] = v;
+          if (lc == 0) red[((size_t)warp * 8 + lr) * NACC + ((s * 2 + sp) * NTE + t2) * 2 + c] = v;
         }
   __syncthreads();
-  const int ndd = NT * NT * 8;
+  const int ndd = NTE * NTE * 8;
   double* __restrict__ out = (is_kappa ? g.dd_kap : g.dd_rho) + ((size_t)za * 2 + q) * ndd * B.nghl;
   for (int idx = threadIdx.x; idx < NT * RT * NACC; idx += DTHREADS) {
     const int e = idx % NACC, rr = (idx / NACC) % RT, t = idx / (NACC * RT);
-    const int c = e & 1, t2 = (e >> 1) % NT, ssp = e / (2 * NT);   // ssp = s*2+sp
+    const int c = e & 1, t2 = (e >> 1) % NTE, ssp = e / (2 * NTE);   // ssp = s*2+sp
     double v = 0.0;
     for (int kk = 0; kk < CG; kk++) {
       const int w = t + NT * (rr >> 3) + 2 * NT * kk;   // warp = tw + NT*rh + 2*NT*cg
       v += red[((size_t)w * 8 + (rr & 7)) * NACC + e];
     }
-    const int r = tile * RT + rr;
-    if (r < B.nghl) out[(size_t)(((t * NT + t2) * 4 + ssp) * 2 + c) * B.nghl + r] = v;
+    if (MODE == 0) {
+      const int r = tile * RT + rr;
+      if (r < B.nghl) out[(size_t)(((t * 4 + t2) * 4 + ssp) * 2 + c) * B.nghl + r] = v;
+    } else {
+      const int r = (tile * 4 + t) * RT + rr;
+      if (r < B.nghl) out[(size_t)(ssp * 2 + c) * B.nghl + r] = v;
+    }
   }
 }
 
@@ -277,13 +317,12 @@ void launch_density(const HamArgs& a, cudaStream_t stream) {
   if (a.nactive <= 0) return;
   static bool attr = false;
   if (!attr) {
-    PNFAM_CUDA_CHECK(cudaFuncSetAttribute(density_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DensSmem<4>)));
-    PNFAM_CUDA_CHECK(cudaFuncSetAttribute(density_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DensSmem<1>)));
+    PNFAM_CUDA_CHECK(cudaFuncSetAttribute(density_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DensSmem)));
+    PNFAM_CUDA_CHECK(cudaFuncSetAttribute(density_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DensSmem)));
     attr = true;
   }
-  dim3 grid(a.basis.ntiles, 2, a.nactive);
-  density_kernel<4><<<grid, DTHREADS, sizeof(DensSmem<4>), stream>>>(a, 0);
-  density_kernel<1><<<grid, DTHREADS, sizeof(DensSmem<1>), stream>>>(a, 1);
+  density_kernel<0><<<dim3(a.basis.ntiles, 2, a.nactive), DTHREADS, sizeof(DensSmem), stream>>>(a);
+  density_kernel<1><<<dim3((a.basis.ntiles + 3) / 4, 2, a.nactive), DTHREADS, sizeof(DensSmem), stream>>>(a);
 }
 
 // ================================================================================================

@@ -36,12 +36,15 @@ constexpr int NMF = 5 * 5 * 2 * 2 * 2;       // field tensor mf(ta,tb,sa,sb) com
 constexpr int NPF = 2 * 2 * 2;               // pairing field (sa,sb) complex
 
 // One pipeline step of the density kernel: an (a-chunk x b-chunk) piece of one block of rho / kappa.
+// Rows / columns of a block are spin-sorted (up first).  A chunk may straddle the spin boundary when the padded
+// segments fit (small blocks): the step then runs up to four (s, s') sub-passes on one staged operand set.
 struct DensStep {
-  int a_row0, nac;      // first basis state (global index) and count of the contraction chunk (one spin segment)
-  int b_row0, nbc;      // first column state (global index) and count
-  int rho_off, ld;      // element offset of (a chunk start, b chunk start) inside the block matrix, leading dim
-  int flags;            // bit0: new b-chunk (load phi_b into buffer bbuf); bit1: first a-chunk (zero C); bit2: last (epilogue)
-  int ssp;              // s*2 + sp  (spin of a-segment, spin of b-segment);  bit 4: bbuf
+  int a_row0, na_up, na_dn;   // first basis state (global index) of the contraction chunk; rows per spin
+  int b_row0, nb_up, nb_dn;   // first column state (global index); columns per spin
+  int rho_off, ld;            // element offset of (a chunk start, b chunk start) inside the block matrix, leading dim
+  int flags;                  // bit0: new b-chunk (stage phi_b into buffer bbuf); bit1: first a-chunk (zero C);
+                              // bit2: last a-chunk (epilogue); bit3: bbuf
+  int pad;
 };
 constexpr int DENS_AC = 48;   // contraction chunk
 constexpr int DENS_BC = 32;   // column chunk

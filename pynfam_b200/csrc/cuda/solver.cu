@@ -101,10 +101,17 @@ extern "C" int pnfam_b200_ctx_create(const pnfam_b200_model* m, int device, pnfa
     {
       const double* tab[NTYPE] = {m->wf, m->wfdr, m->wfdp, m->wfdz, m->wfd2_all};
       std::vector<double> h((size_t)c->ntiles * NTYPE * c->dqp * RT, 0.0);
-      for (int t = 0; t < NTYPE; t++)
-        for (int s = 0; s < c->dqp; s++)
-          for (int r = 0; r < c->nghl; r++)
-            h[(((size_t)(r / RT) * NTYPE + t) * c->dqp + s) * RT + (r % RT)] = tab[t][(size_t)s * c->nghl + r];
+      const int dqp = c->dqp, nghl = c->nghl, ntiles = c->ntiles;
+#pragma omp parallel for collapse(2) schedule(static)
+      for (int tile = 0; tile < ntiles; tile++)
+        for (int t = 0; t < NTYPE; t++) {
+          double* dst = &h[((size_t)tile * NTYPE + t) * dqp * RT];
+          const int r0 = tile * RT, nr = std::min(RT, nghl - r0);
+          for (int s = 0; s < dqp; s++) {
+            const double* src = tab[t] + (size_t)s * nghl + r0;
+            for (int r = 0; r < nr; r++) dst[(size_t)s * RT + r] = src[r];
+          }
+        }
       c->d_phi.upload(h);
     }
     auto up = [&](DBuf<double>& d, const double* p, size_t n) { d.upload(std::vector<double>(p, p + n)); };
