@@ -608,8 +608,11 @@ void launch_fields(const HamArgs& a, cudaStream_t stream) {
 // projection: h_ab = 2 sum_{r,t} phi^t_a(r) G^t_{s_a s_b}(r,b),  G^t = sum_t' mf^{t t'} phi^t'_b
 // ================================================================================================
 constexpr int GS = 68;    // padded row stride of G (64 interleaved (b,c) columns): conflict-free B-fragment loads
-constexpr int ACP = 48;   // rows a per output tile = 6 DMMA m-tiles = 6 consumer warps
-constexpr int PCONS = 6, PPROD = 10;                 // warp-specialised: consumers run DMMA, producers stage operands
+constexpr int ACP = 48;   // rows a per output tile = up to 6 DMMA m-tiles
+// warp-specialised: 8 consumer warps run DMMA (one n-tile each, all m-tiles: two consumers per SM sub-partition,
+// equal work -- the FP64 tensor pipe is one DMMA per 16 clk per sub-partition, measured with scripts/dmma_probe.cu),
+// 8 producer warps stage operands and build G
+constexpr int PCONS = 8, PPROD = 8;
 constexpr int PTHREADS = (PCONS + PPROD) * 32;
 
 template <int NT>
@@ -619,16 +622,16 @@ struct ProjSmem {
   double b[2][NT][BC][RS];     // phi^t'_b(r) chunk, staged one r-tile ahead of the G build
 };
 
-// DMMA sequence of one r-tile for a consumer warp (8 rows a x NTN n-tiles), straight-line code
-template <int NT, int NTN>
-__device__ __forceinline__ void proj_mma(double (&C)[8][2], const double* __restrict__ pa, const double* __restrict__ pg) {
+// DMMA sequence of one r-tile for a consumer warp: its n-tile (8 columns) x MT m-tiles of 8 rows, straight-line code
+template <int NT, int MT>
+__device__ __forceinline__ void proj_mma(double (&C)[6][2], const double* __restrict__ pa, const double* __restrict__ pg) {
 #pragma unroll
   for (int t = 0; t < NT; t++)
 #pragma unroll
     for (int ks = 0; ks < RT / 4; ks++) {
-      const double af = pa[(size_t)t * ACP * RS + ks * 4];
+      const double bf = pg[((size_t)t * RT + ks * 4) * GS];
 #pragma unroll
-      for (int j = 0; j < NTN; j++) dmma884(C[j][0], C[j][1], af, pg[((size_t)t * RT + ks * 4) * GS + j * 8]);
+      for (int i = 0; i < MT; i++) dmma884(C[i][0], C[i][1], pa[((size_t)t * ACP + i * 8) * RS + ks * 4], bf);
     }
 }
 
@@ -659,17 +662,18 @@ __global__ void __launch_bounds__(PTHREADS, 1) projection_kernel(HamArgs g, cons
   const bool producer = warp >= PCONS;
   // producer role: grid point rr, output type tg, column group bg (columns bg, bg+NBG, ...)
   const int ptid = threadIdx.x - PCONS * 32;             // 0..319 for producers
-  constexpr int NU = PPROD * 2;                          // 20 (grid point, group) slots of 16 lanes
-  constexpr int NBG = (NT == 5) ? NU / 5 : NU;
+  constexpr int NU = PPROD * 2;                          // 16 (grid point, group) slots of 16 lanes
   const int rr = ptid & (RT - 1), u = ptid >> 4;         // u = 0..NU-1
   const int tg = (NT == 5) ? (u % 5) : 0, bg = (NT == 5) ? (u / 5) : u;
-  const bool builder = producer && bg < NBG;
+  // column groups per output type: 16 slots over 5 types -> type 0 has 4 groups, types 1..4 have 3
+  const int NBG = (NT == 5) ? (tg == 0 ? 4 : 3) : NU;
+  const bool builder = producer;
 
   // rows beyond n are never copied: padded rows / columns of the projection only feed outputs that are discarded
   auto copy_rows = [&](double (*dst)[RS], const double* __restrict__ phit, int t, int row0, int n, int npad) {
     const int c2 = (ptid & 7) * 2, rw = ptid >> 3;       // 8 lanes x 16 bytes per 128-byte row, 40 rows per pass
     const double* __restrict__ src = phit + ((size_t)t * B.dqp + row0) * RT + c2;
-    for (int row = rw; row < n; row += PPROD * 4) cp_async16(&dst[row][c2], src + (size_t)row * RT, true);
+    for (int row = rw; row < n; row += PPROD * 4) cp_async16(&dst[row][c2], src + (size_t)row * RT, true);   // PPROD*4 rows per pass
     (void)npad;
   };
   auto stage_a = [&](int kt, int stage) {
@@ -720,10 +724,12 @@ __global__ void __launch_bounds__(PTHREADS, 1) projection_kernel(HamArgs g, cons
     }
   };
 
-  double C[8][2];
+  double C[6][2];
 #pragma unroll
-  for (int j = 0; j < 8; j++) C[j][0] = C[j][1] = 0.0;
+  for (int i = 0; i < 6; i++) C[i][0] = C[i][1] = 0.0;
   const int nt_tiles = kt1 - kt0;
+  const int mt = nac8 >> 3;                              // m-tiles of this output tile (1..6)
+  const bool cons_active = !producer && warp * 4 < nbc4; // consumer warp w owns n-tile w
   // prologue: a(0), b(0), b(1) -> smem ; build g(0)
   if (producer && nt_tiles > 0) {
     stage_a(kt0, 0); stage_b(kt0, 0);
@@ -750,12 +756,10 @@ __global__ void __launch_bounds__(PTHREADS, 1) projection_kernel(HamArgs g, cons
         if (i + 2 < nt_tiles) load_mf(kt0 + i + 2);
         cp_async_wait<0>();
       }
-    } else if (warp * 8 < nac8) {
-      const double* __restrict__ pa = &sm.a[stage][0][warp * 8 + lr][lc];
-      const double* __restrict__ pg = &sm.g[stage][0][lc][lr];
-      switch (nbc4 >> 2) {
-        case 8: proj_mma<NT, 8>(C, pa, pg); break;
-        case 7: proj_mma<NT, 7>(C, pa, pg); break;
+    } else if (cons_active) {
+      const double* __restrict__ pa = &sm.a[stage][0][lr][lc];
+      const double* __restrict__ pg = &sm.g[stage][0][lc][warp * 8 + lr];
+      switch (mt) {
         case 6: proj_mma<NT, 6>(C, pa, pg); break;
         case 5: proj_mma<NT, 5>(C, pa, pg); break;
         case 4: proj_mma<NT, 4>(C, pa, pg); break;
@@ -767,19 +771,19 @@ __global__ void __launch_bounds__(PTHREADS, 1) projection_kernel(HamArgs g, cons
     __syncthreads();
   }
   // write the partial (factor 2 of the reference's dgemm alpha applied in the reduction)
-  if (!producer) {
+  if (cons_active) {
     const size_t pstride = 2 * g.nxy;   // re | im
     double* __restrict__ part = g.hpart + (((size_t)za * 2 + q) * 2 + is_delta) * (size_t)ksplit * pstride + (size_t)ksp * pstride;
     const size_t off = st.r2m[ix];
-    const int al = warp * 8 + lr;
-    if (al < nac) {
+    const int bl = warp * 4 + lc;
+    if (bl < nbc) {
 #pragma unroll
-      for (int j = 0; j < 8; j++) {
-        const int bl = j * 4 + lc;
-        if (bl < nbc) {
+      for (int i = 0; i < 6; i++) {
+        const int al = i * 8 + lr;
+        if (al < nac) {
           const size_t e = off + (size_t)(a0 + al) + (size_t)(b0 + bl) * di;
-          part[e] = C[j][0];
-          part[g.nxy + e] = C[j][1];
+          part[e] = C[i][0];
+          part[g.nxy + e] = C[i][1];
         }
       }
     }
