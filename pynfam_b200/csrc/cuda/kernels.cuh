@@ -34,6 +34,14 @@ constexpr int NDD_RHO = 4 * 4 * 2 * 2 * 2;  // doubles per grid point (complex)
 constexpr int NDD_KAP = 2 * 2 * 2;
 constexpr int NMF = 5 * 5 * 2 * 2 * 2;       // field tensor mf(ta,tb,sa,sb) complex, doubles per grid point
 constexpr int NPF = 2 * 2 * 2;               // pairing field (sa,sb) complex
+// Both field tensors are stored tile-major so that the projection fetches what one CTA needs for one r-tile with a
+// single linear bulk copy:
+//   mf[kt][sa][ta][tb][sb][rr][c]   (1600 doubles per (r-tile kt, row spin sa))
+//   pf[sa][kt][sb][rr][c]           (64 doubles per (sa, kt); kt padded to a multiple of 4: one copy per 4 r-tiles)
+constexpr int MF_TILE = 5 * 5 * 2 * RT * 2;
+constexpr int PF_TILE = 2 * RT * 2;
+__host__ __device__ inline size_t mf_elems(int ntiles) { return (size_t)ntiles * 2 * MF_TILE; }
+__host__ __device__ inline size_t pf_elems(int ntiles) { return (size_t)2 * ((ntiles + 3) & ~3) * PF_TILE; }
 
 // One pipeline step of the density kernel: an (a-chunk x b-chunk) piece of one block of rho / kappa.
 // Rows / columns of a block are spin-sorted (up first).  A chunk may straddle the spin boundary when the padded
@@ -61,8 +69,8 @@ struct HamArgs {
   size_t nxy;
   double* dd_rho;                 // [nactive][2 q][NDD_RHO][nghl]
   double* dd_kap;                 // [nactive][2 q][NDD_KAP][nghl]
-  double* mf;                     // [nactive][2 q][NMF][nghl]
-  double* pf;                     // [nactive][2 q][NPF][nghl]
+  double* mf;                     // [nactive][2 q][mf_elems]  tile-major, see above
+  double* pf;                     // [nactive][2 q][pf_elems]
   double* hpart;                  // split-K partials of the projection
   const int* active;
   int nactive;

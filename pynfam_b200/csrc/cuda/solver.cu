@@ -97,11 +97,14 @@ extern "C" int pnfam_b200_ctx_create(const pnfam_b200_model* m, int device, pnfa
     c->use_diag = m->qp_fp != nullptr && m->qp_fn != nullptr;
     if (c->use_diag) { c->qp_fp.assign(m->qp_fp, m->qp_fp + m->dqp); c->qp_fn.assign(m->qp_fn, m->qp_fn + m->dqp); }
     c->d_db.upload(c->db); c->d_isstart.upload(c->isstart); c->d_nsu.upload(c->nsu);
-    // tile-major wave-function tables: phi[tile][type][state][RT]
+    // tile-major wave-function tables: phi[tile][type][state][RT], zero-padded to a multiple of 4 tiles.
+    // Inside a 128-byte row the 16 grid points are ROTATED by 4*(state & 3) positions: a plain linear (bulk) copy
+    // of consecutive rows into shared memory is then bank-conflict free for the DMMA fragment loads (4 consecutive
+    // rows x 4 consecutive points hit 16 different 8-byte banks) without any padding.
     {
       const double* tab[NTYPE] = {m->wf, m->wfdr, m->wfdp, m->wfdz, m->wfd2_all};
-      std::vector<double> h((size_t)c->ntiles * NTYPE * c->dqp * RT, 0.0);
-      const int dqp = c->dqp, nghl = c->nghl, ntiles = c->ntiles;
+      const int dqp = c->dqp, nghl = c->nghl, ntiles = c->ntiles, ntiles4 = (c->ntiles + 3) & ~3;
+      std::vector<double> h((size_t)ntiles4 * NTYPE * dqp * RT, 0.0);
 #pragma omp parallel for collapse(2) schedule(static)
       for (int tile = 0; tile < ntiles; tile++)
         for (int t = 0; t < NTYPE; t++) {
@@ -109,7 +112,8 @@ extern "C" int pnfam_b200_ctx_create(const pnfam_b200_model* m, int device, pnfa
           const int r0 = tile * RT, nr = std::min(RT, nghl - r0);
           for (int s = 0; s < dqp; s++) {
             const double* src = tab[t] + (size_t)s * nghl + r0;
-            for (int r = 0; r < nr; r++) dst[(size_t)s * RT + r] = src[r];
+            const int rot = 4 * (s & 3);
+            for (int r = 0; r < nr; r++) dst[(size_t)s * RT + ((r + rot) & (RT - 1))] = src[r];
           }
         }
       c->d_phi.upload(h);
@@ -336,7 +340,9 @@ extern "C" int pnfam_b200_solve(pnfam_b200_ctx* c, const pnfam_b200_operator* op
     rsp.zero(); hsp.zero(); hqp.zero();
     scratch.alloc((size_t)P * 2 * std::max<size_t>(od->scratch_elems, 1));
     dd_rho.alloc((size_t)P * 2 * NDD_RHO * c->nghl); dd_kap.alloc((size_t)P * 2 * NDD_KAP * c->nghl);
-    mf.alloc((size_t)P * 2 * NMF * c->nghl); pf.alloc((size_t)P * 2 * NPF * c->nghl);
+    // field tensors are tile-major (kernels.cuh); the padding grid points are zeroed once and never written
+    mf.alloc((size_t)P * 2 * mf_elems(c->ntiles)); pf.alloc((size_t)P * 2 * pf_elems(c->ntiles));
+    mf.zero(); pf.zero();
     hpart.alloc((size_t)P * projection_partial_elems(od->proj, nxy));
     d_active.alloc(P);
     {
@@ -543,7 +549,8 @@ extern "C" int pnfam_b200_calc_hamiltonian(pnfam_b200_ctx* c, const pnfam_b200_b
       pp.ksplit = std::min(std::min(c->ntiles, 32), std::max(1, (2 * 148 + per - 1) / per));
     }
     dd_rho.alloc((size_t)2 * NDD_RHO * c->nghl); dd_kap.alloc((size_t)2 * NDD_KAP * c->nghl);
-    mf.alloc((size_t)2 * NMF * c->nghl); pf.alloc((size_t)2 * NPF * c->nghl);
+    mf.alloc((size_t)2 * mf_elems(c->ntiles)); pf.alloc((size_t)2 * pf_elems(c->ntiles));
+    mf.zero(); pf.zero();
     hpart.alloc(projection_partial_elems(pp, nxy));
     std::vector<int> act = {0};
     d_active.upload(act);
