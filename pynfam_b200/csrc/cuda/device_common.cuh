@@ -22,6 +22,13 @@ constexpr int RT = 16;        // grid points per r-tile (2 DMMA m-tiles)
 constexpr int RS = 20;        // padded r-stride of a wave-function row in shared memory (bank-conflict free)
 constexpr int NTYPE = 5;      // wf, d/dr, (Lambda/r), d/dz, laplacian_all
 
+// The wave-function tables are stored tile-major, [r-tile][type][state][RT], and inside each 128-byte row the 16 grid
+// points are rotated by phi_rot(state) positions: 0, 8, 4, 12 for state & 3 = 0, 1, 2, 3.  Rows copied linearly
+// (cp.async.bulk) into shared memory are then bank-conflict free without padding for both access patterns of the
+// kernels: DMMA fragments (4 consecutive states x 4 consecutive points -> 16 different 8-byte banks) and the G build
+// (8 consecutive points of two adjacent states).
+__host__ __device__ __forceinline__ int phi_rot(int state) { return ((state & 1) << 3) | ((state & 2) << 1); }
+
 // FP64 tensor-core MMA: D(8x8) += A(8x4, row) * B(4x8, col).
 // Fragment layout (PTX ISA, mma.m8n8k4 .f64): lane l holds A[l/4][l%4], B[l%4][l/4],
 // C[l/4][2*(l%4)] and C[l/4][2*(l%4)+1].

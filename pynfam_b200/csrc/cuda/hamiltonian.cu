@@ -16,6 +16,7 @@
 // builds G^t(r,b) = sum_t' mf^{t t'} phi^t'_b on the fly in shared memory and contracts over (r,t)
 // with DMMA, so the 20 Ng x N "hpsi" arrays of the reference never exist either.
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "device_common.cuh"
@@ -25,61 +26,57 @@ namespace pnfam {
 
 constexpr int BC = 32;    // columns b per chunk of the projection (8 DMMA n-tiles of 4 b x {re,im})
 
-// ---- asynchronous global -> shared copies (LDGSTS); src-size 0 zero-fills -------------------------------
-__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gmem_src, bool valid) {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-  const int sz = valid ? 8 : 0;
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem_src), "r"(sz));
+// ---- mbarrier + bulk-copy primitives (PTX) --------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* b, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(b)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gmem_src, bool valid) {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-  const int sz = valid ? 16 : 0;
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem_src), "r"(sz));
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {
+  const unsigned a = smem_u32(b);
+  unsigned ok;
+  do {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* b) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(b)) : "memory");
+}
 
-// cooperative asynchronous copy of a spin-sorted run of rows (n_up spin-up rows followed by n_dn spin-down rows,
-// starting at global row row0) of 4 tables into dst[t][.][0..15]: up rows land at [0, n_up), down rows at
-// [pad4(n_up), ...); padding rows are zero-filled.  base(t) gives the table of slot t (nullptr: all padding).
-// 8 lanes x 16 bytes move one 128-byte row.  The global rows are stored rotated by 4*(state & 3) points
-// (solver.cu); the copy undoes the rotation, the padded shared-memory rows are in natural order.
-template <int ROWS, int NTHREADS, class Base>
-__device__ __forceinline__ void load_phi_rows_async(double (*dst)[ROWS][RS], Base base, const double* safe, int row0, int n_up,
-                                                    int n_dn) {
-  const int rr = (threadIdx.x & 7) * 2, r0 = threadIdx.x >> 3;
-  const int up4 = (n_up + 3) & ~3, tot4 = up4 + ((n_dn + 3) & ~3);
-#pragma unroll
-  for (int t = 0; t < 4; t++) {
-    const double* __restrict__ tb = base(t);
-    const double* __restrict__ src = (tb ? tb : safe) + (size_t)row0 * RT;
-    for (int sr = r0; sr < tot4; sr += NTHREADS / 8) {
-      const int gr = sr < up4 ? sr : n_up + (sr - up4);
-      const bool ok = tb != nullptr && (sr < up4 ? sr < n_up : gr < n_up + n_dn);
-      cp_async16(&dst[t][sr][rr], ok ? src + (size_t)gr * RT + ((rr + 4 * ((row0 + gr) & 3)) & (RT - 1)) : safe, ok);
-    }
-  }
-}
 
 // ================================================================================================
 // density: D^{t t'}_{s s'}(r)
-//   software-pipelined: the (block, spin, chunk) loop nest is flattened on the host into a list of steps;
-//   step k+1's operands stream into the second shared-memory stage (cp.async) while step k runs on DMMA
+//   The (block, spin, chunk) loop nest is flattened on the host into a list of steps.  A CTA owns 64 "rows"
+//   (4 row slots x 16 grid points) and walks the step list through a 3-stage shared-memory ring.  The operands of
+//   a step arrive by linear bulk copies (phi_a, phi_b rows from the rotated tables, the rho chunk from the
+//   step-packed array written by pack_rho_kernel) issued by ONE thread two steps ahead of the math -- the duty
+//   rotates over the 8 warps so that no warp carries it alone.  All 8 warps run the DMMAs and contract the product
+//   tile with phi_b(r) in the epilogue.  Stage hand-over is by mbarrier only (no CTA-wide barrier in the loop).
 // ================================================================================================
 constexpr int DAC = DENS_AC, DBC = DENS_BC;
-constexpr int RHS = DAC + 4;  // padded row stride of the transposed rho chunk [n=(b,c)][k=a] (bank-conflict free)
+constexpr int RKP = DAC + 4;        // largest packed row stride (kp % 8 == 4)
+constexpr int DSTAGES = 3;
+constexpr int DCONS = 8;            // consumer warps: (row half rh) x (slot pair) x (n-tile parity)
+constexpr int DTHREADS = DCONS * 32;  // exactly two warps per SM sub-partition: up to 255 registers per thread
 
 // Row slots of a density CTA: MODE 0 (rho): 4 derivative types of ONE 16-point tile;
 //                             MODE 1 (kappa): the wave function (type 0) of FOUR consecutive 16-point tiles.
 struct DensSmem {
-  double a[2][4][DAC][RS];       // phi_a(r)   [stage][slot][a][r]
-  double rho[2][2 * DBC][RHS];   // rho chunk, transposed and interleaved: [stage][(b,c)][a]
-  double b[2][4][DBC][RS];       // phi_b(r)   [bbuf][slot][b][r]
+  double a[DSTAGES][4][DAC][RT];      // phi_a(r)   [stage][slot][a][r rotated]; up rows at [0,n_up), down rows at [pad4(n_up),..)
+  double b[DSTAGES][4][DBC][RT];      // phi_b(r)   same row convention
+  double rho[DSTAGES][2 * DBC * RKP]; // rho chunk, transposed and interleaved: [(b,c)][a], row stride kp
+  unsigned long long full[DSTAGES], empty[DSTAGES];
 };
 
 void build_density_steps(int nb, const int* db, const int* isstart, const int* nsu, const int* r2c, const int* r2m,
-                         DensStep* out, int* nout) {
+                         DensStep* out, int* nout, size_t* pk_elems) {
   auto pad4 = [](int x) { return (x + 3) & ~3; };
   // split [0,d) with spin boundary nu into chunks of at most `cap` PADDED entries; a chunk holds (n_up, n_dn)
   struct Chunk { int start, n_up, n_dn; };
@@ -89,28 +86,21 @@ void build_density_steps(int nb, const int* db, const int* isstart, const int* n
     for (int c0 = 0; c0 < nu; c0 += cap) v.push_back({c0, std::min(cap, nu - c0), 0});
     for (int c0 = nu; c0 < d; c0 += cap) v.push_back({c0, 0, std::min(cap, d - c0)});
   };
-  int n = 0, bbuf = 0;
+  int n = 0;
+  size_t pk = 0;
   std::vector<Chunk> ac, bc;
   for (int ix = 0; ix < nb; ix++) {
     const int iy = r2c[ix];
     if (iy < 0) continue;
     const int di = db[ix], dj = db[iy];
     chunks(di, nsu[ix], DENS_AC, ac);
-    // a spin segment longer than one chunk accumulates C across steps: then the b-chunk must hold a single spin
-    const bool a_multi = nsu[ix] > DENS_AC || di - nsu[ix] > DENS_AC;
-    chunks(dj, nsu[iy], a_multi ? 0 : DENS_BC, bc);
-    if (a_multi) {
-      bc.clear();
-      for (int c0 = 0; c0 < nsu[iy]; c0 += DENS_BC) bc.push_back({c0, std::min(DENS_BC, nsu[iy] - c0), 0});
-      for (int c0 = nsu[iy]; c0 < dj; c0 += DENS_BC) bc.push_back({c0, 0, std::min(DENS_BC, dj - c0)});
-    }
+    chunks(dj, nsu[iy], DENS_BC, bc);
     for (const Chunk& b : bc) {
       bool newb = true;
       // a-chunks of one spin segment accumulate into the same C: they must be consecutive -> order: all chunks
       // (merged chunks are complete on their own; split segments come up-chunks first, then down-chunks)
       for (size_t ia = 0; ia < ac.size(); ia++) {
         const Chunk& a = ac[ia];
-        if (newb) bbuf ^= 1;
         const bool merged = a.n_up > 0 && a.n_dn > 0;
         bool first = true, last = true;
         if (!merged) {
@@ -118,179 +108,216 @@ void build_density_steps(int nb, const int* db, const int* isstart, const int* n
           first = ia == 0 || (up ? ac[ia - 1].n_up == 0 : ac[ia - 1].n_dn == 0) || (ac[ia - 1].n_up > 0 && ac[ia - 1].n_dn > 0);
           last = ia + 1 == ac.size() || (up ? ac[ia + 1].n_up == 0 : ac[ia + 1].n_dn == 0);
         }
+        const int atot4 = pad4(a.n_up) + pad4(a.n_dn), btot4 = pad4(b.n_up) + pad4(b.n_dn);
+        const int kp = (atot4 & 7) == 4 ? atot4 : atot4 + 4;
         if (out) {
           DensStep& d = out[n];
           d.a_row0 = isstart[ix] + a.start; d.na_up = a.n_up; d.na_dn = a.n_dn;
           d.b_row0 = isstart[iy] + b.start; d.nb_up = b.n_up; d.nb_dn = b.n_dn;
           d.rho_off = r2m[ix] + a.start + b.start * di; d.ld = di;
-          d.flags = (newb ? 1 : 0) | (first ? 2 : 0) | (last ? 4 : 0) | (bbuf << 3);
-          d.pad = 0;
+          d.flags = (newb ? 1 : 0) | (first ? 2 : 0) | (last ? 4 : 0);
+          d.kp = kp; d.pk_off = (int)pk; d.pad = 0;
         }
+        pk += (size_t)2 * btot4 * kp;
         newb = false;
         n++;
       }
     }
   }
   *nout = n;
+  if (pk_elems) *pk_elems = pk;
 }
 
-// K-loop of one density step for a warp owning NTN n-tiles (every CG-th tile): C[j] += A(8 x 4k) * B(4k x 8)
-template <int NTN, int CG, int NTW>
-__device__ __forceinline__ void dens_mma(double (&C)[NTW][2], const double* __restrict__ pa, const double* __restrict__ pb, int ksteps) {
-  for (int ks = 0; ks < ksteps; ks++) {
-    const double af = pa[(size_t)ks * 4 * RS];
-#pragma unroll
-    for (int j = 0; j < NTN; j++)
-      if (j < NTW) dmma884(C[j][0], C[j][1], af, pb[(size_t)(CG * j) * 8 * RHS + ks * 4]);
+// Repack the rho / kappa block matrices into the per-step operand images of the density kernel:
+// chunk(step)[n = 2 b + c][k = a], spin-segment padded like the shared-memory rows, padding zero-filled.
+__global__ void __launch_bounds__(256) pack_rho_kernel(HamArgs g) {
+  const int kind = blockIdx.y >> 1, q = blockIdx.y & 1, za = blockIdx.z;
+  const int nsteps = kind ? g.nsteps_kap[q] : g.nsteps_rho[q];
+  if ((int)blockIdx.x >= nsteps) return;
+  const DensStep d = (kind ? g.steps_kap[q] : g.steps_rho[q])[blockIdx.x];
+  const int p = g.active[za];
+  const int quad = kind ? g.kap_quad[q] : g.rho_quad[q];
+  const double* __restrict__ src0 = g.rsp + ((size_t)p * 2 + 0) * 4 * g.nxy + (size_t)quad * g.nxy + d.rho_off;
+  const double* __restrict__ src1 = g.rsp + ((size_t)p * 2 + 1) * 4 * g.nxy + (size_t)quad * g.nxy + d.rho_off;
+  double* __restrict__ dst = (kind ? g.pk_kap + ((size_t)za * 2 + q) * g.pk_stride_kap : g.pk_rho + ((size_t)za * 2 + q) * g.pk_stride_rho) + d.pk_off;
+  const int aup4 = (d.na_up + 3) & ~3, bup4 = (d.nb_up + 3) & ~3, btot4 = bup4 + ((d.nb_dn + 3) & ~3);
+  const int total = 2 * btot4 * d.kp;
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int n = idx / d.kp, k = idx - n * d.kp;
+    const int sb = n >> 1, c = n & 1;
+    const int ga = k < aup4 ? k : d.na_up + (k - aup4);
+    const int gb = sb < bup4 ? sb : d.nb_up + (sb - bup4);
+    const bool ok = (k < aup4 ? k < d.na_up : ga < d.na_up + d.na_dn) && (sb < bup4 ? sb < d.nb_up : gb < d.nb_up + d.nb_dn);
+    dst[idx] = ok ? (c ? src1 : src0)[(size_t)ga + (size_t)gb * d.ld] : 0.0;
   }
 }
 
-constexpr int DTHREADS = 512;   // 16 warps: (type t) x (r-half) x (column group)
+// K-loop of one density step for a consumer warp: 2 m-tiles (its two row slots) x NTN n-tiles
+template <int NTN>
+__device__ __forceinline__ void dens_mma(double (&C)[2][4][2], const double* __restrict__ pa, const double* __restrict__ pb, int kp,
+                                         int ksteps) {
+  const double* __restrict__ pbj[NTN];
+#pragma unroll
+  for (int j = 0; j < NTN; j++) pbj[j] = pb + (size_t)j * 16 * kp;
+#pragma unroll 2
+  for (int ks = 0; ks < ksteps; ks++) {
+    const double a0 = pa[(size_t)ks * 4 * RT], a1 = pa[(size_t)(DAC + ks * 4) * RT];
+#pragma unroll
+    for (int j = 0; j < NTN; j++) {
+      const double bf = pbj[j][ks * 4];
+      dmma884(C[0][j][0], C[0][j][1], a0, bf);
+      dmma884(C[1][j][0], C[1][j][1], a1, bf);
+    }
+  }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(DTHREADS, 1) density_kernel(HamArgs g) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   DensSmem& sm = *reinterpret_cast<DensSmem*>(smem_raw);
-  constexpr int NT = 4;                       // row slots
   constexpr int NTE = MODE == 0 ? 4 : 1;      // phi_b types contracted in the epilogue
   constexpr int is_kappa = MODE;
-  constexpr int NWARP = DTHREADS / 32;
-  constexpr int CG = NWARP / (2 * NT);        // column groups: warps sharing a (type, r-half) split the 8 n-tiles
-  constexpr int NTW = 8 / CG;                 // n-tiles per warp per chunk
   const int tile = blockIdx.x, q = blockIdx.y, za = blockIdx.z;
-  const int p = g.active[za];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, lr = lane >> 2, lc = lane & 3;
-  const int tw = warp % NT;
-  const int rh = (warp / NT) & 1;
-  const int cg = warp / (2 * NT);
   const DevBasis& B = g.basis;
   const DensStep* __restrict__ steps = is_kappa ? g.steps_kap[q] : g.steps_rho[q];
   const int nsteps = is_kappa ? g.nsteps_kap[q] : g.nsteps_rho[q];
-  const int quad = is_kappa ? g.kap_quad[q] : g.rho_quad[q];
-  const double* __restrict__ rre = g.rsp + ((size_t)p * 2 + 0) * 4 * g.nxy + (size_t)quad * g.nxy;
-  const double* __restrict__ rim = g.rsp + ((size_t)p * 2 + 1) * 4 * g.nxy + (size_t)quad * g.nxy;
-  // table of row slot t for this CTA
+  const double* __restrict__ pk = is_kappa ? g.pk_kap + ((size_t)za * 2 + q) * g.pk_stride_kap : g.pk_rho + ((size_t)za * 2 + q) * g.pk_stride_rho;
+  // table of row slot t for this CTA (the tables are zero-padded to a multiple of 4 tiles)
   auto slot_base = [&](int t) -> const double* {
-    if (MODE == 0) return B.phi + ((size_t)tile * NTYPE + t) * B.dqp * RT;
-    const int tl = tile * 4 + t;
-    return tl < B.ntiles ? B.phi + (size_t)tl * NTYPE * B.dqp * RT : nullptr;
+    return MODE == 0 ? B.phi + ((size_t)tile * NTYPE + t) * B.dqp * RT : B.phi + (size_t)(tile * 4 + t) * NTYPE * B.dqp * RT;
   };
-  double acc[2][2][NTE][2];
+  // shared memory starts out finite (zero): rows that a step does not overwrite only ever meet zero-filled rho padding
+  for (int i = threadIdx.x; i < (int)(offsetof(DensSmem, full) / 16); i += DTHREADS) reinterpret_cast<double2*>(smem_raw)[i] = make_double2(0.0, 0.0);
+  if (threadIdx.x == 0) {
 #pragma unroll
-  for (int s = 0; s < 2; s++)
-#pragma unroll
-    for (int sp = 0; sp < 2; sp++)
-#pragma unroll
-      for (int t = 0; t < NTE; t++) acc[s][sp][t][0] = acc[s][sp][t][1] = 0.0;
-  const int row_a = rh * 8 + lr;
+    for (int s = 0; s < DSTAGES; s++) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], DCONS); }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  __syncthreads();
 
-  auto prefetch = [&](int k) {
+  // consumer role: row half rh (grid points rh*8 .. rh*8+7), slots 2*sp2 and 2*sp2+1, n-tiles nh, nh+2, nh+4, nh+6
+  const int rh = warp & 1, sp2 = (warp >> 1) & 1, nh = (warp >> 2) & 1;
+  const int row = rh * 8 + lr;
+  double acc[2][2][2][NTE][2];                // [slot of the pair][s][s'][t'][c]
+#pragma unroll
+  for (int i = 0; i < 2 * 2 * 2 * NTE * 2; i++) (&acc[0][0][0][0][0])[i] = 0.0;
+
+  // ---- operand movement of step k (one thread)
+  auto issue = [&](int k) {
+    const int stage = k % DSTAGES, use = k / DSTAGES;
     const DensStep d = steps[k];
-    const int stage = k & 1;
-    load_phi_rows_async<DAC, DTHREADS>(sm.a[stage], slot_base, B.phi, d.a_row0, d.na_up, d.na_dn);
-    if (d.flags & 1) load_phi_rows_async<DBC, DTHREADS>(sm.b[(d.flags >> 3) & 1], slot_base, B.phi, d.b_row0, d.nb_up, d.nb_dn);
-    // rho chunk: threads sweep a (coalesced) for 8 columns at a time; smem index = padded (spin-segmented) index
-    const int aup4 = (d.na_up + 3) & ~3, atot4 = aup4 + ((d.na_dn + 3) & ~3);
-    const int bup4 = (d.nb_up + 3) & ~3, btot4 = bup4 + ((d.nb_dn + 3) & ~3);
-    const int sa_ = threadIdx.x & 63;
-    if (sa_ < atot4) {
-      const int ga = sa_ < aup4 ? sa_ : d.na_up + (sa_ - aup4);
-      const bool aok = sa_ < aup4 ? sa_ < d.na_up : ga < d.na_up + d.na_dn;
-      const double* __restrict__ pr = rre + d.rho_off + ga;
-      const double* __restrict__ pi = rim + d.rho_off + ga;
-      for (int sb_ = threadIdx.x >> 6; sb_ < btot4; sb_ += DTHREADS / 64) {
-        const int gb = sb_ < bup4 ? sb_ : d.nb_up + (sb_ - bup4);
-        const bool ok = aok && (sb_ < bup4 ? sb_ < d.nb_up : gb < d.nb_up + d.nb_dn);
-        cp_async8(&sm.rho[stage][2 * sb_][sa_], ok ? pr + (size_t)gb * d.ld : rre, ok);
-        cp_async8(&sm.rho[stage][2 * sb_ + 1][sa_], ok ? pi + (size_t)gb * d.ld : rim, ok);
-      }
+    if (use > 0) mbar_wait(&sm.empty[stage], (use - 1) & 1);   // all 8 warps are done with the previous tenant
+    const int aup4 = (d.na_up + 3) & ~3, bup4 = (d.nb_up + 3) & ~3, btot4 = bup4 + ((d.nb_dn + 3) & ~3);
+    const unsigned rho_bytes = (unsigned)(2 * btot4 * d.kp) * 8;
+    mbar_expect_tx(&sm.full[stage], 4u * (unsigned)(d.na_up + d.na_dn + d.nb_up + d.nb_dn) * RT * 8 + rho_bytes);
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+      const double* __restrict__ tb = slot_base(t);
+      if (d.na_up) bulk_g2s(&sm.a[stage][t][0][0], tb + (size_t)d.a_row0 * RT, (unsigned)d.na_up * RT * 8, &sm.full[stage]);
+      if (d.na_dn) bulk_g2s(&sm.a[stage][t][aup4][0], tb + (size_t)(d.a_row0 + d.na_up) * RT, (unsigned)d.na_dn * RT * 8, &sm.full[stage]);
+      if (d.nb_up) bulk_g2s(&sm.b[stage][t][0][0], tb + (size_t)d.b_row0 * RT, (unsigned)d.nb_up * RT * 8, &sm.full[stage]);
+      if (d.nb_dn) bulk_g2s(&sm.b[stage][t][bup4][0], tb + (size_t)(d.b_row0 + d.nb_up) * RT, (unsigned)d.nb_dn * RT * 8, &sm.full[stage]);
     }
-    cp_async_commit();
+    bulk_g2s(&sm.rho[stage][0], pk + d.pk_off, rho_bytes, &sm.full[stage]);
   };
-
-  double C[NTW][2];
+  if (threadIdx.x == 0) {
+    if (nsteps > 0) issue(0);
+    if (nsteps > 1) issue(1);
+  }
+  {
+    // ---- consumers
+    double C[2][4][2];
 #pragma unroll
-  for (int j = 0; j < NTW; j++) C[j][0] = C[j][1] = 0.0;
-  if (nsteps > 0) prefetch(0);
-  for (int k = 0; k < nsteps; k++) {
-    if (k + 1 < nsteps) { prefetch(k + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
-    __syncthreads();
-    const DensStep d = steps[k];
-    const int stage = k & 1, bbuf = (d.flags >> 3) & 1;
-    const int aup4 = (d.na_up + 3) & ~3, adn4 = (d.na_dn + 3) & ~3;
-    const int bup4 = (d.nb_up + 3) & ~3, bdn4 = (d.nb_dn + 3) & ~3;
+    for (int i = 0; i < 16; i++) (&C[0][0][0])[i] = 0.0;
+    DensStep dnext = nsteps > 0 ? steps[0] : DensStep{};
+    for (int k = 0; k < nsteps; k++) {
+      const int stage = k % DSTAGES;
+      const DensStep d = dnext;
+      if (k + 1 < nsteps) dnext = steps[k + 1];              // descriptor of the next step: off the critical path
+      const int aup4 = (d.na_up + 3) & ~3, adn4 = (d.na_dn + 3) & ~3;
+      const int bup4 = (d.nb_up + 3) & ~3, btot4 = bup4 + ((d.nb_dn + 3) & ~3);
+      const int ntn = max(0, ((btot4 >> 2) - nh + 1) >> 1);    // n-tiles nh + 2j < btot4/4 owned by this warp
+      // step k+2 goes into the stage of step k-1; it can only be waited for by a warp that has itself left step k-1
+      if (k + 2 < nsteps && (k + 2) % DCONS == warp && lane == 0) issue(k + 2);
+      __syncwarp();
+      mbar_wait(&sm.full[stage], (k / DSTAGES) & 1);
+      if (ntn > 0) {
 #pragma unroll
-    for (int s = 0; s < 2; s++) {
-      const int k0 = s == 0 ? 0 : aup4, ksteps = (s == 0 ? aup4 : adn4) >> 2;
-      if (ksteps == 0) continue;
+        for (int s = 0; s < 2; s++) {
+          const int k0 = s == 0 ? 0 : aup4, ksteps = (s == 0 ? aup4 : adn4) >> 2;
+          if (ksteps == 0) continue;
+          if (d.flags & 2) {
 #pragma unroll
-      for (int sp = 0; sp < 2; sp++) {
-        const int nt0 = (sp == 0 ? 0 : bup4) >> 2, ntiles_n = (sp == 0 ? bup4 : bdn4) >> 2;
-        if (ntiles_n == 0) continue;
-        if (d.flags & 2) {
+            for (int i = 0; i < 16; i++) (&C[0][0][0])[i] = 0.0;
+          }
+          // this lane's a rows are global rows a_row0 (+ n_up) + lc + 4 ks: their rotation does not depend on ks
+          const int pos_a = (row + phi_rot(d.a_row0 + (s == 0 ? 0 : d.na_up) + lc)) & (RT - 1);
+          const double* __restrict__ pa = &sm.a[stage][2 * sp2][k0 + lc][pos_a];
+          const double* __restrict__ pb = &sm.rho[stage][(size_t)(nh * 8 + lr) * d.kp + k0 + lc];
+          switch (ntn) {
+            case 4: dens_mma<4>(C, pa, pb, d.kp, ksteps); break;
+            case 3: dens_mma<3>(C, pa, pb, d.kp, ksteps); break;
+            case 2: dens_mma<2>(C, pa, pb, d.kp, ksteps); break;
+            default: dens_mma<1>(C, pa, pb, d.kp, ksteps); break;
+          }
+          if (d.flags & 4) {
+            // epilogue: contract the product tile with phi_b(r) into the (s, s') accumulators (static indices)
 #pragma unroll
-          for (int j = 0; j < NTW; j++) C[j][0] = C[j][1] = 0.0;
-        }
-        // n-tiles owned by this warp: local index cg + CG*j < ntiles_n -> dispatch on the count so that the DMMA
-        // sequence is unpredicated straight-line code
-        const int ntn = (ntiles_n - cg + CG - 1) / CG;
-        const double* __restrict__ pa = &sm.a[stage][tw][k0 + lc][row_a];
-        const double* __restrict__ pb = &sm.rho[stage][(nt0 + cg) * 8 + lr][k0 + lc];
-        switch (ntn) {
-          case 8: dens_mma<8, CG>(C, pa, pb, ksteps); break;
-          case 7: dens_mma<7, CG>(C, pa, pb, ksteps); break;
-          case 6: dens_mma<6, CG>(C, pa, pb, ksteps); break;
-          case 5: dens_mma<5, CG>(C, pa, pb, ksteps); break;
-          case 4: dens_mma<4, CG>(C, pa, pb, ksteps); break;
-          case 3: dens_mma<3, CG>(C, pa, pb, ksteps); break;
-          case 2: dens_mma<2, CG>(C, pa, pb, ksteps); break;
-          case 1: dens_mma<1, CG>(C, pa, pb, ksteps); break;
-          default: break;
-        }
-        if (d.flags & 4) {
-          // epilogue: contract the product tile with phi_b(r) into the (s, s') accumulators (static indices)
+            for (int j = 0; j < 4; j++) {
+              if (j < ntn) {
+                const int bl = (nh + 2 * j) * 4 + lc;
+                const bool dn = bl >= bup4;                  // warp-uniform: an n-tile lies inside one spin segment
+                const int pos_b = (row + phi_rot(d.b_row0 + (dn ? d.nb_up + bl - bup4 : bl))) & (RT - 1);
 #pragma unroll
-          for (int j = 0; j < NTW; j++) {
-            if (j < ntn) {
-              const int bl = (nt0 + cg + CG * j) * 4 + lc;
-#pragma unroll
-              for (int t2 = 0; t2 < NTE; t2++) {
-                const double ph = sm.b[bbuf][MODE == 0 ? t2 : tw][bl][row_a];
-                acc[s][sp][t2][0] += C[j][0] * ph;
-                acc[s][sp][t2][1] += C[j][1] * ph;
+                for (int t2 = 0; t2 < NTE; t2++) {
+                  double ph0, ph1;
+                  if (MODE == 0) { ph0 = ph1 = sm.b[stage][t2][bl][pos_b]; }
+                  else { ph0 = sm.b[stage][2 * sp2][bl][pos_b]; ph1 = sm.b[stage][2 * sp2 + 1][bl][pos_b]; }
+                  if (!dn) {
+                    acc[0][s][0][t2][0] += C[0][j][0] * ph0; acc[0][s][0][t2][1] += C[0][j][1] * ph0;
+                    acc[1][s][0][t2][0] += C[1][j][0] * ph1; acc[1][s][0][t2][1] += C[1][j][1] * ph1;
+                  } else {
+                    acc[0][s][1][t2][0] += C[0][j][0] * ph0; acc[0][s][1][t2][1] += C[0][j][1] * ph0;
+                    acc[1][s][1][t2][0] += C[1][j][0] * ph1; acc[1][s][1][t2][1] += C[1][j][1] * ph1;
+                  }
+                }
               }
             }
           }
         }
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.empty[stage]);         // this warp is done with the stage
     }
-    __syncthreads();   // stage k&1 is free for the prefetch of step k+2
   }
-  // reduce over the 4 lanes of a row, then over column-group warps (fixed order: deterministic)
-  double* red = reinterpret_cast<double*>(smem_raw);  // [NWARP][8 rows][2*2*NTE*2]
+  __syncthreads();
+  // reduce over the 4 lanes of a row, then over the two n-tile-parity warps (fixed order: deterministic)
+  double* red = reinterpret_cast<double*>(smem_raw);  // [DCONS][8 rows][2 slots][NACC]
   constexpr int NACC = 2 * 2 * NTE * 2;
+  {
 #pragma unroll
-  for (int s = 0; s < 2; s++)
+    for (int sl = 0; sl < 2; sl++)
 #pragma unroll
-    for (int sp = 0; sp < 2; sp++)
-#pragma unroll
-      for (int t2 = 0; t2 < NTE; t2++)
-#pragma unroll
-        for (int c = 0; c < 2; c++) {
-          double v = acc[s][sp][t2][c];
-          v += __shfl_xor_sync(0xffffffffu, v, 1);
-          v += __shfl_xor_sync(0xffffffffu, v, 2);
-          if (lc == 0) red[((size_t)warp * 8 + lr) * NACC + ((s * 2 + sp) * NTE + t2) * 2 + c] = v;
-        }
+      for (int e = 0; e < NACC; e++) {
+        double v = (&acc[sl][0][0][0][0])[e];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        if (lc == 0) red[(((size_t)warp * 8 + lr) * 2 + sl) * NACC + e] = v;
+      }
+  }
   __syncthreads();
   const int ndd = NTE * NTE * 8;
   double* __restrict__ out = (is_kappa ? g.dd_kap : g.dd_rho) + ((size_t)za * 2 + q) * ndd * B.nghl;
-  for (int idx = threadIdx.x; idx < NT * RT * NACC; idx += DTHREADS) {
-    const int e = idx % NACC, rr = (idx / NACC) % RT, t = idx / (NACC * RT);
-    const int c = e & 1, t2 = (e >> 1) % NTE, ssp = e / (2 * NTE);   // ssp = s*2+sp
+  for (int idx = threadIdx.x; idx < 4 * RT * NACC; idx += DTHREADS) {
+    const int e = idx % NACC, rr = (idx / NACC) % RT, t = idx / (NACC * RT);   // t = row slot
+    const int c = e & 1, t2 = (e >> 1) % NTE, ssp = e / (2 * NTE);           // ssp = s*2+sp
     double v = 0.0;
-    for (int kk = 0; kk < CG; kk++) {
-      const int w = t + NT * (rr >> 3) + 2 * NT * kk;   // warp = tw + NT*rh + 2*NT*cg
-      v += red[((size_t)w * 8 + (rr & 7)) * NACC + e];
+#pragma unroll
+    for (int kk = 0; kk < 2; kk++) {
+      const int w = (rr >> 3) + 2 * (t >> 1) + 4 * kk;                          // warp = rh + 2*sp2 + 4*nh
+      v += red[(((size_t)w * 8 + (rr & 7)) * 2 + (t & 1)) * NACC + e];
     }
     if (MODE == 0) {
       const int r = tile * RT + rr;
@@ -310,6 +337,8 @@ void launch_density(const HamArgs& a, cudaStream_t stream) {
     PNFAM_CUDA_CHECK(cudaFuncSetAttribute(density_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DensSmem)));
     attr = true;
   }
+  const int maxsteps = std::max(std::max(a.nsteps_rho[0], a.nsteps_rho[1]), std::max(a.nsteps_kap[0], a.nsteps_kap[1]));
+  if (maxsteps > 0) pack_rho_kernel<<<dim3(maxsteps, 4, a.nactive), 256, 0, stream>>>(a);
   density_kernel<0><<<dim3(a.basis.ntiles, 2, a.nactive), DTHREADS, sizeof(DensSmem), stream>>>(a);
   density_kernel<1><<<dim3((a.basis.ntiles + 3) / 4, 2, a.nactive), DTHREADS, sizeof(DensSmem), stream>>>(a);
 }
@@ -600,33 +629,14 @@ void launch_fields(const HamArgs& a, cudaStream_t stream) {
 // ================================================================================================
 constexpr int GS = 68;    // padded row stride of G (64 interleaved (b,c) columns): conflict-free B-fragment loads
 constexpr int ACP = 48;   // rows a per output tile = up to 6 DMMA m-tiles
-// warp-specialised: 8 consumer warps run DMMA (one n-tile each, all m-tiles: two consumers per SM sub-partition,
-// equal work -- the FP64 tensor pipe is one DMMA per 16 clk per sub-partition, measured with scripts/dmma_probe.cu),
+// warp-specialised: 4 consumer warps run DMMA, one per SM sub-partition (the FP64 tensor pipe is one DMMA per
+// 16 clk per sub-partition and one warp with >= 2 independent accumulators saturates it: scripts/dmma_probe.cu).
+// A consumer owns n-tiles w and w+4 and all m-tiles: 8 fragment loads feed 12 DMMAs, which keeps the shared-memory
+// pipe (the second limiter of this kernel) at about a third of its bandwidth.
 // 8 producer warps build G; ONE producer thread moves all operands with linear bulk copies (cp.async.bulk)
 // that complete on mbarriers.
-constexpr int PCONS = 8, PPROD = 8;
+constexpr int PCONS = 4, PPROD = 8;
 constexpr int PTHREADS = (PCONS + PPROD) * 32;
-
-// ---- mbarrier + bulk-copy primitives (PTX) --------------------------------------------------------
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* b, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(b)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {
-  const unsigned a = smem_u32(b);
-  unsigned ok;
-  do {
-    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-                 : "=r"(ok) : "r"(a), "r"(parity) : "memory");
-  } while (!ok);
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* b) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
-               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(b)) : "memory");
-}
 
 // MODE 0 (h):     the NS = 5 k-slabs of one iteration are the 5 derivative types of ONE r-tile; G mixes types through mf.
 // MODE 1 (Delta): the NS = 4 k-slabs are the wave functions (type 0) of FOUR consecutive r-tiles; G^j = pf(r) phi_b(r).
@@ -641,18 +651,37 @@ struct ProjSmem {
   unsigned long long barA[2], barB[2];
 };
 
-// DMMA sequence of one iteration for a consumer warp: its n-tile (8 columns) x MT m-tiles of 8 rows, straight-line code
-template <int NS, int MT>
-__device__ __forceinline__ void proj_mma(double (&C)[6][2], const double* __restrict__ pa, const double* __restrict__ pg,
+// DMMA sequence of one iteration for a consumer warp: NN n-tiles (8 columns each, 32 columns apart) x MT m-tiles
+// of 8 rows, straight-line code
+template <int NS, int MT, int NN>
+__device__ __forceinline__ void proj_mma(double (&C)[6][2][2], const double* __restrict__ pa, const double* __restrict__ pg,
                                          const int (&kp)[RT / 4]) {
 #pragma unroll
   for (int t = 0; t < NS; t++)
 #pragma unroll
     for (int ks = 0; ks < RT / 4; ks++) {
-      const double bf = pg[((size_t)t * RT + ks * 4) * GS];
+      double bf[NN];
 #pragma unroll
-      for (int i = 0; i < MT; i++) dmma884(C[i][0], C[i][1], pa[((size_t)t * ACP + i * 8) * RT + kp[ks]], bf);
+      for (int n = 0; n < NN; n++) bf[n] = pg[((size_t)t * RT + ks * 4) * GS + n * 32];
+#pragma unroll
+      for (int i = 0; i < MT; i++) {
+        const double af = pa[((size_t)t * ACP + i * 8) * RT + kp[ks]];
+#pragma unroll
+        for (int n = 0; n < NN; n++) dmma884(C[i][n][0], C[i][n][1], af, bf[n]);
+      }
     }
+}
+template <int NS, int NN>
+__device__ __forceinline__ void proj_mma_mt(int mt, double (&C)[6][2][2], const double* __restrict__ pa, const double* __restrict__ pg,
+                                            const int (&kp)[RT / 4]) {
+  switch (mt) {
+    case 6: proj_mma<NS, 6, NN>(C, pa, pg, kp); break;
+    case 5: proj_mma<NS, 5, NN>(C, pa, pg, kp); break;
+    case 4: proj_mma<NS, 4, NN>(C, pa, pg, kp); break;
+    case 3: proj_mma<NS, 3, NN>(C, pa, pg, kp); break;
+    case 2: proj_mma<NS, 2, NN>(C, pa, pg, kp); break;
+    default: proj_mma<NS, 1, NN>(C, pa, pg, kp); break;
+  }
 }
 
 // structurally non-zero (t, t') entries of the Skyrme field tensor (fields_kernel): the Laplacian only pairs with
@@ -662,7 +691,7 @@ __host__ __device__ constexpr bool mf_nonzero(int t, int t2) { return t == 0 || 
 // tile descriptor: x = block row, y = first row a of the chunk (inside one spin segment), z = first column b
 template <int MODE>
 __global__ void __launch_bounds__(PTHREADS, 1) projection_kernel(HamArgs g, const int4* __restrict__ tiles, int tile_off, int ntiles_q,
-                                                                 int ksplit, int q) {
+                                                                 int ksplit, int q, int dbg) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   using Smem = ProjSmem<MODE>;
   constexpr int NS = Smem::NS;
@@ -711,36 +740,44 @@ __global__ void __launch_bounds__(PTHREADS, 1) projection_kernel(HamArgs g, cons
     for (int s = 0; s < NS; s++) bulk_g2s(&sm.b[stage][s][0][0], slab(it, s) + (size_t)(ib + b0) * RT, bytes, &sm.barB[stage]);
     bulk_g2s(&sm.mf[stage][0], mfg + (size_t)it * (is_delta ? 4 * PF_TILE : 2 * MF_TILE), Smem::MFD * 8, &sm.barB[stage]);
   };
-  // ---- G build: producer thread = (grid point rr, column bq and bq + 16), all slabs
-  const int rr = ptid & (RT - 1), bq = ptid >> 4;
+  // ---- G build: producer thread = (grid point rr, columns bq and bq + 16), all slabs.  Lane mapping inside a warp:
+  // a quarter-warp holds 4 grid points x 2 adjacent columns, which makes the 16-byte G stores, the phi_b loads
+  // (adjacent rows are rotated 8 points apart) and the field-tensor loads bank-conflict free.
+  const int rr = (ptid & 3) + 4 * ((ptid >> 3) & 3), bq = 2 * (ptid >> 5) + ((ptid >> 2) & 1);
   auto build_g = [&](int stage) {
+    if (bq >= nbc4) return;                               // warp-uniform (nbc4 is a multiple of 4)
+    const bool two = bq + 16 < nbc4;
+    const int bl0 = bq, bl1 = two ? bq + 16 : bq;
+    const int sb0 = bl0 < nb_up ? 0 : 1, sb1 = bl1 < nb_up ? 0 : 1;
+    double ph0[NS], ph1[NS];
+    {
+      const int p0 = (rr + phi_rot(ib + b0 + bl0)) & (RT - 1), p1 = (rr + phi_rot(ib + b0 + bl1)) & (RT - 1);
 #pragma unroll
-    for (int j = 0; j < BC / 16; j++) {
-      const int bl = bq + 16 * j;
-      if (bl < nbc4) {                                    // warp-uniform: a warp holds columns 2w', 2w'+1
-        const int sb = bl < nb_up ? 0 : 1;
-        const int pos = (rr + 4 * ((ib + b0 + bl) & 3)) & (RT - 1);
-        double ph[NS];
+      for (int s = 0; s < NS; s++) { ph0[s] = sm.b[stage][s][bl0][p0]; ph1[s] = sm.b[stage][s][bl1][p1]; }
+    }
+    const double2* __restrict__ m0 = reinterpret_cast<const double2*>(&sm.mf[stage][0]) + sb0 * RT + rr;
+    const double2* __restrict__ m1 = reinterpret_cast<const double2*>(&sm.mf[stage][0]) + sb1 * RT + rr;
+    const bool same = sb0 == sb1;                        // both columns in one spin segment: one field load serves both
 #pragma unroll
-        for (int s = 0; s < NS; s++) ph[s] = sm.b[stage][s][bl][pos];
-        const double2* __restrict__ m = reinterpret_cast<const double2*>(&sm.mf[stage][0]) + sb * RT + rr;
+    for (int t = 0; t < NS; t++) {
+      double gr0 = 0.0, gi0 = 0.0, gr1 = 0.0, gi1 = 0.0;
+      if (is_delta) {
+        const double2 v0 = m0[t * 2 * RT];
+        const double2 v1 = same ? v0 : m1[t * 2 * RT];
+        gr0 = v0.x * ph0[t]; gi0 = v0.y * ph0[t];
+        gr1 = v1.x * ph1[t]; gi1 = v1.y * ph1[t];
+      } else {
 #pragma unroll
-        for (int t = 0; t < NS; t++) {
-          double gr = 0.0, gi = 0.0;
-          if (is_delta) {
-            const double2 v = m[t * 2 * RT];
-            gr = v.x * ph[t]; gi = v.y * ph[t];
-          } else {
-#pragma unroll
-            for (int t2 = 0; t2 < NS; t2++)
-              if (mf_nonzero(t, t2)) {
-                const double2 v = m[(t * NS + t2) * 2 * RT];
-                gr += v.x * ph[t2]; gi += v.y * ph[t2];
-              }
+        for (int t2 = 0; t2 < NS; t2++)
+          if (mf_nonzero(t, t2)) {
+            const double2 v0 = m0[(t * NS + t2) * 2 * RT];
+            const double2 v1 = same ? v0 : m1[(t * NS + t2) * 2 * RT];
+            gr0 += v0.x * ph0[t2]; gi0 += v0.y * ph0[t2];
+            gr1 += v1.x * ph1[t2]; gi1 += v1.y * ph1[t2];
           }
-          *reinterpret_cast<double2*>(&sm.g[stage][t][rr][2 * bl]) = make_double2(gr, gi);
-        }
       }
+      *reinterpret_cast<double2*>(&sm.g[stage][t][rr][2 * bl0]) = make_double2(gr0, gi0);
+      if (two) *reinterpret_cast<double2*>(&sm.g[stage][t][rr][2 * bl1]) = make_double2(gr1, gi1);
     }
   };
 
@@ -754,14 +791,15 @@ __global__ void __launch_bounds__(PTHREADS, 1) projection_kernel(HamArgs g, cons
     }
   }
   __syncthreads();
-  double C[6][2];
+  double C[6][2][2];
 #pragma unroll
-  for (int i = 0; i < 6; i++) C[i][0] = C[i][1] = 0.0;
+  for (int i = 0; i < 6; i++) C[i][0][0] = C[i][0][1] = C[i][1][0] = C[i][1][1] = 0.0;
   const int mt = nac8 >> 3;                              // m-tiles of this output tile (1..6)
-  const bool cons_active = !producer && warp * 4 < nbc4; // consumer warp w owns n-tile w
+  const bool cons_active = !producer && warp * 4 < nbc4; // consumer warp w owns n-tiles w and w + 4
+  const bool cons_two = (warp + 4) * 4 < nbc4;
   int kp[RT / 4];                                        // rotated position of grid point 4*ks + lc in this lane's a rows
 #pragma unroll
-  for (int ks = 0; ks < RT / 4; ks++) kp[ks] = (4 * ks + lc + 4 * ((ia + a0 + lr) & 3)) & (RT - 1);
+  for (int ks = 0; ks < RT / 4; ks++) kp[ks] = (4 * ks + lc + phi_rot(ia + a0 + lr)) & (RT - 1);
   if (producer && nit > 0) {
     mbar_wait(&sm.barB[0], 0);
     build_g(0);
@@ -778,20 +816,15 @@ __global__ void __launch_bounds__(PTHREADS, 1) projection_kernel(HamArgs g, cons
       }
       if (i + 1 < nit) {
         mbar_wait(&sm.barB[stage ^ 1], ((i + 1) >> 1) & 1);
-        build_g(stage ^ 1);                              // g(i+1) while the consumers work on g(i)
+        if (!(dbg & 2)) build_g(stage ^ 1);              // g(i+1) while the consumers work on g(i)
       }
     } else if (cons_active) {
       mbar_wait(&sm.barA[stage], (i >> 1) & 1);
       const double* __restrict__ pa = &sm.a[stage][0][lr][0];
       const double* __restrict__ pg = &sm.g[stage][0][lc][warp * 8 + lr];
-      switch (mt) {
-        case 6: proj_mma<NS, 6>(C, pa, pg, kp); break;
-        case 5: proj_mma<NS, 5>(C, pa, pg, kp); break;
-        case 4: proj_mma<NS, 4>(C, pa, pg, kp); break;
-        case 3: proj_mma<NS, 3>(C, pa, pg, kp); break;
-        case 2: proj_mma<NS, 2>(C, pa, pg, kp); break;
-        default: proj_mma<NS, 1>(C, pa, pg, kp); break;
-      }
+      if (dbg & 1) {
+      } else if (cons_two) proj_mma_mt<NS, 2>(mt, C, pa, pg, kp);
+      else proj_mma_mt<NS, 1>(mt, C, pa, pg, kp);
     }
     __syncthreads();
   }
@@ -800,15 +833,18 @@ __global__ void __launch_bounds__(PTHREADS, 1) projection_kernel(HamArgs g, cons
     const size_t pstride = 2 * g.nxy;   // re | im
     double* __restrict__ part = g.hpart + (((size_t)za * 2 + q) * 2 + MODE) * (size_t)ksplit * pstride + (size_t)ksp * pstride;
     const size_t off = st.r2m[ix];
-    const int bl = warp * 4 + lc;
-    if (bl < nbc) {
 #pragma unroll
-      for (int i = 0; i < 6; i++) {
-        const int al = i * 8 + lr;
-        if (al < nac) {
-          const size_t e = off + (size_t)(a0 + al) + (size_t)(b0 + bl) * di;
-          part[e] = C[i][0];
-          part[g.nxy + e] = C[i][1];
+    for (int n = 0; n < 2; n++) {
+      const int bl = (warp + 4 * n) * 4 + lc;
+      if (bl < nbc) {
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+          const int al = i * 8 + lr;
+          if (al < nac) {
+            const size_t e = off + (size_t)(a0 + al) + (size_t)(b0 + bl) * di;
+            part[e] = C[i][n][0];
+            part[g.nxy + e] = C[i][n][1];
+          }
         }
       }
     }
@@ -840,14 +876,16 @@ void launch_projection(const HamArgs& a, const ProjPlan& pp, cudaStream_t stream
     PNFAM_CUDA_CHECK(cudaFuncSetAttribute(projection_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ProjSmem<1>)));
     attr = true;
   }
+  // development knob (timing experiments only; results are wrong when set): bit0 skips the DMMA, bit1 the G build
+  static const int dbg = getenv("PNFAM_B200_PROJ_DEBUG") ? atoi(getenv("PNFAM_B200_PROJ_DEBUG")) : 0;
   for (int q = 0; q < 2; q++) {
     if (pp.ntiles_h[q] > 0) {
       dim3 grid(pp.ntiles_h[q], pp.ksplit, a.nactive);
-      projection_kernel<0><<<grid, PTHREADS, sizeof(ProjSmem<0>), stream>>>(a, pp.tiles_h, pp.tile_off_h[q], pp.ntiles_h[q], pp.ksplit, q);
+      projection_kernel<0><<<grid, PTHREADS, sizeof(ProjSmem<0>), stream>>>(a, pp.tiles_h, pp.tile_off_h[q], pp.ntiles_h[q], pp.ksplit, q, dbg);
     }
     if (pp.ntiles_d[q] > 0) {
       dim3 grid(pp.ntiles_d[q], pp.ksplit, a.nactive);
-      projection_kernel<1><<<grid, PTHREADS, sizeof(ProjSmem<1>), stream>>>(a, pp.tiles_d, pp.tile_off_d[q], pp.ntiles_d[q], pp.ksplit, q);
+      projection_kernel<1><<<grid, PTHREADS, sizeof(ProjSmem<1>), stream>>>(a, pp.tiles_d, pp.tile_off_d[q], pp.ntiles_d[q], pp.ksplit, q, dbg);
     }
   }
   dim3 gr((unsigned)((2 * a.nxy + 255) / 256), 4, a.nactive);

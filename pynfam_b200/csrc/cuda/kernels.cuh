@@ -50,8 +50,9 @@ struct DensStep {
   int a_row0, na_up, na_dn;   // first basis state (global index) of the contraction chunk; rows per spin
   int b_row0, nb_up, nb_dn;   // first column state (global index); columns per spin
   int rho_off, ld;            // element offset of (a chunk start, b chunk start) inside the block matrix, leading dim
-  int flags;                  // bit0: new b-chunk (stage phi_b into buffer bbuf); bit1: first a-chunk (zero C);
-                              // bit2: last a-chunk (epilogue); bit3: bbuf
+  int flags;                  // bit0: new b-chunk; bit1: first a-chunk (zero C); bit2: last a-chunk (epilogue)
+  int kp;                     // row stride of the packed chunk: >= padded a-count, kp % 8 == 4 (bank-conflict free)
+  int pk_off;                 // offset (doubles) of the packed chunk [n = (b,c)][k = a] in the packed rho array
   int pad;
 };
 constexpr int DENS_AC = 48;   // contraction chunk
@@ -64,6 +65,9 @@ struct HamArgs {
   int rho_quad[2], kap_quad[2];   // storage quadrant of rho / kappa (and of h / Delta) for each pass
   const DensStep* steps_rho[2]; int nsteps_rho[2];   // pipeline step lists of the density kernel, per pass
   const DensStep* steps_kap[2]; int nsteps_kap[2];
+  double* pk_rho;                 // [nactive][2 q][pk_stride_rho]  rho chunks repacked step by step (pack_rho_kernel)
+  double* pk_kap;                 // [nactive][2 q][pk_stride_kap]
+  size_t pk_stride_rho, pk_stride_kap;
   const double* rsp;              // [P][2 c][4][nxy]
   double* hsp;                    // [P][2 c][4][nxy]
   size_t nxy;
@@ -87,7 +91,7 @@ struct ProjPlan {                 // output tiles of the grid->HO projection
 void launch_density(const HamArgs& a, cudaStream_t stream);
 // host helper: flatten a block structure into density pipeline steps
 void build_density_steps(int nb, const int* db, const int* isstart, const int* nsu, const int* r2c, const int* r2m,
-                         DensStep* out, int* nout);  // out may be null to count
+                         DensStep* out, int* nout, size_t* pk_elems);  // out may be null to count
 void launch_fields(const HamArgs& a, cudaStream_t stream);
 void launch_projection(const HamArgs& a, const ProjPlan& pp, cudaStream_t stream);
 size_t projection_partial_elems(const ProjPlan& pp, size_t nxy);

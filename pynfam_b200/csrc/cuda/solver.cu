@@ -98,9 +98,7 @@ extern "C" int pnfam_b200_ctx_create(const pnfam_b200_model* m, int device, pnfa
     if (c->use_diag) { c->qp_fp.assign(m->qp_fp, m->qp_fp + m->dqp); c->qp_fn.assign(m->qp_fn, m->qp_fn + m->dqp); }
     c->d_db.upload(c->db); c->d_isstart.upload(c->isstart); c->d_nsu.upload(c->nsu);
     // tile-major wave-function tables: phi[tile][type][state][RT], zero-padded to a multiple of 4 tiles.
-    // Inside a 128-byte row the 16 grid points are ROTATED by 4*(state & 3) positions: a plain linear (bulk) copy
-    // of consecutive rows into shared memory is then bank-conflict free for the DMMA fragment loads (4 consecutive
-    // rows x 4 consecutive points hit 16 different 8-byte banks) without any padding.
+    // Inside a 128-byte row the 16 grid points are rotated by phi_rot(state) positions (device_common.cuh).
     {
       const double* tab[NTYPE] = {m->wf, m->wfdr, m->wfdp, m->wfdz, m->wfd2_all};
       const int dqp = c->dqp, nghl = c->nghl, ntiles = c->ntiles, ntiles4 = (c->ntiles + 3) & ~3;
@@ -112,7 +110,7 @@ extern "C" int pnfam_b200_ctx_create(const pnfam_b200_model* m, int device, pnfa
           const int r0 = tile * RT, nr = std::min(RT, nghl - r0);
           for (int s = 0; s < dqp; s++) {
             const double* src = tab[t] + (size_t)s * nghl + r0;
-            const int rot = 4 * (s & 3);
+            const int rot = phi_rot(s);
             for (int r = 0; r < nr; r++) dst[(size_t)s * RT + ((r + rot) & (RT - 1))] = src[r];
           }
         }
@@ -159,13 +157,17 @@ struct OperatorDev {
   DBuf<DensStep> dsteps[4];       // rho pass0, rho pass1, kappa pass0, kappa pass1
   int ndsteps[4] = {0, 0, 0, 0};
   size_t scratch_elems = 0;
+  size_t pk_rho = 0, pk_kap = 0;  // doubles of the packed rho / kappa chunks per (point, pass)
 };
 
-void upload_density_steps(const pnfam_b200_ctx& c, const BlockStruct& st, DBuf<DensStep>& buf, int& n) {
-  build_density_steps(c.nb, c.db.data(), c.isstart.data(), c.nsu.data(), st.r2c.data(), st.r2m.data(), nullptr, &n);
+// returns the number of doubles of the packed rho chunks of this step list
+size_t upload_density_steps(const pnfam_b200_ctx& c, const BlockStruct& st, DBuf<DensStep>& buf, int& n) {
+  size_t pk = 0;
+  build_density_steps(c.nb, c.db.data(), c.isstart.data(), c.nsu.data(), st.r2c.data(), st.r2m.data(), nullptr, &n, &pk);
   std::vector<DensStep> h(std::max(n, 1));
-  build_density_steps(c.nb, c.db.data(), c.isstart.data(), c.nsu.data(), st.r2c.data(), st.r2m.data(), h.data(), &n);
+  build_density_steps(c.nb, c.db.data(), c.isstart.data(), c.nsu.data(), st.r2c.data(), st.r2m.data(), h.data(), &n, &pk);
   buf.upload(h);
+  return pk;
 }
 
 void flatten(const TransformPlan& tp, DBuf<DevTask>& dt, DBuf<int2>& de, DevicePlan& out) {
@@ -234,10 +236,10 @@ std::unique_ptr<OperatorDev> make_operator(pnfam_b200_ctx& c, const pnfam_b200_o
   flatten(od->plan.backward, od->bwd_tasks, od->bwd_entries, od->bwd);
   od->scratch_elems = std::max(od->fwd.scratch_elems, od->bwd.scratch_elems);
   for (int k = 0; k < 4; k++) { od->sp[k].upload(od->plan.sp[k]); od->hsp[k].upload(od->plan.hsp[k]); }
-  upload_density_steps(c, od->plan.sp[0], od->dsteps[0], od->ndsteps[0]);
-  upload_density_steps(c, od->plan.sp[3], od->dsteps[1], od->ndsteps[1]);
-  upload_density_steps(c, od->plan.sp[1], od->dsteps[2], od->ndsteps[2]);
-  upload_density_steps(c, od->plan.sp[2], od->dsteps[3], od->ndsteps[3]);
+  od->pk_rho = std::max(upload_density_steps(c, od->plan.sp[0], od->dsteps[0], od->ndsteps[0]),
+                        upload_density_steps(c, od->plan.sp[3], od->dsteps[1], od->ndsteps[1]));
+  od->pk_kap = std::max(upload_density_steps(c, od->plan.sp[1], od->dsteps[2], od->ndsteps[2]),
+                        upload_density_steps(c, od->plan.sp[2], od->dsteps[3], od->ndsteps[3]));
   // projection output tiles: pass 0 -> (h_pn = hsp[0], Delta+ = hsp[1]); pass 1 -> (h_np = hsp[3], Delta- = hsp[2])
   {
     std::vector<int4> th, td;
@@ -268,6 +270,7 @@ HamArgs make_ham_args(const pnfam_b200_ctx& c, const OperatorDev& od) {
     h.steps_rho[q] = od.dsteps[q].p; h.nsteps_rho[q] = od.ndsteps[q];
     h.steps_kap[q] = od.dsteps[2 + q].p; h.nsteps_kap[q] = od.ndsteps[2 + q];
   }
+  h.pk_stride_rho = od.pk_rho; h.pk_stride_kap = od.pk_kap;
   return h;
 }
 
@@ -326,7 +329,7 @@ extern "C" int pnfam_b200_solve(pnfam_b200_ctx* c, const pnfam_b200_operator* op
 
     // ---- per-point state ---------------------------------------------------------------------------------
     DBuf<double> vin, vout, df, dv, gram, work, gamma, red, d_si, d_normi, d_omega, d_str;
-    DBuf<double> rsp, hsp, hqp, scratch, dd_rho, dd_kap, mf, pf, hpart;
+    DBuf<double> rsp, hsp, hqp, scratch, dd_rho, dd_kap, mf, pf, hpart, pk_rho, pk_kap;
     DBuf<int> d_active;
     const int nred = 64;
     vin.alloc((size_t)P * n); vout.alloc((size_t)P * n);
@@ -343,6 +346,7 @@ extern "C" int pnfam_b200_solve(pnfam_b200_ctx* c, const pnfam_b200_operator* op
     // field tensors are tile-major (kernels.cuh); the padding grid points are zeroed once and never written
     mf.alloc((size_t)P * 2 * mf_elems(c->ntiles)); pf.alloc((size_t)P * 2 * pf_elems(c->ntiles));
     mf.zero(); pf.zero();
+    pk_rho.alloc((size_t)P * 2 * std::max<size_t>(od->pk_rho, 1)); pk_kap.alloc((size_t)P * 2 * std::max<size_t>(od->pk_kap, 1));
     hpart.alloc((size_t)P * projection_partial_elems(od->proj, nxy));
     d_active.alloc(P);
     {
@@ -382,6 +386,7 @@ extern "C" int pnfam_b200_solve(pnfam_b200_ctx* c, const pnfam_b200_operator* op
 
     HamArgs ha = make_ham_args(*c, *od);
     ha.rsp = rsp.p; ha.hsp = hsp.p; ha.dd_rho = dd_rho.p; ha.dd_kap = dd_kap.p; ha.mf = mf.p; ha.pf = pf.p;
+    ha.pk_rho = pk_rho.p; ha.pk_kap = pk_kap.p;
     ha.hpart = hpart.p; ha.active = d_active.p;
 
     MixArgs ma{};
@@ -528,10 +533,11 @@ extern "C" int pnfam_b200_calc_hamiltonian(pnfam_b200_ctx* c, const pnfam_b200_b
     h.nxy = nxy;
     DBuf<DensStep> dsteps[4];
     int ndsteps[4];
-    upload_density_steps(*c, hin[0], dsteps[0], ndsteps[0]);
-    upload_density_steps(*c, hin[2], dsteps[1], ndsteps[1]);
-    upload_density_steps(*c, hin[1], dsteps[2], ndsteps[2]);
-    upload_density_steps(*c, hin[3], dsteps[3], ndsteps[3]);
+    h.pk_stride_rho = std::max(upload_density_steps(*c, hin[0], dsteps[0], ndsteps[0]), upload_density_steps(*c, hin[2], dsteps[1], ndsteps[1]));
+    h.pk_stride_kap = std::max(upload_density_steps(*c, hin[1], dsteps[2], ndsteps[2]), upload_density_steps(*c, hin[3], dsteps[3], ndsteps[3]));
+    DBuf<double> pk_rho, pk_kap;
+    pk_rho.alloc(2 * std::max<size_t>(h.pk_stride_rho, 1)); pk_kap.alloc(2 * std::max<size_t>(h.pk_stride_kap, 1));
+    h.pk_rho = pk_rho.p; h.pk_kap = pk_kap.p;
     for (int q = 0; q < 2; q++) {
       h.steps_rho[q] = dsteps[q].p; h.nsteps_rho[q] = ndsteps[q];
       h.steps_kap[q] = dsteps[2 + q].p; h.nsteps_kap[q] = ndsteps[2 + q];
