@@ -54,25 +54,26 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
 // ================================================================================================
 // density: D^{t t'}_{s s'}(r)
 //   The (block, spin, chunk) loop nest is flattened on the host into a list of steps.  A CTA owns 64 "rows"
-//   (4 row slots x 16 grid points) and walks the step list through a 3-stage shared-memory ring.  The operands of
-//   a step arrive by linear bulk copies (phi_a, phi_b rows from the rotated tables, the rho chunk from the
-//   step-packed array written by pack_rho_kernel) issued by ONE thread two steps ahead of the math -- the duty
-//   rotates over the 8 warps so that no warp carries it alone.  All 8 warps run the DMMAs and contract the product
+//   (4 row slots x 16 grid points) and walks the step list through a shared-memory ring whose allocation is
+//   simulated on the host: small steps take little room, so up to 12 of them are in flight ahead of the math.
+//   The operands of a step arrive by linear bulk copies (phi_a, phi_b rows from the rotated tables, the rho chunk
+//   from the step-packed array written by pack_rho_kernel) issued by ONE thread -- the duty rotates over the 8
+//   warps so that no warp carries it alone.  All 8 warps run the DMMAs and contract the product
 //   tile with phi_b(r) in the epilogue.  Stage hand-over is by mbarrier only (no CTA-wide barrier in the loop).
 // ================================================================================================
 constexpr int DAC = DENS_AC, DBC = DENS_BC;
-constexpr int RKP = DAC + 4;        // largest packed row stride (kp % 8 == 4)
-constexpr int DSTAGES = 3;
 constexpr int DCONS = 8;            // consumer warps: (row half rh) x (slot pair) x (n-tile parity)
 constexpr int DTHREADS = DCONS * 32;  // exactly two warps per SM sub-partition: up to 255 registers per thread
 
 // Row slots of a density CTA: MODE 0 (rho): 4 derivative types of ONE 16-point tile;
 //                             MODE 1 (kappa): the wave function (type 0) of FOUR consecutive 16-point tiles.
+// Operand image of one step inside the arena (sizes follow the step, not the maximum chunk):
+//   phi_a [4 slots][atot4][RT]   up rows at [0, n_up), down rows at [pad4(n_up), ..), rows rotated as in the tables
+//   phi_b [4 slots][btot4][RT]   same convention
+//   rho   [2 btot4][kp]          rho chunk, transposed and interleaved: [(b,c)][a]
 struct DensSmem {
-  double a[DSTAGES][4][DAC][RT];      // phi_a(r)   [stage][slot][a][r rotated]; up rows at [0,n_up), down rows at [pad4(n_up),..)
-  double b[DSTAGES][4][DBC][RT];      // phi_b(r)   same row convention
-  double rho[DSTAGES][2 * DBC * RKP]; // rho chunk, transposed and interleaved: [(b,c)][a], row stride kp
-  unsigned long long full[DSTAGES], empty[DSTAGES];
+  unsigned char arena[DENS_ARENA];
+  unsigned long long full[DENS_NBAR], empty[DENS_NBAR];
 };
 
 void build_density_steps(int nb, const int* db, const int* isstart, const int* nsu, const int* r2c, const int* r2m,
@@ -116,7 +117,7 @@ void build_density_steps(int nb, const int* db, const int* isstart, const int* n
           d.b_row0 = isstart[iy] + b.start; d.nb_up = b.n_up; d.nb_dn = b.n_dn;
           d.rho_off = r2m[ix] + a.start + b.start * di; d.ld = di;
           d.flags = (newb ? 1 : 0) | (first ? 2 : 0) | (last ? 4 : 0);
-          d.kp = kp; d.pk_off = (int)pk; d.pad = 0;
+          d.kp = kp; d.pk_off = (int)pk; d.soff = 0; d.dep = -1; d.issue_to = 0; d.pad[0] = d.pad[1] = 0;
         }
         pk += (size_t)2 * btot4 * kp;
         newb = false;
@@ -126,6 +127,38 @@ void build_density_steps(int nb, const int* db, const int* isstart, const int* n
   }
   *nout = n;
   if (pk_elems) *pk_elems = pk;
+  if (!out) return;
+  // ---- shared-memory ring schedule: first-in first-out allocation of the operand images in the arena
+  struct Live { int k, start, end; };
+  std::vector<Live> live;   // oldest first
+  size_t head = 0;          // index of the oldest live allocation
+  int tail = 0, dep = -1, ip_prev = 0;
+  std::vector<int> ip(n);
+  for (int k = 0; k < n; k++) {
+    const DensStep& d = out[k];
+    const int atot4 = pad4(d.na_up) + pad4(d.na_dn), btot4 = pad4(d.nb_up) + pad4(d.nb_dn);
+    const int sz = (4 * atot4 + 4 * btot4) * RT * 8 + 2 * btot4 * d.kp * 8;
+    int start = tail;
+    if (start + sz > DENS_ARENA) {
+      // wrap: whatever still lives between the tail and the end of the arena is the oldest data
+      while (head < live.size() && live[head].start >= tail) dep = std::max(dep, live[head++].k);
+      start = 0;
+    }
+    while (head < live.size() && live[head].start < start + sz && live[head].end > start) dep = std::max(dep, live[head++].k);
+    dep = std::max(dep, k - DENS_NBAR);     // barrier slot reuse
+    live.push_back({k, start, start + sz});
+    tail = start + sz;
+    out[k].soff = start;
+    out[k].dep = dep;
+    // issued at the start of step ip(k) <= k: dep(k) < ip(k) so that the issuer never waits for itself
+    ip[k] = std::max(std::max(dep + 1, ip_prev), std::max(0, k - DENS_LOOKAHEAD));
+    if (ip[k] > k) throw std::runtime_error("density ring: the arena cannot hold two consecutive steps");
+    ip_prev = ip[k];
+  }
+  for (int m = 0, c = 0; m < n; m++) {
+    while (c < n && ip[c] <= m) c++;
+    out[m].issue_to = c;
+  }
 }
 
 // Repack the rho / kappa block matrices into the per-step operand images of the density kernel:
@@ -154,14 +187,14 @@ __global__ void __launch_bounds__(256) pack_rho_kernel(HamArgs g) {
 
 // K-loop of one density step for a consumer warp: 2 m-tiles (its two row slots) x NTN n-tiles
 template <int NTN>
-__device__ __forceinline__ void dens_mma(double (&C)[2][4][2], const double* __restrict__ pa, const double* __restrict__ pb, int kp,
-                                         int ksteps) {
+__device__ __forceinline__ void dens_mma(double (&C)[2][4][2], const double* __restrict__ pa, int slot_stride,
+                                         const double* __restrict__ pb, int kp, int ksteps) {
   const double* __restrict__ pbj[NTN];
 #pragma unroll
   for (int j = 0; j < NTN; j++) pbj[j] = pb + (size_t)j * 16 * kp;
 #pragma unroll 2
   for (int ks = 0; ks < ksteps; ks++) {
-    const double a0 = pa[(size_t)ks * 4 * RT], a1 = pa[(size_t)(DAC + ks * 4) * RT];
+    const double a0 = pa[(size_t)ks * 4 * RT], a1 = pa[(size_t)ks * 4 * RT + slot_stride];
 #pragma unroll
     for (int j = 0; j < NTN; j++) {
       const double bf = pbj[j][ks * 4];
@@ -188,10 +221,10 @@ __global__ void __launch_bounds__(DTHREADS, 1) density_kernel(HamArgs g) {
     return MODE == 0 ? B.phi + ((size_t)tile * NTYPE + t) * B.dqp * RT : B.phi + (size_t)(tile * 4 + t) * NTYPE * B.dqp * RT;
   };
   // shared memory starts out finite (zero): rows that a step does not overwrite only ever meet zero-filled rho padding
-  for (int i = threadIdx.x; i < (int)(offsetof(DensSmem, full) / 16); i += DTHREADS) reinterpret_cast<double2*>(smem_raw)[i] = make_double2(0.0, 0.0);
+  for (int i = threadIdx.x; i < DENS_ARENA / 16; i += DTHREADS) reinterpret_cast<double2*>(smem_raw)[i] = make_double2(0.0, 0.0);
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int s = 0; s < DSTAGES; s++) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], DCONS); }
+    for (int s = 0; s < DENS_NBAR; s++) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], DCONS); }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
@@ -206,43 +239,49 @@ __global__ void __launch_bounds__(DTHREADS, 1) density_kernel(HamArgs g) {
 
   // ---- operand movement of step k (one thread)
   auto issue = [&](int k) {
-    const int stage = k % DSTAGES, use = k / DSTAGES;
     const DensStep d = steps[k];
-    if (use > 0) mbar_wait(&sm.empty[stage], (use - 1) & 1);   // all 8 warps are done with the previous tenant
-    const int aup4 = (d.na_up + 3) & ~3, bup4 = (d.nb_up + 3) & ~3, btot4 = bup4 + ((d.nb_dn + 3) & ~3);
+    if (d.dep >= 0) mbar_wait(&sm.empty[d.dep % DENS_NBAR], (d.dep / DENS_NBAR) & 1);   // all 8 warps have left step dep
+    unsigned long long* bar = &sm.full[k % DENS_NBAR];
+    const int aup4 = (d.na_up + 3) & ~3, atot4 = aup4 + ((d.na_dn + 3) & ~3);
+    const int bup4 = (d.nb_up + 3) & ~3, btot4 = bup4 + ((d.nb_dn + 3) & ~3);
     const unsigned rho_bytes = (unsigned)(2 * btot4 * d.kp) * 8;
-    mbar_expect_tx(&sm.full[stage], 4u * (unsigned)(d.na_up + d.na_dn + d.nb_up + d.nb_dn) * RT * 8 + rho_bytes);
+    mbar_expect_tx(bar, 4u * (unsigned)(d.na_up + d.na_dn + d.nb_up + d.nb_dn) * RT * 8 + rho_bytes);
+    double* __restrict__ sa = reinterpret_cast<double*>(sm.arena + d.soff);
+    double* __restrict__ sb = sa + (size_t)4 * atot4 * RT;
 #pragma unroll
     for (int t = 0; t < 4; t++) {
       const double* __restrict__ tb = slot_base(t);
-      if (d.na_up) bulk_g2s(&sm.a[stage][t][0][0], tb + (size_t)d.a_row0 * RT, (unsigned)d.na_up * RT * 8, &sm.full[stage]);
-      if (d.na_dn) bulk_g2s(&sm.a[stage][t][aup4][0], tb + (size_t)(d.a_row0 + d.na_up) * RT, (unsigned)d.na_dn * RT * 8, &sm.full[stage]);
-      if (d.nb_up) bulk_g2s(&sm.b[stage][t][0][0], tb + (size_t)d.b_row0 * RT, (unsigned)d.nb_up * RT * 8, &sm.full[stage]);
-      if (d.nb_dn) bulk_g2s(&sm.b[stage][t][bup4][0], tb + (size_t)(d.b_row0 + d.nb_up) * RT, (unsigned)d.nb_dn * RT * 8, &sm.full[stage]);
+      if (d.na_up) bulk_g2s(sa + (size_t)t * atot4 * RT, tb + (size_t)d.a_row0 * RT, (unsigned)d.na_up * RT * 8, bar);
+      if (d.na_dn) bulk_g2s(sa + (size_t)(t * atot4 + aup4) * RT, tb + (size_t)(d.a_row0 + d.na_up) * RT, (unsigned)d.na_dn * RT * 8, bar);
+      if (d.nb_up) bulk_g2s(sb + (size_t)t * btot4 * RT, tb + (size_t)d.b_row0 * RT, (unsigned)d.nb_up * RT * 8, bar);
+      if (d.nb_dn) bulk_g2s(sb + (size_t)(t * btot4 + bup4) * RT, tb + (size_t)(d.b_row0 + d.nb_up) * RT, (unsigned)d.nb_dn * RT * 8, bar);
     }
-    bulk_g2s(&sm.rho[stage][0], pk + d.pk_off, rho_bytes, &sm.full[stage]);
+    bulk_g2s(sb + (size_t)4 * btot4 * RT, pk + d.pk_off, rho_bytes, bar);
   };
-  if (threadIdx.x == 0) {
-    if (nsteps > 0) issue(0);
-    if (nsteps > 1) issue(1);
-  }
   {
     // ---- consumers
     double C[2][4][2];
 #pragma unroll
     for (int i = 0; i < 16; i++) (&C[0][0][0])[i] = 0.0;
     DensStep dnext = nsteps > 0 ? steps[0] : DensStep{};
+    int issued = 0;
     for (int k = 0; k < nsteps; k++) {
-      const int stage = k % DSTAGES;
       const DensStep d = dnext;
       if (k + 1 < nsteps) dnext = steps[k + 1];              // descriptor of the next step: off the critical path
       const int aup4 = (d.na_up + 3) & ~3, adn4 = (d.na_dn + 3) & ~3;
       const int bup4 = (d.nb_up + 3) & ~3, btot4 = bup4 + ((d.nb_dn + 3) & ~3);
       const int ntn = max(0, ((btot4 >> 2) - nh + 1) >> 1);    // n-tiles nh + 2j < btot4/4 owned by this warp
-      // step k+2 goes into the stage of step k-1; it can only be waited for by a warp that has itself left step k-1
-      if (k + 2 < nsteps && (k + 2) % DCONS == warp && lane == 0) issue(k + 2);
+      // the issuer of step k (the duty rotates) launches the copies the host schedule releases here; each of them
+      // depends on steps < k only, which the issuing warp has itself left: no wait can involve its own progress
+      if (k % DCONS == warp && lane == 0)
+        for (int j = issued; j < d.issue_to; j++) issue(j);
+      issued = d.issue_to;
       __syncwarp();
-      mbar_wait(&sm.full[stage], (k / DSTAGES) & 1);
+      const int atot4 = aup4 + adn4;
+      const double* __restrict__ sa = reinterpret_cast<const double*>(sm.arena + d.soff);
+      const double* __restrict__ sb = sa + (size_t)4 * atot4 * RT;
+      const double* __restrict__ srho = sb + (size_t)4 * btot4 * RT;
+      mbar_wait(&sm.full[k % DENS_NBAR], (k / DENS_NBAR) & 1);
       if (ntn > 0) {
 #pragma unroll
         for (int s = 0; s < 2; s++) {
@@ -254,13 +293,13 @@ __global__ void __launch_bounds__(DTHREADS, 1) density_kernel(HamArgs g) {
           }
           // this lane's a rows are global rows a_row0 (+ n_up) + lc + 4 ks: their rotation does not depend on ks
           const int pos_a = (row + phi_rot(d.a_row0 + (s == 0 ? 0 : d.na_up) + lc)) & (RT - 1);
-          const double* __restrict__ pa = &sm.a[stage][2 * sp2][k0 + lc][pos_a];
-          const double* __restrict__ pb = &sm.rho[stage][(size_t)(nh * 8 + lr) * d.kp + k0 + lc];
+          const double* __restrict__ pa = sa + (size_t)(2 * sp2 * atot4 + k0 + lc) * RT + pos_a;
+          const double* __restrict__ pb = srho + (size_t)(nh * 8 + lr) * d.kp + k0 + lc;
           switch (ntn) {
-            case 4: dens_mma<4>(C, pa, pb, d.kp, ksteps); break;
-            case 3: dens_mma<3>(C, pa, pb, d.kp, ksteps); break;
-            case 2: dens_mma<2>(C, pa, pb, d.kp, ksteps); break;
-            default: dens_mma<1>(C, pa, pb, d.kp, ksteps); break;
+            case 4: dens_mma<4>(C, pa, atot4 * RT, pb, d.kp, ksteps); break;
+            case 3: dens_mma<3>(C, pa, atot4 * RT, pb, d.kp, ksteps); break;
+            case 2: dens_mma<2>(C, pa, atot4 * RT, pb, d.kp, ksteps); break;
+            default: dens_mma<1>(C, pa, atot4 * RT, pb, d.kp, ksteps); break;
           }
           if (d.flags & 4) {
             // epilogue: contract the product tile with phi_b(r) into the (s, s') accumulators (static indices)
@@ -273,8 +312,8 @@ __global__ void __launch_bounds__(DTHREADS, 1) density_kernel(HamArgs g) {
 #pragma unroll
                 for (int t2 = 0; t2 < NTE; t2++) {
                   double ph0, ph1;
-                  if (MODE == 0) { ph0 = ph1 = sm.b[stage][t2][bl][pos_b]; }
-                  else { ph0 = sm.b[stage][2 * sp2][bl][pos_b]; ph1 = sm.b[stage][2 * sp2 + 1][bl][pos_b]; }
+                  if (MODE == 0) { ph0 = ph1 = sb[(size_t)(t2 * btot4 + bl) * RT + pos_b]; }
+                  else { ph0 = sb[(size_t)(2 * sp2 * btot4 + bl) * RT + pos_b]; ph1 = sb[(size_t)((2 * sp2 + 1) * btot4 + bl) * RT + pos_b]; }
                   if (!dn) {
                     acc[0][s][0][t2][0] += C[0][j][0] * ph0; acc[0][s][0][t2][1] += C[0][j][1] * ph0;
                     acc[1][s][0][t2][0] += C[1][j][0] * ph1; acc[1][s][0][t2][1] += C[1][j][1] * ph1;
@@ -289,7 +328,7 @@ __global__ void __launch_bounds__(DTHREADS, 1) density_kernel(HamArgs g) {
         }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.empty[stage]);         // this warp is done with the stage
+      if (lane == 0) mbar_arrive(&sm.empty[k % DENS_NBAR]);  // this warp is done with the step's operands
     }
   }
   __syncthreads();
