@@ -42,6 +42,12 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity
                  : "=r"(ok) : "r"(a), "r"(parity) : "memory");
   } while (!ok);
 }
+__device__ __forceinline__ bool mbar_test(unsigned long long* b, unsigned parity) {   // non-blocking
+  unsigned ok;
+  asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+               : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_arrive(unsigned long long* b) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(b)) : "memory");
 }
@@ -74,6 +80,7 @@ constexpr int DTHREADS = DCONS * 32;  // exactly two warps per SM sub-partition:
 struct DensSmem {
   unsigned char arena[DENS_ARENA];
   unsigned long long full[DENS_NBAR], empty[DENS_NBAR];
+  int cursor;                 // next step to issue
 };
 
 void build_density_steps(int nb, const int* db, const int* isstart, const int* nsu, const int* r2c, const int* r2m,
@@ -225,6 +232,7 @@ __global__ void __launch_bounds__(DTHREADS, 1) density_kernel(HamArgs g) {
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int s = 0; s < DENS_NBAR; s++) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], DCONS); }
+    sm.cursor = 0;
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
@@ -238,9 +246,7 @@ __global__ void __launch_bounds__(DTHREADS, 1) density_kernel(HamArgs g) {
   for (int i = 0; i < 2 * 2 * 2 * NTE * 2; i++) (&acc[0][0][0][0][0])[i] = 0.0;
 
   // ---- operand movement of step k (one thread)
-  auto issue = [&](int k) {
-    const DensStep d = steps[k];
-    if (d.dep >= 0) mbar_wait(&sm.empty[d.dep % DENS_NBAR], (d.dep / DENS_NBAR) & 1);   // all 8 warps have left step dep
+  auto issue = [&](const DensStep& d, int k) {
     unsigned long long* bar = &sm.full[k % DENS_NBAR];
     const int aup4 = (d.na_up + 3) & ~3, atot4 = aup4 + ((d.na_dn + 3) & ~3);
     const int bup4 = (d.nb_up + 3) & ~3, btot4 = bup4 + ((d.nb_dn + 3) & ~3);
@@ -264,18 +270,24 @@ __global__ void __launch_bounds__(DTHREADS, 1) density_kernel(HamArgs g) {
 #pragma unroll
     for (int i = 0; i < 16; i++) (&C[0][0][0])[i] = 0.0;
     DensStep dnext = nsteps > 0 ? steps[0] : DensStep{};
-    int issued = 0;
     for (int k = 0; k < nsteps; k++) {
       const DensStep d = dnext;
       if (k + 1 < nsteps) dnext = steps[k + 1];              // descriptor of the next step: off the critical path
       const int aup4 = (d.na_up + 3) & ~3, adn4 = (d.na_dn + 3) & ~3;
       const int bup4 = (d.nb_up + 3) & ~3, btot4 = bup4 + ((d.nb_dn + 3) & ~3);
       const int ntn = max(0, ((btot4 >> 2) - nh + 1) >> 1);    // n-tiles nh + 2j < btot4/4 owned by this warp
-      // the issuer of step k (the duty rotates) launches the copies the host schedule releases here; each of them
-      // depends on steps < k only, which the issuing warp has itself left: no wait can involve its own progress
-      if (k % DCONS == warp && lane == 0)
-        for (int j = issued; j < d.issue_to; j++) issue(j);
-      issued = d.issue_to;
+      // Operand movement never blocks the math: at every step boundary one lane of every warp tries to advance the
+      // issue cursor.  A step is issued as soon as the step whose arena space it reuses has been released by all 8
+      // warps -- at the latest by the warp that released it last, which comes through here right afterwards.
+      if (lane == 0) {
+        for (;;) {
+          const int c = *reinterpret_cast<volatile int*>(&sm.cursor);
+          if (c >= d.issue_to) break;
+          const DensStep dc = steps[c];
+          if (dc.dep >= 0 && !mbar_test(&sm.empty[dc.dep % DENS_NBAR], (dc.dep / DENS_NBAR) & 1)) break;
+          if (atomicCAS(&sm.cursor, c, c + 1) == c) issue(dc, c);
+        }
+      }
       __syncwarp();
       const int atot4 = aup4 + adn4;
       const double* __restrict__ sa = reinterpret_cast<const double*>(sm.arena + d.soff);
