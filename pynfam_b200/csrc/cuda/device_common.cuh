@@ -22,11 +22,18 @@ constexpr int RT = 16;        // grid points per r-tile (2 DMMA m-tiles)
 constexpr int RS = 20;        // padded r-stride of a wave-function row in shared memory (bank-conflict free)
 constexpr int NTYPE = 5;      // wf, d/dr, (Lambda/r), d/dz, laplacian_all
 
-// The wave-function tables are stored tile-major, [r-tile][type][state][RT], and inside each 128-byte row the 16 grid
-// points are rotated by phi_rot(state) positions: 0, 8, 4, 12 for state & 3 = 0, 1, 2, 3.  Rows copied linearly
-// (cp.async.bulk) into shared memory are then bank-conflict free without padding for both access patterns of the
-// kernels: DMMA fragments (4 consecutive states x 4 consecutive points -> 16 different 8-byte banks) and the G build
-// (8 consecutive points of two adjacent states).
+// Padded index space: inside every block the spin-up states and the spin-down states are each padded to a multiple
+// of 4 rows (zero wave functions), so that DMMA k-steps / n-tiles never straddle a spin boundary.  pstart[block] is the
+// first padded row of a block; a chunk of consecutive padded rows is what the kernels stage in shared memory.
+// Wave-function tables (all rows in the padded space, all chunk copies linear = ONE cp.async.bulk each):
+//   phi4[r-tile][row][4 types][RT]   density (rho):   wf, d/dr, Lambda/r, d/dz
+//   phi5[r-tile][row][5 types][RT]   projection (h):  the same + laplacian
+//   phi0[4-tile group][row][4][RT]   kappa / Delta:   wf of four consecutive r-tiles
+// Inside each 128-byte (row, slot) line the 16 grid points are rotated by phi_rot(row) positions: 0, 8, 4, 12 for
+// row & 3 = 0, 1, 2, 3.  Lines copied linearly into shared memory are then bank-conflict free without padding for
+// both access patterns of the kernels: DMMA fragments (4 consecutive rows x 4 consecutive points -> 16 different
+// 8-byte banks) and the G build (8 consecutive points of two adjacent rows).  Chunks start at multiples of 4 rows, so
+// the rotation of a lane's rows is a function of its lane index alone.
 __host__ __device__ __forceinline__ int phi_rot(int state) { return ((state & 1) << 3) | ((state & 2) << 1); }
 
 // FP64 tensor-core MMA: D(8x8) += A(8x4, row) * B(4x8, col).
@@ -60,7 +67,11 @@ struct DevBasis {
   const int* db;        // [nb]
   const int* isstart;   // [nb] 0-based first state of block
   const int* nsu;       // [nb] number of spin-up states (they come first inside a block)
-  const double* phi;    // [ntiles][NTYPE][dqp][RT] tile-major wave-function tables
+  const int* pstart;    // [nb] first row of the block in the padded index space
+  int dqp_p;            // rows of the padded index space
+  const double* phi4;   // wave-function tables, see above
+  const double* phi5;
+  const double* phi0;
   const double* wdcori; // [nghl]
   const double* crho;   // [nghl]
   const double* cs;

@@ -47,8 +47,8 @@ __host__ __device__ inline size_t pf_elems(int ntiles) { return (size_t)2 * ((nt
 // Rows / columns of a block are spin-sorted (up first).  A chunk may straddle the spin boundary when the padded
 // segments fit (small blocks): the step then runs up to four (s, s') sub-passes on one staged operand set.
 struct DensStep {
-  int a_row0, na_up, na_dn;   // first basis state (global index) of the contraction chunk; rows per spin
-  int b_row0, nb_up, nb_dn;   // first column state (global index); columns per spin
+  int a_row0, na_up, na_dn;   // first row of the contraction chunk in the padded index space; valid rows per spin
+  int b_row0, nb_up, nb_dn;   // first row of the column chunk in the padded index space; valid columns per spin
   int rho_off, ld;            // element offset of (a chunk start, b chunk start) inside the block matrix, leading dim
   int flags;                  // bit0: new b-chunk; bit1: first a-chunk (zero C); bit2: last a-chunk (epilogue)
   int kp;                     // row stride of the packed chunk: >= padded a-count, kp % 8 == 4 (bank-conflict free)
@@ -99,7 +99,7 @@ struct ProjPlan {                 // output tiles of the grid->HO projection
 
 void launch_density(const HamArgs& a, cudaStream_t stream);
 // host helper: flatten a block structure into density pipeline steps
-void build_density_steps(int nb, const int* db, const int* isstart, const int* nsu, const int* r2c, const int* r2m,
+void build_density_steps(int nb, const int* db, const int* pstart, const int* nsu, const int* r2c, const int* r2m,
                          DensStep* out, int* nout, size_t* pk_elems);  // out may be null to count
 void launch_fields(const HamArgs& a, cudaStream_t stream);
 void launch_projection(const HamArgs& a, const ProjPlan& pp, cudaStream_t stream);

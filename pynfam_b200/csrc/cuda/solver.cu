@@ -50,11 +50,12 @@ struct pnfam_b200_ctx {
   int device = 0;
   int nb = 0, dqp = 0, nghl = 0, ntiles = 0;
   size_t dmat = 0;
-  std::vector<int> db, isstart, nsu;
+  std::vector<int> db, isstart, nsu, pstart;
+  int dqp_p = 0;                  // rows of the spin-segment-padded index space (device_common.cuh)
   std::vector<double> Ep, En, qp_fp, qp_fn;
   bool use_diag = false;
-  DBuf<int> d_db, d_isstart, d_nsu;
-  DBuf<double> d_phi, d_wdcori, d_crho, d_cs, d_cpair, d_cspair;
+  DBuf<int> d_db, d_isstart, d_nsu, d_pstart;
+  DBuf<double> d_phi4, d_phi5, d_phi0, d_wdcori, d_crho, d_cs, d_cpair, d_cspair;
   DBuf<double> d_Up, d_Vp, d_Un, d_Vn;
   DevBasis basis{};
   cudaStream_t stream = nullptr;
@@ -97,24 +98,45 @@ extern "C" int pnfam_b200_ctx_create(const pnfam_b200_model* m, int device, pnfa
     c->use_diag = m->qp_fp != nullptr && m->qp_fn != nullptr;
     if (c->use_diag) { c->qp_fp.assign(m->qp_fp, m->qp_fp + m->dqp); c->qp_fn.assign(m->qp_fn, m->qp_fn + m->dqp); }
     c->d_db.upload(c->db); c->d_isstart.upload(c->isstart); c->d_nsu.upload(c->nsu);
-    // tile-major wave-function tables: phi[tile][type][state][RT], zero-padded to a multiple of 4 tiles.
-    // Inside a 128-byte row the 16 grid points are rotated by phi_rot(state) positions (device_common.cuh).
+    // ---- wave-function tables in the layouts the kernels copy linearly (device_common.cuh)
     {
+      auto pad4 = [](int x) { return (x + 3) & ~3; };
+      c->pstart.resize(m->nb);
+      std::vector<int> p2s;                                  // padded row -> state (-1: zero padding row)
+      for (int i = 0; i < m->nb; i++) {
+        c->pstart[i] = (int)p2s.size();
+        for (int l = 0; l < pad4(c->nsu[i]); l++) p2s.push_back(l < c->nsu[i] ? c->isstart[i] + l : -1);
+        for (int l = 0; l < pad4(c->db[i] - c->nsu[i]); l++) p2s.push_back(l < c->db[i] - c->nsu[i] ? c->isstart[i] + c->nsu[i] + l : -1);
+      }
+      c->dqp_p = (int)p2s.size();
+      c->d_pstart.upload(c->pstart);
       const double* tab[NTYPE] = {m->wf, m->wfdr, m->wfdp, m->wfdz, m->wfd2_all};
-      const int dqp = c->dqp, nghl = c->nghl, ntiles = c->ntiles, ntiles4 = (c->ntiles + 3) & ~3;
-      std::vector<double> h((size_t)ntiles4 * NTYPE * dqp * RT, 0.0);
-#pragma omp parallel for collapse(2) schedule(static)
-      for (int tile = 0; tile < ntiles; tile++)
-        for (int t = 0; t < NTYPE; t++) {
-          double* dst = &h[((size_t)tile * NTYPE + t) * dqp * RT];
-          const int r0 = tile * RT, nr = std::min(RT, nghl - r0);
-          for (int s = 0; s < dqp; s++) {
-            const double* src = tab[t] + (size_t)s * nghl + r0;
-            const int rot = phi_rot(s);
-            for (int r = 0; r < nr; r++) dst[(size_t)s * RT + ((r + rot) & (RT - 1))] = src[r];
+      const int dqp_p = c->dqp_p, nghl = c->nghl, ntiles = c->ntiles, nsuper = (c->ntiles + 3) / 4;
+      const size_t tail = (size_t)8 * NTYPE * RT;              // chunk copies may run a few rows past the last block
+      std::vector<double> h5((size_t)ntiles * dqp_p * NTYPE * RT + tail, 0.0), h4((size_t)ntiles * dqp_p * 4 * RT + tail, 0.0),
+          h0((size_t)nsuper * dqp_p * 4 * RT + tail, 0.0);
+#pragma omp parallel for schedule(static)
+      for (int tile = 0; tile < ntiles; tile++) {
+        const int r0 = tile * RT, nr = std::min(RT, nghl - r0);
+        for (int pr = 0; pr < dqp_p; pr++) {
+          const int st = p2s[pr];
+          if (st < 0) continue;
+          const int rot = phi_rot(pr);
+          double* d5 = &h5[((size_t)tile * dqp_p + pr) * NTYPE * RT];
+          double* d4 = &h4[((size_t)tile * dqp_p + pr) * 4 * RT];
+          double* d0 = &h0[(((size_t)(tile >> 2) * dqp_p + pr) * 4 + (tile & 3)) * RT];
+          for (int t = 0; t < NTYPE; t++) {
+            const double* src = tab[t] + (size_t)st * nghl + r0;
+            for (int r = 0; r < nr; r++) {
+              const int pos = (r + rot) & (RT - 1);
+              d5[t * RT + pos] = src[r];
+              if (t < 4) d4[t * RT + pos] = src[r];
+              if (t == 0) d0[pos] = src[r];
+            }
           }
         }
-      c->d_phi.upload(h);
+      }
+      c->d_phi5.upload(h5); c->d_phi4.upload(h4); c->d_phi0.upload(h0);
     }
     auto up = [&](DBuf<double>& d, const double* p, size_t n) { d.upload(std::vector<double>(p, p + n)); };
     up(c->d_wdcori, m->wdcori, m->nghl); up(c->d_crho, m->crho, m->nghl); up(c->d_cs, m->cs, m->nghl);
@@ -122,7 +144,8 @@ extern "C" int pnfam_b200_ctx_create(const pnfam_b200_model* m, int device, pnfa
     up(c->d_Up, m->Up, c->dmat); up(c->d_Vp, m->Vp, c->dmat); up(c->d_Un, m->Un, c->dmat); up(c->d_Vn, m->Vn, c->dmat);
     DevBasis& B = c->basis;
     B.nb = c->nb; B.dqp = c->dqp; B.nghl = c->nghl; B.ntiles = c->ntiles;
-    B.db = c->d_db.p; B.isstart = c->d_isstart.p; B.nsu = c->d_nsu.p; B.phi = c->d_phi.p;
+    B.db = c->d_db.p; B.isstart = c->d_isstart.p; B.nsu = c->d_nsu.p;
+    B.pstart = c->d_pstart.p; B.dqp_p = c->dqp_p; B.phi4 = c->d_phi4.p; B.phi5 = c->d_phi5.p; B.phi0 = c->d_phi0.p;
     B.wdcori = c->d_wdcori.p; B.crho = c->d_crho.p; B.cs = c->d_cs.p; B.cpair = c->d_cpair.p; B.cspair = c->d_cspair.p;
     B.cdrho = m->cdrho; B.ctau = m->ctau; B.ctj0 = m->ctj0; B.ctj1 = m->ctj1; B.ctj2 = m->ctj2; B.crdj = m->crdj;
     B.cds = m->cds; B.ct = m->ct; B.cj = m->cj; B.cgs = m->cgs; B.cf = m->cf; B.csdj = m->csdj;
@@ -163,9 +186,9 @@ struct OperatorDev {
 // returns the number of doubles of the packed rho chunks of this step list
 size_t upload_density_steps(const pnfam_b200_ctx& c, const BlockStruct& st, DBuf<DensStep>& buf, int& n) {
   size_t pk = 0;
-  build_density_steps(c.nb, c.db.data(), c.isstart.data(), c.nsu.data(), st.r2c.data(), st.r2m.data(), nullptr, &n, &pk);
+  build_density_steps(c.nb, c.db.data(), c.pstart.data(), c.nsu.data(), st.r2c.data(), st.r2m.data(), nullptr, &n, &pk);
   std::vector<DensStep> h(std::max(n, 1));
-  build_density_steps(c.nb, c.db.data(), c.isstart.data(), c.nsu.data(), st.r2c.data(), st.r2m.data(), h.data(), &n, &pk);
+  build_density_steps(c.nb, c.db.data(), c.pstart.data(), c.nsu.data(), st.r2c.data(), st.r2m.data(), h.data(), &n, &pk);
   buf.upload(h);
   return pk;
 }
@@ -217,11 +240,14 @@ void build_proj_tiles(const pnfam_b200_ctx& c, const BlockStruct st[2], std::vec
     for (int ix = 0; ix < c.nb; ix++) {
       const int iy = st[q].r2c[ix];
       if (iy < 0) continue;
+      // chunks in the padded index space of the blocks: a-chunks stay inside one spin segment
+      auto pad4 = [](int x) { return (x + 3) & ~3; };
       const int di = c.db[ix], dj = c.db[iy], nu = c.nsu[ix];
+      const int pj = pad4(c.nsu[iy]) + pad4(dj - c.nsu[iy]);
       for (int s = 0; s < 2; s++) {
-        const int lo = s == 0 ? 0 : nu, hi = s == 0 ? nu : di;
+        const int lo = s == 0 ? 0 : pad4(nu), hi = s == 0 ? pad4(nu) : pad4(nu) + pad4(di - nu);
         for (int a0 = lo; a0 < hi; a0 += 48)
-          for (int b0 = 0; b0 < dj; b0 += 32) tiles.push_back(make_int4(ix, a0, b0, 0));
+          for (int b0 = 0; b0 < pj; b0 += 32) tiles.push_back(make_int4(ix, a0, b0, 0));
       }
     }
     ntiles[q] = (int)tiles.size() - off[q];

@@ -15,6 +15,6 @@ ctx = gpu.Context(p)
 for rep in range(2):
     r = ctx.solve(p, omegas=oms, max_iter=iters)
 st = r["stats"]
-print("PROJ_DEBUG=%s points %d: density %.3f ms/launch, projection %.3f ms/launch, device total %.1f ms" % (
-    os.environ.get("PNFAM_B200_PROJ_DEBUG", "0"), npts, 1e3 * st["seconds_density"] / max(1, st["launches_density"]),
+print("PROJ_DEBUG=%s DENS_DEBUG=%s points %d: density %.3f ms/launch, projection %.3f ms/launch, device total %.1f ms" % (
+    os.environ.get("PNFAM_B200_PROJ_DEBUG", "0"), os.environ.get("PNFAM_B200_DENS_DEBUG", "0"), npts, 1e3 * st["seconds_density"] / max(1, st["launches_density"]),
     1e3 * st["seconds_projection"] / max(1, st["launches_projection"]), 1e3 * st["seconds_device"]))
