@@ -672,13 +672,12 @@ void launch_fields(const HamArgs& a, cudaStream_t stream) {
 // ================================================================================================
 constexpr int GS = 68;    // padded row stride of G (64 interleaved (b,c) columns): conflict-free B-fragment loads
 constexpr int ACP = 48;   // rows a per output tile = up to 6 DMMA m-tiles
-// warp-specialised: 4 consumer warps run DMMA, one per SM sub-partition (the FP64 tensor pipe is one DMMA per
-// 16 clk per sub-partition and one warp with >= 2 independent accumulators saturates it: scripts/dmma_probe.cu).
-// A consumer owns n-tiles w and w+4 and all m-tiles: 8 fragment loads feed 12 DMMAs, which keeps the shared-memory
-// pipe (the second limiter of this kernel) at about a third of its bandwidth.
+// warp-specialised: 8 consumer warps run DMMA, two per SM sub-partition (the FP64 tensor pipe is one DMMA per
+// 16 clk per sub-partition, scripts/dmma_probe.cu; the second warp covers the fragment-load latency of the first).
+// Consumer w owns n-tiles (w&3) and (w&3)+4 and one half of the m-tiles: 5 fragment loads feed 6 DMMAs.
 // 8 producer warps build G; ONE producer thread moves all operands with linear bulk copies (cp.async.bulk)
 // that complete on mbarriers.
-constexpr int PCONS = 4, PPROD = 8;
+constexpr int PCONS = 8, PPROD = 8;
 constexpr int PTHREADS = (PCONS + PPROD) * 32;
 
 // MODE 0 (h):     the NS = 5 k-slabs of one iteration are the 5 derivative types of ONE r-tile; G mixes types through mf.
@@ -697,7 +696,7 @@ struct ProjSmem {
 // DMMA sequence of one iteration for a consumer warp: NN n-tiles (8 columns each, 32 columns apart) x MT m-tiles
 // of 8 rows, straight-line code
 template <int NS, int MT, int NN>
-__device__ __forceinline__ void proj_mma(double (&C)[6][2][2], const double* __restrict__ pa, const double* __restrict__ pg,
+__device__ __forceinline__ void proj_mma(double (&C)[3][2][2], const double* __restrict__ pa, const double* __restrict__ pg,
                                          const int (&kp)[RT / 4]) {
 #pragma unroll
   for (int t = 0; t < NS; t++)
@@ -715,12 +714,9 @@ __device__ __forceinline__ void proj_mma(double (&C)[6][2][2], const double* __r
     }
 }
 template <int NS, int NN>
-__device__ __forceinline__ void proj_mma_mt(int mt, double (&C)[6][2][2], const double* __restrict__ pa, const double* __restrict__ pg,
+__device__ __forceinline__ void proj_mma_mt(int mt, double (&C)[3][2][2], const double* __restrict__ pa, const double* __restrict__ pg,
                                             const int (&kp)[RT / 4]) {
   switch (mt) {
-    case 6: proj_mma<NS, 6, NN>(C, pa, pg, kp); break;
-    case 5: proj_mma<NS, 5, NN>(C, pa, pg, kp); break;
-    case 4: proj_mma<NS, 4, NN>(C, pa, pg, kp); break;
     case 3: proj_mma<NS, 3, NN>(C, pa, pg, kp); break;
     case 2: proj_mma<NS, 2, NN>(C, pa, pg, kp); break;
     default: proj_mma<NS, 1, NN>(C, pa, pg, kp); break;
@@ -833,12 +829,14 @@ __global__ void __launch_bounds__(PTHREADS, 1) projection_kernel(HamArgs g, cons
     }
   }
   __syncthreads();
-  double C[6][2][2];
+  double C[3][2][2];
 #pragma unroll
-  for (int i = 0; i < 6; i++) C[i][0][0] = C[i][0][1] = C[i][1][0] = C[i][1][1] = 0.0;
-  const int mt = nac8 >> 3;                              // m-tiles of this output tile (1..6)
-  const bool cons_active = !producer && warp * 4 < nbc4; // consumer warp w owns n-tiles w and w + 4
-  const bool cons_two = (warp + 4) * 4 < nbc4;
+  for (int i = 0; i < 3; i++) C[i][0][0] = C[i][0][1] = C[i][1][0] = C[i][1][1] = 0.0;
+  // consumer warp w: n-tiles nw and nw + 4, m-tiles [m_off, m_off + mt) -- its half of the 1..6 m-tiles of the tile
+  const int nw = warp & 3, mt_all = nac8 >> 3, mt_lo = (mt_all + 1) >> 1;
+  const int m_off = (warp >> 2) & 1 ? mt_lo : 0, mt = (warp >> 2) & 1 ? mt_all - mt_lo : mt_lo;
+  const bool cons_active = !producer && nw * 4 < nbc4 && mt > 0;
+  const bool cons_two = (nw + 4) * 4 < nbc4;
   int kp[RT / 4];                                        // rotated position of grid point 4*ks + lc in this lane's a rows
 #pragma unroll
   for (int ks = 0; ks < RT / 4; ks++) kp[ks] = (4 * ks + lc + phi_rot(lr)) & (RT - 1);
@@ -862,8 +860,8 @@ __global__ void __launch_bounds__(PTHREADS, 1) projection_kernel(HamArgs g, cons
       }
     } else if (cons_active) {
       mbar_wait(&sm.barA[stage], (i >> 1) & 1);
-      const double* __restrict__ pa = &sm.a[stage][lr][0][0];
-      const double* __restrict__ pg = &sm.g[stage][0][lc][warp * 8 + lr];
+      const double* __restrict__ pa = &sm.a[stage][m_off * 8 + lr][0][0];
+      const double* __restrict__ pg = &sm.g[stage][0][lc][nw * 8 + lr];
       if (dbg & 1) {
       } else if (cons_two) proj_mma_mt<NS, 2>(mt, C, pa, pg, kp);
       else proj_mma_mt<NS, 1>(mt, C, pa, pg, kp);
@@ -878,13 +876,14 @@ __global__ void __launch_bounds__(PTHREADS, 1) projection_kernel(HamArgs g, cons
 #pragma unroll
     for (int n = 0; n < 2; n++) {
       // padded column -> column of the block matrix
-      const int bp = b0 + (warp + 4 * n) * 4 + lc;
+      const int bp = b0 + (nw + 4 * n) * 4 + lc;
       const int bcol = bp < puj ? bp : nuj + (bp - puj);
-      const bool bok = (warp + 4 * n) * 4 < nbc4 && (bp < puj ? bp < nuj : bcol < dj);
+      const bool bok = (nw + 4 * n) * 4 < nbc4 && (bp < puj ? bp < nuj : bcol < dj);
       if (bok) {
 #pragma unroll
-        for (int i = 0; i < 6; i++) {
-          const int ap = a0 + i * 8 + lr;
+        for (int i = 0; i < 3; i++) {
+          if (i >= mt) break;
+          const int ap = a0 + (m_off + i) * 8 + lr;
           const int arow = sa == 0 ? ap : nui + (ap - pui);
           if (ap < a_hi && (sa == 0 ? ap < nui : arow < di)) {
             const size_t e = off + (size_t)arow + (size_t)bcol * di;

@@ -42,6 +42,24 @@ struct DevStructBuf {
   DevBlockStruct view() const { return {r2c.p, r2m.p}; }
 };
 
+// Re-layout of the reference's (nghl, dqp) wave-function tables into the padded, slot-interleaved, rotated tables
+// of device_common.cuh.  One thread per (grid point of the r-tile, padded row).
+__global__ void build_tables_kernel(const double* __restrict__ raw, size_t nraw, const int* __restrict__ p2s, int dqp_p, int nghl,
+                                    double* __restrict__ phi5, double* __restrict__ phi4, double* __restrict__ phi0) {
+  const int tile = blockIdx.x, pr = blockIdx.y * blockDim.y + threadIdx.y, rr = threadIdx.x;
+  if (pr >= dqp_p) return;
+  const int st = p2s[pr], r = tile * RT + rr;
+  if (st < 0 || r >= nghl) return;                          // padding stays zero
+  const int pos = (rr + phi_rot(pr)) & (RT - 1);
+#pragma unroll
+  for (int t = 0; t < NTYPE; t++) {
+    const double v = raw[(size_t)t * nraw + (size_t)st * nghl + r];
+    phi5[(((size_t)tile * dqp_p + pr) * NTYPE + t) * RT + pos] = v;
+    if (t < 4) phi4[(((size_t)tile * dqp_p + pr) * 4 + t) * RT + pos] = v;
+    if (t == 0) phi0[(((size_t)(tile >> 2) * dqp_p + pr) * 4 + (tile & 3)) * RT + pos] = v;
+  }
+}
+
 }  // namespace pnfam
 
 using namespace pnfam;
@@ -110,33 +128,23 @@ extern "C" int pnfam_b200_ctx_create(const pnfam_b200_model* m, int device, pnfa
       }
       c->dqp_p = (int)p2s.size();
       c->d_pstart.upload(c->pstart);
+      // the reference's (nghl, dqp) tables go up as they are; the re-layout runs on the device
       const double* tab[NTYPE] = {m->wf, m->wfdr, m->wfdp, m->wfdz, m->wfd2_all};
-      const int dqp_p = c->dqp_p, nghl = c->nghl, ntiles = c->ntiles, nsuper = (c->ntiles + 3) / 4;
+      const size_t nraw = (size_t)c->dqp * c->nghl;
+      DBuf<double> raw;
+      raw.alloc(NTYPE * nraw);
+      for (int t = 0; t < NTYPE; t++) PNFAM_CUDA_CHECK(cudaMemcpy(raw.p + t * nraw, tab[t], nraw * sizeof(double), cudaMemcpyHostToDevice));
+      DBuf<int> d_p2s;
+      d_p2s.upload(p2s);
+      const int nsuper = (c->ntiles + 3) / 4;
       const size_t tail = (size_t)8 * NTYPE * RT;              // chunk copies may run a few rows past the last block
-      std::vector<double> h5((size_t)ntiles * dqp_p * NTYPE * RT + tail, 0.0), h4((size_t)ntiles * dqp_p * 4 * RT + tail, 0.0),
-          h0((size_t)nsuper * dqp_p * 4 * RT + tail, 0.0);
-#pragma omp parallel for schedule(static)
-      for (int tile = 0; tile < ntiles; tile++) {
-        const int r0 = tile * RT, nr = std::min(RT, nghl - r0);
-        for (int pr = 0; pr < dqp_p; pr++) {
-          const int st = p2s[pr];
-          if (st < 0) continue;
-          const int rot = phi_rot(pr);
-          double* d5 = &h5[((size_t)tile * dqp_p + pr) * NTYPE * RT];
-          double* d4 = &h4[((size_t)tile * dqp_p + pr) * 4 * RT];
-          double* d0 = &h0[(((size_t)(tile >> 2) * dqp_p + pr) * 4 + (tile & 3)) * RT];
-          for (int t = 0; t < NTYPE; t++) {
-            const double* src = tab[t] + (size_t)st * nghl + r0;
-            for (int r = 0; r < nr; r++) {
-              const int pos = (r + rot) & (RT - 1);
-              d5[t * RT + pos] = src[r];
-              if (t < 4) d4[t * RT + pos] = src[r];
-              if (t == 0) d0[pos] = src[r];
-            }
-          }
-        }
-      }
-      c->d_phi5.upload(h5); c->d_phi4.upload(h4); c->d_phi0.upload(h0);
+      c->d_phi5.alloc((size_t)c->ntiles * c->dqp_p * NTYPE * RT + tail); c->d_phi4.alloc((size_t)c->ntiles * c->dqp_p * 4 * RT + tail);
+      c->d_phi0.alloc((size_t)nsuper * c->dqp_p * 4 * RT + tail);
+      c->d_phi5.zero(); c->d_phi4.zero(); c->d_phi0.zero();
+      build_tables_kernel<<<dim3(c->ntiles, (c->dqp_p + 7) / 8), dim3(RT, 8)>>>(raw.p, nraw, d_p2s.p, c->dqp_p, c->nghl, c->d_phi5.p, c->d_phi4.p,
+                                                                           c->d_phi0.p);
+      PNFAM_CUDA_CHECK(cudaGetLastError());
+      PNFAM_CUDA_CHECK(cudaDeviceSynchronize());
     }
     auto up = [&](DBuf<double>& d, const double* p, size_t n) { d.upload(std::vector<double>(p, p + n)); };
     up(c->d_wdcori, m->wdcori, m->nghl); up(c->d_crho, m->crho, m->nghl); up(c->d_cs, m->cs, m->nghl);
