@@ -81,6 +81,7 @@ struct DensSmem {
   unsigned char arena[DENS_ARENA];
   unsigned long long full[DENS_NBAR], empty[DENS_NBAR];
   int cursor;                 // next step to issue
+  short dep[DENS_MAXSTEPS];   // DensStep::dep of every step (the issue loop must not wait for global memory)
 };
 
 void build_density_steps(int nb, const int* db, const int* pstart, const int* nsu, const int* r2c, const int* r2m,
@@ -159,15 +160,15 @@ void build_density_steps(int nb, const int* db, const int* pstart, const int* ns
     tail = start + sz;
     out[k].soff = start;
     out[k].dep = dep;
-    // issued at the start of step ip(k) <= k: dep(k) < ip(k) so that the issuer never waits for itself
+    // issued when the math reaches step ip(k) <= k (in order, at most DENS_LOOKAHEAD steps ahead)
     ip[k] = std::max(std::max(dep + 1, ip_prev), std::max(0, k - DENS_LOOKAHEAD));
-    if (ip[k] > k) throw std::runtime_error("density ring: the arena cannot hold two consecutive steps");
     ip_prev = ip[k];
   }
   for (int m = 0, c = 0; m < n; m++) {
     while (c < n && ip[c] <= m) c++;
     out[m].issue_to = c;
   }
+  if (n > DENS_MAXSTEPS) throw std::runtime_error("density: more steps than DENS_MAXSTEPS");
 }
 
 // Repack the rho / kappa block matrices into the per-step operand images of the density kernel:
@@ -233,6 +234,7 @@ __global__ void __launch_bounds__(DTHREADS, 1) density_kernel(HamArgs g, int dbg
     sm.cursor = 0;
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
+  for (int k = threadIdx.x; k < nsteps; k += DTHREADS) sm.dep[k] = (short)steps[k].dep;
   __syncthreads();
 
   // consumer role: row half rh (grid points rh*8 .. rh*8+7), slots 2*sp2 and 2*sp2+1, n-tiles nh, nh+2, nh+4, nh+6
@@ -256,6 +258,19 @@ __global__ void __launch_bounds__(DTHREADS, 1) density_kernel(HamArgs g, int dbg
     bulk_g2s(dst + a_bytes, tab + (size_t)d.b_row0 * 4 * RT, b_bytes, bar);
     bulk_g2s(dst + a_bytes + b_bytes, pk + d.pk_off, rho_bytes, bar);
   };
+  // Operand movement never blocks the math.  A step can be issued once the step whose arena space it reuses (dep) has
+  // been released by all 8 warps.  At every step boundary one lane of every warp tries to advance the issue cursor up
+  // to the step the host schedule allows here (shared-memory reads only unless it wins a step) -- at the latest the
+  // warp that released `dep` last does it when it comes through here right afterwards.
+  auto try_issue = [&](int issue_to) {
+    for (;;) {
+      const int c = *reinterpret_cast<volatile int*>(&sm.cursor);
+      if (c >= issue_to) break;
+      const int dp = sm.dep[c];
+      if (dp >= 0 && !mbar_test(&sm.empty[dp % DENS_NBAR], (dp / DENS_NBAR) & 1)) break;
+      if (atomicCAS(&sm.cursor, c, c + 1) == c) issue(steps[c], c);
+    }
+  };
   {
     // ---- consumers
     double C[2][4][2];
@@ -268,19 +283,9 @@ __global__ void __launch_bounds__(DTHREADS, 1) density_kernel(HamArgs g, int dbg
       const int aup4 = (d.na_up + 3) & ~3, adn4 = (d.na_dn + 3) & ~3;
       const int bup4 = (d.nb_up + 3) & ~3, btot4 = bup4 + ((d.nb_dn + 3) & ~3);
       const int ntn = max(0, ((btot4 >> 2) - nh + 1) >> 1);    // n-tiles nh + 2j < btot4/4 owned by this warp
-      // Operand movement never blocks the math: at every step boundary one lane of every warp tries to advance the
-      // issue cursor.  A step is issued as soon as the step whose arena space it reuses has been released by all 8
-      // warps -- at the latest by the warp that released it last, which comes through here right afterwards.
-      if (lane == 0 && !(dbg & 4)) {
-        for (;;) {
-          const int c = *reinterpret_cast<volatile int*>(&sm.cursor);
-          if (c >= d.issue_to) break;
-          const DensStep dc = steps[c];
-          if (dc.dep >= 0 && !mbar_test(&sm.empty[dc.dep % DENS_NBAR], (dc.dep / DENS_NBAR) & 1)) break;
-          if (atomicCAS(&sm.cursor, c, c + 1) == c) issue(dc, c);
-        }
-      }
+      if (lane == 0 && !(dbg & 4)) try_issue(d.issue_to);
       __syncwarp();
+
       const int atot4 = aup4 + adn4;
       const double* __restrict__ sa = reinterpret_cast<const double*>(sm.arena + d.soff);
       const double* __restrict__ sb = sa + (size_t)4 * atot4 * RT;

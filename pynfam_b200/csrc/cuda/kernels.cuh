@@ -55,15 +55,16 @@ struct DensStep {
   int pk_off;                 // offset (doubles) of the packed chunk [n = (b,c)][k = a] in the packed rho array
   // shared-memory ring schedule, simulated on the host (build_density_steps): the operands of a step occupy
   // [soff, soff + size) of the arena; they may be written once step `dep` has been released by all warps; when the
-  // math reaches this step, steps [.., issue_to) must have been issued.
+  // math reaches this step, steps [.., issue_to) are due.
   int soff;                   // byte offset of the step's operand image in the arena
   int dep;                    // last step whose arena space / barrier slot this step reuses (-1: none)
-  int issue_to;               // number of steps issued once the issuer of this step has run
+  int issue_to;               // steps [.., issue_to) are issued when the math reaches this step
   int pad[2];
 };
 constexpr int DENS_ARENA = 220 * 1024;   // bytes of shared memory cycled through by the density kernel
 constexpr int DENS_NBAR = 16;            // mbarrier slots (step k uses slot k % DENS_NBAR)
 constexpr int DENS_LOOKAHEAD = 12;       // at most this many steps are in flight ahead of the math
+constexpr int DENS_MAXSTEPS = 2048;      // steps of one density pass (their dependency list lives in shared memory)
 constexpr int DENS_AC = 48;   // contraction chunk
 constexpr int DENS_BC = 32;   // column chunk
 
