@@ -106,19 +106,24 @@ void build_density_steps(int nb, const int* db, const int* pstart, const int* ns
     const int di = db[ix], dj = db[iy];
     chunks(di, nsu[ix], DENS_AC, ac);
     chunks(dj, nsu[iy], DENS_BC, bc);
-    for (const Chunk& b : bc) {
-      bool newb = true;
-      // a-chunks of one spin segment accumulate into the same C: they must be consecutive -> order: all chunks
-      // (merged chunks are complete on their own; split segments come up-chunks first, then down-chunks)
-      for (size_t ia = 0; ia < ac.size(); ia++) {
+    // A spin segment longer than one chunk accumulates C over its a-chunks: they must then be consecutive steps
+    // (b outer, a inner).  Otherwise every step is complete on its own and a is the OUTER loop: the staged phi_a
+    // image is shared by the consecutive steps of all b-chunks (flag bit0 marks the step that brings it in).
+    const bool a_multi = nsu[ix] > DENS_AC || di - nsu[ix] > DENS_AC;
+    const size_t n_outer = a_multi ? bc.size() : ac.size(), n_inner = a_multi ? ac.size() : bc.size();
+    for (size_t io = 0; io < n_outer; io++)
+      for (size_t ii = 0; ii < n_inner; ii++) {
+        const size_t ia = a_multi ? ii : io;
         const Chunk& a = ac[ia];
+        const Chunk& b = bc[a_multi ? io : ii];
         const bool merged = a.n_up > 0 && a.n_dn > 0;
         bool first = true, last = true;
-        if (!merged) {
+        if (a_multi && !merged) {
           const bool up = a.n_up > 0;
           first = ia == 0 || (up ? ac[ia - 1].n_up == 0 : ac[ia - 1].n_dn == 0) || (ac[ia - 1].n_up > 0 && ac[ia - 1].n_dn > 0);
           last = ia + 1 == ac.size() || (up ? ac[ia + 1].n_up == 0 : ac[ia + 1].n_dn == 0);
         }
+        const bool newa = a_multi || ii == 0;
         const int atot4 = pad4(a.n_up) + pad4(a.n_dn), btot4 = pad4(b.n_up) + pad4(b.n_dn);
         const int kp = (atot4 & 7) == 4 ? atot4 : atot4 + 4;
         if (out) {
@@ -126,14 +131,12 @@ void build_density_steps(int nb, const int* db, const int* pstart, const int* ns
           d.a_row0 = prow(ix, a.start); d.na_up = a.n_up; d.na_dn = a.n_dn;
           d.b_row0 = prow(iy, b.start); d.nb_up = b.n_up; d.nb_dn = b.n_dn;
           d.rho_off = r2m[ix] + a.start + b.start * di; d.ld = di;
-          d.flags = (newb ? 1 : 0) | (first ? 2 : 0) | (last ? 4 : 0);
-          d.kp = kp; d.pk_off = (int)pk; d.soff = 0; d.dep = -1; d.issue_to = 0; d.pad[0] = d.pad[1] = 0;
+          d.flags = (newa ? 1 : 0) | (first ? 2 : 0) | (last ? 4 : 0);
+          d.kp = kp; d.pk_off = (int)pk; d.soff = 0; d.aoff = 0; d.dep = -1; d.issue_to = 0; d.pad = 0;
         }
         pk += (size_t)2 * btot4 * kp;
-        newb = false;
         n++;
       }
-    }
   }
   *nout = n;
   if (pk_elems) *pk_elems = pk;
@@ -142,12 +145,14 @@ void build_density_steps(int nb, const int* db, const int* pstart, const int* ns
   struct Live { int k, start, end; };
   std::vector<Live> live;   // oldest first
   size_t head = 0;          // index of the oldest live allocation
-  int tail = 0, dep = -1, ip_prev = 0;
+  int tail = 0, dep = -1, ip_prev = 0, aoff = 0;
   std::vector<int> ip(n);
   for (int k = 0; k < n; k++) {
     const DensStep& d = out[k];
     const int atot4 = pad4(d.na_up) + pad4(d.na_dn), btot4 = pad4(d.nb_up) + pad4(d.nb_dn);
-    const int sz = (4 * atot4 + 4 * btot4) * RT * 8 + 2 * btot4 * d.kp * 8;
+    const bool newa = d.flags & 1;
+    const int a_bytes = newa ? 4 * atot4 * RT * 8 : 0;
+    const int sz = a_bytes + 4 * btot4 * RT * 8 + 2 * btot4 * d.kp * 8;
     int start = tail;
     if (start + sz > DENS_ARENA) {
       // wrap: whatever still lives between the tail and the end of the arena is the oldest data
@@ -156,9 +161,17 @@ void build_density_steps(int nb, const int* db, const int* pstart, const int* ns
     }
     while (head < live.size() && live[head].start < start + sz && live[head].end > start) dep = std::max(dep, live[head++].k);
     dep = std::max(dep, k - DENS_NBAR);     // barrier slot reuse
-    live.push_back({k, start, start + sz});
+    if (newa) {
+      // the phi_a image stays until the last step that shares it has been released
+      int klast = k;
+      while (klast + 1 < n && !(out[klast + 1].flags & 1)) klast++;
+      live.push_back({klast, start, start + a_bytes});
+      aoff = start;
+    }
+    live.push_back({k, start + a_bytes, start + sz});
     tail = start + sz;
-    out[k].soff = start;
+    out[k].aoff = aoff;
+    out[k].soff = start + a_bytes;
     out[k].dep = dep;
     // issued when the math reaches step ip(k) <= k (in order, at most DENS_LOOKAHEAD steps ahead)
     ip[k] = std::max(std::max(dep + 1, ip_prev), std::max(0, k - DENS_LOOKAHEAD));
@@ -252,11 +265,12 @@ __global__ void __launch_bounds__(DTHREADS, 1) density_kernel(HamArgs g, int dbg
     unsigned long long* bar = &sm.full[k % DENS_NBAR];
     const int atot4 = ((d.na_up + 3) & ~3) + ((d.na_dn + 3) & ~3), btot4 = ((d.nb_up + 3) & ~3) + ((d.nb_dn + 3) & ~3);
     const unsigned a_bytes = (unsigned)atot4 * 4 * RT * 8, b_bytes = (unsigned)btot4 * 4 * RT * 8, rho_bytes = (unsigned)(2 * btot4 * d.kp) * 8;
-    mbar_expect_tx(bar, a_bytes + b_bytes + rho_bytes);
+    const bool newa = d.flags & 1;                         // otherwise the phi_a image of an earlier step is shared
+    mbar_expect_tx(bar, (newa ? a_bytes : 0u) + b_bytes + rho_bytes);
+    if (newa) bulk_g2s(sm.arena + d.aoff, tab + (size_t)d.a_row0 * 4 * RT, a_bytes, bar);
     unsigned char* dst = sm.arena + d.soff;
-    bulk_g2s(dst, tab + (size_t)d.a_row0 * 4 * RT, a_bytes, bar);
-    bulk_g2s(dst + a_bytes, tab + (size_t)d.b_row0 * 4 * RT, b_bytes, bar);
-    bulk_g2s(dst + a_bytes + b_bytes, pk + d.pk_off, rho_bytes, bar);
+    bulk_g2s(dst, tab + (size_t)d.b_row0 * 4 * RT, b_bytes, bar);
+    bulk_g2s(dst + b_bytes, pk + d.pk_off, rho_bytes, bar);
   };
   // Operand movement never blocks the math.  A step can be issued once the step whose arena space it reuses (dep) has
   // been released by all 8 warps.  At every step boundary one lane of every warp tries to advance the issue cursor up
@@ -287,8 +301,8 @@ __global__ void __launch_bounds__(DTHREADS, 1) density_kernel(HamArgs g, int dbg
       __syncwarp();
 
       const int atot4 = aup4 + adn4;
-      const double* __restrict__ sa = reinterpret_cast<const double*>(sm.arena + d.soff);
-      const double* __restrict__ sb = sa + (size_t)4 * atot4 * RT;
+      const double* __restrict__ sa = reinterpret_cast<const double*>(sm.arena + d.aoff);
+      const double* __restrict__ sb = reinterpret_cast<const double*>(sm.arena + d.soff);
       const double* __restrict__ srho = sb + (size_t)4 * btot4 * RT;
       if (!(dbg & 4)) mbar_wait(&sm.full[k % DENS_NBAR], (k / DENS_NBAR) & 1);
       if (ntn > 0) {

@@ -50,20 +50,22 @@ struct DensStep {
   int a_row0, na_up, na_dn;   // first row of the contraction chunk in the padded index space; valid rows per spin
   int b_row0, nb_up, nb_dn;   // first row of the column chunk in the padded index space; valid columns per spin
   int rho_off, ld;            // element offset of (a chunk start, b chunk start) inside the block matrix, leading dim
-  int flags;                  // bit0: new b-chunk; bit1: first a-chunk (zero C); bit2: last a-chunk (epilogue)
+  int flags;                  // bit0: this step brings in its phi_a image (else it shares the one of an earlier
+                              // step); bit1: first a-chunk (zero C); bit2: last a-chunk (epilogue)
   int kp;                     // row stride of the packed chunk: >= padded a-count, kp % 8 == 4 (bank-conflict free)
   int pk_off;                 // offset (doubles) of the packed chunk [n = (b,c)][k = a] in the packed rho array
-  // shared-memory ring schedule, simulated on the host (build_density_steps): the operands of a step occupy
-  // [soff, soff + size) of the arena; they may be written once step `dep` has been released by all warps; when the
+  // shared-memory ring schedule, simulated on the host (build_density_steps): phi_a lives at aoff, phi_b and the rho
+  // chunk at [soff, ..) of the arena; they may be written once step `dep` has been released by all warps; when the
   // math reaches this step, steps [.., issue_to) are due.
-  int soff;                   // byte offset of the step's operand image in the arena
+  int soff, aoff;             // byte offsets in the arena
   int dep;                    // last step whose arena space / barrier slot this step reuses (-1: none)
   int issue_to;               // steps [.., issue_to) are issued when the math reaches this step
-  int pad[2];
+  int pad;
 };
 constexpr int DENS_ARENA = 220 * 1024;   // bytes of shared memory cycled through by the density kernel
 constexpr int DENS_NBAR = 16;            // mbarrier slots (step k uses slot k % DENS_NBAR)
-constexpr int DENS_LOOKAHEAD = 12;       // at most this many steps are in flight ahead of the math
+constexpr int DENS_LOOKAHEAD = 2;        // steps issued ahead of the math (measured: deeper queues of bulk copies delay
+                                         // the operands that are needed next; 2 is the optimum on B200)
 constexpr int DENS_MAXSTEPS = 2048;      // steps of one density pass (their dependency list lives in shared memory)
 constexpr int DENS_AC = 48;   // contraction chunk
 constexpr int DENS_BC = 32;   // column chunk

@@ -14,6 +14,21 @@
 namespace pnfam {
 
 // ---- small RAII device buffer -------------------------------------------------------------------------
+// Stream-ordered allocations from the device's default memory pool, which is told to keep freed memory: a solve
+// needs tens of GB of work space (Broyden history), and a fresh context / solve then reuses what the previous one
+// returned instead of going back to the driver.  All allocations and frees are ordered on the legacy default
+// stream, with which the (blocking) work stream of a context synchronises implicitly.
+inline void keep_pool_memory() {
+  static bool done = false;
+  if (done) return;
+  int dev = 0;
+  cudaMemPool_t pool;
+  if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    unsigned long long keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  done = true;
+}
 template <class T>
 struct DBuf {
   T* p = nullptr;
@@ -22,11 +37,11 @@ struct DBuf {
   DBuf(const DBuf&) = delete;
   DBuf& operator=(const DBuf&) = delete;
   ~DBuf() { release(); }
-  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  void release() { if (p) cudaFreeAsync(p, 0); p = nullptr; n = 0; }
   void alloc(size_t count) {
     release();
     n = count;
-    if (count) PNFAM_CUDA_CHECK(cudaMalloc(&p, count * sizeof(T)));
+    if (count) { keep_pool_memory(); PNFAM_CUDA_CHECK(cudaMallocAsync(&p, count * sizeof(T), 0)); }
   }
   void upload(const std::vector<T>& h) {
     alloc(h.size());
@@ -368,7 +383,8 @@ extern "C" int pnfam_b200_solve(pnfam_b200_ctx* c, const pnfam_b200_operator* op
     const int nred = 64;
     vin.alloc((size_t)P * n); vout.alloc((size_t)P * n);
     vin.zero(); vout.zero();
-    if (M > 0) { df.alloc((size_t)P * Malloc * n); dv.alloc((size_t)P * Malloc * n); df.zero(); dv.zero(); }
+    // Broyden history: only slots that have been written are ever read (iter_used bounds every loop): no clearing
+    if (M > 0) { df.alloc((size_t)P * Malloc * n); dv.alloc((size_t)P * Malloc * n); }
     gram.alloc((size_t)P * Malloc * Malloc); work.alloc((size_t)P * Malloc); gamma.alloc((size_t)P * Malloc);
     gram.zero(); work.zero(); gamma.zero();
     red.alloc((size_t)P * nred * 2); d_si.alloc(P); d_normi.alloc(P); d_omega.alloc((size_t)P * 2);
