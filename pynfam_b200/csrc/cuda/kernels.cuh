@@ -36,9 +36,11 @@ constexpr int NMF = 5 * 5 * 2 * 2 * 2;       // field tensor mf(ta,tb,sa,sb) com
 constexpr int NPF = 2 * 2 * 2;               // pairing field (sa,sb) complex
 // Both field tensors are stored tile-major so that the projection fetches what one CTA needs for one r-tile with a
 // single linear bulk copy:
-//   mf[kt][sa][ta][tb][sb][rr][c]   (1600 doubles per (r-tile kt, row spin sa))
+//   mf[kt][sa][sb][pair][rr][c]     (the 18 structurally non-zero (ta,tb) pairs: 1152 doubles per (r-tile kt,
+//                                    row spin sa); a column chunk inside one spin segment fetches one sb half)
 //   pf[sa][kt][sb][rr][c]           (64 doubles per (sa, kt); kt padded to a multiple of 4: one copy per 4 r-tiles)
-constexpr int MF_TILE = 5 * 5 * 2 * RT * 2;
+constexpr int MF_PAIRS = 18;
+constexpr int MF_TILE = 2 * MF_PAIRS * RT * 2;
 constexpr int PF_TILE = 2 * RT * 2;
 __host__ __device__ inline size_t mf_elems(int ntiles) { return (size_t)ntiles * 2 * MF_TILE; }
 __host__ __device__ inline size_t pf_elems(int ntiles) { return (size_t)2 * ((ntiles + 3) & ~3) * PF_TILE; }
@@ -136,10 +138,12 @@ struct MixArgs {
   const double* gqp;              // [1+nx][4][nxy] (F first, then cross-terms)
   int nstr;                       // 1 + nxterms
   double* strength;               // [P][nstr][2]
+  double* strpart;                // [nactive][nstr][STR_SPLIT][2] slices of the strength sums
   const int* active;
   int nactive;
 };
 void launch_greens(const MixArgs& a, cudaStream_t stream);
+size_t strength_partial_elems(int npoints, int nstr);
 void launch_broyden(const MixArgs& a, int iter, cudaStream_t stream);
 void launch_strength(const MixArgs& a, cudaStream_t stream);
 

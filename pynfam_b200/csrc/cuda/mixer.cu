@@ -231,18 +231,22 @@ void launch_broyden(const MixArgs& a, int iter, cudaStream_t stream) {
 }
 
 // ---- strength function ----------------------------------------------------------------------------------
+// S = -(1/pi) F . dR (contract_bbm, pnfam_solver.f90:196-203): STR_SPLIT CTAs per (operator, point) sum slices of the
+// quadrants, the last stage adds the slices in a fixed order (deterministic)
+constexpr int STR_SPLIT = 32;
 __global__ void __launch_bounds__(256) strength_kernel(MixArgs a) {
   __shared__ double sh[8];
-  const int k = blockIdx.x, za = blockIdx.y, p = a.active[za];
+  const int k = blockIdx.x, za = blockIdx.y, sp = blockIdx.z, p = a.active[za];
   const double* g = a.gqp + (size_t)k * 4 * a.nxy;
   const double* v = a.vin + (size_t)p * a.n;
   const int nq = a.nvec / 2;
+  const size_t per = (a.nxy + STR_SPLIT - 1) / STR_SPLIT, e0 = sp * per, e1 = e0 + per < a.nxy ? e0 + per : a.nxy;
   double sre = 0.0, sim = 0.0;
   for (int q = 0; q < nq; q++) {
     const double* gq = g + (size_t)q * a.nxy;
     const double* vr = v + pack_offset(0, q, a.nxy);
     const double* vi = v + pack_offset(1, q, a.nxy);
-    for (size_t e = threadIdx.x; e < a.nxy; e += blockDim.x) {
+    for (size_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
       const double gg = gq[e];
       sre += gg * vr[e];
       sim += gg * vi[e];
@@ -251,15 +255,26 @@ __global__ void __launch_bounds__(256) strength_kernel(MixArgs a) {
   sre = block_sum(sre, sh);
   sim = block_sum(sim, sh);
   if (threadIdx.x == 0) {
-    const double pi = 3.14159265358979323846264338327950288;
-    a.strength[((size_t)p * a.nstr + k) * 2] = -sre / pi;
-    a.strength[((size_t)p * a.nstr + k) * 2 + 1] = -sim / pi;
+    double* part = a.strpart + (((size_t)za * a.nstr + k) * STR_SPLIT + sp) * 2;
+    part[0] = sre; part[1] = sim;
   }
 }
+__global__ void strength_final_kernel(MixArgs a) {
+  const int k = blockIdx.x, za = blockIdx.y, p = a.active[za];
+  if (threadIdx.x != 0) return;
+  const double* part = a.strpart + ((size_t)za * a.nstr + k) * STR_SPLIT * 2;
+  double sre = 0.0, sim = 0.0;
+  for (int s = 0; s < STR_SPLIT; s++) { sre += part[2 * s]; sim += part[2 * s + 1]; }
+  const double pi = 3.14159265358979323846264338327950288;
+  a.strength[((size_t)p * a.nstr + k) * 2] = -sre / pi;
+  a.strength[((size_t)p * a.nstr + k) * 2 + 1] = -sim / pi;
+}
+size_t strength_partial_elems(int npoints, int nstr) { return (size_t)npoints * nstr * STR_SPLIT * 2; }
 
 void launch_strength(const MixArgs& a, cudaStream_t stream) {
   if (a.nactive <= 0) return;
-  strength_kernel<<<dim3(a.nstr, a.nactive), 256, 0, stream>>>(a);
+  strength_kernel<<<dim3(a.nstr, a.nactive, STR_SPLIT), 256, 0, stream>>>(a);
+  strength_final_kernel<<<dim3(a.nstr, a.nactive), 32, 0, stream>>>(a);
 }
 
 }  // namespace pnfam

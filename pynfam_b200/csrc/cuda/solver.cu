@@ -377,7 +377,7 @@ extern "C" int pnfam_b200_solve(pnfam_b200_ctx* c, const pnfam_b200_operator* op
     }
 
     // ---- per-point state ---------------------------------------------------------------------------------
-    DBuf<double> vin, vout, df, dv, gram, work, gamma, red, d_si, d_normi, d_omega, d_str;
+    DBuf<double> vin, vout, df, dv, gram, work, gamma, red, d_si, d_normi, d_omega, d_str, d_strpart;
     DBuf<double> rsp, hsp, hqp, scratch, dd_rho, dd_kap, mf, pf, hpart, pk_rho, pk_kap;
     DBuf<int> d_active;
     const int nred = 64;
@@ -388,7 +388,7 @@ extern "C" int pnfam_b200_solve(pnfam_b200_ctx* c, const pnfam_b200_operator* op
     gram.alloc((size_t)P * Malloc * Malloc); work.alloc((size_t)P * Malloc); gamma.alloc((size_t)P * Malloc);
     gram.zero(); work.zero(); gamma.zero();
     red.alloc((size_t)P * nred * 2); d_si.alloc(P); d_normi.alloc(P); d_omega.alloc((size_t)P * 2);
-    d_str.alloc((size_t)P * nstr * 2);
+    d_str.alloc((size_t)P * nstr * 2); d_strpart.alloc(strength_partial_elems(P, nstr));
     rsp.alloc((size_t)P * 8 * nxy); hsp.alloc((size_t)P * 8 * nxy); hqp.alloc((size_t)P * 8 * nxy);
     rsp.zero(); hsp.zero(); hqp.zero();
     scratch.alloc((size_t)P * 2 * std::max<size_t>(od->scratch_elems, 1));
@@ -445,7 +445,7 @@ extern "C" int pnfam_b200_solve(pnfam_b200_ctx* c, const pnfam_b200_operator* op
     ma.omega = d_omega.p; ma.quench = no_residual ? 0.0 : quench;
     ma.vin = vin.p; ma.vout = vout.p; ma.df = df.p; ma.dv = dv.p; ma.gram = gram.p; ma.work = work.p; ma.gamma = gamma.p;
     ma.red = red.p; ma.nred = nred; ma.si = d_si.p; ma.normi = d_normi.p; ma.gqp = od->gqp.p; ma.nstr = nstr;
-    ma.strength = d_str.p; ma.active = d_active.p;
+    ma.strength = d_str.p; ma.strpart = d_strpart.p; ma.active = d_active.p;
 
     std::vector<double> h_si(P, 1.0), h_str((size_t)P * nstr * 2, 0.0);
     for (int p = 0; p < P; p++) { iters[p] = 0; conv[p] = 0; si_out[p] = 1.0; }
@@ -493,7 +493,7 @@ extern "C" int pnfam_b200_solve(pnfam_b200_ctx* c, const pnfam_b200_operator* op
       launch_greens(ma, st);
       launch_broyden(ma, it, st);
       launch_strength(ma, st);
-      launches += 1 + 5 + 1;
+      launches += 1 + 5 + 2;
       PNFAM_CUDA_CHECK(cudaMemcpyAsync(h_si.data(), d_si.p, P * sizeof(double), cudaMemcpyDeviceToHost, st));
       PNFAM_CUDA_CHECK(cudaMemcpyAsync(h_str.data(), d_str.p, (size_t)P * nstr * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
       PNFAM_CUDA_CHECK(cudaStreamSynchronize(st));
