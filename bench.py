@@ -270,7 +270,7 @@ def main():
                     "d2h_bytes_per_step": int(sums[5] / args.steps / world), "omega_points_per_s": sums[3] / vals[1]},
             "gpu_launches": int(sums[2]),
             "roofline": {"bound": "tensor", "kernel": top[0], "achieved": ach, "peak": dmma_peak, "unit": "TFLOP/s",
-                         "frac": ach / dmma_peak if dmma_peak else None, "traffic": None,
+                         "frac": ach / dmma_peak if dmma_peak else None, "traffic": ncu_traffic(top[0]),
                          "peak_source": "FP64 DMMA (mma.sync m8n8k4) measured live by pnfam_b200_dmma_peak; "
                                         "MEASURED_PEAKS.json carries no FP64 figure",
                          "density": {"tflops": dens_fl / dens_s / 1e12 if dens_s else None, "share_of_step": dens_s / dev_s,
@@ -284,6 +284,17 @@ def main():
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture of this workload (profiles/ncu_traffic.json, written by scripts/ncu_traffic.py);
+    None if no capture is committed."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        return {"bytes_per_launch": d[kernel]["bytes_per_launch"], "kernel": d[kernel]["kernel"], "source": d["source"]}
+    except Exception:
+        return None
 
 
 def cpu_baseline(args):

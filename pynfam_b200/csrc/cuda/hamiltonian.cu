@@ -24,6 +24,43 @@
 
 namespace pnfam {
 
+// development timing knobs (scripts/kernel_probe.py): skipping parts of a kernel makes its results WRONG -- say so loudly
+static int dev_knob(const char* name) {
+  const char* v = getenv(name);
+  const int k = v ? atoi(v) : 0;
+  if (k) fprintf(stderr, "pnfam_b200: WARNING: %s=%d skips kernel work for timing experiments -- RESULTS ARE INVALID\n", name, k);
+  return k;
+}
+
+// Independent kernels of one stage (rho and kappa densities; h and Delta projections of both passes) run on side
+// streams forked from / joined to the caller's stream, so that the tail of one fills with CTAs of the next.
+struct SideStreams {
+  static constexpr int N = 3;
+  cudaStream_t s[N];
+  cudaEvent_t fork, join[N];
+  SideStreams() {
+    for (int i = 0; i < N; i++) {
+      PNFAM_CUDA_CHECK(cudaStreamCreateWithFlags(&s[i], cudaStreamNonBlocking));
+      PNFAM_CUDA_CHECK(cudaEventCreateWithFlags(&join[i], cudaEventDisableTiming));
+    }
+    PNFAM_CUDA_CHECK(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+  }
+  void fork_from(cudaStream_t main, int n) {
+    PNFAM_CUDA_CHECK(cudaEventRecord(fork, main));
+    for (int i = 0; i < n; i++) PNFAM_CUDA_CHECK(cudaStreamWaitEvent(s[i], fork, 0));
+  }
+  void join_to(cudaStream_t main, int n) {
+    for (int i = 0; i < n; i++) {
+      PNFAM_CUDA_CHECK(cudaEventRecord(join[i], s[i]));
+      PNFAM_CUDA_CHECK(cudaStreamWaitEvent(main, join[i], 0));
+    }
+  }
+};
+static SideStreams& side_streams() {
+  static SideStreams ss;   // one process drives one GPU
+  return ss;
+}
+
 constexpr int BC = 32;    // columns b per chunk of the projection (8 DMMA n-tiles of 4 b x {re,im})
 
 // ---- mbarrier + bulk-copy primitives (PTX) --------------------------------------------------------
@@ -400,9 +437,12 @@ void launch_density(const HamArgs& a, cudaStream_t stream) {
   if (maxsteps > 0) pack_rho_kernel<<<dim3(maxsteps, 4, a.nactive), 256, 0, stream>>>(a);
   // development knob (timing experiments only; results are wrong when set): bit0 skips the DMMA, bit1 the epilogue,
   // bit2 the operand movement
-  static const int dbg = getenv("PNFAM_B200_DENS_DEBUG") ? atoi(getenv("PNFAM_B200_DENS_DEBUG")) : 0;
+  static const int dbg = dev_knob("PNFAM_B200_DENS_DEBUG");
+  SideStreams& ss = side_streams();
+  ss.fork_from(stream, 1);
   density_kernel<0><<<dim3(a.basis.ntiles, 2, a.nactive), DTHREADS, sizeof(DensSmem), stream>>>(a, dbg);
-  density_kernel<1><<<dim3((a.basis.ntiles + 3) / 4, 2, a.nactive), DTHREADS, sizeof(DensSmem), stream>>>(a, dbg);
+  density_kernel<1><<<dim3((a.basis.ntiles + 3) / 4, 2, a.nactive), DTHREADS, sizeof(DensSmem), ss.s[0]>>>(a, dbg);
+  ss.join_to(stream, 1);
 }
 
 // structurally non-zero (t, t') entries of the Skyrme field tensor (fields_kernel): the Laplacian only pairs with
@@ -948,17 +988,22 @@ void launch_projection(const HamArgs& a, const ProjPlan& pp, cudaStream_t stream
     attr = true;
   }
   // development knob (timing experiments only; results are wrong when set): bit0 skips the DMMA, bit1 the G build
-  static const int dbg = getenv("PNFAM_B200_PROJ_DEBUG") ? atoi(getenv("PNFAM_B200_PROJ_DEBUG")) : 0;
-  for (int q = 0; q < 2; q++) {
+  static const int dbg = dev_knob("PNFAM_B200_PROJ_DEBUG");
+  SideStreams& ss = side_streams();
+  ss.fork_from(stream, 3);
+  // the two long kernels (h of both passes) first, the short ones (Delta) fill in behind them
+  for (int q = 0; q < 2; q++)
     if (pp.ntiles_h[q] > 0) {
       dim3 grid(pp.ntiles_h[q], pp.ksplit, a.nactive);
-      projection_kernel<0><<<grid, PTHREADS, sizeof(ProjSmem<0>), stream>>>(a, pp.tiles_h, pp.tile_off_h[q], pp.ntiles_h[q], pp.ksplit, q, dbg);
+      projection_kernel<0><<<grid, PTHREADS, sizeof(ProjSmem<0>), q == 0 ? stream : ss.s[0]>>>(a, pp.tiles_h, pp.tile_off_h[q], pp.ntiles_h[q],
+                                                                                             pp.ksplit, q, dbg);
     }
+  for (int q = 0; q < 2; q++)
     if (pp.ntiles_d[q] > 0) {
       dim3 grid(pp.ntiles_d[q], pp.ksplit, a.nactive);
-      projection_kernel<1><<<grid, PTHREADS, sizeof(ProjSmem<1>), stream>>>(a, pp.tiles_d, pp.tile_off_d[q], pp.ntiles_d[q], pp.ksplit, q, dbg);
+      projection_kernel<1><<<grid, PTHREADS, sizeof(ProjSmem<1>), ss.s[1 + q]>>>(a, pp.tiles_d, pp.tile_off_d[q], pp.ntiles_d[q], pp.ksplit, q, dbg);
     }
-  }
+  ss.join_to(stream, 3);
   dim3 gr((unsigned)((2 * a.nxy + 255) / 256), 4, a.nactive);
   projection_reduce_kernel<<<gr, 256, 0, stream>>>(a, pp.ksplit);
 }

@@ -191,6 +191,29 @@ def test_gd162_16_shells_against_reference_binary(gpu, tmp_path):
                     assert _rel(r["strength"][0, k], gold[lab]) < TOL, (op, i, lab)
 
 
+def test_gd162_20_shells_multi_chunk_blocks(gpu, tmp_path):
+    """20 shells (N=3542): the largest blocks have spin segments longer than one 48-row chunk, which exercises the
+    accumulation over a-chunks in the density kernel and several a-chunks per segment in the projection.  Known
+    answers from the reference's pnfam_main.x at fixed iteration counts (tests/golden/make_gd162_20sh.py)."""
+    pts = load_points("Gd162_SKOP_20sh")
+    ctx = None
+    base = None
+    for op, lst in pts.items():
+        for i, pt in enumerate(lst):
+            stage_point("Gd162_SKOP_20sh", op, i, str(tmp_path), name="%s_%d.in" % (op, i))
+            p = host.Problem(str(tmp_path), "%s_%d.in" % (op, i), share_nucleus_with=base)
+            if base is None:
+                base = p
+                ctx = gpu.Context(p)
+                assert (p.i32("num_spin_up") > 48).any() or ((p.i32("db") - p.i32("num_spin_up")) > 48).any()
+            r = ctx.solve(p)
+            gold = gold_rows(pt)
+            assert int(r["iters"][0]) == pt["iters"]
+            for k, lab in enumerate(["Strength"] + r["labels"][1:]):
+                if lab in gold:
+                    assert _rel(r["strength"][0, k], gold[lab]) < TOL, (op, i, lab)
+
+
 def test_drop_in_executable_writes_the_reference_dat_contract(gpu, tmp_path):
     """pnfam_main.x <namelist> in a rundir, exactly as pynfam's fortProcess launches it
     (pynfam/fortran/fortran_utils.py:222-247); the .dat is parsed with the restated pnfamParser."""
