@@ -112,6 +112,38 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons)}
 
 
+ITER_RE = re.compile(r"^#\s+\d+[LB]\s+\S+\s+\S+\s+\S+\s+(\S+)\s*$", re.M)
+
+
+def reference_farm(args, nproc):
+    """The way pynfam itself uses the reference (README: MPI over serial executables): `nproc` single-threaded
+    pnfam_main.x processes side by side, one omega point each, args.ref_iters iterations.  Returns (aggregate
+    iterations/s from the processes' own per-iteration timers, iterations, wall seconds, mean setup seconds)."""
+    from oracle import refrun
+    oms = circle_contour(max(args.points, nproc))
+    res = [None] * nproc
+
+    def work(k):
+        wd = tempfile.mkdtemp()
+        stage(wd, oms[(k * len(oms)) // nproc], args.ref_iters)
+        dat, wall, out = refrun.run_pnfam(wd, "GT-K0.in", threads=1)
+        res[k] = (wall, [float(m.group(1)) for m in ITER_RE.finditer(out)])
+        shutil.rmtree(wd, ignore_errors=True)
+
+    t0 = time.perf_counter()
+    th = [threading.Thread(target=work, args=(k,)) for k in range(nproc)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    wall = time.perf_counter() - t0
+    ok = [r for r in res if r and r[1]]
+    if not ok:
+        return None
+    rate = sum(len(t) / sum(t) for _, t in ok)
+    return rate, sum(len(t) for _, t in ok), wall, sum(w - sum(t) for w, t in ok) / len(ok)
+
+
 def run_reference(args, rank):
     """Reference arm: the unmodified prebuilt pnfam_main.x on the host cores (kind 'reference')."""
     if rank != 0:
@@ -128,25 +160,34 @@ def run_reference(args, rank):
     setup = []
     for step in range(args.warmup + args.steps):
         dat, wall, out = refrun.run_pnfam(wd, "GT-K0.in", threads=cores)
-        times = [float(m.group(1)) for m in re.finditer(r"^#\s+\d+[LB]\s+\S+\s+\S+\s+\S+\s+(\S+)\s*$", out, re.M)]
+        times = [float(m.group(1)) for m in ITER_RE.finditer(out)]
         if not times:
             print(json.dumps({"impl": "reference", "unavailable": "reference run produced no iteration table"}))
             return
         if step >= args.warmup:
             per_iter += times
             setup.append(wall - sum(times))
-    ips = len(per_iter) / sum(per_iter)
+    ips_threaded = len(per_iter) / sum(per_iter)
+    # second mode: one single-threaded process per core (how pynfam farms the executable); the better mode is reported
+    farm = [reference_farm(args, cores) for _ in range(min(args.warmup, 1) + args.steps)][min(args.warmup, 1):]
+    farm = [f for f in farm if f]
+    ips_farm = sum(f[0] for f in farm) / len(farm) if farm else 0.0
+    ips = max(ips_threaded, ips_farm)
+    mode = ("%d single-threaded processes side by side, 1 omega point x %d iterations each (setup %.1f s/process excluded)"
+            % (cores, args.ref_iters, farm[0][3])) if ips_farm >= ips_threaded and farm else \
+           ("1 process, OMP=OPENBLAS threads=%d, 1 omega point x %d iterations per step (setup %.1f s/launch excluded)"
+            % (cores, args.ref_iters, sum(setup) / len(setup)))
     line = {
         "impl": "reference", "metric": "FAM iterations/s (omega-points/s in omega_points_per_s)", "value": ips,
         "unit": "iterations/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * sum(per_iter) / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": 1e3 * (farm[0][2] if ips_farm >= ips_threaded and farm else sum(per_iter) / max(1, args.steps)),
+        "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "points_per_gpu": args.points, "shells": 16, "nghl": 1600},
         "omega_points_per_s": ips / args.assumed_iters_per_point,
         "cpu_baseline": {"value": ips, "unit": "iterations/s", "cores": cores, "kind": "reference",
-                         "sample": "1 omega point x %d FAM iterations per step, OMP=OPENBLAS threads=%d; per-iteration "
-                                   "time from pnfam_main.x's own timer; setup (HFB reconstruction, %.1f s/launch) excluded"
-                                   % (args.ref_iters, cores, sum(setup) / len(setup))},
+                         "sample": mode + "; per-iteration times from pnfam_main.x's own timer",
+                         "threaded_iterations_per_s": ips_threaded, "farm_iterations_per_s": ips_farm},
         "e2e": {"value": ips, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -195,6 +236,9 @@ def main():
     setup_s = time.time() - t0
     ctx = gpu.Context(prob, device=local)
     nghl, nxy, dqp = prob.iscalar("nghl"), prob.iscalar("nxy"), prob.iscalar("dqp")
+    db, r2c = prob.i32("db"), prob.i32("f_ir2c")
+    t3 = sum(int(db[i]) ** 2 * int(db[j - 1]) + int(db[i]) * int(db[j - 1]) ** 2 for i, j in enumerate(r2c) if j > 0)
+    f_iter = 88.0 * nghl * nxy + 32 * 2.0 * t3 + 650.0 * nghl * dqp
 
     def barrier():
         torch.cuda.synchronize()
@@ -273,6 +317,10 @@ def main():
                          "frac": ach / dmma_peak if dmma_peak else None, "traffic": ncu_traffic(top[0]),
                          "peak_source": "FP64 DMMA (mma.sync m8n8k4) measured live by pnfam_b200_dmma_peak; "
                                         "MEASURED_PEAKS.json carries no FP64 figure",
+                         "whole_iteration": {"F_iter": f_iter, "achieved": f_iter * value / world / 1e12,
+                                             "frac": f_iter * value / world / 1e12 / dmma_peak if dmma_peak else None,
+                                             "note": "SURVEY 8(d): F_iter = 88*Ng*nxy + 32*2*T3 + 650*Ng*N algorithmic FP64 flop "
+                                                     "per FAM iteration, x iterations/s per GPU, / measured DMMA peak"},
                          "density": {"tflops": dens_fl / dens_s / 1e12 if dens_s else None, "share_of_step": dens_s / dev_s,
                                      "ms_per_launch": 1e3 * dens_s / max(1, dens_n)},
                          "projection": {"tflops": proj_fl / proj_s / 1e12 if proj_s else None, "share_of_step": proj_s / dev_s,
@@ -307,11 +355,19 @@ def cpu_baseline(args):
     stage(wd, om, args.ref_iters)
     if refrun.ensure_built():
         dat, wall, out = refrun.run_pnfam(wd, "GT-K0.in", threads=cores)
-        times = [float(m.group(1)) for m in re.finditer(r"^#\s+\d+[LB]\s+\S+\s+\S+\s+\S+\s+(\S+)\s*$", out, re.M)]
+        times = [float(m.group(1)) for m in ITER_RE.finditer(out)]
         if times:
-            return {"value": len(times) / sum(times), "unit": "iterations/s", "cores": cores, "kind": "reference",
+            threaded = len(times) / sum(times)
+            farm = reference_farm(args, cores)
+            if farm and farm[0] > threaded:
+                return {"value": farm[0], "unit": "iterations/s", "cores": cores, "kind": "reference",
+                        "sample": "oracle/_ref/pnfam_main.x, %d single-threaded processes side by side, 1 omega point x %d "
+                                  "iterations each; wall %.1f s incl. %.1f s setup per process" % (cores, args.ref_iters, farm[2], farm[3]),
+                        "threaded_iterations_per_s": threaded}
+            return {"value": threaded, "unit": "iterations/s", "cores": cores, "kind": "reference",
                     "sample": "oracle/_ref/pnfam_main.x, 1 omega point x %d iterations, %d threads; wall %.1f s incl. %.1f s setup"
-                              % (len(times), cores, wall, wall - sum(times))}
+                              % (len(times), cores, wall, wall - sum(times)),
+                    "farm_iterations_per_s": farm[0] if farm else None}
     from oracle import fam_oracle as fo
     from pynfam_b200 import host
     p = host.Problem(wd, "GT-K0.in")
