@@ -485,7 +485,7 @@ extern "C" int pnfam_b200_solve(pnfam_b200_ctx* c, const pnfam_b200_operator* op
         b.in = hsp.p; b.in_pstride = 8 * nxy; b.in_pack = 0;
         b.out = hqp.p; b.out_pstride = 8 * nxy; b.out_pack = 0;
         launch_transform(od->bwd, b, nactive, st);
-        launches += 2 + 2 + 1 + 5 + 2;
+        launches += 2 + 3 + 1 + 5 + 2;   // transform, pack + 2 densities, fields, 4 projections + reduce, transform
         n_dens += 2; n_proj += 4;
         fl_dens += (double)nactive * 2.0 * 20.0 * c->nghl * (double)nxy;
         fl_proj += (double)nactive * 2.0 * 24.0 * c->nghl * (double)nxy;
@@ -621,7 +621,7 @@ extern "C" int pnfam_b200_calc_hamiltonian(pnfam_b200_ctx* c, const pnfam_b200_b
       for (int cc = 0; cc < 2; cc++)
         PNFAM_CUDA_CHECK(cudaMemcpy(out[2 * pr + cc].elem, hsp.p + ((size_t)cc * 4 + quad_of_pair[pr]) * nxy,
                                     out[2 * pr + cc].nelem * sizeof(double), cudaMemcpyDeviceToHost));
-    c->launches += 2 + 1 + 5;
+    c->launches += 3 + 1 + 5;
     return 0;
   } catch (const std::exception& e) {
     set_err(err, errlen, e.what());
