@@ -66,10 +66,22 @@ typedef struct {
   const double *Ep, *En;        /* [dqp]  quasiparticle energies (0 above the pairing window) */
   const double *Up, *Vp, *Un, *Vn; /* [sum db^2] block-diagonal storage (pnfam_setup.f90:292-321) */
   const double *qp_fp, *qp_fn;  /* [dqp] equal-filling / thermal occupations, or NULL        */
+  /* Optional separable description of the same tables (harmonic-oscillator basis; HFBTHO builds them as
+   * products QH(nz,ih) * QL(nr,Lambda,il), hfbtho_solver.f90:3463-3671, hfbtho_solution.f90:199-202, 346-351):
+   *   ihil = ih + il*ngh (0-based),  z = sep_zrow[state]
+   *   wf = Z0[z][ih] R0[state][il]   wfdr = Z0 R1   wfdp = Z0 R2   wfdz = Z1 R0   wfd2_all = Z2 R0 + Z0 R3
+   * When given (ngh > 0) the density / projection kernels contract the two grid directions one after the other
+   * (sum factorisation) and the full tables are only used to verify the factors.  ngh = 0: general tables. */
+  int32_t ngh, ngl, sep_nzrows;
+  const int32_t* sep_zrow;      /* [dqp]                                                      */
+  const double* sep_z;          /* [3][sep_nzrows][ngh]   Z0, Z1, Z2                          */
+  const double* sep_r;          /* [4][dqp][ngl]          R0, R1, R2, R3                      */
 } pnfam_b200_model;
 
 int pnfam_b200_ctx_create(const pnfam_b200_model* model, int device, pnfam_b200_ctx** out, char* err, int errlen);
 void pnfam_b200_ctx_destroy(pnfam_b200_ctx* ctx);
+/* 1 if the context runs the sum-factorised kernels (separable factors given and accepted), 0 if the general-table ones */
+int pnfam_b200_ctx_separable(const pnfam_b200_ctx* ctx);
 
 /* External field f (+ cross-term fields g_k sharing f's block structure), single-particle basis,
  * as produced by init_external_field / setup_crossterms (pnfam_extfield.f90:37-108, 882-949). */

@@ -63,37 +63,6 @@ static SideStreams& side_streams() {
 
 constexpr int BC = 32;    // columns b per chunk of the projection (8 DMMA n-tiles of 4 b x {re,im})
 
-// ---- mbarrier + bulk-copy primitives (PTX) --------------------------------------------------------
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* b, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(b)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {
-  const unsigned a = smem_u32(b);
-  unsigned ok;
-  do {
-    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-                 : "=r"(ok) : "r"(a), "r"(parity) : "memory");
-  } while (!ok);
-}
-__device__ __forceinline__ bool mbar_test(unsigned long long* b, unsigned parity) {   // non-blocking
-  unsigned ok;
-  asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-               : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long* b) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(b)) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* b) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
-               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(b)) : "memory");
-}
-
-
 // ================================================================================================
 // density: D^{t t'}_{s s'}(r)
 //   The (block, spin, chunk) loop nest is flattened on the host into a list of steps.  A CTA owns 64 "rows"
@@ -427,6 +396,7 @@ __global__ void __launch_bounds__(DTHREADS, 1) density_kernel(HamArgs g, int dbg
 
 void launch_density(const HamArgs& a, cudaStream_t stream) {
   if (a.nactive <= 0) return;
+  if (a.sf.enabled) { launch_density_sf(a, stream); return; }
   static bool attr = false;
   if (!attr) {
     PNFAM_CUDA_CHECK(cudaFuncSetAttribute(density_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DensSmem)));
@@ -697,6 +667,30 @@ __global__ void __launch_bounds__(128) fields_kernel(HamArgs g) {
   ADD(2, 2, P, M, 1, aux); ADD(2, 2, M, P, -1, aux);
 #undef ADD
 #undef MF
+  // ---- pairing field (pnfam_hamiltonian_blas.f90:1201-1208): index (sa, sb)
+  const double cp = B.cpair[r], csp = B.cspair[r];
+  cplx pfv[2][2];
+  pfv[0][0] = csp * (sbr + mul_mi(sbp));             // |a>=+, |b>=+
+  pfv[1][0] = (-cp) * rb - csp * sbz;                // |a>=-, |b>=+
+  pfv[0][1] = cp * rb - csp * sbz;                   // |a>=+, |b>=-
+  pfv[1][1] = csp * (-sbr + mul_mi(sbp));            // |a>=-, |b>=-
+  if (g.sf.enabled) {
+    // sum-factorised projection: one linear copy per (il, sa, sb):  mf[il][sa][sb][pair(ta,tb)][ih][c],  pf[il][sa][sb][ih][c]
+    const int il = r / g.sf.ngh, ih = r - il * g.sf.ngh, kih = g.sf.kih;
+    double* __restrict__ mo = g.mf + ((size_t)za * 2 + q) * sf_mf_elems(g.sf.ngl, kih) + (size_t)il * 4 * SF_MFP * kih * 2 + ih * 2;
+    double* __restrict__ po = g.pf + ((size_t)za * 2 + q) * sf_pf_elems(g.sf.ngl, kih) + (size_t)il * 4 * kih * 2 + ih * 2;
+#pragma unroll
+    for (int a = 0; a < 5; a++)
+#pragma unroll
+      for (int b = 0; b < 5; b++)
+#pragma unroll
+        for (int s = 0; s < 4; s++)
+          if (mf_nonzero(a, b))
+            *reinterpret_cast<double2*>(mo + ((size_t)s * SF_MFP + mf_pair(a, b)) * kih * 2) = make_double2(mf[a][b][s >> 1][s & 1].re, mf[a][b][s >> 1][s & 1].im);
+#pragma unroll
+    for (int s = 0; s < 4; s++) *reinterpret_cast<double2*>(po + (size_t)s * kih * 2) = make_double2(pfv[s >> 1][s & 1].re, pfv[s >> 1][s & 1].im);
+    return;
+  }
   // tile-major output (kernels.cuh): mf[kt][sa][sb][pair(ta,tb)][rr][c], structurally non-zero pairs only
   const int kt = r / RT, rr = r % RT;
   double* __restrict__ mo = g.mf + ((size_t)za * 2 + q) * mf_elems(B.ntiles) + (size_t)kt * 2 * MF_TILE + rr * 2;
@@ -711,13 +705,6 @@ __global__ void __launch_bounds__(128) fields_kernel(HamArgs g) {
           *reinterpret_cast<double2*>(mo + (size_t)sa * MF_TILE + (sb * MF_PAIRS + mf_pair(a, b)) * (RT * 2)) =
               make_double2(mf[a][b][sa][sb].re, mf[a][b][sa][sb].im);
       }
-  // ---- pairing field (pnfam_hamiltonian_blas.f90:1201-1208): index (sa, sb)
-  const double cp = B.cpair[r], csp = B.cspair[r];
-  cplx pfv[2][2];
-  pfv[0][0] = csp * (sbr + mul_mi(sbp));             // |a>=+, |b>=+
-  pfv[1][0] = (-cp) * rb - csp * sbz;                // |a>=-, |b>=+
-  pfv[0][1] = cp * rb - csp * sbz;                   // |a>=+, |b>=-
-  pfv[1][1] = csp * (-sbr + mul_mi(sbp));            // |a>=-, |b>=-
   // pf[sa][kt][sb][rr][c]
   const int ntiles4 = (B.ntiles + 3) & ~3;
   double* __restrict__ po = g.pf + ((size_t)za * 2 + q) * pf_elems(B.ntiles) + (size_t)kt * PF_TILE + rr * 2;
@@ -981,6 +968,7 @@ size_t projection_partial_elems(const ProjPlan& pp, size_t nxy) { return (size_t
 
 void launch_projection(const HamArgs& a, const ProjPlan& pp, cudaStream_t stream) {
   if (a.nactive <= 0) return;
+  if (a.sf.enabled) { launch_projection_sf(a, stream); return; }
   static bool attr = false;
   if (!attr) {
     PNFAM_CUDA_CHECK(cudaFuncSetAttribute(projection_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ProjSmem<0>)));

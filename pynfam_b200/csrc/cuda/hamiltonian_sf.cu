@@ -1,0 +1,552 @@
+// Sum-factorised density and projection kernels (blocks (b) and (c) of the FAM iteration) for a separable basis.
+// Same results as density / meanfield / pairingfield of the reference (exes/pnfam/pnfam_hamiltonian_blas.f90:124-711,
+// 717-1169, 1175-1262) and as the general-table kernels of hamiltonian.cu, different operation order.
+//
+// In the harmonic-oscillator basis every table is a product, phi^t_a(ih, il) = Z^t(n_z(a), ih) R^t_a(il)
+// (HFBTHO builds them that way, hfbtho_solver.f90:3463-3671), with at most ~N_sh/2 distinct n_z inside one
+// (block, spin) segment.  The reference (and hamiltonian.cu) contract  sum_a phi_a(r) rho_ab  over all states a of a
+// segment for every grid point: 2 Ng d_a d_b flops per type.  Here, for one Gauss-Laguerre node il at a time:
+//
+//   density     T^j[k][b]    = sum_{a in slot k} R^j_a(il) rho_ab               FMA,  3 d_a d_b       (j: R0, R1, R2)
+//               A^t(ih, b)   = sum_k Z^t(k, ih) T^j(t)[k][b]                    DMMA, M = ih, K = #n_z slots, N = (b, re/im)
+//               D^{tt'}(ih) += A^t(ih, b) Z^t'(n_z(b), ih) R^t'_b(il)           FMA epilogue on the accumulator fragments
+//   projection  G^t(ih, b)   = sum_t' mf^{tt'}(ih, il) Z^t'(n_z(b), ih) R^t'_b  FMA
+//               W^w[k][b]    = sum_ih Z(k, ih) G(ih, b)                         DMMA, M = n_z slots, K = ih, N = (b, re/im)
+//               h_ab        += sum_w R^w_a(il) W^w[slot(a)][b]                  FMA,  4 d_a d_b
+//
+// which executes 2.1x (projection) to 2.4x (density) fewer pipe cycles at 16 shells and moves no Ng x N table at all:
+// a CTA reads the rho images (density) or the field tensor of its il (projection) plus a few KB of factors.
+// FP64 FMA and DMMA share the issue port of an SM sub-partition, so the kernels run their phases
+// one after the other on all warps, separated by CTA barriers, and overlap only the operand copies (cp.async.bulk
+// completing on mbarriers, double buffered).
+#include <algorithm>
+#include <vector>
+
+#include "device_common.cuh"
+#include "kernels.cuh"
+
+namespace pnfam {
+
+__host__ __device__ constexpr bool sf_mf_nonzero(int t, int t2) { return t == 0 || t2 == 0 || (t < 4 && t2 < 4); }
+__host__ __device__ constexpr int sf_mf_pair(int t, int t2) { return t == 0 ? t2 : (t < 4 ? 5 + (t - 1) * 4 + t2 : 17); }
+
+// ================================================================================================
+// packed rho / kappa images: image(step)[a][2 b + c], rows a of the segment in slot order, padded columns zero
+// ================================================================================================
+__global__ void __launch_bounds__(256) sf_pack_kernel(HamArgs g) {
+  const SfDev& S = g.sf;
+  const int list = blockIdx.y, kind = list >> 1, q = list & 1, za = blockIdx.z;
+  if ((int)blockIdx.x >= S.nsteps[list]) return;
+  const SfDensStep d = S.steps[list][blockIdx.x];
+  const int p = g.active[za];
+  const int quad = kind ? g.kap_quad[q] : g.rho_quad[q];
+  const double* __restrict__ src0 = g.rsp + ((size_t)p * 2 + 0) * 4 * g.nxy + (size_t)quad * g.nxy + d.rho_off;
+  const double* __restrict__ src1 = g.rsp + ((size_t)p * 2 + 1) * 4 * g.nxy + (size_t)quad * g.nxy + d.rho_off;
+  double* __restrict__ dst = S.pk[kind] + ((size_t)za * 2 + q) * S.pk_stride[kind] + d.img_off;
+  const int ncol = 2 * d.nbc, total = d.na * ncol;
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int a = idx / ncol, col = idx - a * ncol;
+    const int la = S.p2l[d.a_row0 + a], lb = S.p2l[d.b_row0 + (col >> 1)];
+    dst[idx] = lb >= 0 ? ((col & 1) ? src1 : src0)[(size_t)la + (size_t)lb * d.ld] : 0.0;
+  }
+}
+
+// ================================================================================================
+// density
+// ================================================================================================
+struct SfDensLayout {
+  int off_stage[2], off_T[2], off_bar;   // byte offsets in dynamic shared memory
+  int st_zb, st_ra, st_rb, st_rho;       // inside an operand stage: segtab at 0
+  int t_rb, t_zb, t_sz;                  // inside a T stage: T at 0
+  int ts;                                // row stride of T (doubles), ts % 16 == 4
+  int total;
+};
+
+static SfDensLayout make_dens_layout(const SfDev& S) {
+  SfDensLayout L{};
+  auto up = [](int x) { return (x + 127) & ~127; };
+  L.ts = 2 * S.nbc_max + 4;
+  L.st_zb = SF_SEGTAB * 4;
+  L.st_ra = L.st_zb + S.nbc_max * 4;
+  L.st_rb = L.st_ra + 2 * S.na_max * 32;
+  L.st_rho = L.st_rb + 2 * S.nbc_max * 32;
+  const int stage = up(L.st_rho + S.na_max * 2 * S.nbc_max * 8);
+  L.t_rb = 2 * 3 * S.kpad_max * L.ts * 8;
+  L.t_zb = L.t_rb + 2 * S.nbc_max * 32;
+  L.t_sz = L.t_zb + S.nbc_max * 4;
+  const int tstage = up(L.t_sz + SF_KMAX * 4);
+  int off = up(2 * S.nzrows * S.zs * 8);
+  for (int i = 0; i < 2; i++) { L.off_stage[i] = off; off += stage; }
+  for (int i = 0; i < 2; i++) { L.off_T[i] = off; off += tstage; }
+  L.off_bar = off;
+  L.total = off + 64;
+  return L;
+}
+
+// MODE 0: rho -> D^{tt'}_{ss'} (4 x 4 derivative types);  MODE 1: kappa -> K_{ss'} (plain wave functions)
+template <int MODE>
+__global__ void __launch_bounds__(SF_THREADS, 1) sf_density_kernel(HamArgs g, SfDensLayout L) {
+  constexpr int NJ = MODE == 0 ? 3 : 1;   // radial factor types entering T
+  constexpr int NT = MODE == 0 ? 4 : 1;   // derivative types
+  extern __shared__ __align__(128) unsigned char smem[];
+  const SfDev& S = g.sf;
+  const int ilp = blockIdx.x, q = blockIdx.y, za = blockIdx.z;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, lr = lane >> 2, lc = lane & 3;
+  const int list = MODE * 2 + q;
+  const SfDensStep* __restrict__ steps = S.steps[list];
+  const int nsteps = S.nsteps[list];
+  const double* __restrict__ pk = S.pk[MODE] + ((size_t)za * 2 + q) * S.pk_stride[MODE];
+  double* Zs = reinterpret_cast<double*>(smem);                 // [2][nzrows][zs]
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(smem + L.off_bar);
+  const int zs = S.zs, nzr = S.nzrows, na_max = S.na_max, nbc_max = S.nbc_max, kpad_max = S.kpad_max, ts = L.ts;
+  const int il0 = 2 * ilp, il1 = min(il0 + 1, S.ngl - 1);
+
+  for (int i = tid; i < 2 * nzr * zs; i += SF_THREADS) Zs[i] = S.zt[i];
+  if (tid == 0) {
+    mbar_init(&full[0], 1); mbar_init(&full[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+
+  // operand movement of one step: 7 linear bulk copies (segment table, z rows of the columns, radial factors of the
+  // a rows and of the b columns for both il, the packed rho image)
+  auto issue = [&](const SfDensStep& d, int k) {
+    unsigned char* st = smem + L.off_stage[k & 1];
+    unsigned long long* bar = &full[k & 1];
+    const unsigned ra_b = (unsigned)d.na * 32, rb_b = (unsigned)d.nbc * 32, rho_b = (unsigned)d.na * d.nbc * 16;
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    mbar_expect_tx(bar, SF_SEGTAB * 4 + (unsigned)d.nbc * 4 + 2 * ra_b + 2 * rb_b + rho_b);
+    bulk_g2s(st, S.segtab + (size_t)d.seg_a * SF_SEGTAB, SF_SEGTAB * 4, bar);
+    bulk_g2s(st + L.st_zb, S.zrow + d.b_row0, (unsigned)d.nbc * 4, bar);
+    bulk_g2s(st + L.st_ra, S.rg + ((size_t)il0 * S.dqp_p + d.a_row0) * 4, ra_b, bar);
+    bulk_g2s(st + L.st_ra + na_max * 32, S.rg + ((size_t)il1 * S.dqp_p + d.a_row0) * 4, ra_b, bar);
+    bulk_g2s(st + L.st_rb, S.rg + ((size_t)il0 * S.dqp_p + d.b_row0) * 4, rb_b, bar);
+    bulk_g2s(st + L.st_rb + nbc_max * 32, S.rg + ((size_t)il1 * S.dqp_p + d.b_row0) * 4, rb_b, bar);
+    bulk_g2s(st + L.st_rho, pk + d.img_off, rho_b, bar);
+  };
+  constexpr int ISSUER = SF_THREADS - 32;     // lane 0 of the last warp (never a DMMA warp for ngh <= 56)
+  // step descriptors travel in registers, fetched two steps ahead of their use
+  SfDensStep d_cur = nsteps > 0 ? steps[0] : SfDensStep{}, d_next = nsteps > 1 ? steps[1] : SfDensStep{};
+  if (tid == ISSUER) {
+    if (nsteps > 0) issue(d_cur, 0);
+    if (nsteps > 1) issue(d_next, 1);
+  }
+
+  // ---- phase T of step k (all threads): T^j[il][slot][col] = sum_{a in slot} R^j_a(il) rho[a][col];
+  //      forwards what the DMMA phase needs from the operand stage (which is recycled one step earlier than T)
+  auto phase_T = [&](const SfDensStep& d, int k) {
+    mbar_wait(&full[k & 1], (k >> 1) & 1);
+    const unsigned char* st = smem + L.off_stage[k & 1];
+    unsigned char* tst = smem + L.off_T[k & 1];
+    const int* __restrict__ segt = reinterpret_cast<const int*>(st);
+    const double* __restrict__ Ra = reinterpret_cast<const double*>(st + L.st_ra);
+    const double* __restrict__ rho = reinterpret_cast<const double*>(st + L.st_rho);
+    double* __restrict__ T = reinterpret_cast<double*>(tst);
+    const int ncol = 2 * d.nbc, kpad = (d.nslots + 3) & ~3, ntask = kpad * ncol;
+    for (int t = tid; t < ntask; t += SF_THREADS) {
+      const int slot = t / ncol, col = t - slot * ncol;
+      int a0 = 0, a1 = 0;
+      if (slot < d.nslots) { a0 = segt[slot]; a1 = segt[slot + 1]; }
+      double acc[2][NJ];
+#pragma unroll
+      for (int i = 0; i < 2 * NJ; i++) (&acc[0][0])[i] = 0.0;
+      for (int a = a0; a < a1; a++) {
+        const double v = rho[a * ncol + col];
+#pragma unroll
+        for (int il = 0; il < 2; il++)
+#pragma unroll
+          for (int j = 0; j < NJ; j++) acc[il][j] += Ra[(il * na_max + a) * 4 + j] * v;
+      }
+#pragma unroll
+      for (int il = 0; il < 2; il++)
+#pragma unroll
+        for (int j = 0; j < NJ; j++) T[((il * 3 + j) * kpad_max + slot) * ts + col] = acc[il][j];
+    }
+    const double* __restrict__ Rb = reinterpret_cast<const double*>(st + L.st_rb);
+    double* __restrict__ Rbt = reinterpret_cast<double*>(tst + L.t_rb);
+    for (int t = tid; t < 2 * nbc_max * 4; t += SF_THREADS) Rbt[t] = Rb[t];
+    if (tid < d.nbc) reinterpret_cast<int*>(tst + L.t_zb)[tid] = reinterpret_cast<const int*>(st + L.st_zb)[tid];
+    if (tid < SF_KMAX) reinterpret_cast<int*>(tst + L.t_sz)[tid] = segt[17 + tid];
+  };
+
+  // consumer role: warp w < 2 mt owns m-tile w % mt of il (w / mt); accumulators of ONE (s, s') sweep at a time
+  const bool consumer = warp < 2 * S.mt;
+  const int ilc = warp / S.mt, ih = (warp % S.mt) * 8 + lr;
+  double acc[NT][NT][2];
+#pragma unroll
+  for (int i = 0; i < NT * NT * 2; i++) (&acc[0][0][0])[i] = 0.0;
+
+  if (nsteps > 0) phase_T(d_cur, 0);
+  __syncthreads();
+  for (int k = 0; k < nsteps; k++) {
+    const SfDensStep d_nn = k + 2 < nsteps ? steps[k + 2] : SfDensStep{};
+    // the operand stage of step k was consumed by phase T(k) before the last barrier
+    if (tid == ISSUER && k + 2 < nsteps) issue(d_nn, k + 2);
+    if (k + 1 < nsteps) phase_T(d_next, k + 1);
+    if (consumer) {
+      const SfDensStep& d = d_cur;
+      const unsigned char* tst = smem + L.off_T[k & 1];
+      const double* __restrict__ T = reinterpret_cast<const double*>(tst) + (size_t)ilc * 3 * kpad_max * ts;
+      const double* __restrict__ Rb = reinterpret_cast<const double*>(tst + L.t_rb) + ilc * nbc_max * 4;
+      const int* __restrict__ zb = reinterpret_cast<const int*>(tst + L.t_zb);
+      const int* __restrict__ sz = reinterpret_cast<const int*>(tst + L.t_sz);
+      const int ksteps = (d.nslots + 3) >> 2, ntn = d.nbc >> 2;
+      double a0[SF_KMAX / 4], a1[SF_KMAX / 4];
+#pragma unroll
+      for (int ks = 0; ks < SF_KMAX / 4; ks++) {
+        a0[ks] = 0.0; a1[ks] = 0.0;
+        if (ks < ksteps) {
+          const int slot = ks * 4 + lc;
+          const int zr = slot < d.nslots ? sz[slot] : 0;
+          a0[ks] = Zs[zr * zs + ih];
+          if (MODE == 0) a1[ks] = Zs[(nzr + zr) * zs + ih];
+        }
+      }
+      const size_t tj = (size_t)kpad_max * ts;
+      for (int nt = 0; nt < ntn; nt++) {
+        double C[NT][2];
+#pragma unroll
+        for (int i = 0; i < NT * 2; i++) (&C[0][0])[i] = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < SF_KMAX / 4; ks++) {
+          if (ks < ksteps) {
+            const double* __restrict__ tb = T + (size_t)(ks * 4 + lc) * ts + nt * 8 + lr;
+            const double b0 = tb[0];
+            dmma884(C[0][0], C[0][1], a0[ks], b0);
+            if (MODE == 0) {
+              const double b1 = tb[tj], b2 = tb[2 * tj];
+              dmma884(C[1][0], C[1][1], a0[ks], b1);
+              dmma884(C[2][0], C[2][1], a0[ks], b2);
+              dmma884(C[3][0], C[3][1], a1[ks], b0);
+            }
+          }
+        }
+        // epilogue: contract with phi^t'_b(ih, il) = Z(n_z(b), ih) R_b(il) of this lane's column b
+        const int b = nt * 4 + lc, zr = zb[b];
+        const double z0 = Zs[zr * zs + ih];
+        double ph[NT];
+        ph[0] = z0 * Rb[b * 4];
+        if (MODE == 0) {
+          const double z1 = Zs[(nzr + zr) * zs + ih];
+          ph[1] = z0 * Rb[b * 4 + 1]; ph[2] = z0 * Rb[b * 4 + 2]; ph[3] = z1 * Rb[b * 4];
+        }
+#pragma unroll
+        for (int t = 0; t < NT; t++)
+#pragma unroll
+          for (int t2 = 0; t2 < NT; t2++) { acc[t][t2][0] += C[t][0] * ph[t2]; acc[t][t2][1] += C[t][1] * ph[t2]; }
+      }
+      if (d.flags & 1) {
+        // end of the (s, s') sweep: reduce over the 4 lanes of a grid point, write, restart
+        const int il = il0 + ilc;
+        const bool ok = ih < S.ngh && il < S.ngl;
+        constexpr int ndd = NT * NT * 8;
+        double* __restrict__ out = (MODE ? g.dd_kap : g.dd_rho) + ((size_t)za * 2 + q) * ndd * g.basis.nghl + (size_t)il * S.ngh + ih;
+#pragma unroll
+        for (int t = 0; t < NT; t++)
+#pragma unroll
+          for (int t2 = 0; t2 < NT; t2++)
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+              double v = acc[t][t2][c];
+              v += __shfl_xor_sync(0xffffffffu, v, 1);
+              v += __shfl_xor_sync(0xffffffffu, v, 2);
+              const int e = (t * NT + t2) * 2 + c;
+              if (ok && (e & 3) == lc) out[(size_t)(((t * NT + t2) * 4 + d.sweep) * 2 + c) * g.basis.nghl] = v;
+              acc[t][t2][c] = 0.0;
+            }
+      }
+    }
+    d_cur = d_next; d_next = d_nn;
+    __syncthreads();
+  }
+}
+
+void launch_density_sf(const HamArgs& a, cudaStream_t stream) {
+  if (a.nactive <= 0) return;
+  const SfDev& S = a.sf;
+  const SfDensLayout L = make_dens_layout(S);
+  static int attr_bytes = 0;
+  if (L.total > attr_bytes) {
+    PNFAM_CUDA_CHECK(cudaFuncSetAttribute(sf_density_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    PNFAM_CUDA_CHECK(cudaFuncSetAttribute(sf_density_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    attr_bytes = L.total;
+  }
+  const int maxsteps = std::max(std::max(S.nsteps[0], S.nsteps[1]), std::max(S.nsteps[2], S.nsteps[3]));
+  if (maxsteps > 0) sf_pack_kernel<<<dim3(maxsteps, 4, a.nactive), 256, 0, stream>>>(a);
+  const int nilp = (S.ngl + 1) / 2;
+  sf_density_kernel<0><<<dim3(nilp, 2, a.nactive), SF_THREADS, L.total, stream>>>(a, L);
+  sf_density_kernel<1><<<dim3(nilp, 2, a.nactive), SF_THREADS, L.total, stream>>>(a, L);
+}
+
+// ================================================================================================
+// projection
+// ================================================================================================
+constexpr int SF_GS = 68;    // row stride of G and W (64 interleaved (b,c) columns + 4): conflict-free fragment loads
+constexpr int SF_NBC = 32;   // columns b per output tile
+constexpr int SF_HACC = 12;  // accumulators per thread: rows a = (tid >> 6) + 8 i  (na <= 96)
+
+struct SfProjLayout {
+  int off_G, off_W, off_mf[2], off_ra[2], off_rb[2], off_int, off_bar;
+  int mf_bytes;              // bytes of the field tensor of one (il, sa, sb)
+  int total;
+};
+
+template <int MODE>
+static SfProjLayout make_proj_layout(const SfDev& S) {
+  constexpr int NS = MODE == 0 ? 5 : 1;
+  SfProjLayout L{};
+  auto up = [](int x) { return (x + 127) & ~127; };
+  int off = up(3 * S.nzrows * S.zs * 8);
+  L.off_G = off; off += up(std::max(NS * S.kih * SF_GS * 8, 2 * SF_NBC * (S.na_max | 1) * 8));   // reused as transpose buffer
+  L.off_W = off; off += up(2 * 4 * 8 * SF_GS * 8);
+  L.mf_bytes = (MODE == 0 ? SF_MFP : 1) * S.kih * 16;
+  for (int i = 0; i < 2; i++) { L.off_mf[i] = off; off += up(L.mf_bytes); }
+  for (int i = 0; i < 2; i++) { L.off_ra[i] = off; off += up(S.na_max * 32); }
+  for (int i = 0; i < 2; i++) { L.off_rb[i] = off; off += up(SF_NBC * 32); }
+  L.off_int = off; off += up((2 * S.na_max + 2 * SF_NBC + SF_KMAX) * 4);
+  L.off_bar = off;
+  L.total = off + 64;
+  return L;
+}
+
+// MODE 0: mf -> h;  MODE 1: pf -> Delta
+template <int MODE>
+__global__ void __launch_bounds__(SF_THREADS, 1) sf_projection_kernel(HamArgs g, SfProjLayout L, int q) {
+  constexpr int NS = MODE == 0 ? 5 : 1;
+  constexpr int NW = MODE == 0 ? 4 : 1;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const SfDev& S = g.sf;
+  const SfProjTile td = S.tiles[MODE][q][blockIdx.x];
+  const int ksp = blockIdx.y, za = blockIdx.z;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, lr = lane >> 2, lc = lane & 3;
+  const int zs = S.zs, nzr = S.nzrows, kih = S.kih;
+  const int na = td.na, nbc = td.nbc, nslots = td.nslots;
+  double* Zs = reinterpret_cast<double*>(smem);                 // [3][nzrows][zs]
+  double* G = reinterpret_cast<double*>(smem + L.off_G);        // [NS][kih][GS]
+  double* W = reinterpret_cast<double*>(smem + L.off_W);        // [2 parts][4][8][GS]
+  int* ints = reinterpret_cast<int*>(smem + L.off_int);
+  int* slot_a = ints;                       // [na_max]
+  int* p2l_a = ints + S.na_max;             // [na_max]
+  int* zrow_b = ints + 2 * S.na_max;        // [SF_NBC]
+  int* p2l_b = zrow_b + SF_NBC;             // [SF_NBC]
+  int* slot_z = p2l_b + SF_NBC;             // [SF_KMAX]
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem + L.off_bar);
+  // il range of this split
+  const int k_per = (S.ngl + S.ksplit - 1) / S.ksplit;
+  const int k0 = ksp * k_per, k1 = min(S.ngl, k0 + k_per), nit = max(0, k1 - k0);
+
+  for (int i = tid; i < 3 * nzr * zs; i += SF_THREADS) Zs[i] = S.zt[i];
+  for (int i = tid; i < na; i += SF_THREADS) { slot_a[i] = S.slot[td.a_row0 + i]; p2l_a[i] = S.p2l[td.a_row0 + i]; }
+  if (tid < nbc) { zrow_b[tid] = S.zrow[td.b_row0 + tid]; p2l_b[tid] = S.p2l[td.b_row0 + tid]; }
+  if (tid < SF_KMAX) slot_z[tid] = tid < nslots ? S.segtab[(size_t)td.seg_a * SF_SEGTAB + 17 + tid] : 0;
+  if (tid == 0) {
+    mbar_init(&bar[0], 1); mbar_init(&bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+  const double* __restrict__ mfg = MODE == 0 ? g.mf + ((size_t)za * 2 + q) * sf_mf_elems(S.ngl, kih)
+                                             : g.pf + ((size_t)za * 2 + q) * sf_pf_elems(S.ngl, kih);
+  auto issue = [&](int il, int buf) {
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    mbar_expect_tx(&bar[buf], (unsigned)L.mf_bytes + (unsigned)na * 32 + (unsigned)nbc * 32);
+    bulk_g2s(smem + L.off_mf[buf], mfg + (size_t)((il * 2 + td.sa) * 2 + td.sb) * (L.mf_bytes / 8), (unsigned)L.mf_bytes, &bar[buf]);
+    bulk_g2s(smem + L.off_ra[buf], S.rg + ((size_t)il * S.dqp_p + td.a_row0) * 4, (unsigned)na * 32, &bar[buf]);
+    bulk_g2s(smem + L.off_rb[buf], S.rg + ((size_t)il * S.dqp_p + td.b_row0) * 4, (unsigned)nbc * 32, &bar[buf]);
+  };
+  if (tid == 0 && nit > 0) issue(k0, 0);
+
+  double hacc[SF_HACC];
+#pragma unroll
+  for (int i = 0; i < SF_HACC; i++) hacc[i] = 0.0;
+  const bool mt2 = nslots > 8;              // two m-tiles of n_z slots: warps split by m-tile, else by K half
+  const int nks = kih >> 2;
+
+  for (int it = 0; it < nit; it++) {
+    const int buf = it & 1;
+    mbar_wait(&bar[buf], (it >> 1) & 1);
+    const double* __restrict__ Rb = reinterpret_cast<const double*>(smem + L.off_rb[buf]);
+    const double* __restrict__ Ra = reinterpret_cast<const double*>(smem + L.off_ra[buf]);
+    // ---- phase G: G^t(ih, (b,c)) = sum_t' mf^{tt'}(ih) phi^t'_b(ih).  A quarter-warp holds 4 grid points x 2 adjacent
+    //      columns (conflict-free 16-byte stores); a thread serves columns b, b+8, b+16, b+24 with one field-tensor load.
+    {
+      const int u = tid >> 3, nihq = kih >> 2;
+      if (u < nihq * 4) {
+        const int ihg = (u % nihq) * 4 + (lane & 3), bpair = u / nihq, bb = (lane >> 2) & 1;
+        const double2* __restrict__ mfs = reinterpret_cast<const double2*>(smem + L.off_mf[buf]) + ihg;
+        double ph[4][NS];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const int b = 2 * bpair + bb + 8 * k;
+          if (b < nbc) {
+            const int zr = zrow_b[b];
+            const double z0 = Zs[zr * zs + ihg];
+            const double r0 = Rb[b * 4];
+            ph[k][0] = z0 * r0;
+            if (MODE == 0) {
+              const double z1 = Zs[(nzr + zr) * zs + ihg], z2 = Zs[(2 * nzr + zr) * zs + ihg];
+              ph[k][1] = z0 * Rb[b * 4 + 1]; ph[k][2] = z0 * Rb[b * 4 + 2]; ph[k][3] = z1 * r0;
+              ph[k][4] = z2 * r0 + z0 * Rb[b * 4 + 3];
+            }
+          } else {
+#pragma unroll
+            for (int t = 0; t < NS; t++) ph[k][t] = 0.0;
+          }
+        }
+#pragma unroll
+        for (int t = 0; t < NS; t++) {
+          double gr[4] = {0.0, 0.0, 0.0, 0.0}, gi[4] = {0.0, 0.0, 0.0, 0.0};
+          if (MODE == 1) {
+            const double2 v = mfs[0];
+#pragma unroll
+            for (int k = 0; k < 4; k++) { gr[k] = v.x * ph[k][0]; gi[k] = v.y * ph[k][0]; }
+          } else {
+#pragma unroll
+            for (int t2 = 0; t2 < NS; t2++)
+              if (sf_mf_nonzero(t, t2)) {
+                const double2 v = mfs[sf_mf_pair(t, t2) * kih];
+#pragma unroll
+                for (int k = 0; k < 4; k++) { gr[k] += v.x * ph[k][t2]; gi[k] += v.y * ph[k][t2]; }
+              }
+          }
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const int b = 2 * bpair + bb + 8 * k;
+            if (b < nbc) *reinterpret_cast<double2*>(&G[((size_t)t * kih + ihg) * SF_GS + 2 * b]) = make_double2(gr[k], gi[k]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // the buffers of the other parity were last read before this barrier (phase G / phase C of the previous iteration)
+    if (tid == 0 && it + 1 < nit) issue(k0 + it + 1, buf ^ 1);
+    // ---- phase W: W^w[slot][(b,c)] = sum_ih Z(slot, ih) G(ih, (b,c)) on the tensor cores
+    {
+      const int nt = warp & 7, part = warp >> 3;
+      if (nt * 4 < nbc) {
+        const int mtile = mt2 ? part : 0;
+        const int ks0 = mt2 ? 0 : (part == 0 ? 0 : (nks + 1) >> 1), ks1 = mt2 ? nks : (part == 0 ? (nks + 1) >> 1 : nks);
+        const int zr = slot_z[mtile * 8 + lr];
+        const double* __restrict__ A0 = Zs + (size_t)zr * zs + lc;
+        const double* __restrict__ gp = G + (size_t)lc * SF_GS + nt * 8 + lr;
+        double C[6][2];
+#pragma unroll
+        for (int i = 0; i < 12; i++) (&C[0][0])[i] = 0.0;
+#pragma unroll 2
+        for (int ks = ks0; ks < ks1; ks++) {
+          const double a0 = A0[ks * 4];
+          const double* __restrict__ gk = gp + (size_t)ks * 4 * SF_GS;
+          const double g0 = gk[0];
+          dmma884(C[0][0], C[0][1], a0, g0);
+          if (MODE == 0) {
+            const double a1 = A0[(size_t)nzr * zs + ks * 4], a2 = A0[(size_t)2 * nzr * zs + ks * 4];
+            const size_t gt = (size_t)kih * SF_GS;
+            const double g1 = gk[gt], g2 = gk[2 * gt], g3 = gk[3 * gt], g4 = gk[4 * gt];
+            dmma884(C[1][0], C[1][1], a0, g1);
+            dmma884(C[2][0], C[2][1], a0, g2);
+            dmma884(C[3][0], C[3][1], a0, g4);
+            dmma884(C[4][0], C[4][1], a1, g3);
+            dmma884(C[5][0], C[5][1], a2, g4);
+          }
+        }
+        double* __restrict__ wp = W + ((size_t)(part * 4) * 8 + lr) * SF_GS + nt * 8 + 2 * lc;
+        if (MODE == 0) {
+          *reinterpret_cast<double2*>(wp) = make_double2(C[0][0] + C[4][0] + C[5][0], C[0][1] + C[4][1] + C[5][1]);
+          *reinterpret_cast<double2*>(wp + 8 * SF_GS) = make_double2(C[1][0], C[1][1]);
+          *reinterpret_cast<double2*>(wp + 16 * SF_GS) = make_double2(C[2][0], C[2][1]);
+          *reinterpret_cast<double2*>(wp + 24 * SF_GS) = make_double2(C[3][0], C[3][1]);
+        } else {
+          *reinterpret_cast<double2*>(wp) = make_double2(C[0][0], C[0][1]);
+        }
+      }
+    }
+    __syncthreads();
+    // ---- phase C: h[a][(b,c)] += sum_w R^w_a(il) W^w[slot(a)][(b,c)]
+    {
+      const int col = tid & 63, ar = tid >> 6;
+      if (col < 2 * nbc) {
+#pragma unroll
+        for (int i = 0; i < SF_HACC; i++) {
+          const int a = ar + 8 * i;
+          if (a < na) {
+            const int sl = slot_a[a];
+            const double* __restrict__ w0 = W + ((size_t)((mt2 ? sl >> 3 : 0) * 4) * 8 + (sl & 7)) * SF_GS + col;
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < NW; w++) {
+              double x = w0[(size_t)w * 8 * SF_GS];
+              if (!mt2) x += w0[(size_t)(4 + w) * 8 * SF_GS];
+              s += Ra[a * 4 + w] * x;
+            }
+            hacc[i] += s;
+          }
+        }
+      }
+    }
+    // W is rewritten after the first barrier of the next iteration, G after this phase: no barrier needed here
+  }
+  __syncthreads();
+  // ---- output through shared memory (rows a fastest): partial of this il split, factor 2 applied by the reduction
+  {
+    double* Tr = G;                                     // [col][na | 1]
+    const int lda = na | 1;
+    const int col = tid & 63, ar = tid >> 6;
+    if (col < 2 * nbc) {
+#pragma unroll
+      for (int i = 0; i < SF_HACC; i++) {
+        const int a = ar + 8 * i;
+        if (a < na) Tr[col * lda + a] = hacc[i];
+      }
+    }
+    __syncthreads();
+    const size_t pstride = 2 * g.nxy;
+    double* __restrict__ part = g.hpart + (((size_t)za * 2 + q) * 2 + MODE) * (size_t)S.ksplit * pstride + (size_t)ksp * pstride;
+    for (int idx = tid; idx < 2 * nbc * na; idx += SF_THREADS) {
+      const int colx = idx / na, a = idx - colx * na;
+      const int lb = p2l_b[colx >> 1];
+      if (lb >= 0) part[(size_t)(colx & 1) * g.nxy + td.out_off + p2l_a[a] + (size_t)lb * td.ld] = Tr[colx * lda + a];
+    }
+  }
+}
+
+// sum the split-K partials (fixed order) and scale by 2
+__global__ void sf_projection_reduce_kernel(HamArgs g, int ksplit) {
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int q = blockIdx.y >> 1, is_delta = blockIdx.y & 1, za = blockIdx.z;
+  if (e >= 2 * g.nxy) return;
+  const int p = g.active[za];
+  const double* part = g.hpart + (((size_t)za * 2 + q) * 2 + is_delta) * (size_t)ksplit * 2 * g.nxy;
+  double s = 0.0;
+  for (int k = 0; k < ksplit; k++) s += part[(size_t)k * 2 * g.nxy + e];
+  const int c = e >= g.nxy ? 1 : 0;
+  const size_t ee = e - (size_t)c * g.nxy;
+  const int quad = is_delta ? g.kap_quad[q] : g.rho_quad[q];
+  g.hsp[(((size_t)p * 2 + c) * 4 + quad) * g.nxy + ee] = 2.0 * s;
+}
+
+void launch_projection_sf(const HamArgs& a, cudaStream_t stream) {
+  if (a.nactive <= 0) return;
+  const SfDev& S = a.sf;
+  const SfProjLayout L0 = make_proj_layout<0>(S), L1 = make_proj_layout<1>(S);
+  static int attr0 = 0, attr1 = 0;
+  if (L0.total > attr0) {
+    PNFAM_CUDA_CHECK(cudaFuncSetAttribute(sf_projection_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, L0.total));
+    attr0 = L0.total;
+  }
+  if (L1.total > attr1) {
+    PNFAM_CUDA_CHECK(cudaFuncSetAttribute(sf_projection_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, L1.total));
+    attr1 = L1.total;
+  }
+  for (int q = 0; q < 2; q++) {
+    if (S.ntiles[0][q] > 0)
+      sf_projection_kernel<0><<<dim3(S.ntiles[0][q], S.ksplit, a.nactive), SF_THREADS, L0.total, stream>>>(a, L0, q);
+    if (S.ntiles[1][q] > 0)
+      sf_projection_kernel<1><<<dim3(S.ntiles[1][q], S.ksplit, a.nactive), SF_THREADS, L1.total, stream>>>(a, L1, q);
+  }
+  dim3 gr((unsigned)((2 * a.nxy + 255) / 256), 4, a.nactive);
+  sf_projection_reduce_kernel<<<gr, 256, 0, stream>>>(a, S.ksplit);
+}
+
+int sf_density_smem_bytes(const SfDev& S) { return make_dens_layout(S).total; }
+int sf_projection_smem_bytes(const SfDev& S) { return std::max(make_proj_layout<0>(S).total, make_proj_layout<1>(S).total); }
+
+}  // namespace pnfam

@@ -72,8 +72,55 @@ constexpr int DENS_MAXSTEPS = 2048;      // steps of one density pass (their dep
 constexpr int DENS_AC = 48;   // contraction chunk
 constexpr int DENS_BC = 32;   // column chunk
 
+// ---- sum-factorised path (hamiltonian_sf.cu): used when the model carries the separable factors of the basis ----
+// phi^t_a(ih, il) = Z(zrow_a, ih) R_a(il):  the contraction over a runs over the radial index first (FMA, small) and
+// over n_z second (DMMA with K = number of distinct n_z of the spin segment), see hamiltonian_sf.cu.
+constexpr int SF_KMAX = 16;      // distinct n_z ("slots") per spin segment
+constexpr int SF_SEGTAB = 40;    // ints per segment table: [0..16] first row of slot k (rows sorted by slot; [nslots] = n),
+                                 // [17..32] z-table row of slot k, [33] nslots, [34] n
+constexpr int SF_THREADS = 512;
+constexpr int SF_MFP = 18;       // structurally non-zero (t,t') pairs of the field tensor
+struct SfDensStep {              // one (a spin segment) x (b column chunk inside one spin segment) piece of a block
+  int seg_a, a_row0, na, nslots; // segment index 2*block+s, first padded row, states, distinct n_z
+  int b_row0, nbc;               // first padded row of the column chunk, padded columns (multiple of 4)
+  int img_off;                   // offset (doubles) of the packed rho image [na][2 nbc] of this step
+  int sweep;                     // s*2 + s'  (the kernel accumulates one (s,s') combination at a time)
+  int flags;                     // bit0: last step of its sweep
+  int rho_off, ld;               // element offset of the block in the block matrix, leading dimension
+  int pad;
+};
+struct SfProjTile {              // output tile of the projection: (a spin segment) x (b column chunk in one spin segment)
+  int seg_a, a_row0, na, nslots;
+  int b_row0, nbc, sa, sb;
+  int out_off, ld, pad0, pad1;
+};
+struct SfDev {
+  int enabled = 0;
+  int ngh = 0, ngl = 0, mt = 0;  // mt: DMMA m-tiles (8 grid points) per il
+  int kih = 0;                   // ngh padded to a multiple of 4
+  int zs = 0;                    // row stride of the z tables (doubles), zs % 16 == 4
+  int nzrows = 0, dqp_p = 0;
+  const double* zt = nullptr;    // [3][nzrows][zs]  Z0, Z1, Z2 (zero beyond ngh)
+  const double* rg = nullptr;    // [ngl][dqp_p][4]  R0..R3 per padded row (rows of a segment sorted by n_z slot)
+  const int* zrow = nullptr;     // [dqp_p] z-table row of a padded row (0 for padding)
+  const int* p2l = nullptr;      // [dqp_p] index of the state inside its block, -1 for padding
+  const int* slot = nullptr;     // [dqp_p] n_z slot of the row inside its spin segment
+  const int* segtab = nullptr;   // [2 nb][SF_SEGTAB]
+  const SfDensStep* steps[4] = {nullptr, nullptr, nullptr, nullptr};   // rho q0, rho q1, kappa q0, kappa q1
+  int nsteps[4] = {0, 0, 0, 0};
+  size_t pk_stride[2] = {0, 0};  // doubles of packed images per (point, pass): rho, kappa
+  double* pk[2] = {nullptr, nullptr};
+  int na_max = 0, nbc_max = 0, kpad_max = 0;
+  const SfProjTile* tiles[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [h / Delta][pass]
+  int ntiles[2][2] = {{0, 0}, {0, 0}};
+  int ksplit = 1;
+};
+__host__ __device__ inline size_t sf_mf_elems(int ngl, int kih) { return (size_t)ngl * 4 * SF_MFP * kih * 2; }
+__host__ __device__ inline size_t sf_pf_elems(int ngl, int kih) { return (size_t)ngl * 4 * kih * 2; }
+
 struct HamArgs {
   DevBasis basis;
+  SfDev sf;
   // per pass q=0 (pn,+) / q=1 (np,-): input structures (dRsp quadrants) and output structures (dHsp quadrants)
   DevBlockStruct rho_in[2], kap_in[2], h_out[2], d_out[2];
   int rho_quad[2], kap_quad[2];   // storage quadrant of rho / kappa (and of h / Delta) for each pass
@@ -109,6 +156,11 @@ void build_density_steps(int nb, const int* db, const int* pstart, const int* ns
 void launch_fields(const HamArgs& a, cudaStream_t stream);
 void launch_projection(const HamArgs& a, const ProjPlan& pp, cudaStream_t stream);
 size_t projection_partial_elems(const ProjPlan& pp, size_t nxy);
+// sum-factorised variants (hamiltonian_sf.cu)
+void launch_density_sf(const HamArgs& a, cudaStream_t stream);
+void launch_projection_sf(const HamArgs& a, cudaStream_t stream);
+int sf_density_smem_bytes(const SfDev& S);      // dynamic shared memory the kernels need for this basis
+int sf_projection_smem_bytes(const SfDev& S);
 
 // ---- (d) Greens function update, Broyden mixer, strength -----------------------------------------
 struct MixArgs {

@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <vector>
@@ -91,9 +92,107 @@ struct pnfam_b200_ctx {
   DBuf<double> d_phi4, d_phi5, d_phi0, d_wdcori, d_crho, d_cs, d_cpair, d_cspair;
   DBuf<double> d_Up, d_Vp, d_Un, d_Vn;
   DevBasis basis{};
+  // sum-factorised path (separable basis, hamiltonian_sf.cu)
+  SfDev sf{};
+  std::vector<int> seg_prow0, seg_n, seg_nslots;   // per (block, spin) segment: first padded row, states, n_z slots
+  DBuf<double> d_zt, d_rg;
+  DBuf<int> d_zrow, d_p2l, d_slot, d_segtab;
   cudaStream_t stream = nullptr;
   int64_t launches = 0;
+  int64_t table_h2d_bytes = 0;   // bytes of basis tables uploaded by ctx_create
 };
+
+// Set-up of the sum-factorised path from the separable factors of the model (include/pnfam_b200.h).  Returns false
+// (general-table kernels are used) when the factors are absent or outside the tile limits of the kernels; throws when
+// they do not reproduce the full tables.
+static bool setup_separable(pnfam_b200_ctx& c, const pnfam_b200_model& m) {
+  if (m.ngh <= 0 || m.ngl <= 0 || !m.sep_zrow || !m.sep_z || !m.sep_r || getenv("PNFAM_B200_GENERAL_TABLES")) return false;
+  const int ngh = m.ngh, ngl = m.ngl, nzr = m.sep_nzrows, N = c.dqp, nghl = c.nghl;
+  if ((size_t)ngh * ngl != (size_t)nghl) throw std::runtime_error("model: ngh*ngl != nghl");
+  const int mt = (ngh + 7) / 8, kih = (ngh + 3) & ~3;
+  if (2 * mt > SF_THREADS / 32 || 8 * kih > SF_THREADS) return false;
+  int zs = std::max(8 * mt, kih);
+  while (zs % 16 != 4) zs++;
+  // the factors must reproduce the tables
+  {
+    const double* tab[5] = {m.wf, m.wfdr, m.wfdp, m.wfdz, m.wfd2_all};
+    double scale[5] = {0, 0, 0, 0, 0}, err[5] = {0, 0, 0, 0, 0};
+#pragma omp parallel for schedule(static)
+    for (int a = 0; a < N; a++) {
+      double sc[5] = {0, 0, 0, 0, 0}, er[5] = {0, 0, 0, 0, 0};
+      const int z = m.sep_zrow[a];
+      if (z < 0 || z >= nzr) { er[0] = 1e300; sc[0] = 1; }
+      else
+        for (int il = 0; il < ngl; il++) {
+          double R[4];
+          for (int j = 0; j < 4; j++) R[j] = m.sep_r[((size_t)j * N + a) * ngl + il];
+          for (int ih = 0; ih < ngh; ih++) {
+            const double z0 = m.sep_z[((size_t)0 * nzr + z) * ngh + ih], z1 = m.sep_z[((size_t)1 * nzr + z) * ngh + ih];
+            const double z2 = m.sep_z[((size_t)2 * nzr + z) * ngh + ih];
+            const double v[5] = {z0 * R[0], z0 * R[1], z0 * R[2], z1 * R[0], z2 * R[0] + z0 * R[3]};
+            const size_t o = (size_t)a * nghl + ih + (size_t)il * ngh;
+            for (int t = 0; t < 5; t++) { sc[t] = std::max(sc[t], std::fabs(tab[t][o])); er[t] = std::max(er[t], std::fabs(tab[t][o] - v[t])); }
+          }
+        }
+#pragma omp critical
+      for (int t = 0; t < 5; t++) { scale[t] = std::max(scale[t], sc[t]); err[t] = std::max(err[t], er[t]); }
+    }
+    for (int t = 0; t < 5; t++)
+      if (err[t] > 1e-11 * std::max(scale[t], 1e-300))
+        throw std::runtime_error("model: the separable factors (sep_z, sep_r) do not reproduce wave-function table " + std::to_string(t));
+  }
+  // z rows: even and odd n_z in two contiguous groups, so that the slots of a spin segment (n_z of one parity in a
+  // regular basis) are consecutive rows (conflict-free fragment loads)
+  std::vector<int> rmap(nzr);
+  for (int z = 0; z < nzr; z++) rmap[z] = (z >> 1) + (z & 1) * ((nzr + 1) / 2);
+  std::vector<double> zt((size_t)3 * nzr * zs, 0.0);
+  for (int k = 0; k < 3; k++)
+    for (int z = 0; z < nzr; z++)
+      for (int ih = 0; ih < ngh; ih++) zt[((size_t)k * nzr + rmap[z]) * zs + ih] = m.sep_z[((size_t)k * nzr + z) * ngh + ih];
+  auto pad4 = [](int x) { return (x + 3) & ~3; };
+  const int nseg = 2 * c.nb;
+  c.seg_prow0.assign(nseg, 0); c.seg_n.assign(nseg, 0); c.seg_nslots.assign(nseg, 0);
+  std::vector<int> zrow(c.dqp_p, 0), p2l(c.dqp_p, -1), slot(c.dqp_p, 0), segtab((size_t)nseg * SF_SEGTAB, 0), p2s(c.dqp_p, -1);
+  for (int ib = 0; ib < c.nb; ib++)
+    for (int sp = 0; sp < 2; sp++) {
+      const int seg = 2 * ib + sp;
+      const int first = sp == 0 ? 0 : c.nsu[ib], n = sp == 0 ? c.nsu[ib] : c.db[ib] - c.nsu[ib];
+      const int prow0 = c.pstart[ib] + (sp == 0 ? 0 : pad4(c.nsu[ib]));
+      c.seg_prow0[seg] = prow0; c.seg_n[seg] = n;
+      std::vector<int> loc(n);
+      for (int i = 0; i < n; i++) loc[i] = first + i;
+      std::stable_sort(loc.begin(), loc.end(), [&](int x, int y) { return rmap[m.sep_zrow[c.isstart[ib] + x]] < rmap[m.sep_zrow[c.isstart[ib] + y]]; });
+      int* st = &segtab[(size_t)seg * SF_SEGTAB];
+      int ns = 0;
+      for (int i = 0; i < n; i++) {
+        const int zr = rmap[m.sep_zrow[c.isstart[ib] + loc[i]]];
+        if (i == 0 || zr != zrow[prow0 + i - 1]) {
+          if (ns >= SF_KMAX) return false;
+          st[ns] = i; st[17 + ns] = zr; ns++;
+        }
+        zrow[prow0 + i] = zr; p2l[prow0 + i] = loc[i]; slot[prow0 + i] = ns - 1; p2s[prow0 + i] = c.isstart[ib] + loc[i];
+      }
+      st[ns] = n; st[33] = ns; st[34] = n;
+      c.seg_nslots[seg] = ns;
+    }
+  std::vector<double> rg((size_t)ngl * c.dqp_p * 4, 0.0);
+  for (int il = 0; il < ngl; il++)
+    for (int pr = 0; pr < c.dqp_p; pr++)
+      if (p2s[pr] >= 0)
+        for (int j = 0; j < 4; j++) rg[((size_t)il * c.dqp_p + pr) * 4 + j] = m.sep_r[((size_t)j * N + p2s[pr]) * ngl + il];
+  c.d_zt.upload(zt); c.d_rg.upload(rg); c.d_zrow.upload(zrow); c.d_p2l.upload(p2l); c.d_slot.upload(slot); c.d_segtab.upload(segtab);
+  SfDev& S = c.sf;
+  S.enabled = 1; S.ngh = ngh; S.ngl = ngl; S.mt = mt; S.kih = kih; S.zs = zs; S.nzrows = nzr; S.dqp_p = c.dqp_p;
+  S.zt = c.d_zt.p; S.rg = c.d_rg.p; S.zrow = c.d_zrow.p; S.p2l = c.d_p2l.p; S.slot = c.d_slot.p; S.segtab = c.d_segtab.p;
+  S.na_max = 1; S.kpad_max = 4;
+  for (int seg = 0; seg < nseg; seg++) { S.na_max = std::max(S.na_max, c.seg_n[seg]); S.kpad_max = std::max(S.kpad_max, pad4(c.seg_nslots[seg])); }
+  if (S.na_max > 8 * 12) return S.enabled = 0, false;
+  // column chunk of the density: the largest that fits the shared memory of an SM
+  S.nbc_max = 32;
+  if (sf_density_smem_bytes(S) > 227 * 1024) S.nbc_max = 16;
+  if (sf_density_smem_bytes(S) > 227 * 1024 || sf_projection_smem_bytes(S) > 227 * 1024) return S.enabled = 0, false;
+  return true;
+}
 
 static void set_err(char* err, int errlen, const std::string& s) {
   if (err && errlen > 0) {
@@ -131,7 +230,7 @@ extern "C" int pnfam_b200_ctx_create(const pnfam_b200_model* m, int device, pnfa
     c->use_diag = m->qp_fp != nullptr && m->qp_fn != nullptr;
     if (c->use_diag) { c->qp_fp.assign(m->qp_fp, m->qp_fp + m->dqp); c->qp_fn.assign(m->qp_fn, m->qp_fn + m->dqp); }
     c->d_db.upload(c->db); c->d_isstart.upload(c->isstart); c->d_nsu.upload(c->nsu);
-    // ---- wave-function tables in the layouts the kernels copy linearly (device_common.cuh)
+    // ---- padded index space; wave-function tables in the layouts the kernels copy linearly (device_common.cuh)
     {
       auto pad4 = [](int x) { return (x + 3) & ~3; };
       c->pstart.resize(m->nb);
@@ -143,23 +242,29 @@ extern "C" int pnfam_b200_ctx_create(const pnfam_b200_model* m, int device, pnfa
       }
       c->dqp_p = (int)p2s.size();
       c->d_pstart.upload(c->pstart);
-      // the reference's (nghl, dqp) tables go up as they are; the re-layout runs on the device
-      const double* tab[NTYPE] = {m->wf, m->wfdr, m->wfdp, m->wfdz, m->wfd2_all};
-      const size_t nraw = (size_t)c->dqp * c->nghl;
-      DBuf<double> raw;
-      raw.alloc(NTYPE * nraw);
-      for (int t = 0; t < NTYPE; t++) PNFAM_CUDA_CHECK(cudaMemcpy(raw.p + t * nraw, tab[t], nraw * sizeof(double), cudaMemcpyHostToDevice));
-      DBuf<int> d_p2s;
-      d_p2s.upload(p2s);
-      const int nsuper = (c->ntiles + 3) / 4;
-      const size_t tail = (size_t)8 * NTYPE * RT;              // chunk copies may run a few rows past the last block
-      c->d_phi5.alloc((size_t)c->ntiles * c->dqp_p * NTYPE * RT + tail); c->d_phi4.alloc((size_t)c->ntiles * c->dqp_p * 4 * RT + tail);
-      c->d_phi0.alloc((size_t)nsuper * c->dqp_p * 4 * RT + tail);
-      c->d_phi5.zero(); c->d_phi4.zero(); c->d_phi0.zero();
-      build_tables_kernel<<<dim3(c->ntiles, (c->dqp_p + 7) / 8), dim3(RT, 8)>>>(raw.p, nraw, d_p2s.p, c->dqp_p, c->nghl, c->d_phi5.p, c->d_phi4.p,
-                                                                           c->d_phi0.p);
-      PNFAM_CUDA_CHECK(cudaGetLastError());
-      PNFAM_CUDA_CHECK(cudaDeviceSynchronize());
+      // separable basis: the sum-factorised kernels need no Ng x N table on the device at all
+      if (!setup_separable(*c, *m)) {
+        // the reference's (nghl, dqp) tables go up as they are; the re-layout runs on the device
+        const double* tab[NTYPE] = {m->wf, m->wfdr, m->wfdp, m->wfdz, m->wfd2_all};
+        const size_t nraw = (size_t)c->dqp * c->nghl;
+        DBuf<double> raw;
+        raw.alloc(NTYPE * nraw);
+        for (int t = 0; t < NTYPE; t++) PNFAM_CUDA_CHECK(cudaMemcpy(raw.p + t * nraw, tab[t], nraw * sizeof(double), cudaMemcpyHostToDevice));
+        DBuf<int> d_p2s;
+        d_p2s.upload(p2s);
+        const int nsuper = (c->ntiles + 3) / 4;
+        const size_t tail = (size_t)8 * NTYPE * RT;              // chunk copies may run a few rows past the last block
+        c->d_phi5.alloc((size_t)c->ntiles * c->dqp_p * NTYPE * RT + tail); c->d_phi4.alloc((size_t)c->ntiles * c->dqp_p * 4 * RT + tail);
+        c->d_phi0.alloc((size_t)nsuper * c->dqp_p * 4 * RT + tail);
+        c->d_phi5.zero(); c->d_phi4.zero(); c->d_phi0.zero();
+        build_tables_kernel<<<dim3(c->ntiles, (c->dqp_p + 7) / 8), dim3(RT, 8)>>>(raw.p, nraw, d_p2s.p, c->dqp_p, c->nghl, c->d_phi5.p, c->d_phi4.p,
+                                                                             c->d_phi0.p);
+        PNFAM_CUDA_CHECK(cudaGetLastError());
+        PNFAM_CUDA_CHECK(cudaDeviceSynchronize());
+        c->table_h2d_bytes = (int64_t)NTYPE * nraw * 8;
+      } else {
+        c->table_h2d_bytes = (int64_t)(c->d_zt.n + c->d_rg.n) * 8 + (int64_t)(c->d_zrow.n + c->d_p2l.n + c->d_slot.n + c->d_segtab.n) * 4;
+      }
     }
     auto up = [&](DBuf<double>& d, const double* p, size_t n) { d.upload(std::vector<double>(p, p + n)); };
     up(c->d_wdcori, m->wdcori, m->nghl); up(c->d_crho, m->crho, m->nghl); up(c->d_cs, m->cs, m->nghl);
@@ -180,6 +285,8 @@ extern "C" int pnfam_b200_ctx_create(const pnfam_b200_model* m, int device, pnfa
     return 1;
   }
 }
+
+extern "C" int pnfam_b200_ctx_separable(const pnfam_b200_ctx* c) { return c && c->sf.enabled ? 1 : 0; }
 
 extern "C" void pnfam_b200_ctx_destroy(pnfam_b200_ctx* c) {
   if (!c) return;
@@ -204,7 +311,70 @@ struct OperatorDev {
   int ndsteps[4] = {0, 0, 0, 0};
   size_t scratch_elems = 0;
   size_t pk_rho = 0, pk_kap = 0;  // doubles of the packed rho / kappa chunks per (point, pass)
+  // sum-factorised path
+  DBuf<SfDensStep> sf_steps[4];
+  int sf_nsteps[4] = {0, 0, 0, 0};
+  DBuf<SfProjTile> sf_tiles[2][2];
+  int sf_ntiles[2][2] = {{0, 0}, {0, 0}};
+  int sf_ksplit = 1;
 };
+
+// sum-factorised density: (s, s') sweeps over the blocks of a structure, columns in chunks of nbc_max
+size_t upload_sf_density_steps(const pnfam_b200_ctx& c, const BlockStruct& st, DBuf<SfDensStep>& buf, int& n) {
+  std::vector<SfDensStep> h;
+  size_t img = 0;
+  for (int sweep = 0; sweep < 4; sweep++) {
+    const size_t first = h.size();
+    for (int ix = 0; ix < c.nb; ix++) {
+      const int iy = st.r2c[ix];
+      if (iy < 0) continue;
+      const int sa = 2 * ix + (sweep >> 1), sb = 2 * iy + (sweep & 1);
+      if (c.seg_n[sa] == 0 || c.seg_n[sb] == 0) continue;
+      const int nb4 = (c.seg_n[sb] + 3) & ~3;
+      for (int b0 = 0; b0 < nb4; b0 += c.sf.nbc_max) {
+        SfDensStep d{};
+        d.seg_a = sa; d.a_row0 = c.seg_prow0[sa]; d.na = c.seg_n[sa]; d.nslots = c.seg_nslots[sa];
+        d.b_row0 = c.seg_prow0[sb] + b0; d.nbc = std::min(c.sf.nbc_max, nb4 - b0);
+        d.img_off = (int)img; d.sweep = sweep; d.flags = 0; d.rho_off = st.r2m[ix]; d.ld = c.db[ix];
+        img += (size_t)d.na * 2 * d.nbc;
+        h.push_back(d);
+      }
+    }
+    if (h.size() > first) h.back().flags |= 1;
+  }
+  if (img > 0x7fffffffull) throw std::runtime_error("density: packed image offsets overflow");
+  n = (int)h.size();
+  if (h.empty()) h.push_back(SfDensStep{});
+  buf.upload(h);
+  return img;
+}
+
+void upload_sf_proj_tiles(const pnfam_b200_ctx& c, const BlockStruct& st, DBuf<SfProjTile>& buf, int& n) {
+  std::vector<SfProjTile> h;
+  for (int ix = 0; ix < c.nb; ix++) {
+    const int iy = st.r2c[ix];
+    if (iy < 0) continue;
+    for (int s = 0; s < 4; s++) {
+      const int sa = 2 * ix + (s >> 1), sb = 2 * iy + (s & 1);
+      if (c.seg_n[sa] == 0 || c.seg_n[sb] == 0) continue;
+      const int nb4 = (c.seg_n[sb] + 3) & ~3;
+      for (int b0 = 0; b0 < nb4; b0 += 32) {
+        SfProjTile t{};
+        t.seg_a = sa; t.a_row0 = c.seg_prow0[sa]; t.na = c.seg_n[sa]; t.nslots = c.seg_nslots[sa];
+        t.b_row0 = c.seg_prow0[sb] + b0; t.nbc = std::min(32, nb4 - b0); t.sa = s >> 1; t.sb = s & 1;
+        t.out_off = st.r2m[ix]; t.ld = c.db[ix];
+        h.push_back(t);
+      }
+    }
+  }
+  // the long tiles first: the short ones fill the tail of the launch
+  std::stable_sort(h.begin(), h.end(), [](const SfProjTile& x, const SfProjTile& y) {
+    return (long)x.nbc * (x.nslots > 8 ? 16 : 8) > (long)y.nbc * (y.nslots > 8 ? 16 : 8);
+  });
+  n = (int)h.size();
+  if (h.empty()) h.push_back(SfProjTile{});
+  buf.upload(h);
+}
 
 // returns the number of doubles of the packed rho chunks of this step list
 size_t upload_density_steps(const pnfam_b200_ctx& c, const BlockStruct& st, DBuf<DensStep>& buf, int& n) {
@@ -285,6 +455,20 @@ std::unique_ptr<OperatorDev> make_operator(pnfam_b200_ctx& c, const pnfam_b200_o
   flatten(od->plan.backward, od->bwd_tasks, od->bwd_entries, od->bwd);
   od->scratch_elems = std::max(od->fwd.scratch_elems, od->bwd.scratch_elems);
   for (int k = 0; k < 4; k++) { od->sp[k].upload(od->plan.sp[k]); od->hsp[k].upload(od->plan.hsp[k]); }
+  if (c.sf.enabled) {
+    od->pk_rho = std::max(upload_sf_density_steps(c, od->plan.sp[0], od->sf_steps[0], od->sf_nsteps[0]),
+                          upload_sf_density_steps(c, od->plan.sp[3], od->sf_steps[1], od->sf_nsteps[1]));
+    od->pk_kap = std::max(upload_sf_density_steps(c, od->plan.sp[1], od->sf_steps[2], od->sf_nsteps[2]),
+                          upload_sf_density_steps(c, od->plan.sp[2], od->sf_steps[3], od->sf_nsteps[3]));
+    upload_sf_proj_tiles(c, od->plan.hsp[0], od->sf_tiles[0][0], od->sf_ntiles[0][0]);
+    upload_sf_proj_tiles(c, od->plan.hsp[3], od->sf_tiles[0][1], od->sf_ntiles[0][1]);
+    upload_sf_proj_tiles(c, od->plan.hsp[1], od->sf_tiles[1][0], od->sf_ntiles[1][0]);
+    upload_sf_proj_tiles(c, od->plan.hsp[2], od->sf_tiles[1][1], od->sf_ntiles[1][1]);
+    const int per = std::max(1, od->sf_ntiles[0][0] * std::max(1, npoints));
+    od->sf_ksplit = std::min(c.sf.ngl, std::max(1, (2 * 148 + per - 1) / per));
+    od->proj.ksplit = od->sf_ksplit;      // sizes the split-K partials
+    return od;
+  }
   od->pk_rho = std::max(upload_density_steps(c, od->plan.sp[0], od->dsteps[0], od->ndsteps[0]),
                         upload_density_steps(c, od->plan.sp[3], od->dsteps[1], od->ndsteps[1]));
   od->pk_kap = std::max(upload_density_steps(c, od->plan.sp[1], od->dsteps[2], od->ndsteps[2]),
@@ -320,6 +504,14 @@ HamArgs make_ham_args(const pnfam_b200_ctx& c, const OperatorDev& od) {
     h.steps_kap[q] = od.dsteps[2 + q].p; h.nsteps_kap[q] = od.ndsteps[2 + q];
   }
   h.pk_stride_rho = od.pk_rho; h.pk_stride_kap = od.pk_kap;
+  h.sf = c.sf;
+  if (c.sf.enabled) {
+    for (int k = 0; k < 4; k++) { h.sf.steps[k] = od.sf_steps[k].p; h.sf.nsteps[k] = od.sf_nsteps[k]; }
+    for (int m = 0; m < 2; m++)
+      for (int q = 0; q < 2; q++) { h.sf.tiles[m][q] = od.sf_tiles[m][q].p; h.sf.ntiles[m][q] = od.sf_ntiles[m][q]; }
+    h.sf.ksplit = od.sf_ksplit;
+    h.sf.pk_stride[0] = od.pk_rho; h.sf.pk_stride[1] = od.pk_kap;
+  }
   return h;
 }
 
@@ -394,8 +586,11 @@ extern "C" int pnfam_b200_solve(pnfam_b200_ctx* c, const pnfam_b200_operator* op
     scratch.alloc((size_t)P * 2 * std::max<size_t>(od->scratch_elems, 1));
     dd_rho.alloc((size_t)P * 2 * NDD_RHO * c->nghl); dd_kap.alloc((size_t)P * 2 * NDD_KAP * c->nghl);
     // field tensors are tile-major (kernels.cuh); the padding grid points are zeroed once and never written
-    mf.alloc((size_t)P * 2 * mf_elems(c->ntiles)); pf.alloc((size_t)P * 2 * pf_elems(c->ntiles));
+    const bool sf = c->sf.enabled != 0;
+    mf.alloc((size_t)P * 2 * (sf ? sf_mf_elems(c->sf.ngl, c->sf.kih) : mf_elems(c->ntiles)));
+    pf.alloc((size_t)P * 2 * (sf ? sf_pf_elems(c->sf.ngl, c->sf.kih) : pf_elems(c->ntiles)));
     mf.zero(); pf.zero();
+    if (sf) { dd_rho.zero(); dd_kap.zero(); }             // (s, s') sweeps without any step are never written
     pk_rho.alloc((size_t)P * 2 * std::max<size_t>(od->pk_rho, 1)); pk_kap.alloc((size_t)P * 2 * std::max<size_t>(od->pk_kap, 1));
     hpart.alloc((size_t)P * projection_partial_elems(od->proj, nxy));
     d_active.alloc(P);
@@ -437,6 +632,7 @@ extern "C" int pnfam_b200_solve(pnfam_b200_ctx* c, const pnfam_b200_operator* op
     HamArgs ha = make_ham_args(*c, *od);
     ha.rsp = rsp.p; ha.hsp = hsp.p; ha.dd_rho = dd_rho.p; ha.dd_kap = dd_kap.p; ha.mf = mf.p; ha.pf = pf.p;
     ha.pk_rho = pk_rho.p; ha.pk_kap = pk_kap.p;
+    ha.sf.pk[0] = pk_rho.p; ha.sf.pk[1] = pk_kap.p;
     ha.hpart = hpart.p; ha.active = d_active.p;
 
     MixArgs ma{};
@@ -581,20 +777,36 @@ extern "C" int pnfam_b200_calc_hamiltonian(pnfam_b200_ctx* c, const pnfam_b200_b
     h.h_out[0] = sout[0].view(); h.d_out[0] = sout[1].view(); h.h_out[1] = sout[2].view(); h.d_out[1] = sout[3].view();
     h.rho_quad[0] = 0; h.kap_quad[0] = 1; h.rho_quad[1] = 3; h.kap_quad[1] = 2;
     h.nxy = nxy;
+    const bool sf = c->sf.enabled != 0;
     DBuf<DensStep> dsteps[4];
     int ndsteps[4];
-    h.pk_stride_rho = std::max(upload_density_steps(*c, hin[0], dsteps[0], ndsteps[0]), upload_density_steps(*c, hin[2], dsteps[1], ndsteps[1]));
-    h.pk_stride_kap = std::max(upload_density_steps(*c, hin[1], dsteps[2], ndsteps[2]), upload_density_steps(*c, hin[3], dsteps[3], ndsteps[3]));
+    DBuf<SfDensStep> sf_steps[4];
+    DBuf<SfProjTile> sf_tiles[2][2];
     DBuf<double> pk_rho, pk_kap;
-    pk_rho.alloc(2 * std::max<size_t>(h.pk_stride_rho, 1)); pk_kap.alloc(2 * std::max<size_t>(h.pk_stride_kap, 1));
-    h.pk_rho = pk_rho.p; h.pk_kap = pk_kap.p;
-    for (int q = 0; q < 2; q++) {
-      h.steps_rho[q] = dsteps[q].p; h.nsteps_rho[q] = ndsteps[q];
-      h.steps_kap[q] = dsteps[2 + q].p; h.nsteps_kap[q] = ndsteps[2 + q];
-    }
     ProjPlan pp;
     DBuf<int4> th, td;
-    {
+    h.sf = c->sf;
+    if (sf) {
+      // argument pairs: 0 rho_pn (pass 0), 1 kappa+ (pass 0), 2 rho_np (pass 1), 3 kappa- (pass 1)
+      h.pk_stride_rho = std::max(upload_sf_density_steps(*c, hin[0], sf_steps[0], h.sf.nsteps[0]), upload_sf_density_steps(*c, hin[2], sf_steps[1], h.sf.nsteps[1]));
+      h.pk_stride_kap = std::max(upload_sf_density_steps(*c, hin[1], sf_steps[2], h.sf.nsteps[2]), upload_sf_density_steps(*c, hin[3], sf_steps[3], h.sf.nsteps[3]));
+      for (int k = 0; k < 4; k++) h.sf.steps[k] = sf_steps[k].p;
+      upload_sf_proj_tiles(*c, hout[0], sf_tiles[0][0], h.sf.ntiles[0][0]);
+      upload_sf_proj_tiles(*c, hout[2], sf_tiles[0][1], h.sf.ntiles[0][1]);
+      upload_sf_proj_tiles(*c, hout[1], sf_tiles[1][0], h.sf.ntiles[1][0]);
+      upload_sf_proj_tiles(*c, hout[3], sf_tiles[1][1], h.sf.ntiles[1][1]);
+      for (int m = 0; m < 2; m++)
+        for (int q = 0; q < 2; q++) h.sf.tiles[m][q] = sf_tiles[m][q].p;
+      h.sf.ksplit = std::min(c->sf.ngl, std::max(1, (2 * 148 + std::max(1, h.sf.ntiles[0][0]) - 1) / std::max(1, h.sf.ntiles[0][0])));
+      pp.ksplit = h.sf.ksplit;
+      h.sf.pk_stride[0] = h.pk_stride_rho; h.sf.pk_stride[1] = h.pk_stride_kap;
+    } else {
+      h.pk_stride_rho = std::max(upload_density_steps(*c, hin[0], dsteps[0], ndsteps[0]), upload_density_steps(*c, hin[2], dsteps[1], ndsteps[1]));
+      h.pk_stride_kap = std::max(upload_density_steps(*c, hin[1], dsteps[2], ndsteps[2]), upload_density_steps(*c, hin[3], dsteps[3], ndsteps[3]));
+      for (int q = 0; q < 2; q++) {
+        h.steps_rho[q] = dsteps[q].p; h.nsteps_rho[q] = ndsteps[q];
+        h.steps_kap[q] = dsteps[2 + q].p; h.nsteps_kap[q] = ndsteps[2 + q];
+      }
       std::vector<int4> vh, vd;
       BlockStruct shh[2] = {hout[0], hout[2]}, sdd[2] = {hout[1], hout[3]};
       build_proj_tiles(*c, shh, vh, pp.ntiles_h, pp.tile_off_h);
@@ -604,8 +816,13 @@ extern "C" int pnfam_b200_calc_hamiltonian(pnfam_b200_ctx* c, const pnfam_b200_b
       const int per = std::max(1, pp.ntiles_h[0]);
       pp.ksplit = std::min(std::min(c->ntiles, 32), std::max(1, (2 * 148 + per - 1) / per));
     }
+    pk_rho.alloc(2 * std::max<size_t>(h.pk_stride_rho, 1)); pk_kap.alloc(2 * std::max<size_t>(h.pk_stride_kap, 1));
+    h.pk_rho = pk_rho.p; h.pk_kap = pk_kap.p;
+    h.sf.pk[0] = pk_rho.p; h.sf.pk[1] = pk_kap.p;
     dd_rho.alloc((size_t)2 * NDD_RHO * c->nghl); dd_kap.alloc((size_t)2 * NDD_KAP * c->nghl);
-    mf.alloc((size_t)2 * mf_elems(c->ntiles)); pf.alloc((size_t)2 * pf_elems(c->ntiles));
+    dd_rho.zero(); dd_kap.zero();
+    mf.alloc((size_t)2 * (sf ? sf_mf_elems(c->sf.ngl, c->sf.kih) : mf_elems(c->ntiles)));
+    pf.alloc((size_t)2 * (sf ? sf_pf_elems(c->sf.ngl, c->sf.kih) : pf_elems(c->ntiles)));
     mf.zero(); pf.zero();
     hpart.alloc(projection_partial_elems(pp, nxy));
     std::vector<int> act = {0};

@@ -57,7 +57,7 @@ int pnfam_problem_scalar(const pnfam_problem* h, const char* name, double* out) 
   const FamInput& in = p.in;
   const std::string n(name);
   std::map<std::string, double> m = {
-      {"nb", b.nb}, {"dqp", b.dqp}, {"nghl", b.nghl}, {"n_shells", b.n_shells}, {"dmat", (double)b.dmat},
+      {"nb", b.nb}, {"dqp", b.dqp}, {"nghl", b.nghl}, {"ngh", b.ngh}, {"ngl", b.ngl}, {"sep_nzrows", b.sep_nzrows}, {"n_shells", b.n_shells}, {"dmat", (double)b.dmat},
       {"npr_n", b.npr[0]}, {"npr_p", b.npr[1]}, {"nxy", (double)p.f.mat.elem.size()}, {"nxterms", (double)p.g.size()},
       {"beta_minus", p.f.beta_minus}, {"blo_active", b.blo_active},
       {"blo_qp_n", b.blo_qp[0]}, {"blo_qp_p", b.blo_qp[1]},
@@ -89,7 +89,7 @@ int pnfam_problem_array_f64(pnfam_problem* h, const char* name, const double** p
   const std::vector<double>* v = nullptr;
   std::map<std::string, const std::vector<double>*> m = {
       {"wf", &b.wf}, {"wfdr", &b.wfdr}, {"wfdz", &b.wfdz}, {"wfd2", &b.wfd2}, {"wfdp", &b.wfdp}, {"wfd2_all", &b.wfd2_all},
-      {"y", &b.y}, {"z", &b.z}, {"wdcori", &b.wdcori}, {"Ep", &b.Ep}, {"En", &b.En},
+      {"y", &b.y}, {"z", &b.z}, {"sep_z", &b.sep_z}, {"sep_r", &b.sep_r}, {"wdcori", &b.wdcori}, {"Ep", &b.Ep}, {"En", &b.En},
       {"Up", &b.Up}, {"Vp", &b.Vp}, {"Un", &b.Un}, {"Vn", &b.Vn}, {"rho_n", &b.rho_n}, {"rho_p", &b.rho_p},
       {"qp_fn", &b.qp_fn}, {"qp_fp", &b.qp_fp},
       {"crho", &x.crho}, {"cs", &x.cs}, {"cpair", &x.cpair}, {"cspair", &x.cspair},
@@ -117,7 +117,7 @@ int pnfam_problem_array_i32(pnfam_problem* h, const char* name, const int32_t** 
   const std::vector<int>* v = nullptr;
   std::map<std::string, const std::vector<int>*> m = {
       {"db", &b.db}, {"isstart", &b.isstart}, {"nr", &b.nr}, {"nz", &b.nz}, {"nl", &b.nl}, {"ns", &b.ns},
-      {"npar", &b.npar}, {"num_spin_up", &b.num_spin_up},
+      {"npar", &b.npar}, {"num_spin_up", &b.num_spin_up}, {"sep_zrow", &b.sep_zrow},
       {"f_ir2c", &p.f.mat.ir2c}, {"f_ic2r", &p.f.mat.ic2r}, {"f_ir2m", &p.f.mat.ir2m}, {"f_ic2m", &p.f.mat.ic2m},
       {"hfb_id", &p.nuc->hfb.id},
   };

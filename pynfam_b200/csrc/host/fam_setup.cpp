@@ -121,6 +121,22 @@ FamBasis FamBasis::build(const HfbSolution& s) {
       wa[r] = w2[r] - b.y[r] * b.nl[i] * wp[r];
     }
   }
+  // separable factors in the doubled, spin-sorted order
+  b.ngh = s.ngh; b.ngl = s.ngl; b.sep_nzrows = s.sep_nzrows; b.sep_z = s.sep_z;
+  b.sep_zrow = b.nz;
+  b.sep_r.assign((size_t)4 * N * s.ngl, 0.0);
+  for (int i = 0; i < N; i++) {
+    const int src = order[i], h = src < ht ? src : src - ht;
+    const double sgn = (src >= ht && s.ns[h] < 0) ? -1.0 : 1.0;
+    for (int il = 0; il < s.ngl; il++) {
+      const double yl = b.y[(size_t)il * s.ngh] * b.nl[i];   // Lambda / r
+      const double r0 = sgn * s.sep_r[((size_t)0 * ht + h) * s.ngl + il];
+      b.sep_r[((size_t)0 * N + i) * s.ngl + il] = r0;
+      b.sep_r[((size_t)1 * N + i) * s.ngl + il] = sgn * s.sep_r[((size_t)1 * ht + h) * s.ngl + il];
+      b.sep_r[((size_t)2 * N + i) * s.ngl + il] = yl * r0;
+      b.sep_r[((size_t)3 * N + i) * s.ngl + il] = sgn * s.sep_r[((size_t)2 * ht + h) * s.ngl + il] - yl * yl * r0;
+    }
+  }
   // quasiparticles: E doubled; U doubled; V: first half = -V, second half = +V (:225-230)
   auto dbl_E = [&](const std::vector<double>& e) { std::vector<double> o(N); for (int i = 0; i < ht; i++) o[i] = o[i + ht] = e[i]; return o; };
   b.Ep = dbl_E(s.E[1]); b.En = dbl_E(s.E[0]);

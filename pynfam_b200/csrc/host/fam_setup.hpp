@@ -64,6 +64,12 @@ struct FamBasis {
   std::vector<int> nr, nz, nl, ns, npar, num_spin_up;
   std::vector<double> wf, wfdr, wfdz, wfd2, wfdp, wfd2_all;  // (nghl, dqp) column-major
   std::vector<double> y, z, wdcori;
+  // separable factors of the tables above (HO basis): wf = Z0 R0, wfdr = Z0 R1, wfdp = Z0 R2, wfdz = Z1 R0,
+  // wfd2_all = Z2 R0 + Z0 R3 with Z*[sep_zrow[state]][ih], R*[state][il] and ihil = ih + il*ngh
+  int ngh = 0, ngl = 0, sep_nzrows = 0;
+  std::vector<int> sep_zrow;             // [dqp]
+  std::vector<double> sep_z;             // [3][sep_nzrows][ngh]
+  std::vector<double> sep_r;             // [4][dqp][ngl]
   std::vector<double> Ep, En, Up, Vp, Un, Vn;
   std::vector<double> rho_n, rho_p;      // coordinate-space densities (normalised)
   bool blo_active = false;

@@ -332,6 +332,27 @@ static void build_tables(HfbSolution& s, const HelData& h) {
     }
   s.qhla.assign((size_t)nt * nghl, 0.0); s.fi1r = s.qhla; s.fi1z = s.qhla; s.fi2d = s.qhla;
   const double bpi = 1.0 / h.bp, bpi2 = bpi * bpi, bzi = 1.0 / h.bz, bzi2 = bzi * bzi;
+  // separable factors (consumed by the sum-factorised GPU kernels)
+  s.sep_nzrows = nzm + 1;
+  s.sep_z.assign((size_t)3 * s.sep_nzrows * ngh, 0.0);
+  s.sep_r.assign((size_t)3 * nt * ngl, 0.0);
+  for (int n = 0; n <= nzm; n++)
+    for (int ih = 0; ih < ngh; ih++) {
+      const double xh2 = h.xh[ih] * h.xh[ih];
+      s.sep_z[((size_t)0 * s.sep_nzrows + n) * ngh + ih] = QH(n, ih);
+      s.sep_z[((size_t)1 * s.sep_nzrows + n) * ngh + ih] = bzi * QH1(n, ih);
+      s.sep_z[((size_t)2 * s.sep_nzrows + n) * ngh + ih] = (xh2 - (double)(n + n + 1)) * bzi2 * QH(n, ih);
+    }
+  for (int ja = 0; ja < nt; ja++) {
+    const int nla = h.nl[ja], nra = h.nr[ja];
+    const double sml2 = (double)(nla * nla), cnraa = nra + nra + nla + 1;
+    for (int il = 0; il < ngl; il++) {
+      const double v2 = 0.5 / h.xl[il], v4 = v2 * v2, qla = QL(nra, nla, il);
+      s.sep_r[((size_t)0 * nt + ja) * ngl + il] = qla;
+      s.sep_r[((size_t)1 * nt + ja) * ngl + il] = (2.0 * std::sqrt(h.xl[il]) * bpi) * (QL1(nra, nla, il) * v2);
+      s.sep_r[((size_t)2 * nt + ja) * ngl + il] = 4.0 * (0.25 - cnraa * v2 + sml2 * v4) * h.xl[il] * bpi2 * qla;
+    }
+  }
   for (int ja = 0; ja < nt; ja++) {
     const int nla = h.nl[ja], nra = h.nr[ja], nza = h.nz[ja];
     const double sml2 = (double)(nla * nla), cnzaa = nza + nza + 1, cnraa = nra + nra + nla + 1;

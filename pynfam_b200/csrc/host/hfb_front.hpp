@@ -69,6 +69,11 @@ struct HfbSolution {
   std::vector<int> id, ia, nr, nz, nl, ns, npar;
   std::vector<double> y, z, wdcor, wdcori;          // (nghl): 1/r, z, weights
   std::vector<double> qhla, fi1r, fi1z, fi2d;       // [state][nghl]
+  // separable factors of the same tables (ihil = ih + il*ngh):  qhla = Z0 R0, fi1r = Z0 R1, fi1z = Z1 R0,
+  // fi2d = Z2 R0 + Z0 R3c;  Z*[nz][ih] depend on n_z only, R*[state][il] on (n_r, Lambda)
+  int sep_nzrows = 0;
+  std::vector<double> sep_z;                        // [3][sep_nzrows][ngh]
+  std::vector<double> sep_r;                        // [3][nt][ngl]: R0, R1, R3c
   int npr[3] = {0, 0, 0};                           // N, Z, A of the (possibly odd) nucleus
   // per isospin it = 0 (n), 1 (p)
   std::vector<double> hmat[2], dmat[2];             // packed lower triangles per block (gamdel)

@@ -244,6 +244,8 @@ int main(int argc, char** argv) {
   m.ct = x.ct; m.cj = x.cj; m.cgs = x.cgs; m.cf = x.cf; m.csdj = x.csdj;
   m.Ep = b.Ep.data(); m.En = b.En.data(); m.Up = b.Up.data(); m.Vp = b.Vp.data(); m.Un = b.Un.data(); m.Vn = b.Vn.data();
   m.qp_fp = b.blo_active ? b.qp_fp.data() : nullptr; m.qp_fn = b.blo_active ? b.qp_fn.data() : nullptr;
+  m.ngh = b.ngh; m.ngl = b.ngl; m.sep_nzrows = b.sep_nzrows;
+  m.sep_zrow = b.sep_zrow.data(); m.sep_z = b.sep_z.data(); m.sep_r = b.sep_r.data();
   char err[1024] = {0};
   pnfam_b200_ctx* ctx = nullptr;
   if (pnfam_b200_ctx_create(&m, 0, &ctx, err, sizeof err) != 0) {

@@ -21,7 +21,9 @@ class Model(ctypes.Structure):
                                              "wdcori", "crho", "cs", "cpair", "cspair")]
                 + [(k, ctypes.c_double) for k in ("cdrho", "ctau", "ctj0", "ctj1", "ctj2", "crdj",
                                                   "cds", "ct", "cj", "cgs", "cf", "csdj")]
-                + [(k, c_double_p) for k in ("Ep", "En", "Up", "Vp", "Un", "Vn", "qp_fp", "qp_fn")])
+                + [(k, c_double_p) for k in ("Ep", "En", "Up", "Vp", "Un", "Vn", "qp_fp", "qp_fn")]
+                + [("ngh", ctypes.c_int32), ("ngl", ctypes.c_int32), ("sep_nzrows", ctypes.c_int32),
+                   ("sep_zrow", c_int32_p), ("sep_z", c_double_p), ("sep_r", c_double_p)])
 
 
 class Operator(ctypes.Structure):
@@ -66,6 +68,7 @@ def lib():
         L.pnfam_b200_ctx_create.argtypes = [ctypes.POINTER(Model), ci, ctypes.POINTER(vp), cp, ci]
         L.pnfam_b200_ctx_destroy.argtypes = [vp]
         L.pnfam_b200_ctx_destroy.restype = None
+        L.pnfam_b200_ctx_separable.argtypes = [vp]
         L.pnfam_b200_solve.argtypes = [vp, ctypes.POINTER(Operator), ctypes.POINTER(SolverParams), ctypes.c_int32,
                                        c_double_p, c_double_p, c_double_p, c_int32_p, c_int32_p, c_double_p,
                                        c_double_p, ctypes.POINTER(Stats), cp, ci]
@@ -86,7 +89,8 @@ def _ip(a):
 class Context:
     """Device-resident nucleus + interaction (pnfam_b200_ctx)."""
 
-    def __init__(self, problem, device=0):
+    def __init__(self, problem, device=0, separable=True):
+        """separable=False withholds the separable factors of the basis tables: the general-table kernels run."""
         L = lib()
         p = problem
         self._keep = k = {}
@@ -104,12 +108,22 @@ class Context:
         if p.iscalar("blo_active"):
             k["qp_fp"], k["qp_fn"] = np.ascontiguousarray(p.f64("qp_fp")), np.ascontiguousarray(p.f64("qp_fn"))
             m.qp_fp, m.qp_fn = _dp(k["qp_fp"]), _dp(k["qp_fn"])
+        if separable:
+            m.ngh, m.ngl, m.sep_nzrows = p.iscalar("ngh"), p.iscalar("ngl"), p.iscalar("sep_nzrows")
+            k["sep_zrow"] = np.ascontiguousarray(p.i32("sep_zrow"))
+            k["sep_z"], k["sep_r"] = np.ascontiguousarray(p.f64("sep_z")), np.ascontiguousarray(p.f64("sep_r"))
+            m.sep_zrow, m.sep_z, m.sep_r = _ip(k["sep_zrow"]), _dp(k["sep_z"]), _dp(k["sep_r"])
         self.nb = m.nb
         self._h = ctypes.c_void_p()
         err = ctypes.create_string_buffer(1024)
         if L.pnfam_b200_ctx_create(ctypes.byref(m), device, ctypes.byref(self._h), err, 1024) != 0:
             self._h = None
             raise GpuError(err.value.decode())
+
+    @property
+    def separable(self):
+        """True when the sum-factorised kernels run (the model carried usable separable factors)."""
+        return bool(lib().pnfam_b200_ctx_separable(self._h))
 
     def __del__(self):
         if getattr(self, "_h", None):

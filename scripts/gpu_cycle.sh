@@ -2,7 +2,7 @@
 # One GPU iteration cycle (run on the B200 box through gpurun): GPU parity tests, a short bench, and an ncu capture
 # of the dominant kernels.  Usage: scripts/gpu_cycle.sh <tag> [ncu_kernel_regex]
 tag=${1:-x}
-rx=${2:-density_kernel|projection_kernel}
+rx=${2:-sf_density_kernel|sf_projection_kernel}
 mkdir -p gpurun_out
 (timeout 900 python -m pytest tests -q -m gpu -x 2>&1 | tail -15) > gpurun_out/pytest_gpu_$tag.log
 cat gpurun_out/pytest_gpu_$tag.log

@@ -22,6 +22,19 @@ def gpu():
     return g
 
 
+@pytest.fixture(params=["separable", "general"])
+def mkctx(gpu, request):
+    """Context factory for both kernel families: the sum-factorised ones (the model carries the separable factors
+    of the HO basis -- the default) and the general-table ones."""
+    sep = request.param == "separable"
+
+    def make(problem):
+        ctx = gpu.Context(problem, separable=sep)
+        assert ctx.separable == sep
+        return ctx
+    return make
+
+
 def _rel(a, b):
     return abs(a - b) / abs(b)
 
@@ -44,10 +57,10 @@ CASES = [
 
 
 @pytest.mark.parametrize("case,op,idx", CASES)
-def test_trajectory_matches_oracle_and_golden(gpu, case, op, idx, tmp_path):
+def test_trajectory_matches_oracle_and_golden(mkctx, case, op, idx, tmp_path):
     pt = stage_point(case, op, idx, str(tmp_path))
     p = host.Problem(str(tmp_path), "x.in")
-    ctx = gpu.Context(p)
+    ctx = mkctx(p)
     model = fo.model_from_problem(p)
     for mi in (1, 2, 4):
         so = fo.solver_from_problem(p, model)
@@ -68,12 +81,12 @@ def test_trajectory_matches_oracle_and_golden(gpu, case, op, idx, tmp_path):
 
 
 @pytest.mark.parametrize("case,op", [("S40_SKOP_6sh", "GT-K0"), ("S40_GT_All", "RS1-K1"), ("Gd162_GT_open_6sh", "GT-K0")])
-def test_whole_contour_batched_against_golden(gpu, case, op, tmp_path):
+def test_whole_contour_batched_against_golden(mkctx, case, op, tmp_path):
     """All omega points of one operator in ONE batched call (how the product is meant to be driven)."""
     pts = load_points(case)[op]
     stage_point(case, op, 0, str(tmp_path))
     p = host.Problem(str(tmp_path), "x.in")
-    ctx = gpu.Context(p)
+    ctx = mkctx(p)
     import re
     om = []
     for pt in pts:
@@ -99,10 +112,10 @@ def test_whole_contour_batched_against_golden(gpu, case, op, tmp_path):
                 assert _rel(r["strength"][i, k], gold[lab]) < tol, (i, lab)
 
 
-def test_calc_hamiltonian_entry_matches_oracle(gpu, tmp_path):
+def test_calc_hamiltonian_entry_matches_oracle(mkctx, tmp_path):
     stage_point("Gd162_GT_open_6sh", "GT-K1", 40, str(tmp_path))
     p = host.Problem(str(tmp_path), "x.in")
-    ctx = gpu.Context(p)
+    ctx = mkctx(p)
     s = fo.solver_from_problem(p)
     s.iterate(0)
     s.iterate(1)
@@ -170,7 +183,7 @@ def test_symmetry_and_batch_independence(gpu, tmp_path):
         assert np.abs(r1["strength"][0] - rb["strength"][i]).max() <= 1e-13 * np.abs(rb["strength"][i]).max()
 
 
-def test_gd162_16_shells_against_reference_binary(gpu, tmp_path):
+def test_gd162_16_shells_against_reference_binary(mkctx, tmp_path):
     """Full production size (N=1958, nghl=1600, nxy=103926): known answers produced by the reference's own
     pnfam_main.x (tests/golden/make_gd162_16sh.py)."""
     pts = load_points("Gd162_SKOP_16sh")
@@ -182,7 +195,7 @@ def test_gd162_16_shells_against_reference_binary(gpu, tmp_path):
             p = host.Problem(str(tmp_path), "%s_%d.in" % (op, i), share_nucleus_with=base)
             if base is None:
                 base = p
-                ctx = gpu.Context(p)
+                ctx = mkctx(p)
             r = ctx.solve(p)
             gold = gold_rows(pt)
             assert int(r["iters"][0]) == pt["iters"]
@@ -191,7 +204,7 @@ def test_gd162_16_shells_against_reference_binary(gpu, tmp_path):
                     assert _rel(r["strength"][0, k], gold[lab]) < TOL, (op, i, lab)
 
 
-def test_gd162_20_shells_multi_chunk_blocks(gpu, tmp_path):
+def test_gd162_20_shells_multi_chunk_blocks(mkctx, tmp_path):
     """20 shells (N=3542): the largest blocks have spin segments longer than one 48-row chunk, which exercises the
     accumulation over a-chunks in the density kernel and several a-chunks per segment in the projection.  Known
     answers from the reference's pnfam_main.x at fixed iteration counts (tests/golden/make_gd162_20sh.py)."""
@@ -204,7 +217,7 @@ def test_gd162_20_shells_multi_chunk_blocks(gpu, tmp_path):
             p = host.Problem(str(tmp_path), "%s_%d.in" % (op, i), share_nucleus_with=base)
             if base is None:
                 base = p
-                ctx = gpu.Context(p)
+                ctx = mkctx(p)
                 assert (p.i32("num_spin_up") > 48).any() or ((p.i32("db") - p.i32("num_spin_up")) > 48).any()
             r = ctx.solve(p)
             gold = gold_rows(pt)
