@@ -54,8 +54,12 @@ __global__ void __launch_bounds__(256) sf_pack_kernel(HamArgs g) {
 // ================================================================================================
 // density
 // ================================================================================================
+constexpr int SF_DSTAGES = 4;   // operand stages of the density kernel (as many as fit, at least 2)
+constexpr int SF_DPROD = 3;     // producer warps (phase T)
+constexpr int SF_DCONS = 12;    // consumer warps (DMMA + epilogue)
 struct SfDensLayout {
-  int off_stage[2], off_T[2], off_bar;   // byte offsets in dynamic shared memory
+  int off_stage[SF_DSTAGES], off_T[2], off_bar, off_x;   // byte offsets in dynamic shared memory
+  int nst;                               // operand stages in use
   int st_zb, st_ra, st_rb, st_rho;       // inside an operand stage: segtab at 0
   int t_rb, t_zb, t_sz;                  // inside a T stage: T at 0
   int ts;                                // row stride of T (doubles), ts % 16 == 4
@@ -68,22 +72,35 @@ static SfDensLayout make_dens_layout(const SfDev& S) {
   L.ts = 2 * S.nbc_max + 4;
   L.st_zb = SF_SEGTAB * 4;
   L.st_ra = L.st_zb + S.nbc_max * 4;
-  L.st_rb = L.st_ra + 2 * S.na_max * 32;
-  L.st_rho = L.st_rb + 2 * S.nbc_max * 32;
+  L.st_rb = L.st_ra + S.na_max * 64;
+  L.st_rho = L.st_rb + S.nbc_max * 64;
   const int stage = up(L.st_rho + S.na_max * 2 * S.nbc_max * 8);
   L.t_rb = 2 * 3 * S.kpad_max * L.ts * 8;
-  L.t_zb = L.t_rb + 2 * S.nbc_max * 32;
+  L.t_zb = L.t_rb + S.nbc_max * 64;
   L.t_sz = L.t_zb + S.nbc_max * 4;
   const int tstage = up(L.t_sz + SF_KMAX * 4);
   int off = up(2 * S.nzrows * S.zs * 8);
-  for (int i = 0; i < 2; i++) { L.off_stage[i] = off; off += stage; }
   for (int i = 0; i < 2; i++) { L.off_T[i] = off; off += tstage; }
-  L.off_bar = off;
-  L.total = off + 64;
+  L.off_bar = off; off += 128;
+  L.off_x = off; off += 6 * 8 * 32 * 8;          // exchange buffer of the m-tiles shared by two warps
+  const int room = 227 * 1024 - off;
+  L.nst = std::max(2, std::min(SF_DSTAGES, room / stage));
+  for (int i = 0; i < L.nst; i++) { L.off_stage[i] = off; off += stage; }
+  L.total = off;
   return L;
 }
 
-// MODE 0: rho -> D^{tt'}_{ss'} (4 x 4 derivative types);  MODE 1: kappa -> K_{ss'} (plain wave functions)
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// MODE 0: rho -> D^{tt'}_{ss'} (4 x 4 derivative types);  MODE 1: kappa -> K_{ss'} (plain wave functions).
+// One CTA = two Gauss-Laguerre nodes (il pair) of one (pass, omega); it walks the step list of the pass.
+// Warp roles (no CTA-wide barrier in the loop, hand-over by mbarriers):
+//   warp 15       issues the operand copies of a step (7 linear bulk copies) up to nst steps ahead
+//   warps 12..14  phase T: T^j[il][slot][col] = sum_{a in slot} R^j_a(il) rho[a][col]  (FP64 FMA), double buffered
+//   warps 0..11   DMMA + epilogue of one m-tile (8 grid points) each; with 2 mt = 10 m-tiles the last two are shared
+//                 by two warps (half of the n-tiles each) so that every SM sub-partition carries the same DMMA load
 template <int MODE>
 __global__ void __launch_bounds__(SF_THREADS, 1) sf_density_kernel(HamArgs g, SfDensLayout L) {
   constexpr int NJ = MODE == 0 ? 3 : 1;   // radial factor types entering T
@@ -97,167 +114,202 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sf_density_kernel(HamArgs g, Sf
   const int nsteps = S.nsteps[list];
   const double* __restrict__ pk = S.pk[MODE] + ((size_t)za * 2 + q) * S.pk_stride[MODE];
   double* Zs = reinterpret_cast<double*>(smem);                 // [2][nzrows][zs]
-  unsigned long long* full = reinterpret_cast<unsigned long long*>(smem + L.off_bar);
-  const int zs = S.zs, nzr = S.nzrows, na_max = S.na_max, nbc_max = S.nbc_max, kpad_max = S.kpad_max, ts = L.ts;
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + L.off_bar);
+  unsigned long long *st_full = bars, *st_empty = bars + SF_DSTAGES, *t_full = bars + 2 * SF_DSTAGES, *t_empty = bars + 2 * SF_DSTAGES + 2;
+  const int zs = S.zs, nzr = S.nzrows, na_max = S.na_max, nbc_max = S.nbc_max, kpad_max = S.kpad_max, ts = L.ts, nst = L.nst;
   const int il0 = 2 * ilp, il1 = min(il0 + 1, S.ngl - 1);
+  // consumer roles
+  const int M = 2 * S.mt;                                       // m-tiles of the il pair (<= 12)
+  const int ncons = M >= 6 ? SF_DCONS : 2 * M;
+  const int first_split = M >= 6 ? 2 * M - SF_DCONS : 0;        // m-tiles >= first_split are shared by two warps
 
   for (int i = tid; i < 2 * nzr * zs; i += SF_THREADS) Zs[i] = S.zt[i];
   if (tid == 0) {
-    mbar_init(&full[0], 1); mbar_init(&full[1], 1);
+    for (int i = 0; i < SF_DSTAGES; i++) { mbar_init(&st_full[i], 1); mbar_init(&st_empty[i], SF_DPROD); }
+    for (int i = 0; i < 2; i++) { mbar_init(&t_full[i], SF_DPROD); mbar_init(&t_empty[i], ncons); }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
 
-  // operand movement of one step: 7 linear bulk copies (segment table, z rows of the columns, radial factors of the
-  // a rows and of the b columns for both il, the packed rho image)
-  auto issue = [&](const SfDensStep& d, int k) {
-    unsigned char* st = smem + L.off_stage[k & 1];
-    unsigned long long* bar = &full[k & 1];
-    const unsigned ra_b = (unsigned)d.na * 32, rb_b = (unsigned)d.nbc * 32, rho_b = (unsigned)d.na * d.nbc * 16;
-    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-    mbar_expect_tx(bar, SF_SEGTAB * 4 + (unsigned)d.nbc * 4 + 2 * ra_b + 2 * rb_b + rho_b);
-    bulk_g2s(st, S.segtab + (size_t)d.seg_a * SF_SEGTAB, SF_SEGTAB * 4, bar);
-    bulk_g2s(st + L.st_zb, S.zrow + d.b_row0, (unsigned)d.nbc * 4, bar);
-    bulk_g2s(st + L.st_ra, S.rg + ((size_t)il0 * S.dqp_p + d.a_row0) * 4, ra_b, bar);
-    bulk_g2s(st + L.st_ra + na_max * 32, S.rg + ((size_t)il1 * S.dqp_p + d.a_row0) * 4, ra_b, bar);
-    bulk_g2s(st + L.st_rb, S.rg + ((size_t)il0 * S.dqp_p + d.b_row0) * 4, rb_b, bar);
-    bulk_g2s(st + L.st_rb + nbc_max * 32, S.rg + ((size_t)il1 * S.dqp_p + d.b_row0) * 4, rb_b, bar);
-    bulk_g2s(st + L.st_rho, pk + d.img_off, rho_b, bar);
-  };
-  constexpr int ISSUER = SF_THREADS - 32;     // lane 0 of the last warp (never a DMMA warp for ngh <= 56)
-  // step descriptors travel in registers, fetched two steps ahead of their use
-  SfDensStep d_cur = nsteps > 0 ? steps[0] : SfDensStep{}, d_next = nsteps > 1 ? steps[1] : SfDensStep{};
-  if (tid == ISSUER) {
-    if (nsteps > 0) issue(d_cur, 0);
-    if (nsteps > 1) issue(d_next, 1);
+  if (warp == 15) {
+    // ---- operand movement: segment table, z rows of the columns, radial factors of the a rows and of the b columns
+    //      for both il, the packed rho image
+    if (lane == 0)
+      for (int k = 0; k < nsteps; k++) {
+        const SfDensStep d = steps[k];
+        const int sg = k % nst;
+        if (k >= nst) mbar_wait(&st_empty[sg], ((k / nst) - 1) & 1);
+        unsigned char* st = smem + L.off_stage[sg];
+        unsigned long long* bar = &st_full[sg];
+        const unsigned ra_b = (unsigned)d.na * 64, rb_b = (unsigned)d.nbc * 64, rho_b = (unsigned)d.na * d.nbc * 16;
+        mbar_expect_tx(bar, SF_SEGTAB * 4 + (unsigned)d.nbc * 4 + ra_b + rb_b + rho_b);
+        bulk_g2s(st + L.st_rho, pk + d.img_off, rho_b, bar);
+        bulk_g2s(st, S.segtab + (size_t)d.seg_a * SF_SEGTAB, SF_SEGTAB * 4, bar);
+        bulk_g2s(st + L.st_zb, S.zrow + d.b_row0, (unsigned)d.nbc * 4, bar);
+        bulk_g2s(st + L.st_ra, S.rgp + ((size_t)ilp * S.dqp_p + d.a_row0) * 8, ra_b, bar);
+        bulk_g2s(st + L.st_rb, S.rgp + ((size_t)ilp * S.dqp_p + d.b_row0) * 8, rb_b, bar);
+      }
+    return;
   }
 
-  // ---- phase T of step k (all threads): T^j[il][slot][col] = sum_{a in slot} R^j_a(il) rho[a][col];
-  //      forwards what the DMMA phase needs from the operand stage (which is recycled one step earlier than T)
-  auto phase_T = [&](const SfDensStep& d, int k) {
-    mbar_wait(&full[k & 1], (k >> 1) & 1);
-    const unsigned char* st = smem + L.off_stage[k & 1];
-    unsigned char* tst = smem + L.off_T[k & 1];
-    const int* __restrict__ segt = reinterpret_cast<const int*>(st);
-    const double* __restrict__ Ra = reinterpret_cast<const double*>(st + L.st_ra);
-    const double* __restrict__ rho = reinterpret_cast<const double*>(st + L.st_rho);
-    double* __restrict__ T = reinterpret_cast<double*>(tst);
-    const int ncol = 2 * d.nbc, kpad = (d.nslots + 3) & ~3, ntask = kpad * ncol;
-    for (int t = tid; t < ntask; t += SF_THREADS) {
-      const int slot = t / ncol, col = t - slot * ncol;
-      int a0 = 0, a1 = 0;
-      if (slot < d.nslots) { a0 = segt[slot]; a1 = segt[slot + 1]; }
-      double acc[2][NJ];
+  if (warp >= SF_DCONS) {
+    // ---- phase T (producers); forwards what the consumers need from the operand stage, which is recycled earlier
+    const int ptid = tid - SF_DCONS * 32, pw = warp - SF_DCONS;
+    constexpr int NP = SF_DPROD * 32;
+    SfDensStep dn = nsteps > 0 ? steps[0] : SfDensStep{};
+    for (int k = 0; k < nsteps; k++) {
+      const SfDensStep d = dn;
+      if (k + 1 < nsteps) dn = steps[k + 1];
+      const int sg = k % nst;
+      mbar_wait(&st_full[sg], (k / nst) & 1);
+      if (k >= 2) mbar_wait(&t_empty[k & 1], ((k >> 1) - 1) & 1);
+      const unsigned char* st = smem + L.off_stage[sg];
+      unsigned char* tst = smem + L.off_T[k & 1];
+      const int* __restrict__ segt = reinterpret_cast<const int*>(st);
+      const double* __restrict__ Ra = reinterpret_cast<const double*>(st + L.st_ra);      // [a][il][4]
+      const double2* __restrict__ rho = reinterpret_cast<const double2*>(st + L.st_rho);  // [a][b] (re, im)
+      double* __restrict__ T = reinterpret_cast<double*>(tst);
+      const int kpad = (d.nslots + 3) & ~3;
+      // a lane owns one column b (re, im); a warp owns every third n_z slot: the radial factors are warp-uniform
+      if (lane < d.nbc) {
+        for (int slot = pw; slot < kpad; slot += SF_DPROD) {
+          int a0 = 0, a1 = 0;
+          if (slot < d.nslots) { a0 = segt[slot]; a1 = segt[slot + 1]; }
+          double acc[2][NJ][2];
 #pragma unroll
-      for (int i = 0; i < 2 * NJ; i++) (&acc[0][0])[i] = 0.0;
-      for (int a = a0; a < a1; a++) {
-        const double v = rho[a * ncol + col];
+          for (int i = 0; i < 4 * NJ; i++) (&acc[0][0][0])[i] = 0.0;
+#pragma unroll 2
+          for (int a = a0; a < a1; a++) {
+            const double2 v = rho[a * d.nbc + lane];
 #pragma unroll
-        for (int il = 0; il < 2; il++)
+            for (int il = 0; il < 2; il++)
 #pragma unroll
-          for (int j = 0; j < NJ; j++) acc[il][j] += Ra[(il * na_max + a) * 4 + j] * v;
+              for (int j = 0; j < NJ; j++) {
+                const double r = Ra[a * 8 + il * 4 + j];
+                acc[il][j][0] += r * v.x; acc[il][j][1] += r * v.y;
+              }
+          }
+#pragma unroll
+          for (int il = 0; il < 2; il++)
+#pragma unroll
+            for (int j = 0; j < NJ; j++)
+              *reinterpret_cast<double2*>(&T[((il * 3 + j) * kpad_max + slot) * ts + 2 * lane]) = make_double2(acc[il][j][0], acc[il][j][1]);
+        }
       }
-#pragma unroll
-      for (int il = 0; il < 2; il++)
-#pragma unroll
-        for (int j = 0; j < NJ; j++) T[((il * 3 + j) * kpad_max + slot) * ts + col] = acc[il][j];
+      const double* __restrict__ Rb = reinterpret_cast<const double*>(st + L.st_rb);
+      double* __restrict__ Rbt = reinterpret_cast<double*>(tst + L.t_rb);
+      for (int t = ptid; t < d.nbc * 8; t += NP) Rbt[t] = Rb[t];
+      if (ptid < d.nbc) reinterpret_cast<int*>(tst + L.t_zb)[ptid] = reinterpret_cast<const int*>(st + L.st_zb)[ptid];
+      if (ptid >= 64 && ptid < 64 + SF_KMAX) reinterpret_cast<int*>(tst + L.t_sz)[ptid - 64] = segt[17 + ptid - 64];
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(&t_full[k & 1]); mbar_arrive(&st_empty[sg]); }
     }
-    const double* __restrict__ Rb = reinterpret_cast<const double*>(st + L.st_rb);
-    double* __restrict__ Rbt = reinterpret_cast<double*>(tst + L.t_rb);
-    for (int t = tid; t < 2 * nbc_max * 4; t += SF_THREADS) Rbt[t] = Rb[t];
-    if (tid < d.nbc) reinterpret_cast<int*>(tst + L.t_zb)[tid] = reinterpret_cast<const int*>(st + L.st_zb)[tid];
-    if (tid < SF_KMAX) reinterpret_cast<int*>(tst + L.t_sz)[tid] = segt[17 + tid];
-  };
+    return;
+  }
 
-  // consumer role: warp w < 2 mt owns m-tile w % mt of il (w / mt); accumulators of ONE (s, s') sweep at a time
-  const bool consumer = warp < 2 * S.mt;
-  const int ilc = warp / S.mt, ih = (warp % S.mt) * 8 + lr;
+  // ---- consumers: warp -> (m-tile, half of the n-tiles)
+  int m, half = 0;
+  bool split;
+  if (M >= 6) {
+    if (warp < M) { m = warp; split = m >= first_split; }
+    else { m = M - 1 - (warp - M); split = true; half = 1; }
+  } else {
+    if (warp >= 2 * M) return;
+    m = warp < M ? warp : warp - M; split = true; half = warp < M ? 0 : 1;
+  }
+  const int ilc = m / S.mt, ih = (m % S.mt) * 8 + lr;
   double acc[NT][NT][2];
 #pragma unroll
   for (int i = 0; i < NT * NT * 2; i++) (&acc[0][0][0])[i] = 0.0;
-
-  if (nsteps > 0) phase_T(d_cur, 0);
-  __syncthreads();
+  SfDensStep dn = nsteps > 0 ? steps[0] : SfDensStep{};
   for (int k = 0; k < nsteps; k++) {
-    const SfDensStep d_nn = k + 2 < nsteps ? steps[k + 2] : SfDensStep{};
-    // the operand stage of step k was consumed by phase T(k) before the last barrier
-    if (tid == ISSUER && k + 2 < nsteps) issue(d_nn, k + 2);
-    if (k + 1 < nsteps) phase_T(d_next, k + 1);
-    if (consumer) {
-      const SfDensStep& d = d_cur;
-      const unsigned char* tst = smem + L.off_T[k & 1];
-      const double* __restrict__ T = reinterpret_cast<const double*>(tst) + (size_t)ilc * 3 * kpad_max * ts;
-      const double* __restrict__ Rb = reinterpret_cast<const double*>(tst + L.t_rb) + ilc * nbc_max * 4;
-      const int* __restrict__ zb = reinterpret_cast<const int*>(tst + L.t_zb);
-      const int* __restrict__ sz = reinterpret_cast<const int*>(tst + L.t_sz);
-      const int ksteps = (d.nslots + 3) >> 2, ntn = d.nbc >> 2;
-      double a0[SF_KMAX / 4], a1[SF_KMAX / 4];
+    const SfDensStep d = dn;
+    if (k + 1 < nsteps) dn = steps[k + 1];
+    mbar_wait(&t_full[k & 1], (k >> 1) & 1);
+    const unsigned char* tst = smem + L.off_T[k & 1];
+    const double* __restrict__ T = reinterpret_cast<const double*>(tst) + (size_t)ilc * 3 * kpad_max * ts;
+    const double* __restrict__ Rb = reinterpret_cast<const double*>(tst + L.t_rb) + ilc * 4;   // [b][il][4]
+    const int* __restrict__ zb = reinterpret_cast<const int*>(tst + L.t_zb);
+    const int* __restrict__ sz = reinterpret_cast<const int*>(tst + L.t_sz);
+    const int ksteps = (d.nslots + 3) >> 2, ntn = d.nbc >> 2;
+    const int nt_mid = (ntn + 1) >> 1;
+    const int nt0 = split ? (half ? nt_mid : 0) : 0, nt1 = split ? (half ? ntn : nt_mid) : ntn;
+    double a0[SF_KMAX / 4], a1[SF_KMAX / 4];
 #pragma unroll
-      for (int ks = 0; ks < SF_KMAX / 4; ks++) {
-        a0[ks] = 0.0; a1[ks] = 0.0;
-        if (ks < ksteps) {
-          const int slot = ks * 4 + lc;
-          const int zr = slot < d.nslots ? sz[slot] : 0;
-          a0[ks] = Zs[zr * zs + ih];
-          if (MODE == 0) a1[ks] = Zs[(nzr + zr) * zs + ih];
-        }
-      }
-      const size_t tj = (size_t)kpad_max * ts;
-      for (int nt = 0; nt < ntn; nt++) {
-        double C[NT][2];
-#pragma unroll
-        for (int i = 0; i < NT * 2; i++) (&C[0][0])[i] = 0.0;
-#pragma unroll
-        for (int ks = 0; ks < SF_KMAX / 4; ks++) {
-          if (ks < ksteps) {
-            const double* __restrict__ tb = T + (size_t)(ks * 4 + lc) * ts + nt * 8 + lr;
-            const double b0 = tb[0];
-            dmma884(C[0][0], C[0][1], a0[ks], b0);
-            if (MODE == 0) {
-              const double b1 = tb[tj], b2 = tb[2 * tj];
-              dmma884(C[1][0], C[1][1], a0[ks], b1);
-              dmma884(C[2][0], C[2][1], a0[ks], b2);
-              dmma884(C[3][0], C[3][1], a1[ks], b0);
-            }
-          }
-        }
-        // epilogue: contract with phi^t'_b(ih, il) = Z(n_z(b), ih) R_b(il) of this lane's column b
-        const int b = nt * 4 + lc, zr = zb[b];
-        const double z0 = Zs[zr * zs + ih];
-        double ph[NT];
-        ph[0] = z0 * Rb[b * 4];
-        if (MODE == 0) {
-          const double z1 = Zs[(nzr + zr) * zs + ih];
-          ph[1] = z0 * Rb[b * 4 + 1]; ph[2] = z0 * Rb[b * 4 + 2]; ph[3] = z1 * Rb[b * 4];
-        }
-#pragma unroll
-        for (int t = 0; t < NT; t++)
-#pragma unroll
-          for (int t2 = 0; t2 < NT; t2++) { acc[t][t2][0] += C[t][0] * ph[t2]; acc[t][t2][1] += C[t][1] * ph[t2]; }
-      }
-      if (d.flags & 1) {
-        // end of the (s, s') sweep: reduce over the 4 lanes of a grid point, write, restart
-        const int il = il0 + ilc;
-        const bool ok = ih < S.ngh && il < S.ngl;
-        constexpr int ndd = NT * NT * 8;
-        double* __restrict__ out = (MODE ? g.dd_kap : g.dd_rho) + ((size_t)za * 2 + q) * ndd * g.basis.nghl + (size_t)il * S.ngh + ih;
-#pragma unroll
-        for (int t = 0; t < NT; t++)
-#pragma unroll
-          for (int t2 = 0; t2 < NT; t2++)
-#pragma unroll
-            for (int c = 0; c < 2; c++) {
-              double v = acc[t][t2][c];
-              v += __shfl_xor_sync(0xffffffffu, v, 1);
-              v += __shfl_xor_sync(0xffffffffu, v, 2);
-              const int e = (t * NT + t2) * 2 + c;
-              if (ok && (e & 3) == lc) out[(size_t)(((t * NT + t2) * 4 + d.sweep) * 2 + c) * g.basis.nghl] = v;
-              acc[t][t2][c] = 0.0;
-            }
+    for (int ks = 0; ks < SF_KMAX / 4; ks++) {
+      a0[ks] = 0.0; a1[ks] = 0.0;
+      if (ks < ksteps) {
+        const int slot = ks * 4 + lc;
+        const int zr = slot < d.nslots ? sz[slot] : 0;
+        a0[ks] = Zs[zr * zs + ih];
+        if (MODE == 0) a1[ks] = Zs[(nzr + zr) * zs + ih];
       }
     }
-    d_cur = d_next; d_next = d_nn;
-    __syncthreads();
+    const size_t tj = (size_t)kpad_max * ts;
+    for (int nt = nt0; nt < nt1; nt++) {
+      double C[NT][2];
+#pragma unroll
+      for (int i = 0; i < NT * 2; i++) (&C[0][0])[i] = 0.0;
+#pragma unroll
+      for (int ks = 0; ks < SF_KMAX / 4; ks++) {
+        if (ks < ksteps) {
+          const double* __restrict__ tb = T + (size_t)(ks * 4 + lc) * ts + nt * 8 + lr;
+          const double b0 = tb[0];
+          dmma884(C[0][0], C[0][1], a0[ks], b0);
+          if (MODE == 0) {
+            const double b1 = tb[tj], b2 = tb[2 * tj];
+            dmma884(C[1][0], C[1][1], a0[ks], b1);
+            dmma884(C[2][0], C[2][1], a0[ks], b2);
+            dmma884(C[3][0], C[3][1], a1[ks], b0);
+          }
+        }
+      }
+      // epilogue: contract with phi^t'_b(ih, il) = Z(n_z(b), ih) R_b(il) of this lane's column b
+      const int b = nt * 4 + lc, zr = zb[b];
+      const double z0 = Zs[zr * zs + ih];
+      double ph[NT];
+      ph[0] = z0 * Rb[b * 8];
+      if (MODE == 0) {
+        const double z1 = Zs[(nzr + zr) * zs + ih];
+        ph[1] = z0 * Rb[b * 8 + 1]; ph[2] = z0 * Rb[b * 8 + 2]; ph[3] = z1 * Rb[b * 8];
+      }
+#pragma unroll
+      for (int t = 0; t < NT; t++)
+#pragma unroll
+        for (int t2 = 0; t2 < NT; t2++) { acc[t][t2][0] += C[t][0] * ph[t2]; acc[t][t2][1] += C[t][1] * ph[t2]; }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&t_empty[k & 1]);
+    if (d.flags & 1) {
+      // end of the (s, s') sweep: reduce over the 4 lanes of a grid point (and over the two warps of a shared m-tile,
+      // fixed order), write, restart
+      const int il = il0 + ilc;
+      const bool ok = ih < S.ngh && il < S.ngl;
+      constexpr int ndd = NT * NT * 8;
+      double* __restrict__ out = (MODE ? g.dd_kap : g.dd_rho) + ((size_t)za * 2 + q) * ndd * g.basis.nghl + (size_t)il * S.ngh + ih;
+      double* xb = reinterpret_cast<double*>(smem + L.off_x) + (size_t)((m - first_split) * 8 + lr) * 32;
+      double v[NT * NT * 2];
+#pragma unroll
+      for (int e = 0; e < NT * NT * 2; e++) {
+        double x = (&acc[0][0][0])[e];
+        x += __shfl_xor_sync(0xffffffffu, x, 1);
+        x += __shfl_xor_sync(0xffffffffu, x, 2);
+        v[e] = x;
+        (&acc[0][0][0])[e] = 0.0;
+      }
+      if (split && half == 1) {
+#pragma unroll
+        for (int e = 0; e < NT * NT * 2; e++)
+          if ((e & 3) == lc) xb[e] = v[e];
+      }
+      if (split) named_bar_sync(1 + m - first_split, 64);
+      if (half == 0) {
+#pragma unroll
+        for (int e = 0; e < NT * NT * 2; e++)
+          if (ok && (e & 3) == lc) out[(size_t)(((e >> 1) * 4 + d.sweep) * 2 + (e & 1)) * g.basis.nghl] = split ? v[e] + xb[e] : v[e];
+      }
+      if (split) named_bar_sync(1 + m - first_split, 64);
+    }
   }
 }
 
@@ -285,8 +337,9 @@ constexpr int SF_GS = 68;    // row stride of G and W (64 interleaved (b,c) colu
 constexpr int SF_NBC = 32;   // columns b per output tile
 constexpr int SF_HACC = 12;  // accumulators per thread: rows a = (tid >> 6) + 8 i  (na <= 96)
 
+constexpr int SF_PSTAGES = 3;  // per-il operand stages of the projection (field tensor + radial factors), prefetch distance 2
 struct SfProjLayout {
-  int off_G, off_W, off_mf[2], off_ra[2], off_rb[2], off_int, off_bar;
+  int off_G, off_W, off_mf[SF_PSTAGES], off_ra[SF_PSTAGES], off_rb[SF_PSTAGES], off_int, off_bar;
   int mf_bytes;              // bytes of the field tensor of one (il, sa, sb)
   int total;
 };
@@ -300,9 +353,9 @@ static SfProjLayout make_proj_layout(const SfDev& S) {
   L.off_G = off; off += up(std::max(NS * S.kih * SF_GS * 8, 2 * SF_NBC * (S.na_max | 1) * 8));   // reused as transpose buffer
   L.off_W = off; off += up(2 * 4 * 8 * SF_GS * 8);
   L.mf_bytes = (MODE == 0 ? SF_MFP : 1) * S.kih * 16;
-  for (int i = 0; i < 2; i++) { L.off_mf[i] = off; off += up(L.mf_bytes); }
-  for (int i = 0; i < 2; i++) { L.off_ra[i] = off; off += up(S.na_max * 32); }
-  for (int i = 0; i < 2; i++) { L.off_rb[i] = off; off += up(SF_NBC * 32); }
+  for (int i = 0; i < SF_PSTAGES; i++) { L.off_mf[i] = off; off += up(L.mf_bytes); }
+  for (int i = 0; i < SF_PSTAGES; i++) { L.off_ra[i] = off; off += up(S.na_max * 32); }
+  for (int i = 0; i < SF_PSTAGES; i++) { L.off_rb[i] = off; off += up(SF_NBC * 32); }
   L.off_int = off; off += up((2 * S.na_max + 2 * SF_NBC + SF_KMAX) * 4);
   L.off_bar = off;
   L.total = off + 64;
@@ -340,7 +393,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sf_projection_kernel(HamArgs g,
   if (tid < nbc) { zrow_b[tid] = S.zrow[td.b_row0 + tid]; p2l_b[tid] = S.p2l[td.b_row0 + tid]; }
   if (tid < SF_KMAX) slot_z[tid] = tid < nslots ? S.segtab[(size_t)td.seg_a * SF_SEGTAB + 17 + tid] : 0;
   if (tid == 0) {
-    mbar_init(&bar[0], 1); mbar_init(&bar[1], 1);
+    for (int i = 0; i < SF_PSTAGES; i++) mbar_init(&bar[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
@@ -353,7 +406,10 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sf_projection_kernel(HamArgs g,
     bulk_g2s(smem + L.off_ra[buf], S.rg + ((size_t)il * S.dqp_p + td.a_row0) * 4, (unsigned)na * 32, &bar[buf]);
     bulk_g2s(smem + L.off_rb[buf], S.rg + ((size_t)il * S.dqp_p + td.b_row0) * 4, (unsigned)nbc * 32, &bar[buf]);
   };
-  if (tid == 0 && nit > 0) issue(k0, 0);
+  if (tid == 0) {
+    if (nit > 0) issue(k0, 0);
+    if (nit > 1) issue(k0 + 1, 1);
+  }
 
   double hacc[SF_HACC];
 #pragma unroll
@@ -362,8 +418,8 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sf_projection_kernel(HamArgs g,
   const int nks = kih >> 2;
 
   for (int it = 0; it < nit; it++) {
-    const int buf = it & 1;
-    mbar_wait(&bar[buf], (it >> 1) & 1);
+    const int buf = it % SF_PSTAGES;
+    mbar_wait(&bar[buf], (it / SF_PSTAGES) & 1);
     const double* __restrict__ Rb = reinterpret_cast<const double*>(smem + L.off_rb[buf]);
     const double* __restrict__ Ra = reinterpret_cast<const double*>(smem + L.off_ra[buf]);
     // ---- phase G: G^t(ih, (b,c)) = sum_t' mf^{tt'}(ih) phi^t'_b(ih).  A quarter-warp holds 4 grid points x 2 adjacent
@@ -417,8 +473,8 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sf_projection_kernel(HamArgs g,
       }
     }
     __syncthreads();
-    // the buffers of the other parity were last read before this barrier (phase G / phase C of the previous iteration)
-    if (tid == 0 && it + 1 < nit) issue(k0 + it + 1, buf ^ 1);
+    // the stage of iteration it-1 was last read before this barrier (its phase C): refill it for iteration it+2
+    if (tid == 0 && it + 2 < nit) issue(k0 + it + 2, (it + 2) % SF_PSTAGES);
     // ---- phase W: W^w[slot][(b,c)] = sum_ih Z(slot, ih) G(ih, (b,c)) on the tensor cores
     {
       const int nt = warp & 7, part = warp >> 3;

@@ -95,7 +95,7 @@ struct pnfam_b200_ctx {
   // sum-factorised path (separable basis, hamiltonian_sf.cu)
   SfDev sf{};
   std::vector<int> seg_prow0, seg_n, seg_nslots;   // per (block, spin) segment: first padded row, states, n_z slots
-  DBuf<double> d_zt, d_rg;
+  DBuf<double> d_zt, d_rg, d_rgp;
   DBuf<int> d_zrow, d_p2l, d_slot, d_segtab;
   cudaStream_t stream = nullptr;
   int64_t launches = 0;
@@ -110,7 +110,7 @@ static bool setup_separable(pnfam_b200_ctx& c, const pnfam_b200_model& m) {
   const int ngh = m.ngh, ngl = m.ngl, nzr = m.sep_nzrows, N = c.dqp, nghl = c.nghl;
   if ((size_t)ngh * ngl != (size_t)nghl) throw std::runtime_error("model: ngh*ngl != nghl");
   const int mt = (ngh + 7) / 8, kih = (ngh + 3) & ~3;
-  if (2 * mt > SF_THREADS / 32 || 8 * kih > SF_THREADS) return false;
+  if (2 * mt > 12 || 8 * kih > SF_THREADS) return false;   // warp roles of the density, thread map of the G build
   int zs = std::max(8 * mt, kih);
   while (zs % 16 != 4) zs++;
   // the factors must reproduce the tables
@@ -180,10 +180,19 @@ static bool setup_separable(pnfam_b200_ctx& c, const pnfam_b200_model& m) {
     for (int pr = 0; pr < c.dqp_p; pr++)
       if (p2s[pr] >= 0)
         for (int j = 0; j < 4; j++) rg[((size_t)il * c.dqp_p + pr) * 4 + j] = m.sep_r[((size_t)j * N + p2s[pr]) * ngl + il];
+  const int nilp = (ngl + 1) / 2;
+  std::vector<double> rgp((size_t)nilp * c.dqp_p * 8, 0.0);
+  for (int ip = 0; ip < nilp; ip++)
+    for (int pr = 0; pr < c.dqp_p; pr++)
+      for (int k = 0; k < 2; k++) {
+        const int il = std::min(2 * ip + k, ngl - 1);
+        for (int j = 0; j < 4; j++) rgp[((size_t)ip * c.dqp_p + pr) * 8 + k * 4 + j] = rg[((size_t)il * c.dqp_p + pr) * 4 + j];
+      }
+  c.d_rgp.upload(rgp);
   c.d_zt.upload(zt); c.d_rg.upload(rg); c.d_zrow.upload(zrow); c.d_p2l.upload(p2l); c.d_slot.upload(slot); c.d_segtab.upload(segtab);
   SfDev& S = c.sf;
   S.enabled = 1; S.ngh = ngh; S.ngl = ngl; S.mt = mt; S.kih = kih; S.zs = zs; S.nzrows = nzr; S.dqp_p = c.dqp_p;
-  S.zt = c.d_zt.p; S.rg = c.d_rg.p; S.zrow = c.d_zrow.p; S.p2l = c.d_p2l.p; S.slot = c.d_slot.p; S.segtab = c.d_segtab.p;
+  S.zt = c.d_zt.p; S.rg = c.d_rg.p; S.rgp = c.d_rgp.p; S.zrow = c.d_zrow.p; S.p2l = c.d_p2l.p; S.slot = c.d_slot.p; S.segtab = c.d_segtab.p;
   S.na_max = 1; S.kpad_max = 4;
   for (int seg = 0; seg < nseg; seg++) { S.na_max = std::max(S.na_max, c.seg_n[seg]); S.kpad_max = std::max(S.kpad_max, pad4(c.seg_nslots[seg])); }
   if (S.na_max > 8 * 12) return S.enabled = 0, false;
@@ -263,7 +272,7 @@ extern "C" int pnfam_b200_ctx_create(const pnfam_b200_model* m, int device, pnfa
         PNFAM_CUDA_CHECK(cudaDeviceSynchronize());
         c->table_h2d_bytes = (int64_t)NTYPE * nraw * 8;
       } else {
-        c->table_h2d_bytes = (int64_t)(c->d_zt.n + c->d_rg.n) * 8 + (int64_t)(c->d_zrow.n + c->d_p2l.n + c->d_slot.n + c->d_segtab.n) * 4;
+        c->table_h2d_bytes = (int64_t)(c->d_zt.n + c->d_rg.n + c->d_rgp.n) * 8 + (int64_t)(c->d_zrow.n + c->d_p2l.n + c->d_slot.n + c->d_segtab.n) * 4;
       }
     }
     auto up = [&](DBuf<double>& d, const double* p, size_t n) { d.upload(std::vector<double>(p, p + n)); };
