@@ -333,14 +333,20 @@ void launch_density_sf(const HamArgs& a, cudaStream_t stream) {
 // ================================================================================================
 // projection
 // ================================================================================================
-constexpr int SF_GS = 68;    // row stride of G and W (64 interleaved (b,c) columns + 4): conflict-free fragment loads
-constexpr int SF_NBC = 32;   // columns b per output tile
-constexpr int SF_HACC = 12;  // accumulators per thread: rows a = (tid >> 6) + 8 i  (na <= 96)
+// The unit of work is a PAIR TASK: one DMMA n-tile (4 columns b of one spin segment, re/im interleaved) of one
+// (block, a spin segment) output tile, for all il of the CTA's split.  A CTA runs 8 pair tasks that share the spin
+// combination (sa, sb) -- and therefore the field tensor of every il -- on 8 independent warp pairs: the phases of a
+// pair (G build / DMMA / accumulation) are separated by 64-thread named barriers only, so pairs drift against each
+// other and FP64 FMA work of one pair overlaps DMMA work of another; small and large blocks pack on the same SM.
+constexpr int SF_PPAIRS = 8;
+constexpr int SF_HACC = 12;  // accumulators per lane: rows a = (lane64 >> 3) + 8 i  (na <= 96)
 
-constexpr int SF_PSTAGES = 3;  // per-il operand stages of the projection (field tensor + radial factors), prefetch distance 2
 struct SfProjLayout {
-  int off_G, off_W, off_mf[SF_PSTAGES], off_ra[SF_PSTAGES], off_rb[SF_PSTAGES], off_int, off_bar;
-  int mf_bytes;              // bytes of the field tensor of one (il, sa, sb)
+  int off_mf, off_pair, off_bar;   // byte offsets: field tensor ring, per-pair regions, mbarriers
+  int mf_bytes;                    // bytes of the field tensor of one (il, sa, sb)
+  int nst;                         // stages of the field-tensor ring
+  int pair_bytes;                  // per pair: G slice | W slice | Ra | ints
+  int p_W, p_ra, p_int;            // offsets inside a pair region (G slice at 0)
   int total;
 };
 
@@ -350,15 +356,19 @@ static SfProjLayout make_proj_layout(const SfDev& S) {
   SfProjLayout L{};
   auto up = [](int x) { return (x + 127) & ~127; };
   int off = up(3 * S.nzrows * S.zs * 8);
-  L.off_G = off; off += up(std::max(NS * S.kih * SF_GS * 8, 2 * SF_NBC * (S.na_max | 1) * 8));   // reused as transpose buffer
-  L.off_W = off; off += up(2 * 4 * 8 * SF_GS * 8);
   L.mf_bytes = (MODE == 0 ? SF_MFP : 1) * S.kih * 16;
-  for (int i = 0; i < SF_PSTAGES; i++) { L.off_mf[i] = off; off += up(L.mf_bytes); }
-  for (int i = 0; i < SF_PSTAGES; i++) { L.off_ra[i] = off; off += up(S.na_max * 32); }
-  for (int i = 0; i < SF_PSTAGES; i++) { L.off_rb[i] = off; off += up(SF_NBC * 32); }
-  L.off_int = off; off += up((2 * S.na_max + 2 * SF_NBC + SF_KMAX) * 4);
-  L.off_bar = off;
-  L.total = off + 64;
+  const int na_pad = (S.na_max + 7) & ~7;
+  const int g_bytes = std::max(NS * S.kih * 8 * 8, 8 * (na_pad + 1) * 8);    // G slice, reused to transpose the output
+  L.p_W = up(g_bytes);
+  L.p_ra = L.p_W + 2 * 4 * 8 * 8 * 8;
+  L.p_int = L.p_ra + up(na_pad * 32);
+  L.pair_bytes = up(L.p_int + (2 * na_pad + 8) * 4);
+  L.off_pair = off; off += SF_PPAIRS * L.pair_bytes;
+  L.off_bar = off; off += 128;
+  L.off_mf = off;
+  L.nst = std::max(2, std::min(3, (227 * 1024 - off) / up(L.mf_bytes)));
+  off += L.nst * up(L.mf_bytes);
+  L.total = off;
   return L;
 }
 
@@ -369,133 +379,151 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sf_projection_kernel(HamArgs g,
   constexpr int NW = MODE == 0 ? 4 : 1;
   extern __shared__ __align__(128) unsigned char smem[];
   const SfDev& S = g.sf;
-  const SfProjTile td = S.tiles[MODE][q][blockIdx.x];
   const int ksp = blockIdx.y, za = blockIdx.z;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, lr = lane >> 2, lc = lane & 3;
+  const int pr = warp >> 1, h = warp & 1, l64 = h * 32 + lane;       // pair, warp of the pair, lane of the pair
+  const SfProjTile td = S.tiles[MODE][q][(size_t)blockIdx.x * SF_PPAIRS + pr];
+  const SfProjTile t0 = S.tiles[MODE][q][(size_t)blockIdx.x * SF_PPAIRS];   // carries (sa, sb) of the CTA
   const int zs = S.zs, nzr = S.nzrows, kih = S.kih;
-  const int na = td.na, nbc = td.nbc, nslots = td.nslots;
+  const int na = td.na, nslots = td.nslots;
+  const bool active = na > 0;
   double* Zs = reinterpret_cast<double*>(smem);                 // [3][nzrows][zs]
-  double* G = reinterpret_cast<double*>(smem + L.off_G);        // [NS][kih][GS]
-  double* W = reinterpret_cast<double*>(smem + L.off_W);        // [2 parts][4][8][GS]
-  int* ints = reinterpret_cast<int*>(smem + L.off_int);
-  int* slot_a = ints;                       // [na_max]
-  int* p2l_a = ints + S.na_max;             // [na_max]
-  int* zrow_b = ints + 2 * S.na_max;        // [SF_NBC]
-  int* p2l_b = zrow_b + SF_NBC;             // [SF_NBC]
-  int* slot_z = p2l_b + SF_NBC;             // [SF_KMAX]
-  unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem + L.off_bar);
+  unsigned char* pbase = smem + L.off_pair + (size_t)pr * L.pair_bytes;
+  double* G = reinterpret_cast<double*>(pbase);                 // [NS][kih][8], columns swizzled
+  double* W = reinterpret_cast<double*>(pbase + L.p_W);         // [2 parts][4][8 slots][8]
+  double* Ras = reinterpret_cast<double*>(pbase + L.p_ra);      // [na][4]
+  int* slot_a = reinterpret_cast<int*>(pbase + L.p_int);
+  const int na_pad = (S.na_max + 7) & ~7;
+  int* p2l_a = slot_a + na_pad;
+  int* p2l_b = p2l_a + na_pad;                                  // [4]
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(smem + L.off_bar);
+  unsigned long long* empty = full + 4;
+  const int nst = L.nst, dist = nst - 1;
+  const int mf_stride = (L.mf_bytes + 127) & ~127;
   // il range of this split
   const int k_per = (S.ngl + S.ksplit - 1) / S.ksplit;
   const int k0 = ksp * k_per, k1 = min(S.ngl, k0 + k_per), nit = max(0, k1 - k0);
 
   for (int i = tid; i < 3 * nzr * zs; i += SF_THREADS) Zs[i] = S.zt[i];
-  for (int i = tid; i < na; i += SF_THREADS) { slot_a[i] = S.slot[td.a_row0 + i]; p2l_a[i] = S.p2l[td.a_row0 + i]; }
-  if (tid < nbc) { zrow_b[tid] = S.zrow[td.b_row0 + tid]; p2l_b[tid] = S.p2l[td.b_row0 + tid]; }
-  if (tid < SF_KMAX) slot_z[tid] = tid < nslots ? S.segtab[(size_t)td.seg_a * SF_SEGTAB + 17 + tid] : 0;
+  if (active) {
+    for (int i = l64; i < na; i += 64) { slot_a[i] = S.slot[td.a_row0 + i]; p2l_a[i] = S.p2l[td.a_row0 + i]; }
+    if (l64 < 4) p2l_b[l64] = S.p2l[td.b_row0 + l64];
+  }
   if (tid == 0) {
-    for (int i = 0; i < SF_PSTAGES; i++) mbar_init(&bar[i], 1);
+    for (int i = 0; i < nst; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], SF_THREADS / 32); }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
-  const double* __restrict__ mfg = MODE == 0 ? g.mf + ((size_t)za * 2 + q) * sf_mf_elems(S.ngl, kih)
-                                             : g.pf + ((size_t)za * 2 + q) * sf_pf_elems(S.ngl, kih);
-  auto issue = [&](int il, int buf) {
-    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-    mbar_expect_tx(&bar[buf], (unsigned)L.mf_bytes + (unsigned)na * 32 + (unsigned)nbc * 32);
-    bulk_g2s(smem + L.off_mf[buf], mfg + (size_t)((il * 2 + td.sa) * 2 + td.sb) * (L.mf_bytes / 8), (unsigned)L.mf_bytes, &bar[buf]);
-    bulk_g2s(smem + L.off_ra[buf], S.rg + ((size_t)il * S.dqp_p + td.a_row0) * 4, (unsigned)na * 32, &bar[buf]);
-    bulk_g2s(smem + L.off_rb[buf], S.rg + ((size_t)il * S.dqp_p + td.b_row0) * 4, (unsigned)nbc * 32, &bar[buf]);
+  const double* __restrict__ mfg = (MODE == 0 ? g.mf + ((size_t)za * 2 + q) * sf_mf_elems(S.ngl, kih)
+                                              : g.pf + ((size_t)za * 2 + q) * sf_pf_elems(S.ngl, kih)) +
+                                   (size_t)(t0.sa * 2 + t0.sb) * (L.mf_bytes / 8);
+  auto issue = [&](int i) {   // field tensor of iteration i (il = k0 + i) -> stage i % nst
+    const int sg = i % nst;
+    mbar_expect_tx(&full[sg], (unsigned)L.mf_bytes);
+    bulk_g2s(smem + L.off_mf + (size_t)sg * mf_stride, mfg + (size_t)(k0 + i) * 4 * (L.mf_bytes / 8), (unsigned)L.mf_bytes, &full[sg]);
   };
-  if (tid == 0) {
-    if (nit > 0) issue(k0, 0);
-    if (nit > 1) issue(k0 + 1, 1);
-  }
+  if (tid == 0)
+    for (int i = 0; i < dist && i < nit; i++) issue(i);
 
+  // lane-private constants of the pair task
+  const int mt2 = nslots > 8;                                   // two m-tiles of n_z slots: the warps split by m-tile, else by K half
+  const int bq = lane & 3;                                      // G phase: column b of this lane
+  int zb = 0, zrA = 0;
+  if (active) {
+    zb = S.zrow[td.b_row0 + bq];
+    const int slot = (mt2 ? h * 8 : 0) + lr;
+    zrA = slot < nslots ? S.segtab[(size_t)td.seg_a * SF_SEGTAB + 17 + slot] : 0;
+  }
+  const int noct = (kih + 7) >> 3, oct0 = h == 0 ? 0 : (noct + 1) >> 1, oct1 = h == 0 ? (noct + 1) >> 1 : noct;
+  const int nks = kih >> 2;
+  const int ks0 = mt2 ? 0 : (h == 0 ? 0 : (nks + 1) >> 1), ks1 = mt2 ? nks : (h == 0 ? (nks + 1) >> 1 : nks);
+  const int gsw_st = ((lane >> 3) & 1) << 2, gsw_ld = lr ^ ((lc >> 1) << 2);   // column swizzle of the G slice (store / fragment load)
+  // radial factors of iteration 0: R_b of this lane's column (registers), R_a of the rows (3 double2 per lane of the pair)
+  double rb[4] = {0.0, 0.0, 0.0, 0.0};
+  double2 ra[3];
+  auto fetch_r = [&](int il) {
+    if (!active) return;
+    const double* __restrict__ rrow = S.rg + (size_t)il * S.dqp_p * 4;
+#pragma unroll
+    for (int j = 0; j < 4; j++) rb[j] = rrow[(size_t)(td.b_row0 + bq) * 4 + j];
+    const double2* __restrict__ ra2 = reinterpret_cast<const double2*>(rrow + (size_t)td.a_row0 * 4);
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+      const int idx = l64 + 64 * r;
+      ra[r] = idx < 2 * na ? ra2[idx] : make_double2(0.0, 0.0);
+    }
+  };
+  if (nit > 0) fetch_r(k0);
   double hacc[SF_HACC];
 #pragma unroll
   for (int i = 0; i < SF_HACC; i++) hacc[i] = 0.0;
-  const bool mt2 = nslots > 8;              // two m-tiles of n_z slots: warps split by m-tile, else by K half
-  const int nks = kih >> 2;
 
   for (int it = 0; it < nit; it++) {
-    const int buf = it % SF_PSTAGES;
-    mbar_wait(&bar[buf], (it / SF_PSTAGES) & 1);
-    const double* __restrict__ Rb = reinterpret_cast<const double*>(smem + L.off_rb[buf]);
-    const double* __restrict__ Ra = reinterpret_cast<const double*>(smem + L.off_ra[buf]);
-    // ---- phase G: G^t(ih, (b,c)) = sum_t' mf^{tt'}(ih) phi^t'_b(ih).  A quarter-warp holds 4 grid points x 2 adjacent
-    //      columns (conflict-free 16-byte stores); a thread serves columns b, b+8, b+16, b+24 with one field-tensor load.
-    {
-      const int u = tid >> 3, nihq = kih >> 2;
-      if (u < nihq * 4) {
-        const int ihg = (u % nihq) * 4 + (lane & 3), bpair = u / nihq, bb = (lane >> 2) & 1;
-        const double2* __restrict__ mfs = reinterpret_cast<const double2*>(smem + L.off_mf[buf]) + ihg;
-        double ph[4][NS];
+    const int sg = it % nst;
+    // refill the ring: the stage of iteration it-1 is free once every warp has left its G phase
+    if (tid == 0 && it + dist < nit) {
+      if (it >= 1) mbar_wait(&empty[(it + dist) % nst], ((it - 1) / nst) & 1);
+      issue(it + dist);
+    }
+    mbar_wait(&full[sg], (it / nst) & 1);
+    if (active) {
+      // ---- phase G: G^t(ih, (b,c)) = sum_t' mf^{tt'}(ih) phi^t'_b(ih); lane = (ih of an octet, column b)
+      const double2* __restrict__ mfs = reinterpret_cast<const double2*>(smem + L.off_mf + (size_t)sg * mf_stride);
+      for (int oc = oct0; oc < oct1; oc++) {
+        const int ihg = oc * 8 + (lane >> 2);
+        if (ihg < kih) {
+          double ph[NS];
+          const double z0 = Zs[zb * zs + ihg];
+          ph[0] = z0 * rb[0];
+          if (MODE == 0) {
+            const double z1 = Zs[(nzr + zb) * zs + ihg], z2 = Zs[(2 * nzr + zb) * zs + ihg];
+            ph[1] = z0 * rb[1]; ph[2] = z0 * rb[2]; ph[3] = z1 * rb[0]; ph[4] = z2 * rb[0] + z0 * rb[3];
+          }
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-          const int b = 2 * bpair + bb + 8 * k;
-          if (b < nbc) {
-            const int zr = zrow_b[b];
-            const double z0 = Zs[zr * zs + ihg];
-            const double r0 = Rb[b * 4];
-            ph[k][0] = z0 * r0;
-            if (MODE == 0) {
-              const double z1 = Zs[(nzr + zr) * zs + ihg], z2 = Zs[(2 * nzr + zr) * zs + ihg];
-              ph[k][1] = z0 * Rb[b * 4 + 1]; ph[k][2] = z0 * Rb[b * 4 + 2]; ph[k][3] = z1 * r0;
-              ph[k][4] = z2 * r0 + z0 * Rb[b * 4 + 3];
+          for (int t = 0; t < NS; t++) {
+            double gr = 0.0, gi = 0.0;
+            if (MODE == 1) {
+              const double2 v = mfs[ihg];
+              gr = v.x * ph[0]; gi = v.y * ph[0];
+            } else {
+#pragma unroll
+              for (int t2 = 0; t2 < NS; t2++)
+                if (sf_mf_nonzero(t, t2)) {
+                  const double2 v = mfs[sf_mf_pair(t, t2) * kih + ihg];
+                  gr += v.x * ph[t2]; gi += v.y * ph[t2];
+                }
             }
-          } else {
-#pragma unroll
-            for (int t = 0; t < NS; t++) ph[k][t] = 0.0;
-          }
-        }
-#pragma unroll
-        for (int t = 0; t < NS; t++) {
-          double gr[4] = {0.0, 0.0, 0.0, 0.0}, gi[4] = {0.0, 0.0, 0.0, 0.0};
-          if (MODE == 1) {
-            const double2 v = mfs[0];
-#pragma unroll
-            for (int k = 0; k < 4; k++) { gr[k] = v.x * ph[k][0]; gi[k] = v.y * ph[k][0]; }
-          } else {
-#pragma unroll
-            for (int t2 = 0; t2 < NS; t2++)
-              if (sf_mf_nonzero(t, t2)) {
-                const double2 v = mfs[sf_mf_pair(t, t2) * kih];
-#pragma unroll
-                for (int k = 0; k < 4; k++) { gr[k] += v.x * ph[k][t2]; gi[k] += v.y * ph[k][t2]; }
-              }
-          }
-#pragma unroll
-          for (int k = 0; k < 4; k++) {
-            const int b = 2 * bpair + bb + 8 * k;
-            if (b < nbc) *reinterpret_cast<double2*>(&G[((size_t)t * kih + ihg) * SF_GS + 2 * b]) = make_double2(gr[k], gi[k]);
+            *reinterpret_cast<double2*>(&G[((size_t)t * kih + ihg) * 8 + ((2 * bq) ^ gsw_st)]) = make_double2(gr, gi);
           }
         }
       }
     }
-    __syncthreads();
-    // the stage of iteration it-1 was last read before this barrier (its phase C): refill it for iteration it+2
-    if (tid == 0 && it + 2 < nit) issue(k0 + it + 2, (it + 2) % SF_PSTAGES);
-    // ---- phase W: W^w[slot][(b,c)] = sum_ih Z(slot, ih) G(ih, (b,c)) on the tensor cores
-    {
-      const int nt = warp & 7, part = warp >> 3;
-      if (nt * 4 < nbc) {
-        const int mtile = mt2 ? part : 0;
-        const int ks0 = mt2 ? 0 : (part == 0 ? 0 : (nks + 1) >> 1), ks1 = mt2 ? nks : (part == 0 ? (nks + 1) >> 1 : nks);
-        const int zr = slot_z[mtile * 8 + lr];
-        const double* __restrict__ A0 = Zs + (size_t)zr * zs + lc;
-        const double* __restrict__ gp = G + (size_t)lc * SF_GS + nt * 8 + lr;
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[sg]);
+    if (active) {
+      named_bar_sync(1 + pr, 64);
+      // radial factors of the rows for this il -> shared memory of the pair (phase C of il-1 is behind the barrier)
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        const int idx = l64 + 64 * r;
+        if (idx < 2 * na) reinterpret_cast<double2*>(Ras)[idx] = ra[r];
+      }
+      // ---- phase W: W^w[slot][(b,c)] = sum_ih Z(slot, ih) G(ih, (b,c)) on the tensor cores
+      {
+        const double* __restrict__ A0 = Zs + (size_t)zrA * zs + lc;
+        const double* __restrict__ gp = G + (size_t)lc * 8 + gsw_ld;
         double C[6][2];
 #pragma unroll
         for (int i = 0; i < 12; i++) (&C[0][0])[i] = 0.0;
 #pragma unroll 2
         for (int ks = ks0; ks < ks1; ks++) {
           const double a0 = A0[ks * 4];
-          const double* __restrict__ gk = gp + (size_t)ks * 4 * SF_GS;
+          const double* __restrict__ gk = gp + (size_t)ks * 32;
           const double g0 = gk[0];
           dmma884(C[0][0], C[0][1], a0, g0);
           if (MODE == 0) {
             const double a1 = A0[(size_t)nzr * zs + ks * 4], a2 = A0[(size_t)2 * nzr * zs + ks * 4];
-            const size_t gt = (size_t)kih * SF_GS;
+            const size_t gt = (size_t)kih * 8;
             const double g1 = gk[gt], g2 = gk[2 * gt], g3 = gk[3 * gt], g4 = gk[4 * gt];
             dmma884(C[1][0], C[1][1], a0, g1);
             dmma884(C[2][0], C[2][1], a0, g2);
@@ -504,59 +532,56 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sf_projection_kernel(HamArgs g,
             dmma884(C[5][0], C[5][1], a2, g4);
           }
         }
-        double* __restrict__ wp = W + ((size_t)(part * 4) * 8 + lr) * SF_GS + nt * 8 + 2 * lc;
+        double* __restrict__ wp = W + ((size_t)(h * 4) * 8 + lr) * 8 + 2 * lc;
         if (MODE == 0) {
           *reinterpret_cast<double2*>(wp) = make_double2(C[0][0] + C[4][0] + C[5][0], C[0][1] + C[4][1] + C[5][1]);
-          *reinterpret_cast<double2*>(wp + 8 * SF_GS) = make_double2(C[1][0], C[1][1]);
-          *reinterpret_cast<double2*>(wp + 16 * SF_GS) = make_double2(C[2][0], C[2][1]);
-          *reinterpret_cast<double2*>(wp + 24 * SF_GS) = make_double2(C[3][0], C[3][1]);
+          *reinterpret_cast<double2*>(wp + 64) = make_double2(C[1][0], C[1][1]);
+          *reinterpret_cast<double2*>(wp + 128) = make_double2(C[2][0], C[2][1]);
+          *reinterpret_cast<double2*>(wp + 192) = make_double2(C[3][0], C[3][1]);
         } else {
           *reinterpret_cast<double2*>(wp) = make_double2(C[0][0], C[0][1]);
         }
       }
-    }
-    __syncthreads();
-    // ---- phase C: h[a][(b,c)] += sum_w R^w_a(il) W^w[slot(a)][(b,c)]
-    {
-      const int col = tid & 63, ar = tid >> 6;
-      if (col < 2 * nbc) {
+      // next il's radial factors: issued here, consumed one iteration later
+      if (it + 1 < nit) fetch_r(k0 + it + 1);
+      named_bar_sync(1 + pr, 64);
+      // ---- phase C: h[a][(b,c)] += sum_w R^w_a(il) W^w[slot(a)][(b,c)]
+      {
+        const int col = l64 & 7, ar = l64 >> 3;
 #pragma unroll
         for (int i = 0; i < SF_HACC; i++) {
           const int a = ar + 8 * i;
           if (a < na) {
             const int sl = slot_a[a];
-            const double* __restrict__ w0 = W + ((size_t)((mt2 ? sl >> 3 : 0) * 4) * 8 + (sl & 7)) * SF_GS + col;
+            const double* __restrict__ w0 = W + ((size_t)((mt2 ? sl >> 3 : 0) * 4) * 8 + (sl & 7)) * 8 + col;
             double s = 0.0;
 #pragma unroll
             for (int w = 0; w < NW; w++) {
-              double x = w0[(size_t)w * 8 * SF_GS];
-              if (!mt2) x += w0[(size_t)(4 + w) * 8 * SF_GS];
-              s += Ra[a * 4 + w] * x;
+              double x = w0[w * 64];
+              if (!mt2) x += w0[(4 + w) * 64];
+              s += Ras[a * 4 + w] * x;
             }
             hacc[i] += s;
           }
         }
       }
     }
-    // W is rewritten after the first barrier of the next iteration, G after this phase: no barrier needed here
   }
-  __syncthreads();
-  // ---- output through shared memory (rows a fastest): partial of this il split, factor 2 applied by the reduction
-  {
+  // ---- output through the pair's G slice (rows a fastest): partial of this il split, factor 2 applied by the reduction
+  if (active) {
+    named_bar_sync(1 + pr, 64);
     double* Tr = G;                                     // [col][na | 1]
     const int lda = na | 1;
-    const int col = tid & 63, ar = tid >> 6;
-    if (col < 2 * nbc) {
+    const int col = l64 & 7, ar = l64 >> 3;
 #pragma unroll
-      for (int i = 0; i < SF_HACC; i++) {
-        const int a = ar + 8 * i;
-        if (a < na) Tr[col * lda + a] = hacc[i];
-      }
+    for (int i = 0; i < SF_HACC; i++) {
+      const int a = ar + 8 * i;
+      if (a < na) Tr[col * lda + a] = hacc[i];
     }
-    __syncthreads();
+    named_bar_sync(1 + pr, 64);
     const size_t pstride = 2 * g.nxy;
     double* __restrict__ part = g.hpart + (((size_t)za * 2 + q) * 2 + MODE) * (size_t)S.ksplit * pstride + (size_t)ksp * pstride;
-    for (int idx = tid; idx < 2 * nbc * na; idx += SF_THREADS) {
+    for (int idx = l64; idx < 8 * na; idx += 64) {
       const int colx = idx / na, a = idx - colx * na;
       const int lb = p2l_b[colx >> 1];
       if (lb >= 0) part[(size_t)(colx & 1) * g.nxy + td.out_off + p2l_a[a] + (size_t)lb * td.ld] = Tr[colx * lda + a];
@@ -594,9 +619,9 @@ void launch_projection_sf(const HamArgs& a, cudaStream_t stream) {
   }
   for (int q = 0; q < 2; q++) {
     if (S.ntiles[0][q] > 0)
-      sf_projection_kernel<0><<<dim3(S.ntiles[0][q], S.ksplit, a.nactive), SF_THREADS, L0.total, stream>>>(a, L0, q);
+      sf_projection_kernel<0><<<dim3(S.ntiles[0][q] / SF_PPAIRS, S.ksplit, a.nactive), SF_THREADS, L0.total, stream>>>(a, L0, q);
     if (S.ntiles[1][q] > 0)
-      sf_projection_kernel<1><<<dim3(S.ntiles[1][q], S.ksplit, a.nactive), SF_THREADS, L1.total, stream>>>(a, L1, q);
+      sf_projection_kernel<1><<<dim3(S.ntiles[1][q] / SF_PPAIRS, S.ksplit, a.nactive), SF_THREADS, L1.total, stream>>>(a, L1, q);
   }
   dim3 gr((unsigned)((2 * a.nxy + 255) / 256), 4, a.nactive);
   sf_projection_reduce_kernel<<<gr, 256, 0, stream>>>(a, S.ksplit);

@@ -89,7 +89,8 @@ struct SfDensStep {              // one (a spin segment) x (b column chunk insid
   int rho_off, ld;               // element offset of the block in the block matrix, leading dimension
   int pad;
 };
-struct SfProjTile {              // output tile of the projection: (a spin segment) x (b column chunk in one spin segment)
+struct SfProjTile {              // pair task of the projection: (a spin segment) x (4 padded columns b of one spin segment);
+                                 // na = 0: padding entry (the list holds groups of 8 tasks with equal (sa, sb))
   int seg_a, a_row0, na, nslots;
   int b_row0, nbc, sa, sb;
   int out_off, ld, pad0, pad1;

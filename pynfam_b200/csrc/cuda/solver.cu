@@ -359,27 +359,36 @@ size_t upload_sf_density_steps(const pnfam_b200_ctx& c, const BlockStruct& st, D
 }
 
 void upload_sf_proj_tiles(const pnfam_b200_ctx& c, const BlockStruct& st, DBuf<SfProjTile>& buf, int& n) {
+  // pair tasks (4 padded columns each), grouped by spin combination, the long ones first inside a group, groups
+  // padded to multiples of 8 (one CTA = 8 tasks with the same field tensor)
   std::vector<SfProjTile> h;
-  for (int ix = 0; ix < c.nb; ix++) {
-    const int iy = st.r2c[ix];
-    if (iy < 0) continue;
-    for (int s = 0; s < 4; s++) {
+  for (int s = 0; s < 4; s++) {
+    std::vector<SfProjTile> grp;
+    for (int ix = 0; ix < c.nb; ix++) {
+      const int iy = st.r2c[ix];
+      if (iy < 0) continue;
       const int sa = 2 * ix + (s >> 1), sb = 2 * iy + (s & 1);
       if (c.seg_n[sa] == 0 || c.seg_n[sb] == 0) continue;
       const int nb4 = (c.seg_n[sb] + 3) & ~3;
-      for (int b0 = 0; b0 < nb4; b0 += 32) {
+      for (int b0 = 0; b0 < nb4; b0 += 4) {
         SfProjTile t{};
         t.seg_a = sa; t.a_row0 = c.seg_prow0[sa]; t.na = c.seg_n[sa]; t.nslots = c.seg_nslots[sa];
-        t.b_row0 = c.seg_prow0[sb] + b0; t.nbc = std::min(32, nb4 - b0); t.sa = s >> 1; t.sb = s & 1;
+        t.b_row0 = c.seg_prow0[sb] + b0; t.nbc = 4; t.sa = s >> 1; t.sb = s & 1;
         t.out_off = st.r2m[ix]; t.ld = c.db[ix];
-        h.push_back(t);
+        grp.push_back(t);
       }
     }
+    std::stable_sort(grp.begin(), grp.end(), [](const SfProjTile& x, const SfProjTile& y) {
+      const long cx = (x.nslots > 8 ? 2000 : 1000) + x.na, cy = (y.nslots > 8 ? 2000 : 1000) + y.na;
+      return cx > cy;
+    });
+    while (grp.size() % 8 != 0) {
+      SfProjTile t{};
+      t.sa = s >> 1; t.sb = s & 1;
+      grp.push_back(t);
+    }
+    h.insert(h.end(), grp.begin(), grp.end());
   }
-  // the long tiles first: the short ones fill the tail of the launch
-  std::stable_sort(h.begin(), h.end(), [](const SfProjTile& x, const SfProjTile& y) {
-    return (long)x.nbc * (x.nslots > 8 ? 16 : 8) > (long)y.nbc * (y.nslots > 8 ? 16 : 8);
-  });
   n = (int)h.size();
   if (h.empty()) h.push_back(SfProjTile{});
   buf.upload(h);
@@ -473,7 +482,7 @@ std::unique_ptr<OperatorDev> make_operator(pnfam_b200_ctx& c, const pnfam_b200_o
     upload_sf_proj_tiles(c, od->plan.hsp[3], od->sf_tiles[0][1], od->sf_ntiles[0][1]);
     upload_sf_proj_tiles(c, od->plan.hsp[1], od->sf_tiles[1][0], od->sf_ntiles[1][0]);
     upload_sf_proj_tiles(c, od->plan.hsp[2], od->sf_tiles[1][1], od->sf_ntiles[1][1]);
-    const int per = std::max(1, od->sf_ntiles[0][0] * std::max(1, npoints));
+    const int per = std::max(1, od->sf_ntiles[0][0] / 8 * std::max(1, npoints));
     od->sf_ksplit = std::min(c.sf.ngl, std::max(1, (2 * 148 + per - 1) / per));
     od->proj.ksplit = od->sf_ksplit;      // sizes the split-K partials
     return od;
@@ -806,7 +815,7 @@ extern "C" int pnfam_b200_calc_hamiltonian(pnfam_b200_ctx* c, const pnfam_b200_b
       upload_sf_proj_tiles(*c, hout[3], sf_tiles[1][1], h.sf.ntiles[1][1]);
       for (int m = 0; m < 2; m++)
         for (int q = 0; q < 2; q++) h.sf.tiles[m][q] = sf_tiles[m][q].p;
-      h.sf.ksplit = std::min(c->sf.ngl, std::max(1, (2 * 148 + std::max(1, h.sf.ntiles[0][0]) - 1) / std::max(1, h.sf.ntiles[0][0])));
+      h.sf.ksplit = std::min(c->sf.ngl, std::max(1, (2 * 148 + std::max(1, h.sf.ntiles[0][0] / 8) - 1) / std::max(1, h.sf.ntiles[0][0] / 8)));
       pp.ksplit = h.sf.ksplit;
       h.sf.pk_stride[0] = h.pk_stride_rho; h.sf.pk_stride[1] = h.pk_stride_kap;
     } else {
