@@ -185,6 +185,8 @@ struct MixArgs {
   double* gram;                   // [P][M][M]
   double* work;                   // [P][M]   df_i . vout
   double* gamma;                  // [P][M]
+  double* dotpart;                // [P][M][nslices][2] slice partials of (df_i . df_new, df_i . vout)
+  int nslices;                    // broyden_slices(n)
   double* red;                    // [P][nred][2] partial (max, sumsq)
   int nred;
   double* si;                     // [P]
@@ -197,6 +199,8 @@ struct MixArgs {
   int nactive;
 };
 void launch_greens(const MixArgs& a, cudaStream_t stream);
+int broyden_slices(size_t n);
+int broyden_max_history();       // largest broyden_history_size the dots kernel stages
 size_t strength_partial_elems(int npoints, int nstr);
 void launch_broyden(const MixArgs& a, int iter, cudaStream_t stream);
 void launch_strength(const MixArgs& a, cudaStream_t stream);

@@ -118,63 +118,115 @@ __global__ void bro_linear_kernel(MixArgs a, double alpha) {
   a.vin[(size_t)p * a.n + e] += alpha * a.vout[(size_t)p * a.n + e];
 }
 
-// dots of the (raw) newest difference vector and of vout with every stored df_i
+// dots of the (raw) newest difference vector and of vout with every stored df_i.  One CTA owns a slice of BRO_SLICE
+// elements of one point: the slices of df_new and vout stay in registers while the CTA streams the same slice of every
+// history vector once (8 independent 8-byte loads per thread in flight), so the history is read exactly once per
+// iteration at HBM rate.  Slice partials are summed in a fixed order by bro_solve_kernel (deterministic).
+constexpr int BRO_SLICE = 2048;
+constexpr int BRO_MMAX = 64;     // history slots the shared staging of the dots kernel holds
 __global__ void __launch_bounds__(256) bro_dots_kernel(MixArgs a, int ipos, int iter_used) {
-  __shared__ double sh[8];
-  const int i = blockIdx.x, za = blockIdx.y, p = a.active[za];
-  const double* dfi = a.df + ((size_t)p * a.M + i) * a.n;
-  const double* dfn = a.df + ((size_t)p * a.M + ipos) * a.n;
-  const double* vo = a.vout + (size_t)p * a.n;
-  double s1 = 0.0, s2 = 0.0;
-  for (size_t e = threadIdx.x; e < a.n; e += blockDim.x) {
-    const double f = dfi[e];
-    s1 += f * dfn[e];
-    s2 += f * vo[e];
+  __shared__ double sh[BRO_MMAX][8][2];
+  const int sl = blockIdx.x, za = blockIdx.y, p = a.active[za];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t e0 = (size_t)sl * BRO_SLICE + threadIdx.x;
+  const double* __restrict__ dfp = a.df + (size_t)p * a.M * a.n;
+  const double* __restrict__ dfn = dfp + (size_t)ipos * a.n;
+  const double* __restrict__ vo = a.vout + (size_t)p * a.n;
+  double fn[8], v[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const size_t e = e0 + (size_t)j * 256;
+    fn[j] = e < a.n ? dfn[e] : 0.0;
+    v[j] = e < a.n ? vo[e] : 0.0;
   }
-  s1 = block_sum(s1, sh);
-  s2 = block_sum(s2, sh);
-  if (threadIdx.x == 0) {
-    const double nm = a.normi[p];
-    // df_ipos is still un-normalised in memory: scale the dots instead
-    double* G = a.gram + (size_t)p * a.M * a.M;
-    if (i == ipos) {
-      G[(size_t)i * a.M + i] = 1.0 + a.w0 * a.w0;
-      a.work[(size_t)p * a.M + i] = s2 * nm;
-    } else {
-      G[(size_t)i * a.M + ipos] = G[(size_t)ipos * a.M + i] = s1 * nm;
-      a.work[(size_t)p * a.M + i] = s2;
+  for (int i = 0; i < iter_used; i++) {
+    const double* __restrict__ dfi = dfp + (size_t)i * a.n;
+    double f[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const size_t e = e0 + (size_t)j * 256;
+      f[j] = e < a.n ? dfi[e] : 0.0;
     }
+    double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) { s1 += f[j] * fn[j]; s2 += f[j] * v[j]; }
+    for (int o = 16; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if (lane == 0) { sh[i][warp][0] = s1; sh[i][warp][1] = s2; }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < iter_used; i += blockDim.x) {
+    double s1 = 0.0, s2 = 0.0;
+    for (int w = 0; w < 8; w++) { s1 += sh[i][w][0]; s2 += sh[i][w][1]; }
+    double* part = a.dotpart + (((size_t)p * a.M + i) * a.nslices + sl) * 2;
+    part[0] = s1; part[1] = s2;
   }
 }
 
-// gamma = B^{-1} work, B = Gram + w0^2 on the diagonal (SPD): Cholesky in one thread (M <= ~50)
-__global__ void bro_solve_kernel(MixArgs a, int iter_used) {
+// gamma = B^{-1} work, B = Gram + w0^2 on the diagonal (SPD): Cholesky in shared memory by one CTA (M <= 64)
+__global__ void bro_solve_kernel(MixArgs a, int ipos, int iter_used) {
   extern __shared__ double L[];
   const int p = a.active[blockIdx.x];
-  if (threadIdx.x != 0) return;
   const int n = iter_used, M = a.M;
-  const double* G = a.gram + (size_t)p * M * M;
-  double* y = L + (size_t)n * n;
-  for (int j = 0; j < n; j++) {
-    for (int i = j; i < n; i++) {
-      double s = (i == j) ? (1.0 + a.w0 * a.w0) : G[(size_t)i * M + j];
-      for (int k = 0; k < j; k++) s -= L[i * n + k] * L[j * n + k];
-      if (i == j) L[j * n + j] = sqrt(s);
-      else L[i * n + j] = s / L[j * n + j];
+  double* G = a.gram + (size_t)p * M * M;
+  // finish the dots: sum the slice partials in a fixed order; df_ipos is still un-normalised in memory, so the dots
+  // with it are scaled instead
+  {
+    const double nm = a.normi[p];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const double* part = a.dotpart + ((size_t)p * M + i) * a.nslices * 2;
+      double s1 = 0.0, s2 = 0.0;
+      for (int k = 0; k < a.nslices; k++) { s1 += part[2 * k]; s2 += part[2 * k + 1]; }
+      if (i == ipos) {
+        G[(size_t)i * M + i] = 1.0 + a.w0 * a.w0;
+        a.work[(size_t)p * M + i] = s2 * nm;
+      } else {
+        G[(size_t)i * M + ipos] = G[(size_t)ipos * M + i] = s1 * nm;
+        a.work[(size_t)p * M + i] = s2;
+      }
     }
   }
-  const double* w = a.work + (size_t)p * M;
-  for (int i = 0; i < n; i++) {
-    double s = w[i];
-    for (int k = 0; k < i; k++) s -= L[i * n + k] * y[k];
-    y[i] = s / L[i * n + i];
+  __syncthreads();
+  // Cholesky of B (right-looking, the trailing update spread over the CTA), then the two triangular solves
+  const int ld = n + 1, tid = threadIdx.x, nt = blockDim.x;
+  double* y = L + (size_t)n * ld;
+  for (int idx = tid; idx < n * n; idx += nt) {
+    const int i = idx / n, j = idx - i * n;
+    L[i * ld + j] = (i == j) ? (1.0 + a.w0 * a.w0) : G[(size_t)i * M + j];
+  }
+  for (int i = tid; i < n; i += nt) y[i] = a.work[(size_t)p * M + i];
+  __syncthreads();
+  for (int j = 0; j < n; j++) {
+    if (tid == 0) L[j * ld + j] = sqrt(L[j * ld + j]);
+    __syncthreads();
+    const double d = L[j * ld + j];
+    for (int i = j + 1 + tid; i < n; i += nt) L[i * ld + j] /= d;
+    __syncthreads();
+    const int m = n - j - 1;
+    for (int idx = tid; idx < m * m; idx += nt) {
+      const int ii = idx / m, kk = idx - ii * m;
+      if (kk <= ii) L[(j + 1 + ii) * ld + j + 1 + kk] -= L[(j + 1 + ii) * ld + j] * L[(j + 1 + kk) * ld + j];
+    }
+    __syncthreads();
+  }
+  for (int i = 0; i < n; i++) {          // L y = work
+    if (tid == 0) y[i] /= L[i * ld + i];
+    __syncthreads();
+    const double yi = y[i];
+    for (int r = i + 1 + tid; r < n; r += nt) y[r] -= L[r * ld + i] * yi;
+    __syncthreads();
+  }
+  for (int i = n - 1; i >= 0; i--) {     // L^T gamma = y
+    if (tid == 0) y[i] /= L[i * ld + i];
+    __syncthreads();
+    const double yi = y[i];
+    for (int r = tid; r < i; r += nt) y[r] -= L[i * ld + r] * yi;
+    __syncthreads();
   }
   double* gm = a.gamma + (size_t)p * M;
-  for (int i = n - 1; i >= 0; i--) {
-    double s = y[i];
-    for (int k = i + 1; k < n; k++) s -= L[k * n + i] * gm[k];
-    gm[i] = s / L[i * n + i];
-  }
+  for (int i = tid; i < n; i += nt) gm[i] = y[i];
 }
 
 // curv = alpha*vout - sum_i gamma_i (dv_i + alpha df_i); store (vout, vin) in slot inext; vin += curv
@@ -223,9 +275,9 @@ void launch_broyden(const MixArgs& a, int iter, cudaStream_t stream) {
     return;
   }
   if (iter_used > 0) {
-    bro_dots_kernel<<<dim3(iter_used, a.nactive), 256, 0, stream>>>(a, ipos, iter_used);
-    const size_t sh = ((size_t)iter_used * iter_used + iter_used) * sizeof(double);
-    bro_solve_kernel<<<a.nactive, 32, sh, stream>>>(a, iter_used);
+    bro_dots_kernel<<<dim3(a.nslices, a.nactive), 256, 0, stream>>>(a, ipos, iter_used);
+    const size_t sh = ((size_t)iter_used * (iter_used + 1) + iter_used) * sizeof(double);
+    bro_solve_kernel<<<a.nactive, 128, sh, stream>>>(a, ipos, iter_used);
   }
   bro_update_kernel<<<dim3(nblk, a.nactive), 256, 0, stream>>>(a, ipos, inext, iter_used);
 }
@@ -269,6 +321,8 @@ __global__ void strength_final_kernel(MixArgs a) {
   a.strength[((size_t)p * a.nstr + k) * 2] = -sre / pi;
   a.strength[((size_t)p * a.nstr + k) * 2 + 1] = -sim / pi;
 }
+int broyden_slices(size_t n) { return (int)((n + BRO_SLICE - 1) / BRO_SLICE); }
+int broyden_max_history() { return BRO_MMAX; }
 size_t strength_partial_elems(int npoints, int nstr) { return (size_t)npoints * nstr * STR_SPLIT * 2; }
 
 void launch_strength(const MixArgs& a, cudaStream_t stream) {

@@ -555,6 +555,7 @@ extern "C" int pnfam_b200_solve(pnfam_b200_ctx* c, const pnfam_b200_operator* op
     const bool no_residual = std::fabs(quench) < 1e-10;
     const int M = no_residual ? -1 : prm->broyden_history_size;
     const int Malloc = std::max(M, 1);
+    if (M > broyden_max_history()) throw std::runtime_error("broyden_history_size above the " + std::to_string(broyden_max_history()) + " slots the device mixer stages");
     const bool bminus = op->beta_minus != 0;
 
     // ---- static per-operator tables ---------------------------------------------------------------
@@ -587,7 +588,7 @@ extern "C" int pnfam_b200_solve(pnfam_b200_ctx* c, const pnfam_b200_operator* op
     }
 
     // ---- per-point state ---------------------------------------------------------------------------------
-    DBuf<double> vin, vout, df, dv, gram, work, gamma, red, d_si, d_normi, d_omega, d_str, d_strpart;
+    DBuf<double> vin, vout, df, dv, gram, work, gamma, dotpart, red, d_si, d_normi, d_omega, d_str, d_strpart;
     DBuf<double> rsp, hsp, hqp, scratch, dd_rho, dd_kap, mf, pf, hpart, pk_rho, pk_kap;
     DBuf<int> d_active;
     const int nred = 64;
@@ -597,6 +598,7 @@ extern "C" int pnfam_b200_solve(pnfam_b200_ctx* c, const pnfam_b200_operator* op
     if (M > 0) { df.alloc((size_t)P * Malloc * n); dv.alloc((size_t)P * Malloc * n); }
     gram.alloc((size_t)P * Malloc * Malloc); work.alloc((size_t)P * Malloc); gamma.alloc((size_t)P * Malloc);
     gram.zero(); work.zero(); gamma.zero();
+    dotpart.alloc((size_t)P * Malloc * broyden_slices(n) * 2);
     red.alloc((size_t)P * nred * 2); d_si.alloc(P); d_normi.alloc(P); d_omega.alloc((size_t)P * 2);
     d_str.alloc((size_t)P * nstr * 2); d_strpart.alloc(strength_partial_elems(P, nstr));
     rsp.alloc((size_t)P * 8 * nxy); hsp.alloc((size_t)P * 8 * nxy); hqp.alloc((size_t)P * 8 * nxy);
@@ -658,6 +660,7 @@ extern "C" int pnfam_b200_solve(pnfam_b200_ctx* c, const pnfam_b200_operator* op
     ma.hqp = hqp.p; ma.fqp = od->gqp.p; ma.esum = od->esum.p; ma.tfac = c->use_diag ? od->tfac.p : nullptr;
     ma.omega = d_omega.p; ma.quench = no_residual ? 0.0 : quench;
     ma.vin = vin.p; ma.vout = vout.p; ma.df = df.p; ma.dv = dv.p; ma.gram = gram.p; ma.work = work.p; ma.gamma = gamma.p;
+    ma.dotpart = dotpart.p; ma.nslices = broyden_slices(n);
     ma.red = red.p; ma.nred = nred; ma.si = d_si.p; ma.normi = d_normi.p; ma.gqp = od->gqp.p; ma.nstr = nstr;
     ma.strength = d_str.p; ma.strpart = d_strpart.p; ma.active = d_active.p;
 

@@ -1,0 +1,449 @@
+"""In-process contour driver and strength assembly.
+
+The reference computes the strength function of one (operator, K) along a complex-energy contour by farming one
+`pnfam_main.x` process per contour point (pynfam/strength/fam_strength.py:204-249), parsing the `.dat` files back and
+concatenating them into `OP.out` (text) and `OP.out.ctr` (Fortran-unformatted, the file betadecay / shapeFactor read).
+Here the whole contour of an operator is ONE batched GPU solve (`gpu.Context.solve`), and this module mirrors the
+reference-side interface around it -- same class / method names, argument meaning and file formats:
+
+    famContour      pynfam/strength/contour.py:19-340      (CIRCLE, CONSTL, CONSTR)
+    famStrength     pynfam/strength/fam_strength.py:28-680 (concatFamStr, writeStrengthOut, writeCtrBinary, readCtrBinary)
+
+so a maintainer replaces the `getFamList` + task-farm + `concatFamData` sequence by `famStrength.compute(...)`
+(INTEGRATION.md).  There is no CPU fallback: `compute` needs the CUDA library and a device.
+"""
+import os
+import re
+import struct
+import time
+
+import numpy as np
+
+TMIN = 1e-3   # pynfam/config.py: finite temperature is not supported by this path (fails loudly in the host set-up)
+
+_CONTOUR_DEFAULTS = {
+    # pynfam/config.py:147-164 (+ the energy interval keys every contour carries, :140-146)
+    "CIRCLE": dict(energy_min=0.0, energy_max=0.0, hfb_emin_buff=0.0, nr_points=60, use_gauleg_ctr=True,
+                   beta_quadrature="GAUSS", shift_imag=0.0, theta_init=np.pi, max_height=30),
+    "CONSTL": dict(energy_min=0.0, energy_max=0.0, hfb_emin_buff=0.0, nr_points=60, half_width=0.1,
+                   beta_quadrature="TRAP"),
+    "CONSTR": dict(energy_min=0.0, energy_max=0.0, hfb_emin_buff=0.0, half_width=0.1, de_hw_ratio=1.0,
+                   beta_quadrature="TRAP"),
+}
+
+
+class famContour(object):
+    """Complex-energy contour and its integration data (pynfam/strength/contour.py:19-131).
+
+    Args:
+        contour (str): 'CIRCLE', 'CONSTL' or 'CONSTR'.
+        override (dict): settings overriding the defaults (unknown keys raise KeyError, as in the reference).
+    """
+
+    def __init__(self, contour, override=None):
+        self.name = contour.upper()
+        if self.name not in _CONTOUR_DEFAULTS:
+            raise ValueError("contour type %r is not supported by this path (CIRCLE, CONSTL, CONSTR)" % contour)
+        self._settings = dict(_CONTOUR_DEFAULTS[self.name])
+        self._generateCtrData()
+        if override is not None:
+            self.updateSettings(override)
+
+    name_and_int = property(lambda s: "{:} on ({:.2e}, {:.2e})".format(s.name, s.energy_min, s.energy_max))
+    closed = property(lambda s: s._ctr_data["closed"])
+    nr_points = property(lambda s: s._ctr_data["nr_points"])
+    nr_compute = property(lambda s: s._ctr_data["nr_compute"])
+    use_gauleg = property(lambda s: s._ctr_data["use_gl_ctr"])
+    ctr_z = property(lambda s: s._ctr_data["ctr_z"])
+    ctr_dzdt = property(lambda s: s._ctr_data["ctr_dzdt"])
+    theta = property(lambda s: s._ctr_data["theta"])
+    glwts = property(lambda s: s._ctr_data["glwts"])
+    half_width = property(lambda s: s._ctr_data["half_width"])
+    quadrature = property(lambda s: s._ctr_data["quad"])
+    energy_min = property(lambda s: s._settings["energy_min"])
+    energy_max = property(lambda s: s._settings["energy_max"])
+
+    def updateSettings(self, override):
+        for h in override:
+            if h not in self._settings:
+                raise KeyError("Invalid override setting {:} for contour {:}.".format(h, self.name))
+            self._settings[h] = override[h]
+        self._generateCtrData()
+
+    def setHfbInterval(self, hfb, beta, shift=0.0):
+        """Interval [min(E_gs - buffer, 0), EQRPA_max] (+ shift) from a dict of HFB properties
+        (contour.py:147-205; zero-temperature branch)."""
+        Egs, eqrpamax = hfb["E_gs"], hfb["EQRPA_max"]
+        if hfb.get("ft_active", False):
+            raise NotImplementedError("finite temperature is outside this path")
+        emin = min(Egs - self._settings["hfb_emin_buff"], 0.0)
+        self._settings["energy_min"] = emin + shift
+        self._settings["energy_max"] = eqrpamax + shift
+        if np.isnan(Egs) or np.isnan(eqrpamax):
+            self._settings["energy_min"] = self._settings["energy_max"] = 0.0
+        self._generateCtrData()
+
+    def _generateCtrData(self):
+        self._ctr_data = {"CIRCLE": self._contourCircle, "CONSTL": self._contourConstL,
+                          "CONSTR": self._contourConstR}[self.name]()
+
+    def _contourCircle(self):
+        """contour.py:212-283: circle through (energy_min, energy_max) centred on the real axis (an ellipse of height
+        max_height when the radius exceeds it), Gauss-Legendre or equally spaced in theta; the lower half is computed
+        and the upper half follows from S(w*) = S(w)* unless the contour is shifted or rotated."""
+        s = self._settings
+        npts, t0 = s["nr_points"], s["theta_init"]
+        if s["use_gauleg_ctr"]:
+            theta, glwts = np.polynomial.legendre.leggauss(npts)
+            t1 = t0 + 2.0 * np.pi
+            f1, f2 = 0.5 * (t0 + t1), 0.5 * (t1 - t0)
+            glwts = glwts * f2
+            theta = theta * f2 + f1
+        else:
+            theta = np.linspace(t0, t0 + 2.0 * np.pi, npts)
+            glwts = np.zeros(npts)
+        r0 = 0.5 * (s["energy_max"] + s["energy_min"])
+        r = s["energy_max"] - r0
+        if r > s["max_height"]:
+            cos, sin = np.cos(theta), np.sin(theta)
+            ctr_z = r0 + r * cos + s["max_height"] * sin * 1j
+            ctr_dzdt = -r * sin + s["max_height"] * cos * 1j
+        else:
+            ctr_z = r0 + r * np.exp(1j * theta)
+            ctr_dzdt = 1j * (ctr_z - r0)
+        nr_compute = (npts + 1) // 2
+        if s["shift_imag"] != 0:
+            ctr_z = ctr_z + s["shift_imag"] * 1j
+            nr_compute = npts
+        elif s["use_gauleg_ctr"]:
+            if abs(np.mod(t0, np.pi)) > 1e-10:
+                nr_compute = npts
+        else:
+            if abs(np.mod(t0, np.pi / (npts - 1))) > 1e-10:
+                nr_compute = npts
+        return dict(nr_points=npts, nr_compute=nr_compute, use_gl_ctr=s["use_gauleg_ctr"], ctr_z=ctr_z,
+                    ctr_dzdt=ctr_dzdt, theta=theta, glwts=glwts, half_width=None, quad=s["beta_quadrature"], closed=True)
+
+    def _line(self, w):
+        hw = self._settings["half_width"]
+        ctr_z = (w * 1j + np.imag(hw)) if not np.isreal(hw) else (w + np.real(hw) * 1j)
+        n = len(ctr_z)
+        return dict(nr_points=n, nr_compute=n, use_gl_ctr=False, ctr_z=ctr_z, ctr_dzdt=np.ones(n), theta=np.zeros(n),
+                    glwts=np.zeros(n), half_width=hw, quad=self._settings["beta_quadrature"], closed=False)
+
+    def _contourConstR(self):
+        """contour.py:286-318: line at constant half width, spacing = half_width * de_hw_ratio."""
+        s = self._settings
+        de = np.real(s["half_width"]) * s["de_hw_ratio"]
+        return self._line(np.arange(s["energy_min"], s["energy_max"] + de, de))
+
+    def _contourConstL(self):
+        """contour.py:321-349: line at constant half width, nr_points equally spaced."""
+        s = self._settings
+        return self._line(np.linspace(s["energy_min"], s["energy_max"], s["nr_points"]))
+
+
+def patch_namelist(text, **values):
+    """Return the pnfam namelist `text` with `key = value` replaced for every keyword (the keys pnfamRun overrides per
+    task, pynfam/fortran/pnfam_run.py:208-270)."""
+    for k, v in values.items():
+        if isinstance(v, str):
+            rep = "'%s'" % v
+        elif isinstance(v, bool):
+            rep = ".true." if v else ".false."
+        elif isinstance(v, float):
+            rep = repr(v)
+        else:
+            rep = str(v)
+        text, n = re.subn(r"(?im)^(\s*%s\s*=\s*)[^\n,/]*" % re.escape(k), lambda m: m.group(1) + rep, text)
+        if n == 0:
+            raise KeyError("namelist has no key %r" % k)
+    return text
+
+
+class _FortranRecords(object):
+    """Sequential unformatted records with 4-byte markers (what gfortran and scipy.io.FortranFile write)."""
+
+    def __init__(self, path, mode):
+        self.f = open(path, mode + "b")
+
+    def write_record(self, *arrays):
+        payload = b"".join(np.ascontiguousarray(a).tobytes() for a in arrays)
+        m = struct.pack("<i", len(payload))
+        self.f.write(m + payload + m)
+
+    def read_record(self, dtype):
+        head = self.f.read(4)
+        if len(head) != 4:
+            raise IOError("end of file")
+        (n,) = struct.unpack("<i", head)
+        data = self.f.read(n)
+        (n2,) = struct.unpack("<i", self.f.read(4))
+        if n2 != n:
+            raise IOError("record markers disagree")
+        return np.frombuffer(data, dtype=dtype).copy()
+
+    def close(self):
+        self.f.close()
+
+
+def convString(conv_list):
+    """pynfam/utilities/hfb_utils.py convString: 'Yes' only if every point converged."""
+    return "Yes" if all(c == "Yes" for c in conv_list) else "No"
+
+
+class famStrength(object):
+    """Strength function of one (operator, K) along a contour (pynfam/strength/fam_strength.py:28-92).
+
+    Args:
+        operator (str): operator name with the beta type, e.g. 'GT-' (pnfam namelist's operator_name).
+        k (int): K projection.
+        contour (famContour, str): contour, or a contour type name for the defaults.
+        nucleus (tuple): (N, Z, A) of the parent (the reference takes it from the hfbthoRun object).
+    """
+
+    def __init__(self, operator, k, contour, nucleus=None):
+        self.op, self.k = operator, k
+        self.nucleus = nucleus
+        self.temperature, self.ft_active = 0.0, False
+        self.contour = famContour(contour) if isinstance(contour, str) else contour
+        self.str_df = None      # DataFrame: Re(Strength), Im(Strength), Re(x1), Im(x1), ...
+        self.meta_df = None     # DataFrame: Time (minutes), Conv ('Yes' / 'No')
+        self._meta = {"Version": "Unknown", "Interaction": "Unknown", "Time": None, "Conv": None}
+        self.stats = None
+
+    file_txt = property(lambda s: "{:}.out".format(s.opname))
+    file_bin = property(lambda s: "{:}.out.ctr".format(s.opname))
+    opname = property(lambda s: "{:}K{:1d}".format(s.op, s.k))
+    bareop = property(lambda s: s.op[:-1])
+    beta = property(lambda s: s.op[-1])
+    genopname = property(lambda s: "{:}_K{:1d}".format(s.bareop, s.k))
+    use_FT_prefactor = property(lambda s: False)
+
+    @property
+    def xterms(self):
+        return None if self.str_df is None else [str(c[3:-1]) for c in self.str_df.columns[2:] if "Re" in c]
+
+    @property
+    def nxterms(self):
+        return None if self.str_df is None else len(self.xterms)
+
+    @property
+    def meta(self):
+        if self.meta_df is not None:
+            self._meta["Conv"] = convString(list(self.meta_df["Conv"].values))
+            self._meta["Time"] = float(np.sum(self.meta_df["Time"].values))
+        return self._meta
+
+    @property
+    def ctr_param_df(self):
+        import pandas as pd
+        df = pd.DataFrame()
+        if self.contour.closed:
+            df["Theta"] = self.contour.theta
+        df["Re(EQRPA)"] = np.real(self.contour.ctr_z)
+        df["Im(EQRPA)"] = np.imag(self.contour.ctr_z)
+        return df
+
+    @property
+    def ctr_integ_df(self):
+        import pandas as pd
+        df = pd.DataFrame()
+        if self.contour.closed:
+            df["GL_Weights"] = self.contour.glwts
+            df["Re(dzdt)"] = np.real(self.contour.ctr_dzdt)
+            df["Im(dzdt)"] = np.imag(self.contour.ctr_dzdt)
+        return df
+
+    @property
+    def cstr_df(self):
+        """One complex column per strength / cross-term (fam_strength.py:166-178)."""
+        if self.str_df is None:
+            return None
+        import pandas as pd
+        out = pd.DataFrame()
+        cols = list(self.str_df.columns)
+        for i in range(0, len(cols), 2):
+            out[cols[i][3:-1]] = self.str_df[cols[i]].values + self.str_df[cols[i + 1]].values * 1j
+        return out
+
+    # ---- the batched replacement of getFamList + task farm + concatFamData -------------------------------------
+    def compute(self, rundir, namelist, ctx=None, device=0, share_nucleus_with=None, **solve_kw):
+        """Solve the operator on contour.ctr_z[:nr_compute] in one batched GPU call and fill str_df / meta_df.
+
+        rundir holds hfbtho_NAMELIST.dat + hfbtho_output.hel (+ .tbc); `namelist` is a pnfam namelist in rundir whose
+        operator_name / operator_k are overridden by this object's (what pnfamRun does per task).  Returns
+        (problem, ctx) so the caller can reuse the device-resident nucleus for the next operator."""
+        from . import gpu, host
+        text = open(os.path.join(rundir, namelist)).read()
+        text = patch_namelist(text, operator_name=self.op, operator_k=int(self.k))
+        name = "%s.b200.in" % self.opname
+        with open(os.path.join(rundir, name), "w") as f:
+            f.write(text)
+        t0 = time.time()
+        prob = host.Problem(rundir, name, share_nucleus_with=share_nucleus_with)
+        if ctx is None:
+            ctx = gpu.Context(prob, device=device)
+        om = np.asarray(self.contour.ctr_z[:self.contour.nr_compute])
+        res = ctx.solve(prob, omegas=om, **solve_kw)
+        wall_min = (time.time() - t0) / 60.0
+        if self.nucleus is None:
+            n, z = prob.iscalar("npr_n"), prob.iscalar("npr_p")
+            self.nucleus = (n, z, n + z)
+        m = re.search(r"(?im)^\s*interaction_name\s*=\s*['\"]([^'\"]*)['\"]", text)
+        self._meta["Interaction"] = m.group(1).strip() if m else "Unknown"
+        self._meta["Version"] = "b200"
+        # per-point share of the batched wall time in proportion to the iterations the point took (minutes)
+        it = np.maximum(res["iters"].astype(float), 1.0)
+        self.concatFamData(res["strength"], res["labels"], ["Yes" if c else "No" for c in res["conv"]],
+                           list(wall_min * it / it.sum()))
+        self.stats = res["stats"]
+        self.iters = res["iters"]
+        return prob, ctx
+
+    def concatFamStr(self, strength, labels):
+        """Computed points -> full-contour DataFrame; a closed contour with nr_compute = (nr_points+1)//2 is completed
+        with S(w*) = S(w)* (fam_strength.py:293-337).  strength: complex [nr_compute, 1 + nxterms]; labels: the row
+        labels of the .dat result table ('Strength', cross-term labels)."""
+        import pandas as pd
+        strength = np.asarray(strength)
+        c = self.contour
+        if strength.shape[0] != c.nr_compute:
+            raise RuntimeError("fam data does not match contour data.")
+        data = {}
+        header_order = []
+        for j, lab in enumerate(labels):
+            lab = "Strength" if j == 0 else lab
+            data["Re(%s)" % lab] = strength[:, j].real.copy()
+            data["Im(%s)" % lab] = strength[:, j].imag.copy()
+            header_order += ["Re(%s)" % lab, "Im(%s)" % lab]
+        op_str_df = pd.DataFrame(data)
+        if strength.shape[0] != c.nr_points:
+            endpoints = c.ctr_z[0] == c.ctr_z[-1]
+            sym = op_str_df.iloc[::-1].copy()
+            if c.nr_compute * 2 != c.nr_points:
+                sym.drop(sym.head(1).index, inplace=True)
+            for h in header_order:
+                if "Im" in h:
+                    sym[h] = -sym[h].values
+            if endpoints and c.nr_points != 1:
+                sym.iloc[-1] = op_str_df.iloc[0].values
+            op_str_df = pd.concat([op_str_df, sym], axis=0, ignore_index=True)
+        return op_str_df[header_order]
+
+    def concatFamData(self, strength, labels, conv_list, time_list):
+        import pandas as pd
+        self.str_df = self.concatFamStr(strength, labels)
+        self.meta_df = pd.DataFrame({"Time": time_list, "Conv": conv_list})
+
+    # ---- outputs ------------------------------------------------------------------------------------------------
+    def writeStrengthOut(self, dest="./", fname=None):
+        """OP.out, the text summary pynfam writes and re-reads (fam_strength.py:456-488)."""
+        import pandas as pd
+        if self.str_df is None:
+            raise RuntimeError("Strength dataframe has not been populated. Cannot write to .out")
+        out_df = pd.concat([self.ctr_param_df, self.str_df, self.ctr_integ_df, self.meta_df], axis=1)
+        if fname is None:
+            fname = self.file_txt
+        pd_string = out_df.to_string(header=True, index=True, col_space=3,
+                                     float_format=lambda x: "{:25.16e}".format(x))
+        header = ["# pnFAM code version:   {:}\n".format(self.meta["Version"]),
+                  "# Total run time:       {:<.6f} mins\n".format(self.meta["Time"]),
+                  "# All points converged: {:}\n".format(self.meta["Conv"]),
+                  "# Residual interaction: {:}\n".format(self.meta["Interaction"]),
+                  "# Operator:             {:} with K={:d}\n".format(self.op, self.k),
+                  "# Contour:              {:}\n".format(self.contour.name_and_int),
+                  "# Temperature:          {:<.6f} (Prefactor={:})\n".format(self.temperature, self.use_FT_prefactor),
+                  "#\n"]
+        with open(os.path.join(dest, fname), "w") as f:
+            f.writelines(header)
+            f.write(pd_string + "\n")
+
+    def writeCtrBinary(self, dest="./", fname=None):
+        """OP.out.ctr, version 3 of the Fortran-unformatted contour file read by betadecay.x and shapeFactor
+        (fam_strength.py:491-568): version | Z, A | operator(80) | K, nr_points, nxterms | labels(80 each) | theta |
+        dz/dt | z | strength(nr_points, 1+nxterms) column-major | use_gauleg | GL weights."""
+        if self.str_df is None:
+            raise RuntimeError("Strength dataframe has not been populated. Cannot write to .ctr")
+        if fname is None:
+            fname = self.file_bin
+        i4, f8, c16 = np.int32, np.float64, np.complex128
+        c = self.contour
+        w = _FortranRecords(os.path.join(dest, fname), "w")
+        w.write_record(np.array([3], dtype=i4))
+        w.write_record(np.array([self.nucleus[1], self.nucleus[2]], dtype=i4))
+        pad = lambda s: np.frombuffer(s.encode() + (80 - len(s)) * b" ", dtype="S80")
+        w.write_record(pad(self.bareop))
+        w.write_record(np.array([self.k, c.nr_points, self.nxterms], dtype=i4))
+        if self.nxterms > 0:
+            w.write_record(*[pad(xt) for xt in self.xterms])
+        else:
+            w.write_record(pad(""))
+        w.write_record(np.asarray(c.theta).astype(f8))
+        w.write_record(np.asarray(c.ctr_dzdt).astype(c16))
+        w.write_record(np.asarray(c.ctr_z).astype(c16))
+        w.write_record(np.ascontiguousarray(self.cstr_df.values.T).astype(c16))
+        w.write_record(np.array([int(c.use_gauleg)], dtype=i4))
+        w.write_record(np.asarray(c.glwts).astype(f8))
+        w.close()
+
+    def readCtrBinary(self, src="./", fname=None):
+        """Populate this object from an OP.out.ctr file (fam_strength.py:571-668)."""
+        import pandas as pd
+        if fname is None:
+            fname = self.file_bin
+        path = os.path.join(src, fname)
+        if not os.path.exists(path):
+            raise IOError("Binary file not found.")
+        r = _FortranRecords(path, "r")
+        i4, f8, c16 = np.int32, np.float64, np.complex128
+        version = r.read_record(i4)[0]
+        nucleus = r.read_record(i4)
+        op = r.read_record("S80")[0]
+        k, nr_points, nxterms = r.read_record(i4)
+        raw = r.read_record("S1").tobytes()
+        xterms = [raw[i:i + 80].decode().strip() for i in range(0, len(raw), 80)] if len(raw) >= 80 else []
+        xterms = [x for x in xterms if x]
+        theta = r.read_record(f8)
+        ctr_dzdt = r.read_record(c16)
+        ctr_z = r.read_record(c16)
+        strength = r.read_record(c16).reshape(len(xterms) + 1, len(theta)).T
+        use_gauleg = r.read_record(i4)[0]
+        glwts = r.read_record(f8)
+        r.close()
+        bareop = op.decode().strip()
+        if bareop != self.bareop or k != self.k:
+            raise IOError("File contents do not match requested operator.\nExpected: {:}, {:}, Read: {:}, {:}."
+                          .format(self.bareop, self.k, bareop, k))
+        str_df = pd.DataFrame()
+        for h, col in zip(["Strength"] + xterms, strength.T):
+            str_df["Re({:})".format(h)] = np.real(col)
+            str_df["Im({:})".format(h)] = np.imag(col)
+        closed, quad = self.contour.closed, self.contour.quadrature
+        if np.any(theta != 0.0) and not closed:
+            closed, quad = True, "GAUSS"
+        half_width = None if np.any(np.imag(ctr_z) != np.imag(ctr_z[0])) else np.imag(ctr_z[0])
+        self.contour._ctr_data = dict(nr_points=int(nr_points), nr_compute=(int(nr_points) + 1) // 2 if closed else int(nr_points),
+                                      use_gl_ctr=int(use_gauleg), ctr_z=ctr_z, ctr_dzdt=ctr_dzdt, theta=theta, glwts=glwts,
+                                      half_width=half_width, quad=quad, closed=closed)
+        self.str_df = str_df
+        self.nucleus = (int(nucleus[1] - nucleus[0]), int(nucleus[0]), int(nucleus[1]))
+        self.version = int(version)
+
+
+def run_contours(rundir, namelist, operators, contour, dest=None, device=0, **solve_kw):
+    """All (operator, K) of a nucleus on one contour: the nucleus (HFB reconstruction, basis tables) is set up and
+    uploaded once and shared, each operator is one batched solve, and OP.out / OP.out.ctr are written to `dest`
+    (default rundir) -- what mpi_workflow_fam + famStrength do with nr_compute x len(operators) process launches.
+    operators: iterable of (operator_name, K).  Returns the list of famStrength objects."""
+    dest = rundir if dest is None else dest
+    out, first, ctx = [], None, None
+    for op, k in operators:
+        fs = famStrength(op, k, contour)
+        prob, ctx = fs.compute(rundir, namelist, ctx=ctx, device=device, share_nucleus_with=first, **solve_kw)
+        first = first or prob
+        fs._keep = prob
+        fs.writeStrengthOut(dest)
+        fs.writeCtrBinary(dest)
+        out.append(fs)
+    return out
