@@ -23,12 +23,17 @@ static int digit(int v, int p) {
 
 std::unique_ptr<Problem> Problem::load(const std::string& rundir, const std::string& namelist,
                                        std::shared_ptr<Nucleus> nuc) {
-  auto t0 = std::chrono::steady_clock::now();
-  auto p = std::make_unique<Problem>();
   const std::string d = rundir.empty() ? std::string(".") : rundir;
   std::string nml = namelist;
   if (!nml.empty() && nml[0] != '/') nml = d + "/" + nml;
-  p->in = FamInput::read(nml);
+  return build(rundir, FamInput::read(nml), nuc);
+}
+
+std::unique_ptr<Problem> Problem::build(const std::string& rundir, const FamInput& input, std::shared_ptr<Nucleus> nuc) {
+  auto t0 = std::chrono::steady_clock::now();
+  auto p = std::make_unique<Problem>();
+  const std::string d = rundir.empty() ? std::string(".") : rundir;
+  p->in = input;
   p->nuc = nuc ? nuc : Nucleus::load(d);
   FamBasis& b = p->nuc->basis;
   p->inter = Interaction::build(p->in, b);

@@ -26,6 +26,9 @@ struct Problem {
   double setup_seconds = 0;
   static std::unique_ptr<Problem> load(const std::string& rundir, const std::string& namelist,
                                        std::shared_ptr<Nucleus> nuc = nullptr);
+  // the same from an already parsed (and possibly overridden) namelist -- what the contour driver does per task
+  // (contour_setup.f90:262-275 apply_task_values)
+  static std::unique_ptr<Problem> build(const std::string& rundir, const FamInput& in, std::shared_ptr<Nucleus> nuc = nullptr);
 };
 
 }  // namespace pnfam

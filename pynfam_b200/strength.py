@@ -272,11 +272,11 @@ class famStrength(object):
         """Solve the operator on contour.ctr_z[:nr_compute] in one batched GPU call and fill str_df / meta_df.
 
         rundir holds hfbtho_NAMELIST.dat + hfbtho_output.hel (+ .tbc); `namelist` is a pnfam namelist in rundir whose
-        operator_name / operator_k are overridden by this object's (what pnfamRun does per task).  Returns
+        operator_name / beta_type / operator_k are overridden by this object's (what pnfamRun does per task).  Returns
         (problem, ctx) so the caller can reuse the device-resident nucleus for the next operator."""
         from . import gpu, host
         text = open(os.path.join(rundir, namelist)).read()
-        text = patch_namelist(text, operator_name=self.op, operator_k=int(self.k))
+        text = patch_namelist(text, operator_name=self.bareop, beta_type=self.beta, operator_k=int(self.k))
         name = "%s.b200.in" % self.opname
         with open(os.path.join(rundir, name), "w") as f:
             f.write(text)

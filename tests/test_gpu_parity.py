@@ -247,3 +247,81 @@ def test_drop_in_executable_writes_the_reference_dat_contract(gpu, tmp_path):
     assert refrun.parse_dat(r.stdout)["rows"].keys() == dat["rows"].keys()   # print_stdout = .true.
     for (i, lab, si_g, re_g, im_g), t in zip(pt["trace"], dat["trace"]):
         assert t[0] == i and abs(t[2] - si_g) < 6e-11 and abs(t[3] - re_g) < 6e-11
+
+
+def test_contour_driver_writes_the_reference_strength_files(gpu, tmp_path):
+    """one batched solve per operator -> OP.out + OP.out.ctr in pynfam's formats, checked against the
+    reference's own files for the same nucleus and contour (tests/pynfam_test_S40 and tests/S40_GT_All, 000000/fam_soln)."""
+    import os
+    from conftest import GOLDEN
+    from pynfam_b200.strength import famContour, famStrength, run_contours
+    wd = str(tmp_path)
+    stage_point("S40_SKOP_6sh", "GT-K0", 0, wd)
+    contour = famContour("CIRCLE", {"energy_min": 0.0, "energy_max": 10.476036})
+    res = run_contours(wd, "x.in", [("GT-", 0), ("RS1-", 1)], contour)
+    for fs in res:
+        # GT from tests/pynfam_test_S40, RS1 from tests/S40_GT_All (same HFB solution; the older tree's RS1xP cross-term
+        # predates the current operator definition, DESIGN.md section 6)
+        case = "S40_SKOP_6sh" if fs.bareop == "GT" else "S40_GT_All"
+        soln = os.path.join(GOLDEN, case, "fam_soln")
+        assert fs.meta["Conv"] == "Yes"
+        ref = famStrength(fs.op, fs.k, "CIRCLE")
+        ref.readCtrBinary(soln)
+        got = famStrength(fs.op, fs.k, "CIRCLE")
+        got.readCtrBinary(wd)                      # what betadecay / shapeFactor would read back
+        assert got.nucleus == ref.nucleus == (24, 16, 40) and got.contour.nr_points == 60
+        assert np.max(np.abs(got.contour.ctr_z - ref.contour.ctr_z)) < 1e-12
+        a, b = got.cstr_df, ref.cstr_df
+        z = ref.contour.ctr_z
+        pts = load_points(case)[fs.opname]
+        for lab in b.columns:                      # the 2023 fixture holds fewer cross-terms: compare by label
+            assert lab in a.columns
+            for i in range(60):
+                j = i if i < 30 else 59 - i        # computed point this row mirrors
+                loose = abs(z[j].imag) < 0.5 or pts[j]["iters"] >= 25
+                assert _rel(a[lab].values[i], b[lab].values[i]) < (5e-8 if loose else TOL), (fs.opname, lab, i)
+        # the text summary parses the way pynfam re-reads it (strengthOutParser: header lines + whitespace table)
+        lines = open(os.path.join(wd, fs.file_txt)).read().split("\n")
+        assert lines[2] == "# All points converged: Yes" and lines[4] == "# Operator:             %s with K=%d" % (fs.op, fs.k)
+        assert lines[8].split()[:5] == ["Theta", "Re(EQRPA)", "Im(EQRPA)", "Re(Strength)", "Im(Strength)"]
+        row = lines[9 + 7].split()
+        assert int(row[0]) == 7 and abs(float(row[4]) - b["Strength"].values[7].real) < 1e-9
+
+
+def test_contour_executable_against_oracle(gpu, tmp_path):
+    """contour_main.x, STR mode (exes/pnfam/contour_prog.f90 + contour_setup.f90): both 1+ operators on a 3-point line
+    in one launch; the summary files hold what the oracle computes point by point, the per-point .dat files follow the
+    pnfam_main.x contract."""
+    import os
+    import subprocess
+    from conftest import ROOT
+    from oracle import refrun
+    from pynfam_b200.strength import patch_namelist
+    wd = str(tmp_path)
+    exe = os.path.join(ROOT, "pynfam_b200", "bin", "contour_main.x")
+    stage_point("S40_SKOP_6sh", "GT-K0", 10, wd, name="pnfam_NAMELIST.dat")
+    open(os.path.join(wd, "pnfam_CONTOUR.dat"), "w").write(
+        "&ctr_general\n fam_mode = 'STR'\n fam_input_filename = 'pnfam_NAMELIST.dat'\n/\n"
+        "&ctr_extfield\n operator_groups = '0+', '1+', '0-', '1-', '2-'\n operator_active = 0, 1, 0, 0, 0\n/\n"
+        "&str_parameters\n energy_start = 1.0\n energy_step = 2.5\n nr_points = 3\n half_width = 0.75\n/\n")
+    r = subprocess.run([exe], cwd=wd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stderr.strip() == "", r.stdout[-500:]
+    nml = open(os.path.join(wd, "pnfam_NAMELIST.dat")).read()
+    for k in (0, 1):
+        lines = open(os.path.join(wd, "GT-K%d.out" % k)).read().split("\n")
+        assert lines[4] == "# Operator: GT with K = %d" % k and lines[5] == "# Gamma (half-width): .7500"
+        assert lines[7].split()[:4] == ["#", "Conv", "Re(EQRPA)", "Re(Strength)"] and lines[7].startswith("# Conv")
+        rows = [ln.split() for ln in lines[8:] if ln.strip()]
+        assert len(rows) == 3
+        open(os.path.join(wd, "o.in"), "w").write(patch_namelist(nml, operator_k=k))
+        prob = host.Problem(wd, "o.in")
+        model = fo.model_from_problem(prob)
+        for i, row in enumerate(rows):
+            w = complex(1.0 + 2.5 * i, 0.75)
+            assert int(row[0]) == 1 and abs(float(row[1]) - w.real) < 1e-15
+            dat = refrun.parse_dat(open(os.path.join(wd, "GT-K%d_%06d.dat" % (k, i))).read())
+            assert dat["conv"] is True and abs(dat["rows"]["Energy"] - w) < 1e-15
+            s = complex(float(row[2]), float(row[3]))
+            assert _rel(s, dat["rows"]["Strength"]) < 1e-15
+            it, _, st = fo.solver_from_problem(prob, model=model, omega=w).solve(300, 1e-7)
+            assert it == dat["iters"] and _rel(s, st[0]) < TOL, (k, i)

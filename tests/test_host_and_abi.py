@@ -118,3 +118,28 @@ def test_drop_in_exe_without_gpu_reports_failure_the_reference_way(tmp_path):
     assert "no CUDA device" in r.stdout
     assert "Strength" not in refrun.parse_dat(r.stdout)["rows"]
     assert not os.path.isfile(str(tmp_path / "GT-K0.dat"))
+
+
+def test_contour_exe_without_gpu_reports_failure_the_reference_way(tmp_path):
+    """contour_main.x (drop-in for exes/pnfam/contour_prog.f90): namelists parsed, operator list built, and without a
+    CUDA device no summary file appears (no CPU fallback); exit 0 and silent stderr like the reference's `stop`."""
+    import subprocess
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    exe = os.path.join(ROOT, "pynfam_b200", "bin", "contour_main.x")
+    assert os.path.isfile(exe)
+    stage_point("S40_SKOP_6sh", "GT-K0", 10, str(tmp_path), name="pnfam_NAMELIST.dat")
+    (tmp_path / "pnfam_CONTOUR.dat").write_text(
+        "&ctr_general\n fam_mode = 'STR'\n fam_input_filename = 'pnfam_NAMELIST.dat'\n/\n"
+        "&ctr_extfield\n operator_groups = '0+', '1+', '0-', '1-', '2-'\n operator_active = 0, 1, 0, 0, 0\n/\n"
+        "&str_parameters\n energy_start = 0.0\n energy_step = 1.0\n nr_points = 3\n half_width = 0.25\n/\n")
+    r = subprocess.run([exe], cwd=str(tmp_path), capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stderr.strip() == ""
+    assert "no CUDA device" in r.stdout
+    assert not os.path.isfile(str(tmp_path / "GT-K0.out"))
+    r = subprocess.run([exe, "a", "b"], cwd=str(tmp_path), capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "More than one command-line argument" in r.stdout
+    (tmp_path / "bad.dat").write_text("&ctr_general\n fam_mode = 'FINDMAX'\n/\n")
+    r = subprocess.run([exe, "bad.dat"], cwd=str(tmp_path), capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "not available" in r.stdout

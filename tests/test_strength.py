@@ -1,0 +1,97 @@
+"""Contour geometry and strength assembly (pynfam_b200/strength.py) against the reference's own OP.out / OP.out.ctr
+files (tests/golden/*/fam_soln, copied from tests/pynfam_test_S40 and tests/S40_GT_All by tests/golden/make_strength.py).
+CPU only: the file formats are byte-exact, the contour to round-off of the Gauss-Legendre nodes."""
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from conftest import GOLDEN
+from pynfam_b200.strength import famContour, famStrength, patch_namelist
+
+SOLN = {"GT-": os.path.join(GOLDEN, "S40_SKOP_6sh", "fam_soln"),     # tests/pynfam_test_S40
+        "RS1-": os.path.join(GOLDEN, "S40_GT_All", "fam_soln"),      # tests/S40_GT_All (current cross-term definitions)
+        "PS0-": os.path.join(GOLDEN, "S40_GT_All", "fam_soln")}
+EMAX = 10.476036   # EQRPA_max of the S-40 HFB solution ("CIRCLE on (0.00e+00, 1.05e+01)" in the fixture headers)
+OPS = [("GT-", 0), ("GT-", 1), ("RS1-", 1), ("PS0-", 0)]
+
+
+def _fixture(op, k):
+    fs = famStrength(op, k, "CIRCLE")
+    fs.readCtrBinary(SOLN[op])
+    return fs
+
+
+@pytest.mark.parametrize("op,k", OPS)
+def test_circle_contour_matches_the_reference_files(op, k):
+    ref = _fixture(op, k).contour
+    c = famContour("CIRCLE", {"energy_min": 0.0, "energy_max": EMAX})
+    assert c.nr_points == 60 and c.nr_compute == 30 and c.closed and c.use_gauleg
+    for name in ("theta", "ctr_z", "ctr_dzdt", "glwts"):
+        a, b = getattr(c, name), getattr(ref, name)
+        assert np.max(np.abs(a - b)) < 1e-12 * max(1.0, np.max(np.abs(b))), name
+    assert abs(np.sum(c.glwts) - 2 * np.pi) < 1e-12
+
+
+@pytest.mark.parametrize("op,k", OPS)
+def test_ctr_binary_round_trip_is_byte_exact(op, k, tmp_path):
+    fs = _fixture(op, k)
+    assert fs.nucleus == (24, 16, 40) and fs.version == 3
+    fs.writeCtrBinary(str(tmp_path))
+    name = fs.file_bin
+    assert open(os.path.join(str(tmp_path), name), "rb").read() == open(os.path.join(SOLN[op], name), "rb").read()
+
+
+@pytest.mark.parametrize("op,k", OPS)
+def test_strength_out_text_is_byte_exact(op, k, tmp_path):
+    """Feed the reference's numbers through concatFamData (computed half only) + writeStrengthOut."""
+    fs = _fixture(op, k)
+    lines = open(os.path.join(SOLN[op], fs.file_txt)).read().split("\n")
+    rows = [ln.split() for ln in lines[9:] if ln.strip()][:30]
+    full = fs.cstr_df.values
+    fresh = famStrength(op, k, famContour("CIRCLE", {"energy_min": 0.0, "energy_max": EMAX}), nucleus=(24, 16, 40))
+    fresh.contour._ctr_data = fs.contour._ctr_data     # the file's own nodes (numpy-version round-off of leggauss)
+    fresh.concatFamData(full[:30], ["Strength"] + fs.xterms, [r[-1] for r in rows], [float(r[-2]) for r in rows])
+    fresh._meta["Version"], fresh._meta["Interaction"] = "2.00", "SKOP"
+    # the symmetric completion S(w*) = S(w)* reproduces the stored upper half exactly
+    assert np.array_equal(fresh.cstr_df.values, full)
+    fresh.writeStrengthOut(str(tmp_path))
+    assert open(os.path.join(str(tmp_path), fs.file_txt)).read() == open(os.path.join(SOLN[op], fs.file_txt)).read()
+
+
+def test_line_contours_and_settings():
+    c = famContour("CONSTL", {"energy_min": 0.0, "energy_max": 3.0, "nr_points": 4, "half_width": 0.25})
+    assert np.allclose(c.ctr_z, np.array([0, 1, 2, 3]) + 0.25j) and not c.closed and c.nr_compute == 4
+    assert np.all(c.ctr_dzdt == 1) and np.all(c.theta == 0) and c.half_width == 0.25
+    c = famContour("CONSTR", {"energy_min": 0.0, "energy_max": 1.0, "half_width": 0.5})
+    assert np.allclose(c.ctr_z, np.array([0, 0.5, 1.0]) + 0.5j)
+    with pytest.raises(KeyError):
+        famContour("CIRCLE", {"no_such_key": 1})
+    with pytest.raises(ValueError):
+        famContour("FERMIA")
+    c = famContour("CIRCLE", {"energy_min": 0.0, "energy_max": 10.0, "shift_imag": 0.1})
+    assert c.nr_compute == 60
+    c = famContour("CIRCLE", {"energy_min": 0.0, "energy_max": 80.0, "nr_points": 9, "use_gauleg_ctr": False})
+    assert c.nr_compute == 5 and abs(c.ctr_z[2].imag) <= 30 + 1e-12     # ellipse capped at max_height
+    c.setHfbInterval({"E_gs": 1.2, "EQRPA_max": 7.0}, "-")
+    assert (c.energy_min, c.energy_max) == (0.0, 7.0)
+
+
+def test_odd_point_count_symmetry_fill():
+    c = famContour("CIRCLE", {"energy_min": 0.0, "energy_max": 4.0, "nr_points": 7})
+    assert c.nr_compute == 4
+    fs = famStrength("GT-", 0, c, nucleus=(24, 16, 40))
+    s = (np.arange(4) + 1.0)[:, None] * np.array([[1 + 2j, 3 - 1j]])
+    df = fs.concatFamStr(s, ["Strength", "GTxX"])
+    assert list(df.columns) == ["Re(Strength)", "Im(Strength)", "Re(GTxX)", "Im(GTxX)"] and len(df) == 7
+    assert np.array_equal(df["Re(Strength)"].values, [1, 2, 3, 4, 3, 2, 1])
+    assert np.array_equal(df["Im(Strength)"].values, [2, 4, 6, 8, -6, -4, -2])
+
+
+def test_patch_namelist():
+    t = "&ext_field\n    beta_type = '-'\n    operator_name = 'GT'\n    operator_k = 0\n/\n"
+    u = patch_namelist(t, operator_name="RS1", operator_k=1)
+    assert "operator_name = 'RS1'" in u and "operator_k = 1" in u and "beta_type = '-'" in u
+    with pytest.raises(KeyError):
+        patch_namelist(t, nonexistent=1)
