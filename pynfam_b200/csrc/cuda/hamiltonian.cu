@@ -675,10 +675,10 @@ __global__ void __launch_bounds__(128) fields_kernel(HamArgs g) {
   pfv[0][1] = cp * rb - csp * sbz;                   // |a>=+, |b>=-
   pfv[1][1] = csp * (-sbr + mul_mi(sbp));            // |a>=-, |b>=-
   if (g.sf.enabled) {
-    // sum-factorised projection: one linear copy per (il, sa, sb):  mf[il][sa][sb][pair(ta,tb)][ih][c],  pf[il][sa][sb][ih][c]
+    // sum-factorised projection: one linear copy per (il, sa, sb):  mf[il][sa][sb][pair(ta,tb)][ih][c],  pf[sa][sb][il][ih][c]
     const int il = r / g.sf.ngh, ih = r - il * g.sf.ngh, kih = g.sf.kih;
     double* __restrict__ mo = g.mf + ((size_t)za * 2 + q) * sf_mf_elems(g.sf.ngl, kih) + (size_t)il * 4 * SF_MFP * kih * 2 + ih * 2;
-    double* __restrict__ po = g.pf + ((size_t)za * 2 + q) * sf_pf_elems(g.sf.ngl, kih) + (size_t)il * 4 * kih * 2 + ih * 2;
+    double* __restrict__ po = g.pf + ((size_t)za * 2 + q) * sf_pf_elems(g.sf.ngl, kih) + (size_t)il * kih * 2 + ih * 2;
 #pragma unroll
     for (int a = 0; a < 5; a++)
 #pragma unroll
@@ -688,7 +688,8 @@ __global__ void __launch_bounds__(128) fields_kernel(HamArgs g) {
           if (mf_nonzero(a, b))
             *reinterpret_cast<double2*>(mo + ((size_t)s * SF_MFP + mf_pair(a, b)) * kih * 2) = make_double2(mf[a][b][s >> 1][s & 1].re, mf[a][b][s >> 1][s & 1].im);
 #pragma unroll
-    for (int s = 0; s < 4; s++) *reinterpret_cast<double2*>(po + (size_t)s * kih * 2) = make_double2(pfv[s >> 1][s & 1].re, pfv[s >> 1][s & 1].im);
+    for (int s = 0; s < 4; s++)
+      *reinterpret_cast<double2*>(po + (size_t)s * (g.sf.ngl + SF_DIL) * kih * 2) = make_double2(pfv[s >> 1][s & 1].re, pfv[s >> 1][s & 1].im);
     return;
   }
   // tile-major output (kernels.cuh): mf[kt][sa][sb][pair(ta,tb)][rr][c], structurally non-zero pairs only

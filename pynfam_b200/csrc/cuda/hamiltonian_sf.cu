@@ -134,21 +134,31 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sf_density_kernel(HamArgs g, Sf
   if (warp == 15) {
     // ---- operand movement: segment table, z rows of the columns, radial factors of the a rows and of the b columns
     //      for both il, the packed rho image
-    if (lane == 0)
-      for (int k = 0; k < nsteps; k++) {
-        const SfDensStep d = steps[k];
-        const int sg = k % nst;
-        if (k >= nst) mbar_wait(&st_empty[sg], ((k / nst) - 1) & 1);
-        unsigned char* st = smem + L.off_stage[sg];
-        unsigned long long* bar = &st_full[sg];
-        const unsigned ra_b = (unsigned)d.na * 64, rb_b = (unsigned)d.nbc * 64, rho_b = (unsigned)d.na * d.nbc * 16;
-        mbar_expect_tx(bar, SF_SEGTAB * 4 + (unsigned)d.nbc * 4 + ra_b + rb_b + rho_b);
-        bulk_g2s(st + L.st_rho, pk + d.img_off, rho_b, bar);
-        bulk_g2s(st, S.segtab + (size_t)d.seg_a * SF_SEGTAB, SF_SEGTAB * 4, bar);
-        bulk_g2s(st + L.st_zb, S.zrow + d.b_row0, (unsigned)d.nbc * 4, bar);
-        bulk_g2s(st + L.st_ra, S.rgp + ((size_t)ilp * S.dqp_p + d.a_row0) * 8, ra_b, bar);
-        bulk_g2s(st + L.st_rb, S.rgp + ((size_t)ilp * S.dqp_p + d.b_row0) * 8, rb_b, bar);
+    //      The step descriptor of k+1 is fetched while step k is issued, and the five copies of a step are issued by
+    //      five lanes side by side (a bulk copy costs ~100 clk of issue time in its thread).
+    SfDensStep dn = nsteps > 0 ? steps[0] : SfDensStep{};
+    for (int k = 0; k < nsteps; k++) {
+      const SfDensStep d = dn;
+      if (k + 1 < nsteps) dn = steps[k + 1];
+      const int sg = k % nst;
+      if (k >= nst) mbar_wait(&st_empty[sg], ((k / nst) - 1) & 1);
+      unsigned char* st = smem + L.off_stage[sg];
+      unsigned long long* bar = &st_full[sg];
+      const unsigned ra_b = (unsigned)d.na * 64, rb_b = (unsigned)d.nbc * 64, rho_b = (unsigned)d.na * d.nbc * 16;
+      if (lane == 0) mbar_expect_tx(bar, SF_SEGTAB * 4 + (unsigned)d.nbc * 4 + ra_b + rb_b + rho_b);
+      __syncwarp();
+      {
+        // one instruction, per-lane operands: lane j moves operand j
+        const void* src = pk + d.img_off;
+        unsigned char* dst = st + L.st_rho;
+        unsigned bytes = rho_b;
+        if (lane == 1) { src = S.segtab + (size_t)d.seg_a * SF_SEGTAB; dst = st; bytes = SF_SEGTAB * 4; }
+        if (lane == 2) { src = S.zrow + d.b_row0; dst = st + L.st_zb; bytes = (unsigned)d.nbc * 4; }
+        if (lane == 3) { src = S.rgp + ((size_t)ilp * S.dqp_p + d.a_row0) * 8; dst = st + L.st_ra; bytes = ra_b; }
+        if (lane == 4) { src = S.rgp + ((size_t)ilp * S.dqp_p + d.b_row0) * 8; dst = st + L.st_rb; bytes = rb_b; }
+        if (lane < 5) bulk_g2s(dst, src, bytes, bar);
       }
+    }
     return;
   }
 
@@ -352,11 +362,11 @@ struct SfProjLayout {
 
 template <int MODE>
 static SfProjLayout make_proj_layout(const SfDev& S) {
-  constexpr int NS = MODE == 0 ? 5 : 1;
+  constexpr int NS = MODE == 0 ? 5 : SF_DIL;
   SfProjLayout L{};
   auto up = [](int x) { return (x + 127) & ~127; };
   int off = up(3 * S.nzrows * S.zs * 8);
-  L.mf_bytes = (MODE == 0 ? SF_MFP : 1) * S.kih * 16;
+  L.mf_bytes = (MODE == 0 ? SF_MFP : SF_DIL) * S.kih * 16;
   const int na_pad = (S.na_max + 7) & ~7;
   const int g_bytes = std::max(NS * S.kih * 8 * 8, 8 * (na_pad + 1) * 8);    // G slice, reused to transpose the output
   L.p_W = up(g_bytes);
@@ -375,8 +385,9 @@ static SfProjLayout make_proj_layout(const SfDev& S) {
 // MODE 0: mf -> h;  MODE 1: pf -> Delta
 template <int MODE>
 __global__ void __launch_bounds__(SF_THREADS, 1) sf_projection_kernel(HamArgs g, SfProjLayout L, int q) {
-  constexpr int NS = MODE == 0 ? 5 : 1;
-  constexpr int NW = MODE == 0 ? 4 : 1;
+  constexpr int NS = MODE == 0 ? 5 : SF_DIL;   // G slices per iteration: derivative types (h) / Gauss-Laguerre nodes (Delta)
+  constexpr int NW = 4;                        // W planes per iteration: radial factor types (h) / nodes (Delta)
+  static_assert(SF_DIL == 4, "the W / R_a planes of the Delta pass hold four nodes");
   extern __shared__ __align__(128) unsigned char smem[];
   const SfDev& S = g.sf;
   const int ksp = blockIdx.y, za = blockIdx.z;
@@ -402,7 +413,8 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sf_projection_kernel(HamArgs g,
   const int mf_stride = (L.mf_bytes + 127) & ~127;
   // il range of this split
   const int k_per = (S.ngl + S.ksplit - 1) / S.ksplit;
-  const int k0 = ksp * k_per, k1 = min(S.ngl, k0 + k_per), nit = max(0, k1 - k0);
+  const int k0 = ksp * k_per, k1 = min(S.ngl, k0 + k_per);
+  const int nit = MODE == 0 ? max(0, k1 - k0) : (max(0, k1 - k0) + SF_DIL - 1) / SF_DIL;   // Delta: SF_DIL nodes per iteration
 
   for (int i = tid; i < 3 * nzr * zs; i += SF_THREADS) Zs[i] = S.zt[i];
   if (active) {
@@ -414,13 +426,16 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sf_projection_kernel(HamArgs g,
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
-  const double* __restrict__ mfg = (MODE == 0 ? g.mf + ((size_t)za * 2 + q) * sf_mf_elems(S.ngl, kih)
-                                              : g.pf + ((size_t)za * 2 + q) * sf_pf_elems(S.ngl, kih)) +
-                                   (size_t)(t0.sa * 2 + t0.sb) * (L.mf_bytes / 8);
-  auto issue = [&](int i) {   // field tensor of iteration i (il = k0 + i) -> stage i % nst
+  // h: mf[il][sa][sb][pair][ih][c];  Delta: pf[sa][sb][il][ih][c] (SF_DIL consecutive nodes are one linear copy; rows
+  // beyond the split or the grid are read but masked by zero radial factors)
+  const double* __restrict__ mfg =
+      MODE == 0 ? g.mf + ((size_t)za * 2 + q) * sf_mf_elems(S.ngl, kih) + (size_t)(t0.sa * 2 + t0.sb) * (L.mf_bytes / 8)
+                : g.pf + ((size_t)za * 2 + q) * sf_pf_elems(S.ngl, kih) + (size_t)(t0.sa * 2 + t0.sb) * (S.ngl + SF_DIL) * kih * 2;
+  auto issue = [&](int i) {   // field tensor of iteration i -> stage i % nst
     const int sg = i % nst;
     mbar_expect_tx(&full[sg], (unsigned)L.mf_bytes);
-    bulk_g2s(smem + L.off_mf + (size_t)sg * mf_stride, mfg + (size_t)(k0 + i) * 4 * (L.mf_bytes / 8), (unsigned)L.mf_bytes, &full[sg]);
+    const double* src = MODE == 0 ? mfg + (size_t)(k0 + i) * 4 * (L.mf_bytes / 8) : mfg + (size_t)(k0 + i * SF_DIL) * kih * 2;
+    bulk_g2s(smem + L.off_mf + (size_t)sg * mf_stride, src, (unsigned)L.mf_bytes, &full[sg]);
   };
   if (tid == 0)
     for (int i = 0; i < dist && i < nit; i++) issue(i);
@@ -441,19 +456,38 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sf_projection_kernel(HamArgs g,
   // radial factors of iteration 0: R_b of this lane's column (registers), R_a of the rows (3 double2 per lane of the pair)
   double rb[4] = {0.0, 0.0, 0.0, 0.0};
   double2 ra[3];
-  auto fetch_r = [&](int il) {
+  auto fetch_r = [&](int i) {   // radial factors of iteration i
     if (!active) return;
-    const double* __restrict__ rrow = S.rg + (size_t)il * S.dqp_p * 4;
+    if (MODE == 0) {
+      const double* __restrict__ rrow = S.rg + (size_t)(k0 + i) * S.dqp_p * 4;
 #pragma unroll
-    for (int j = 0; j < 4; j++) rb[j] = rrow[(size_t)(td.b_row0 + bq) * 4 + j];
-    const double2* __restrict__ ra2 = reinterpret_cast<const double2*>(rrow + (size_t)td.a_row0 * 4);
+      for (int j = 0; j < 4; j++) rb[j] = rrow[(size_t)(td.b_row0 + bq) * 4 + j];
+      const double2* __restrict__ ra2 = reinterpret_cast<const double2*>(rrow + (size_t)td.a_row0 * 4);
 #pragma unroll
-    for (int r = 0; r < 3; r++) {
-      const int idx = l64 + 64 * r;
-      ra[r] = idx < 2 * na ? ra2[idx] : make_double2(0.0, 0.0);
+      for (int r = 0; r < 3; r++) {
+        const int idx = l64 + 64 * r;
+        ra[r] = idx < 2 * na ? ra2[idx] : make_double2(0.0, 0.0);
+      }
+    } else {
+      // R0 of SF_DIL nodes: plane j of rb / of the [na][4] row factors is node k0 + i SF_DIL + j (zero beyond the split)
+      const int il0 = k0 + i * SF_DIL;
+      const size_t ilst = (size_t)S.dqp_p * 4;
+#pragma unroll
+      for (int j = 0; j < 4; j++) rb[j] = il0 + j < k1 ? S.rg[(size_t)(il0 + j) * ilst + (size_t)(td.b_row0 + bq) * 4] : 0.0;
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        const int idx = l64 + 64 * r, a = idx >> 1, j0 = (idx & 1) * 2;
+        double x = 0.0, y = 0.0;
+        if (idx < 2 * na) {
+          const double* __restrict__ ra0 = S.rg + (size_t)(td.a_row0 + a) * 4;
+          if (il0 + j0 < k1) x = ra0[(size_t)(il0 + j0) * ilst];
+          if (il0 + j0 + 1 < k1) y = ra0[(size_t)(il0 + j0 + 1) * ilst];
+        }
+        ra[r] = make_double2(x, y);
+      }
     }
   };
-  if (nit > 0) fetch_r(k0);
+  if (nit > 0) fetch_r(0);
   double hacc[SF_HACC];
 #pragma unroll
   for (int i = 0; i < SF_HACC; i++) hacc[i] = 0.0;
@@ -483,8 +517,9 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sf_projection_kernel(HamArgs g,
           for (int t = 0; t < NS; t++) {
             double gr = 0.0, gi = 0.0;
             if (MODE == 1) {
-              const double2 v = mfs[ihg];
-              gr = v.x * ph[0]; gi = v.y * ph[0];
+              const double2 v = mfs[t * kih + ihg];
+              const double f = z0 * rb[t];
+              gr = v.x * f; gi = v.y * f;
             } else {
 #pragma unroll
               for (int t2 = 0; t2 < NS; t2++)
@@ -521,7 +556,13 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sf_projection_kernel(HamArgs g,
           const double* __restrict__ gk = gp + (size_t)ks * 32;
           const double g0 = gk[0];
           dmma884(C[0][0], C[0][1], a0, g0);
-          if (MODE == 0) {
+          if (MODE == 1) {
+            const size_t gt = (size_t)kih * 8;
+            const double g1 = gk[gt], g2 = gk[2 * gt], g3 = gk[3 * gt];
+            dmma884(C[1][0], C[1][1], a0, g1);
+            dmma884(C[2][0], C[2][1], a0, g2);
+            dmma884(C[3][0], C[3][1], a0, g3);
+          } else {
             const double a1 = A0[(size_t)nzr * zs + ks * 4], a2 = A0[(size_t)2 * nzr * zs + ks * 4];
             const size_t gt = (size_t)kih * 8;
             const double g1 = gk[gt], g2 = gk[2 * gt], g3 = gk[3 * gt], g4 = gk[4 * gt];
@@ -533,17 +574,14 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sf_projection_kernel(HamArgs g,
           }
         }
         double* __restrict__ wp = W + ((size_t)(h * 4) * 8 + lr) * 8 + 2 * lc;
-        if (MODE == 0) {
-          *reinterpret_cast<double2*>(wp) = make_double2(C[0][0] + C[4][0] + C[5][0], C[0][1] + C[4][1] + C[5][1]);
-          *reinterpret_cast<double2*>(wp + 64) = make_double2(C[1][0], C[1][1]);
-          *reinterpret_cast<double2*>(wp + 128) = make_double2(C[2][0], C[2][1]);
-          *reinterpret_cast<double2*>(wp + 192) = make_double2(C[3][0], C[3][1]);
-        } else {
-          *reinterpret_cast<double2*>(wp) = make_double2(C[0][0], C[0][1]);
-        }
+        if (MODE == 0) *reinterpret_cast<double2*>(wp) = make_double2(C[0][0] + C[4][0] + C[5][0], C[0][1] + C[4][1] + C[5][1]);
+        else *reinterpret_cast<double2*>(wp) = make_double2(C[0][0], C[0][1]);
+        *reinterpret_cast<double2*>(wp + 64) = make_double2(C[1][0], C[1][1]);
+        *reinterpret_cast<double2*>(wp + 128) = make_double2(C[2][0], C[2][1]);
+        *reinterpret_cast<double2*>(wp + 192) = make_double2(C[3][0], C[3][1]);
       }
       // next il's radial factors: issued here, consumed one iteration later
-      if (it + 1 < nit) fetch_r(k0 + it + 1);
+      if (it + 1 < nit) fetch_r(it + 1);
       named_bar_sync(1 + pr, 64);
       // ---- phase C: h[a][(b,c)] += sum_w R^w_a(il) W^w[slot(a)][(b,c)]
       {

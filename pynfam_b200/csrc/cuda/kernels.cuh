@@ -118,7 +118,9 @@ struct SfDev {
   int ksplit = 1;
 };
 __host__ __device__ inline size_t sf_mf_elems(int ngl, int kih) { return (size_t)ngl * 4 * SF_MFP * kih * 2; }
-__host__ __device__ inline size_t sf_pf_elems(int ngl, int kih) { return (size_t)ngl * 4 * kih * 2; }
+constexpr int SF_DIL = 4;       // Gauss-Laguerre nodes per iteration of the Delta projection (their work is a quarter of h's)
+// pf[sa][sb][il][ih][c] with SF_DIL rows of zero padding per (sa, sb): SF_DIL consecutive nodes are one linear copy
+__host__ __device__ inline size_t sf_pf_elems(int ngl, int kih) { return (size_t)4 * (ngl + SF_DIL) * kih * 2; }
 
 struct HamArgs {
   DevBasis basis;
