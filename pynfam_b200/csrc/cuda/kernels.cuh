@@ -7,8 +7,9 @@ namespace pnfam {
 // ---- (a)/(d) transforms ---------------------------------------------------------------------------
 struct DevicePlan {
   const DevTask* tasks = nullptr;
-  const void* entries = nullptr;  // Phase1Entry[nentries]
-  int ntasks = 0, nentries = 0, max_dim = 0;
+  const int4* tiles1 = nullptr;   // phase 1: (task, term, first row, first column) of every non-empty 32x32 tile
+  const int4* tiles2 = nullptr;   // phase 2: (task, 0, first row, first column)
+  int ntasks = 0, ntiles1 = 0, ntiles2 = 0, max_dim = 0;
   size_t scratch_elems = 0;       // doubles of scratch per (point, re/im)
 };
 

@@ -310,7 +310,7 @@ namespace {
 struct OperatorDev {
   OperatorPlan plan;
   DBuf<DevTask> fwd_tasks, bwd_tasks;
-  DBuf<int2> fwd_entries, bwd_entries;
+  DBuf<int4> fwd_tiles1, fwd_tiles2, bwd_tiles1, bwd_tiles2;
   DevicePlan fwd, bwd;
   DevStructBuf sp[4], hsp[4];
   DBuf<int4> tiles_h, tiles_d;
@@ -404,10 +404,14 @@ size_t upload_density_steps(const pnfam_b200_ctx& c, const BlockStruct& st, DBuf
   return pk;
 }
 
-void flatten(const TransformPlan& tp, DBuf<DevTask>& dt, DBuf<int2>& de, DevicePlan& out) {
+void flatten(const TransformPlan& tp, DBuf<DevTask>& dt, DBuf<int4>& d1, DBuf<int4>& d2, DevicePlan& out) {
   std::vector<DevTask> tasks;
-  std::vector<int2> entries;
+  std::vector<int4> t1, t2;
   int toff = 0, maxd = 0;
+  auto tiles_of = [](std::vector<int4>& v, int task, int term, int m, int n) {
+    for (int i = 0; i < m; i += 32)
+      for (int j = 0; j < n; j += 32) v.push_back(make_int4(task, term, i, j));
+  };
   for (const BlockTask& b : tp.tasks) {
     DevTask d{};
     d.out_quad = b.out_quad; d.out_off = b.out_off; d.m = b.m; d.n = b.n; d.nterms = b.nterms;
@@ -421,12 +425,19 @@ void flatten(const TransformPlan& tp, DBuf<DevTask>& dt, DBuf<int2>& de, DeviceP
       x.alpha_re = s.alpha_re; x.alpha_im = s.alpha_im;
       x.t_off = toff;
       toff += b.m * b.n;
-      entries.push_back(make_int2((int)tasks.size(), t));
+      tiles_of(t1, (int)tasks.size(), t, b.m, b.n);
     }
+    tiles_of(t2, (int)tasks.size(), 0, b.m, b.n);
     tasks.push_back(d);
   }
-  dt.upload(tasks); de.upload(entries);
-  out.tasks = dt.p; out.entries = de.p; out.ntasks = (int)tasks.size(); out.nentries = (int)entries.size();
+  // longest tiles first (inner dimension x filled area), so the tail of a launch is made of short ones
+  auto work1 = [&](const int4& e) { const DevTask& k = tasks[e.x]; return (long)k.m * std::min(32, k.m - e.z) * std::min(32, k.n - e.w); };
+  auto work2 = [&](const int4& e) { const DevTask& k = tasks[e.x]; return (long)k.n * k.nterms * std::min(32, k.m - e.z) * std::min(32, k.n - e.w); };
+  std::stable_sort(t1.begin(), t1.end(), [&](const int4& a, const int4& b) { return work1(a) > work1(b); });
+  std::stable_sort(t2.begin(), t2.end(), [&](const int4& a, const int4& b) { return work2(a) > work2(b); });
+  dt.upload(tasks); d1.upload(t1); d2.upload(t2);
+  out.tasks = dt.p; out.tiles1 = d1.p; out.tiles2 = d2.p; out.ntasks = (int)tasks.size();
+  out.ntiles1 = (int)t1.size(); out.ntiles2 = (int)t2.size();
   out.max_dim = maxd; out.scratch_elems = (size_t)toff;
 }
 
@@ -469,8 +480,8 @@ std::unique_ptr<OperatorDev> make_operator(pnfam_b200_ctx& c, const pnfam_b200_o
   auto od = std::make_unique<OperatorDev>();
   std::vector<int> ir2c(op.f_ir2c, op.f_ir2c + c.nb);
   od->plan = make_operator_plan(c.db, ir2c, c.use_diag, op.beta_minus != 0);
-  flatten(od->plan.forward, od->fwd_tasks, od->fwd_entries, od->fwd);
-  flatten(od->plan.backward, od->bwd_tasks, od->bwd_entries, od->bwd);
+  flatten(od->plan.forward, od->fwd_tasks, od->fwd_tiles1, od->fwd_tiles2, od->fwd);
+  flatten(od->plan.backward, od->bwd_tasks, od->bwd_tiles1, od->bwd_tiles2, od->bwd);
   od->scratch_elems = std::max(od->fwd.scratch_elems, od->bwd.scratch_elems);
   for (int k = 0; k < 4; k++) { od->sp[k].upload(od->plan.sp[k]); od->hsp[k].upload(od->plan.hsp[k]); }
   if (c.sf.enabled) {

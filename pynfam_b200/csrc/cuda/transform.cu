@@ -2,10 +2,10 @@
 //     dRsp = W_a . dRqp . W_b^T       (reference: pnfam_solver.f90:144-150 -> triprod_bbm -> 2 dgemm per block,
 //     dHqp = W_a^T . dHsp . W_b        pnfam_solver.f90:160-166,       pnfam_type_blockmatrix.f90:202-206)
 // executed as two grouped-GEMM launches over the task list built by host/symbolic.cpp:
-//   phase 1:  T_t   = op(A_t) . op(B_t)               one CTA tile per (task term, 32x32 tile, point, re/im)
-//   phase 2:  out   = sum_t alpha_t . T_t . op(C_t)   one CTA tile per (task, 32x32 tile, point, re/im)
-// The inner product runs on the FP64 tensor cores (mma.sync m8n8k4 -> DMMA); operands are read
-// through L1/L2 (the U,V blocks and the amplitudes of all batched points stay L2-resident).
+//   phase 1:  T_t   = op(A_t) . op(B_t)               one CTA per (non-empty 32x32 tile of a task term, point, re/im)
+//   phase 2:  out   = sum_t alpha_t . T_t . op(C_t)   one CTA per (non-empty 32x32 tile of a task, point, re/im)
+// The inner product runs on the FP64 tensor cores (mma.sync m8n8k4 -> DMMA) from operand panels staged in shared
+// memory (the U,V blocks and the amplitudes of all batched points stay L2-resident).
 #include "device_common.cuh"
 #include "kernels.cuh"
 
@@ -17,54 +17,57 @@ __device__ __forceinline__ size_t quad_offset(int layout_pack, int c, int k, siz
   return ((size_t)c * 4 + k) * nxy;  // [re: q0..q3 | im: q0..q3]
 }
 
-// One warp computes a 16x16 sub-tile (2x2 DMMA tiles) of C = A(MxK) * B(KxN) with generic accessors.
-template <class FA, class FB>
-__device__ __forceinline__ void warp_gemm_16x16(double (&acc)[2][2][2], int m0, int n0, int M, int N, int K, FA A, FB B) {
-  const int lane = threadIdx.x & 31;
-  const int lr = lane >> 2, lc = lane & 3;
-  for (int k0 = 0; k0 < K; k0 += 4) {
-    const int k = k0 + lc;
-    double a[2], b[2];
+// Both phases: one CTA (256 threads) per non-empty 32x32 output tile of one point, the host lists the tiles largest
+// first.  Warps 0-3 compute the real flavour, warps 4-7 the imaginary one (a 16x16 sub-tile = 2x2 DMMA tiles each): the
+// operand that does not depend on the flavour (the U/V block) is staged once for both.  The full-K operand panels are
+// staged in shared memory as [k][32 + 4] (zero padded to a multiple of 4 in k, so the DMMA loop has no bounds checks;
+// row stride 36 makes the 8-byte fragment loads bank-conflict free) and every staged element feeds 16 DMMA lanes.
+constexpr int TR_LD = 36;
+
+// panel[k][x] = src(x0 + x, k), x < 32: `xfast` tells which index is contiguous in memory (coalesced global reads).
+// 256 threads; four independent loads per thread are in flight before the first store (the staging is latency bound).
+template <class F>
+__device__ __forceinline__ void stage_panel(double* __restrict__ panel, int K4, int K, int X, int x0, bool xfast, F src) {
+  const int lo = threadIdx.x & 31, hi = threadIdx.x >> 5;
+  if (xfast) {
+    const int x = lo;
+    const bool xin = x0 + x < X;
+    for (int k0 = hi; k0 < K4; k0 += 32) {
+      double v[4];
 #pragma unroll
-    for (int i = 0; i < 2; i++) {
-      const int m = m0 + i * 8 + lr;
-      a[i] = (m < M && k < K) ? A(m, k) : 0.0;
-      const int n = n0 + i * 8 + lr;
-      b[i] = (n < N && k < K) ? B(k, n) : 0.0;
+      for (int u = 0; u < 4; u++) v[u] = (xin && k0 + 8 * u < K) ? src(x0 + x, k0 + 8 * u) : 0.0;
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if (k0 + 8 * u < K4) panel[(k0 + 8 * u) * TR_LD + x] = v[u];
     }
+  } else {
+    for (int k = lo; k < K4; k += 32) {
+      double v[4];
 #pragma unroll
-    for (int i = 0; i < 2; i++)
+      for (int u = 0; u < 4; u++) v[u] = (x0 + hi + 8 * u < X && k < K) ? src(x0 + hi + 8 * u, k) : 0.0;
 #pragma unroll
-      for (int j = 0; j < 2; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+      for (int u = 0; u < 4; u++) panel[k * TR_LD + hi + 8 * u] = v[u];
+    }
   }
 }
 
-struct Phase1Entry {
-  int task, term;
-};
+__device__ __forceinline__ void panel_gemm_16x16(double (&acc)[2][2][2], const double* __restrict__ As, const double* __restrict__ Bs,
+                                                 int K4, int m0, int n0) {
+  const int lane = threadIdx.x & 31, lr = lane >> 2, lc = lane & 3;
+  const double* __restrict__ ap = As + lc * TR_LD + m0 + lr;
+  const double* __restrict__ bp = Bs + lc * TR_LD + n0 + lr;
+#pragma unroll 2
+  for (int k0 = 0; k0 < K4; k0 += 4) {
+    const double a0 = ap[k0 * TR_LD], a1 = ap[k0 * TR_LD + 8], b0 = bp[k0 * TR_LD], b1 = bp[k0 * TR_LD + 8];
+    dmma884(acc[0][0][0], acc[0][0][1], a0, b0);
+    dmma884(acc[0][1][0], acc[0][1][1], a0, b1);
+    dmma884(acc[1][0][0], acc[1][0][1], a1, b0);
+    dmma884(acc[1][1][0], acc[1][1][1], a1, b1);
+  }
+}
 
-__global__ void __launch_bounds__(128) transform_phase1_kernel(const DevTask* __restrict__ tasks, const Phase1Entry* __restrict__ entries,
-                                                              TransformArgs args) {
-  const Phase1Entry e = entries[blockIdx.y];
-  const DevTask& tk = tasks[e.task];
-  const DevTerm& tm = tk.t[e.term];
-  const int M = tk.m, N = tk.n;
-  const int tiles_n = (N + 31) / 32, tiles_m = (M + 31) / 32;
-  if ((int)blockIdx.x >= tiles_m * tiles_n) return;
-  const int z = blockIdx.z, c = z & 1, p = args.active[z >> 1];
-  const int tm0 = (blockIdx.x / tiles_n) * 32, tn0 = (blockIdx.x % tiles_n) * 32;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = tm0 + (warp >> 1) * 16, n0 = tn0 + (warp & 1) * 16;
-  const double* __restrict__ Am = args.W[tm.a_mat] + tm.a_off;
-  const double* __restrict__ Bm = args.in + (size_t)p * args.in_pstride + quad_offset(args.in_pack, c, tm.b_quad, args.nxy) + tm.b_off;
-  double acc[2][2][2] = {};
-  const int at = tm.a_trans, bt = tm.b_trans;
-  warp_gemm_16x16(
-      acc, m0, n0, M, N, M,
-      [&](int i, int k) { return at ? Am[k + (size_t)i * M] : Am[i + (size_t)k * M]; },
-      [&](int k, int j) { return bt ? Bm[j + (size_t)k * N] : Bm[k + (size_t)j * M]; });
-  double* __restrict__ T = args.scratch + ((size_t)(z >> 1) * 2 + c) * args.scratch_stride + tm.t_off;
-  const int lr = lane >> 2, lc = lane & 3;
+__device__ __forceinline__ void store_tile(double* __restrict__ O, const double (&v)[2][2][2], int M, int N, int m0, int n0) {
+  const int lane = threadIdx.x & 31, lr = lane >> 2, lc = lane & 3;
 #pragma unroll
   for (int i = 0; i < 2; i++)
 #pragma unroll
@@ -72,57 +75,92 @@ __global__ void __launch_bounds__(128) transform_phase1_kernel(const DevTask* __
 #pragma unroll
       for (int q = 0; q < 2; q++) {
         const int m = m0 + i * 8 + lr, n = n0 + j * 8 + 2 * lc + q;
-        if (m < M && n < N) T[m + (size_t)n * M] = acc[i][j][q];
+        if (m < M && n < N) O[m + (size_t)n * M] = v[i][j][q];
       }
 }
 
-__global__ void __launch_bounds__(128) transform_phase2_kernel(const DevTask* __restrict__ tasks, TransformArgs args) {
-  const DevTask& tk = tasks[blockIdx.y];
-  const int M = tk.m, N = tk.n;
-  const int tiles_n = (N + 31) / 32, tiles_m = (M + 31) / 32;
-  if ((int)blockIdx.x >= tiles_m * tiles_n) return;
-  const int z = blockIdx.z, c = z & 1, p = args.active[z >> 1];
-  const int tm0 = (blockIdx.x / tiles_n) * 32, tn0 = (blockIdx.x % tiles_n) * 32;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = tm0 + (warp >> 1) * 16, n0 = tn0 + (warp & 1) * 16;
+__global__ void __launch_bounds__(256, 3) transform_phase1_kernel(const DevTask* __restrict__ tasks, const int4* __restrict__ tiles,
+                                                              TransformArgs args, int kpad) {
+  extern __shared__ __align__(16) double tr_smem[];
+  const int4 e = tiles[blockIdx.x];                 // (task, term, first row, first column)
+  const DevTask& tk = tasks[e.x];
+  const DevTerm& tm = tk.t[e.y];
+  const int M = tk.m, N = tk.n, K = M, K4 = (K + 3) & ~3;
+  const int za = blockIdx.y, p = args.active[za];
+  const int tm0 = e.z, tn0 = e.w;
+  const int warp = threadIdx.x >> 5, c = warp >> 2;
+  const int m0 = ((warp >> 1) & 1) * 16, n0 = (warp & 1) * 16;
+  double* As = tr_smem;                              // op(A): shared by both flavours
+  double* Bs = tr_smem + (size_t)(1 + c) * kpad * TR_LD;
+  const double* __restrict__ Am = args.W[tm.a_mat] + tm.a_off;
+  const int at = tm.a_trans, bt = tm.b_trans;
+  stage_panel(As, K4, K, M, tm0, !at, [&](int i, int k) { return at ? Am[k + (size_t)i * M] : Am[i + (size_t)k * M]; });
+#pragma unroll
+  for (int cc = 0; cc < 2; cc++) {
+    const double* __restrict__ Bm = args.in + (size_t)p * args.in_pstride + quad_offset(args.in_pack, cc, tm.b_quad, args.nxy) + tm.b_off;
+    stage_panel(tr_smem + (size_t)(1 + cc) * kpad * TR_LD, K4, K, N, tn0, bt != 0,
+                [&](int j, int k) { return bt ? Bm[j + (size_t)k * N] : Bm[k + (size_t)j * M]; });
+  }
+  __syncthreads();
+  if (tm0 + m0 >= M || tn0 + n0 >= N) return;
+  double acc[2][2][2] = {};
+  panel_gemm_16x16(acc, As, Bs, K4, m0, n0);
+  double* __restrict__ T = args.scratch + ((size_t)za * 2 + c) * args.scratch_stride + tm.t_off;
+  store_tile(T, acc, M, N, tm0 + m0, tn0 + n0);
+}
+
+__global__ void __launch_bounds__(256, 3) transform_phase2_kernel(const DevTask* __restrict__ tasks, const int4* __restrict__ tiles,
+                                                              TransformArgs args, int kpad) {
+  extern __shared__ __align__(16) double tr_smem[];
+  const int4 e = tiles[blockIdx.x];                 // (task, -, first row, first column)
+  const DevTask& tk = tasks[e.x];
+  const int M = tk.m, N = tk.n, K = N, K4 = (K + 3) & ~3;
+  const int za = blockIdx.y, p = args.active[za];
+  const int tm0 = e.z, tn0 = e.w;
+  const int warp = threadIdx.x >> 5, c = warp >> 2;
+  const int m0 = ((warp >> 1) & 1) * 16, n0 = (warp & 1) * 16;
+  double* Cs = tr_smem;                              // op(C): shared by both flavours
+  double* Ts = tr_smem + (size_t)(1 + c) * kpad * TR_LD;
+  const bool live = tm0 + m0 < M && tn0 + n0 < N;
   double out[2][2][2] = {};
   for (int t = 0; t < tk.nterms; t++) {
     const DevTerm& tm = tk.t[t];
-    const double* __restrict__ T = args.scratch + ((size_t)(z >> 1) * 2 + c) * args.scratch_stride + tm.t_off;
     const double* __restrict__ Cm = args.W[tm.c_mat] + tm.c_off;
     const int ct = tm.c_trans;
-    double acc[2][2][2] = {};
-    warp_gemm_16x16(
-        acc, m0, n0, M, N, N, [&](int i, int k) { return T[i + (size_t)k * M]; },
-        [&](int k, int j) { return ct ? Cm[j + (size_t)k * N] : Cm[k + (size_t)j * N]; });
-    const double alpha = c ? tm.alpha_im : tm.alpha_re;
+    if (t > 0) __syncthreads();
+    stage_panel(Cs, K4, K, N, tn0, ct != 0, [&](int j, int k) { return ct ? Cm[j + (size_t)k * N] : Cm[k + (size_t)j * N]; });
 #pragma unroll
-    for (int i = 0; i < 2; i++)
+    for (int cc = 0; cc < 2; cc++) {
+      const double* __restrict__ T = args.scratch + ((size_t)za * 2 + cc) * args.scratch_stride + tm.t_off;
+      stage_panel(tr_smem + (size_t)(1 + cc) * kpad * TR_LD, K4, K, M, tm0, true, [&](int i, int k) { return T[i + (size_t)k * M]; });
+    }
+    __syncthreads();
+    if (live) {
+      double acc[2][2][2] = {};
+      panel_gemm_16x16(acc, Ts, Cs, K4, m0, n0);
+      const double alpha = c ? tm.alpha_im : tm.alpha_re;
 #pragma unroll
-      for (int j = 0; j < 2; j++) {
-        out[i][j][0] += alpha * acc[i][j][0];
-        out[i][j][1] += alpha * acc[i][j][1];
-      }
+      for (int i = 0; i < 8; i++) (&out[0][0][0])[i] += alpha * (&acc[0][0][0])[i];
+    }
   }
+  if (!live) return;
   double* __restrict__ O = args.out + (size_t)p * args.out_pstride + quad_offset(args.out_pack, c, tk.out_quad, args.nxy) + tk.out_off;
-  const int lr = lane >> 2, lc = lane & 3;
-#pragma unroll
-  for (int i = 0; i < 2; i++)
-#pragma unroll
-    for (int j = 0; j < 2; j++)
-#pragma unroll
-      for (int q = 0; q < 2; q++) {
-        const int m = m0 + i * 8 + lr, n = n0 + j * 8 + 2 * lc + q;
-        if (m < M && n < N) O[m + (size_t)n * M] = out[i][j][q];
-      }
+  store_tile(O, out, M, N, tm0 + m0, tn0 + n0);
 }
 
 void launch_transform(const DevicePlan& plan, const TransformArgs& args, int nactive, cudaStream_t stream) {
   if (nactive <= 0) return;
-  const int tiles = ((plan.max_dim + 31) / 32) * ((plan.max_dim + 31) / 32);
-  dim3 g1(tiles, plan.nentries, nactive * 2), g2(tiles, plan.ntasks, nactive * 2);
-  transform_phase1_kernel<<<g1, 128, 0, stream>>>(plan.tasks, reinterpret_cast<const Phase1Entry*>(plan.entries), args);
-  transform_phase2_kernel<<<g2, 128, 0, stream>>>(plan.tasks, args);
+  const int kpad = (plan.max_dim + 3) & ~3;
+  const size_t smem = (size_t)3 * kpad * TR_LD * sizeof(double);
+  static size_t attr = 48 * 1024;
+  if (smem > attr) {
+    PNFAM_CUDA_CHECK(cudaFuncSetAttribute(transform_phase1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PNFAM_CUDA_CHECK(cudaFuncSetAttribute(transform_phase2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  dim3 g1(plan.ntiles1, nactive), g2(plan.ntiles2, nactive);
+  if (plan.ntiles1 > 0) transform_phase1_kernel<<<g1, 256, smem, stream>>>(plan.tasks, plan.tiles1, args, kpad);
+  if (plan.ntiles2 > 0) transform_phase2_kernel<<<g2, 256, smem, stream>>>(plan.tasks, plan.tiles2, args, kpad);
 }
 
 }  // namespace pnfam
