@@ -24,30 +24,32 @@ __device__ __forceinline__ size_t quad_offset(int layout_pack, int c, int k, siz
 // row stride 36 makes the 8-byte fragment loads bank-conflict free) and every staged element feeds 16 DMMA lanes.
 constexpr int TR_LD = 36;
 
-// panel[k][x] = src(x0 + x, k), x < 32: `xfast` tells which index is contiguous in memory (coalesced global reads).
-// 256 threads; four independent loads per thread are in flight before the first store (the staging is latency bound).
+__device__ __forceinline__ void cp_async8(double* dst, const double* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+// panel[k][x] = *src(x0 + x, k), x < 32: `xfast` tells which index is contiguous in memory (coalesced global reads).
+// 256 threads.  Every element is an asynchronous 8-byte copy (zero stored directly outside the block), so all loads of
+// all panels of a CTA are in flight together; the caller waits with cp_async_wait_all() + __syncthreads().
 template <class F>
 __device__ __forceinline__ void stage_panel(double* __restrict__ panel, int K4, int K, int X, int x0, bool xfast, F src) {
   const int lo = threadIdx.x & 31, hi = threadIdx.x >> 5;
   if (xfast) {
     const int x = lo;
     const bool xin = x0 + x < X;
-    for (int k0 = hi; k0 < K4; k0 += 32) {
-      double v[4];
-#pragma unroll
-      for (int u = 0; u < 4; u++) v[u] = (xin && k0 + 8 * u < K) ? src(x0 + x, k0 + 8 * u) : 0.0;
-#pragma unroll
-      for (int u = 0; u < 4; u++)
-        if (k0 + 8 * u < K4) panel[(k0 + 8 * u) * TR_LD + x] = v[u];
+    for (int k = hi; k < K4; k += 8) {
+      if (xin && k < K) cp_async8(&panel[k * TR_LD + x], src(x0 + x, k));
+      else panel[k * TR_LD + x] = 0.0;
     }
   } else {
-    for (int k = lo; k < K4; k += 32) {
-      double v[4];
+    for (int k = lo; k < K4; k += 32)
 #pragma unroll
-      for (int u = 0; u < 4; u++) v[u] = (x0 + hi + 8 * u < X && k < K) ? src(x0 + hi + 8 * u, k) : 0.0;
-#pragma unroll
-      for (int u = 0; u < 4; u++) panel[k * TR_LD + hi + 8 * u] = v[u];
-    }
+      for (int u = 0; u < 4; u++) {
+        const int x = hi + 8 * u;
+        if (x0 + x < X && k < K) cp_async8(&panel[k * TR_LD + x], src(x0 + x, k));
+        else panel[k * TR_LD + x] = 0.0;
+      }
   }
 }
 
@@ -94,13 +96,14 @@ __global__ void __launch_bounds__(256, 3) transform_phase1_kernel(const DevTask*
   double* Bs = tr_smem + (size_t)(1 + c) * kpad * TR_LD;
   const double* __restrict__ Am = args.W[tm.a_mat] + tm.a_off;
   const int at = tm.a_trans, bt = tm.b_trans;
-  stage_panel(As, K4, K, M, tm0, !at, [&](int i, int k) { return at ? Am[k + (size_t)i * M] : Am[i + (size_t)k * M]; });
+  stage_panel(As, K4, K, M, tm0, !at, [&](int i, int k) { return at ? Am + k + (size_t)i * M : Am + i + (size_t)k * M; });
 #pragma unroll
   for (int cc = 0; cc < 2; cc++) {
     const double* __restrict__ Bm = args.in + (size_t)p * args.in_pstride + quad_offset(args.in_pack, cc, tm.b_quad, args.nxy) + tm.b_off;
     stage_panel(tr_smem + (size_t)(1 + cc) * kpad * TR_LD, K4, K, N, tn0, bt != 0,
-                [&](int j, int k) { return bt ? Bm[j + (size_t)k * N] : Bm[k + (size_t)j * M]; });
+                [&](int j, int k) { return bt ? Bm + j + (size_t)k * N : Bm + k + (size_t)j * M; });
   }
+  cp_async_wait_all();
   __syncthreads();
   if (tm0 + m0 >= M || tn0 + n0 >= N) return;
   double acc[2][2][2] = {};
@@ -128,12 +131,13 @@ __global__ void __launch_bounds__(256, 3) transform_phase2_kernel(const DevTask*
     const double* __restrict__ Cm = args.W[tm.c_mat] + tm.c_off;
     const int ct = tm.c_trans;
     if (t > 0) __syncthreads();
-    stage_panel(Cs, K4, K, N, tn0, ct != 0, [&](int j, int k) { return ct ? Cm[j + (size_t)k * N] : Cm[k + (size_t)j * N]; });
+    stage_panel(Cs, K4, K, N, tn0, ct != 0, [&](int j, int k) { return ct ? Cm + j + (size_t)k * N : Cm + k + (size_t)j * N; });
 #pragma unroll
     for (int cc = 0; cc < 2; cc++) {
       const double* __restrict__ T = args.scratch + ((size_t)za * 2 + cc) * args.scratch_stride + tm.t_off;
-      stage_panel(tr_smem + (size_t)(1 + cc) * kpad * TR_LD, K4, K, M, tm0, true, [&](int i, int k) { return T[i + (size_t)k * M]; });
+      stage_panel(tr_smem + (size_t)(1 + cc) * kpad * TR_LD, K4, K, M, tm0, true, [&](int i, int k) { return T + i + (size_t)k * M; });
     }
+    cp_async_wait_all();
     __syncthreads();
     if (live) {
       double acc[2][2][2] = {};
