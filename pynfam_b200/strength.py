@@ -19,6 +19,7 @@ import time
 
 import numpy as np
 
+KAPPA = 6147.0   # pynfam/config.py:225, decay constant [s]
 TMIN = 1e-3   # pynfam/config.py: finite temperature is not supported by this path (fails loudly in the host set-up)
 
 _CONTOUR_DEFAULTS = {
@@ -429,6 +430,44 @@ class famStrength(object):
         self.str_df = str_df
         self.nucleus = (int(nucleus[1] - nucleus[0]), int(nucleus[0]), int(nucleus[1]))
         self.version = int(version)
+
+
+def complex_quadrature(quad, contour, y, xmin=None, xmax=None):
+    """Quadrature of y along the contour: complex contour integral / (2 pi i) on a closed contour, plain integral over
+    Re(z) on an open one (shapeFactor.complex_quadrature, pynfam/strength/shape_factor.py:1161-1197)."""
+    if quad not in ("TRAP", "GAUSS", "SIMPSON"):
+        raise ValueError("Invalid quadrature requested.")
+    y = np.asarray(y)
+    if contour.closed:
+        fac, dzdt, dt = 1.0 / (2.0 * np.pi * 1j), contour.ctr_dzdt, contour.theta
+    else:
+        fac, dzdt, dt = 1.0, 1.0, np.real(contour.ctr_z)
+        xmin = min(dt) if xmin is None else xmin
+        xmax = max(dt) if xmax is None else xmax
+        mask = (dt >= xmin) & (dt <= xmax)
+        dt, y = dt[mask], y[mask]
+    if quad == "GAUSS":
+        if not contour.use_gauleg:
+            raise RuntimeError("Integration points do not lie on a gauss-legendre grid.")
+        return fac * sum((y * dzdt) * contour.glwts)
+    if quad == "TRAP":
+        return fac * np.trapezoid(y * dzdt, dt)
+    from scipy.integrate import simpson
+    return fac * simpson(y * dzdt, x=dt)
+
+
+def beta_rate(contour, weighted_shape_factor, quad=None, emin=None, emax=None):
+    """Rate [1/s] and half-life [s] of one channel from its phase-space weighted shape factor on the contour
+    (shapeFactor.calcBetaRates, shape_factor.py:956-1031): ln2/kappa * Re(contour integral) on a closed contour
+    (the strengths carry -1/pi), ln2/kappa * Im(integral) on an open one."""
+    quad = contour.quadrature if quad is None else quad
+    cint = complex_quadrature(quad, contour, weighted_shape_factor, emin, emax)
+    if contour.closed:
+        rate = np.log(2) / KAPPA * np.imag(-1j * np.pi * cint)
+    else:
+        rate = np.log(2) / KAPPA * np.imag(cint)
+    with np.errstate(divide="ignore"):
+        return rate, np.log(2) / rate
 
 
 def run_contours(rundir, namelist, operators, contour, dest=None, device=0, **solve_kw):

@@ -258,7 +258,7 @@ def test_contour_driver_writes_the_reference_strength_files(gpu, tmp_path):
     wd = str(tmp_path)
     stage_point("S40_SKOP_6sh", "GT-K0", 0, wd)
     contour = famContour("CIRCLE", {"energy_min": 0.0, "energy_max": 10.476036})
-    res = run_contours(wd, "x.in", [("GT-", 0), ("RS1-", 1)], contour)
+    res = run_contours(wd, "x.in", [("GT-", 0), ("GT-", 1), ("RS1-", 1)], contour)
     for fs in res:
         # GT from tests/pynfam_test_S40, RS1 from tests/S40_GT_All (same HFB solution; the older tree's RS1xP cross-term
         # predates the current operator definition)
@@ -280,6 +280,18 @@ def test_contour_driver_writes_the_reference_strength_files(gpu, tmp_path):
                 j = i if i < 30 else 59 - i        # computed point this row mirrors
                 loose = abs(z[j].imag) < 0.5 or pts[j]["iters"] >= 25
                 assert _rel(a[lab].values[i], b[lab].values[i]) < (5e-8 if loose else TOL), (fs.opname, lab, i)
+        if fs.bareop == "GT":
+            # integrated beta-decay rate of the allowed channel (north-star: 1e-9 relative): the reference's own
+            # phase-space weights at the contour points (its shape factor / its strength, tests/golden/make_beta.py)
+            # applied to OUR strengths, integrated the way shapeFactor.calcBetaRates does, against its beta.out
+            from pynfam_b200.strength import beta_rate
+            from test_strength import beta_fixture
+            sf, rates, _ = beta_fixture()
+            col = "Allowed-GT_K=%d" % fs.k
+            w = sf[col] / b["Strength"].values
+            rate, _ = beta_rate(got.contour, w * a["Strength"].values)
+            print("rate", col, rate, rates[col], abs(rate - rates[col]) / rates[col])
+            assert abs(rate - rates[col]) < TOL * rates[col], (col, rate, rates[col])
         # the text summary parses the way pynfam re-reads it (strengthOutParser: header lines + whitespace table)
         lines = open(os.path.join(wd, fs.file_txt)).read().split("\n")
         assert lines[2] == "# All points converged: Yes" and lines[4] == "# Operator:             %s with K=%d" % (fs.op, fs.k)

@@ -8,7 +8,7 @@ import pandas as pd
 import pytest
 
 from conftest import GOLDEN
-from pynfam_b200.strength import famContour, famStrength, patch_namelist
+from pynfam_b200.strength import beta_rate, complex_quadrature, famContour, famStrength, patch_namelist
 
 SOLN = {"GT-": os.path.join(GOLDEN, "S40_SKOP_6sh", "fam_soln"),     # tests/pynfam_test_S40
         "RS1-": os.path.join(GOLDEN, "S40_GT_All", "fam_soln"),      # tests/S40_GT_All (current cross-term definitions)
@@ -95,3 +95,26 @@ def test_patch_namelist():
     assert "operator_name = 'RS1'" in u and "operator_k = 1" in u and "beta_type = '-'" in u
     with pytest.raises(KeyError):
         patch_namelist(t, nonexistent=1)
+
+
+def beta_fixture():
+    import json
+    d = json.load(open(os.path.join(GOLDEN, "S40_SKOP_6sh", "beta_soln.json")))
+    sf = {c: np.array(v["re"], float) + 1j * np.array(v["im"], float) for c, v in d["shape_factor"].items()}
+    return sf, {c: float(v["rate"]) for c, v in d["rates"].items()}, {c: float(v["halflife"]) for c, v in d["rates"].items()}
+
+
+@pytest.mark.parametrize("col,op,k", [("Allowed-GT_K=0", "GT-", 0), ("Allowed-GT_K=1", "GT-", 1)])
+def test_integrated_rate_from_the_reference_shape_factor(col, op, k):
+    """beta.out of the reference from its own shape factor columns: pins complex_quadrature / beta_rate; and the shape
+    factor of an allowed channel is a smooth phase-space weight times the FAM strength stored in OP.out.ctr."""
+    sf, rates, half = beta_fixture()
+    fs = _fixture(op, k)
+    rate, hl = beta_rate(fs.contour, sf[col])
+    assert abs(rate - rates[col]) < 1e-13 * rates[col] and abs(hl - half[col]) < 1e-13 * half[col]
+    w = sf[col] / fs.cstr_df["Strength"].values          # the reference's integration weights at the contour points
+    assert np.all(np.isfinite(w)) and np.max(np.abs(w[:30] - np.conj(w[:29:-1]))) < 1e-9 * np.max(np.abs(w))
+    with pytest.raises(ValueError):
+        complex_quadrature("BOOLE", fs.contour, sf[col])
+    line = famContour("CONSTL", {"energy_min": 0.0, "energy_max": 2.0, "nr_points": 5, "half_width": 0.1})
+    assert abs(complex_quadrature("TRAP", line, np.ones(5) * 1j) - 2.0j) < 1e-15
