@@ -26,8 +26,15 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-CASE = os.path.join(ROOT, "tests", "golden", "Gd162_SKOP_16sh")
-WORKLOAD = "Gd162 SkO' 16 shells 40x40 grid, GT- K=0, synthetic CIRCLE contour sweep"
+SHELLS = 16     # --shells 20 switches to tests/golden/Gd162_SKOP_20sh (BASELINE.json configs[3]/[4] basis size)
+
+
+def case_dir():
+    return os.path.join(ROOT, "tests", "golden", "Gd162_SKOP_%dsh" % SHELLS)
+
+
+def workload():
+    return "Gd162 SkO' %d shells 40x40 grid, GT- K=0, synthetic CIRCLE contour sweep" % SHELLS
 
 FAM_NML = """&general
     fam_output_filename = 'GT-K0'
@@ -75,7 +82,7 @@ def circle_contour(npts, emin=0.0, emax=10.0):
 def stage(wd, omega, max_iter):
     os.makedirs(wd, exist_ok=True)
     for f in ("hfbtho_NAMELIST.dat", "hfbtho_output.hel"):
-        shutil.copy(os.path.join(CASE, f), wd)
+        shutil.copy(os.path.join(case_dir(), f), wd)
     with open(os.path.join(wd, "GT-K0.in"), "w") as f:
         f.write(FAM_NML.format(re=repr(float(omega.real)), im=repr(float(omega.imag)), max_iter=max_iter))
 
@@ -183,7 +190,7 @@ def run_reference(args, rank):
         "ms_per_step": 1e3 * (farm[0][2] if ips_farm >= ips_threaded and farm else sum(per_iter) / max(1, args.steps)),
         "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "points_per_gpu": args.points, "shells": 16, "nghl": 1600},
+        "config": {"workload": workload(), "points_per_gpu": args.points, "shells": SHELLS, "nghl": 1600},
         "omega_points_per_s": ips / args.assumed_iters_per_point,
         "cpu_baseline": {"value": ips, "unit": "iterations/s", "cores": cores, "kind": "reference",
                          "sample": mode + "; per-iteration times from pnfam_main.x's own timer",
@@ -201,10 +208,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--points", type=int, default=32, help="omega points per GPU (weak scaling)")
+    ap.add_argument("--shells", type=int, default=16, choices=[16, 20], help="HO shells of the Gd162 basis (fixture)")
     ap.add_argument("--ref-iters", type=int, default=4)
     ap.add_argument("--assumed-iters-per-point", type=float, default=25.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    global SHELLS
+    SHELLS = args.shells
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -302,7 +312,7 @@ def main():
             "metric": "FAM iterations/s (omega-points/s in omega_points_per_s)", "value": value, "unit": "iterations/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * vals[0] / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "points_per_gpu": args.points, "shells": 16, "basis_states": dqp,
+            "config": {"workload": workload(), "points_per_gpu": args.points, "shells": SHELLS, "basis_states": dqp,
                        "nghl": nghl, "nxy": nxy, "eps": 1e-7, "broyden_history": 50,
                        "l2": "per-step working set (Broyden history 2*50*4*nxy*8 B per point = %.1f GB) >> 126 MB L2; "
                              "no flush needed" % (len(mine) * 2 * 50 * 4 * nxy * 8 / 1e9)},
