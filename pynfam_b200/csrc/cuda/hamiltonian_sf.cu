@@ -101,7 +101,10 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 //   warps 12..14  phase T: T^j[il][slot][col] = sum_{a in slot} R^j_a(il) rho[a][col]  (FP64 FMA), double buffered
 //   warps 0..11   DMMA + epilogue of one m-tile (8 grid points) each; with 2 mt = 10 m-tiles the last two are shared
 //                 by two warps (half of the n-tiles each) so that every SM sub-partition carries the same DMMA load
-template <int MODE>
+// TS_, KPAD_, ZS_ (0 = take the run-time value): row stride of T, padded slot count and row stride of the z tables as
+// compile-time constants for the common shapes, so that the fragment addresses of the DMMA loop are immediate offsets
+// (the kernel sits at the 128-register limit and would otherwise recompute them with integer multiplies per load).
+template <int MODE, int TS_, int KPAD_, int ZS_>
 __global__ void __launch_bounds__(SF_THREADS, 1) sf_density_kernel(HamArgs g, SfDensLayout L) {
   constexpr int NJ = MODE == 0 ? 3 : 1;   // radial factor types entering T
   constexpr int NT = MODE == 0 ? 4 : 1;   // derivative types
@@ -116,7 +119,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sf_density_kernel(HamArgs g, Sf
   double* Zs = reinterpret_cast<double*>(smem);                 // [2][nzrows][zs]
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + L.off_bar);
   unsigned long long *st_full = bars, *st_empty = bars + SF_DSTAGES, *t_full = bars + 2 * SF_DSTAGES, *t_empty = bars + 2 * SF_DSTAGES + 2;
-  const int zs = S.zs, nzr = S.nzrows, na_max = S.na_max, nbc_max = S.nbc_max, kpad_max = S.kpad_max, ts = L.ts, nst = L.nst;
+  const int zs = ZS_ ? ZS_ : S.zs, nzr = S.nzrows, kpad_max = KPAD_ ? KPAD_ : S.kpad_max, ts = TS_ ? TS_ : L.ts, nst = L.nst;
   const int il0 = 2 * ilp, il1 = min(il0 + 1, S.ngl - 1);
   // consumer roles
   const int M = 2 * S.mt;                                       // m-tiles of the il pair (<= 12)
@@ -329,15 +332,23 @@ void launch_density_sf(const HamArgs& a, cudaStream_t stream) {
   const SfDensLayout L = make_dens_layout(S);
   static int attr_bytes = 0;
   if (L.total > attr_bytes) {
-    PNFAM_CUDA_CHECK(cudaFuncSetAttribute(sf_density_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-    PNFAM_CUDA_CHECK(cudaFuncSetAttribute(sf_density_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    PNFAM_CUDA_CHECK(cudaFuncSetAttribute(sf_density_kernel<0, 0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    PNFAM_CUDA_CHECK(cudaFuncSetAttribute(sf_density_kernel<1, 0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    PNFAM_CUDA_CHECK(cudaFuncSetAttribute(sf_density_kernel<0, 68, 12, 52>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    PNFAM_CUDA_CHECK(cudaFuncSetAttribute(sf_density_kernel<1, 68, 12, 52>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
     attr_bytes = L.total;
   }
   const int maxsteps = std::max(std::max(S.nsteps[0], S.nsteps[1]), std::max(S.nsteps[2], S.nsteps[3]));
   if (maxsteps > 0) sf_pack_kernel<<<dim3(maxsteps, 4, a.nactive), 256, 0, stream>>>(a);
   const int nilp = (S.ngl + 1) / 2;
-  sf_density_kernel<0><<<dim3(nilp, 2, a.nactive), SF_THREADS, L.total, stream>>>(a, L);
-  sf_density_kernel<1><<<dim3(nilp, 2, a.nactive), SF_THREADS, L.total, stream>>>(a, L);
+  const dim3 grid(nilp, 2, a.nactive);
+  if (L.ts == 68 && S.kpad_max == 12 && S.zs == 52) {          // 40-point Gauss-Hermite grid, up to 22 shells
+    sf_density_kernel<0, 68, 12, 52><<<grid, SF_THREADS, L.total, stream>>>(a, L);
+    sf_density_kernel<1, 68, 12, 52><<<grid, SF_THREADS, L.total, stream>>>(a, L);
+  } else {
+    sf_density_kernel<0, 0, 0, 0><<<grid, SF_THREADS, L.total, stream>>>(a, L);
+    sf_density_kernel<1, 0, 0, 0><<<grid, SF_THREADS, L.total, stream>>>(a, L);
+  }
 }
 
 // ================================================================================================
@@ -383,7 +394,9 @@ static SfProjLayout make_proj_layout(const SfDev& S) {
 }
 
 // MODE 0: mf -> h;  MODE 1: pf -> Delta
-template <int MODE>
+// KIH_, ZS_ (0 = run-time value): padded Gauss-Hermite count and row stride of the z tables as compile-time constants
+// for the common grid (see sf_density_kernel)
+template <int MODE, int KIH_, int ZS_>
 __global__ void __launch_bounds__(SF_THREADS, 1) sf_projection_kernel(HamArgs g, SfProjLayout L, int q) {
   constexpr int NS = MODE == 0 ? 5 : SF_DIL;   // G slices per iteration: derivative types (h) / Gauss-Laguerre nodes (Delta)
   constexpr int NW = 4;                        // W planes per iteration: radial factor types (h) / nodes (Delta)
@@ -395,7 +408,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sf_projection_kernel(HamArgs g,
   const int pr = warp >> 1, h = warp & 1, l64 = h * 32 + lane;       // pair, warp of the pair, lane of the pair
   const SfProjTile td = S.tiles[MODE][q][(size_t)blockIdx.x * SF_PPAIRS + pr];
   const SfProjTile t0 = S.tiles[MODE][q][(size_t)blockIdx.x * SF_PPAIRS];   // carries (sa, sb) of the CTA
-  const int zs = S.zs, nzr = S.nzrows, kih = S.kih;
+  const int zs = ZS_ ? ZS_ : S.zs, nzr = S.nzrows, kih = KIH_ ? KIH_ : S.kih;
   const int na = td.na, nslots = td.nslots;
   const bool active = na > 0;
   double* Zs = reinterpret_cast<double*>(smem);                 // [3][nzrows][zs]
@@ -648,18 +661,26 @@ void launch_projection_sf(const HamArgs& a, cudaStream_t stream) {
   const SfProjLayout L0 = make_proj_layout<0>(S), L1 = make_proj_layout<1>(S);
   static int attr0 = 0, attr1 = 0;
   if (L0.total > attr0) {
-    PNFAM_CUDA_CHECK(cudaFuncSetAttribute(sf_projection_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, L0.total));
+    PNFAM_CUDA_CHECK(cudaFuncSetAttribute(sf_projection_kernel<0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, L0.total));
+    PNFAM_CUDA_CHECK(cudaFuncSetAttribute(sf_projection_kernel<0, 40, 52>, cudaFuncAttributeMaxDynamicSharedMemorySize, L0.total));
     attr0 = L0.total;
   }
   if (L1.total > attr1) {
-    PNFAM_CUDA_CHECK(cudaFuncSetAttribute(sf_projection_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, L1.total));
+    PNFAM_CUDA_CHECK(cudaFuncSetAttribute(sf_projection_kernel<1, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, L1.total));
+    PNFAM_CUDA_CHECK(cudaFuncSetAttribute(sf_projection_kernel<1, 40, 52>, cudaFuncAttributeMaxDynamicSharedMemorySize, L1.total));
     attr1 = L1.total;
   }
+  const bool common = S.kih == 40 && S.zs == 52;               // 40-point Gauss-Hermite grid
   for (int q = 0; q < 2; q++) {
-    if (S.ntiles[0][q] > 0)
-      sf_projection_kernel<0><<<dim3(S.ntiles[0][q] / SF_PPAIRS, S.ksplit, a.nactive), SF_THREADS, L0.total, stream>>>(a, L0, q);
-    if (S.ntiles[1][q] > 0)
-      sf_projection_kernel<1><<<dim3(S.ntiles[1][q] / SF_PPAIRS, S.ksplit, a.nactive), SF_THREADS, L1.total, stream>>>(a, L1, q);
+    const dim3 g0(S.ntiles[0][q] / SF_PPAIRS, S.ksplit, a.nactive), g1(S.ntiles[1][q] / SF_PPAIRS, S.ksplit, a.nactive);
+    if (S.ntiles[0][q] > 0) {
+      if (common) sf_projection_kernel<0, 40, 52><<<g0, SF_THREADS, L0.total, stream>>>(a, L0, q);
+      else sf_projection_kernel<0, 0, 0><<<g0, SF_THREADS, L0.total, stream>>>(a, L0, q);
+    }
+    if (S.ntiles[1][q] > 0) {
+      if (common) sf_projection_kernel<1, 40, 52><<<g1, SF_THREADS, L1.total, stream>>>(a, L1, q);
+      else sf_projection_kernel<1, 0, 0><<<g1, SF_THREADS, L1.total, stream>>>(a, L1, q);
+    }
   }
   dim3 gr((unsigned)((2 * a.nxy + 255) / 256), 4, a.nactive);
   sf_projection_reduce_kernel<<<gr, 256, 0, stream>>>(a, S.ksplit);
