@@ -82,6 +82,8 @@ int pnfam_b200_ctx_create(const pnfam_b200_model* model, int device, pnfam_b200_
 void pnfam_b200_ctx_destroy(pnfam_b200_ctx* ctx);
 /* 1 if the context runs the sum-factorised kernels (separable factors given and accepted), 0 if the general-table ones */
 int pnfam_b200_ctx_separable(const pnfam_b200_ctx* ctx);
+/* Bytes ctx_create copied host -> device (basis tables or their separable factors, U, V, grid couplings). */
+int64_t pnfam_b200_ctx_h2d_bytes(const pnfam_b200_ctx* ctx);
 
 /* External field f (+ cross-term fields g_k sharing f's block structure), single-particle basis,
  * as produced by init_external_field / setup_crossterms (pnfam_extfield.f90:37-108, 882-949). */

@@ -55,11 +55,13 @@ __global__ void __launch_bounds__(256) sf_pack_kernel(HamArgs g) {
 // density
 // ================================================================================================
 constexpr int SF_DSTAGES = 4;   // operand stages of the density kernel (as many as fit, at least 2)
+constexpr int SF_TSTAGES = 2;   // T stages (at most; SfDensLayout::ntst in use): the producers may run this many steps ahead
+                                // of the DMMA warps (measured: 3 T stages + 3 operand stages is 2 % slower than 2 + 4)
 constexpr int SF_DPROD = 3;     // producer warps (phase T)
 constexpr int SF_DCONS = 12;    // consumer warps (DMMA + epilogue)
 struct SfDensLayout {
-  int off_stage[SF_DSTAGES], off_T[2], off_bar, off_x;   // byte offsets in dynamic shared memory
-  int nst;                               // operand stages in use
+  int off_stage[SF_DSTAGES], off_T[SF_TSTAGES], off_bar, off_x;   // byte offsets in dynamic shared memory
+  int nst, ntst;                         // operand stages / T stages in use
   int st_zb, st_ra, st_rb, st_rho;       // inside an operand stage: segtab at 0
   int t_rb, t_zb, t_sz;                  // inside a T stage: T at 0
   int ts;                                // row stride of T (doubles), ts % 16 == 4
@@ -79,14 +81,18 @@ static SfDensLayout make_dens_layout(const SfDev& S) {
   L.t_zb = L.t_rb + S.nbc_max * 64;
   L.t_sz = L.t_zb + S.nbc_max * 4;
   const int tstage = up(L.t_sz + SF_KMAX * 4);
-  int off = up(2 * S.nzrows * S.zs * 8);
-  for (int i = 0; i < 2; i++) { L.off_T[i] = off; off += tstage; }
-  L.off_bar = off; off += 128;
-  L.off_x = off; off += 6 * 8 * 32 * 8;          // exchange buffer of the m-tiles shared by two warps
-  const int room = 227 * 1024 - off;
-  L.nst = std::max(2, std::min(SF_DSTAGES, room / stage));
-  for (int i = 0; i < L.nst; i++) { L.off_stage[i] = off; off += stage; }
-  L.total = off;
+  // SF_TSTAGES T stages when at least three operand stages still fit next to them, else two
+  for (L.ntst = SF_TSTAGES; L.ntst >= 2; L.ntst--) {
+    int off = up(2 * S.nzrows * S.zs * 8);
+    for (int i = 0; i < L.ntst; i++) { L.off_T[i] = off; off += tstage; }
+    L.off_bar = off; off += 128;
+    L.off_x = off; off += 6 * 8 * 32 * 8;          // exchange buffer of the m-tiles shared by two warps
+    const int room = 227 * 1024 - off;
+    L.nst = std::max(2, std::min(SF_DSTAGES, room / stage));
+    for (int i = 0; i < L.nst; i++) { L.off_stage[i] = off; off += stage; }
+    L.total = off;
+    if (L.ntst == 2 || room / stage >= 3) break;
+  }
   return L;
 }
 
@@ -98,7 +104,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // One CTA = two Gauss-Laguerre nodes (il pair) of one (pass, omega); it walks the step list of the pass.
 // Warp roles (no CTA-wide barrier in the loop, hand-over by mbarriers):
 //   warp 15       issues the operand copies of a step (7 linear bulk copies) up to nst steps ahead
-//   warps 12..14  phase T: T^j[il][slot][col] = sum_{a in slot} R^j_a(il) rho[a][col]  (FP64 FMA), double buffered
+//   warps 12..14  phase T: T^j[il][slot][col] = sum_{a in slot} R^j_a(il) rho[a][col]  (FP64 FMA), SF_TSTAGES buffers
 //   warps 0..11   DMMA + epilogue of one m-tile (8 grid points) each; with 2 mt = 10 m-tiles the last two are shared
 //                 by two warps (half of the n-tiles each) so that every SM sub-partition carries the same DMMA load
 // TS_, KPAD_, ZS_ (0 = take the run-time value): row stride of T, padded slot count and row stride of the z tables as
@@ -118,8 +124,8 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sf_density_kernel(HamArgs g, Sf
   const double* __restrict__ pk = S.pk[MODE] + ((size_t)za * 2 + q) * S.pk_stride[MODE];
   double* Zs = reinterpret_cast<double*>(smem);                 // [2][nzrows][zs]
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + L.off_bar);
-  unsigned long long *st_full = bars, *st_empty = bars + SF_DSTAGES, *t_full = bars + 2 * SF_DSTAGES, *t_empty = bars + 2 * SF_DSTAGES + 2;
-  const int zs = ZS_ ? ZS_ : S.zs, nzr = S.nzrows, kpad_max = KPAD_ ? KPAD_ : S.kpad_max, ts = TS_ ? TS_ : L.ts, nst = L.nst;
+  unsigned long long *st_full = bars, *st_empty = bars + SF_DSTAGES, *t_full = bars + 2 * SF_DSTAGES, *t_empty = bars + 2 * SF_DSTAGES + SF_TSTAGES;
+  const int zs = ZS_ ? ZS_ : S.zs, nzr = S.nzrows, kpad_max = KPAD_ ? KPAD_ : S.kpad_max, ts = TS_ ? TS_ : L.ts, nst = L.nst, ntst = L.ntst;
   const int il0 = 2 * ilp, il1 = min(il0 + 1, S.ngl - 1);
   // consumer roles
   const int M = 2 * S.mt;                                       // m-tiles of the il pair (<= 12)
@@ -129,7 +135,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sf_density_kernel(HamArgs g, Sf
   for (int i = tid; i < 2 * nzr * zs; i += SF_THREADS) Zs[i] = S.zt[i];
   if (tid == 0) {
     for (int i = 0; i < SF_DSTAGES; i++) { mbar_init(&st_full[i], 1); mbar_init(&st_empty[i], SF_DPROD); }
-    for (int i = 0; i < 2; i++) { mbar_init(&t_full[i], SF_DPROD); mbar_init(&t_empty[i], ncons); }
+    for (int i = 0; i < SF_TSTAGES; i++) { mbar_init(&t_full[i], SF_DPROD); mbar_init(&t_empty[i], ncons); }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
@@ -175,9 +181,10 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sf_density_kernel(HamArgs g, Sf
       if (k + 1 < nsteps) dn = steps[k + 1];
       const int sg = k % nst;
       mbar_wait(&st_full[sg], (k / nst) & 1);
-      if (k >= 2) mbar_wait(&t_empty[k & 1], ((k >> 1) - 1) & 1);
+      const int tg = k % ntst;
+      if (k >= ntst) mbar_wait(&t_empty[tg], ((k / ntst) - 1) & 1);
       const unsigned char* st = smem + L.off_stage[sg];
-      unsigned char* tst = smem + L.off_T[k & 1];
+      unsigned char* tst = smem + L.off_T[tg];
       const int* __restrict__ segt = reinterpret_cast<const int*>(st);
       const double* __restrict__ Ra = reinterpret_cast<const double*>(st + L.st_ra);      // [a][il][4]
       const double2* __restrict__ rho = reinterpret_cast<const double2*>(st + L.st_rho);  // [a][b] (re, im)
@@ -215,7 +222,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sf_density_kernel(HamArgs g, Sf
       if (ptid < d.nbc) reinterpret_cast<int*>(tst + L.t_zb)[ptid] = reinterpret_cast<const int*>(st + L.st_zb)[ptid];
       if (ptid >= 64 && ptid < 64 + SF_KMAX) reinterpret_cast<int*>(tst + L.t_sz)[ptid - 64] = segt[17 + ptid - 64];
       __syncwarp();
-      if (lane == 0) { mbar_arrive(&t_full[k & 1]); mbar_arrive(&st_empty[sg]); }
+      if (lane == 0) { mbar_arrive(&t_full[tg]); mbar_arrive(&st_empty[sg]); }
     }
     return;
   }
@@ -238,8 +245,9 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sf_density_kernel(HamArgs g, Sf
   for (int k = 0; k < nsteps; k++) {
     const SfDensStep d = dn;
     if (k + 1 < nsteps) dn = steps[k + 1];
-    mbar_wait(&t_full[k & 1], (k >> 1) & 1);
-    const unsigned char* tst = smem + L.off_T[k & 1];
+    const int tg = k % ntst;
+    mbar_wait(&t_full[tg], (k / ntst) & 1);
+    const unsigned char* tst = smem + L.off_T[tg];
     const double* __restrict__ T = reinterpret_cast<const double*>(tst) + (size_t)ilc * 3 * kpad_max * ts;
     const double* __restrict__ Rb = reinterpret_cast<const double*>(tst + L.t_rb) + ilc * 4;   // [b][il][4]
     const int* __restrict__ zb = reinterpret_cast<const int*>(tst + L.t_zb);
@@ -292,7 +300,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sf_density_kernel(HamArgs g, Sf
         for (int t2 = 0; t2 < NT; t2++) { acc[t][t2][0] += C[t][0] * ph[t2]; acc[t][t2][1] += C[t][1] * ph[t2]; }
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(&t_empty[k & 1]);
+    if (lane == 0) mbar_arrive(&t_empty[tg]);
     if (d.flags & 1) {
       // end of the (s, s') sweep: reduce over the 4 lanes of a grid point (and over the two warps of a shared m-tile,
       // fixed order), write, restart

@@ -297,6 +297,11 @@ extern "C" int pnfam_b200_ctx_create(const pnfam_b200_model* m, int device, pnfa
 
 extern "C" int pnfam_b200_ctx_separable(const pnfam_b200_ctx* c) { return c && c->sf.enabled ? 1 : 0; }
 
+extern "C" int64_t pnfam_b200_ctx_h2d_bytes(const pnfam_b200_ctx* c) {
+  if (!c) return 0;
+  return c->table_h2d_bytes + (int64_t)(5 * (size_t)c->nghl + 4 * c->dmat) * 8 + (int64_t)(3 * c->nb + c->nb) * 4;
+}
+
 extern "C" void pnfam_b200_ctx_destroy(pnfam_b200_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);

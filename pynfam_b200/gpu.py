@@ -69,6 +69,8 @@ def lib():
         L.pnfam_b200_ctx_destroy.argtypes = [vp]
         L.pnfam_b200_ctx_destroy.restype = None
         L.pnfam_b200_ctx_separable.argtypes = [vp]
+        L.pnfam_b200_ctx_h2d_bytes.argtypes = [vp]
+        L.pnfam_b200_ctx_h2d_bytes.restype = ctypes.c_int64
         L.pnfam_b200_solve.argtypes = [vp, ctypes.POINTER(Operator), ctypes.POINTER(SolverParams), ctypes.c_int32,
                                        c_double_p, c_double_p, c_double_p, c_int32_p, c_int32_p, c_double_p,
                                        c_double_p, ctypes.POINTER(Stats), cp, ci]
@@ -93,7 +95,7 @@ class Context:
         """separable=False withholds the separable factors of the basis tables: the general-table kernels run."""
         L = lib()
         p = problem
-        self._keep = k = {}
+        self._keep = k = {"problem": problem}    # the model points into the problem's own arrays (no host copies)
         m = Model()
         m.nb, m.dqp, m.nghl = p.iscalar("nb"), p.iscalar("dqp"), p.iscalar("nghl")
         k["db"] = np.ascontiguousarray(p.i32("db"))
@@ -101,7 +103,7 @@ class Context:
         m.db, m.num_spin_up = _ip(k["db"]), _ip(k["nsu"])
         for name in ("wf", "wfdr", "wfdp", "wfdz", "wfd2_all", "wdcori", "crho", "cs", "cpair", "cspair",
                      "Ep", "En", "Up", "Vp", "Un", "Vn"):
-            k[name] = np.ascontiguousarray(p.f64(name))
+            k[name] = p.f64(name, copy=False)
             setattr(m, name, _dp(k[name]))
         for name in ("cdrho", "ctau", "ctj0", "ctj1", "ctj2", "crdj", "cds", "ct", "cj", "cgs", "cf", "csdj"):
             setattr(m, name, p.scalar(name))
@@ -111,7 +113,7 @@ class Context:
         if separable:
             m.ngh, m.ngl, m.sep_nzrows = p.iscalar("ngh"), p.iscalar("ngl"), p.iscalar("sep_nzrows")
             k["sep_zrow"] = np.ascontiguousarray(p.i32("sep_zrow"))
-            k["sep_z"], k["sep_r"] = np.ascontiguousarray(p.f64("sep_z")), np.ascontiguousarray(p.f64("sep_r"))
+            k["sep_z"], k["sep_r"] = p.f64("sep_z", copy=False), p.f64("sep_r", copy=False)
             m.sep_zrow, m.sep_z, m.sep_r = _ip(k["sep_zrow"]), _dp(k["sep_z"]), _dp(k["sep_r"])
         self.nb = m.nb
         self._h = ctypes.c_void_p()
@@ -124,6 +126,11 @@ class Context:
     def separable(self):
         """True when the sum-factorised kernels run (the model carried usable separable factors)."""
         return bool(lib().pnfam_b200_ctx_separable(self._h))
+
+    @property
+    def h2d_bytes(self):
+        """Bytes the context creation copied host -> device."""
+        return int(lib().pnfam_b200_ctx_h2d_bytes(self._h))
 
     def __del__(self):
         if getattr(self, "_h", None):

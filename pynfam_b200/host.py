@@ -72,14 +72,20 @@ class Problem:
     def iscalar(self, name):
         return int(round(self.scalar(name)))
 
-    def f64(self, name):
+    def f64(self, name, copy=True):
+        """Named array; copy=False returns a read-only view of the library's own storage (valid while this Problem
+        is alive) -- what gpu.Context passes straight to the C ABI, as a Fortran caller would pass its module arrays."""
         p = ctypes.POINTER(ctypes.c_double)()
         n = ctypes.c_int64()
         if lib().pnfam_problem_array_f64(self._h, name.encode(), ctypes.byref(p), ctypes.byref(n)) != 0:
             raise KeyError(name)
         if n.value == 0:
             return np.zeros(0)
-        return np.ctypeslib.as_array(p, shape=(n.value,)).copy()
+        a = np.ctypeslib.as_array(p, shape=(n.value,))
+        if copy:
+            return a.copy()
+        a.flags.writeable = False
+        return a
 
     def i32(self, name):
         p = ctypes.POINTER(ctypes.c_int32)()
