@@ -146,11 +146,11 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sf_density_kernel(HamArgs g, Sf
     //      The step descriptor of k+1 is fetched while step k is issued, and the five copies of a step are issued by
     //      five lanes side by side (a bulk copy costs ~100 clk of issue time in its thread).
     SfDensStep dn = nsteps > 0 ? steps[0] : SfDensStep{};
+    int sg = 0, sph = 0;
     for (int k = 0; k < nsteps; k++) {
       const SfDensStep d = dn;
       if (k + 1 < nsteps) dn = steps[k + 1];
-      const int sg = k % nst;
-      if (k >= nst) mbar_wait(&st_empty[sg], ((k / nst) - 1) & 1);
+      if (k >= nst) mbar_wait(&st_empty[sg], sph ^ 1);       // stage sg, ring pass parity sph (no division per step)
       unsigned char* st = smem + L.off_stage[sg];
       unsigned long long* bar = &st_full[sg];
       const unsigned ra_b = (unsigned)d.na * 64, rb_b = (unsigned)d.nbc * 64, rho_b = (unsigned)d.na * d.nbc * 16;
@@ -167,6 +167,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sf_density_kernel(HamArgs g, Sf
         if (lane == 4) { src = S.rgp + ((size_t)ilp * S.dqp_p + d.b_row0) * 8; dst = st + L.st_rb; bytes = rb_b; }
         if (lane < 5) bulk_g2s(dst, src, bytes, bar);
       }
+      if (++sg == nst) { sg = 0; sph ^= 1; }
     }
     return;
   }
@@ -175,14 +176,13 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sf_density_kernel(HamArgs g, Sf
     // ---- phase T (producers); forwards what the consumers need from the operand stage, which is recycled earlier
     const int ptid = tid - SF_DCONS * 32, pw = warp - SF_DCONS;
     constexpr int NP = SF_DPROD * 32;
+    int sg = 0, sph = 0, tg = 0, tph = 0;                   // stage / ring pass parity of the operand and T rings
     SfDensStep dn = nsteps > 0 ? steps[0] : SfDensStep{};
     for (int k = 0; k < nsteps; k++) {
       const SfDensStep d = dn;
       if (k + 1 < nsteps) dn = steps[k + 1];
-      const int sg = k % nst;
-      mbar_wait(&st_full[sg], (k / nst) & 1);
-      const int tg = k % ntst;
-      if (k >= ntst) mbar_wait(&t_empty[tg], ((k / ntst) - 1) & 1);
+      mbar_wait(&st_full[sg], sph);
+      if (k >= ntst) mbar_wait(&t_empty[tg], tph ^ 1);
       const unsigned char* st = smem + L.off_stage[sg];
       unsigned char* tst = smem + L.off_T[tg];
       const int* __restrict__ segt = reinterpret_cast<const int*>(st);
@@ -223,6 +223,8 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sf_density_kernel(HamArgs g, Sf
       if (ptid >= 64 && ptid < 64 + SF_KMAX) reinterpret_cast<int*>(tst + L.t_sz)[ptid - 64] = segt[17 + ptid - 64];
       __syncwarp();
       if (lane == 0) { mbar_arrive(&t_full[tg]); mbar_arrive(&st_empty[sg]); }
+      if (++sg == nst) { sg = 0; sph ^= 1; }
+      if (++tg == ntst) { tg = 0; tph ^= 1; }
     }
     return;
   }
@@ -242,11 +244,11 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sf_density_kernel(HamArgs g, Sf
 #pragma unroll
   for (int i = 0; i < NT * NT * 2; i++) (&acc[0][0][0])[i] = 0.0;
   SfDensStep dn = nsteps > 0 ? steps[0] : SfDensStep{};
+  int tg = 0, tph = 0;
   for (int k = 0; k < nsteps; k++) {
     const SfDensStep d = dn;
     if (k + 1 < nsteps) dn = steps[k + 1];
-    const int tg = k % ntst;
-    mbar_wait(&t_full[tg], (k / ntst) & 1);
+    mbar_wait(&t_full[tg], tph);
     const unsigned char* tst = smem + L.off_T[tg];
     const double* __restrict__ T = reinterpret_cast<const double*>(tst) + (size_t)ilc * 3 * kpad_max * ts;
     const double* __restrict__ Rb = reinterpret_cast<const double*>(tst + L.t_rb) + ilc * 4;   // [b][il][4]
@@ -301,6 +303,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sf_density_kernel(HamArgs g, Sf
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&t_empty[tg]);
+    if (++tg == ntst) { tg = 0; tph ^= 1; }
     if (d.flags & 1) {
       // end of the (s, s') sweep: reduce over the 4 lanes of a grid point (and over the two warps of a shared m-tile,
       // fixed order), write, restart

@@ -53,19 +53,34 @@ __device__ __forceinline__ void stage_panel(double* __restrict__ panel, int K4, 
   }
 }
 
+// MI x NJ DMMA tiles (8 x 8 each) of a warp's 16 x 16 sub-tile: the tiles that lie wholly outside the block are skipped
+template <int MI, int NJ>
+__device__ __forceinline__ void panel_gemm_tiles(double (&acc)[2][2][2], const double* __restrict__ ap, const double* __restrict__ bp, int K4) {
+#pragma unroll 2
+  for (int k0 = 0; k0 < K4; k0 += 4) {
+    double a[2], b[2];
+#pragma unroll
+    for (int i = 0; i < MI; i++) a[i] = ap[k0 * TR_LD + 8 * i];
+#pragma unroll
+    for (int j = 0; j < NJ; j++) b[j] = bp[k0 * TR_LD + 8 * j];
+#pragma unroll
+    for (int i = 0; i < MI; i++)
+#pragma unroll
+      for (int j = 0; j < NJ; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+  }
+}
+
+// mrem / nrem: rows / columns of the block left from the first row / column of the warp's sub-tile (> 0)
 __device__ __forceinline__ void panel_gemm_16x16(double (&acc)[2][2][2], const double* __restrict__ As, const double* __restrict__ Bs,
-                                                 int K4, int m0, int n0) {
+                                                 int K4, int m0, int n0, int mrem, int nrem) {
   const int lane = threadIdx.x & 31, lr = lane >> 2, lc = lane & 3;
   const double* __restrict__ ap = As + lc * TR_LD + m0 + lr;
   const double* __restrict__ bp = Bs + lc * TR_LD + n0 + lr;
-#pragma unroll 2
-  for (int k0 = 0; k0 < K4; k0 += 4) {
-    const double a0 = ap[k0 * TR_LD], a1 = ap[k0 * TR_LD + 8], b0 = bp[k0 * TR_LD], b1 = bp[k0 * TR_LD + 8];
-    dmma884(acc[0][0][0], acc[0][0][1], a0, b0);
-    dmma884(acc[0][1][0], acc[0][1][1], a0, b1);
-    dmma884(acc[1][0][0], acc[1][0][1], a1, b0);
-    dmma884(acc[1][1][0], acc[1][1][1], a1, b1);
-  }
+  const bool m2 = mrem > 8, n2 = nrem > 8;
+  if (m2 && n2) panel_gemm_tiles<2, 2>(acc, ap, bp, K4);
+  else if (m2) panel_gemm_tiles<2, 1>(acc, ap, bp, K4);
+  else if (n2) panel_gemm_tiles<1, 2>(acc, ap, bp, K4);
+  else panel_gemm_tiles<1, 1>(acc, ap, bp, K4);
 }
 
 __device__ __forceinline__ void store_tile(double* __restrict__ O, const double (&v)[2][2][2], int M, int N, int m0, int n0) {
@@ -107,7 +122,7 @@ __global__ void __launch_bounds__(256, 3) transform_phase1_kernel(const DevTask*
   __syncthreads();
   if (tm0 + m0 >= M || tn0 + n0 >= N) return;
   double acc[2][2][2] = {};
-  panel_gemm_16x16(acc, As, Bs, K4, m0, n0);
+  panel_gemm_16x16(acc, As, Bs, K4, m0, n0, M - tm0 - m0, N - tn0 - n0);
   double* __restrict__ T = args.scratch + ((size_t)za * 2 + c) * args.scratch_stride + tm.t_off;
   store_tile(T, acc, M, N, tm0 + m0, tn0 + n0);
 }
@@ -141,7 +156,7 @@ __global__ void __launch_bounds__(256, 3) transform_phase2_kernel(const DevTask*
     __syncthreads();
     if (live) {
       double acc[2][2][2] = {};
-      panel_gemm_16x16(acc, Ts, Cs, K4, m0, n0);
+      panel_gemm_16x16(acc, Ts, Cs, K4, m0, n0, M - tm0 - m0, N - tn0 - n0);
       const double alpha = c ? tm.alpha_im : tm.alpha_re;
 #pragma unroll
       for (int i = 0; i < 8; i++) (&out[0][0][0])[i] += alpha * (&acc[0][0][0])[i];
