@@ -57,8 +57,9 @@ __global__ void __launch_bounds__(256) sf_pack_kernel(HamArgs g) {
 constexpr int SF_DSTAGES = 4;   // operand stages of the density kernel (as many as fit, at least 2)
 constexpr int SF_TSTAGES = 2;   // T stages (at most; SfDensLayout::ntst in use): the producers may run this many steps ahead
                                 // of the DMMA warps (measured: 3 T stages + 3 operand stages is 2 % slower than 2 + 4)
-constexpr int SF_DPROD = 3;     // producer warps (phase T)
-constexpr int SF_DCONS = 12;    // consumer warps (DMMA + epilogue)
+constexpr int SF_DPROD = 3;     // producer warps (phase T) of the rho pass; the kappa pass, whose DMMA work is a quarter, runs
+constexpr int SF_DCONS = 12;    // 5 producer + 10 consumer warps when its m-tiles fit (measured: its consumers waited 31 %
+                                // of their time for T with 3 producers)
 struct SfDensLayout {
   int off_stage[SF_DSTAGES], off_T[SF_TSTAGES], off_bar, off_x;   // byte offsets in dynamic shared memory
   int nst, ntst;                         // operand stages / T stages in use
@@ -129,13 +130,14 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sf_density_kernel(HamArgs g, Sf
   const int il0 = 2 * ilp, il1 = min(il0 + 1, S.ngl - 1);
   // consumer roles
   const int M = 2 * S.mt;                                       // m-tiles of the il pair (<= 12)
-  const int ncons = M >= 6 ? SF_DCONS : 2 * M;
-  const int first_split = M >= 6 ? 2 * M - SF_DCONS : 0;        // m-tiles >= first_split are shared by two warps
+  const int dcons = (MODE == 1 && M >= 6 && M <= 10) ? 10 : SF_DCONS, dprod = 15 - dcons;   // warp roles (warp 15: copies)
+  const int ncons = M >= 6 ? dcons : 2 * M;
+  const int first_split = M >= 6 ? 2 * M - dcons : 0;           // m-tiles >= first_split are shared by two warps
 
   for (int i = tid; i < 2 * nzr * zs; i += SF_THREADS) Zs[i] = S.zt[i];
   if (tid == 0) {
-    for (int i = 0; i < SF_DSTAGES; i++) { mbar_init(&st_full[i], 1); mbar_init(&st_empty[i], SF_DPROD); }
-    for (int i = 0; i < SF_TSTAGES; i++) { mbar_init(&t_full[i], SF_DPROD); mbar_init(&t_empty[i], ncons); }
+    for (int i = 0; i < SF_DSTAGES; i++) { mbar_init(&st_full[i], 1); mbar_init(&st_empty[i], dprod); }
+    for (int i = 0; i < SF_TSTAGES; i++) { mbar_init(&t_full[i], dprod); mbar_init(&t_empty[i], ncons); }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
@@ -172,10 +174,10 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sf_density_kernel(HamArgs g, Sf
     return;
   }
 
-  if (warp >= SF_DCONS) {
+  if (warp >= dcons) {
     // ---- phase T (producers); forwards what the consumers need from the operand stage, which is recycled earlier
-    const int ptid = tid - SF_DCONS * 32, pw = warp - SF_DCONS;
-    constexpr int NP = SF_DPROD * 32;
+    const int ptid = tid - dcons * 32, pw = warp - dcons;
+    const int NP = dprod * 32;
     int sg = 0, sph = 0, tg = 0, tph = 0;                   // stage / ring pass parity of the operand and T rings
     SfDensStep dn = nsteps > 0 ? steps[0] : SfDensStep{};
     for (int k = 0; k < nsteps; k++) {
@@ -192,7 +194,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sf_density_kernel(HamArgs g, Sf
       const int kpad = (d.nslots + 3) & ~3;
       // a lane owns one column b (re, im); a warp owns every third n_z slot: the radial factors are warp-uniform
       if (lane < d.nbc) {
-        for (int slot = pw; slot < kpad; slot += SF_DPROD) {
+        for (int slot = pw; slot < kpad; slot += dprod) {
           int a0 = 0, a1 = 0;
           if (slot < d.nslots) { a0 = segt[slot]; a1 = segt[slot + 1]; }
           double acc[2][NJ][2];

@@ -3,8 +3,9 @@ usage: ncu_hot.py report.ncu-rep kernel_regex [ntop]"""
 import csv, subprocess, sys, collections
 rep, pat = sys.argv[1], sys.argv[2]
 ntop = int(sys.argv[3]) if len(sys.argv) > 3 else 30
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + pat, "--launch-count", "1"],
-                     capture_output=True, text=True).stdout
+# kernel_regex, or "#N" = the N-th profiled launch of the report (1-based)
+sel = ["--kernel-id", ":::" + pat[1:]] if pat.startswith("#") else ["--kernel-name", "regex:" + pat, "--launch-count", "1"]
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + sel, capture_output=True, text=True).stdout
 rs = list(csv.reader(src.splitlines()))
 print(rs[0][1][:100])
 hh = rs[1]
