@@ -285,7 +285,7 @@ def main():
         r2 = c2.solve(prob, omegas=mine)
         torch.cuda.synchronize()
         e2e_s += time.perf_counter() - t0
-        if os.environ.get("PNFAM_BENCH_DEBUG"):
+        if rank == 0:
             print("e2e step %.1f ms (C ABI solve %.1f ms, device loop %.1f ms)" % (1e3 * (time.perf_counter() - t0),
                   1e3 * r2["stats"]["seconds_total"], 1e3 * r2["stats"]["seconds_device"]), file=sys.stderr)
         e2e_iters += r2["stats"]["iterations"]
