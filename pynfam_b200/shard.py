@@ -16,6 +16,32 @@ def partition(omegas, world):
     return [order[r::world] for r in range(world)]
 
 
+def partition_tasks(n_operators, omegas, world):
+    """(operator, omega point) tasks of a full contour run -> per rank a list of (operator index, point indices).
+
+    The flattened operator-major task list is cut into `world` contiguous runs of equal length, so a rank holds whole
+    operators plus at most two partial ones (large batches per solve), and the totals differ by at most one point.
+    Inside an operator the points are listed cost-interleaved (stride permutation of the order by |Im omega|), so
+    every run gets the same mix of cheap and expensive points."""
+    om = np.asarray(omegas, dtype=complex)
+    npts = len(om)
+    order = np.argsort(np.abs(om.imag), kind="stable")
+    stride = max(1, -(-world // max(1, n_operators))) + 1
+    perm = np.concatenate([order[s::stride] for s in range(stride)]) if npts else order
+    total = n_operators * npts
+    out = []
+    for r in range(world):
+        lo, hi = (total * r) // world, (total * (r + 1)) // world
+        tasks = []
+        for o in range(lo // npts if npts else 0, n_operators):
+            a, b = max(lo, o * npts), min(hi, (o + 1) * npts)
+            if a >= b:
+                break
+            tasks.append((o, np.sort(perm[a - o * npts:b - o * npts])))
+        out.append(tasks)
+    return out
+
+
 def gather_strengths(local_idx, local_strength, npoints, dist=None, device=None):
     """All-gather the per-rank results into the original point order.
 

@@ -269,35 +269,51 @@ class famStrength(object):
         return out
 
     # ---- the batched replacement of getFamList + task farm + concatFamData -------------------------------------
-    def compute(self, rundir, namelist, ctx=None, device=0, share_nucleus_with=None, **solve_kw):
-        """Solve the operator on contour.ctr_z[:nr_compute] in one batched GPU call and fill str_df / meta_df.
-
-        rundir holds hfbtho_NAMELIST.dat + hfbtho_output.hel (+ .tbc); `namelist` is a pnfam namelist in rundir whose
-        operator_name / beta_type / operator_k are overridden by this object's (what pnfamRun does per task).  Returns
-        (problem, ctx) so the caller can reuse the device-resident nucleus for the next operator."""
-        from . import gpu, host
+    def setup(self, rundir, namelist, share_nucleus_with=None):
+        """Host set-up of this operator in rundir (what pnfamRun does per task: the namelist's operator_name /
+        beta_type / operator_k are overridden by this object's).  Returns the host.Problem."""
+        from . import host
         text = open(os.path.join(rundir, namelist)).read()
         text = patch_namelist(text, operator_name=self.bareop, beta_type=self.beta, operator_k=int(self.k))
         name = "%s.b200.in" % self.opname
-        with open(os.path.join(rundir, name), "w") as f:
+        tmp = os.path.join(rundir, ".%s.%d.tmp" % (name, os.getpid()))      # several ranks may share the rundir
+        with open(tmp, "w") as f:
             f.write(text)
-        t0 = time.time()
+        os.replace(tmp, os.path.join(rundir, name))
         prob = host.Problem(rundir, name, share_nucleus_with=share_nucleus_with)
-        if ctx is None:
-            ctx = gpu.Context(prob, device=device)
-        om = np.asarray(self.contour.ctr_z[:self.contour.nr_compute])
-        res = ctx.solve(prob, omegas=om, **solve_kw)
-        wall_min = (time.time() - t0) / 60.0
         if self.nucleus is None:
             n, z = prob.iscalar("npr_n"), prob.iscalar("npr_p")
             self.nucleus = (n, z, n + z)
         m = re.search(r"(?im)^\s*interaction_name\s*=\s*['\"]([^'\"]*)['\"]", text)
         self._meta["Interaction"] = m.group(1).strip() if m else "Unknown"
         self._meta["Version"] = "b200"
-        # per-point share of the batched wall time in proportion to the iterations the point took (minutes)
+        return prob
+
+    def solve_points(self, prob, ctx, points=None, **solve_kw):
+        """One batched GPU solve of contour.ctr_z[points] (default: the nr_compute points that are computed).
+        Returns the dict of gpu.Context.solve plus 'minutes' (per-point share of the wall time, by iterations)."""
+        c = self.contour
+        idx = np.arange(c.nr_compute) if points is None else np.asarray(points, dtype=int)
+        t0 = time.time()
+        res = ctx.solve(prob, omegas=np.asarray(c.ctr_z)[idx], **solve_kw)
+        wall_min = (time.time() - t0) / 60.0
         it = np.maximum(res["iters"].astype(float), 1.0)
-        self.concatFamData(res["strength"], res["labels"], ["Yes" if c else "No" for c in res["conv"]],
-                           list(wall_min * it / it.sum()))
+        res["minutes"] = wall_min * it / it.sum()
+        res["points"] = idx
+        return res
+
+    def compute(self, rundir, namelist, ctx=None, device=0, share_nucleus_with=None, **solve_kw):
+        """Solve the operator on contour.ctr_z[:nr_compute] in one batched GPU call and fill str_df / meta_df.
+
+        rundir holds hfbtho_NAMELIST.dat + hfbtho_output.hel (+ .tbc); `namelist` is a pnfam namelist in rundir whose
+        operator_name / beta_type / operator_k are overridden by this object's (what pnfamRun does per task).  Returns
+        (problem, ctx) so the caller can reuse the device-resident nucleus for the next operator."""
+        from . import gpu
+        prob = self.setup(rundir, namelist, share_nucleus_with=share_nucleus_with)
+        if ctx is None:
+            ctx = gpu.Context(prob, device=device)
+        res = self.solve_points(prob, ctx, **solve_kw)
+        self.concatFamData(res["strength"], res["labels"], ["Yes" if c else "No" for c in res["conv"]], list(res["minutes"]))
         self.stats = res["stats"]
         self.iters = res["iters"]
         return prob, ctx
@@ -486,3 +502,65 @@ def run_contours(rundir, namelist, operators, contour, dest=None, device=0, **so
         fs.writeCtrBinary(dest)
         out.append(fs)
     return out
+
+
+def run_contours_sharded(rundir, namelist, operators, contour, dest=None, dist=None, device=0, solve_points=None, **solve_kw):
+    """run_contours over the ranks of a torch.distributed job (one process per GPU): the (operator, contour point) tasks
+    are dealt to the ranks by shard.partition_tasks, every rank sets the nucleus up once and solves its points of each
+    operator as one batch, and the ONLY exchange is one all_reduce of the strengths (disjoint ownership, so a sum is a
+    gather) -- NCCL on GPUs, gloo in the CPU tests.  Rank 0 assembles and writes OP.out / OP.out.ctr for every operator;
+    every rank returns the list of famStrength objects.  `solve_points(fs, prob, ctx, points)` may replace the GPU
+    solve (tests)."""
+    import torch
+    from . import shard
+    dest = rundir if dest is None else dest
+    multi = dist is not None and dist.is_initialized() and dist.get_world_size() > 1
+    rank = dist.get_rank() if multi else 0
+    world = dist.get_world_size() if multi else 1
+    operators = list(operators)
+    nc = contour.nr_compute
+    mine = shard.partition_tasks(len(operators), contour.ctr_z[:nc], world)[rank]
+    # every rank sets up every operator on the host (cheap; gives the labels), the nucleus once
+    fss, probs, first = [], [], None
+    for op, k in operators:
+        fs = famStrength(op, k, contour)
+        prob = fs.setup(rundir, namelist, share_nucleus_with=first)
+        first = first or prob
+        fss.append(fs); probs.append(prob)
+    nstr = max(1 + p.iscalar("nxterms") for p in probs)
+    buf = np.zeros((len(operators), nc, 2 * nstr + 3))          # re | im | conv, iterations, minutes
+    ctx = None
+    for o, idx in mine:
+        if len(idx) == 0:
+            continue
+        if solve_points is not None:
+            res = solve_points(fss[o], probs[o], ctx, idx)
+        else:
+            if ctx is None:
+                from . import gpu
+                ctx = gpu.Context(probs[o], device=device)
+            res = fss[o].solve_points(probs[o], ctx, points=idx, **solve_kw)
+        n1 = res["strength"].shape[1]
+        buf[o, idx, :n1] = res["strength"].real
+        buf[o, idx, nstr:nstr + n1] = res["strength"].imag
+        buf[o, idx, 2 * nstr] = res["conv"]
+        buf[o, idx, 2 * nstr + 1] = res["iters"]
+        buf[o, idx, 2 * nstr + 2] = res["minutes"]
+    if multi:
+        on_gpu = dist.get_backend() == "nccl"
+        t = torch.as_tensor(buf, device=("cuda:%d" % device) if on_gpu else "cpu")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        buf = t.cpu().numpy()
+    for o, fs in enumerate(fss):
+        n1 = 1 + probs[o].iscalar("nxterms")
+        labels = [probs[o].label(i) for i in range(n1)]
+        fs.concatFamData(buf[o, :, :n1] + 1j * buf[o, :, nstr:nstr + n1], labels,
+                         ["Yes" if c > 0.5 else "No" for c in buf[o, :, 2 * nstr]], list(buf[o, :, 2 * nstr + 2]))
+        fs.iters = buf[o, :, 2 * nstr + 1].astype(int)
+        fs._keep = probs[o]
+        if rank == 0:
+            fs.writeStrengthOut(dest)
+            fs.writeCtrBinary(dest)
+    if multi:
+        dist.barrier()
+    return fss

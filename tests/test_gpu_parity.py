@@ -337,3 +337,46 @@ def test_contour_executable_against_oracle(gpu, tmp_path):
             assert _rel(s, dat["rows"]["Strength"]) < 1e-15
             it, _, st = fo.solver_from_problem(prob, model=model, omega=w).solve(300, 1e-7)
             assert it == dat["iters"] and _rel(s, st[0]) < TOL, (k, i)
+
+
+def _sharded_worker(rank, world, port, wd, dest):
+    import os
+    import torch.distributed as dist
+    from pynfam_b200.strength import famContour, run_contours_sharded
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)      # both ranks share cuda:0 here; NCCL on a real box
+    c = famContour("CIRCLE", {"energy_min": 0.0, "energy_max": 10.476036, "nr_points": 20})
+    run_contours_sharded(wd, "x.in", [("GT-", 0), ("GT-", 1), ("RS0-", 0)], c, dest=dest, dist=dist, device=0)
+    dist.destroy_process_group()
+
+
+def test_sharded_contour_driver_matches_the_single_process_run(gpu, tmp_path):
+    """(operator, omega) tasks sharded over two ranks (whole points per rank, one all_reduce of the strengths) give the
+    files of the single-process run: the strengths of a point do not depend on the batch it is solved in."""
+    import os
+    import socket
+    import torch.multiprocessing as mp
+    from pynfam_b200.strength import famContour, famStrength, run_contours
+    wd, d1, d2 = str(tmp_path / "w"), str(tmp_path / "o1"), str(tmp_path / "o2")
+    os.makedirs(d1), os.makedirs(d2)
+    stage_point("S40_SKOP_6sh", "GT-K0", 0, wd)
+    ops = [("GT-", 0), ("GT-", 1), ("RS0-", 0)]
+    c = famContour("CIRCLE", {"energy_min": 0.0, "energy_max": 10.476036, "nr_points": 20})
+    run_contours(wd, "x.in", ops, c, dest=d1)
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    procs = [ctx.Process(target=_sharded_worker, args=(r, 2, port, wd, d2)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=300)
+        assert p.exitcode == 0
+    for op, k in ops:
+        a, b = famStrength(op, k, "CIRCLE"), famStrength(op, k, "CIRCLE")
+        a.readCtrBinary(d1)
+        b.readCtrBinary(d2)
+        x, y = a.cstr_df.values, b.cstr_df.values
+        assert x.shape == y.shape and np.max(np.abs(x - y) / np.abs(x)) < 1e-12

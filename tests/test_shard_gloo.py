@@ -64,3 +64,75 @@ def test_single_process_gather_is_a_reorder():
     idx = shard.partition(om, 1)[0]
     full = shard.gather_strengths(idx, _fake_solve(om[idx]), 3)
     assert np.array_equal(full, _fake_solve(om))
+
+
+# ---- full-contour driver over ranks (strength.run_contours_sharded) -------------------------------------------------
+def _stub_solve(fs, prob, ctx, idx):
+    """Deterministic stand-in for the batched GPU solve: 'strengths' that depend on (operator, K, omega) only."""
+    z = np.asarray(fs.contour.ctr_z)[idx]
+    n = 1 + prob.iscalar("nxterms")
+    s = np.stack([(j + 1 + fs.k) / (z - (3.0 + len(fs.op))) for j in range(n)], axis=1)
+    return dict(strength=s, conv=np.ones(len(idx), int), iters=np.full(len(idx), 7), minutes=np.full(len(idx), 0.01),
+                labels=[prob.label(i) for i in range(n)])
+
+
+OPS = [("GT-", 0), ("GT-", 1), ("RS0-", 0)]
+
+
+def _stage(wd):
+    from conftest import stage_point
+    stage_point("S40_SKOP_6sh", "GT-K0", 0, wd)
+
+
+def _contour_worker(rank, world, port, wd, dest):
+    from pynfam_b200.strength import famContour, run_contours_sharded
+    d = None
+    if world > 1:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        d = dist
+    c = famContour("CIRCLE", {"energy_min": 0.0, "energy_max": 10.476036, "nr_points": 14})
+    fss = run_contours_sharded(wd, "x.in", OPS, c, dest=dest, dist=d, solve_points=_stub_solve)
+    assert [f.opname for f in fss] == ["GT-K0", "GT-K1", "RS0-K0"] and all(f.meta["Conv"] == "Yes" for f in fss)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def test_partition_tasks_covers_every_task_once():
+    om = 5.0 + 5.0 * np.exp(1j * np.linspace(np.pi, 2 * np.pi, 30))
+    for nops, world in ((14, 8), (3, 8), (1, 2), (2, 1), (5, 4)):
+        parts = shard.partition_tasks(nops, om, world)
+        cover = np.zeros((nops, 30), int)
+        for tasks in parts:
+            for o, idx in tasks:
+                cover[o, idx] += 1
+        assert (cover == 1).all()
+        load = [sum(len(i) for _, i in t) for t in parts]
+        assert max(load) - min(load) <= 1 and max(len(t) for t in parts) <= 3
+
+
+def test_two_rank_contour_driver_writes_the_same_files_as_one_rank(tmp_path):
+    """world_size 2 (gloo): tasks sharded, strengths all-reduced, rank 0 writes OP.out / OP.out.ctr -- byte-identical
+    .ctr files to the single-process run (the host set-up is real, the GPU solve is a stub: no GPU here)."""
+    wd1, wd2 = str(tmp_path / "w1"), str(tmp_path / "w2")
+    d1, d2 = str(tmp_path / "o1"), str(tmp_path / "o2")
+    for d in (d1, d2):
+        os.makedirs(d)
+    _stage(wd1)
+    _stage(wd2)
+    _contour_worker(0, 1, 0, wd1, d1)
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    procs = [ctx.Process(target=_contour_worker, args=(r, 2, port, wd2, d2)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=180)
+        assert p.exitcode == 0
+    for op in ("GT-K0", "GT-K1", "RS0-K0"):
+        a = open(os.path.join(d1, op + ".out.ctr"), "rb").read()
+        assert a == open(os.path.join(d2, op + ".out.ctr"), "rb").read() and len(a) > 500
+        assert os.path.isfile(os.path.join(d2, op + ".out"))
