@@ -488,6 +488,10 @@ ExtField make_external_field(const FamBasis& b, const std::string& beta_type, co
 }
 
 std::vector<ExtField> make_crossterms(const FamBasis& b, const ExtField& op) {
+  return make_crossterms(op, [&](const std::string& beta, const std::string& l, int k) { return make_external_field(b, beta, l, k); });
+}
+
+std::vector<ExtField> make_crossterms(const ExtField& op, const FieldProvider& field) {
   std::vector<ExtField> out;
   if (op.parity_even) return out;
   const std::string& L = op.label;
@@ -496,7 +500,7 @@ std::vector<ExtField> make_crossterms(const FamBasis& b, const ExtField& op) {
   if (L == "R" || L == "P" || L == "RS1" || L == "RI" || L == "RS1I") labels = {"R", "RS1", "P", "RI", "RS1I"};
   else if (L == "RS0" || L == "PS0" || L == "RS0I") labels = {"RS0", "PS0", "RS0I"};
   for (const auto& l : labels) {
-    ExtField g = make_external_field(b, beta, l, op.k);
+    ExtField g = field(beta, l, op.k);
     g.label = L + "x" + l;
     out.push_back(std::move(g));
   }

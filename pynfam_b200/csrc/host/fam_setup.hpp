@@ -4,6 +4,7 @@
 // the external-field matrices and their block maps (pnfam_extfield.f90:37-108,110-622,763-840,
 // 882-949) and the pnFAM namelist (pnfam_setup.f90:98-108,178-250).
 #pragma once
+#include <functional>
 #include <array>
 #include <string>
 #include <vector>
@@ -109,6 +110,10 @@ struct ExtField {
 ExtField make_external_field(const FamBasis& b, const std::string& beta_type, const std::string& label, int k,
                              const std::vector<double>* rho_fac = nullptr);
 std::vector<ExtField> make_crossterms(const FamBasis& b, const ExtField& op);
+// the same with the fields taken from a provider (beta type, label, K) -> field, e.g. a per-nucleus cache: the
+// operators of one J^pi group share their cross-term fields
+using FieldProvider = std::function<ExtField(const std::string&, const std::string&, int)>;
+std::vector<ExtField> make_crossterms(const ExtField& op, const FieldProvider& field);
 // Read the Yukawa part of a two-body-current field from <name>.tbc (pnfam_storage.f90:562-727).
 // On success f.mat.elem holds c3/c4-weighted gamma (direct + exchange) exactly as read_tbc leaves it.
 bool read_tbc(const std::string& path, const FamBasis& b, const FamInput& in, ExtField& f, std::string& why);

@@ -16,6 +16,13 @@ std::shared_ptr<Nucleus> Nucleus::load(const std::string& rundir) {
   return n;
 }
 
+const ExtField& Nucleus::field(const std::string& beta, const std::string& label, int k) {
+  const std::string key = beta + "|" + label + "|" + std::to_string(k);
+  auto it = fields.find(key);
+  if (it == fields.end()) it = fields.emplace(key, make_external_field(basis, beta, label, k)).first;
+  return it->second;
+}
+
 static int digit(int v, int p) {
   for (int i = 0; i < p; i++) v /= 10;
   return v % 10;
@@ -50,8 +57,10 @@ std::unique_ptr<Problem> Problem::build(const std::string& rundir, const FamInpu
     if (u[5] != 0 || u[6] != 0 || u[4] >= 2)
       throw std::runtime_error("two-body-current corrections to P / PS0 / RS* operators are not supported yet");
   }
-  p->f = make_external_field(b, in.beta_type, in.operator_name, in.operator_k);
-  if (in.compute_crossterms) p->g = make_crossterms(b, p->f);
+  Nucleus& nucl = *p->nuc;
+  p->f = nucl.field(in.beta_type, in.operator_name, in.operator_k);          // a copy: the 2BC correction below edits it
+  if (in.compute_crossterms)
+    p->g = make_crossterms(p->f, [&](const std::string& beta, const std::string& l, int k) { return nucl.field(beta, l, k); });
   if (mode != 0 && p->f.label == "GT" && u[4] != 0) {
     if (u[2] != 1) throw std::runtime_error("two_body_current_mode: only the full-FAM Yukawa field read from <name>.tbc (2nd digit = 1) is supported");
     apply_two_body_current_gt(d + "/" + in.fam_output_filename + ".tbc", b, in, u[1], p->f);

@@ -14,6 +14,10 @@ struct Nucleus {  // everything that depends only on the HFB files (shared by al
   HelData hel;
   HfbSolution hfb;
   FamBasis basis;
+  // external fields already built for this nucleus, keyed by beta type / label / K (shared by the operators of a
+  // contour run: R, P, RS1 ... all need the same five cross-term fields)
+  std::map<std::string, ExtField> fields;
+  const ExtField& field(const std::string& beta, const std::string& label, int k);
   static std::shared_ptr<Nucleus> load(const std::string& rundir);
 };
 

@@ -20,6 +20,7 @@ import time
 import numpy as np
 
 KAPPA = 6147.0   # pynfam/config.py:225, decay constant [s]
+NSTR_MAX = 8     # strength + cross-term columns of one operator (the reference has at most 1 + 5, pnfam_extfield.f90:908-947)
 TMIN = 1e-3   # pynfam/config.py: finite temperature is not supported by this path (fails loudly in the host set-up)
 
 _CONTOUR_DEFAULTS = {
@@ -506,9 +507,9 @@ def run_contours(rundir, namelist, operators, contour, dest=None, device=0, **so
 
 def run_contours_sharded(rundir, namelist, operators, contour, dest=None, dist=None, device=0, solve_points=None, **solve_kw):
     """run_contours over the ranks of a torch.distributed job (one process per GPU): the (operator, contour point) tasks
-    are dealt to the ranks by shard.partition_tasks, every rank sets the nucleus up once and solves its points of each
+    are dealt to the ranks by shard.partition_tasks, every rank sets the nucleus and the operators it owns up once and solves its points of each
     operator as one batch, and the ONLY exchange is one all_reduce of the strengths (disjoint ownership, so a sum is a
-    gather) -- NCCL on GPUs, gloo in the CPU tests.  Rank 0 assembles and writes OP.out / OP.out.ctr for every operator;
+    gather; the row labels travel beside it) -- NCCL on GPUs, gloo in the CPU tests.  Rank 0 assembles and writes OP.out / OP.out.ctr for every operator;
     every rank returns the list of famStrength objects.  `solve_points(fs, prob, ctx, points)` may replace the GPU
     solve (tests)."""
     import torch
@@ -520,15 +521,18 @@ def run_contours_sharded(rundir, namelist, operators, contour, dest=None, dist=N
     operators = list(operators)
     nc = contour.nr_compute
     mine = shard.partition_tasks(len(operators), contour.ctr_z[:nc], world)[rank]
-    # every rank sets up every operator on the host (cheap; gives the labels), the nucleus once
-    fss, probs, first = [], [], None
-    for op, k in operators:
-        fs = famStrength(op, k, contour)
-        prob = fs.setup(rundir, namelist, share_nucleus_with=first)
-        first = first or prob
-        fss.append(fs); probs.append(prob)
-    nstr = max(1 + p.iscalar("nxterms") for p in probs)
+    # a rank sets up the nucleus once and only the operators it owns points of; labels travel with the results
+    t_start = time.perf_counter()
+    fss = [famStrength(op, k, contour) for op, k in operators]
+    probs, first = {}, None
+    for o, idx in mine:
+        if len(idx):
+            probs[o] = fss[o].setup(rundir, namelist, share_nucleus_with=first)
+            first = first or probs[o]
+    t_setup = time.perf_counter()
+    nstr = NSTR_MAX
     buf = np.zeros((len(operators), nc, 2 * nstr + 3))          # re | im | conv, iterations, minutes
+    labels = {}
     ctx = None
     for o, idx in mine:
         if len(idx) == 0:
@@ -541,26 +545,41 @@ def run_contours_sharded(rundir, namelist, operators, contour, dest=None, dist=N
                 ctx = gpu.Context(probs[o], device=device)
             res = fss[o].solve_points(probs[o], ctx, points=idx, **solve_kw)
         n1 = res["strength"].shape[1]
+        if n1 > nstr:
+            raise RuntimeError("operator with more than %d strength columns" % nstr)
+        labels[o] = list(res["labels"])
         buf[o, idx, :n1] = res["strength"].real
         buf[o, idx, nstr:nstr + n1] = res["strength"].imag
         buf[o, idx, 2 * nstr] = res["conv"]
         buf[o, idx, 2 * nstr + 1] = res["iters"]
         buf[o, idx, 2 * nstr + 2] = res["minutes"]
+    t_solve = time.perf_counter()
+    meta = {"nucleus": fss[mine[0][0]].nucleus, "meta": dict(fss[mine[0][0]]._meta)} if mine and len(mine[0][1]) else None
     if multi:
         on_gpu = dist.get_backend() == "nccl"
         t = torch.as_tensor(buf, device=("cuda:%d" % device) if on_gpu else "cpu")
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         buf = t.cpu().numpy()
+        parts = [None] * world
+        dist.all_gather_object(parts, (labels, meta))
+        for lab, m in parts:
+            labels.update(lab)
+            meta = meta or m
     for o, fs in enumerate(fss):
-        n1 = 1 + probs[o].iscalar("nxterms")
-        labels = [probs[o].label(i) for i in range(n1)]
-        fs.concatFamData(buf[o, :, :n1] + 1j * buf[o, :, nstr:nstr + n1], labels,
+        n1 = len(labels[o])
+        if fs.nucleus is None:
+            fs.nucleus = tuple(meta["nucleus"])
+            fs._meta.update({k: meta["meta"][k] for k in ("Version", "Interaction")})
+        fs.concatFamData(buf[o, :, :n1] + 1j * buf[o, :, nstr:nstr + n1], labels[o],
                          ["Yes" if c > 0.5 else "No" for c in buf[o, :, 2 * nstr]], list(buf[o, :, 2 * nstr + 2]))
         fs.iters = buf[o, :, 2 * nstr + 1].astype(int)
-        fs._keep = probs[o]
+        fs._keep = probs.get(o)
         if rank == 0:
             fs.writeStrengthOut(dest)
             fs.writeCtrBinary(dest)
     if multi:
         dist.barrier()
+    t_end = time.perf_counter()
+    run_contours_sharded.last_timing = {"host_setup_s": t_setup - t_start, "solve_s": t_solve - t_setup,
+                                        "gather_and_write_s": t_end - t_solve}
     return fss
