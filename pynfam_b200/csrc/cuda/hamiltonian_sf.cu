@@ -355,13 +355,18 @@ void launch_density_sf(const HamArgs& a, cudaStream_t stream) {
   if (maxsteps > 0) sf_pack_kernel<<<dim3(maxsteps, 4, a.nactive), 256, 0, stream>>>(a);
   const int nilp = (S.ngl + 1) / 2;
   const dim3 grid(nilp, 2, a.nactive);
+  // rho and kappa are independent: the kappa pass runs on a side stream, so its CTAs fill the SMs the rho pass leaves
+  // idle (its tail at full batch, most of the GPU once few points are still active)
+  SideStreams& ss = side_streams();
+  ss.fork_from(stream, 1);
   if (L.ts == 68 && S.kpad_max == 12 && S.zs == 52) {          // 40-point Gauss-Hermite grid, up to 22 shells
     sf_density_kernel<0, 68, 12, 52><<<grid, SF_THREADS, L.total, stream>>>(a, L);
-    sf_density_kernel<1, 68, 12, 52><<<grid, SF_THREADS, L.total, stream>>>(a, L);
+    sf_density_kernel<1, 68, 12, 52><<<grid, SF_THREADS, L.total, ss.s[0]>>>(a, L);
   } else {
     sf_density_kernel<0, 0, 0, 0><<<grid, SF_THREADS, L.total, stream>>>(a, L);
-    sf_density_kernel<1, 0, 0, 0><<<grid, SF_THREADS, L.total, stream>>>(a, L);
+    sf_density_kernel<1, 0, 0, 0><<<grid, SF_THREADS, L.total, ss.s[0]>>>(a, L);
   }
+  ss.join_to(stream, 1);
 }
 
 // ================================================================================================
@@ -684,17 +689,25 @@ void launch_projection_sf(const HamArgs& a, cudaStream_t stream) {
     attr1 = L1.total;
   }
   const bool common = S.kih == 40 && S.zs == 52;               // 40-point Gauss-Hermite grid
+  // four independent launches (h and Delta of both passes): the long ones first, each on its own stream
+  SideStreams& ss = side_streams();
+  ss.fork_from(stream, 3);
   for (int q = 0; q < 2; q++) {
-    const dim3 g0(S.ntiles[0][q] / SF_PPAIRS, S.ksplit, a.nactive), g1(S.ntiles[1][q] / SF_PPAIRS, S.ksplit, a.nactive);
+    const dim3 g0(S.ntiles[0][q] / SF_PPAIRS, S.ksplit, a.nactive);
+    cudaStream_t st = q == 0 ? stream : ss.s[0];
     if (S.ntiles[0][q] > 0) {
-      if (common) sf_projection_kernel<0, 40, 52><<<g0, SF_THREADS, L0.total, stream>>>(a, L0, q);
-      else sf_projection_kernel<0, 0, 0><<<g0, SF_THREADS, L0.total, stream>>>(a, L0, q);
-    }
-    if (S.ntiles[1][q] > 0) {
-      if (common) sf_projection_kernel<1, 40, 52><<<g1, SF_THREADS, L1.total, stream>>>(a, L1, q);
-      else sf_projection_kernel<1, 0, 0><<<g1, SF_THREADS, L1.total, stream>>>(a, L1, q);
+      if (common) sf_projection_kernel<0, 40, 52><<<g0, SF_THREADS, L0.total, st>>>(a, L0, q);
+      else sf_projection_kernel<0, 0, 0><<<g0, SF_THREADS, L0.total, st>>>(a, L0, q);
     }
   }
+  for (int q = 0; q < 2; q++) {
+    const dim3 g1(S.ntiles[1][q] / SF_PPAIRS, S.ksplit, a.nactive);
+    if (S.ntiles[1][q] > 0) {
+      if (common) sf_projection_kernel<1, 40, 52><<<g1, SF_THREADS, L1.total, ss.s[1 + q]>>>(a, L1, q);
+      else sf_projection_kernel<1, 0, 0><<<g1, SF_THREADS, L1.total, ss.s[1 + q]>>>(a, L1, q);
+    }
+  }
+  ss.join_to(stream, 3);
   dim3 gr((unsigned)((2 * a.nxy + 255) / 256), 4, a.nactive);
   sf_projection_reduce_kernel<<<gr, 256, 0, stream>>>(a, S.ksplit);
 }

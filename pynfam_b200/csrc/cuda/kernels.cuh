@@ -154,6 +154,32 @@ struct ProjPlan {                 // output tiles of the grid->HO projection
   int ksplit = 1;
 };
 
+// Independent kernels of one stage (rho and kappa densities; h and Delta projections of both passes) run on side
+// streams forked from / joined to the caller's stream, so that the tail of one fills with CTAs of the next.
+struct SideStreams {
+  static constexpr int N = 3;
+  cudaStream_t s[N];
+  cudaEvent_t fork, join[N];
+  SideStreams() {
+    for (int i = 0; i < N; i++) {
+      PNFAM_CUDA_CHECK(cudaStreamCreateWithFlags(&s[i], cudaStreamNonBlocking));
+      PNFAM_CUDA_CHECK(cudaEventCreateWithFlags(&join[i], cudaEventDisableTiming));
+    }
+    PNFAM_CUDA_CHECK(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+  }
+  void fork_from(cudaStream_t main, int n) {
+    PNFAM_CUDA_CHECK(cudaEventRecord(fork, main));
+    for (int i = 0; i < n; i++) PNFAM_CUDA_CHECK(cudaStreamWaitEvent(s[i], fork, 0));
+  }
+  void join_to(cudaStream_t main, int n) {
+    for (int i = 0; i < n; i++) {
+      PNFAM_CUDA_CHECK(cudaEventRecord(join[i], s[i]));
+      PNFAM_CUDA_CHECK(cudaStreamWaitEvent(main, join[i], 0));
+    }
+  }
+};
+SideStreams& side_streams();
+
 void launch_density(const HamArgs& a, cudaStream_t stream);
 // host helper: flatten a block structure into density pipeline steps
 void build_density_steps(int nb, const int* db, const int* pstart, const int* nsu, const int* r2c, const int* r2m,

@@ -409,6 +409,11 @@ size_t upload_density_steps(const pnfam_b200_ctx& c, const BlockStruct& st, DBuf
   return pk;
 }
 
+int sf_ksplit_for(const pnfam_b200_ctx& c, const OperatorDev& od, int nactive) {
+  const int per = std::max(1, od.sf_ntiles[0][0] / 8 * std::max(1, nactive));
+  return std::min(c.sf.ngl, std::max(1, (2 * 148 + per - 1) / per));
+}
+
 void flatten(const TransformPlan& tp, DBuf<DevTask>& dt, DBuf<int4>& d1, DBuf<int4>& d2, DevicePlan& out) {
   std::vector<DevTask> tasks;
   std::vector<int4> t1, t2;
@@ -498,9 +503,12 @@ std::unique_ptr<OperatorDev> make_operator(pnfam_b200_ctx& c, const pnfam_b200_o
     upload_sf_proj_tiles(c, od->plan.hsp[3], od->sf_tiles[0][1], od->sf_ntiles[0][1]);
     upload_sf_proj_tiles(c, od->plan.hsp[1], od->sf_tiles[1][0], od->sf_ntiles[1][0]);
     upload_sf_proj_tiles(c, od->plan.hsp[2], od->sf_tiles[1][1], od->sf_ntiles[1][1]);
-    const int per = std::max(1, od->sf_ntiles[0][0] / 8 * std::max(1, npoints));
-    od->sf_ksplit = std::min(c.sf.ngl, std::max(1, (2 * 148 + per - 1) / per));
-    od->proj.ksplit = od->sf_ksplit;      // sizes the split-K partials
+    // split-K factor as a function of the points still active (the batch shrinks as points converge): at least two
+    // waves of CTAs per launch.  proj.ksplit sizes the partials for the largest nactive x ksplit(nactive).
+    od->sf_ksplit = sf_ksplit_for(c, *od, std::max(1, npoints));
+    int need = od->sf_ksplit * std::max(1, npoints);
+    for (int n = 1; n <= std::max(1, npoints); n++) need = std::max(need, n * sf_ksplit_for(c, *od, n));
+    od->proj.ksplit = (need + std::max(1, npoints) - 1) / std::max(1, npoints);
     return od;
   }
   od->pk_rho = std::max(upload_density_steps(c, od->plan.sp[0], od->dsteps[0], od->ndsteps[0]),
@@ -702,6 +710,7 @@ extern "C" int pnfam_b200_solve(pnfam_b200_ctx* c, const pnfam_b200_operator* op
     for (int it = 0; it < prm->max_iter && nactive > 0; it++) {
       Timer titer;
       ha.nactive = nactive; ma.nactive = nactive;
+      if (sf) ha.sf.ksplit = sf_ksplit_for(*c, *od, nactive);
       if (!no_residual) {
         TransformArgs f = ta;
         f.in = vin.p; f.in_pstride = n; f.in_pack = 1;
