@@ -8,8 +8,9 @@ Inputs: tests/golden/Gd162_SKOP_16sh/ (made with the reference's own hfbtho_main
 
 One "step" = one full batched contour solve on each rank (all FAM iterations of all its points).
   value   = FAM iterations/s, whole job, device-resident (CUDA events around the iteration loop)
-  e2e     = same metric through the C ABI from HOST buffers: context creation (H2D of all tables) +
-            operator upload + solve + D2H of the strengths, wall clock, every step
+  e2e     = same metric through the C ABI from HOST buffers: context creation (H2D of the model) +
+            operator upload + solve + D2H of the strengths, wall clock, every step (after one untimed
+            warm-up of that path)
   impl=reference : the reference's unmodified pnfam_main.x (oracle/_ref) on the host cores, a bounded
             sample of the same workload (one omega point, `--ref-iters` iterations), iterations/s from its
             own per-iteration timer.

@@ -13,4 +13,5 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --
   python bench.py --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/b_launch_$tag.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"density_kernel|projection_kernel" -s 8 -c 6 -o gpurun_out/prof_$tag \
   python bench.py --steps 1 --warmup 0 --points 8 --no-cpu-baseline > gpurun_out/b_ncu_$tag.log 2>&1
+(timeout 300 python __graft_entry__.py smoke 2>&1 | tail -3) > gpurun_out/smoke_$tag.log; cat gpurun_out/smoke_$tag.log
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi_$tag.csv
