@@ -276,6 +276,10 @@ class famStrength(object):
         from . import host
         text = open(os.path.join(rundir, namelist)).read()
         text = patch_namelist(text, operator_name=self.bareop, beta_type=self.beta, operator_k=int(self.k))
+        try:    # pynfam names every operator's files after it (OP.dat, OP.tbc for the two-body-current field)
+            text = patch_namelist(text, fam_output_filename=self.opname)
+        except KeyError:
+            pass
         name = "%s.b200.in" % self.opname
         tmp = os.path.join(rundir, ".%s.%d.tmp" % (name, os.getpid()))      # several ranks may share the rundir
         with open(tmp, "w") as f:

@@ -380,3 +380,22 @@ def test_sharded_contour_driver_matches_the_single_process_run(gpu, tmp_path):
         b.readCtrBinary(d2)
         x, y = a.cstr_df.values, b.cstr_df.values
         assert x.shape == y.shape and np.max(np.abs(x - y) / np.abs(x)) < 1e-12
+
+
+def test_contour_driver_with_two_body_currents(gpu, tmp_path):
+    """run_contours on the 2BC tree (tests/S40_All_GT2bc): every operator reads its own <OP>.tbc, so starting from the
+    GT-K0 namelist the K=1 operator must pick GT-K1.tbc; all 30 computed points of both operators against the golden
+    per-point results."""
+    from pynfam_b200.strength import famContour, run_contours
+    wd = str(tmp_path)
+    stage_point("S40_All_GT2bc", "GT-K0", 0, wd)
+    pts = {op: load_points("S40_All_GT2bc")[op] for op in ("GT-K0", "GT-K1")}
+    contour = famContour("CIRCLE", {"energy_min": 0.0, "energy_max": 10.476036})
+    res = run_contours(wd, "x.in", [("GT-", 0), ("GT-", 1)], contour)
+    for fs in res:
+        got = fs.cstr_df["Strength"].values
+        for i, pt in enumerate(pts[fs.opname]):
+            gold = gold_rows(pt)
+            assert abs(contour.ctr_z[i] - gold["Energy"]) < 1e-12
+            loose = abs(contour.ctr_z[i].imag) < 0.5 or pt["iters"] >= 25
+            assert _rel(got[i], gold["Strength"]) < (5e-8 if loose else TOL), (fs.opname, i)
