@@ -2,8 +2,9 @@
 """bench.py -- pnFAM throughput on B200: FAM iterations/s and omega-points/s.
 
 Workload (config.workload): 162Gd, SkO', 16 HO shells, 40x40 Gauss grid (N=1958, nghl=1600, nxy=103926),
-Gamow-Teller K=0, synthetic CIRCLE contour sweep (pynfam/strength/contour.py:212-283 restated) with
-`--points` Gauss-Legendre nodes PER GPU, every point solved to convergence (eps=1e-7, M=50, max_iter=300).
+Gamow-Teller K=0, synthetic contour sweep: CIRCLE contours (pynfam/strength/contour.py:212-283 restated) of 64
+Gauss-Legendre nodes on [0, 10+0.25g] MeV, `--points` points PER GPU (default 128 = two contours; 1024 points at 8
+GPUs, the span BASELINE.json configs[4] names), every point solved to convergence (eps=1e-7, M=50, max_iter=300).
 Inputs: tests/golden/Gd162_SKOP_16sh/ (made with the reference's own hfbtho_main).
 
 One "step" = one full batched contour solve on each rank (all FAM iterations of all its points).
@@ -35,7 +36,8 @@ def case_dir():
 
 
 def workload():
-    return "Gd162 SkO' %d shells 40x40 grid, GT- K=0, synthetic CIRCLE contour sweep" % SHELLS
+    return ("Gd162 SkO' %d shells 40x40 grid, GT- K=0, synthetic contour sweep (CIRCLE contours of %d Gauss-Legendre nodes "
+            "on [0, 10+0.25g] MeV)" % (SHELLS, NODES_PER_CIRCLE))
 
 FAM_NML = """&general
     fam_output_filename = 'GT-K0'
@@ -78,6 +80,22 @@ def circle_contour(npts, emin=0.0, emax=10.0):
     theta = np.pi + (x + 1.0) * np.pi
     r0, r = 0.5 * (emin + emax), 0.5 * (emax - emin)
     return r0 + r * np.exp(1j * theta)
+
+
+NODES_PER_CIRCLE = 64   # pynfam's default contour has 60 nodes; a single circle with hundreds of nodes would put dozens
+                        # of points within 1e-3 MeV of the real axis (on the poles of the response)
+
+
+def sweep_contour(npts):
+    """Synthetic contour sweep of `npts` points: CIRCLE contours of 64 Gauss-Legendre nodes on [0, 10 + 0.25 g] MeV,
+    g = 0, 1, ... (the last one with the remaining nodes).  --points 32 is one 32-node circle on [0, 10]."""
+    import numpy as np
+    out, g = [], 0
+    while len(out) < npts:
+        n = min(NODES_PER_CIRCLE, npts - len(out))
+        out.extend(circle_contour(n, 0.0, 10.0 + 0.25 * g))
+        g += 1
+    return np.array(out)
 
 
 def stage(wd, omega, max_iter):
@@ -128,7 +146,7 @@ def reference_farm(args, nproc):
     pnfam_main.x processes side by side, one omega point each, args.ref_iters iterations.  Returns (aggregate
     iterations/s from the processes' own per-iteration timers, iterations, wall seconds, mean setup seconds)."""
     from oracle import refrun
-    oms = circle_contour(max(args.points, nproc))
+    oms = sweep_contour(max(args.points, nproc))
     res = [None] * nproc
 
     def work(k):
@@ -161,7 +179,7 @@ def run_reference(args, rank):
     if not refrun.ensure_built():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/pnfam_main.x or the OpenBLAS wheel is missing"}))
         return
-    om = circle_contour(args.points)[args.points // 3]
+    om = sweep_contour(args.points)[min(args.points, NODES_PER_CIRCLE) // 3]
     wd = tempfile.mkdtemp()
     stage(wd, om, args.ref_iters)
     per_iter = []
@@ -208,7 +226,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--points", type=int, default=32, help="omega points per GPU (weak scaling)")
+    ap.add_argument("--points", type=int, default=128,
+                    help="omega points per GPU (weak scaling): 128 -> 1024 at 8 GPUs, the span BASELINE.json configs[4] names")
     ap.add_argument("--shells", type=int, default=16, choices=[16, 20], help="HO shells of the Gd162 basis (fixture)")
     ap.add_argument("--ref-iters", type=int, default=4)
     ap.add_argument("--assumed-iters-per-point", type=float, default=25.0)
@@ -240,7 +259,7 @@ def main():
 
     # ---- this rank's shard of the contour (independent omega points: no data-path collective) --------
     npts = args.points * world
-    omegas = circle_contour(npts)
+    omegas = sweep_contour(npts)
     my_idx = shard.partition(omegas, world)[rank]
     mine = omegas[my_idx]
     wd = tempfile.mkdtemp()
@@ -373,7 +392,7 @@ def cpu_baseline(args):
     bounded sample of the same workload."""
     from oracle import refrun
     cores = os.cpu_count()
-    om = circle_contour(args.points)[args.points // 3]
+    om = sweep_contour(args.points)[min(args.points, NODES_PER_CIRCLE) // 3]
     wd = tempfile.mkdtemp()
     stage(wd, om, args.ref_iters)
     if refrun.ensure_built():
