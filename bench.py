@@ -252,9 +252,8 @@ def main():
         raise SystemExit("bench.py: no CUDA device -- the FAM iteration has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        # keep stdout to the one JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # keep stdout to the one JSON line: NCCL writes its version banner / debug log there unless told otherwise
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     # ---- this rank's shard of the contour (independent omega points: no data-path collective) --------

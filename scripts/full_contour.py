@@ -42,8 +42,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep stdout to the JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     bench.SHELLS = args.shells
     wd = tempfile.mkdtemp()
