@@ -399,3 +399,33 @@ def test_contour_driver_with_two_body_currents(gpu, tmp_path):
             assert abs(contour.ctr_z[i] - gold["Energy"]) < 1e-12
             loose = abs(contour.ctr_z[i].imag) < 0.5 or pt["iters"] >= 25
             assert _rel(got[i], gold["Strength"]) < (5e-8 if loose else TOL), (fs.opname, i)
+
+
+def test_history_limit_and_contour_mode_of_the_executable(gpu, tmp_path):
+    """Loud failures and the CONTOUR mode: a Broyden history above the device mixer's staging limit is refused with a
+    message (no silent truncation); contour_main.x fam_mode='CONTOUR' (a circle, absent from the reference) solves and
+    lists every point."""
+    import os
+    import subprocess
+    from conftest import ROOT
+    wd = str(tmp_path)
+    stage_point("S40_SKOP_6sh", "GT-K0", 10, wd, name="pnfam_NAMELIST.dat")
+    p = host.Problem(wd, "pnfam_NAMELIST.dat")
+    ctx = gpu.Context(p)
+    with pytest.raises(gpu.GpuError, match="broyden_history_size"):
+        ctx.solve(p, history=65)
+    r = ctx.solve(p, history=64, max_iter=5)            # at the limit: runs, interrupted after 5 steps
+    assert int(r["iters"][0]) == 5 and int(r["conv"][0]) == 0
+    open(os.path.join(wd, "ctr.dat"), "w").write(
+        "&ctr_general\n fam_mode = 'CONTOUR'\n fam_input_filename = 'pnfam_NAMELIST.dat'\n/\n"
+        "&ctr_extfield\n operator_active = 0, 0, 0, 0, 0\n/\n"
+        "&contour_parameters\n energy_min = 0.0\n energy_max = 8.0\n nr_points = 5\n shift_imag = 0.5\n/\n")
+    exe = os.path.join(ROOT, "pynfam_b200", "bin", "contour_main.x")
+    out = subprocess.run([exe, "ctr.dat"], cwd=wd, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stderr.strip() == "", out.stdout[-400:]
+    rows = [ln.split() for ln in open(os.path.join(wd, "GT-K0.out")).read().split("\n") if ln.strip() and not ln.startswith("#")]
+    assert len(rows) == 5 and all(int(r_[0]) == 1 for r_ in rows)
+    # equally spaced circle theta = pi .. 3 pi: Re(EQRPA) = 4 + 4 cos(theta)
+    want = 4.0 + 4.0 * np.cos(np.pi + 2.0 * np.pi * np.arange(5) / 4.0)
+    assert np.allclose([float(r_[1]) for r_ in rows], want, atol=1e-12)
+    assert all(abs(complex(float(r_[2]), float(r_[3]))) > 0 for r_ in rows)
