@@ -259,9 +259,10 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sf_density_kernel(HamArgs g, Sf
     const int ksteps = (d.nslots + 3) >> 2, ntn = d.nbc >> 2;
     const int nt_mid = (ntn + 1) >> 1;
     const int nt0 = split ? (half ? nt_mid : 0) : 0, nt1 = split ? (half ? ntn : nt_mid) : ntn;
-    double a0[SF_KMAX / 4], a1[SF_KMAX / 4];
+    constexpr int KS = (KPAD_ ? KPAD_ : SF_KMAX) / 4;       // k-steps a step can have
+    double a0[KS], a1[KS];
 #pragma unroll
-    for (int ks = 0; ks < SF_KMAX / 4; ks++) {
+    for (int ks = 0; ks < KS; ks++) {
       a0[ks] = 0.0; a1[ks] = 0.0;
       if (ks < ksteps) {
         const int slot = ks * 4 + lc;
@@ -276,7 +277,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sf_density_kernel(HamArgs g, Sf
 #pragma unroll
       for (int i = 0; i < NT * 2; i++) (&C[0][0])[i] = 0.0;
 #pragma unroll
-      for (int ks = 0; ks < SF_KMAX / 4; ks++) {
+      for (int ks = 0; ks < KS; ks++) {
         if (ks < ksteps) {
           const double* __restrict__ tb = T + (size_t)(ks * 4 + lc) * ts + nt * 8 + lr;
           const double b0 = tb[0];
