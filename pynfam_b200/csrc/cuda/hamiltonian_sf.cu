@@ -415,7 +415,8 @@ static SfProjLayout make_proj_layout(const SfDev& S) {
 // MODE 0: mf -> h;  MODE 1: pf -> Delta
 // KIH_, ZS_ (0 = run-time value): padded Gauss-Hermite count and row stride of the z tables as compile-time constants
 // for the common grid (see sf_density_kernel)
-template <int MODE, int KIH_, int ZS_>
+// HACC_: accumulators per lane (8 rows a each): 6 when no spin segment has more than 48 states, else SF_HACC
+template <int MODE, int KIH_, int ZS_, int HACC_>
 __global__ void __launch_bounds__(SF_THREADS, 1) sf_projection_kernel(HamArgs g, SfProjLayout L, int q) {
   constexpr int NS = MODE == 0 ? 5 : SF_DIL;   // G slices per iteration: derivative types (h) / Gauss-Laguerre nodes (Delta)
   constexpr int NW = 4;                        // W planes per iteration: radial factor types (h) / nodes (Delta)
@@ -520,9 +521,9 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sf_projection_kernel(HamArgs g,
     }
   };
   if (nit > 0) fetch_r(0);
-  double hacc[SF_HACC];
+  double hacc[HACC_];
 #pragma unroll
-  for (int i = 0; i < SF_HACC; i++) hacc[i] = 0.0;
+  for (int i = 0; i < HACC_; i++) hacc[i] = 0.0;
 
   for (int it = 0; it < nit; it++) {
     const int sg = it % nst;
@@ -619,7 +620,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sf_projection_kernel(HamArgs g,
       {
         const int col = l64 & 7, ar = l64 >> 3;
 #pragma unroll
-        for (int i = 0; i < SF_HACC; i++) {
+        for (int i = 0; i < HACC_; i++) {
           const int a = ar + 8 * i;
           if (a < na) {
             const int sl = slot_a[a];
@@ -644,7 +645,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sf_projection_kernel(HamArgs g,
     const int lda = na | 1;
     const int col = l64 & 7, ar = l64 >> 3;
 #pragma unroll
-    for (int i = 0; i < SF_HACC; i++) {
+    for (int i = 0; i < HACC_; i++) {
       const int a = ar + 8 * i;
       if (a < na) Tr[col * lda + a] = hacc[i];
     }
@@ -680,16 +681,19 @@ void launch_projection_sf(const HamArgs& a, cudaStream_t stream) {
   const SfProjLayout L0 = make_proj_layout<0>(S), L1 = make_proj_layout<1>(S);
   static int attr0 = 0, attr1 = 0;
   if (L0.total > attr0) {
-    PNFAM_CUDA_CHECK(cudaFuncSetAttribute(sf_projection_kernel<0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, L0.total));
-    PNFAM_CUDA_CHECK(cudaFuncSetAttribute(sf_projection_kernel<0, 40, 52>, cudaFuncAttributeMaxDynamicSharedMemorySize, L0.total));
+    PNFAM_CUDA_CHECK(cudaFuncSetAttribute(sf_projection_kernel<0, 0, 0, SF_HACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, L0.total));
+    PNFAM_CUDA_CHECK(cudaFuncSetAttribute(sf_projection_kernel<0, 40, 52, SF_HACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, L0.total));
+    PNFAM_CUDA_CHECK(cudaFuncSetAttribute(sf_projection_kernel<0, 40, 52, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, L0.total));
     attr0 = L0.total;
   }
   if (L1.total > attr1) {
-    PNFAM_CUDA_CHECK(cudaFuncSetAttribute(sf_projection_kernel<1, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, L1.total));
-    PNFAM_CUDA_CHECK(cudaFuncSetAttribute(sf_projection_kernel<1, 40, 52>, cudaFuncAttributeMaxDynamicSharedMemorySize, L1.total));
+    PNFAM_CUDA_CHECK(cudaFuncSetAttribute(sf_projection_kernel<1, 0, 0, SF_HACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, L1.total));
+    PNFAM_CUDA_CHECK(cudaFuncSetAttribute(sf_projection_kernel<1, 40, 52, SF_HACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, L1.total));
+    PNFAM_CUDA_CHECK(cudaFuncSetAttribute(sf_projection_kernel<1, 40, 52, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, L1.total));
     attr1 = L1.total;
   }
   const bool common = S.kih == 40 && S.zs == 52;               // 40-point Gauss-Hermite grid
+  const bool small = common && S.na_max <= 48;                 // spin segments of at most 48 states (up to 17 shells)
   // four independent launches (h and Delta of both passes): the long ones first, each on its own stream
   SideStreams& ss = side_streams();
   ss.fork_from(stream, 3);
@@ -697,15 +701,17 @@ void launch_projection_sf(const HamArgs& a, cudaStream_t stream) {
     const dim3 g0(S.ntiles[0][q] / SF_PPAIRS, S.ksplit, a.nactive);
     cudaStream_t st = q == 0 ? stream : ss.s[0];
     if (S.ntiles[0][q] > 0) {
-      if (common) sf_projection_kernel<0, 40, 52><<<g0, SF_THREADS, L0.total, st>>>(a, L0, q);
-      else sf_projection_kernel<0, 0, 0><<<g0, SF_THREADS, L0.total, st>>>(a, L0, q);
+      if (small) sf_projection_kernel<0, 40, 52, 6><<<g0, SF_THREADS, L0.total, st>>>(a, L0, q);
+      else if (common) sf_projection_kernel<0, 40, 52, SF_HACC><<<g0, SF_THREADS, L0.total, st>>>(a, L0, q);
+      else sf_projection_kernel<0, 0, 0, SF_HACC><<<g0, SF_THREADS, L0.total, st>>>(a, L0, q);
     }
   }
   for (int q = 0; q < 2; q++) {
     const dim3 g1(S.ntiles[1][q] / SF_PPAIRS, S.ksplit, a.nactive);
     if (S.ntiles[1][q] > 0) {
-      if (common) sf_projection_kernel<1, 40, 52><<<g1, SF_THREADS, L1.total, ss.s[1 + q]>>>(a, L1, q);
-      else sf_projection_kernel<1, 0, 0><<<g1, SF_THREADS, L1.total, ss.s[1 + q]>>>(a, L1, q);
+      if (small) sf_projection_kernel<1, 40, 52, 6><<<g1, SF_THREADS, L1.total, ss.s[1 + q]>>>(a, L1, q);
+      else if (common) sf_projection_kernel<1, 40, 52, SF_HACC><<<g1, SF_THREADS, L1.total, ss.s[1 + q]>>>(a, L1, q);
+      else sf_projection_kernel<1, 0, 0, SF_HACC><<<g1, SF_THREADS, L1.total, ss.s[1 + q]>>>(a, L1, q);
     }
   }
   ss.join_to(stream, 3);
