@@ -251,9 +251,13 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the FAM iteration has no CPU fallback")
     torch.cuda.set_device(local)
+    saved_stdout = None
     if world > 1:
-        # keep stdout to the one JSON line: NCCL writes its version banner / debug log there unless told otherwise
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # keep stdout to the one JSON line: NCCL prints its version banner there from C code, so file descriptor 1 points
+        # to stderr until rank 0 prints the result
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     # ---- this rank's shard of the contour (independent omega points: no data-path collective) --------
@@ -370,7 +374,11 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args)
+        if saved_stdout is not None:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
         print(json.dumps(line))
+        sys.stdout.flush()
     if world > 1:
         dist.destroy_process_group()
 

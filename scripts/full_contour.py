@@ -41,8 +41,11 @@ def main():
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    saved_stdout = None
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep stdout to the JSON line
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)      # NCCL prints its banner on stdout from C code: fd 1 -> stderr until the JSON line
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     bench.SHELLS = args.shells
     wd = tempfile.mkdtemp()
@@ -61,6 +64,9 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     t = t.cpu()
+    if saved_stdout is not None:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
     if rank == 0:
         iters = int(sum(int(np.sum(f.iters)) for f in fss))
         npts = len(OPERATORS) * contour.nr_compute
