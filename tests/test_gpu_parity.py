@@ -429,3 +429,34 @@ def test_history_limit_and_contour_mode_of_the_executable(gpu, tmp_path):
     want = 4.0 + 4.0 * np.cos(np.pi + 2.0 * np.pi * np.arange(5) / 4.0)
     assert np.allclose([float(r_[1]) for r_ in rows], want, atol=1e-12)
     assert all(abs(complex(float(r_[2]), float(r_[3]))) > 0 for r_ in rows)
+
+
+def test_full_beta_decay_chain_against_beta_out(gpu, tmp_path):
+    """The whole flow the north-star names, on the GPU: all 14 (operator, K) of 40S on pynfam's contour (one batched
+    solve each) -> phase space -> shape factor -> integrated rates, against the reference's beta.out
+    (tests/S40_GT_All/000000/beta_soln).  The reference's own rate chain carries ~1e-9 of interpolation noise
+    (tests/test_rates.py), the strengths of the near-axis points 5e-8."""
+    import json
+    import os
+    from conftest import GOLDEN
+    from pynfam_b200 import rates
+    from pynfam_b200.strength import famContour, run_contours
+    wd = str(tmp_path)
+    stage_point("S40_GT_All", "GT-K0", 0, wd)
+    ops = [("F-", 0), ("GT-", 0), ("GT-", 1), ("RS0-", 0), ("PS0-", 0), ("R-", 0), ("P-", 0), ("RS1-", 0), ("R-", 1), ("P-", 1),
+           ("RS1-", 1), ("RS2-", 0), ("RS2-", 1), ("RS2-", 2)]
+    contour = famContour("CIRCLE", {"energy_min": 0.0, "energy_max": 10.476036})
+    fss = run_contours(wd, "x.in", ops, contour)
+    gold = json.load(open(os.path.join(GOLDEN, "S40_GT_All", "beta_soln.json")))
+    sf = rates.shapeFactor(fss, "-")
+    sf.calcShapeFactor({k: float(v) for k, v in gold["hfb"].items()})
+    df = sf.writeBetaOut(wd)
+    total = float(gold["rates"]["Total"]["rate"])
+    worst = 0.0
+    for k, v in gold["rates"].items():
+        err = abs(df.loc[k, "Rate(s^-1)"] - float(v["rate"])) / total
+        worst = max(worst, err)
+        assert err < 1e-8, (k, df.loc[k, "Rate(s^-1)"], v["rate"])
+    print("rates vs beta.out: worst |d rate| / total = %.2e ; total %.16e vs %s" % (worst, df.loc["Total", "Rate(s^-1)"], gold["rates"]["Total"]["rate"]))
+    assert abs(df.loc["Total", "Half-Life(s)"] / float(gold["rates"]["Total"]["halflife"]) - 1) < 1e-8
+    assert os.path.isfile(os.path.join(wd, "beta.out"))
