@@ -9,6 +9,9 @@
 //   hfbdiag + ALambda   hfbtho_solver.f90:1441-2075    -> hfbdiag / alambda
 //   DENSIT (rho only)   hfbtho_solver.f90:4318-4734    -> densit_rho
 // Written from the algorithm's description; data layouts are our own.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include "hfb_front.hpp"
 
 #include <algorithm>
@@ -785,13 +788,25 @@ HfbSolution HfbSolution::build(const HfbInput& in, const HelData& h) {
   s.hfb_cr0 = h.Crho[1]; s.hfb_crr = h.Cdrho[1]; s.hfb_cdrho = h.CrDr[1];
   s.hfb_ctau = h.Ctau[1]; s.hfb_ctj = h.CJ[1]; s.hfb_crdj = h.CrdJ[1];
   build_tables(s, h);
+  auto t0 = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (getenv("PNFAM_B200_SETUP_TIMING")) {
+      auto t1 = std::chrono::steady_clock::now();
+      std::fprintf(stderr, "[setup]   %-20s %.3f s\n", what, std::chrono::duration<double>(t1 - t0).count());
+      t0 = t1;
+    }
+  };
+  lap("basis, tables");
   gamdel(s, h);
+  lap("gamdel");
   // the blocking request is by |2*Omega| with the sign telling particle/hole
   HfbInput in2 = in;
   in2.neutron_blocking[0] = std::abs(in.neutron_blocking[0]);
   in2.proton_blocking[0] = std::abs(in.proton_blocking[0]);
   for (int it = 0; it < 2; it++) hfbdiag(s, h, in2, it, iparenti[it], in.compatibility_hfodd);
+  lap("hfbdiag");
   densit_rho(s);
+  lap("densit");
   return s;
 }
 

@@ -1,6 +1,8 @@
 #include "problem.hpp"
 
 #include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <stdexcept>
 
 namespace pnfam {
@@ -9,10 +11,21 @@ std::shared_ptr<Nucleus> Nucleus::load(const std::string& rundir) {
   auto n = std::make_shared<Nucleus>();
   const std::string d = rundir.empty() ? std::string(".") : rundir;
   // file names are hard-coded in the reference (hfbtho_interface.f90:33, hfbtho_io.f90:209)
+  auto t0 = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (getenv("PNFAM_B200_SETUP_TIMING")) {
+      auto t1 = std::chrono::steady_clock::now();
+      std::fprintf(stderr, "[setup] %-22s %.3f s\n", what, std::chrono::duration<double>(t1 - t0).count());
+      t0 = t1;
+    }
+  };
   n->hfb_in = HfbInput::read(d + "/hfbtho_NAMELIST.dat");
   n->hel = HelData::read(d + "/hfbtho_output.hel");
+  lap("read files");
   n->hfb = HfbSolution::build(n->hfb_in, n->hel);
+  lap("HFB reconstruction");
   n->basis = FamBasis::build(n->hfb);
+  lap("FAM basis and tables");
   return n;
 }
 
