@@ -16,9 +16,14 @@
 //
 // which executes 2.1x (projection) to 2.4x (density) fewer pipe cycles at 16 shells and moves no Ng x N table at all:
 // a CTA reads the rho images (density) or the field tensor of its il (projection) plus a few KB of factors.
-// FP64 FMA and DMMA share the issue port of an SM sub-partition, so the kernels run their phases
-// one after the other on all warps, separated by CTA barriers, and overlap only the operand copies (cp.async.bulk
-// completing on mbarriers, double buffered).
+// FP64 FMA and DMMA share the issue port of an SM sub-partition, so neither kernel can hide one
+// behind the other inside a warp; instead the density is warp-specialised (copy issuer / T-phase producers / DMMA
+// consumers, mbarrier hand-over) and the projection runs eight independent warp pairs per CTA whose phases drift
+// against each other.  Operand copies are cp.async.bulk completing on mbarriers.  The kernels are instantiated with
+// compile-time strides for the common 40-point Gauss-Hermite grid (the DMMA loops are instruction bound: immediates
+// instead of integer multiplies are worth 8 %), the kappa / Delta passes (a quarter of the work of rho / h) have their
+// own warp-role split and four Gauss-Laguerre nodes per iteration, and the independent launches of a stage go to
+// side streams so that they fill the SMs together when few omega points are still active.
 #include <algorithm>
 #include <vector>
 
