@@ -460,3 +460,17 @@ def test_full_beta_decay_chain_against_beta_out(gpu, tmp_path):
     print("rates vs beta.out: worst |d rate| / total = %.2e ; total %.16e vs %s" % (worst, df.loc["Total", "Rate(s^-1)"], gold["rates"]["Total"]["rate"]))
     assert abs(df.loc["Total", "Half-Life(s)"] / float(gold["rates"]["Total"]["halflife"]) - 1) < 1e-8
     assert os.path.isfile(os.path.join(wd, "beta.out"))
+
+
+def test_empty_and_single_point_batches(gpu, tmp_path):
+    """Edge cases of the batch: no omega point at all (nothing to do, no error) and a batch of one equal to the same
+    point inside a larger batch."""
+    stage_point("S40_SKOP_6sh", "GT-K0", 10, str(tmp_path))
+    p = host.Problem(str(tmp_path), "x.in")
+    ctx = gpu.Context(p)
+    r0 = ctx.solve(p, omegas=[])
+    assert r0["strength"].shape == (0, 1) and len(r0["iters"]) == 0 and r0["stats"]["iterations"] == 0
+    om = [0.58 - 2.4j, 3.0 + 1.0j, 7.0 - 0.7j]
+    rb = ctx.solve(p, omegas=om)
+    r1 = ctx.solve(p, omegas=om[1:2])
+    assert int(r1["iters"][0]) == int(rb["iters"][1]) and _rel(r1["strength"][0, 0], rb["strength"][1, 0]) < 1e-13

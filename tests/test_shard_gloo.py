@@ -109,6 +109,9 @@ def test_partition_tasks_covers_every_task_once():
         assert (cover == 1).all()
         load = [sum(len(i) for _, i in t) for t in parts]
         assert max(load) - min(load) <= 1 and max(len(t) for t in parts) <= 3
+    # fewer tasks than ranks: some ranks (possibly rank 0) hold nothing, every task is still owned exactly once
+    parts = shard.partition_tasks(1, om[:3], 8)
+    assert sorted(int(i) for t in parts for _, idx in t for i in idx) == [0, 1, 2] and sum(1 for t in parts if not t) == 5
 
 
 def test_two_rank_contour_driver_writes_the_same_files_as_one_rank(tmp_path):
