@@ -118,3 +118,32 @@ def test_beta_out_file_layout(sf, tmp_path):
     rows = [ln.split() for ln in got[13:] if ln.strip()]
     assert [r[0] for r in rows] == sf.betaout_keys
     assert abs(float(rows[0][1]) - df.loc["Total", "Rate(s^-1)"]) < 1e-18 and len(rows[0][1]) == 22
+
+
+def test_heavy_deformed_nucleus_gamow_teller_only():
+    """162Gd (Z = 64, strong Coulomb distortion, small Q value), Gamow-Teller strengths only: phase space, shape
+    factors and the rates of the reference's beta.out; the absent forbidden operators contribute exactly zero."""
+    case = os.path.join(GOLDEN, "Gd162_GT_closed_6sh")
+    d = json.load(open(os.path.join(case, "beta_soln.json")))
+    cx = lambda t: {k: np.array(v["re"], float) + 1j * np.array(v["im"], float) for k, v in t.items()}
+    ps, want = cx(d["phase_space"]), cx(d["shape_factor"])
+    fss = []
+    for k in (0, 1):
+        fs = famStrength("GT-", k, "CIRCLE")
+        fs.readCtrBinary(os.path.join(case, "fam_soln"))
+        fs.contour._settings.update(energy_min=0.0, energy_max=d["settings"]["energy_max"])
+        fss.append(fs)
+    assert fss[0].nucleus == (98, 64, 162)
+    s = rates.shapeFactor(fss, "-")
+    s.calcShapeFactor({k: float(v) for k, v in d["hfb"].items()})
+    for n in range(1, 7):
+        a, b = s.ps_df["f%d" % n], ps["f%d" % n]
+        assert np.max(np.abs(a - b)) < 2e-9 * np.max(np.abs(b)), n
+    for k in ("Total", "Allowed-GT_K=0", "Allowed-GT_K=1"):
+        assert np.max(np.abs(s.sf_df[k] - want[k])) < 2e-9 * np.max(np.abs(want[k])), k
+    df = s.calcBetaRates()
+    total = float(d["rates"]["Total"]["rate"])
+    for k, v in d["rates"].items():
+        assert abs(df.loc[k, "Rate(s^-1)"] - float(v["rate"])) < 3e-9 * total, k
+    assert df.loc["Total-Forbidden", "Rate(s^-1)"] == 0.0 and np.isinf(df.loc["Total-Forbidden", "Half-Life(s)"])
+    assert abs(df.loc["Total", "Half-Life(s)"] - 13.567947034686856) < 1e-7
