@@ -6,7 +6,7 @@ concatenating them into `OP.out` (text) and `OP.out.ctr` (Fortran-unformatted, t
 Here the whole contour of an operator is ONE batched GPU solve (`gpu.Context.solve`), and this module mirrors the
 reference-side interface around it -- same class / method names, argument meaning and file formats:
 
-    famContour      pynfam/strength/contour.py:19-340      (CIRCLE, CONSTL, CONSTR)
+    famContour      pynfam/strength/contour.py:19-677      (all seven types: CIRCLE, CONSTL, CONSTR, FERMIS, FERMIA, EXP, MONOMIAL)
     famStrength     pynfam/strength/fam_strength.py:28-680 (concatFamStr, writeStrengthOut, writeCtrBinary, readCtrBinary)
 
 so a maintainer replaces the `getFamList` + task-farm + `concatFamData` sequence by `famStrength.compute(...)`
@@ -23,14 +23,18 @@ KAPPA = 6147.0   # pynfam/config.py:225, decay constant [s]
 NSTR_MAX = 8     # strength + cross-term columns of one operator (the reference has at most 1 + 5, pnfam_extfield.f90:908-947)
 TMIN = 1e-3   # pynfam/config.py: finite temperature is not supported by this path (fails loudly in the host set-up)
 
+_INTERVAL = dict(energy_min=0.0, energy_max=6.0, hfb_emin_buff=0.0)          # pynfam/config.py:141-146
+_PROFILE = dict(hw_min=0.01, hw_max=0.4, de_hw_ratio=1.0, beta_quadrature="TRAP")
 _CONTOUR_DEFAULTS = {
-    # pynfam/config.py:147-164 (+ the energy interval keys every contour carries, :140-146)
-    "CIRCLE": dict(energy_min=0.0, energy_max=0.0, hfb_emin_buff=0.0, nr_points=60, use_gauleg_ctr=True,
-                   beta_quadrature="GAUSS", shift_imag=0.0, theta_init=np.pi, max_height=30),
-    "CONSTL": dict(energy_min=0.0, energy_max=0.0, hfb_emin_buff=0.0, nr_points=60, half_width=0.1,
-                   beta_quadrature="TRAP"),
-    "CONSTR": dict(energy_min=0.0, energy_max=0.0, hfb_emin_buff=0.0, half_width=0.1, de_hw_ratio=1.0,
-                   beta_quadrature="TRAP"),
+    # pynfam/config.py:147-196
+    "CIRCLE": dict(_INTERVAL, nr_points=60, use_gauleg_ctr=True, beta_quadrature="GAUSS", shift_imag=0.0, theta_init=np.pi,
+                   max_height=30),
+    "CONSTL": dict(_INTERVAL, nr_points=60, half_width=0.1, beta_quadrature="TRAP"),
+    "CONSTR": dict(_INTERVAL, half_width=0.1, de_hw_ratio=1.0, beta_quadrature="TRAP"),
+    "EXP": dict(_INTERVAL, p_percent_interval=-0.25, **_PROFILE),
+    "MONOMIAL": dict(_INTERVAL, power=1.0, **_PROFILE),
+    "FERMIS": dict(_INTERVAL, u_percent_interval=0.50, t_percent_interval=0.10, **_PROFILE),
+    "FERMIA": dict(_INTERVAL, nr_points_min=10, nr_points_max=70, u_percent_interval=0.50, t_percent_interval=0.10, **_PROFILE),
 }
 
 
@@ -38,14 +42,14 @@ class famContour(object):
     """Complex-energy contour and its integration data (pynfam/strength/contour.py:19-131).
 
     Args:
-        contour (str): 'CIRCLE', 'CONSTL' or 'CONSTR'.
+        contour (str): 'CIRCLE', 'CONSTL', 'CONSTR', 'FERMIS', 'FERMIA', 'EXP' or 'MONOMIAL'.
         override (dict): settings overriding the defaults (unknown keys raise KeyError, as in the reference).
     """
 
     def __init__(self, contour, override=None):
         self.name = contour.upper()
         if self.name not in _CONTOUR_DEFAULTS:
-            raise ValueError("contour type %r is not supported by this path (CIRCLE, CONSTL, CONSTR)" % contour)
+            raise ValueError("Requested contour {:} not implemented.".format(self.name))
         self._settings = dict(_CONTOUR_DEFAULTS[self.name])
         self._generateCtrData()
         if override is not None:
@@ -86,8 +90,9 @@ class famContour(object):
         self._generateCtrData()
 
     def _generateCtrData(self):
-        self._ctr_data = {"CIRCLE": self._contourCircle, "CONSTL": self._contourConstL,
-                          "CONSTR": self._contourConstR}[self.name]()
+        self._ctr_data = {"CIRCLE": self._contourCircle, "CONSTL": self._contourConstL, "CONSTR": self._contourConstR,
+                          "FERMIS": self._contourFermiS, "FERMIA": self._contourFermiA, "EXP": self._contourExp,
+                          "MONOMIAL": self._contourMonomial}[self.name]()
 
     def _contourCircle(self):
         """contour.py:212-283: circle through (energy_min, energy_max) centred on the real axis (an ellipse of height
@@ -143,6 +148,106 @@ class famContour(object):
         """contour.py:321-349: line at constant half width, nr_points equally spaced."""
         s = self._settings
         return self._line(np.linspace(s["energy_min"], s["energy_max"], s["nr_points"]))
+
+    # ---- open contours whose half width follows a profile hw(w) = a f(w) + b and whose spacing follows the half width
+    def _open(self, ctr_z):
+        n = len(ctr_z)
+        return dict(nr_points=n, nr_compute=n, use_gl_ctr=False, ctr_z=ctr_z, ctr_dzdt=np.ones(n), theta=np.zeros(n),
+                    glwts=np.zeros(n), half_width=None, quad=self._settings["beta_quadrature"], closed=False)
+
+    def _profile(self, func, anchor_at_max):
+        """March from the interval start with steps de = hw(w) |de_hw_ratio| until the end is passed, then pin the last
+        point to it (contour.py:474-520 FERMIS, 523-568 EXP, 571-617 MONOMIAL).  hw runs from hw_min to hw_max; the
+        offset b is fixed at the upper (FERMIS) or lower (EXP, MONOMIAL) end."""
+        s = self._settings
+        e0, emax = s["energy_min"], float(s["energy_max"] - s["energy_min"])
+        ratio = abs(s["de_hw_ratio"])
+        a = (s["hw_max"] - s["hw_min"]) / (func(emax) - func(0.0))
+        b = s["hw_max"] - a * func(emax) if anchor_at_max else s["hw_min"] - a * func(0.0)
+        w = np.zeros(int(np.ceil(emax / float(s["hw_min"] * ratio))) + 1)
+        i = 0
+        while True:
+            w[i + 1] = w[i] + (a * func(w[i]) + b) * ratio
+            if w[i + 1] >= emax:
+                break
+            i += 1
+        w = np.trim_zeros(w, "b")
+        w[-1] = emax
+        return self._open((w + e0) + (a * func(w) + b) * 1j)
+
+    def _fermi_profile(self):
+        s = self._settings
+        emax = float(s["energy_max"] - s["energy_min"])
+        u, t = s["u_percent_interval"] * emax, s["t_percent_interval"] * emax
+        return lambda x: 1.0 - 1.0 / (np.exp((x - u) / t) + 1.0)
+
+    def _contourFermiS(self):
+        """Static Fermi-function profile."""
+        return self._profile(self._fermi_profile(), True)
+
+    def _contourExp(self):
+        """Static exponential profile exp(w / p), p = p_percent_interval x interval."""
+        s = self._settings
+        p = s["p_percent_interval"] * float(s["energy_max"] - s["energy_min"])
+        return self._profile(lambda x: np.exp(x / p), False)
+
+    def _contourMonomial(self):
+        """Static monomial profile w^power."""
+        power = self._settings["power"]
+        if power <= 0.0:
+            raise ValueError("Monomial power must be >= 0")
+        return self._profile(lambda x: x ** power, False)
+
+    def _contourFermiA(self):
+        """Adaptive Fermi profile (contour.py:352-470): fill the interval with at most nr_points_max points, small widths
+        at small energies first -- a line at hw_min if that fits; else raise the right end of a Fermi profile, then the
+        left end, in steps of 1e-4 MeV until the marched grid reaches the end of the interval; a line at hw_max (with
+        as many points as that needs) when even that is too sparse."""
+        s = self._settings
+        e0, emax = s["energy_min"], float(s["energy_max"] - s["energy_min"])
+        hwmin, hwmax, ncap = s["hw_min"], s["hw_max"], s["nr_points_max"]
+        ratio = abs(s["de_hw_ratio"])
+        de_min, de_max = float(hwmin * ratio), float(hwmax * ratio)
+        if ncap <= int(np.ceil(emax / de_max)) + 1:
+            w = np.arange(0.0, emax + de_max, de_max)
+            return self._open((w + e0) + np.ones(len(w)) * hwmax * 1j)
+        fermi = self._fermi_profile()
+        step, shift_max = 0.0001, hwmax - hwmin
+        shift_u = shift_l = 0.0
+        a = b = 0.0
+        while True:
+            if shift_u == 0.0 and shift_l == 0.0:
+                kind = 0
+                w = np.arange(0.0, emax + de_min, de_min)
+                if len(w) < s["nr_points_min"]:
+                    w = np.linspace(0.0, emax, s["nr_points_min"])
+            elif shift_u >= shift_max and shift_l >= shift_max:
+                kind = 2
+                w = np.arange(0.0, emax + de_max, de_max)
+            else:
+                kind = 1
+                w = np.zeros(ncap)
+                for i in range(ncap - 1):
+                    hw = a * fermi(w[i]) + b
+                    if s["de_hw_ratio"] < 0:      # spacing by arc length
+                        de = np.sqrt((hw * ratio) ** 2 - (hw - (a * fermi(w[i - 1]) + b)) ** 2)
+                    else:
+                        de = hw * ratio
+                    w[i + 1] = w[i] + de
+            if w[-1] >= emax and len(w) <= ncap:
+                break
+            if shift_u < shift_max:
+                shift_u += step
+            else:
+                shift_u = shift_max
+                shift_l = min(shift_l + step, shift_max)
+            ymax, ymin = hwmin + shift_u, hwmin + shift_l
+            a = (ymax - ymin) / (fermi(emax) - fermi(0.0))
+            b = ymin - a * fermi(emax)
+        if w[-1] != emax:
+            w[-1] = emax
+        hw = np.ones(len(w)) * hwmin if kind == 0 else np.ones(len(w)) * hwmax if kind == 2 else a * fermi(w) + b
+        return self._open((w + e0) + hw * 1j)
 
 
 def patch_namelist(text, **values):

@@ -69,7 +69,7 @@ def test_line_contours_and_settings():
     with pytest.raises(KeyError):
         famContour("CIRCLE", {"no_such_key": 1})
     with pytest.raises(ValueError):
-        famContour("FERMIA")
+        famContour("SPIRAL")
     c = famContour("CIRCLE", {"energy_min": 0.0, "energy_max": 10.0, "shift_imag": 0.1})
     assert c.nr_compute == 60
     c = famContour("CIRCLE", {"energy_min": 0.0, "energy_max": 80.0, "nr_points": 9, "use_gauleg_ctr": False})
@@ -118,3 +118,21 @@ def test_integrated_rate_from_the_reference_shape_factor(col, op, k):
         complex_quadrature("BOOLE", fs.contour, sf[col])
     line = famContour("CONSTL", {"energy_min": 0.0, "energy_max": 2.0, "nr_points": 5, "half_width": 0.1})
     assert abs(complex_quadrature("TRAP", line, np.ones(5) * 1j) - 2.0j) < 1e-15
+
+
+def test_every_contour_type_against_the_reference_module():
+    """All seven contour types, default and overridden settings: the arrays the reference's own famContour produces
+    (tests/golden/contours.json, generated by importing pynfam/strength/contour.py -- tests/golden/make_contours.py)."""
+    import json
+    cases = json.load(open(os.path.join(GOLDEN, "contours.json")))["cases"]
+    assert {c["name"] for c in cases} == {"CIRCLE", "CONSTL", "CONSTR", "FERMIS", "FERMIA", "EXP", "MONOMIAL"}
+    for c in cases:
+        k = famContour(c["name"], c["override"])
+        tag = (c["name"], c["override"])
+        assert (k.nr_points, k.nr_compute, k.closed, k.quadrature) == (c["nr_points"], c["nr_compute"], c["closed"], c["quadrature"]), tag
+        assert k.name_and_int == c["name_and_int"], tag
+        z = np.array(c["re"], float) + 1j * np.array(c["im"], float)
+        dz = np.array(c["dzdt_re"], float) + 1j * np.array(c["dzdt_im"], float)
+        tol = 1e-12 if c["name"] == "CIRCLE" else 0.0        # Gauss-Legendre nodes differ in the last bits between numpy builds
+        assert np.max(np.abs(k.ctr_z - z)) <= tol * max(1.0, np.max(np.abs(z))), tag
+        assert np.max(np.abs(k.ctr_dzdt - dz)) <= tol * max(1.0, np.max(np.abs(dz))), tag
