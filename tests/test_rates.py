@@ -147,3 +147,29 @@ def test_heavy_deformed_nucleus_gamow_teller_only():
         assert abs(df.loc[k, "Rate(s^-1)"] - float(v["rate"])) < 3e-9 * total, k
     assert df.loc["Total-Forbidden", "Rate(s^-1)"] == 0.0 and np.isinf(df.loc["Total-Forbidden", "Half-Life(s)"])
     assert abs(df.loc["Total", "Half-Life(s)"] - 13.567947034686856) < 1e-7
+
+
+def test_phase_space_functions_against_the_reference_module():
+    """Fermi functions F_0 / F_1, lambda_2, real-axis integrals and the Thiele continuation for beta-minus and beta-plus
+    (negative Z, Rose screening): values produced by importing the reference's phase_space.py
+    (tests/golden/make_phase_space.py)."""
+    g = json.load(open(os.path.join(GOLDEN, "phase_space.json")))
+    w = np.array(g["w"])
+    flt = lambda v: np.array(v, float)
+    for r in g["fermi"]:
+        got = rates.Fermi(r["F"], r["Z"], r["A"], w.copy(), r["sc"])
+        assert np.allclose(got, flt(r["val"]), rtol=1e-13, atol=0), (r["F"], r["Z"], r["sc"])
+    for r in g["lambda2"]:
+        assert np.allclose(rates.lambda_ke(2, r["Z"], r["A"], w.copy(), r["sc"]), flt(r["val"]), rtol=1e-13, atol=0), r["Z"]
+    for r in g["calcPsi"]:
+        p = rates.phaseSpace(r["beta"])
+        got = p.calcPsi(r["n"], r["Z"], r["A"], np.array(r["w0"]), sc=r["sc"])
+        assert np.allclose(got, flt(r["val"]), rtol=1e-12, atol=0), (r["beta"], r["Z"], r["n"])
+    for r in g["psiFct"]:
+        p = rates.phaseSpace(r["beta"])
+        z = np.array(r["re_z"]) + 1j * np.array(r["im_z"])
+        got = p.psiFct(r["n"], r["Z"], r["A"], r["eqrpamax"], r["eqrpamin"])(z)
+        want = flt(r["re"]) + 1j * flt(r["im"])
+        # the 20-point continued fraction amplifies last-bit differences of its inputs where f_n is small: compare on
+        # the scale of the function
+        assert np.max(np.abs(got - want)) < 1e-10 * np.max(np.abs(want)), (r["beta"], r["Z"], r["n"])
