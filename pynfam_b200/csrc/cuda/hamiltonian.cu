@@ -19,6 +19,10 @@
 #include <cstdlib>
 #include <vector>
 
+#include <map>
+#include <memory>
+#include <mutex>
+
 #include "device_common.cuh"
 #include "kernels.cuh"
 
@@ -33,8 +37,15 @@ static int dev_knob(const char* name) {
 }
 
 SideStreams& side_streams() {
-  static SideStreams ss;   // one process drives one GPU
-  return ss;
+  // one set per device (streams and events belong to the device that was current when they were created)
+  static std::map<int, std::unique_ptr<SideStreams>> per_device;
+  static std::mutex guard;
+  int dev = 0;
+  PNFAM_CUDA_CHECK(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(guard);
+  std::unique_ptr<SideStreams>& p = per_device[dev];
+  if (!p) p = std::make_unique<SideStreams>();
+  return *p;
 }
 
 constexpr int BC = 32;    // columns b per chunk of the projection (8 DMMA n-tiles of 4 b x {re,im})
