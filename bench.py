@@ -28,7 +28,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-SHELLS = 16     # --shells 20 switches to tests/golden/Gd162_SKOP_20sh (BASELINE.json configs[3]/[4] basis size)
+SHELLS = 16     # --shells 12|20|24 switch to tests/golden/Gd162_SKOP_<n>sh (the basis sizes of BASELINE.json configs[3]/[4])
 
 
 def case_dir():
@@ -70,6 +70,34 @@ FAM_NML = """&general
     broyden_history_size = 50
 /
 """
+
+
+def config_of(args):
+    """The `config` object of the JSON line -- the same keys and values in both arms."""
+    return {"workload": workload(), "points_per_gpu": args.points, "shells": SHELLS, "nghl": 1600, "eps": 1e-7,
+            "broyden_history": 50, "max_iter": 300}
+
+
+def parity_sample(all_strength, conv):
+    """Outside the timed region: the strengths this run produced against the reference binary's own converged results
+    for the same sweep points (tests/golden/Gd162_SKOP_<n>sh/prod_points.json or points.json, made by
+    tests/golden/make_production.py).  Returns (max relative error on S and the cross-terms, points compared)."""
+    import numpy as np
+    for fn in ("prod_points.json", "points.json"):
+        path = os.path.join(case_dir(), fn)
+        if not os.path.isfile(path):
+            continue
+        worst, n = 0.0, 0
+        for pt in json.load(open(path))["points"].get("GT-K0", []):
+            i = pt.get("sweep_index")
+            if i is None or i >= len(all_strength) or not pt["conv"] or not conv[i]:
+                continue
+            g = complex(float(pt["rows"]["Strength"][0]), float(pt["rows"]["Strength"][1]))
+            worst = max(worst, abs(all_strength[i, 0] - g) / abs(g))
+            n += 1
+        if n:
+            return worst, n
+    return None, 0
 
 
 def circle_contour(npts, emin=0.0, emax=10.0):
@@ -208,12 +236,16 @@ def run_reference(args, rank):
             % (cores, args.ref_iters, sum(setup) / len(setup)))
     line = {
         "impl": "reference", "metric": "FAM iterations/s (omega-points/s in omega_points_per_s)", "value": ips,
-        "unit": "iterations/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * (farm[0][2] if ips_farm >= ips_threaded and farm else sum(per_iter) / max(1, n_thr)),
+        "unit": "iterations/s", "n_gpus": args.gpus,
+        # one step of this arm = one timed round of the reported mode (the rounds are bounded: every one relaunches the
+        # binary and repeats its HFB reconstruction); steps x ms_per_step is the wall time of those rounds
+        "steps": (n_farm if ips_farm >= ips_threaded and farm else n_thr), "warmup": n_warm,
+        "steps_requested": args.steps, "warmup_requested": args.warmup,
+        "ms_per_step": 1e3 * (sum(f[2] for f in farm) / len(farm) if ips_farm >= ips_threaded and farm else sum(per_iter) / max(1, n_thr) + sum(setup) / max(1, len(setup))),
         "timed_rounds": {"threaded": n_thr, "farm": n_farm},
         "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload(), "points_per_gpu": args.points, "shells": SHELLS, "nghl": 1600},
+        "config": config_of(args),
         "omega_points_per_s": ips / args.assumed_iters_per_point,
         "cpu_baseline": {"value": ips, "unit": "iterations/s", "cores": cores, "kind": "reference",
                          "sample": mode + "; per-iteration times from pnfam_main.x's own timer",
@@ -232,7 +264,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--points", type=int, default=128,
                     help="omega points per GPU (weak scaling): 128 -> 1024 at 8 GPUs, the span BASELINE.json configs[4] names")
-    ap.add_argument("--shells", type=int, default=16, choices=[16, 20], help="HO shells of the Gd162 basis (fixture)")
+    ap.add_argument("--shells", type=int, default=16, choices=[12, 16, 20, 24], help="HO shells of the Gd162 basis (fixture)")
+    ap.add_argument("--slots", type=int, default=0, help="omega points iterated side by side per GPU (0 = the library's default)")
     ap.add_argument("--ref-iters", type=int, default=4)
     ap.add_argument("--assumed-iters-per-point", type=float, default=25.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -288,7 +321,7 @@ def main():
 
     dmma_peak = gpu.dmma_peak_tflops(local)
     for _ in range(args.warmup):
-        ctx.solve(prob, omegas=mine)
+        ctx.solve(prob, omegas=mine, slots=args.slots)
     barrier()
     sampler = ClockSampler(local)
     if not os.environ.get("PNFAM_BENCH_NO_SAMPLER"):
@@ -298,7 +331,7 @@ def main():
     dens_n = proj_n = 0
     last = None
     for _ in range(args.steps):
-        r = ctx.solve(prob, omegas=mine)
+        r = ctx.solve(prob, omegas=mine, slots=args.slots)
         st = r["stats"]
         dev_s += st["seconds_device"]; iters += st["iterations"]; launches += st["kernel_launches"]
         dens_s += st["seconds_density"]; proj_s += st["seconds_projection"]
@@ -311,13 +344,13 @@ def main():
     # one untimed warm-up of the e2e path: the first context created next to a live one carves its small arrays out of
     # the pooled blocks the previous solve returned, and the 10 GB Broyden history then needs fresh device memory once
     cw = gpu.Context(prob, device=local)
-    cw.solve(prob, omegas=mine)
+    cw.solve(prob, omegas=mine, slots=args.slots)
     del cw
     for _ in range(args.steps):
         barrier()
         t0 = time.perf_counter()
         c2 = gpu.Context(prob, device=local)
-        r2 = c2.solve(prob, omegas=mine)
+        r2 = c2.solve(prob, omegas=mine, slots=args.slots)
         torch.cuda.synchronize()
         e2e_s += time.perf_counter() - t0
         if rank == 0:
@@ -340,10 +373,18 @@ def main():
     # the only exchange the path has: gather the strengths of all points (NCCL all_gather over NVLink)
     all_strength = shard.gather_strengths(my_idx, last["strength"], npts, dist=dist if world > 1 else None, device="cuda")
     assert np.isfinite(all_strength).all() and np.abs(all_strength[:, 0]).min() > 0
+    conv_all = shard.gather_strengths(my_idx, last["conv"].astype(np.float64).reshape(-1, 1), npts,
+                                      dist=dist if world > 1 else None, device="cuda")[:, 0].real > 0.5
+    iters_conv = torch.tensor([float(last["iters"][last["conv"] > 0].sum()) * args.steps, float((last["conv"] > 0).sum()) * args.steps],
+                              dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(iters_conv, op=dist.ReduceOp.SUM)
+    iters_conv = iters_conv.cpu().numpy()
     vals, sums = vals.cpu().numpy(), sums.cpu().numpy()
     if rank == 0:
         value = sums[0] / vals[0]
-        pts_per_s = sums[3] / vals[0]
+        pts_per_s = iters_conv[1] / vals[0]          # converged points only
+        par_rel, par_n = parity_sample(all_strength, conv_all)
         # roofline of the dominant kernels (tensor-bound, FP64 DMMA): algorithmic flops / CUDA-event time
         top = ("density", dens_fl, dens_s, dens_n) if dens_s >= proj_s else ("projection", proj_fl, proj_s, proj_n)
         ach = top[1] / top[2] / 1e12 if top[2] > 0 else 0.0
@@ -351,11 +392,17 @@ def main():
             "metric": "FAM iterations/s (omega-points/s in omega_points_per_s)", "value": value, "unit": "iterations/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * vals[0] / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload(), "points_per_gpu": args.points, "shells": SHELLS, "basis_states": dqp,
-                       "nghl": nghl, "nxy": nxy, "eps": 1e-7, "broyden_history": 50,
-                       "l2": "per-step working set (Broyden history 2*50*4*nxy*8 B per point = %.1f GB) >> 126 MB L2; "
-                             "no flush needed" % (len(mine) * 2 * 50 * 4 * nxy * 8 / 1e9)},
+            "config": config_of(args),
+            "problem": {"basis_states": dqp, "nxy": nxy, "batch_slots": last["stats"]["batch_slots"],
+                        "lock_steps_per_solve": last["stats"]["lock_steps"],
+                        "l2": "per-step working set (Broyden history 2*50*4*nxy*8 B per slot = %.1f GB) >> 126 MB L2; "
+                              "no flush needed" % (last["stats"]["batch_slots"] * 2 * 50 * 4 * nxy * 8 / 1e9)},
             "omega_points_per_s": pts_per_s,
+            "converged_fraction": float(conv_all.mean()),
+            "converged_iterations_fraction": float(iters_conv[0] / max(1.0, sums[0])),
+            "parity_max_rel": par_rel, "parity_points": par_n,
+            "parity_note": "strengths of this run vs the reference binary's converged results for the same sweep points "
+                           "(tests/golden/.../prod_points.json), checked outside the timed region",
             "iterations_per_point": sums[0] / sums[3],
             "iterations_per_s_per_gpu": value / world,
             "host_setup_s": setup_s,

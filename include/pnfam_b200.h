@@ -97,8 +97,12 @@ typedef struct {
 
 typedef struct {
   int32_t max_iter;             /* &solver max_iter                                          */
-  int32_t broyden_history_size; /* &solver broyden_history_size                              */
+  int32_t broyden_history_size; /* &solver broyden_history_size (any size, as the reference)  */
   double convergence_epsilon, quench_residual_int, energy_shift_prot, energy_shift_neut;
+  int32_t batch_slots;          /* omega points iterated side by side (work space = slots x per-point state);
+                                   0 = automatic: min(npoints, 64, what fits the free device memory).  Points beyond
+                                   the slot count are admitted as running ones finish; results do not depend on it */
+  int32_t reserved;             /* 0                                                         */
 } pnfam_b200_solver_params;
 
 typedef struct {
@@ -111,6 +115,8 @@ typedef struct {
   int64_t launches_density, launches_projection;
   double flops_density, flops_projection;     /* algorithmic FP64 flops of those launches: (16+4) and (20+4) x nghl x nxy
                                                  per (point, pass), SURVEY.md section 8d */
+  int32_t batch_slots;          /* slots the solve ran with                                   */
+  int32_t lock_steps;           /* lock-step iterations of the batch (>= max over points of iters) */
 } pnfam_b200_stats;
 
 /* Solve npoints complex frequencies of one operator.  Outputs (host buffers):

@@ -36,18 +36,6 @@ static int dev_knob(const char* name) {
   return k;
 }
 
-SideStreams& side_streams() {
-  // one set per device (streams and events belong to the device that was current when they were created)
-  static std::map<int, std::unique_ptr<SideStreams>> per_device;
-  static std::mutex guard;
-  int dev = 0;
-  PNFAM_CUDA_CHECK(cudaGetDevice(&dev));
-  std::lock_guard<std::mutex> lock(guard);
-  std::unique_ptr<SideStreams>& p = per_device[dev];
-  if (!p) p = std::make_unique<SideStreams>();
-  return *p;
-}
-
 constexpr int BC = 32;    // columns b per chunk of the projection (8 DMMA n-tiles of 4 b x {re,im})
 
 // ================================================================================================
@@ -181,6 +169,7 @@ void build_density_steps(int nb, const int* db, const int* pstart, const int* ns
 // chunk(step)[n = 2 b + c][k = a], spin-segment padded like the shared-memory rows, padding zero-filled.
 __global__ void __launch_bounds__(256) pack_rho_kernel(HamArgs g) {
   const int kind = blockIdx.y >> 1, q = blockIdx.y & 1, za = blockIdx.z;
+  if (g.ctrl && za >= g.ctrl->nactive) return;   // the host sizes the grid with a stale upper bound of the active slots
   const int nsteps = kind ? g.nsteps_kap[q] : g.nsteps_rho[q];
   if ((int)blockIdx.x >= nsteps) return;
   const DensStep d = (kind ? g.steps_kap[q] : g.steps_rho[q])[blockIdx.x];
@@ -227,6 +216,7 @@ __global__ void __launch_bounds__(DTHREADS, 1) density_kernel(HamArgs g, int dbg
   constexpr int NTE = MODE == 0 ? 4 : 1;      // phi_b types contracted in the epilogue
   constexpr int is_kappa = MODE;
   const int tile = blockIdx.x, q = blockIdx.y, za = blockIdx.z;
+  if (g.ctrl && za >= g.ctrl->nactive) return;   // the host sizes the grid with a stale upper bound of the active slots
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, lr = lane >> 2, lc = lane & 3;
   const DevBasis& B = g.basis;
   const DensStep* __restrict__ steps = is_kappa ? g.steps_kap[q] : g.steps_rho[q];
@@ -384,18 +374,17 @@ __global__ void __launch_bounds__(DTHREADS, 1) density_kernel(HamArgs g, int dbg
 void launch_density(const HamArgs& a, cudaStream_t stream) {
   if (a.nactive <= 0) return;
   if (a.sf.enabled) { launch_density_sf(a, stream); return; }
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceMax attr;
+  if (attr.raise(sizeof(DensSmem))) {
     PNFAM_CUDA_CHECK(cudaFuncSetAttribute(density_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DensSmem)));
     PNFAM_CUDA_CHECK(cudaFuncSetAttribute(density_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DensSmem)));
-    attr = true;
   }
   const int maxsteps = std::max(std::max(a.nsteps_rho[0], a.nsteps_rho[1]), std::max(a.nsteps_kap[0], a.nsteps_kap[1]));
   if (maxsteps > 0) pack_rho_kernel<<<dim3(maxsteps, 4, a.nactive), 256, 0, stream>>>(a);
   // development knob (timing experiments only; results are wrong when set): bit0 skips the DMMA, bit1 the epilogue,
   // bit2 the operand movement
   static const int dbg = dev_knob("PNFAM_B200_DENS_DEBUG");
-  SideStreams& ss = side_streams();
+  SideStreams& ss = *a.side;
   ss.fork_from(stream, 1);
   density_kernel<0><<<dim3(a.basis.ntiles, 2, a.nactive), DTHREADS, sizeof(DensSmem), stream>>>(a, dbg);
   density_kernel<1><<<dim3((a.basis.ntiles + 3) / 4, 2, a.nactive), DTHREADS, sizeof(DensSmem), ss.s[0]>>>(a, dbg);
@@ -415,6 +404,7 @@ __global__ void __launch_bounds__(128) fields_kernel(HamArgs g) {
   const DevBasis& B = g.basis;
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   const int q = blockIdx.y, za = blockIdx.z;
+  if (g.ctrl && za >= g.ctrl->nactive) return;   // the host sizes the grid with a stale upper bound of the active slots
   if (r >= B.nghl) return;
   const size_t Ng = B.nghl;
   const double* __restrict__ dd = g.dd_rho + ((size_t)za * 2 + q) * NDD_RHO * Ng + r;
@@ -776,6 +766,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) projection_kernel(HamArgs g, cons
   const DevBasis& B = g.basis;
   const int4 td = tiles[tile_off + blockIdx.x];
   const int ksp = blockIdx.y, za = blockIdx.z;
+  if (g.ctrl && za >= g.ctrl->nactive) return;   // the host sizes the grid with a stale upper bound of the active slots
   const int ix = td.x, a0 = td.y, b0 = td.z;
   const DevBlockStruct st = is_delta ? g.d_out[q] : g.h_out[q];
   const int iy = st.r2c[ix];
@@ -941,6 +932,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) projection_kernel(HamArgs g, cons
 __global__ void projection_reduce_kernel(HamArgs g, int ksplit) {
   const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int q = blockIdx.y >> 1, is_delta = blockIdx.y & 1, za = blockIdx.z;
+  if (g.ctrl && za >= g.ctrl->nactive) return;   // the host sizes the grid with a stale upper bound of the active slots
   if (e >= 2 * g.nxy) return;
   const int p = g.active[za];
   const double* part = g.hpart + (((size_t)za * 2 + q) * 2 + is_delta) * (size_t)ksplit * 2 * g.nxy;
@@ -957,15 +949,14 @@ size_t projection_partial_elems(const ProjPlan& pp, size_t nxy) { return (size_t
 void launch_projection(const HamArgs& a, const ProjPlan& pp, cudaStream_t stream) {
   if (a.nactive <= 0) return;
   if (a.sf.enabled) { launch_projection_sf(a, stream); return; }
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceMax attr;
+  if (attr.raise(sizeof(ProjSmem<0>))) {
     PNFAM_CUDA_CHECK(cudaFuncSetAttribute(projection_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ProjSmem<0>)));
     PNFAM_CUDA_CHECK(cudaFuncSetAttribute(projection_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ProjSmem<1>)));
-    attr = true;
   }
   // development knob (timing experiments only; results are wrong when set): bit0 skips the DMMA, bit1 the G build
   static const int dbg = dev_knob("PNFAM_B200_PROJ_DEBUG");
-  SideStreams& ss = side_streams();
+  SideStreams& ss = *a.side;
   ss.fork_from(stream, 3);
   // the two long kernels (h of both passes) first, the short ones (Delta) fill in behind them
   for (int q = 0; q < 2; q++)

@@ -41,6 +41,7 @@ __host__ __device__ constexpr int sf_mf_pair(int t, int t2) { return t == 0 ? t2
 __global__ void __launch_bounds__(256) sf_pack_kernel(HamArgs g) {
   const SfDev& S = g.sf;
   const int list = blockIdx.y, kind = list >> 1, q = list & 1, za = blockIdx.z;
+  if (g.ctrl && za >= g.ctrl->nactive) return;   // the host sizes the grid with a stale upper bound of the active slots
   if ((int)blockIdx.x >= S.nsteps[list]) return;
   const SfDensStep d = S.steps[list][blockIdx.x];
   const int p = g.active[za];
@@ -123,6 +124,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sf_density_kernel(HamArgs g, Sf
   extern __shared__ __align__(128) unsigned char smem[];
   const SfDev& S = g.sf;
   const int ilp = blockIdx.x, q = blockIdx.y, za = blockIdx.z;
+  if (g.ctrl && za >= g.ctrl->nactive) return;   // the host sizes the grid with a stale upper bound of the active slots
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, lr = lane >> 2, lc = lane & 3;
   const int list = MODE * 2 + q;
   const SfDensStep* __restrict__ steps = S.steps[list];
@@ -349,13 +351,12 @@ void launch_density_sf(const HamArgs& a, cudaStream_t stream) {
   if (a.nactive <= 0) return;
   const SfDev& S = a.sf;
   const SfDensLayout L = make_dens_layout(S);
-  static int attr_bytes = 0;
-  if (L.total > attr_bytes) {
+  static PerDeviceMax attr_bytes;
+  if (attr_bytes.raise(L.total)) {
     PNFAM_CUDA_CHECK(cudaFuncSetAttribute(sf_density_kernel<0, 0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
     PNFAM_CUDA_CHECK(cudaFuncSetAttribute(sf_density_kernel<1, 0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
     PNFAM_CUDA_CHECK(cudaFuncSetAttribute(sf_density_kernel<0, 68, 12, 52>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
     PNFAM_CUDA_CHECK(cudaFuncSetAttribute(sf_density_kernel<1, 68, 12, 52>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-    attr_bytes = L.total;
   }
   const int maxsteps = std::max(std::max(S.nsteps[0], S.nsteps[1]), std::max(S.nsteps[2], S.nsteps[3]));
   if (maxsteps > 0) sf_pack_kernel<<<dim3(maxsteps, 4, a.nactive), 256, 0, stream>>>(a);
@@ -363,7 +364,7 @@ void launch_density_sf(const HamArgs& a, cudaStream_t stream) {
   const dim3 grid(nilp, 2, a.nactive);
   // rho and kappa are independent: the kappa pass runs on a side stream, so its CTAs fill the SMs the rho pass leaves
   // idle (its tail at full batch, most of the GPU once few points are still active)
-  SideStreams& ss = side_streams();
+  SideStreams& ss = *a.side;
   ss.fork_from(stream, 1);
   if (L.ts == 68 && S.kpad_max == 12 && S.zs == 52) {          // 40-point Gauss-Hermite grid, up to 22 shells
     sf_density_kernel<0, 68, 12, 52><<<grid, SF_THREADS, L.total, stream>>>(a, L);
@@ -429,6 +430,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sf_projection_kernel(HamArgs g,
   extern __shared__ __align__(128) unsigned char smem[];
   const SfDev& S = g.sf;
   const int ksp = blockIdx.y, za = blockIdx.z;
+  if (g.ctrl && za >= g.ctrl->nactive) return;   // the host sizes the grid with a stale upper bound of the active slots
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, lr = lane >> 2, lc = lane & 3;
   const int pr = warp >> 1, h = warp & 1, l64 = h * 32 + lane;       // pair, warp of the pair, lane of the pair
   const SfProjTile td = S.tiles[MODE][q][(size_t)blockIdx.x * SF_PPAIRS + pr];
@@ -669,6 +671,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sf_projection_kernel(HamArgs g,
 __global__ void sf_projection_reduce_kernel(HamArgs g, int ksplit) {
   const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int q = blockIdx.y >> 1, is_delta = blockIdx.y & 1, za = blockIdx.z;
+  if (g.ctrl && za >= g.ctrl->nactive) return;   // the host sizes the grid with a stale upper bound of the active slots
   if (e >= 2 * g.nxy) return;
   const int p = g.active[za];
   const double* part = g.hpart + (((size_t)za * 2 + q) * 2 + is_delta) * (size_t)ksplit * 2 * g.nxy;
@@ -684,23 +687,21 @@ void launch_projection_sf(const HamArgs& a, cudaStream_t stream) {
   if (a.nactive <= 0) return;
   const SfDev& S = a.sf;
   const SfProjLayout L0 = make_proj_layout<0>(S), L1 = make_proj_layout<1>(S);
-  static int attr0 = 0, attr1 = 0;
-  if (L0.total > attr0) {
+  static PerDeviceMax attr0, attr1;
+  if (attr0.raise(L0.total)) {
     PNFAM_CUDA_CHECK(cudaFuncSetAttribute(sf_projection_kernel<0, 0, 0, SF_HACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, L0.total));
     PNFAM_CUDA_CHECK(cudaFuncSetAttribute(sf_projection_kernel<0, 40, 52, SF_HACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, L0.total));
     PNFAM_CUDA_CHECK(cudaFuncSetAttribute(sf_projection_kernel<0, 40, 52, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, L0.total));
-    attr0 = L0.total;
   }
-  if (L1.total > attr1) {
+  if (attr1.raise(L1.total)) {
     PNFAM_CUDA_CHECK(cudaFuncSetAttribute(sf_projection_kernel<1, 0, 0, SF_HACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, L1.total));
     PNFAM_CUDA_CHECK(cudaFuncSetAttribute(sf_projection_kernel<1, 40, 52, SF_HACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, L1.total));
     PNFAM_CUDA_CHECK(cudaFuncSetAttribute(sf_projection_kernel<1, 40, 52, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, L1.total));
-    attr1 = L1.total;
   }
   const bool common = S.kih == 40 && S.zs == 52;               // 40-point Gauss-Hermite grid
   const bool small = common && S.na_max <= 48;                 // spin segments of at most 48 states (up to 17 shells)
   // four independent launches (h and Delta of both passes): the long ones first, each on its own stream
-  SideStreams& ss = side_streams();
+  SideStreams& ss = *a.side;
   ss.fork_from(stream, 3);
   for (int q = 0; q < 2; q++) {
     const dim3 g0(S.ntiles[0][q] / SF_PPAIRS, S.ksplit, a.nactive);

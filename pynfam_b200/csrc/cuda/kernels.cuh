@@ -4,6 +4,31 @@
 
 namespace pnfam {
 
+// ---- batch control (device resident) --------------------------------------------------------------
+// A solve keeps S "slots" (work space of one omega point each) busy: when the point of a slot converges, the next
+// pending point is admitted into it by batch_control_kernel (mixer.cu) without the host taking part.  Every kernel of
+// the iteration indexes its work by za < nactive through active[za] = slot; the host sizes the grids with a (stale)
+// upper bound of nactive and CTAs beyond the device-side count return at once.
+struct BatchCtrl {
+  int nactive;        // slots running an iteration
+  int next_pending;   // position in the admission order of the next point to admit
+  int ndone;          // points finished (converged or interrupted at max_iter)
+  int step;           // lock-step iterations executed so far
+};
+
+// a per-device high-water mark (shared-memory attributes are per device: a process may hold contexts on several GPUs)
+struct PerDeviceMax {
+  size_t v[64] = {};
+  bool raise(size_t x) {
+    int d = 0;
+    cudaGetDevice(&d);
+    d &= 63;
+    if (x <= v[d]) return false;
+    v[d] = x;
+    return true;
+  }
+};
+
 // ---- (a)/(d) transforms ---------------------------------------------------------------------------
 struct DevicePlan {
   const DevTask* tasks = nullptr;
@@ -24,7 +49,8 @@ struct TransformArgs {
   double* scratch;                // [nactive][2][scratch_stride]
   size_t scratch_stride;
   size_t nxy;
-  const int* active;              // [nactive] point indices
+  const int* active;              // [nactive] slot indices
+  const BatchCtrl* ctrl;          // device-side active count (nullptr: the grid is exact)
 };
 
 void launch_transform(const DevicePlan& plan, const TransformArgs& args, int nactive, cudaStream_t stream);
@@ -123,6 +149,7 @@ constexpr int SF_DIL = 4;       // Gauss-Laguerre nodes per iteration of the Del
 // pf[sa][sb][il][ih][c] with SF_DIL rows of zero padding per (sa, sb): SF_DIL consecutive nodes are one linear copy
 __host__ __device__ inline size_t sf_pf_elems(int ngl, int kih) { return (size_t)4 * (ngl + SF_DIL) * kih * 2; }
 
+struct SideStreams;
 struct HamArgs {
   DevBasis basis;
   SfDev sf;
@@ -143,7 +170,9 @@ struct HamArgs {
   double* pf;                     // [nactive][2 q][pf_elems]
   double* hpart;                  // split-K partials of the projection
   const int* active;
-  int nactive;
+  int nactive;                    // grid size (upper bound of the device-side count when ctrl is given)
+  const BatchCtrl* ctrl;          // nullptr: nactive is exact
+  SideStreams* side;              // side streams of the owning context (host side only)
 };
 
 struct ProjPlan {                 // output tiles of the grid->HO projection
@@ -155,7 +184,9 @@ struct ProjPlan {                 // output tiles of the grid->HO projection
 };
 
 // Independent kernels of one stage (rho and kappa densities; h and Delta projections of both passes) run on side
-// streams forked from / joined to the caller's stream, so that the tail of one fills with CTAs of the next.
+// streams forked from / joined to the caller's stream, so that the tail of one fills with CTAs of the next.  Every
+// context owns its set (streams and events belong to the device that was current at creation; two contexts never share
+// fork / join events).
 struct SideStreams {
   static constexpr int N = 3;
   cudaStream_t s[N];
@@ -167,6 +198,12 @@ struct SideStreams {
     }
     PNFAM_CUDA_CHECK(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
   }
+  ~SideStreams() {
+    for (int i = 0; i < N; i++) { cudaStreamDestroy(s[i]); cudaEventDestroy(join[i]); }
+    cudaEventDestroy(fork);
+  }
+  SideStreams(const SideStreams&) = delete;
+  SideStreams& operator=(const SideStreams&) = delete;
   void fork_from(cudaStream_t main, int n) {
     PNFAM_CUDA_CHECK(cudaEventRecord(fork, main));
     for (int i = 0; i < n; i++) PNFAM_CUDA_CHECK(cudaStreamWaitEvent(s[i], fork, 0));
@@ -178,7 +215,6 @@ struct SideStreams {
     }
   }
 };
-SideStreams& side_streams();
 
 void launch_density(const HamArgs& a, cudaStream_t stream);
 // host helper: flatten a block structure into density pipeline steps
@@ -224,14 +260,42 @@ struct MixArgs {
   int nstr;                       // 1 + nxterms
   double* strength;               // [P][nstr][2]
   double* strpart;                // [nactive][nstr][STR_SPLIT][2] slices of the strength sums
+  double* chol;                   // [S][M][M+1] Cholesky work space in global memory, used when the history outgrows shared memory
   const int* active;
-  int nactive;
+  int nactive;                    // grid size (upper bound of the device-side count)
+  const BatchCtrl* ctrl;
+  const int* slot_iter;           // [S] iterations the point of a slot has completed (the `iter` of qrpa_broyden)
 };
+void launch_reset(const MixArgs& a, cudaStream_t stream);     // zero the amplitudes of freshly admitted slots
 void launch_greens(const MixArgs& a, cudaStream_t stream);
 int broyden_slices(size_t n);
-int broyden_max_history();       // largest broyden_history_size the dots kernel stages
 size_t strength_partial_elems(int npoints, int nstr);
-void launch_broyden(const MixArgs& a, int iter, cudaStream_t stream);
+void launch_broyden(const MixArgs& a, cudaStream_t stream);
 void launch_strength(const MixArgs& a, cudaStream_t stream);
+int broyden_launches(const MixArgs& a);
+
+// Retire / admit (one CTA, end of every lock-step iteration): for every active slot, count the iteration, publish
+// (iters, si, strengths, trace row) of its point, decide convergence (si < eps) or interruption (max_iter), hand free
+// slots to pending points in admission order, compact the active list.
+struct BatchArgs {
+  BatchCtrl* ctrl;
+  int* active;                    // [S]
+  int* slot_iter;                 // [S]
+  int* slot_point;                // [S] point held by a slot
+  const int* order;               // [P] admission order (point indices)
+  int npoints, nslots, max_iter, nstr;
+  double eps;
+  const double* si;               // [S]
+  const double* strength;         // [S][nstr][2]
+  double* omega;                  // [S][2]   frequency of the point a slot holds
+  const double* omega_pt;         // [P][2]
+  // per-point results
+  int* out_iters;                 // [P]
+  int* out_conv;                  // [P]
+  double* out_si;                 // [P]
+  double* out_strength;           // [P][nstr][2]
+  double* out_trace;              // [P][max_iter+1][4] or nullptr: si, Re S, Im S, lock-step index of the iteration
+};
+void launch_batch_control(const BatchArgs& b, cudaStream_t stream);
 
 }  // namespace pnfam

@@ -19,7 +19,7 @@ __device__ __forceinline__ size_t pack_offset(int c, int k, size_t nxy) {
 __global__ void greens_kernel(MixArgs a) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int k = blockIdx.y, za = blockIdx.z;
-  if (i >= a.nxy) return;
+  if (i >= a.nxy || za >= a.ctrl->nactive) return;
   const int p = a.active[za];
   double hre = a.fqp[(size_t)k * a.nxy + i], him = 0.0;
   if (a.quench != 0.0) {
@@ -69,10 +69,45 @@ __device__ __forceinline__ double block_max(double v, double* sh) {
   return s;
 }
 
+// Where a slot stands in the reference's mixing schedule (broyden_method, pnfam_broyden.f90:117-216) after `iter`
+// completed iterations of its point: iteration 0 (or M <= 0) mixes linearly, later ones run the modified Broyden update
+// on a ring of M history slots.
+struct BroPos {
+  bool broyden;
+  int iter_used, ipos, inext;   // history vectors in use, 0-based slot of the newest difference, slot written next
+};
+__device__ __forceinline__ BroPos bro_pos(int iter, int M) {
+  BroPos b{false, 0, -1, 0};
+  if (M <= 0 || iter == 0) return b;
+  b.broyden = true;
+  b.iter_used = iter - 1 < M ? iter - 1 : M;
+  b.ipos = iter - 1 - ((iter - 2) / M) * M - 1;   // Fortran integer arithmetic (truncation toward zero), 1-based -> 0-based
+  b.inext = iter - ((iter - 1) / M) * M - 1;
+  return b;
+}
+
+// amplitudes of freshly admitted points start from zero (pnfam_solver.f90:63-71 without storage)
+__global__ void __launch_bounds__(256) reset_kernel(MixArgs a) {
+  const int za = blockIdx.y;
+  if (za >= a.ctrl->nactive) return;
+  const int p = a.active[za];
+  if (a.slot_iter[p] != 0) return;
+  double* v = a.vin + (size_t)p * a.n;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < a.n; e += (size_t)gridDim.x * blockDim.x) v[e] = 0.0;
+}
+void launch_reset(const MixArgs& a, cudaStream_t stream) {
+  if (a.nactive <= 0) return;
+  reset_kernel<<<dim3(64, a.nactive), 256, 0, stream>>>(a);
+}
+
 // vout <- vout - vin ; si partial ; (iter>=2) raw difference vectors into slot ipos + partial |df|^2
-__global__ void __launch_bounds__(256) bro_diff_kernel(MixArgs a, int ipos) {
+__global__ void __launch_bounds__(256) bro_diff_kernel(MixArgs a) {
   __shared__ double sh[8];
-  const int za = blockIdx.y, p = a.active[za];
+  const int za = blockIdx.y;
+  if (za >= a.ctrl->nactive) return;
+  const int p = a.active[za], iter = a.slot_iter[p];
+  const BroPos bp = bro_pos(iter, a.Mmode);
+  const int ipos = (bp.broyden && iter >= 2) ? bp.ipos : -1;
   double* vo = a.vout + (size_t)p * a.n;
   const double* vi = a.vin + (size_t)p * a.n;
   double* dfp = ipos >= 0 ? a.df + ((size_t)p * a.M + ipos) * a.n : nullptr;
@@ -98,6 +133,7 @@ __global__ void __launch_bounds__(256) bro_diff_kernel(MixArgs a, int ipos) {
 }
 
 __global__ void bro_finalize_kernel(MixArgs a) {
+  if ((int)blockIdx.x >= a.ctrl->nactive) return;
   const int p = a.active[blockIdx.x];
   if (threadIdx.x == 0) {
     double mx = 0.0, ss = 0.0;
@@ -111,8 +147,12 @@ __global__ void bro_finalize_kernel(MixArgs a) {
 }
 
 // no mixing (M<0): vin = vout_new ; linear: vin += alpha*(vout_new - vin).  vout holds the difference.
-__global__ void bro_linear_kernel(MixArgs a, double alpha) {
-  const int za = blockIdx.y, p = a.active[za];
+__global__ void bro_linear_kernel(MixArgs a) {
+  const int za = blockIdx.y;
+  if (za >= a.ctrl->nactive) return;
+  const int p = a.active[za];
+  if (bro_pos(a.slot_iter[p], a.Mmode).broyden) return;
+  const double alpha = (a.Mmode < 0) ? 1.0 : a.alpha;
   const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= a.n) return;
   a.vin[(size_t)p * a.n + e] += alpha * a.vout[(size_t)p * a.n + e];
@@ -121,12 +161,18 @@ __global__ void bro_linear_kernel(MixArgs a, double alpha) {
 // dots of the (raw) newest difference vector and of vout with every stored df_i.  One CTA owns a slice of BRO_SLICE
 // elements of one point: the slices of df_new and vout stay in registers while the CTA streams the same slice of every
 // history vector once (8 independent 8-byte loads per thread in flight), so the history is read exactly once per
-// iteration at HBM rate.  Slice partials are summed in a fixed order by bro_solve_kernel (deterministic).
+// iteration at HBM rate.  Slice partials are summed in a fixed order by bro_solve_kernel (deterministic).  The warp
+// partials of BRO_CHUNK history vectors at a time are staged in shared memory (any history size).
 constexpr int BRO_SLICE = 2048;
-constexpr int BRO_MMAX = 64;     // history slots the shared staging of the dots kernel holds
-__global__ void __launch_bounds__(256) bro_dots_kernel(MixArgs a, int ipos, int iter_used) {
-  __shared__ double sh[BRO_MMAX][8][2];
-  const int sl = blockIdx.x, za = blockIdx.y, p = a.active[za];
+constexpr int BRO_CHUNK = 64;
+__global__ void __launch_bounds__(256) bro_dots_kernel(MixArgs a) {
+  __shared__ double sh[BRO_CHUNK][8][2];
+  const int sl = blockIdx.x, za = blockIdx.y;
+  if (za >= a.ctrl->nactive) return;
+  const int p = a.active[za];
+  const BroPos bp = bro_pos(a.slot_iter[p], a.Mmode);
+  if (!bp.broyden || bp.iter_used == 0) return;
+  const int ipos = bp.ipos, iter_used = bp.iter_used;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const size_t e0 = (size_t)sl * BRO_SLICE + threadIdx.x;
   const double* __restrict__ dfp = a.df + (size_t)p * a.M * a.n;
@@ -139,37 +185,48 @@ __global__ void __launch_bounds__(256) bro_dots_kernel(MixArgs a, int ipos, int 
     fn[j] = e < a.n ? dfn[e] : 0.0;
     v[j] = e < a.n ? vo[e] : 0.0;
   }
-  for (int i = 0; i < iter_used; i++) {
-    const double* __restrict__ dfi = dfp + (size_t)i * a.n;
-    double f[8];
+  for (int c0 = 0; c0 < iter_used; c0 += BRO_CHUNK) {
+    const int c1 = min(iter_used, c0 + BRO_CHUNK);
+    for (int i = c0; i < c1; i++) {
+      const double* __restrict__ dfi = dfp + (size_t)i * a.n;
+      double f[8];
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-      const size_t e = e0 + (size_t)j * 256;
-      f[j] = e < a.n ? dfi[e] : 0.0;
-    }
-    double s1 = 0.0, s2 = 0.0;
+      for (int j = 0; j < 8; j++) {
+        const size_t e = e0 + (size_t)j * 256;
+        f[j] = e < a.n ? dfi[e] : 0.0;
+      }
+      double s1 = 0.0, s2 = 0.0;
 #pragma unroll
-    for (int j = 0; j < 8; j++) { s1 += f[j] * fn[j]; s2 += f[j] * v[j]; }
-    for (int o = 16; o > 0; o >>= 1) {
-      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      for (int j = 0; j < 8; j++) { s1 += f[j] * fn[j]; s2 += f[j] * v[j]; }
+      for (int o = 16; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      }
+      if (lane == 0) { sh[i - c0][warp][0] = s1; sh[i - c0][warp][1] = s2; }
     }
-    if (lane == 0) { sh[i][warp][0] = s1; sh[i][warp][1] = s2; }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < iter_used; i += blockDim.x) {
-    double s1 = 0.0, s2 = 0.0;
-    for (int w = 0; w < 8; w++) { s1 += sh[i][w][0]; s2 += sh[i][w][1]; }
-    double* part = a.dotpart + (((size_t)p * a.M + i) * a.nslices + sl) * 2;
-    part[0] = s1; part[1] = s2;
+    __syncthreads();
+    for (int i = c0 + threadIdx.x; i < c1; i += blockDim.x) {
+      double s1 = 0.0, s2 = 0.0;
+      for (int w = 0; w < 8; w++) { s1 += sh[i - c0][w][0]; s2 += sh[i - c0][w][1]; }
+      double* part = a.dotpart + (((size_t)p * a.M + i) * a.nslices + sl) * 2;
+      part[0] = s1; part[1] = s2;
+    }
+    __syncthreads();
   }
 }
 
-// gamma = B^{-1} work, B = Gram + w0^2 on the diagonal (SPD): Cholesky in shared memory by one CTA (M <= 64)
-__global__ void bro_solve_kernel(MixArgs a, int ipos, int iter_used) {
-  extern __shared__ double L[];
+// gamma = B^{-1} work, B = Gram + w0^2 on the diagonal (SPD): Cholesky by one CTA, in shared memory while the factor fits
+// (BRO_SOLVE_SMEM_N history vectors), else in the global work space a.chol (the reference: DSYTRF/DSYTRI, any M)
+constexpr int BRO_SOLVE_SMEM_N = 64;
+__global__ void bro_solve_kernel(MixArgs a) {
+  extern __shared__ double Lsh[];
+  if ((int)blockIdx.x >= a.ctrl->nactive) return;
   const int p = a.active[blockIdx.x];
-  const int n = iter_used, M = a.M;
+  const BroPos bp = bro_pos(a.slot_iter[p], a.Mmode);
+  if (!bp.broyden || bp.iter_used == 0) return;
+  const int ipos = bp.ipos;
+  const int n = bp.iter_used, M = a.M;
+  double* L = n <= BRO_SOLVE_SMEM_N ? Lsh : a.chol + (size_t)p * M * (M + 2);
   double* G = a.gram + (size_t)p * M * M;
   // finish the dots: sum the slice partials in a fixed order; df_ipos is still un-normalised in memory, so the dots
   // with it are scaled instead
@@ -230,8 +287,13 @@ __global__ void bro_solve_kernel(MixArgs a, int ipos, int iter_used) {
 }
 
 // curv = alpha*vout - sum_i gamma_i (dv_i + alpha df_i); store (vout, vin) in slot inext; vin += curv
-__global__ void __launch_bounds__(256) bro_update_kernel(MixArgs a, int ipos, int inext, int iter_used) {
-  const int za = blockIdx.y, p = a.active[za];
+__global__ void __launch_bounds__(256) bro_update_kernel(MixArgs a) {
+  const int za = blockIdx.y;
+  if (za >= a.ctrl->nactive) return;
+  const int p = a.active[za];
+  const BroPos bp = bro_pos(a.slot_iter[p], a.Mmode);
+  if (!bp.broyden) return;
+  const int ipos = bp.ipos, inext = bp.inext, iter_used = bp.iter_used;
   const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= a.n) return;
   const double alpha = a.alpha;
@@ -255,32 +317,22 @@ __global__ void __launch_bounds__(256) bro_update_kernel(MixArgs a, int ipos, in
   a.vin[(size_t)p * a.n + e] = vi + curv;
 }
 
-void launch_broyden(const MixArgs& a, int iter, cudaStream_t stream) {
+// Every slot is at its own iteration, so all stages are launched every lock step and each CTA looks up what its slot
+// needs (linear mixing for a fresh point, the Broyden update otherwise).
+void launch_broyden(const MixArgs& a, cudaStream_t stream) {
   if (a.nactive <= 0) return;
-  const int M = a.Mmode;
   const unsigned nblk = (unsigned)((a.n + 255) / 256);
-  int iter_used = 0, ipos = -1, inext = 0;
-  const bool broyden = !(M < 0 || M == 0 || iter == 0);
-  if (broyden) {
-    iter_used = iter - 1 < M ? iter - 1 : M;
-    ipos = iter - 1 - ((iter - 2) / M) * M;   // 1-based slot, Fortran integer arithmetic (truncation toward zero)
-    inext = iter - ((iter - 1) / M) * M;
-    ipos -= 1; inext -= 1;                    // 0-based
-  }
-  bro_diff_kernel<<<dim3(a.nred, a.nactive), 256, 0, stream>>>(a, (broyden && iter >= 2) ? ipos : -1);
+  bro_diff_kernel<<<dim3(a.nred, a.nactive), 256, 0, stream>>>(a);
   bro_finalize_kernel<<<a.nactive, 32, 0, stream>>>(a);
-  if (!broyden) {
-    const double alpha = (M < 0) ? 1.0 : a.alpha;
-    bro_linear_kernel<<<dim3(nblk, a.nactive), 256, 0, stream>>>(a, alpha);
-    return;
-  }
-  if (iter_used > 0) {
-    bro_dots_kernel<<<dim3(a.nslices, a.nactive), 256, 0, stream>>>(a, ipos, iter_used);
-    const size_t sh = ((size_t)iter_used * (iter_used + 1) + iter_used) * sizeof(double);
-    bro_solve_kernel<<<a.nactive, 128, sh, stream>>>(a, ipos, iter_used);
-  }
-  bro_update_kernel<<<dim3(nblk, a.nactive), 256, 0, stream>>>(a, ipos, inext, iter_used);
+  bro_linear_kernel<<<dim3(nblk, a.nactive), 256, 0, stream>>>(a);
+  if (a.Mmode <= 0) return;
+  bro_dots_kernel<<<dim3(a.nslices, a.nactive), 256, 0, stream>>>(a);
+  const int ns = a.Mmode < BRO_SOLVE_SMEM_N ? a.Mmode : BRO_SOLVE_SMEM_N;
+  const size_t sh = ((size_t)ns * (ns + 1) + ns) * sizeof(double);
+  bro_solve_kernel<<<a.nactive, 128, sh, stream>>>(a);
+  bro_update_kernel<<<dim3(nblk, a.nactive), 256, 0, stream>>>(a);
 }
+int broyden_launches(const MixArgs& a) { return a.Mmode <= 0 ? 3 : 6; }
 
 // ---- strength function ----------------------------------------------------------------------------------
 // S = -(1/pi) F . dR (contract_bbm, pnfam_solver.f90:196-203): STR_SPLIT CTAs per (operator, point) sum slices of the
@@ -288,7 +340,9 @@ void launch_broyden(const MixArgs& a, int iter, cudaStream_t stream) {
 constexpr int STR_SPLIT = 32;
 __global__ void __launch_bounds__(256) strength_kernel(MixArgs a) {
   __shared__ double sh[8];
-  const int k = blockIdx.x, za = blockIdx.y, sp = blockIdx.z, p = a.active[za];
+  const int k = blockIdx.x, za = blockIdx.y, sp = blockIdx.z;
+  if (za >= a.ctrl->nactive) return;
+  const int p = a.active[za];
   const double* g = a.gqp + (size_t)k * 4 * a.nxy;
   const double* v = a.vin + (size_t)p * a.n;
   const int nq = a.nvec / 2;
@@ -312,8 +366,9 @@ __global__ void __launch_bounds__(256) strength_kernel(MixArgs a) {
   }
 }
 __global__ void strength_final_kernel(MixArgs a) {
-  const int k = blockIdx.x, za = blockIdx.y, p = a.active[za];
-  if (threadIdx.x != 0) return;
+  const int k = blockIdx.x, za = blockIdx.y;
+  if (threadIdx.x != 0 || za >= a.ctrl->nactive) return;
+  const int p = a.active[za];
   const double* part = a.strpart + ((size_t)za * a.nstr + k) * STR_SPLIT * 2;
   double sre = 0.0, sim = 0.0;
   for (int s = 0; s < STR_SPLIT; s++) { sre += part[2 * s]; sim += part[2 * s + 1]; }
@@ -322,13 +377,60 @@ __global__ void strength_final_kernel(MixArgs a) {
   a.strength[((size_t)p * a.nstr + k) * 2 + 1] = -sim / pi;
 }
 int broyden_slices(size_t n) { return (int)((n + BRO_SLICE - 1) / BRO_SLICE); }
-int broyden_max_history() { return BRO_MMAX; }
 size_t strength_partial_elems(int npoints, int nstr) { return (size_t)npoints * nstr * STR_SPLIT * 2; }
 
 void launch_strength(const MixArgs& a, cudaStream_t stream) {
   if (a.nactive <= 0) return;
   strength_kernel<<<dim3(a.nstr, a.nactive, STR_SPLIT), 256, 0, stream>>>(a);
   strength_final_kernel<<<dim3(a.nstr, a.nactive), 32, 0, stream>>>(a);
+}
+
+// ---- retire / admit -------------------------------------------------------------------------------------
+// One CTA.  Thread za handles active slot za: counts the iteration (ifam's iter, pnfam_solver.f90:114-209), publishes the
+// state of its point and decides whether it is finished (si < eps: converged; max_iter reached: interrupted).  Thread 0
+// then hands the free slots to the pending points in admission order and compacts the active list (stable, serial: the
+// slot a point lands in never changes its result, the order is kept only for reproducible scheduling).
+__global__ void __launch_bounds__(1024) batch_control_kernel(BatchArgs b) {
+  __shared__ int done[1024];
+  const int nact = b.ctrl->nactive, step = b.ctrl->step;
+  for (int za = threadIdx.x; za < nact; za += blockDim.x) {
+    const int s = b.active[za], p = b.slot_point[s];
+    const int it = b.slot_iter[s] + 1;
+    b.slot_iter[s] = it;
+    const double si = b.si[s];
+    b.out_iters[p] = it;
+    b.out_si[p] = si;
+    for (int k = 0; k < 2 * b.nstr; k++) b.out_strength[(size_t)p * 2 * b.nstr + k] = b.strength[(size_t)s * 2 * b.nstr + k];
+    if (b.out_trace) {
+      double* t = b.out_trace + ((size_t)p * (b.max_iter + 1) + it) * 4;
+      t[0] = si; t[1] = b.strength[(size_t)s * 2 * b.nstr]; t[2] = b.strength[(size_t)s * 2 * b.nstr + 1]; t[3] = (double)step;
+    }
+    const bool conv = si < b.eps;
+    if (conv) b.out_conv[p] = 1;
+    done[za] = (conv || it >= b.max_iter) ? 1 : 0;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int n = 0, next = b.ctrl->next_pending, ndone = b.ctrl->ndone;
+    for (int za = 0; za < nact; za++) {
+      const int s = b.active[za];
+      if (done[za]) {
+        ndone++;
+        if (next >= b.npoints) continue;            // nothing pending: the slot leaves the batch
+        const int p = b.order[next++];
+        b.slot_point[s] = p;
+        b.slot_iter[s] = 0;
+        b.omega[2 * s] = b.omega_pt[2 * p];
+        b.omega[2 * s + 1] = b.omega_pt[2 * p + 1];
+      }
+      b.active[n++] = s;
+    }
+    b.ctrl->nactive = n; b.ctrl->next_pending = next; b.ctrl->ndone = ndone; b.ctrl->step = step + 1;
+  }
+}
+void launch_batch_control(const BatchArgs& b, cudaStream_t stream) {
+  if (b.nslots > 1024) throw std::runtime_error("batch control: more than 1024 slots");
+  batch_control_kernel<<<1, 1024, 0, stream>>>(b);
 }
 
 }  // namespace pnfam

@@ -5,6 +5,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <mutex>
+#include <numeric>
 #include <vector>
 
 #include "../../../include/pnfam_b200.h"
@@ -20,16 +22,47 @@ namespace pnfam {
 // returned instead of going back to the driver.  All allocations and frees are ordered on the legacy default
 // stream, with which the (blocking) work stream of a context synchronises implicitly.
 inline void keep_pool_memory() {
-  static bool done = false;
-  if (done) return;
+  static bool done[64] = {};
+  static std::mutex guard;
   int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return;
+  std::lock_guard<std::mutex> lock(guard);
+  if (done[dev & 63]) return;
   cudaMemPool_t pool;
-  if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
     unsigned long long keep = ~0ull;
     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
   }
-  done = true;
+  done[dev & 63] = true;
 }
+// bytes a solve may still allocate on the current device: free device memory + what the pool holds but does not use
+inline size_t device_bytes_available() {
+  size_t fr = 0, tot = 0;
+  PNFAM_CUDA_CHECK(cudaMemGetInfo(&fr, &tot));
+  int dev = 0;
+  cudaMemPool_t pool;
+  unsigned long long reserved = 0, used = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess &&
+      cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
+      cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used)
+    fr += (size_t)(reserved - used);
+  return fr;
+}
+struct Event {
+  cudaEvent_t e = nullptr;
+  Event() { PNFAM_CUDA_CHECK(cudaEventCreate(&e)); }
+  ~Event() { if (e) cudaEventDestroy(e); }
+  Event(const Event&) = delete;
+  Event& operator=(const Event&) = delete;
+};
+template <class T>
+struct PinnedBuf {
+  T* p = nullptr;
+  explicit PinnedBuf(size_t n) { PNFAM_CUDA_CHECK(cudaMallocHost(&p, n * sizeof(T))); std::memset(p, 0, n * sizeof(T)); }
+  ~PinnedBuf() { if (p) cudaFreeHost(p); }
+  PinnedBuf(const PinnedBuf&) = delete;
+  PinnedBuf& operator=(const PinnedBuf&) = delete;
+};
 template <class T>
 struct DBuf {
   T* p = nullptr;
@@ -98,8 +131,10 @@ struct pnfam_b200_ctx {
   DBuf<double> d_zt, d_rg, d_rgp;
   DBuf<int> d_zrow, d_p2l, d_slot, d_segtab;
   cudaStream_t stream = nullptr;
+  std::unique_ptr<SideStreams> side;   // side streams + fork/join events of this context
   int64_t launches = 0;
   int64_t table_h2d_bytes = 0;   // bytes of basis tables uploaded by ctx_create
+  std::shared_ptr<void> ham_ws;  // persistent work space of pnfam_b200_calc_hamiltonian (HamWorkspace below)
 };
 
 // Set-up of the sum-factorised path from the separable factors of the model (include/pnfam_b200.h).  Returns false
@@ -219,10 +254,21 @@ static void require_device(int device) {
   if (device < 0 || device >= n) throw std::runtime_error("invalid CUDA device index");
   PNFAM_CUDA_CHECK(cudaSetDevice(device));
 }
+// Every entry point works on the device of its context and hands the caller's current device back on return.
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    require_device(device);
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
 
 extern "C" int pnfam_b200_ctx_create(const pnfam_b200_model* m, int device, pnfam_b200_ctx** out, char* err, int errlen) {
   try {
-    require_device(device);
+    DeviceGuard dg(device);
     auto c = std::make_unique<pnfam_b200_ctx>();
     c->device = device;
     c->nb = m->nb; c->dqp = m->dqp; c->nghl = m->nghl;
@@ -287,6 +333,7 @@ extern "C" int pnfam_b200_ctx_create(const pnfam_b200_model* m, int device, pnfa
     B.cdrho = m->cdrho; B.ctau = m->ctau; B.ctj0 = m->ctj0; B.ctj1 = m->ctj1; B.ctj2 = m->ctj2; B.crdj = m->crdj;
     B.cds = m->cds; B.ct = m->ct; B.cj = m->cj; B.cgs = m->cgs; B.cf = m->cf; B.csdj = m->csdj;
     PNFAM_CUDA_CHECK(cudaStreamCreate(&c->stream));
+    c->side = std::make_unique<SideStreams>();
     *out = c.release();
     return 0;
   } catch (const std::exception& e) {
@@ -304,9 +351,14 @@ extern "C" int64_t pnfam_b200_ctx_h2d_bytes(const pnfam_b200_ctx* c) {
 
 extern "C" void pnfam_b200_ctx_destroy(pnfam_b200_ctx* c) {
   if (!c) return;
+  int prev = -1;
+  if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
   cudaSetDevice(c->device);
+  c->ham_ws.reset();
+  c->side.reset();
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
+  if (prev >= 0) cudaSetDevice(prev);
 }
 
 // ---- per-operator device data ----------------------------------------------------------------------
@@ -486,7 +538,23 @@ void build_proj_tiles(const pnfam_b200_ctx& c, const BlockStruct st[2], std::vec
   }
 }
 
-std::unique_ptr<OperatorDev> make_operator(pnfam_b200_ctx& c, const pnfam_b200_operator& op, int npoints) {
+// split-K factors of the projection for a batch of `nslots` slots (sizes the partial sums)
+void set_batch_slots(const pnfam_b200_ctx& c, OperatorDev& od, int nslots) {
+  const int S = std::max(1, nslots);
+  if (c.sf.enabled) {
+    // split-K factor as a function of the slots still active (the batch shrinks when the queue has drained): at least
+    // two waves of CTAs per launch.  proj.ksplit sizes the partials for the largest nactive x ksplit(nactive).
+    od.sf_ksplit = sf_ksplit_for(c, od, S);
+    int need = od.sf_ksplit * S;
+    for (int n = 1; n <= S; n++) need = std::max(need, n * sf_ksplit_for(c, od, n));
+    od.proj.ksplit = (need + S - 1) / S;
+  } else {
+    const int per = std::max(1, od.proj.ntiles_h[0] * S);
+    od.proj.ksplit = std::min(std::min(c.ntiles, 32), std::max(1, (2 * 148 + per - 1) / per));
+  }
+}
+
+std::unique_ptr<OperatorDev> make_operator(pnfam_b200_ctx& c, const pnfam_b200_operator& op) {
   auto od = std::make_unique<OperatorDev>();
   std::vector<int> ir2c(op.f_ir2c, op.f_ir2c + c.nb);
   od->plan = make_operator_plan(c.db, ir2c, c.use_diag, op.beta_minus != 0);
@@ -503,12 +571,6 @@ std::unique_ptr<OperatorDev> make_operator(pnfam_b200_ctx& c, const pnfam_b200_o
     upload_sf_proj_tiles(c, od->plan.hsp[3], od->sf_tiles[0][1], od->sf_ntiles[0][1]);
     upload_sf_proj_tiles(c, od->plan.hsp[1], od->sf_tiles[1][0], od->sf_ntiles[1][0]);
     upload_sf_proj_tiles(c, od->plan.hsp[2], od->sf_tiles[1][1], od->sf_ntiles[1][1]);
-    // split-K factor as a function of the points still active (the batch shrinks as points converge): at least two
-    // waves of CTAs per launch.  proj.ksplit sizes the partials for the largest nactive x ksplit(nactive).
-    od->sf_ksplit = sf_ksplit_for(c, *od, std::max(1, npoints));
-    int need = od->sf_ksplit * std::max(1, npoints);
-    for (int n = 1; n <= std::max(1, npoints); n++) need = std::max(need, n * sf_ksplit_for(c, *od, n));
-    od->proj.ksplit = (need + std::max(1, npoints) - 1) / std::max(1, npoints);
     return od;
   }
   od->pk_rho = std::max(upload_density_steps(c, od->plan.sp[0], od->dsteps[0], od->ndsteps[0]),
@@ -523,8 +585,6 @@ std::unique_ptr<OperatorDev> make_operator(pnfam_b200_ctx& c, const pnfam_b200_o
     build_proj_tiles(c, sd, td, od->proj.ntiles_d, od->proj.tile_off_d);
     od->tiles_h.upload(th); od->tiles_d.upload(td);
     od->proj.tiles_h = od->tiles_h.p; od->proj.tiles_d = od->tiles_d.p;
-    const int per = std::max(1, od->proj.ntiles_h[0] * std::max(1, npoints));
-    od->proj.ksplit = std::min(std::min(c.ntiles, 32), std::max(1, (2 * 148 + per - 1) / per));
   }
   return od;
 }
@@ -547,6 +607,7 @@ HamArgs make_ham_args(const pnfam_b200_ctx& c, const OperatorDev& od) {
   }
   h.pk_stride_rho = od.pk_rho; h.pk_stride_kap = od.pk_kap;
   h.sf = c.sf;
+  h.side = c.side.get();
   if (c.sf.enabled) {
     for (int k = 0; k < 4; k++) { h.sf.steps[k] = od.sf_steps[k].p; h.sf.nsteps[k] = od.sf_nsteps[k]; }
     for (int m = 0; m < 2; m++)
@@ -565,12 +626,18 @@ extern "C" int pnfam_b200_solve(pnfam_b200_ctx* c, const pnfam_b200_operator* op
                                 char* err, int errlen) {
   try {
     Timer wall;
-    require_device(c->device);
+    DeviceGuard dg(c->device);
     cudaStream_t st = c->stream;
     const int P = npoints;
     if (P <= 0) return 0;
+    if (stats) std::memset(stats, 0, sizeof(*stats));
+    if (prm->max_iter <= 0) {                      // ifam's loop body never runs: amplitudes and strengths stay zero
+      for (int p = 0; p < P; p++) { iters[p] = 0; conv[p] = 0; si_out[p] = 1.0; }
+      std::fill(strength, strength + (size_t)P * (1 + op->nxterms) * 2, 0.0);
+      return 0;
+    }
     int64_t launches = 0, h2d = 0, d2h = 0;
-    auto od = make_operator(*c, *op, P);
+    auto od = make_operator(*c, *op);
     const size_t nxy = od->plan.nxy;
     const int nvec = c->use_diag ? 8 : 4, nq = nvec / 2;
     const size_t n = (size_t)nvec * nxy;
@@ -579,8 +646,40 @@ extern "C" int pnfam_b200_solve(pnfam_b200_ctx* c, const pnfam_b200_operator* op
     const bool no_residual = std::fabs(quench) < 1e-10;
     const int M = no_residual ? -1 : prm->broyden_history_size;
     const int Malloc = std::max(M, 1);
-    if (M > broyden_max_history()) throw std::runtime_error("broyden_history_size above the " + std::to_string(broyden_max_history()) + " slots the device mixer stages");
     const bool bminus = op->beta_minus != 0;
+    const bool sf = c->sf.enabled != 0;
+    const int nred = 64;
+    const int max_iter = std::max(1, (int)prm->max_iter);
+
+    // ---- slots: the work space of one omega point each; points beyond the slot count wait in the admission queue --
+    const size_t mf_e = sf ? sf_mf_elems(c->sf.ngl, c->sf.kih) : mf_elems(c->ntiles);
+    const size_t pf_e = sf ? sf_pf_elems(c->sf.ngl, c->sf.kih) : pf_elems(c->ntiles);
+    auto slot_doubles = [&]() {
+      size_t d = 2 * n;                                                        // vin, vout
+      if (M > 0) d += 2 * (size_t)Malloc * n;                                  // Broyden history
+      d += (size_t)Malloc * Malloc + 2 * (size_t)Malloc + (size_t)Malloc * broyden_slices(n) * 2;
+      if (M > 64) d += (size_t)Malloc * (Malloc + 2);
+      d += (size_t)nred * 2 + 4 + (size_t)nstr * 2 + strength_partial_elems(1, nstr);
+      d += 3 * 8 * nxy;                                                        // rsp, hsp, hqp
+      d += 2 * std::max<size_t>(od->scratch_elems, 1);
+      d += (size_t)2 * NDD_RHO * c->nghl + (size_t)2 * NDD_KAP * c->nghl + 2 * mf_e + 2 * pf_e;
+      d += 2 * std::max<size_t>(od->pk_rho, 1) + 2 * std::max<size_t>(od->pk_kap, 1);
+      return d;
+    };
+    int S = std::min(P, 1024);
+    {
+      int cap = prm->batch_slots > 0 ? prm->batch_slots : 0;
+      if (const char* e = getenv("PNFAM_B200_SLOTS")) cap = atoi(e);
+      if (cap <= 0) cap = 64;                                                  // measured plateau of the throughput
+      S = std::min(S, cap);
+      const double avail = 0.92 * (double)device_bytes_available();
+      for (;;) {
+        set_batch_slots(*c, *od, S);
+        const double need = 8.0 * ((double)S * (double)slot_doubles() + (double)S * (double)projection_partial_elems(od->proj, nxy));
+        if (need <= avail || S == 1) break;
+        S = std::max(1, std::min(S - 1, (int)(S * avail / need)));
+      }
+    }
 
     // ---- static per-operator tables ---------------------------------------------------------------
     std::vector<double> Ea = bminus ? c->Ep : c->En, Eb = bminus ? c->En : c->Ep;
@@ -611,51 +710,62 @@ extern "C" int pnfam_b200_solve(pnfam_b200_ctx* c, const pnfam_b200_operator* op
       h2d += (int64_t)(es.size() + tf.size()) * 8;
     }
 
-    // ---- per-point state ---------------------------------------------------------------------------------
-    DBuf<double> vin, vout, df, dv, gram, work, gamma, dotpart, red, d_si, d_normi, d_omega, d_str, d_strpart;
+    // ---- per-slot state -----------------------------------------------------------------------------
+    DBuf<double> vin, vout, df, dv, gram, work, gamma, dotpart, chol, red, d_si, d_normi, d_omega, d_str, d_strpart;
     DBuf<double> rsp, hsp, hqp, scratch, dd_rho, dd_kap, mf, pf, hpart, pk_rho, pk_kap;
-    DBuf<int> d_active;
-    const int nred = 64;
-    vin.alloc((size_t)P * n); vout.alloc((size_t)P * n);
+    vin.alloc((size_t)S * n); vout.alloc((size_t)S * n);
     vin.zero(); vout.zero();
     // Broyden history: only slots that have been written are ever read (iter_used bounds every loop): no clearing
-    if (M > 0) { df.alloc((size_t)P * Malloc * n); dv.alloc((size_t)P * Malloc * n); }
-    gram.alloc((size_t)P * Malloc * Malloc); work.alloc((size_t)P * Malloc); gamma.alloc((size_t)P * Malloc);
+    if (M > 0) { df.alloc((size_t)S * Malloc * n); dv.alloc((size_t)S * Malloc * n); }
+    gram.alloc((size_t)S * Malloc * Malloc); work.alloc((size_t)S * Malloc); gamma.alloc((size_t)S * Malloc);
     gram.zero(); work.zero(); gamma.zero();
-    dotpart.alloc((size_t)P * Malloc * broyden_slices(n) * 2);
-    red.alloc((size_t)P * nred * 2); d_si.alloc(P); d_normi.alloc(P); d_omega.alloc((size_t)P * 2);
-    d_str.alloc((size_t)P * nstr * 2); d_strpart.alloc(strength_partial_elems(P, nstr));
-    rsp.alloc((size_t)P * 8 * nxy); hsp.alloc((size_t)P * 8 * nxy); hqp.alloc((size_t)P * 8 * nxy);
+    dotpart.alloc((size_t)S * Malloc * broyden_slices(n) * 2);
+    if (M > 64) chol.alloc((size_t)S * Malloc * (Malloc + 2));
+    red.alloc((size_t)S * nred * 2); d_si.alloc(S); d_normi.alloc(S); d_omega.alloc((size_t)S * 2);
+    d_str.alloc((size_t)S * nstr * 2); d_strpart.alloc(strength_partial_elems(S, nstr));
+    rsp.alloc((size_t)S * 8 * nxy); hsp.alloc((size_t)S * 8 * nxy); hqp.alloc((size_t)S * 8 * nxy);
     rsp.zero(); hsp.zero(); hqp.zero();
-    scratch.alloc((size_t)P * 2 * std::max<size_t>(od->scratch_elems, 1));
-    dd_rho.alloc((size_t)P * 2 * NDD_RHO * c->nghl); dd_kap.alloc((size_t)P * 2 * NDD_KAP * c->nghl);
+    scratch.alloc((size_t)S * 2 * std::max<size_t>(od->scratch_elems, 1));
+    dd_rho.alloc((size_t)S * 2 * NDD_RHO * c->nghl); dd_kap.alloc((size_t)S * 2 * NDD_KAP * c->nghl);
     // field tensors are tile-major (kernels.cuh); the padding grid points are zeroed once and never written
-    const bool sf = c->sf.enabled != 0;
-    mf.alloc((size_t)P * 2 * (sf ? sf_mf_elems(c->sf.ngl, c->sf.kih) : mf_elems(c->ntiles)));
-    pf.alloc((size_t)P * 2 * (sf ? sf_pf_elems(c->sf.ngl, c->sf.kih) : pf_elems(c->ntiles)));
+    mf.alloc((size_t)S * 2 * mf_e); pf.alloc((size_t)S * 2 * pf_e);
     mf.zero(); pf.zero();
     if (sf) { dd_rho.zero(); dd_kap.zero(); }             // (s, s') sweeps without any step are never written
-    pk_rho.alloc((size_t)P * 2 * std::max<size_t>(od->pk_rho, 1)); pk_kap.alloc((size_t)P * 2 * std::max<size_t>(od->pk_kap, 1));
-    hpart.alloc((size_t)P * projection_partial_elems(od->proj, nxy));
-    d_active.alloc(P);
+    pk_rho.alloc((size_t)S * 2 * std::max<size_t>(od->pk_rho, 1)); pk_kap.alloc((size_t)S * 2 * std::max<size_t>(od->pk_kap, 1));
+    hpart.alloc((size_t)S * projection_partial_elems(od->proj, nxy));
+
+    // ---- batch control: admission order (the points that need the most iterations -- small |Im omega| -- first, so
+    //      that the batch drains with the short ones), slot tables, per-point results -----------------------------
+    std::vector<int> order(P);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return std::fabs(omega_im[a]) < std::fabs(omega_im[b]); });
+    DBuf<int> d_active, d_slot_iter, d_slot_point, d_order, d_iters, d_conv;
+    DBuf<double> d_omega_pt, d_out_si, d_out_str, d_trace;
+    DBuf<BatchCtrl> d_ctrl;
+    const int tstride = (max_iter + 1) * 4;
     {
-      std::vector<double> w(2 * (size_t)P);
+      std::vector<int> act(S), sp(S), zero_s(S, 0), zero_p(P, 0);
+      std::vector<double> w(2 * (size_t)P), ws(2 * (size_t)S);
       for (int p = 0; p < P; p++) { w[2 * p] = omega_re[p]; w[2 * p + 1] = omega_im[p]; }
-      PNFAM_CUDA_CHECK(cudaMemcpy(d_omega.p, w.data(), w.size() * 8, cudaMemcpyHostToDevice));
-      h2d += (int64_t)w.size() * 8;
+      for (int s = 0; s < S; s++) { act[s] = s; sp[s] = order[s]; ws[2 * s] = w[2 * order[s]]; ws[2 * s + 1] = w[2 * order[s] + 1]; }
+      d_active.upload(act); d_slot_point.upload(sp); d_slot_iter.upload(zero_s); d_order.upload(order);
+      d_iters.upload(zero_p); d_conv.upload(zero_p);
+      d_omega_pt.upload(w); d_omega.upload(ws);
+      d_out_si.upload(std::vector<double>(P, 1.0));
+      d_out_str.alloc((size_t)P * nstr * 2); d_out_str.zero();
+      if (trace) { d_trace.alloc((size_t)P * tstride); d_trace.zero(); }
+      d_ctrl.upload(std::vector<BatchCtrl>(1, BatchCtrl{S, S, 0, 0}));
+      h2d += (int64_t)w.size() * 8 + (int64_t)ws.size() * 8 + (int64_t)(3 * S + 3 * P) * 4;
     }
-    std::vector<int> active(P);
-    for (int p = 0; p < P; p++) active[p] = p;
-    PNFAM_CUDA_CHECK(cudaMemcpy(d_active.p, active.data(), P * sizeof(int), cudaMemcpyHostToDevice));
 
     TransformArgs ta{};
     if (bminus) { ta.W[0] = c->d_Up.p; ta.W[1] = c->d_Vp.p; ta.W[2] = c->d_Un.p; ta.W[3] = c->d_Vn.p; }
     else { ta.W[0] = c->d_Un.p; ta.W[1] = c->d_Vn.p; ta.W[2] = c->d_Up.p; ta.W[3] = c->d_Vp.p; }
     ta.scratch = scratch.p; ta.scratch_stride = std::max<size_t>(od->scratch_elems, 1);
-    ta.nxy = nxy; ta.active = d_active.p;
+    ta.nxy = nxy; ta.active = d_active.p; ta.ctrl = d_ctrl.p;
 
     // ---- F and cross-term fields -> quasiparticle basis (pnfam_solver.f90:368-382): backward transform of
-    //      dHsp = [f 0; 0 0] (real flavour), one field at a time through point slot 0.
+    //      dHsp = [f 0; 0 0] (real flavour), one field at a time through slot 0.
     od->gqp.alloc((size_t)nstr * 4 * nxy);
     od->gqp.zero();
     for (int k = 0; k < nstr; k++) {
@@ -677,110 +787,124 @@ extern "C" int pnfam_b200_solve(pnfam_b200_ctx* c, const pnfam_b200_operator* op
     ha.rsp = rsp.p; ha.hsp = hsp.p; ha.dd_rho = dd_rho.p; ha.dd_kap = dd_kap.p; ha.mf = mf.p; ha.pf = pf.p;
     ha.pk_rho = pk_rho.p; ha.pk_kap = pk_kap.p;
     ha.sf.pk[0] = pk_rho.p; ha.sf.pk[1] = pk_kap.p;
-    ha.hpart = hpart.p; ha.active = d_active.p;
+    ha.hpart = hpart.p; ha.active = d_active.p; ha.ctrl = d_ctrl.p;
 
     MixArgs ma{};
     ma.nvec = nvec; ma.nxy = nxy; ma.n = n; ma.M = Malloc; ma.Mmode = M; ma.alpha = (double)0.7f; ma.w0 = 0.01;
     ma.hqp = hqp.p; ma.fqp = od->gqp.p; ma.esum = od->esum.p; ma.tfac = c->use_diag ? od->tfac.p : nullptr;
     ma.omega = d_omega.p; ma.quench = no_residual ? 0.0 : quench;
     ma.vin = vin.p; ma.vout = vout.p; ma.df = df.p; ma.dv = dv.p; ma.gram = gram.p; ma.work = work.p; ma.gamma = gamma.p;
-    ma.dotpart = dotpart.p; ma.nslices = broyden_slices(n);
+    ma.dotpart = dotpart.p; ma.nslices = broyden_slices(n); ma.chol = chol.p;
     ma.red = red.p; ma.nred = nred; ma.si = d_si.p; ma.normi = d_normi.p; ma.gqp = od->gqp.p; ma.nstr = nstr;
-    ma.strength = d_str.p; ma.strpart = d_strpart.p; ma.active = d_active.p;
+    ma.strength = d_str.p; ma.strpart = d_strpart.p; ma.active = d_active.p; ma.ctrl = d_ctrl.p; ma.slot_iter = d_slot_iter.p;
 
-    std::vector<double> h_si(P, 1.0), h_str((size_t)P * nstr * 2, 0.0);
-    for (int p = 0; p < P; p++) { iters[p] = 0; conv[p] = 0; si_out[p] = 1.0; }
-    for (size_t i = 0; i < (size_t)P * nstr * 2; i++) strength[i] = 0.0;
-    const int tstride = (prm->max_iter + 1) * 4;
-    if (trace) {
-      std::fill(trace, trace + (size_t)P * tstride, 0.0);
-      for (int p = 0; p < P; p++) trace[(size_t)p * tstride] = 1.0;
-    }
+    BatchArgs ba{};
+    ba.ctrl = d_ctrl.p; ba.active = d_active.p; ba.slot_iter = d_slot_iter.p; ba.slot_point = d_slot_point.p; ba.order = d_order.p;
+    ba.npoints = P; ba.nslots = S; ba.max_iter = max_iter; ba.nstr = nstr; ba.eps = prm->convergence_epsilon;
+    ba.si = d_si.p; ba.strength = d_str.p; ba.omega = d_omega.p; ba.omega_pt = d_omega_pt.p;
+    ba.out_iters = d_iters.p; ba.out_conv = d_conv.p; ba.out_si = d_out_si.p; ba.out_strength = d_out_str.p;
+    ba.out_trace = trace ? d_trace.p : nullptr;
 
-    cudaEvent_t ev0, ev1, evd0, evd1, evp0, evp1;
-    PNFAM_CUDA_CHECK(cudaEventCreate(&ev0)); PNFAM_CUDA_CHECK(cudaEventCreate(&ev1));
-    PNFAM_CUDA_CHECK(cudaEventCreate(&evd0)); PNFAM_CUDA_CHECK(cudaEventCreate(&evd1));
-    PNFAM_CUDA_CHECK(cudaEventCreate(&evp0)); PNFAM_CUDA_CHECK(cudaEventCreate(&evp1));
-    PNFAM_CUDA_CHECK(cudaEventRecord(ev0, st));
+    // ---- the loop of ifam (pnfam_solver.f90:114-209), all active slots in lock step.  The host never drains the
+    //      stream inside the loop: it runs LAG steps ahead of the device and reads the control block of step k (a copy in
+    //      pinned memory, completion known from an event) while steps k+1 .. k+LAG are queued.  The grids are sized with
+    //      that stale -- never too small: the active count does not grow -- number of active slots.
+    constexpr int LAG = 2, RING = LAG + 2;
+    struct StepRec { Event done, d0, d1, p0, p1; bool timed = false; };
+    StepRec ring[RING];
+    PinnedBuf<BatchCtrl> snap(RING);
+    Event ev0, ev1;
+    PNFAM_CUDA_CHECK(cudaEventRecord(ev0.e, st));
     double t_dens = 0, t_proj = 0;
-    int64_t n_dens = 0, n_proj = 0, total_iters = 0;
-    double fl_dens = 0, fl_proj = 0;
-    int nactive = P;
-    // the loop of ifam (pnfam_solver.f90:114-209) for all still-active points in lock step
-    for (int it = 0; it < prm->max_iter && nactive > 0; it++) {
-      Timer titer;
-      ha.nactive = nactive; ma.nactive = nactive;
-      if (sf) ha.sf.ksplit = sf_ksplit_for(*c, *od, nactive);
+    int64_t n_dens = 0, n_proj = 0;
+    std::vector<float> step_ms;
+    int nact = S, launched = 0, harvested = 0;
+    bool finished = false;
+    auto harvest = [&](int k) {
+      StepRec& r = ring[k % RING];
+      PNFAM_CUDA_CHECK(cudaEventSynchronize(r.done.e));
+      float ms = 0;
+      if (r.timed) {
+        cudaEventElapsedTime(&ms, r.d0.e, r.d1.e); t_dens += ms * 1e-3;
+        cudaEventElapsedTime(&ms, r.p0.e, r.p1.e); t_proj += ms * 1e-3;
+      }
+      cudaEventElapsedTime(&ms, k == 0 ? ev0.e : ring[(k - 1) % RING].done.e, r.done.e);
+      step_ms.push_back(ms);
+      const BatchCtrl& bc = snap.p[k % RING];
+      nact = std::min(nact, bc.nactive);
+      if (bc.nactive == 0) finished = true;
+      d2h += (int64_t)sizeof(BatchCtrl);
+    };
+    const int64_t max_steps = (int64_t)max_iter * ((P + S - 1) / S + 1) + LAG + 1;   // cannot be reached; guards the loop
+    while (!finished && launched < max_steps) {
+      StepRec& r = ring[launched % RING];
+      ha.nactive = nact; ma.nactive = nact;
+      if (sf) ha.sf.ksplit = sf_ksplit_for(*c, *od, nact);
+      launch_reset(ma, st);
+      launches += 1;
+      r.timed = !no_residual;
       if (!no_residual) {
         TransformArgs f = ta;
         f.in = vin.p; f.in_pstride = n; f.in_pack = 1;
         f.out = rsp.p; f.out_pstride = 8 * nxy; f.out_pack = 0;
-        launch_transform(od->fwd, f, nactive, st);
-        PNFAM_CUDA_CHECK(cudaEventRecord(evd0, st));
+        launch_transform(od->fwd, f, nact, st);
+        PNFAM_CUDA_CHECK(cudaEventRecord(r.d0.e, st));
         launch_density(ha, st);
-        PNFAM_CUDA_CHECK(cudaEventRecord(evd1, st));
+        PNFAM_CUDA_CHECK(cudaEventRecord(r.d1.e, st));
         launch_fields(ha, st);
-        PNFAM_CUDA_CHECK(cudaEventRecord(evp0, st));
+        PNFAM_CUDA_CHECK(cudaEventRecord(r.p0.e, st));
         launch_projection(ha, od->proj, st);
-        PNFAM_CUDA_CHECK(cudaEventRecord(evp1, st));
+        PNFAM_CUDA_CHECK(cudaEventRecord(r.p1.e, st));
         TransformArgs b = ta;
         b.in = hsp.p; b.in_pstride = 8 * nxy; b.in_pack = 0;
         b.out = hqp.p; b.out_pstride = 8 * nxy; b.out_pack = 0;
-        launch_transform(od->bwd, b, nactive, st);
+        launch_transform(od->bwd, b, nact, st);
         launches += 2 + 3 + 1 + 5 + 2;   // transform, pack + 2 densities, fields, 4 projections + reduce, transform
         n_dens += 2; n_proj += 4;
-        fl_dens += (double)nactive * 2.0 * 20.0 * c->nghl * (double)nxy;
-        fl_proj += (double)nactive * 2.0 * 24.0 * c->nghl * (double)nxy;
       }
       launch_greens(ma, st);
-      launch_broyden(ma, it, st);
+      launch_broyden(ma, st);
       launch_strength(ma, st);
-      launches += 1 + 5 + 2;
-      PNFAM_CUDA_CHECK(cudaMemcpyAsync(h_si.data(), d_si.p, P * sizeof(double), cudaMemcpyDeviceToHost, st));
-      PNFAM_CUDA_CHECK(cudaMemcpyAsync(h_str.data(), d_str.p, (size_t)P * nstr * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
-      PNFAM_CUDA_CHECK(cudaStreamSynchronize(st));
-      d2h += (int64_t)P * 8 + (int64_t)P * nstr * 16;
-      if (!no_residual) {
-        float ms = 0;
-        cudaEventElapsedTime(&ms, evd0, evd1); t_dens += ms * 1e-3;
-        cudaEventElapsedTime(&ms, evp0, evp1); t_proj += ms * 1e-3;
-      }
-      const double dt = titer.s();
-      std::vector<int> next;
-      for (int za = 0; za < nactive; za++) {
-        const int p = active[za];
-        total_iters++;
-        iters[p] = it + 1;
-        si_out[p] = h_si[p];
-        for (int k = 0; k < nstr * 2; k++) strength[(size_t)p * nstr * 2 + k] = h_str[(size_t)p * nstr * 2 + k];
-        if (trace) {
-          double* t = trace + (size_t)p * tstride + (size_t)(it + 1) * 4;
-          t[0] = h_si[p]; t[1] = h_str[(size_t)p * nstr * 2]; t[2] = h_str[(size_t)p * nstr * 2 + 1]; t[3] = dt;
-        }
-        if (h_si[p] < prm->convergence_epsilon) conv[p] = 1;
-        else next.push_back(p);
-      }
-      if (next.size() != (size_t)nactive) {
-        active = next;
-        nactive = (int)active.size();
-        if (nactive > 0) {
-          PNFAM_CUDA_CHECK(cudaMemcpyAsync(d_active.p, active.data(), nactive * sizeof(int), cudaMemcpyHostToDevice, st));
-          h2d += nactive * 4;
-        }
-      }
+      launch_batch_control(ba, st);
+      launches += 1 + broyden_launches(ma) + 2 + 1;
+      PNFAM_CUDA_CHECK(cudaMemcpyAsync(&snap.p[launched % RING], d_ctrl.p, sizeof(BatchCtrl), cudaMemcpyDeviceToHost, st));
+      PNFAM_CUDA_CHECK(cudaEventRecord(r.done.e, st));
+      launched++;
+      if (launched - harvested > LAG) harvest(harvested++);
     }
-    PNFAM_CUDA_CHECK(cudaEventRecord(ev1, st));
+    while (harvested < launched) harvest(harvested++);
+    if (!finished) throw std::runtime_error("solve: the batch did not drain (internal error)");
+    PNFAM_CUDA_CHECK(cudaEventRecord(ev1.e, st));
+    // ---- results ------------------------------------------------------------------------------------
+    PNFAM_CUDA_CHECK(cudaMemcpyAsync(iters, d_iters.p, (size_t)P * sizeof(int), cudaMemcpyDeviceToHost, st));
+    PNFAM_CUDA_CHECK(cudaMemcpyAsync(conv, d_conv.p, (size_t)P * sizeof(int), cudaMemcpyDeviceToHost, st));
+    PNFAM_CUDA_CHECK(cudaMemcpyAsync(si_out, d_out_si.p, (size_t)P * sizeof(double), cudaMemcpyDeviceToHost, st));
+    PNFAM_CUDA_CHECK(cudaMemcpyAsync(strength, d_out_str.p, (size_t)P * nstr * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (trace) PNFAM_CUDA_CHECK(cudaMemcpyAsync(trace, d_trace.p, (size_t)P * tstride * sizeof(double), cudaMemcpyDeviceToHost, st));
     PNFAM_CUDA_CHECK(cudaStreamSynchronize(st));
+    PNFAM_CUDA_CHECK(cudaGetLastError());
+    d2h += (int64_t)P * (8 + 8 + nstr * 16) + (trace ? (int64_t)P * tstride * 8 : 0);
+    int64_t total_iters = 0;
+    for (int p = 0; p < P; p++) total_iters += iters[p];
+    if (trace)
+      for (int p = 0; p < P; p++) {
+        double* t = trace + (size_t)p * tstride;
+        t[0] = 1.0;
+        for (int it = 1; it <= iters[p]; it++) {   // lock-step index -> seconds of that step
+          const int k = (int)t[(size_t)it * 4 + 3];
+          t[(size_t)it * 4 + 3] = (k >= 0 && k < (int)step_ms.size()) ? step_ms[k] * 1e-3 : 0.0;
+        }
+      }
     float ms = 0;
-    cudaEventElapsedTime(&ms, ev0, ev1);
-    cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(evd0); cudaEventDestroy(evd1);
-    cudaEventDestroy(evp0); cudaEventDestroy(evp1);
+    cudaEventElapsedTime(&ms, ev0.e, ev1.e);
     if (stats) {
       stats->seconds_total = wall.s(); stats->seconds_device = ms * 1e-3; stats->iterations = total_iters;
       stats->kernel_launches = launches; stats->h2d_bytes = h2d; stats->d2h_bytes = d2h;
       stats->seconds_density = t_dens; stats->seconds_projection = t_proj;
       stats->launches_density = n_dens; stats->launches_projection = n_proj;
-      stats->flops_density = fl_dens; stats->flops_projection = fl_proj;
+      stats->flops_density = no_residual ? 0.0 : (double)total_iters * 2.0 * 20.0 * c->nghl * (double)nxy;
+      stats->flops_projection = no_residual ? 0.0 : (double)total_iters * 2.0 * 24.0 * c->nghl * (double)nxy;
+      stats->batch_slots = S; stats->lock_steps = launched;
     }
     c->launches += launches;
     return 0;
@@ -791,99 +915,145 @@ extern "C" int pnfam_b200_solve(pnfam_b200_ctx* c, const pnfam_b200_operator* op
 }
 
 // ---- calc_hamiltonian-shaped entry -----------------------------------------------------------------------
+// Work space of the plug-in entry, kept in the context between calls: the FAM loop of the reference calls
+// calc_hamiltonian once per iteration with the SAME eight block structures (they are preset once per solve,
+// pnfam_solver.f90:402-413), so step lists, tile lists and all device buffers are built on the first call and reused
+// while the structures do not change; a call then costs the 8 + 8 element copies and the kernels.
+namespace {
+struct HamWorkspace {
+  std::vector<int> key;           // the 8 + 8 (ir2c, ir2m) arrays and nelem the work space was built for
+  size_t nxy = 0;
+  DevStructBuf sin[4], sout[4];
+  DBuf<double> rsp, hsp, dd_rho, dd_kap, mf, pf, hpart, pk_rho, pk_kap;
+  DBuf<int> d_active;
+  DBuf<DensStep> dsteps[4];
+  DBuf<SfDensStep> sf_steps[4];
+  DBuf<SfProjTile> sf_tiles[2][2];
+  DBuf<int4> th, td;
+  ProjPlan pp;
+  HamArgs h{};
+  PinnedBuf<double> stage;        // pinned staging of the 16 element arrays
+  explicit HamWorkspace(size_t nxy_) : nxy(nxy_), stage(16 * nxy_) {}
+};
+
+std::vector<int> ham_key(const pnfam_b200_ctx& c, const pnfam_b200_blockmatrix in[8], const pnfam_b200_blockmatrix out[8]) {
+  std::vector<int> k;
+  k.reserve((size_t)16 * (2 * c.nb + 1));
+  for (int io = 0; io < 2; io++)
+    for (int i = 0; i < 8; i++) {
+      const pnfam_b200_blockmatrix& b = io ? out[i] : in[i];
+      k.push_back((int)b.nelem);
+      k.insert(k.end(), b.ir2c, b.ir2c + c.nb);
+      k.insert(k.end(), b.ir2m, b.ir2m + c.nb);
+    }
+  return k;
+}
+
+std::shared_ptr<HamWorkspace> build_ham_workspace(pnfam_b200_ctx* c, const pnfam_b200_blockmatrix in[8],
+                                                  const pnfam_b200_blockmatrix out[8]) {
+  size_t nxy = 0;
+  for (int i = 0; i < 8; i++) nxy = std::max(nxy, (size_t)std::max(in[i].nelem, out[i].nelem));
+  auto w = std::make_shared<HamWorkspace>(std::max<size_t>(nxy, 1));
+  w->key = ham_key(*c, in, out);
+  auto mk = [&](const pnfam_b200_blockmatrix& b, DevStructBuf& d, BlockStruct& hs) {
+    hs.r2c.assign(c->nb, -1); hs.r2m.assign(c->nb, -1); hs.allocated = true;
+    for (int i = 0; i < c->nb; i++) if (b.ir2c[i] > 0) { hs.r2c[i] = b.ir2c[i] - 1; hs.r2m[i] = b.ir2m[i] - 1; }
+    d.upload(hs);
+  };
+  // argument order -> (pass, kind): in: rho_pn(0,1) k+(2,3) rho_np(4,5) k-(6,7); storage quads 0,1,3,2
+  BlockStruct hin[4], hout[4];
+  for (int pr = 0; pr < 4; pr++) { mk(in[2 * pr], w->sin[pr], hin[pr]); mk(out[2 * pr], w->sout[pr], hout[pr]); }
+  w->rsp.alloc(8 * nxy); w->hsp.alloc(8 * nxy); w->rsp.zero(); w->hsp.zero();
+  HamArgs& h = w->h;
+  h.basis = c->basis;
+  h.rho_in[0] = w->sin[0].view(); h.kap_in[0] = w->sin[1].view(); h.rho_in[1] = w->sin[2].view(); h.kap_in[1] = w->sin[3].view();
+  h.h_out[0] = w->sout[0].view(); h.d_out[0] = w->sout[1].view(); h.h_out[1] = w->sout[2].view(); h.d_out[1] = w->sout[3].view();
+  h.rho_quad[0] = 0; h.kap_quad[0] = 1; h.rho_quad[1] = 3; h.kap_quad[1] = 2;
+  h.nxy = nxy;
+  const bool sf = c->sf.enabled != 0;
+  ProjPlan& pp = w->pp;
+  h.sf = c->sf;
+  h.side = c->side.get();
+  h.ctrl = nullptr;
+  if (sf) {
+    // argument pairs: 0 rho_pn (pass 0), 1 kappa+ (pass 0), 2 rho_np (pass 1), 3 kappa- (pass 1)
+    h.pk_stride_rho = std::max(upload_sf_density_steps(*c, hin[0], w->sf_steps[0], h.sf.nsteps[0]), upload_sf_density_steps(*c, hin[2], w->sf_steps[1], h.sf.nsteps[1]));
+    h.pk_stride_kap = std::max(upload_sf_density_steps(*c, hin[1], w->sf_steps[2], h.sf.nsteps[2]), upload_sf_density_steps(*c, hin[3], w->sf_steps[3], h.sf.nsteps[3]));
+    for (int k = 0; k < 4; k++) h.sf.steps[k] = w->sf_steps[k].p;
+    upload_sf_proj_tiles(*c, hout[0], w->sf_tiles[0][0], h.sf.ntiles[0][0]);
+    upload_sf_proj_tiles(*c, hout[2], w->sf_tiles[0][1], h.sf.ntiles[0][1]);
+    upload_sf_proj_tiles(*c, hout[1], w->sf_tiles[1][0], h.sf.ntiles[1][0]);
+    upload_sf_proj_tiles(*c, hout[3], w->sf_tiles[1][1], h.sf.ntiles[1][1]);
+    for (int m = 0; m < 2; m++)
+      for (int q = 0; q < 2; q++) h.sf.tiles[m][q] = w->sf_tiles[m][q].p;
+    h.sf.ksplit = std::min(c->sf.ngl, std::max(1, (2 * 148 + std::max(1, h.sf.ntiles[0][0] / 8) - 1) / std::max(1, h.sf.ntiles[0][0] / 8)));
+    pp.ksplit = h.sf.ksplit;
+    h.sf.pk_stride[0] = h.pk_stride_rho; h.sf.pk_stride[1] = h.pk_stride_kap;
+  } else {
+    int ndsteps[4];
+    h.pk_stride_rho = std::max(upload_density_steps(*c, hin[0], w->dsteps[0], ndsteps[0]), upload_density_steps(*c, hin[2], w->dsteps[1], ndsteps[1]));
+    h.pk_stride_kap = std::max(upload_density_steps(*c, hin[1], w->dsteps[2], ndsteps[2]), upload_density_steps(*c, hin[3], w->dsteps[3], ndsteps[3]));
+    for (int q = 0; q < 2; q++) {
+      h.steps_rho[q] = w->dsteps[q].p; h.nsteps_rho[q] = ndsteps[q];
+      h.steps_kap[q] = w->dsteps[2 + q].p; h.nsteps_kap[q] = ndsteps[2 + q];
+    }
+    std::vector<int4> vh, vd;
+    BlockStruct shh[2] = {hout[0], hout[2]}, sdd[2] = {hout[1], hout[3]};
+    build_proj_tiles(*c, shh, vh, pp.ntiles_h, pp.tile_off_h);
+    build_proj_tiles(*c, sdd, vd, pp.ntiles_d, pp.tile_off_d);
+    w->th.upload(vh); w->td.upload(vd);
+    pp.tiles_h = w->th.p; pp.tiles_d = w->td.p;
+    const int per = std::max(1, pp.ntiles_h[0]);
+    pp.ksplit = std::min(std::min(c->ntiles, 32), std::max(1, (2 * 148 + per - 1) / per));
+  }
+  w->pk_rho.alloc(2 * std::max<size_t>(h.pk_stride_rho, 1)); w->pk_kap.alloc(2 * std::max<size_t>(h.pk_stride_kap, 1));
+  h.pk_rho = w->pk_rho.p; h.pk_kap = w->pk_kap.p;
+  h.sf.pk[0] = w->pk_rho.p; h.sf.pk[1] = w->pk_kap.p;
+  w->dd_rho.alloc((size_t)2 * NDD_RHO * c->nghl); w->dd_kap.alloc((size_t)2 * NDD_KAP * c->nghl);
+  w->dd_rho.zero(); w->dd_kap.zero();
+  w->mf.alloc((size_t)2 * (sf ? sf_mf_elems(c->sf.ngl, c->sf.kih) : mf_elems(c->ntiles)));
+  w->pf.alloc((size_t)2 * (sf ? sf_pf_elems(c->sf.ngl, c->sf.kih) : pf_elems(c->ntiles)));
+  w->mf.zero(); w->pf.zero();
+  w->hpart.alloc(projection_partial_elems(pp, nxy));
+  w->d_active.upload(std::vector<int>{0});
+  h.rsp = w->rsp.p; h.hsp = w->hsp.p; h.dd_rho = w->dd_rho.p; h.dd_kap = w->dd_kap.p; h.mf = w->mf.p; h.pf = w->pf.p; h.hpart = w->hpart.p;
+  h.active = w->d_active.p; h.nactive = 1;
+  return w;
+}
+}  // namespace
+
 extern "C" int pnfam_b200_calc_hamiltonian(pnfam_b200_ctx* c, const pnfam_b200_blockmatrix in[8], pnfam_b200_blockmatrix out[8],
                                            char* err, int errlen) {
   try {
-    require_device(c->device);
+    DeviceGuard dg(c->device);
     cudaStream_t st = c->stream;
-    size_t nxy = 0;
-    for (int i = 0; i < 8; i++) nxy = std::max(nxy, (size_t)std::max(in[i].nelem, out[i].nelem));
-    auto mk = [&](const pnfam_b200_blockmatrix& b, DevStructBuf& d, BlockStruct& hs) {
-      hs.r2c.assign(c->nb, -1); hs.r2m.assign(c->nb, -1); hs.allocated = true;
-      for (int i = 0; i < c->nb; i++) if (b.ir2c[i] > 0) { hs.r2c[i] = b.ir2c[i] - 1; hs.r2m[i] = b.ir2m[i] - 1; }
-      d.upload(hs);
-    };
-    // argument order -> (pass, kind): in: rho_pn(0,1) k+(2,3) rho_np(4,5) k-(6,7); storage quads 0,1,3,2
-    DevStructBuf sin[4], sout[4];
-    BlockStruct hin[4], hout[4];
+    auto w = std::static_pointer_cast<HamWorkspace>(c->ham_ws);
+    if (!w || w->key != ham_key(*c, in, out)) {
+      c->ham_ws.reset();
+      w = build_ham_workspace(c, in, out);
+      c->ham_ws = w;
+    }
+    const size_t nxy = w->h.nxy;
     const int quad_of_pair[4] = {0, 1, 3, 2};
-    DBuf<double> rsp, hsp, dd_rho, dd_kap, mf, pf, hpart;
-    DBuf<int> d_active;
-    rsp.alloc(8 * nxy); hsp.alloc(8 * nxy); rsp.zero(); hsp.zero();
-    for (int pr = 0; pr < 4; pr++) {
-      mk(in[2 * pr], sin[pr], hin[pr]);
-      mk(out[2 * pr], sout[pr], hout[pr]);
-      for (int cc = 0; cc < 2; cc++)
-        PNFAM_CUDA_CHECK(cudaMemcpy(rsp.p + ((size_t)cc * 4 + quad_of_pair[pr]) * nxy, in[2 * pr + cc].elem,
-                                    in[2 * pr + cc].nelem * sizeof(double), cudaMemcpyHostToDevice));
-    }
-    HamArgs h{};
-    h.basis = c->basis;
-    h.rho_in[0] = sin[0].view(); h.kap_in[0] = sin[1].view(); h.rho_in[1] = sin[2].view(); h.kap_in[1] = sin[3].view();
-    h.h_out[0] = sout[0].view(); h.d_out[0] = sout[1].view(); h.h_out[1] = sout[2].view(); h.d_out[1] = sout[3].view();
-    h.rho_quad[0] = 0; h.kap_quad[0] = 1; h.rho_quad[1] = 3; h.kap_quad[1] = 2;
-    h.nxy = nxy;
-    const bool sf = c->sf.enabled != 0;
-    DBuf<DensStep> dsteps[4];
-    int ndsteps[4];
-    DBuf<SfDensStep> sf_steps[4];
-    DBuf<SfProjTile> sf_tiles[2][2];
-    DBuf<double> pk_rho, pk_kap;
-    ProjPlan pp;
-    DBuf<int4> th, td;
-    h.sf = c->sf;
-    if (sf) {
-      // argument pairs: 0 rho_pn (pass 0), 1 kappa+ (pass 0), 2 rho_np (pass 1), 3 kappa- (pass 1)
-      h.pk_stride_rho = std::max(upload_sf_density_steps(*c, hin[0], sf_steps[0], h.sf.nsteps[0]), upload_sf_density_steps(*c, hin[2], sf_steps[1], h.sf.nsteps[1]));
-      h.pk_stride_kap = std::max(upload_sf_density_steps(*c, hin[1], sf_steps[2], h.sf.nsteps[2]), upload_sf_density_steps(*c, hin[3], sf_steps[3], h.sf.nsteps[3]));
-      for (int k = 0; k < 4; k++) h.sf.steps[k] = sf_steps[k].p;
-      upload_sf_proj_tiles(*c, hout[0], sf_tiles[0][0], h.sf.ntiles[0][0]);
-      upload_sf_proj_tiles(*c, hout[2], sf_tiles[0][1], h.sf.ntiles[0][1]);
-      upload_sf_proj_tiles(*c, hout[1], sf_tiles[1][0], h.sf.ntiles[1][0]);
-      upload_sf_proj_tiles(*c, hout[3], sf_tiles[1][1], h.sf.ntiles[1][1]);
-      for (int m = 0; m < 2; m++)
-        for (int q = 0; q < 2; q++) h.sf.tiles[m][q] = sf_tiles[m][q].p;
-      h.sf.ksplit = std::min(c->sf.ngl, std::max(1, (2 * 148 + std::max(1, h.sf.ntiles[0][0] / 8) - 1) / std::max(1, h.sf.ntiles[0][0] / 8)));
-      pp.ksplit = h.sf.ksplit;
-      h.sf.pk_stride[0] = h.pk_stride_rho; h.sf.pk_stride[1] = h.pk_stride_kap;
-    } else {
-      h.pk_stride_rho = std::max(upload_density_steps(*c, hin[0], dsteps[0], ndsteps[0]), upload_density_steps(*c, hin[2], dsteps[1], ndsteps[1]));
-      h.pk_stride_kap = std::max(upload_density_steps(*c, hin[1], dsteps[2], ndsteps[2]), upload_density_steps(*c, hin[3], dsteps[3], ndsteps[3]));
-      for (int q = 0; q < 2; q++) {
-        h.steps_rho[q] = dsteps[q].p; h.nsteps_rho[q] = ndsteps[q];
-        h.steps_kap[q] = dsteps[2 + q].p; h.nsteps_kap[q] = ndsteps[2 + q];
+    // elements: host arrays -> pinned staging -> device, all on the context's stream
+    for (int pr = 0; pr < 4; pr++)
+      for (int cc = 0; cc < 2; cc++) {
+        const pnfam_b200_blockmatrix& b = in[2 * pr + cc];
+        double* sg = w->stage.p + (size_t)(2 * pr + cc) * nxy;
+        std::memcpy(sg, b.elem, (size_t)b.nelem * sizeof(double));
+        PNFAM_CUDA_CHECK(cudaMemcpyAsync(w->rsp.p + ((size_t)cc * 4 + quad_of_pair[pr]) * nxy, sg, (size_t)b.nelem * sizeof(double),
+                                         cudaMemcpyHostToDevice, st));
       }
-      std::vector<int4> vh, vd;
-      BlockStruct shh[2] = {hout[0], hout[2]}, sdd[2] = {hout[1], hout[3]};
-      build_proj_tiles(*c, shh, vh, pp.ntiles_h, pp.tile_off_h);
-      build_proj_tiles(*c, sdd, vd, pp.ntiles_d, pp.tile_off_d);
-      th.upload(vh); td.upload(vd);
-      pp.tiles_h = th.p; pp.tiles_d = td.p;
-      const int per = std::max(1, pp.ntiles_h[0]);
-      pp.ksplit = std::min(std::min(c->ntiles, 32), std::max(1, (2 * 148 + per - 1) / per));
-    }
-    pk_rho.alloc(2 * std::max<size_t>(h.pk_stride_rho, 1)); pk_kap.alloc(2 * std::max<size_t>(h.pk_stride_kap, 1));
-    h.pk_rho = pk_rho.p; h.pk_kap = pk_kap.p;
-    h.sf.pk[0] = pk_rho.p; h.sf.pk[1] = pk_kap.p;
-    dd_rho.alloc((size_t)2 * NDD_RHO * c->nghl); dd_kap.alloc((size_t)2 * NDD_KAP * c->nghl);
-    dd_rho.zero(); dd_kap.zero();
-    mf.alloc((size_t)2 * (sf ? sf_mf_elems(c->sf.ngl, c->sf.kih) : mf_elems(c->ntiles)));
-    pf.alloc((size_t)2 * (sf ? sf_pf_elems(c->sf.ngl, c->sf.kih) : pf_elems(c->ntiles)));
-    mf.zero(); pf.zero();
-    hpart.alloc(projection_partial_elems(pp, nxy));
-    std::vector<int> act = {0};
-    d_active.upload(act);
-    h.rsp = rsp.p; h.hsp = hsp.p; h.dd_rho = dd_rho.p; h.dd_kap = dd_kap.p; h.mf = mf.p; h.pf = pf.p; h.hpart = hpart.p;
-    h.active = d_active.p; h.nactive = 1;
-    launch_density(h, st);
-    launch_fields(h, st);
-    launch_projection(h, pp, st);
-    PNFAM_CUDA_CHECK(cudaStreamSynchronize(st));
-    PNFAM_CUDA_CHECK(cudaGetLastError());
+    launch_density(w->h, st);
+    launch_fields(w->h, st);
+    launch_projection(w->h, w->pp, st);
     for (int pr = 0; pr < 4; pr++)
       for (int cc = 0; cc < 2; cc++)
-        PNFAM_CUDA_CHECK(cudaMemcpy(out[2 * pr + cc].elem, hsp.p + ((size_t)cc * 4 + quad_of_pair[pr]) * nxy,
-                                    out[2 * pr + cc].nelem * sizeof(double), cudaMemcpyDeviceToHost));
+        PNFAM_CUDA_CHECK(cudaMemcpyAsync(w->stage.p + (size_t)(8 + 2 * pr + cc) * nxy, w->hsp.p + ((size_t)cc * 4 + quad_of_pair[pr]) * nxy,
+                                         (size_t)out[2 * pr + cc].nelem * sizeof(double), cudaMemcpyDeviceToHost, st));
+    PNFAM_CUDA_CHECK(cudaStreamSynchronize(st));
+    PNFAM_CUDA_CHECK(cudaGetLastError());
+    for (int i = 0; i < 8; i++) std::memcpy(out[i].elem, w->stage.p + (size_t)(8 + i) * nxy, (size_t)out[i].nelem * sizeof(double));
     c->launches += 3 + 1 + 5;
     return 0;
   } catch (const std::exception& e) {
@@ -910,7 +1080,7 @@ __global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters) 
 
 extern "C" int pnfam_b200_dmma_peak(int device, double* tflops, char* err, int errlen) {
   try {
-    require_device(device);
+    DeviceGuard dg(device);
     cudaDeviceProp prop;
     PNFAM_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
     DBuf<double> out;

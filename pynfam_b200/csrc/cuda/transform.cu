@@ -99,6 +99,7 @@ __device__ __forceinline__ void store_tile(double* __restrict__ O, const double 
 __global__ void __launch_bounds__(256, 3) transform_phase1_kernel(const DevTask* __restrict__ tasks, const int4* __restrict__ tiles,
                                                               TransformArgs args, int kpad) {
   extern __shared__ __align__(16) double tr_smem[];
+  if (args.ctrl && (int)blockIdx.y >= args.ctrl->nactive) return;
   const int4 e = tiles[blockIdx.x];                 // (task, term, first row, first column)
   const DevTask& tk = tasks[e.x];
   const DevTerm& tm = tk.t[e.y];
@@ -130,6 +131,7 @@ __global__ void __launch_bounds__(256, 3) transform_phase1_kernel(const DevTask*
 __global__ void __launch_bounds__(256, 3) transform_phase2_kernel(const DevTask* __restrict__ tasks, const int4* __restrict__ tiles,
                                                               TransformArgs args, int kpad) {
   extern __shared__ __align__(16) double tr_smem[];
+  if (args.ctrl && (int)blockIdx.y >= args.ctrl->nactive) return;
   const int4 e = tiles[blockIdx.x];                 // (task, -, first row, first column)
   const DevTask& tk = tasks[e.x];
   const int M = tk.m, N = tk.n, K = N, K4 = (K + 3) & ~3;
@@ -171,11 +173,10 @@ void launch_transform(const DevicePlan& plan, const TransformArgs& args, int nac
   if (nactive <= 0) return;
   const int kpad = (plan.max_dim + 3) & ~3;
   const size_t smem = (size_t)3 * kpad * TR_LD * sizeof(double);
-  static size_t attr = 48 * 1024;
-  if (smem > attr) {
+  static PerDeviceMax attr;
+  if (smem > 48 * 1024 && attr.raise(smem)) {
     PNFAM_CUDA_CHECK(cudaFuncSetAttribute(transform_phase1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PNFAM_CUDA_CHECK(cudaFuncSetAttribute(transform_phase2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
   }
   dim3 g1(plan.ntiles1, nactive), g2(plan.ntiles2, nactive);
   if (plan.ntiles1 > 0) transform_phase1_kernel<<<g1, 256, smem, stream>>>(plan.tasks, plan.tiles1, args, kpad);

@@ -34,7 +34,8 @@ class Operator(ctypes.Structure):
 class SolverParams(ctypes.Structure):
     _fields_ = [("max_iter", ctypes.c_int32), ("broyden_history_size", ctypes.c_int32),
                 ("convergence_epsilon", ctypes.c_double), ("quench_residual_int", ctypes.c_double),
-                ("energy_shift_prot", ctypes.c_double), ("energy_shift_neut", ctypes.c_double)]
+                ("energy_shift_prot", ctypes.c_double), ("energy_shift_neut", ctypes.c_double),
+                ("batch_slots", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
 class Stats(ctypes.Structure):
@@ -43,7 +44,8 @@ class Stats(ctypes.Structure):
                 ("h2d_bytes", ctypes.c_int64), ("d2h_bytes", ctypes.c_int64),
                 ("seconds_density", ctypes.c_double), ("seconds_projection", ctypes.c_double),
                 ("launches_density", ctypes.c_int64), ("launches_projection", ctypes.c_int64),
-                ("flops_density", ctypes.c_double), ("flops_projection", ctypes.c_double)]
+                ("flops_density", ctypes.c_double), ("flops_projection", ctypes.c_double),
+                ("batch_slots", ctypes.c_int32), ("lock_steps", ctypes.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -137,8 +139,9 @@ class Context:
             lib().pnfam_b200_ctx_destroy(self._h)
             self._h = None
 
-    def solve(self, problem, omegas=None, max_iter=None, eps=None, history=None, want_trace=False):
+    def solve(self, problem, omegas=None, max_iter=None, eps=None, history=None, want_trace=False, slots=0):
         """Solve the problem's operator at the given complex frequencies (default: the namelist's one).
+        slots: omega points iterated side by side (0 = automatic); the others are admitted as running points finish.
         Returns dict(strength[P, 1+nx] complex, iters, conv, si, stats, labels, trace)."""
         L = lib()
         p = problem
@@ -158,7 +161,8 @@ class Context:
         prm = SolverParams(int(max_iter if max_iter is not None else p.iscalar("max_iter")),
                            int(history if history is not None else p.iscalar("broyden_history_size")),
                            float(eps if eps is not None else p.scalar("convergence_epsilon")),
-                           p.scalar("quench_residual_int"), p.scalar("energy_shift_prot"), p.scalar("energy_shift_neut"))
+                           p.scalar("quench_residual_int"), p.scalar("energy_shift_prot"), p.scalar("energy_shift_neut"),
+                           int(slots), 0)
         strength = np.zeros((P, 1 + nx, 2))
         iters, conv = np.zeros(P, np.int32), np.zeros(P, np.int32)
         si = np.zeros(P)
