@@ -11,6 +11,10 @@ from pynfam_b200 import host
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-9
+# Ill-conditioned points (>= 25 Broyden steps or |Im omega| < 0.5): 2.5 x the spread the reference binary itself shows
+# between its run in this build container and its own golden files at those points (8.1e-9, recorded in
+# tests/golden/loose_points_6sh.json; measured against the reference-run-here in tests/test_gpu_production.py)
+LOOSE_TOL = 2e-8
 
 
 @pytest.fixture(scope="module")
@@ -106,7 +110,7 @@ def test_whole_contour_batched_against_golden(mkctx, case, op, tmp_path):
             assert int(r["conv"][i]) == 1 and abs(int(r["iters"][i]) - pt["iters"]) <= max(4, pt["iters"] // 5), i
         else:
             assert int(r["iters"][i]) == pt["iters"], i
-        tol = 5e-8 if loose else TOL
+        tol = LOOSE_TOL if loose else TOL
         for k, lab in enumerate(["Strength"] + r["labels"][1:]):
             if lab in gold:
                 assert _rel(r["strength"][i, k], gold[lab]) < tol, (i, lab)
@@ -279,7 +283,7 @@ def test_contour_driver_writes_the_reference_strength_files(gpu, tmp_path):
             for i in range(60):
                 j = i if i < 30 else 59 - i        # computed point this row mirrors
                 loose = abs(z[j].imag) < 0.5 or pts[j]["iters"] >= 25
-                assert _rel(a[lab].values[i], b[lab].values[i]) < (5e-8 if loose else TOL), (fs.opname, lab, i)
+                assert _rel(a[lab].values[i], b[lab].values[i]) < (LOOSE_TOL if loose else TOL), (fs.opname, lab, i)
         if fs.bareop == "GT":
             # integrated beta-decay rate of the allowed channel (north-star: 1e-9 relative): the reference's own
             # phase-space weights at the contour points (its shape factor / its strength, tests/golden/make_beta.py)
@@ -398,7 +402,7 @@ def test_contour_driver_with_two_body_currents(gpu, tmp_path):
             gold = gold_rows(pt)
             assert abs(contour.ctr_z[i] - gold["Energy"]) < 1e-12
             loose = abs(contour.ctr_z[i].imag) < 0.5 or pt["iters"] >= 25
-            assert _rel(got[i], gold["Strength"]) < (5e-8 if loose else TOL), (fs.opname, i)
+            assert _rel(got[i], gold["Strength"]) < (LOOSE_TOL if loose else TOL), (fs.opname, i)
 
 
 def test_large_broyden_history_and_contour_mode_of_the_executable(gpu, tmp_path):
@@ -446,7 +450,7 @@ def test_full_beta_decay_chain_against_beta_out(gpu, tmp_path):
     """The whole flow the north-star names, on the GPU: all 14 (operator, K) of 40S on pynfam's contour (one batched
     solve each) -> phase space -> shape factor -> integrated rates, against the reference's beta.out
     (tests/S40_GT_All/000000/beta_soln).  The reference's own rate chain carries ~1e-9 of interpolation noise
-    (tests/test_rates.py), the strengths of the near-axis points 5e-8."""
+    (tests/test_rates.py), the strengths of the near-axis points 2e-8."""
     import json
     import os
     from conftest import GOLDEN
