@@ -143,3 +143,80 @@ def test_contour_exe_without_gpu_reports_failure_the_reference_way(tmp_path):
     (tmp_path / "bad.dat").write_text("&ctr_general\n fam_mode = 'FINDMAX'\n/\n")
     r = subprocess.run([exe, "bad.dat"], cwd=str(tmp_path), capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "not available" in r.stdout
+
+
+# ---- the Fortran binding source against the C header ------------------------------------------------------
+_CTYPES = {"int32_t": ("integer(c_int32_t)", 4), "int64_t": ("integer(c_int64_t)", 8), "double": ("real(c_double)", 8),
+           "ptr": ("type(c_ptr)", 8)}
+
+
+def _c_structs():
+    """{struct name: [(kind, field)]} of the typedef'd structs of include/pnfam_b200.h, in declaration order."""
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "pnfam_b200.h")).read(), flags=re.S)
+    out = {}
+    for body, name in re.findall(r"typedef\s+struct\s*\{(.*?)\}\s*(\w+)\s*;", hdr, flags=re.S):
+        fields = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            m = re.match(r"(const\s+)?(\w+)\s*(.*)", decl)
+            base, rest = m.group(2), m.group(3)
+            for item in rest.split(","):
+                item = item.strip()
+                nm = re.sub(r"[\s\*]|const", "", item)
+                fields.append(("ptr" if "*" in item else base, nm))
+        out[name] = fields
+    return out
+
+
+def _f90_types():
+    src = open(os.path.join(ROOT, "include", "pnfam_b200_binding.f90")).read()
+    out = {}
+    for name, body in re.findall(r"type,\s*bind\(C\)\s*::\s*(\w+)\n(.*?)\n\s*end type", src, flags=re.S):
+        fields = []
+        for ln in body.split("\n"):
+            ln = ln.split("!")[0].strip()
+            if not ln:
+                continue
+            kind, names = [x.strip() for x in ln.split("::")]
+            fields += [(kind, n.strip()) for n in names.split(",")]
+        out[name] = fields
+    return out
+
+
+def test_fortran_binding_matches_the_c_structs(tmp_path):
+    """include/pnfam_b200_binding.f90 declares every struct of the header field for field (name, kind, order), and the
+    byte offsets a Fortran bind(C) type gets (natural alignment, the C interoperability rule) equal offsetof() of the
+    C structs as compiled here -- a caller built from the binding passes exactly what the library reads."""
+    import subprocess
+    cs, fs = _c_structs(), _f90_types()
+    assert set(cs) == set(fs) and len(cs) == 5
+    prog = ['#include <stdio.h>', '#include <stddef.h>', '#include "pnfam_b200.h"', 'int main(void){']
+    for name, fields in cs.items():
+        assert [n.lower() for _, n in fields] == [n.lower() for _, n in fs[name]], name
+        for (ck, cn), (fk, fn) in zip(fields, fs[name]):
+            assert _CTYPES[ck][0] == fk, (name, cn, ck, fk)
+            prog.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (name, cn, name, cn))
+        prog.append('printf("%s.sizeof %%zu\\n", sizeof(%s));' % (name, name))
+    prog.append("return 0;}")
+    src = tmp_path / "probe.c"
+    src.write_text("\n".join(prog))
+    exe = str(tmp_path / "probe")
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", exe, str(src)], check=True)
+    got = dict(ln.split() for ln in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.splitlines())
+    for name, fields in fs.items():
+        off, amax = 0, 1
+        for kind, fn in fields:
+            size = [v[1] for v in _CTYPES.values() if v[0] == kind][0]
+            off = (off + size - 1) // size * size
+            cname = [n for _, n in cs[name] if n.lower() == fn.lower()][0]
+            assert int(got["%s.%s" % (name, cname)]) == off, (name, fn)
+            off += size
+            amax = max(amax, size)
+        assert int(got[name + ".sizeof"]) == (off + amax - 1) // amax * amax, name
+    # every entry point of section 2 is bound
+    f90 = open(os.path.join(ROOT, "include", "pnfam_b200_binding.f90")).read()
+    for sym in _declared_symbols():
+        if sym.startswith("pnfam_b200_"):
+            assert 'name="%s"' % sym in f90, sym
