@@ -382,8 +382,94 @@ static std::vector<double> i1111(const FamBasis& b) {
   return I;
 }
 
+// ---- closed-form two-body-current factors (nuclear matter + local density approximation) ----------------
+namespace {
+constexpr double TB_HBARC = 197.3269718, TB_FPI = 92.4, TB_MN = 939.0, TB_MPI = 138.04, TB_GA = 1.27;   // pnfam_constants.f90:44-67
+const double TB_PI = 3.14159265358979323846264338327950288;
+inline double tb_caux() { return (TB_HBARC * TB_HBARC * TB_HBARC) / (2.0 * TB_MN * TB_FPI * TB_FPI); }
+// tbc_nmlda_I0: the P = p = 0 limit of the nuclear-matter integrals (pnfam_extfield.f90:976-990)
+inline double tb_i0(double kf) {
+  const double m = TB_MPI / TB_HBARC, kf2 = kf * kf, kf3 = kf * kf * kf;
+  return 1.0 - 3.0 * m * m / kf2 + 3.0 * m * m * m / kf3 * std::atan(kf / m);
+}
+inline double kf_snm(double rho) { return std::pow(1.5 * TB_PI * TB_PI * rho, 1.0 / 3.0); }    // lda_kf_snm
+inline double kf_asnm(double rho) { return std::pow(3.0 * TB_PI * TB_PI * rho, 1.0 / 3.0); }   // lda_kf_asnm
+}  // namespace
+
+// GT: rho_fac of ext_field_operator (pnfam_extfield.f90:157-182): contact term + tbc_nmlda_da1 at Q = 0 (:1063-1128)
+std::vector<double> tbc_gt_rho_fac(const FamBasis& b, const TwoBody& tb) {
+  const double caux = tb_caux(), c3 = tb.lecs[0], c4 = tb.lecs[1], cd = tb.lecs[2] * (-0.25);
+  std::vector<double> rf(b.nghl);
+  for (int r = 0; r < b.nghl; r++) rf[r] = (caux * 2.0 * cd) * (b.rho_n[r] + b.rho_p[r]);
+  if (tb.u[2] == 2 || tb.u[2] == 3) {
+    const bool snm = tb.u[2] == 2;
+    const double caux0 = (TB_HBARC * TB_HBARC * TB_HBARC) / (TB_MN * TB_FPI * TB_FPI);
+    double caux3 = -1.0 / 3.0 * c3;
+    if (tb.use_p) caux3 = caux3 + 1.0 / 12.0;
+    const double caux4 = 1.0 / 3.0 * (c4 + 0.25);
+    std::vector<double> da1(b.nghl, 0.0);
+    for (int it = 1; it <= 3; it++) {
+      if (snm ? it != 3 : it == 3) continue;
+      for (int r = 0; r < b.nghl; r++) {
+        const double ri = it == 1 ? b.rho_n[r] : (it == 2 ? b.rho_p[r] : b.rho_p[r] + b.rho_n[r]);
+        const double ki = it == 3 ? kf_snm(ri) : kf_asnm(ri);
+        const double I1 = tb_i0(ki), I2 = I1;
+        da1[r] = da1[r] + caux0 * ri * (caux4 * (3.0 * I2 - I1) + caux3 * I1);
+      }
+    }
+    for (int r = 0; r < b.nghl; r++) rf[r] = rf[r] + da1[r];
+  }
+  return rf;
+}
+
+// forbidden_2bc_rsL (pnfam_extfield.f90:1146-1193): the RS* fields are weighted with (1 - this)
+std::vector<double> tbc_rsl_correction(const FamBasis& b, const TwoBody& tb, bool snm) {
+  const double ca = 2 * tb_caux(), c3 = tb.lecs[0], c4 = tb.lecs[1], cd = tb.lecs[2] * (-0.25);
+  const double ch = 1.0 / 3.0 * (2 * c4 - c3 + 0.5);
+  std::vector<double> out(b.nghl);
+  for (int r = 0; r < b.nghl; r++) {
+    if (snm) {
+      const double rho = b.rho_n[r] + b.rho_p[r];
+      out[r] = ca * rho * (cd + ch * tb_i0(kf_snm(rho)));
+    } else {
+      const double rn = b.rho_n[r], rp = b.rho_p[r];
+      out[r] = ca * (rn + rp) * cd + ca * ch * rn * tb_i0(kf_asnm(rn)) + ca * ch * rp * tb_i0(kf_asnm(rp));
+    }
+  }
+  return out;
+}
+
+// forbidden_2bc_P (pnfam_extfield.f90:1339-1368)
+std::vector<double> tbc_p_correction(const FamBasis& b) {
+  const double P = (double)(std::sqrt(1.2f) * 1.30465f / 2.0f);   // `sqrt(1.2)*1.30465 / 2.0`: default-real (single precision) arithmetic in the source
+  const double m = TB_MPI / TB_HBARC;
+  std::vector<double> rf(b.nghl);
+  for (int r = 0; r < b.nghl; r++) {
+    const double kf = kf_snm(b.rho_n[r] + b.rho_p[r]);
+    const double lg = std::log((m * m + (P + kf) * (P + kf)) / (m * m + (P - kf) * (P - kf)));
+    const double iout = 1.0 / (P * P * P) * (P * m * m * kf - 0.25 * m * m * (m * m + P * P + kf * kf) * lg);
+    rf[r] = TB_GA * TB_GA * TB_HBARC * TB_MN / (4 * TB_PI * TB_PI * TB_FPI * TB_FPI) * iout;
+  }
+  return rf;
+}
+
+// forbidden_2bc_PS0 (pnfam_extfield.f90:1370-1393)
+std::vector<double> tbc_ps0_correction(const FamBasis& b) {
+  const double P = (double)(std::sqrt(1.2f) * 1.30465f / 2.0f);
+  const double m = TB_MPI / TB_HBARC;
+  std::vector<double> rf(b.nghl);
+  for (int r = 0; r < b.nghl; r++) {
+    const double kf = kf_snm(b.rho_n[r] + b.rho_p[r]);
+    const double lg = std::log((m * m + (P + kf) * (P + kf)) / (m * m + (P - kf) * (P - kf)));
+    const double t1 = (m * m + P * P) * (m * m + P * P) + kf * kf * (kf * kf - 2 * P * P + 2 * m * m);
+    const double iout = 1.0 / (P * P * P) * (-P * kf * (kf * kf + m * m + P * P) + 0.25 * (t1 * lg));
+    rf[r] = -TB_HBARC * TB_MN / (8 * TB_PI * TB_PI * TB_FPI * TB_FPI) * iout;
+  }
+  return rf;
+}
+
 ExtField make_external_field(const FamBasis& b, const std::string& beta_type, const std::string& label_in, int K,
-                             const std::vector<double>* rho_fac) {
+                             const std::vector<double>* rho_fac, const TwoBody* tb) {
   ExtField op;
   op.label = upper(label_in);
   const std::string& L = op.label;
@@ -407,11 +493,38 @@ ExtField make_external_field(const FamBasis& b, const std::string& beta_type, co
   for (int i = 0; i < nghl; i++) r[i] = 1.0 / b.y[i];
   const bool useI = (L == "RS0I" || L == "RI" || L == "RS1I");
   if (useI) ifun = i1111(b);
+  // two-body-current weight on wf_1 (pnfam_extfield.f90:189-197, 349-366, 383-557, 562-607): RS* fields carry
+  // (1 - correction) when the 4th mode digit is >= 2 (3: asymmetric nuclear matter); P and PS0 carry 1 + correction
+  // (1BC + 2BC) or the correction alone (2BC only) when their digit is 1.  The density-matrix-expansion variants
+  // (digit 2) are not restated.
+  std::vector<double> w1;
+  if (tb && tb->active()) {
+    const bool rs = (L == "RS0" || L == "RS1" || L == "RS2" || L == "RS0I" || L == "RS1I");
+    if (rs && tb->u[4] >= 2) {
+      w1 = tbc_rsl_correction(b, *tb, tb->u[4] != 3);
+      for (auto& x : w1) x = 1.0 - x;
+    } else if ((L == "P" && tb->u[5] != 0) || (L == "PS0" && tb->u[6] != 0)) {
+      const int dg = L == "P" ? tb->u[5] : tb->u[6];
+      if (dg == 2) throw std::runtime_error("two_body_current_mode: the density-matrix-expansion current of " + L + " is not supported");
+      if (dg == 1) {
+        w1 = L == "P" ? tbc_p_correction(b) : tbc_ps0_correction(b);
+        if (tb->u[1] == 1) for (auto& x : w1) x = 1 + x;
+      }
+    }
+  }
+  const bool useW1 = !w1.empty();
   // weight functions applied to wf_1 * (...) * wf_2 products
-  auto dot = [&](const double* a, const double* c) { double s = 0; for (int i = 0; i < nghl; i++) s += a[i] * c[i]; return s; };
+  auto dot = [&](const double* a, const double* c) {
+    double s = 0;
+    if (useW1) for (int i = 0; i < nghl; i++) s += (a[i] * w1[i]) * c[i];
+    else for (int i = 0; i < nghl; i++) s += a[i] * c[i];
+    return s;
+  };
   auto dotw = [&](const double* a, const std::vector<double>& w, const double* c) {
     double s = 0;
-    if (useI) for (int i = 0; i < nghl; i++) s += (ifun[i] * a[i]) * (w[i] * c[i]);
+    if (useI && useW1) for (int i = 0; i < nghl; i++) s += ((ifun[i] * a[i]) * w1[i]) * (w[i] * c[i]);
+    else if (useI) for (int i = 0; i < nghl; i++) s += (ifun[i] * a[i]) * (w[i] * c[i]);
+    else if (useW1) for (int i = 0; i < nghl; i++) s += (a[i] * w1[i]) * (w[i] * c[i]);
     else for (int i = 0; i < nghl; i++) s += a[i] * (w[i] * c[i]);
     return s;
   };
@@ -487,8 +600,11 @@ ExtField make_external_field(const FamBasis& b, const std::string& beta_type, co
   return op;
 }
 
-std::vector<ExtField> make_crossterms(const FamBasis& b, const ExtField& op) {
-  return make_crossterms(op, [&](const std::string& beta, const std::string& l, int k) { return make_external_field(b, beta, l, k); });
+std::vector<ExtField> make_crossterms(const FamBasis& b, const ExtField& op, const TwoBody* tb) {
+  // the cross-term field R is always the one-body one (setup_crossterms, pnfam_extfield.f90:918-921)
+  return make_crossterms(op, [&](const std::string& beta, const std::string& l, int k) {
+    return make_external_field(b, beta, l, k, nullptr, l == "R" ? nullptr : tb);
+  });
 }
 
 std::vector<ExtField> make_crossterms(const ExtField& op, const FieldProvider& field) {
@@ -555,19 +671,24 @@ bool read_tbc(const std::string& path, const FamBasis& b, const FamInput& in, Ex
   return found;
 }
 
-void apply_two_body_current_gt(const std::string& tbc_path, const FamBasis& b, const FamInput& in, int i1, ExtField& f) {
-  // constants of init_extfield_2bc_type (pnfam_type_extfield_2bc.f90:47-77, pnfam_constants.f90:44-67)
-  const double hbarc = 197.3269718, Fpi = 92.4, Mn = 939.0;
-  const double caux = (hbarc * hbarc * hbarc) / (2.0 * Mn * Fpi * Fpi);
-  const double cd = in.two_body_current_lecs[2] * (-0.25);
+void apply_two_body_current_gt(const std::string& tbc_path, const FamBasis& b, const FamInput& in, const TwoBody& tb, ExtField& f) {
+  // setup_extfield (pnfam_solver.f90:586-646): F = [-GT_1body if 1BC+2BC] + GT[rho_fac] (+ Yukawa part from <name>.tbc
+  // for the full-FAM mode).  rho_fac: contact term, plus the nuclear-matter exchange term in the LDA modes.
+  if (tb.u[2] == 4 || tb.u[2] == 5)
+    throw std::runtime_error("two_body_current_mode: the density-matrix-expansion modes (2nd digit 4, 5) are not supported");
   std::vector<double> tmp(f.mat.elem.size(), 0.0);
-  if (i1 == 1) for (size_t i = 0; i < tmp.size(); i++) tmp[i] = -f.mat.elem[i];   // Park sign convention: -sigma tau + 2BC
-  std::vector<double> rho_fac(b.nghl);
-  for (int r = 0; r < b.nghl; r++) rho_fac[r] = (caux * 2.0 * cd) * (b.rho_n[r] + b.rho_p[r]);
+  if (tb.u[1] == 1) for (size_t i = 0; i < tmp.size(); i++) tmp[i] = -f.mat.elem[i];   // Park sign convention: -sigma tau + 2BC
+  const std::vector<double> rho_fac = tbc_gt_rho_fac(b, tb);
   ExtField contact = make_external_field(b, f.beta_minus ? "-" : "+", f.label, f.k, &rho_fac);
   for (size_t i = 0; i < tmp.size(); i++) tmp[i] += contact.mat.elem[i];
+  if (tb.u[2] != 1) {                       // no FAM part: F = -sigma tau + sigma tau f(rho)
+    f.mat.elem = tmp;
+    return;
+  }
   std::string why;
-  if (!read_tbc(tbc_path, b, in, f, why)) throw std::runtime_error(why);
+  if (!read_tbc(tbc_path, b, in, f, why))
+    throw std::runtime_error(why + " (the full-FAM two-body-current field generator, pnfam_extfield_2bc.f90, is not part of this "
+                                   "library: provide the .tbc file the reference caches)");
   for (size_t i = 0; i < tmp.size(); i++) f.mat.elem[i] += tmp[i];
 }
 

@@ -107,9 +107,23 @@ struct ExtField {
 
 // rho_fac (optional, nghl): weight folded into the GT operator, sigma tau f(rho) -- the contact part of the
 // two-body current (pnfam_extfield.f90:167-190)
+// Two-body-current request of one field (set_use_2bc, pnfam_extfield.f90:690-720): u[1..6] = the six digits of
+// two_body_current_mode (1: 1 = 1BC+2BC, 2 = 2BC only; 2: 1 full FAM, 2 SNM+LDA, 3 ASNM+LDA, 4/5 DME; 3: 1 = Gamma;
+// 4: GT current active, >= 2 also corrects RS*; 5: P current; 6: PS0 current), all zero = one-body field.
+struct TwoBody {
+  int u[7] = {0, 0, 0, 0, 0, 0, 0};
+  double lecs[3] = {0, 0, 0};      // c3, c4, cd of the namelist
+  bool use_p = false;
+  bool active() const { return u[1] != 0; }
+};
+// closed-form density-dependent factors of the nuclear-matter / LDA two-body currents (pnfam_extfield.f90:976-1410)
+std::vector<double> tbc_gt_rho_fac(const FamBasis& b, const TwoBody& tb);   // GT: contact + SNM / ASNM exchange term
+std::vector<double> tbc_rsl_correction(const FamBasis& b, const TwoBody& tb, bool snm);
+std::vector<double> tbc_p_correction(const FamBasis& b);
+std::vector<double> tbc_ps0_correction(const FamBasis& b);
 ExtField make_external_field(const FamBasis& b, const std::string& beta_type, const std::string& label, int k,
-                             const std::vector<double>* rho_fac = nullptr);
-std::vector<ExtField> make_crossterms(const FamBasis& b, const ExtField& op);
+                             const std::vector<double>* rho_fac = nullptr, const TwoBody* tb = nullptr);
+std::vector<ExtField> make_crossterms(const FamBasis& b, const ExtField& op, const TwoBody* tb = nullptr);
 // the same with the fields taken from a provider (beta type, label, K) -> field, e.g. a per-nucleus cache: the
 // operators of one J^pi group share their cross-term fields
 using FieldProvider = std::function<ExtField(const std::string&, const std::string&, int)>;
@@ -119,6 +133,6 @@ std::vector<ExtField> make_crossterms(const ExtField& op, const FieldProvider& f
 bool read_tbc(const std::string& path, const FamBasis& b, const FamInput& in, ExtField& f, std::string& why);
 // Full two-body-current GT field of mode i1 i2=1 i3=1 i4>0 (pnfam_solver.f90:596-652):
 //   F = [-GT_1body if i1==1] + GT[contact rho_fac] + Yukawa part from <name>.tbc
-void apply_two_body_current_gt(const std::string& tbc_path, const FamBasis& b, const FamInput& in, int i1, ExtField& f);
+void apply_two_body_current_gt(const std::string& tbc_path, const FamBasis& b, const FamInput& in, const TwoBody& tb, ExtField& f);
 
 }  // namespace pnfam

@@ -1,5 +1,6 @@
 #include "problem.hpp"
 
+#include <cctype>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -58,26 +59,37 @@ std::unique_ptr<Problem> Problem::build(const std::string& rundir, const FamInpu
   FamBasis& b = p->nuc->basis;
   p->inter = Interaction::build(p->in, b);
   const FamInput& in = p->in;
-  // external field (pnfam_solver.f90:556-654)
+  // external field (setup_extfield, pnfam_solver.f90:556-654)
   const int mode = in.two_body_current_mode;
-  int u[7] = {0, 0, 0, 0, 0, 0, 0};
+  TwoBody tb;
   if (mode != 0) {
+    int* u = tb.u;
     u[1] = digit(mode, 5); u[2] = digit(mode, 4); u[3] = digit(mode, 3);
     u[4] = digit(mode, 2); u[5] = digit(mode, 1); u[6] = digit(mode, 0);
     if (u[1] < 1 || u[1] > 2 || u[2] < 1 || u[2] > 5 || u[3] < 1 || u[3] > 3 || (u[1] != 1 && u[3] != 1))
       throw std::runtime_error("Invalid value supplied for two_body_current_mode.");
     if (u[3] != 1) throw std::runtime_error("This two_body_current_mode is not yet operational.");
-    if (u[5] != 0 || u[6] != 0 || u[4] >= 2)
-      throw std::runtime_error("two-body-current corrections to P / PS0 / RS* operators are not supported yet");
+    for (int i = 0; i < 3; i++) tb.lecs[i] = in.two_body_current_lecs[i];
+    tb.use_p = in.two_body_current_usep;
   }
   Nucleus& nucl = *p->nuc;
-  p->f = nucl.field(in.beta_type, in.operator_name, in.operator_k);          // a copy: the 2BC correction below edits it
-  if (in.compute_crossterms)
-    p->g = make_crossterms(p->f, [&](const std::string& beta, const std::string& l, int k) { return nucl.field(beta, l, k); });
-  if (mode != 0 && p->f.label == "GT" && u[4] != 0) {
-    if (u[2] != 1) throw std::runtime_error("two_body_current_mode: only the full-FAM Yukawa field read from <name>.tbc (2nd digit = 1) is supported");
-    apply_two_body_current_gt(d + "/" + in.fam_output_filename + ".tbc", b, in, u[1], p->f);
+  // fields with a two-body-current weight depend on the mode: they bypass the per-nucleus cache of one-body fields
+  auto field_of = [&](const std::string& beta, const std::string& l, int k, bool with_2bc) -> ExtField {
+    if (mode == 0 || !with_2bc) return nucl.field(beta, l, k);
+    return make_external_field(b, beta, l, k, nullptr, &tb);
+  };
+  {
+    // only these operators take the mode as the MAIN field (pnfam_solver.f90:574-578); every cross-term field except R
+    // takes it (setup_crossterms, pnfam_extfield.f90:910-944)
+    std::string L = in.operator_name;
+    for (auto& ch : L) ch = (char)std::toupper((unsigned char)ch);
+    const bool main_2bc = L == "P" || L == "PS0" || L == "RS0" || L == "RS1" || L == "RS2" || L == "RS0I" || L == "RS1I";
+    p->f = field_of(in.beta_type, in.operator_name, in.operator_k, main_2bc);     // a copy: the GT correction below edits it
   }
+  if (in.compute_crossterms)
+    p->g = make_crossterms(p->f, [&](const std::string& beta, const std::string& l, int k) { return field_of(beta, l, k, l != "R"); });
+  if (mode != 0 && p->f.label == "GT" && tb.u[4] != 0)
+    apply_two_body_current_gt(d + "/" + in.fam_output_filename + ".tbc", b, in, tb, p->f);
   p->setup_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   return p;
 }

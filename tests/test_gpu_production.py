@@ -156,3 +156,11 @@ def test_ill_conditioned_points_against_the_reference_run_here(gpu, tmp_path):
     print("ill-conditioned 6-shell points: %d (well-conditioned subset %d): worst vs reference-here %.2e (subset %.2e); "
           "reference here-vs-golden %.2e" % (n_all, n_well, worst_all, worst_well, ref_spread))
     assert n_well >= 200
+
+
+def test_closed_form_two_body_current_modes(gpu, tmp_path):
+    """configs[1] beyond the .tbc-fed Gamow-Teller field: nuclear-matter / LDA two-body currents of GT (symmetric and
+    asymmetric matter, 1BC+2BC and 2BC only), the (1 - correction) weight of RS0 / RS1 / RS2, the P and PS0 currents, with
+    the corrected cross-term fields -- against the reference binary (tests/golden/make_2bc_modes.py)."""
+    n, worst = check_fixture(gpu, "S40_2bc_modes", "points.json", str(tmp_path))
+    assert n == 11

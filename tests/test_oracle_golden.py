@@ -1,6 +1,8 @@
 """CPU tests: the oracle (host front-end + numpy FAM loop) against the reference's golden per-point outputs
 (tests/golden/*, extracted from mld1812/pynfam tests/**/fam_meta/*.tar by tests/golden/make_golden.py).
 Tolerance: 1e-9 relative on the complex strength and every cross-term (BASELINE.json north_star)."""
+import os
+
 import pytest
 
 from conftest import gold_rows, stage_point
@@ -60,3 +62,45 @@ def test_no_residual_interaction_two_steps(tmp_path):
 
 def test_broyden_uses_single_precision_mixing_factor():
     assert fo.ALPHAMIX == 0.699999988079071044921875
+
+
+@pytest.mark.parametrize("key", ["GT-K1-131100", "RS0-K0-121211", "P-K0-221110", "PS0-K0-121101"])
+def test_closed_form_two_body_current_fields(key, tmp_path):
+    """Host set-up of the nuclear-matter / LDA two-body-current modes (csrc/host/fam_setup.cpp: tbc_gt_rho_fac,
+    tbc_rsl_correction, tbc_p_correction, tbc_ps0_correction) through the CPU oracle against the reference binary's
+    results (tests/golden/make_2bc_modes.py): strength and every cross-term row, identical iteration count."""
+    import json
+    import shutil
+    from conftest import GOLDEN
+    from pynfam_b200 import host
+    g = os.path.join(GOLDEN, "S40_2bc_modes")
+    pt = json.load(open(os.path.join(g, "points.json")))["points"][key][0]
+    for f in ("hfbtho_NAMELIST.dat", "hfbtho_output.hel"):
+        shutil.copy(os.path.join(g, f), str(tmp_path))
+    (tmp_path / "x.in").write_text(pt["namelist"])
+    p = host.Problem(str(tmp_path), "x.in")
+    it, si, st = fo.solver_from_problem(p).solve(300, 1e-7)
+    assert it == pt["iters"]
+    labels = ["Strength"] + [p.label(i) for i in range(1, 1 + p.iscalar("nxterms"))]
+    for k, lab in enumerate(labels):
+        gold = complex(float(pt["rows"][lab][0]), float(pt["rows"][lab][1]))
+        assert abs(st[k] - gold) / abs(gold) < 1e-9, (key, lab)
+
+
+def test_unsupported_two_body_current_modes_fail_loudly(tmp_path):
+    """The density-matrix-expansion variants and the full-FAM field without its .tbc file are refused with a message."""
+    import json
+    import shutil
+    from conftest import GOLDEN
+    from pynfam_b200 import host
+    g = os.path.join(GOLDEN, "S40_2bc_modes")
+    pts = json.load(open(os.path.join(g, "points.json")))["points"]
+    for f in ("hfbtho_NAMELIST.dat", "hfbtho_output.hel"):
+        shutil.copy(os.path.join(g, f), str(tmp_path))
+    for key, old, new, msg in (("GT-K0-121100", "121100", "141100", "density-matrix-expansion"),
+                               ("P-K0-221110", "221110", "121120", "density-matrix-expansion"),
+                               ("GT-K0-121100", "121100", "111100", "tbc"),
+                               ("GT-K0-121100", "121100", "161100", "Invalid value")):
+        (tmp_path / "x.in").write_text(pts[key][0]["namelist"].replace(old, new))
+        with pytest.raises(host.PnfamError, match=msg):
+            host.Problem(str(tmp_path), "x.in")
