@@ -197,6 +197,34 @@ def loose_6sh(jobs):
         json.dump({"source": NOTE % "loose_6sh", "cases": out}, open(os.path.join(HERE, "loose_points_6sh.json"), "w"), indent=0)
 
 
+def thread_spread(threads):
+    """Reference vs itself at production size: every fixture point that needs >= 25 iterations is run again with
+    `threads` OpenMP/OpenBLAS threads (a different summation order inside its dgemm calls) and the difference to the
+    single-threaded fixture value is recorded -> tests/golden/ref_thread_spread.json"""
+    out = []
+    for case, fname in (("Gd162_SKOP_12sh", "points.json"), ("Gd162_SKOP_16sh", "prod_points.json"), ("Gd163_blocked_16sh", "points.json"),
+                        ("Gd162_SKOP_20sh", "prod_points.json"), ("Gd162_SKOP_24sh", "points.json")):
+        cd = os.path.join(HERE, case)
+        pts = json.load(open(os.path.join(cd, fname)))["points"]
+        for name, lst in pts.items():
+            for i, p in enumerate(lst):
+                if p["iters"] < 25:
+                    continue
+                wd = tempfile.mkdtemp()
+                refrun.stage(wd, cd)
+                open(os.path.join(wd, name + ".in"), "w").write(p["namelist"])
+                dat, wall, o = refrun.run_pnfam(wd, name + ".in", threads=threads, timeout=6 * 3600)
+                shutil.rmtree(wd, ignore_errors=True)
+                g = complex(float(p["rows"]["Strength"][0]), float(p["rows"]["Strength"][1]))
+                h = dat["rows"]["Strength"]
+                rec = {"case": case, "file": fname, "name": name, "index": i, "iters_1thread": p["iters"], "iters_threads": dat["iters"],
+                       "threads": threads, "rel": abs(h - g) / abs(g), "strength_threads": [repr(h.real), repr(h.imag)]}
+                out.append(rec)
+                print(rec, flush=True)
+                json.dump({"source": NOTE % ("thread_spread %d" % threads), "points": out},
+                          open(os.path.join(HERE, "ref_thread_spread.json"), "w"), indent=0)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("case")
@@ -214,6 +242,8 @@ def main():
         gd162_small_large(24, a.jobs, [3, 9, 15, 21, 26, 29])
     elif a.case == "loose_6sh":
         loose_6sh(a.jobs)
+    elif a.case == "thread_spread":
+        thread_spread(a.jobs)
     else:
         raise SystemExit("unknown case")
 
