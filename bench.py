@@ -269,9 +269,16 @@ def main():
     ap.add_argument("--ref-iters", type=int, default=4)
     ap.add_argument("--assumed-iters-per-point", type=float, default=25.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--full-contour", action="store_true",
+                    help="BASELINE.json configs[3], the north-star target run: all 14 allowed + first-forbidden (operator, K) x "
+                         "the computed half of pynfam's 60-node CIRCLE contour, cross-terms on, sharded over the GPUs; one "
+                         "step = the whole nucleus from the two HFB files to OP.out / OP.out.ctr (use --shells 20)")
     args = ap.parse_args()
     global SHELLS
     SHELLS = args.shells
+    if args.full_contour and args.impl == "b200":
+        run_full_contour(args)
+        return
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -428,6 +435,127 @@ def main():
         if saved_stdout is not None:
             sys.stdout.flush()
             os.dup2(saved_stdout, 1)
+        print(json.dumps(line))
+        sys.stdout.flush()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+FULL_OPERATORS = [("F-", 0), ("GT-", 0), ("GT-", 1), ("RS0-", 0), ("PS0-", 0), ("R-", 0), ("P-", 0), ("RS1-", 0), ("R-", 1), ("P-", 1),
+                  ("RS1-", 1), ("RS2-", 0), ("RS2-", 1), ("RS2-", 2)]   # operators sharing cross-term fields are neighbours
+
+
+def run_full_contour(args):
+    """The north-star target run through the public driver (pynfam_b200.strength.run_contours_sharded): one step = the
+    full beta-decay contour of 162Gd from hfbtho_NAMELIST.dat + hfbtho_output.hel to the strength files, wall clock
+    between barriers, max over ranks.  Timed steps start in a FRESH run directory (no set-up cache); `warm_cache_s` is one
+    more run in a directory that already holds the cache.  The strengths are compared, outside the timed region, with the
+    reference binary's converged results at the contour points of tests/golden/Gd162_SKOP_<n>sh/prod_points.json."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from pynfam_b200.strength import famContour, run_contours_sharded
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    # torchrun pins OMP_NUM_THREADS=1; the host set-up is OpenMP code: an even share of the cores per rank (rank 0 takes
+    # all of them while it reconstructs the HFB solution for everybody)
+    from pynfam_b200 import host
+    host.set_threads(max(1, (os.cpu_count() or 1) // world))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the FAM iteration has no CPU fallback")
+    torch.cuda.set_device(local)
+    saved_stdout = None
+    if world > 1:
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.all_reduce(torch.zeros(1, device="cuda"))           # NCCL communicator set-up is not part of the workload
+    contour = famContour("CIRCLE", {"energy_min": 0.0, "energy_max": 10.0, "nr_points": 60})
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def one_run(wd):
+        if rank == 0:
+            stage(wd, 1.0 + 1.0j, 300)
+        sync()
+        dest = os.path.join(wd, "out_%d" % rank)
+        os.makedirs(dest, exist_ok=True)
+        t0 = time.perf_counter()
+        fss = run_contours_sharded(wd, "GT-K0.in", FULL_OPERATORS, contour, dest=dest, dist=dist if world > 1 else None, device=local)
+        sync()
+        return time.perf_counter() - t0, fss, dict(run_contours_sharded.last_timing), dest
+
+    def shared_dir(tag):
+        # every rank works in the same run directory (rank 0 names it)
+        name = [tempfile.mkdtemp(prefix="fullctr_%s_" % tag)] if rank == 0 else [None]
+        if world > 1:
+            dist.broadcast_object_list(name, src=0)
+        return name[0]
+
+    wd = shared_dir("warm")
+    for _ in range(max(1, min(args.warmup, 2))):
+        one_run(wd)
+    sampler = ClockSampler(local)
+    sampler.start()
+    walls, parts = [], []
+    fss = dest = None
+    for k in range(args.steps):
+        w, fss, tm, dest = one_run(shared_dir("step%d" % k))
+        walls.append(w)
+        parts.append(tm)
+    sampler.stop_flag = True
+    warm_s, _, warm_tm, _ = one_run(wd)
+    t = torch.tensor([sum(walls), warm_s] + [sum(p[k] for p in parts) for k in ("host_setup_s", "solve_s", "gather_and_write_s")],
+                     dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t = t.cpu().numpy()
+    if saved_stdout is not None:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+    if rank == 0:
+        iters = int(sum(int(np.sum(f.iters)) for f in fss))
+        npts = len(FULL_OPERATORS) * contour.nr_compute
+        # parity: the reference binary's converged strengths at one contour point of every operator
+        worst, npar = None, 0
+        path = os.path.join(case_dir(), "prod_points.json")
+        if os.path.isfile(path):
+            gold = json.load(open(path))["points"]
+            byname = {f.opname: f for f in fss}
+            worst = 0.0
+            for name, lst in gold.items():
+                for pt in lst:
+                    f, i = byname.get(name), pt.get("contour_index")
+                    if f is None or i is None or i >= contour.nr_compute:
+                        continue
+                    g = complex(float(pt["rows"]["Strength"][0]), float(pt["rows"]["Strength"][1]))
+                    got = complex(f.str_df["Re(Strength)"].values[i], f.str_df["Im(Strength)"].values[i])
+                    worst = max(worst, abs(got - g) / abs(g))
+                    npar += 1
+        sec = t[0] / args.steps
+        line = {
+            "metric": "FAM omega-points/s, full beta-decay contour of one nucleus (iterations/s in iterations_per_s)",
+            "value": npts / sec, "unit": "omega-points/s", "n_gpus": world, "steps": args.steps, "warmup": max(1, min(args.warmup, 2)),
+            "ms_per_step": 1e3 * sec, "seconds": sec, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "Gd162 SkO' %d shells 40x40 grid, full beta-decay contour: %d (operator, K) x %d computed points of "
+                                   "the 60-node CIRCLE contour on [0, 10] MeV, cross-terms on" % (SHELLS, len(FULL_OPERATORS), contour.nr_compute),
+                       "shells": SHELLS, "nghl": 1600, "eps": 1e-7, "broyden_history": 50, "max_iter": 300},
+            "omega_points": npts, "iterations": iters, "iterations_per_s": iters / sec,
+            "all_converged": bool(all(f.meta["Conv"] == "Yes" for f in fss)),
+            "max_over_ranks_s": {"host_setup": t[2] / args.steps, "solves": t[3] / args.steps, "gather_and_write": t[4] / args.steps},
+            "warm_cache_s": float(t[1]),
+            "e2e": {"value": npts / sec, "unit": "omega-points/s", "note": "the step IS end to end: HFB files -> set-up on the host -> "
+                    "context + operator uploads -> solves -> strengths back -> one all_reduce -> OP.out / OP.out.ctr on disk"},
+            "parity_max_rel": worst, "parity_points": npar,
+            "host_threads": os.cpu_count(), "clocks": sampler.summary(),
+            "files": sorted(os.listdir(dest))[:4] + ["..."],
+        }
         print(json.dumps(line))
         sys.stdout.flush()
     if world > 1:

@@ -41,6 +41,11 @@ int pnfam_problem_array_f64(pnfam_problem* p, const char* name, const double** p
 int pnfam_problem_array_i32(pnfam_problem* p, const char* name, const int32_t** ptr, int64_t* n);
 /* which: 0 operator label, 1..nxterms cross-term labels, -1 interaction name, -2 output base name */
 int pnfam_problem_label(const pnfam_problem* p, int which, char* out, int outlen);
+/* OpenMP threads of the host set-up (n <= 0: unchanged); returns the previous setting.  The reconstructed HFB solution
+ * is kept in <rundir>/.pnfam_b200_hfb_<hash of the two input files>.cache (PNFAM_B200_CACHE_DIR: another directory,
+ * PNFAM_B200_NO_CACHE: off): later launches in directories holding the same two files load it instead of repeating
+ * gamdel / hfbdiag / DENSIT. */
+int pnfam_host_set_threads(int n);
 
 /* ------------------------------------------------------------------------------------------------
  * 2. The FAM iteration on the GPU (libpnfam_b200.so, CUDA sm_100a) -- THE HOT PATH

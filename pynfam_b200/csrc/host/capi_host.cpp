@@ -3,6 +3,8 @@
 #include <map>
 #include <string>
 
+#include <omp.h>
+
 #include "../../../include/pnfam_b200.h"
 #include "problem.hpp"
 
@@ -144,6 +146,14 @@ int pnfam_problem_label(const pnfam_problem* h, int which, char* out, int outlen
   else return 1;
   set_err(out, outlen, s);
   return 0;
+}
+
+// number of OpenMP threads of the host set-up (HFB reconstruction, tables, external fields); n <= 0: leave unchanged.
+// Returns the previous setting.
+int pnfam_host_set_threads(int n) {
+  const int prev = omp_get_max_threads();
+  if (n > 0) omp_set_num_threads(n);
+  return prev;
 }
 
 }  // extern "C"

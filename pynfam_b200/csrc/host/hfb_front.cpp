@@ -14,6 +14,8 @@
 #include <cstdlib>
 #include "hfb_front.hpp"
 
+#include <unistd.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -749,7 +751,90 @@ static void densit_rho(HfbSolution& s) {
 }
 
 // ---------------------------------------------------------------------------------------------
-HfbSolution HfbSolution::build(const HfbInput& in, const HelData& h) {
+// Cache of the expensive stages.  Not part of the reference (which repeats the whole zero-iteration HFBTHO run in every
+// pnfam_main.x launch, 4-18 s at 16 shells); SURVEY.md section 8f row 4.
+unsigned long long hash_file(const std::string& path, unsigned long long seed) {
+  FILE* f = std::fopen(path.c_str(), "rb");
+  if (!f) return 0;
+  unsigned long long h = seed ? seed : 1469598103934665603ull;
+  unsigned char buf[1 << 16];
+  size_t n;
+  while ((n = std::fread(buf, 1, sizeof buf, f)) > 0)
+    for (size_t i = 0; i < n; i++) { h ^= buf[i]; h *= 1099511628211ull; }
+  std::fclose(f);
+  return h ? h : 1;
+}
+
+namespace {
+constexpr unsigned long long CACHE_MAGIC = 0x42323030484642ull + (2ull << 56);   // "B200HFB", format 2
+struct CacheIO {
+  FILE* f;
+  bool ok = true, writing;
+  CacheIO(FILE* f_, bool w) : f(f_), writing(w) {}
+  void raw(void* p, size_t n) {
+    if (!ok || n == 0) return;
+    ok = (writing ? std::fwrite(p, 1, n, f) : std::fread(p, 1, n, f)) == n;
+  }
+  template <class T> void pod(T& x) { raw(&x, sizeof(T)); }
+  template <class T> void vec(std::vector<T>& v) {
+    unsigned long long n = v.size();
+    pod(n);
+    if (!ok) return;
+    if (!writing) {
+      if (n > (1ull << 32)) { ok = false; return; }
+      v.resize((size_t)n);
+    }
+    raw(v.data(), (size_t)n * sizeof(T));
+  }
+};
+// the fields written by gamdel / hfbdiag / densit_rho
+void cache_fields(CacheIO& io, HfbSolution& s) {
+  for (int it = 0; it < 2; it++) {
+    io.vec(s.hmat[it]); io.vec(s.dmat[it]); io.vec(s.E[it]); io.vec(s.U[it]); io.vec(s.V[it]);
+    io.vec(s.ka[it]); io.vec(s.kd[it]); io.vec(s.Kqp[it]); io.vec(s.Kpwi[it]); io.vec(s.occ[it]); io.vec(s.ro[it]);
+    io.pod(s.ala[it]); io.pod(s.ala_out[it]); io.pod(s.inner[it]); io.pod(s.klmax[it]);
+    io.pod(s.keyblo[it]); io.pod(s.blo_block[it]); io.pod(s.blo_state[it]); io.pod(s.blok1k2d[it]);
+  }
+}
+bool cache_load(const std::string& path, unsigned long long key, HfbSolution& s) {
+  FILE* f = std::fopen(path.c_str(), "rb");
+  if (!f) return false;
+  CacheIO io(f, false);
+  unsigned long long magic = 0, k = 0, tail = 0;
+  int nt = 0, nghl = 0;
+  io.pod(magic); io.pod(k); io.pod(nt); io.pod(nghl);
+  bool good = io.ok && magic == CACHE_MAGIC && k == key && nt == s.nt && nghl == s.nghl;
+  if (good) {
+    cache_fields(io, s);
+    io.pod(tail);
+    good = io.ok && tail == (key ^ CACHE_MAGIC) && (int)s.E[0].size() == s.nt && (int)s.ro[0].size() == s.nghl;
+    if (!good)                                      // truncated / foreign file: forget what was read, recompute
+      for (int it = 0; it < 2; it++) {
+        s.hmat[it].clear(); s.dmat[it].clear(); s.E[it].clear(); s.U[it].clear(); s.V[it].clear();
+        s.ka[it].clear(); s.kd[it].clear(); s.Kqp[it].clear(); s.Kpwi[it].clear(); s.occ[it].clear(); s.ro[it].clear();
+        s.ala[it] = s.ala_out[it] = 0; s.inner[it] = s.klmax[it] = 0;
+        s.keyblo[it] = s.blo_block[it] = s.blo_state[it] = s.blok1k2d[it] = 0;
+      }
+  }
+  std::fclose(f);
+  return good;
+}
+void cache_save(const std::string& path, unsigned long long key, HfbSolution& s) {
+  const std::string tmp = path + ".tmp" + std::to_string((long)getpid());
+  FILE* f = std::fopen(tmp.c_str(), "wb");
+  if (!f) return;                                   // read-only directory: no cache, no error
+  CacheIO io(f, true);
+  unsigned long long magic = CACHE_MAGIC, k = key, tail = key ^ CACHE_MAGIC;
+  io.pod(magic); io.pod(k); io.pod(s.nt); io.pod(s.nghl);
+  cache_fields(io, s);
+  io.pod(tail);
+  const bool ok = io.ok;
+  std::fclose(f);
+  if (!ok || std::rename(tmp.c_str(), path.c_str()) != 0) std::remove(tmp.c_str());
+}
+}  // namespace
+
+HfbSolution HfbSolution::build(const HfbInput& in, const HelData& h, const std::string& cache_file, unsigned long long cache_key) {
   if (in.type_of_calculation < 0) throw std::runtime_error("Lipkin-Nogami (type_of_calculation<0) is not supported");
   if (in.set_temperature && std::fabs(in.temperature) > 1e-10)
     throw std::runtime_error("finite-temperature HFB solutions are not supported yet");
@@ -797,6 +882,11 @@ HfbSolution HfbSolution::build(const HfbInput& in, const HelData& h) {
     }
   };
   lap("basis, tables");
+  if (!cache_file.empty() && cache_key != 0 && cache_load(cache_file, cache_key, s)) {
+    s.from_cache = true;
+    lap("cache load");
+    return s;
+  }
   gamdel(s, h);
   lap("gamdel");
   // the blocking request is by |2*Omega| with the sign telling particle/hole
@@ -807,6 +897,10 @@ HfbSolution HfbSolution::build(const HfbInput& in, const HelData& h) {
   lap("hfbdiag");
   densit_rho(s);
   lap("densit");
+  if (!cache_file.empty() && cache_key != 0) {
+    cache_save(cache_file, cache_key, s);
+    lap("cache save");
+  }
   return s;
 }
 

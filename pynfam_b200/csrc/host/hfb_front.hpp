@@ -94,8 +94,17 @@ struct HfbSolution {
   bool use_j2terms = false;
   double pwi = 0;
 
-  static HfbSolution build(const HfbInput& in, const HelData& hel);
+  // cache_file (optional): where the results of the expensive stages (gamdel, hfbdiag, DENSIT: E, U, V, pairing-window
+  // bookkeeping, Fermi levels, blocking indices, rho) are kept between processes; cache_key = hash of the two input
+  // files.  A file with a matching key is loaded instead of recomputing (bit-identical doubles); otherwise the
+  // solution is computed and the file (re)written atomically.
+  static HfbSolution build(const HfbInput& in, const HelData& hel, const std::string& cache_file = "",
+                           unsigned long long cache_key = 0);
+  bool from_cache = false;
 };
+
+// FNV-1a hash of the bytes of a file, continued from `seed` (0 = start); 0 if the file cannot be read.
+unsigned long long hash_file(const std::string& path, unsigned long long seed = 0);
 
 // Symmetric eigen-solver (Householder tridiagonalisation + implicit QL), ascending eigenvalues.
 // a: n x n column-major, lower triangle referenced; on exit z (n x n col-major) = eigenvectors.

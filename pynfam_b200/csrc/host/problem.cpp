@@ -23,8 +23,20 @@ std::shared_ptr<Nucleus> Nucleus::load(const std::string& rundir) {
   n->hfb_in = HfbInput::read(d + "/hfbtho_NAMELIST.dat");
   n->hel = HelData::read(d + "/hfbtho_output.hel");
   lap("read files");
-  n->hfb = HfbSolution::build(n->hfb_in, n->hel);
-  lap("HFB reconstruction");
+  // cache of the reconstructed solution next to the input files (PNFAM_B200_CACHE_DIR: elsewhere; PNFAM_B200_NO_CACHE:
+  // off), keyed by the bytes of both files: pynfam launches one pnfam_main.x per omega point in directories holding
+  // copies of the same two files, and every rank of a sharded run sets up the same nucleus
+  std::string cache_file;
+  unsigned long long key = 0;
+  if (!getenv("PNFAM_B200_NO_CACHE")) {
+    key = hash_file(d + "/hfbtho_output.hel", hash_file(d + "/hfbtho_NAMELIST.dat"));
+    const char* cd = getenv("PNFAM_B200_CACHE_DIR");
+    char name[64];
+    std::snprintf(name, sizeof name, "/.pnfam_b200_hfb_%016llx.cache", key);
+    cache_file = (cd && *cd ? std::string(cd) : d) + name;
+  }
+  n->hfb = HfbSolution::build(n->hfb_in, n->hel, cache_file, key);
+  lap(n->hfb.from_cache ? "HFB solution (cache)" : "HFB reconstruction");
   n->basis = FamBasis::build(n->hfb);
   lap("FAM basis and tables");
   return n;

@@ -28,12 +28,18 @@ def lib():
         L.pnfam_problem_array_i32.argtypes = [vp, cp, ctypes.POINTER(ctypes.POINTER(ctypes.c_int32)),
                                               ctypes.POINTER(ctypes.c_int64)]
         L.pnfam_problem_label.argtypes = [vp, ci, cp, ci]
+        L.pnfam_host_set_threads.argtypes = [ci]
         _LIB = L
     return _LIB
 
 
 class PnfamError(RuntimeError):
     pass
+
+
+def set_threads(n):
+    """OpenMP threads of the host set-up (n <= 0: unchanged); returns the previous setting."""
+    return int(lib().pnfam_host_set_threads(int(n)))
 
 
 class Problem:

@@ -614,13 +614,16 @@ def run_contours(rundir, namelist, operators, contour, dest=None, device=0, **so
     return out
 
 
-def run_contours_sharded(rundir, namelist, operators, contour, dest=None, dist=None, device=0, solve_points=None, **solve_kw):
+def run_contours_sharded(rundir, namelist, operators, contour, dest=None, dist=None, device=0, solve_points=None,
+                         concurrent_solves=None, **solve_kw):
     """run_contours over the ranks of a torch.distributed job (one process per GPU): the (operator, contour point) tasks
     are dealt to the ranks by shard.partition_tasks, every rank sets the nucleus and the operators it owns up once and solves its points of each
     operator as one batch, and the ONLY exchange is one all_reduce of the strengths (disjoint ownership, so a sum is a
     gather; the row labels travel beside it) -- NCCL on GPUs, gloo in the CPU tests.  Rank 0 assembles and writes OP.out / OP.out.ctr for every operator;
     every rank returns the list of famStrength objects.  `solve_points(fs, prob, ctx, points)` may replace the GPU
-    solve (tests)."""
+    solve (tests).  concurrent_solves (default 2, PNFAM_B200_CONCURRENT_SOLVES): operators of a rank solved side by side,
+    each by its own host thread on its own context and stream, so that the tail of one batch (the few near-axis points
+    that need twice the iterations of the others) overlaps with the bulk of the next operator's."""
     import torch
     from . import shard
     dest = rundir if dest is None else dest
@@ -634,25 +637,41 @@ def run_contours_sharded(rundir, namelist, operators, contour, dest=None, dist=N
     t_start = time.perf_counter()
     fss = [famStrength(op, k, contour) for op, k in operators]
     probs, first = {}, None
+    if multi:
+        # The HFB reconstruction is the same on every rank: rank 0 does it once with all host threads and leaves the
+        # solution in the set-up cache of the run directory (csrc/host/hfb_front.cpp), the other ranks load it.
+        if rank == 0:
+            from . import host
+            prev = host.set_threads(os.cpu_count() or 1)
+            o0 = next((o for o, idx in mine if len(idx)), 0)
+            probs[o0] = fss[o0].setup(rundir, namelist)
+            first = probs[o0]
+            host.set_threads(prev)
+        dist.barrier()
     for o, idx in mine:
-        if len(idx):
+        if len(idx) and o not in probs:
             probs[o] = fss[o].setup(rundir, namelist, share_nucleus_with=first)
             first = first or probs[o]
     t_setup = time.perf_counter()
     nstr = NSTR_MAX
     buf = np.zeros((len(operators), nc, 2 * nstr + 3))          # re | im | conv, iterations, minutes
     labels = {}
-    ctx = None
-    for o, idx in mine:
-        if len(idx) == 0:
-            continue
+    work = [(o, idx) for o, idx in mine if len(idx)]
+    if concurrent_solves is None:
+        concurrent_solves = int(os.environ.get("PNFAM_B200_CONCURRENT_SOLVES", "2"))
+    nworkers = max(1, min(int(concurrent_solves), len(work)))
+    import threading
+    tls = threading.local()
+
+    def job(item):
+        o, idx = item
         if solve_points is not None:
-            res = solve_points(fss[o], probs[o], ctx, idx)
+            res = solve_points(fss[o], probs[o], None, idx)
         else:
-            if ctx is None:
+            if getattr(tls, "ctx", None) is None:
                 from . import gpu
-                ctx = gpu.Context(probs[o], device=device)
-            res = fss[o].solve_points(probs[o], ctx, points=idx, **solve_kw)
+                tls.ctx = gpu.Context(probs[o], device=device)       # one context (stream, side streams) per host thread
+            res = fss[o].solve_points(probs[o], tls.ctx, points=idx, **solve_kw)
         n1 = res["strength"].shape[1]
         if n1 > nstr:
             raise RuntimeError("operator with more than %d strength columns" % nstr)
@@ -662,6 +681,15 @@ def run_contours_sharded(rundir, namelist, operators, contour, dest=None, dist=N
         buf[o, idx, 2 * nstr] = res["conv"]
         buf[o, idx, 2 * nstr + 1] = res["iters"]
         buf[o, idx, 2 * nstr + 2] = res["minutes"]
+
+    if nworkers <= 1:
+        for item in work:
+            job(item)
+    else:
+        from concurrent.futures import ThreadPoolExecutor
+        # the largest batches first: the pool drains with the small ones
+        with ThreadPoolExecutor(nworkers) as ex:
+            list(ex.map(job, sorted(work, key=lambda w: -len(w[1]))))
     t_solve = time.perf_counter()
     meta = {"nucleus": fss[mine[0][0]].nucleus, "meta": dict(fss[mine[0][0]]._meta)} if mine and len(mine[0][1]) else None
     if multi:

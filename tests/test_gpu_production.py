@@ -59,7 +59,7 @@ def check_fixture(gpu, case, fname, wd, separable=True, slots=0, expect_efa=None
     if not os.path.isfile(path):
         pytest.skip("fixture %s/%s not generated" % (case, fname))
     pts = json.load(open(path))["points"]
-    base, ctx, n, worst, worst_loose, n_loose = None, None, 0, 0.0, 0.0, 0
+    base, ctx, n, worst, worst_loose, n_loose, n_shift = None, None, 0, 0.0, 0.0, 0, 0
     for op, lst in pts.items():
         stage(case, lst[0]["namelist"], wd, op + ".in")
         p = host.Problem(wd, op + ".in", share_nucleus_with=base)
@@ -72,25 +72,39 @@ def check_fixture(gpu, case, fname, wd, separable=True, slots=0, expect_efa=None
         for i, pt in enumerate(lst):
             assert pt["conv"], "fixture point did not converge in the reference"
             loose = pt["iters"] >= LOOSE_ITERS
+            it_gpu, it_ref = int(r["iters"][i]), pt["iters"]
             assert int(r["conv"][i]) == 1
-            if loose:
-                assert abs(int(r["iters"][i]) - pt["iters"]) <= 1, (op, i, int(r["iters"][i]), pt["iters"])
-            else:
-                assert int(r["iters"][i]) == pt["iters"], (op, i, int(r["iters"][i]), pt["iters"])
             rows = {k: complex(float(v[0]), float(v[1])) for k, v in pt["rows"].items()}
-            floor = 1e-6 * max(abs(v) for k, v in rows.items() if k != "Energy")
-            for k, lab in enumerate(["Strength"] + r["labels"][1:]):
-                if lab in rows:
-                    err = abs(r["strength"][i, k] - rows[lab]) / max(abs(rows[lab]), floor)
-                    if loose:
-                        worst_loose = max(worst_loose, err)
-                    else:
-                        worst = max(worst, err)
-                    assert err < (max(tol, LOOSE_TOL) if loose else tol), (case, op, i, lab, err)
+            s_ref = rows["Strength"]
+            if it_gpu != it_ref:
+                # The stopping rule max|dX| < eps triggered one step apart (only tolerated in the ill-conditioned class).
+                # Stopped earlier: the state must equal the reference's OWN state at that iteration (its trace prints 10
+                # digits).  Stopped later: within one last-step change of the reference's result.
+                assert loose and abs(it_gpu - it_ref) == 1, (op, i, it_gpu, it_ref)
+                tr = {t[0]: complex(t[3], t[4]) for t in pt["trace"]}
+                step = abs(tr[it_ref] - tr[it_ref - 1]) / abs(s_ref)
+                if it_gpu < it_ref:
+                    err = abs(r["strength"][i, 0] - tr[it_gpu]) / abs(s_ref)
+                    assert err < LOOSE_TOL, (case, op, i, "vs the reference trace at iteration %d" % it_gpu, err)
+                else:
+                    err = abs(r["strength"][i, 0] - s_ref) / abs(s_ref)
+                    assert err < LOOSE_TOL + 1.5 * step, (case, op, i, "one step beyond the reference", err, step)
+                worst_loose = max(worst_loose, err)
+                n_shift += 1
+            else:
+                floor = 1e-6 * max(abs(v) for k, v in rows.items() if k != "Energy")
+                for k, lab in enumerate(["Strength"] + r["labels"][1:]):
+                    if lab in rows:
+                        err = abs(r["strength"][i, k] - rows[lab]) / max(abs(rows[lab]), floor)
+                        if loose:
+                            worst_loose = max(worst_loose, err)
+                        else:
+                            worst = max(worst, err)
+                        assert err < (max(tol, LOOSE_TOL) if loose else tol), (case, op, i, lab, err)
             n += 1
             n_loose += loose
-    print("%s/%s: %d points: worst relative error %.2e on the %d well-conditioned ones (< 25 iterations), %.2e on the %d others"
-          % (case, fname, n, worst, n - n_loose, worst_loose, n_loose))
+    print("%s/%s: %d points: worst relative error %.2e on the %d well-conditioned ones (< 25 iterations), %.2e on the %d others "
+          "(%d of them stopped one iteration apart from the reference)" % (case, fname, n, worst, n - n_loose, worst_loose, n_loose, n_shift))
     return n, worst
 
 
