@@ -347,8 +347,15 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sf_density_kernel(HamArgs g, Sf
   }
 }
 
+void launch_sf_pack(const HamArgs& a, cudaStream_t stream) {
+  const SfDev& S = a.sf;
+  const int maxsteps = std::max(std::max(S.nsteps[0], S.nsteps[1]), std::max(S.nsteps[2], S.nsteps[3]));
+  if (a.nactive > 0 && maxsteps > 0) sf_pack_kernel<<<dim3(maxsteps, 4, a.nactive), 256, 0, stream>>>(a);
+}
+
 void launch_density_sf(const HamArgs& a, cudaStream_t stream) {
   if (a.nactive <= 0) return;
+  if (a.sf2.enabled) { launch_density_sf2(a, stream); return; }
   const SfDev& S = a.sf;
   const SfDensLayout L = make_dens_layout(S);
   static PerDeviceMax attr_bytes;
@@ -685,6 +692,7 @@ __global__ void sf_projection_reduce_kernel(HamArgs g, int ksplit) {
 
 void launch_projection_sf(const HamArgs& a, cudaStream_t stream) {
   if (a.nactive <= 0) return;
+  if (a.sf2.enabled) { launch_projection_sf2(a, stream); return; }
   const SfDev& S = a.sf;
   const SfProjLayout L0 = make_proj_layout<0>(S), L1 = make_proj_layout<1>(S);
   static PerDeviceMax attr0, attr1;

@@ -144,6 +144,44 @@ struct SfDev {
   int ntiles[2][2] = {{0, 0}, {0, 0}};
   int ksplit = 1;
 };
+// ---- fully factorised path (hamiltonian_sf2.cu) ----------------------------------------------------------------
+// phi^t_a(ih, il) = Z^m(n_z(a), ih) R^j_a(il) on BOTH sides of every grid contraction:
+//   density     D^{tt'}_{ss'}(ih,il) = sum_{zr,zr'} Z^m(zr,ih) Z^m'(zr',ih) Pi^{jj'}_{ss'}[zr][zr'][il],
+//               Pi^{jj'}[zr][zr'][il] = sum_{a in (s,zr), b in (s',zr')} R^j_a(il) rho_ab R^j'_b(il)       (radial part, O(nxy ngl))
+//   projection  kt^{jj'}_{sa sb}[zr][zr'][il] = sum_{(t,t')->(j,j')} sum_ih Z^m(zr,ih) mf^{tt'}(ih,il) Z^m'(zr',ih)
+//               h_ab = 2 sum_il sum_{jj'} R^j_a(il) kt^{jj'}[zr_a][zr_b][il] R^j'_b(il)                      (radial part, O(nxy ngl))
+// (zr: row of the z table = distinct n_z of the whole basis, <= N_sh + 3).  The number of executed flops no longer
+// scales with ngh * nxy: ~10x fewer than the one-sided factorisation of hamiltonian_sf.cu at 16 shells.
+constexpr int SF2_NJJ = 11;      // (j, j') combinations of the radial factors in the mean field:
+                                 // (0,0) (0,1) (0,2) (0,3) (1,0) (1,1) (1,2) (2,0) (2,1) (2,2) (3,0)
+constexpr int SF2_RUN = 8;       // columns per task of the radial projection (runs of equal n_z are cut at this length)
+struct Sf2Pair {                 // one (rows of one n_z slot) x (columns of one n_z run) sub-block of rho / kappa
+  int img_off, na, nb;           // offset (doubles) of its packed copy [b][a][re,im] (contiguous), rows, columns
+  int src_off, src_ld;           // element offset of the block in the block matrix, leading dimension
+  int a_row0, b_row0;            // padded rows of the first row / column (radial factors, p2l)
+  int pad;
+};
+struct Sf2Task {                 // radial projection: one row a x a run of <= SF2_RUN columns with equal n_z
+  int pa, pb0, nb;               // padded row of a, of the first column, columns
+  int out_base, ld;              // element offset of the block in the block matrix, leading dimension
+  int sasb;                      // spin combination 2 sa + sb
+};
+struct Sf2Dev {
+  int enabled = 0;
+  int nzr = 0;
+  const Sf2Pair* pairs[4] = {nullptr, nullptr, nullptr, nullptr};     // rho q0, rho q1, kappa q0, kappa q1
+  const int* pair_ptr[4] = {nullptr, nullptr, nullptr, nullptr};      // [4 sweeps][nzr*nzr + 1]
+  const int2* zrange[4] = {nullptr, nullptr, nullptr, nullptr};       // [4 sweeps][nzr]: zr' range with non-empty pair lists
+  const int* order[4] = {nullptr, nullptr, nullptr, nullptr};          // [4 sweeps][1 + nzr*nzr]: count, then the non-empty (zr, zr')
+                                                                       // entries by decreasing work (balanced dealing to the lanes)
+  const Sf2Task* tasks[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [h / Delta][pass]
+  int ntasks[2][2] = {{0, 0}, {0, 0}};
+  const unsigned char* need[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [h / Delta][pass]: [4 sasb][nzr*nzr] kt entries in use
+  int npairs_max = 0;                  // longest of the four sub-block lists
+  double* kt[2] = {nullptr, nullptr};  // [slot za][2 q][4 sasb][ngl][nzr*nzr][NJJ or 1][2]
+};
+__host__ __device__ inline size_t sf2_kt_elems(int mode, int ngl, int nzr) { return (size_t)4 * ngl * nzr * nzr * (mode == 0 ? SF2_NJJ : 1) * 2; }
+
 __host__ __device__ inline size_t sf_mf_elems(int ngl, int kih) { return (size_t)ngl * 4 * SF_MFP * kih * 2; }
 constexpr int SF_DIL = 4;       // Gauss-Laguerre nodes per iteration of the Delta projection (their work is a quarter of h's)
 // pf[sa][sb][il][ih][c] with SF_DIL rows of zero padding per (sa, sb): SF_DIL consecutive nodes are one linear copy
@@ -153,6 +191,7 @@ struct SideStreams;
 struct HamArgs {
   DevBasis basis;
   SfDev sf;
+  Sf2Dev sf2;
   // per pass q=0 (pn,+) / q=1 (np,-): input structures (dRsp quadrants) and output structures (dHsp quadrants)
   DevBlockStruct rho_in[2], kap_in[2], h_out[2], d_out[2];
   int rho_quad[2], kap_quad[2];   // storage quadrant of rho / kappa (and of h / Delta) for each pass
@@ -226,6 +265,10 @@ size_t projection_partial_elems(const ProjPlan& pp, size_t nxy);
 // sum-factorised variants (hamiltonian_sf.cu)
 void launch_density_sf(const HamArgs& a, cudaStream_t stream);
 void launch_projection_sf(const HamArgs& a, cudaStream_t stream);
+void launch_density_sf2(const HamArgs& a, cudaStream_t stream);     // hamiltonian_sf2.cu
+void launch_projection_sf2(const HamArgs& a, cudaStream_t stream);
+void launch_sf_pack(const HamArgs& a, cudaStream_t stream);          // packed rho / kappa images (hamiltonian_sf.cu)
+int sf2_smem_bytes(const SfDev& S);
 int sf_density_smem_bytes(const SfDev& S);      // dynamic shared memory the kernels need for this basis
 int sf_projection_smem_bytes(const SfDev& S);
 

@@ -128,6 +128,8 @@ struct pnfam_b200_ctx {
   // sum-factorised path (separable basis, hamiltonian_sf.cu)
   SfDev sf{};
   std::vector<int> seg_prow0, seg_n, seg_nslots;   // per (block, spin) segment: first padded row, states, n_z slots
+  std::vector<int> h_zrow, h_p2l;                   // host copies of the per-padded-row tables (list building)
+  bool sf2 = false;                                 // fully factorised kernels (hamiltonian_sf2.cu)
   DBuf<double> d_zt, d_rg, d_rgp;
   DBuf<int> d_zrow, d_p2l, d_slot, d_segtab;
   cudaStream_t stream = nullptr;
@@ -223,6 +225,7 @@ static bool setup_separable(pnfam_b200_ctx& c, const pnfam_b200_model& m) {
         const int il = std::min(2 * ip + k, ngl - 1);
         for (int j = 0; j < 4; j++) rgp[((size_t)ip * c.dqp_p + pr) * 8 + k * 4 + j] = rg[((size_t)il * c.dqp_p + pr) * 4 + j];
       }
+  c.h_zrow = zrow; c.h_p2l = p2l;
   c.d_rgp.upload(rgp);
   c.d_zt.upload(zt); c.d_rg.upload(rg); c.d_zrow.upload(zrow); c.d_p2l.upload(p2l); c.d_slot.upload(slot); c.d_segtab.upload(segtab);
   SfDev& S = c.sf;
@@ -235,6 +238,8 @@ static bool setup_separable(pnfam_b200_ctx& c, const pnfam_b200_model& m) {
   S.nbc_max = 32;
   if (sf_density_smem_bytes(S) > 227 * 1024) S.nbc_max = 16;
   if (sf_density_smem_bytes(S) > 227 * 1024 || sf_projection_smem_bytes(S) > 227 * 1024) return S.enabled = 0, false;
+  // both-sided factorisation (default; PNFAM_B200_SF1 keeps the one-sided kernels of hamiltonian_sf.cu)
+  c.sf2 = !getenv("PNFAM_B200_SF1") && sf2_smem_bytes(S) <= 227 * 1024;
   return true;
 }
 
@@ -364,6 +369,23 @@ extern "C" void pnfam_b200_ctx_destroy(pnfam_b200_ctx* c) {
 // ---- per-operator device data ----------------------------------------------------------------------
 namespace {
 
+struct Sf2Lists {                 // device lists of the fully factorised path (hamiltonian_sf2.cu)
+  DBuf<Sf2Pair> pairs[4];         // rho q0, rho q1, kappa q0, kappa q1
+  DBuf<int> pair_ptr[4];
+  DBuf<int2> zrange[4];
+  DBuf<int> order[4];
+  DBuf<Sf2Task> tasks[2][2];      // [h / Delta][pass]
+  int ntasks[2][2] = {{0, 0}, {0, 0}};
+  DBuf<unsigned char> need[2][2];
+  int npairs_max = 0;
+  void fill(Sf2Dev& F, int nzr) const {
+    F.enabled = 1; F.nzr = nzr; F.npairs_max = npairs_max;
+    for (int k = 0; k < 4; k++) { F.pairs[k] = pairs[k].p; F.pair_ptr[k] = pair_ptr[k].p; F.zrange[k] = zrange[k].p; F.order[k] = order[k].p; }
+    for (int m = 0; m < 2; m++)
+      for (int q = 0; q < 2; q++) { F.tasks[m][q] = tasks[m][q].p; F.ntasks[m][q] = ntasks[m][q]; F.need[m][q] = need[m][q].p; }
+  }
+};
+
 struct OperatorDev {
   OperatorPlan plan;
   DBuf<DevTask> fwd_tasks, bwd_tasks;
@@ -383,10 +405,128 @@ struct OperatorDev {
   DBuf<SfProjTile> sf_tiles[2][2];
   int sf_ntiles[2][2] = {{0, 0}, {0, 0}};
   int sf_ksplit = 1;
+  Sf2Lists sf2;                   // fully factorised path
 };
 
+// fully factorised path: sub-block lists of the density (one list per input structure, built from the same steps as the
+// packed images) and (row, column-run) tasks of the radial projection (one list per output structure)
+void build_sf2_pairs(const pnfam_b200_ctx& c, const BlockStruct& st, DBuf<Sf2Pair>& d_pairs, DBuf<int>& d_ptr, DBuf<int2>& d_zrange,
+                     DBuf<int>& d_order, int& npairs) {
+  const int nzr = c.sf.nzrows, npair = nzr * nzr;
+  std::vector<std::vector<Sf2Pair>> byk((size_t)4 * npair);
+  for (int ix = 0; ix < c.nb; ix++) {
+    const int iy = st.r2c[ix];
+    if (iy < 0) continue;
+    for (int sw = 0; sw < 4; sw++) {
+      const int sa = 2 * ix + (sw >> 1), sb = 2 * iy + (sw & 1);
+      const int na = c.seg_n[sa], nbs = c.seg_n[sb], pa = c.seg_prow0[sa], pb = c.seg_prow0[sb];
+      int i0 = 0;
+      while (i0 < na) {
+        const int zra = c.h_zrow[pa + i0];
+        int i1 = i0 + 1;
+        while (i1 < na && c.h_zrow[pa + i1] == zra) i1++;
+        int j0 = 0;
+        while (j0 < nbs) {
+          const int zrb = c.h_zrow[pb + j0];
+          int j1 = j0 + 1;
+          while (j1 < nbs && c.h_zrow[pb + j1] == zrb) j1++;
+          Sf2Pair p{};
+          p.na = i1 - i0; p.nb = j1 - j0; p.src_off = st.r2m[ix]; p.src_ld = c.db[ix]; p.a_row0 = pa + i0; p.b_row0 = pb + j0;
+          byk[(size_t)sw * npair + (size_t)zra * nzr + zrb].push_back(p);
+          j0 = j1;
+        }
+        i0 = i1;
+      }
+    }
+  }
+  std::vector<Sf2Pair> flat;
+  std::vector<int> ptr((size_t)4 * (npair + 1), 0);
+  std::vector<int2> zr((size_t)4 * nzr, make_int2(0, 0));
+  size_t img = 0;
+  for (int sw = 0; sw < 4; sw++) {
+    for (int p = 0; p < npair; p++) {
+      ptr[(size_t)sw * (npair + 1) + p] = (int)flat.size();
+      for (Sf2Pair e : byk[(size_t)sw * npair + p]) {
+        e.img_off = (int)img;
+        img += (size_t)2 * e.na * e.nb;
+        flat.push_back(e);
+      }
+      if (!byk[(size_t)sw * npair + p].empty()) {
+        int2& r = zr[(size_t)sw * nzr + p / nzr];
+        const int z2 = p % nzr;
+        if (r.x >= r.y) r = make_int2(z2, z2 + 1);
+        else { r.x = std::min(r.x, z2); r.y = std::max(r.y, z2 + 1); }
+      }
+    }
+    ptr[(size_t)sw * (npair + 1) + npair] = (int)flat.size();
+  }
+  if (img > 0x7fffffffull) throw std::runtime_error("density: packed sub-block offsets overflow");
+  // non-empty (zr, zr') entries by decreasing work
+  std::vector<int> order((size_t)4 * (npair + 1), 0);
+  for (int sw = 0; sw < 4; sw++) {
+    std::vector<std::pair<long, int>> w;
+    for (int p = 0; p < npair; p++) {
+      long work = 0;
+      for (const Sf2Pair& e : byk[(size_t)sw * npair + p]) work += (long)e.na * e.nb + e.nb + 4;
+      if (work > 0) w.push_back({-work, p});
+    }
+    std::sort(w.begin(), w.end());
+    int* o = &order[(size_t)sw * (npair + 1)];
+    o[0] = (int)w.size();
+    for (size_t k = 0; k < w.size(); k++) o[1 + k] = w[k].second;
+  }
+  d_order.upload(order);
+  npairs = (int)flat.size();
+  if (flat.empty()) flat.push_back(Sf2Pair{});
+  d_pairs.upload(flat); d_ptr.upload(ptr); d_zrange.upload(zr);
+}
+
+void build_sf2_tasks(const pnfam_b200_ctx& c, const BlockStruct& st, DBuf<Sf2Task>& d_tasks, int& ntasks, DBuf<unsigned char>& d_need) {
+  const int nzr = c.sf.nzrows, npair = nzr * nzr;
+  std::vector<Sf2Task> tasks;
+  std::vector<unsigned char> need((size_t)4 * npair, 0);
+  for (int ix = 0; ix < c.nb; ix++) {
+    const int iy = st.r2c[ix];
+    if (iy < 0) continue;
+    for (int s = 0; s < 4; s++) {
+      const int sa = 2 * ix + (s >> 1), sb = 2 * iy + (s & 1);
+      const int na = c.seg_n[sa], nbs = c.seg_n[sb];
+      if (na == 0 || nbs == 0) continue;
+      int j0 = 0;
+      while (j0 < nbs) {
+        const int pb0 = c.seg_prow0[sb] + j0, zrb = c.h_zrow[pb0];
+        int j1 = j0 + 1;
+        while (j1 < nbs && j1 - j0 < SF2_RUN && c.h_zrow[c.seg_prow0[sb] + j1] == zrb) j1++;
+        for (int i = 0; i < na; i++) {
+          Sf2Task t{};
+          t.pa = c.seg_prow0[sa] + i; t.pb0 = pb0; t.nb = j1 - j0; t.out_base = st.r2m[ix]; t.ld = c.db[ix]; t.sasb = s;
+          tasks.push_back(t);
+          need[(size_t)s * npair + (size_t)c.h_zrow[t.pa] * nzr + zrb] = 1;
+        }
+        j0 = j1;
+      }
+    }
+  }
+  ntasks = (int)tasks.size();
+  if (tasks.empty()) tasks.push_back(Sf2Task{});
+  d_tasks.upload(tasks); d_need.upload(need);
+}
+
+// in[k]: input structures (rho q0, rho q1, kappa q0, kappa q1); out[m][q]: output structures
+void build_sf2_lists(const pnfam_b200_ctx& c, const BlockStruct* in[4], const BlockStruct* out[2][2], Sf2Lists& L) {
+  L.npairs_max = 0;
+  for (int k = 0; k < 4; k++) {
+    int n = 0;
+    build_sf2_pairs(c, *in[k], L.pairs[k], L.pair_ptr[k], L.zrange[k], L.order[k], n);
+    L.npairs_max = std::max(L.npairs_max, n);
+  }
+  for (int m = 0; m < 2; m++)
+    for (int q = 0; q < 2; q++) build_sf2_tasks(c, *out[m][q], L.tasks[m][q], L.ntasks[m][q], L.need[m][q]);
+}
+
 // sum-factorised density: (s, s') sweeps over the blocks of a structure, columns in chunks of nbc_max
-size_t upload_sf_density_steps(const pnfam_b200_ctx& c, const BlockStruct& st, DBuf<SfDensStep>& buf, int& n) {
+size_t upload_sf_density_steps(const pnfam_b200_ctx& c, const BlockStruct& st, DBuf<SfDensStep>& buf, int& n,
+                               std::vector<SfDensStep>* host_copy = nullptr) {
   std::vector<SfDensStep> h;
   size_t img = 0;
   for (int sweep = 0; sweep < 4; sweep++) {
@@ -410,6 +550,7 @@ size_t upload_sf_density_steps(const pnfam_b200_ctx& c, const BlockStruct& st, D
   }
   if (img > 0x7fffffffull) throw std::runtime_error("density: packed image offsets overflow");
   n = (int)h.size();
+  if (host_copy) *host_copy = h;
   if (h.empty()) h.push_back(SfDensStep{});
   buf.upload(h);
   return img;
@@ -563,10 +704,17 @@ std::unique_ptr<OperatorDev> make_operator(pnfam_b200_ctx& c, const pnfam_b200_o
   od->scratch_elems = std::max(od->fwd.scratch_elems, od->bwd.scratch_elems);
   for (int k = 0; k < 4; k++) { od->sp[k].upload(od->plan.sp[k]); od->hsp[k].upload(od->plan.hsp[k]); }
   if (c.sf.enabled) {
-    od->pk_rho = std::max(upload_sf_density_steps(c, od->plan.sp[0], od->sf_steps[0], od->sf_nsteps[0]),
-                          upload_sf_density_steps(c, od->plan.sp[3], od->sf_steps[1], od->sf_nsteps[1]));
-    od->pk_kap = std::max(upload_sf_density_steps(c, od->plan.sp[1], od->sf_steps[2], od->sf_nsteps[2]),
-                          upload_sf_density_steps(c, od->plan.sp[2], od->sf_steps[3], od->sf_nsteps[3]));
+    std::vector<SfDensStep> hs[4];
+    od->pk_rho = std::max(upload_sf_density_steps(c, od->plan.sp[0], od->sf_steps[0], od->sf_nsteps[0], &hs[0]),
+                          upload_sf_density_steps(c, od->plan.sp[3], od->sf_steps[1], od->sf_nsteps[1], &hs[1]));
+    od->pk_kap = std::max(upload_sf_density_steps(c, od->plan.sp[1], od->sf_steps[2], od->sf_nsteps[2], &hs[2]),
+                          upload_sf_density_steps(c, od->plan.sp[2], od->sf_steps[3], od->sf_nsteps[3], &hs[3]));
+    if (c.sf2) {
+      const BlockStruct* in[4] = {&od->plan.sp[0], &od->plan.sp[3], &od->plan.sp[1], &od->plan.sp[2]};
+      const BlockStruct* out[2][2] = {{&od->plan.hsp[0], &od->plan.hsp[3]}, {&od->plan.hsp[1], &od->plan.hsp[2]}};
+      build_sf2_lists(c, in, out, od->sf2);
+      od->pk_rho = od->pk_kap = 2 * od->plan.nxy;      // packed sub-blocks: every element once
+    }
     upload_sf_proj_tiles(c, od->plan.hsp[0], od->sf_tiles[0][0], od->sf_ntiles[0][0]);
     upload_sf_proj_tiles(c, od->plan.hsp[3], od->sf_tiles[0][1], od->sf_ntiles[0][1]);
     upload_sf_proj_tiles(c, od->plan.hsp[1], od->sf_tiles[1][0], od->sf_ntiles[1][0]);
@@ -614,6 +762,7 @@ HamArgs make_ham_args(const pnfam_b200_ctx& c, const OperatorDev& od) {
       for (int q = 0; q < 2; q++) { h.sf.tiles[m][q] = od.sf_tiles[m][q].p; h.sf.ntiles[m][q] = od.sf_ntiles[m][q]; }
     h.sf.ksplit = od.sf_ksplit;
     h.sf.pk_stride[0] = od.pk_rho; h.sf.pk_stride[1] = od.pk_kap;
+    if (c.sf2) od.sf2.fill(h.sf2, c.sf.nzrows);
   }
   return h;
 }
@@ -664,8 +813,10 @@ extern "C" int pnfam_b200_solve(pnfam_b200_ctx* c, const pnfam_b200_operator* op
       d += 2 * std::max<size_t>(od->scratch_elems, 1);
       d += (size_t)2 * NDD_RHO * c->nghl + (size_t)2 * NDD_KAP * c->nghl + 2 * mf_e + 2 * pf_e;
       d += 2 * std::max<size_t>(od->pk_rho, 1) + 2 * std::max<size_t>(od->pk_kap, 1);
+      if (c->sf2) d += 2 * (sf2_kt_elems(0, c->sf.ngl, c->sf.nzrows) + sf2_kt_elems(1, c->sf.ngl, c->sf.nzrows));
       return d;
     };
+    const bool need_hpart = !(sf && c->sf2);     // the fully factorised projection writes h directly (no split-K partials)
     int S = std::min(P, 1024);
     {
       int cap = prm->batch_slots > 0 ? prm->batch_slots : 0;
@@ -675,7 +826,7 @@ extern "C" int pnfam_b200_solve(pnfam_b200_ctx* c, const pnfam_b200_operator* op
       const double avail = 0.92 * (double)device_bytes_available();
       for (;;) {
         set_batch_slots(*c, *od, S);
-        const double need = 8.0 * ((double)S * (double)slot_doubles() + (double)S * (double)projection_partial_elems(od->proj, nxy));
+        const double need = 8.0 * ((double)S * (double)slot_doubles() + (need_hpart ? (double)S * (double)projection_partial_elems(od->proj, nxy) : 0.0));
         if (need <= avail || S == 1) break;
         S = std::max(1, std::min(S - 1, (int)(S * avail / need)));
       }
@@ -732,7 +883,12 @@ extern "C" int pnfam_b200_solve(pnfam_b200_ctx* c, const pnfam_b200_operator* op
     mf.zero(); pf.zero();
     if (sf) { dd_rho.zero(); dd_kap.zero(); }             // (s, s') sweeps without any step are never written
     pk_rho.alloc((size_t)S * 2 * std::max<size_t>(od->pk_rho, 1)); pk_kap.alloc((size_t)S * 2 * std::max<size_t>(od->pk_kap, 1));
-    hpart.alloc((size_t)S * projection_partial_elems(od->proj, nxy));
+    if (need_hpart) hpart.alloc((size_t)S * projection_partial_elems(od->proj, nxy));
+    DBuf<double> kt0, kt1;
+    if (c->sf2 && sf) {
+      kt0.alloc((size_t)S * 2 * sf2_kt_elems(0, c->sf.ngl, c->sf.nzrows));
+      kt1.alloc((size_t)S * 2 * sf2_kt_elems(1, c->sf.ngl, c->sf.nzrows));
+    }
 
     // ---- batch control: admission order (the points that need the most iterations -- small |Im omega| -- first, so
     //      that the batch drains with the short ones), slot tables, per-point results -----------------------------
@@ -788,6 +944,7 @@ extern "C" int pnfam_b200_solve(pnfam_b200_ctx* c, const pnfam_b200_operator* op
     ha.pk_rho = pk_rho.p; ha.pk_kap = pk_kap.p;
     ha.sf.pk[0] = pk_rho.p; ha.sf.pk[1] = pk_kap.p;
     ha.hpart = hpart.p; ha.active = d_active.p; ha.ctrl = d_ctrl.p;
+    ha.sf2.kt[0] = kt0.p; ha.sf2.kt[1] = kt1.p;
 
     MixArgs ma{};
     ma.nvec = nvec; ma.nxy = nxy; ma.n = n; ma.M = Malloc; ma.Mmode = M; ma.alpha = (double)0.7f; ma.w0 = 0.01;
@@ -929,6 +1086,8 @@ struct HamWorkspace {
   DBuf<DensStep> dsteps[4];
   DBuf<SfDensStep> sf_steps[4];
   DBuf<SfProjTile> sf_tiles[2][2];
+  Sf2Lists sf2;
+  DBuf<double> kt0, kt1;
   DBuf<int4> th, td;
   ProjPlan pp;
   HamArgs h{};
@@ -977,8 +1136,19 @@ std::shared_ptr<HamWorkspace> build_ham_workspace(pnfam_b200_ctx* c, const pnfam
   h.ctrl = nullptr;
   if (sf) {
     // argument pairs: 0 rho_pn (pass 0), 1 kappa+ (pass 0), 2 rho_np (pass 1), 3 kappa- (pass 1)
-    h.pk_stride_rho = std::max(upload_sf_density_steps(*c, hin[0], w->sf_steps[0], h.sf.nsteps[0]), upload_sf_density_steps(*c, hin[2], w->sf_steps[1], h.sf.nsteps[1]));
-    h.pk_stride_kap = std::max(upload_sf_density_steps(*c, hin[1], w->sf_steps[2], h.sf.nsteps[2]), upload_sf_density_steps(*c, hin[3], w->sf_steps[3], h.sf.nsteps[3]));
+    std::vector<SfDensStep> hs[4];
+    h.pk_stride_rho = std::max(upload_sf_density_steps(*c, hin[0], w->sf_steps[0], h.sf.nsteps[0], &hs[0]), upload_sf_density_steps(*c, hin[2], w->sf_steps[1], h.sf.nsteps[1], &hs[1]));
+    h.pk_stride_kap = std::max(upload_sf_density_steps(*c, hin[1], w->sf_steps[2], h.sf.nsteps[2], &hs[2]), upload_sf_density_steps(*c, hin[3], w->sf_steps[3], h.sf.nsteps[3], &hs[3]));
+    if (c->sf2) {
+      const BlockStruct* ins[4] = {&hin[0], &hin[2], &hin[1], &hin[3]};
+      const BlockStruct* outs[2][2] = {{&hout[0], &hout[2]}, {&hout[1], &hout[3]}};
+      build_sf2_lists(*c, ins, outs, w->sf2);
+      h.pk_stride_rho = h.pk_stride_kap = 2 * nxy;
+      h.sf.pk_stride[0] = h.sf.pk_stride[1] = 2 * nxy;
+      w->sf2.fill(h.sf2, c->sf.nzrows);
+      w->kt0.alloc(2 * sf2_kt_elems(0, c->sf.ngl, c->sf.nzrows)); w->kt1.alloc(2 * sf2_kt_elems(1, c->sf.ngl, c->sf.nzrows));
+      h.sf2.kt[0] = w->kt0.p; h.sf2.kt[1] = w->kt1.p;
+    }
     for (int k = 0; k < 4; k++) h.sf.steps[k] = w->sf_steps[k].p;
     upload_sf_proj_tiles(*c, hout[0], w->sf_tiles[0][0], h.sf.ntiles[0][0]);
     upload_sf_proj_tiles(*c, hout[2], w->sf_tiles[0][1], h.sf.ntiles[0][1]);
