@@ -18,8 +18,9 @@
 // FP64 operations than the one-sided factorisation and ~25x fewer than the GEMM formulation.  All of it is FP64 FMA
 // work on small operands that live in L1/L2 (on B200 the DFMA and DMMA rates are the same 128 flop/clk/SM); the kernels
 // are plain one-thread-one-output loops without hand-over between warps:
-//   sf2_density_kernel  one CTA per (il, sweep ss', pass, omega): a thread owns the (zr, zr') entries of Pi and walks the
-//                       host-built list of sub-blocks that feed them, then the CTA contracts Pi with the z tables
+//   sf2_density_kernel  one CTA per (il, sweep ss', pass, omega): eight lanes own one (zr, zr') entry of Pi and stride
+//                       through the elements that feed it (rho is repacked in that order), then the CTA contracts Pi
+//                       with the z tables
 //   sf2_kappa_kernel    one CTA per (il, spin combination, pass, omega): a thread owns one (zr, zr') entry of kt
 //   sf2_radial_kernel   one thread per (row a, run of <= 8 columns with equal n_z) of the output block matrix
 // Sums run in a fixed order (no atomics): results are reproducible run to run.
@@ -39,30 +40,20 @@ __host__ __device__ constexpr int mfp(int t, int t2) { return t == 0 ? t2 : (t <
 }  // namespace
 
 // ================================================================================================
-// packed sub-blocks: every (n_z slot of rows) x (n_z run of columns) piece of rho / kappa as one contiguous array
-// [b][a][re, im], in the order of the sub-block lists -- a thread of the density kernel streams it front to back
+// packed copy of rho / kappa in (sweep, zr, zr') order: pk[i] = (re, im) of element el_src[i]
 // ================================================================================================
-__global__ void __launch_bounds__(128) sf2_pack_kernel(HamArgs g) {
+__global__ void __launch_bounds__(256) sf2_pack_kernel(HamArgs g) {
   const SfDev& S = g.sf;
   const Sf2Dev& F = g.sf2;
   const int list = blockIdx.y, kind = list >> 1, q = list & 1, za = blockIdx.z;
   if (g.ctrl && za >= g.ctrl->nactive) return;
-  const int e = blockIdx.x * 128 + threadIdx.x;
-  const int npair = F.nzr * F.nzr;
-  if (e >= F.pair_ptr[list][4 * (npair + 1) - 1]) return;
-  const Sf2Pair pr = F.pairs[list][e];
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= F.nelem[list]) return;
   const int p = g.active[za];
   const int quad = kind ? g.kap_quad[q] : g.rho_quad[q];
-  const double* __restrict__ src0 = g.rsp + ((size_t)p * 2 + 0) * 4 * g.nxy + (size_t)quad * g.nxy + pr.src_off;
-  const double* __restrict__ src1 = src0 + 4 * g.nxy;
-  double2* __restrict__ dst = reinterpret_cast<double2*>(S.pk[kind] + ((size_t)za * 2 + q) * S.pk_stride[kind] + pr.img_off);
-  for (int b = 0; b < pr.nb; b++) {
-    const size_t col = (size_t)S.p2l[pr.b_row0 + b] * pr.src_ld;
-    for (int a = 0; a < pr.na; a++) {
-      const size_t el = col + S.p2l[pr.a_row0 + a];
-      *dst++ = make_double2(src0[el], src1[el]);
-    }
-  }
+  const double* __restrict__ src0 = g.rsp + ((size_t)p * 2 + 0) * 4 * g.nxy + (size_t)quad * g.nxy;
+  const int e = F.el_src[list][i];
+  reinterpret_cast<double2*>(S.pk[kind] + ((size_t)za * 2 + q) * S.pk_stride[kind])[i] = make_double2(src0[e], src0[4 * g.nxy + e]);
 }
 
 // ================================================================================================
@@ -72,7 +63,7 @@ template <int MODE>
 __global__ void __launch_bounds__(256) sf2_density_kernel(HamArgs g) {
   constexpr int NJ = MODE == 0 ? 3 : 1;   // radial factor types of the densities: R0, R1 (d/dr), R2 (Lambda/r)
   constexpr int NT = MODE == 0 ? 4 : 1;   // derivative types: phi, d/dr, Lambda/r, d/dz
-  constexpr int KS = 4;                   // lanes sharing one (zr, zr') entry: they split its sub-block list
+  constexpr int KS = 8;                   // lanes sharing one (zr, zr') entry: they stride through its elements
   extern __shared__ __align__(16) unsigned char smem[];
   const SfDev& S = g.sf;
   const Sf2Dev& F = g.sf2;
@@ -86,55 +77,42 @@ __global__ void __launch_bounds__(256) sf2_density_kernel(HamArgs g) {
     const int m = i / (nzr * ngh), r = i - m * nzr * ngh, zr = r / ngh, ih = r - zr * ngh;
     Zs[i] = S.zt[((size_t)m * nzr + zr) * S.zs + ih];
   }
-  // ---- radial part: Pi^{jj'}[zr][zr'] of this il and sweep.  KS adjacent lanes own one (zr, zr') entry and take its
-  //      sub-blocks round robin; their partial sums are added in a fixed order (shuffles).
-  const Sf2Pair* __restrict__ pairs = F.pairs[list];
-  const int* __restrict__ ptr = F.pair_ptr[list] + (size_t)sweep * (npair + 1);
-  const double* __restrict__ pk = S.pk[MODE] + ((size_t)za * 2 + q) * S.pk_stride[MODE];
-  const double* __restrict__ rgl = S.rg + (size_t)il * S.dqp_p * 4;
-  const int part = tid & (KS - 1);
-  // the non-empty entries, heaviest first, are dealt to the 64 lane groups round by round: the groups of one round carry
-  // nearly equal work (the work of an entry falls steeply with n_z: the low n_z occur in every block)
-  const int* __restrict__ order = F.order[list] + (size_t)sweep * (npair + 1);
-  const int nwork = order[0];
   for (int i = tid; i < NJ * NJ * npair; i += 256) Pi[i] = make_double2(0.0, 0.0);
   __syncthreads();
+  // ---- radial part: Pi^{jj'}[zr][zr'] = sum over the elements of the group of R^j_a rho_ab R^j'_b at this il.
+  //      KS adjacent lanes own one (zr, zr') entry and stride through its elements (coalesced, independent loads);
+  //      their partial sums are added in a fixed order (shuffles).  The non-empty entries, heaviest first, are dealt to
+  //      the lane groups round by round: the groups of one round carry nearly equal work (the work of an entry falls
+  //      steeply with n_z: the low n_z occur in every block).
+  const int* __restrict__ eptr = F.eptr[list] + (size_t)sweep * (npair + 1);
+  const int2* __restrict__ el = F.el_ab[list];
+  const double2* __restrict__ pk = reinterpret_cast<const double2*>(S.pk[MODE] + ((size_t)za * 2 + q) * S.pk_stride[MODE]);
+  const double* __restrict__ rgl = S.rg + (size_t)il * S.dqp_p * 4;
+  const int part = tid & (KS - 1);
+  const int* __restrict__ order = F.order[list] + (size_t)sweep * (npair + 1);
+  const int nwork = order[0];
   for (int k0 = 0; k0 < nwork; k0 += 256 / KS) {
-    const int k = k0 + (tid >> 2);
+    const int k = k0 + (tid >> 3);
     const int p = k < nwork ? order[1 + k] : npair;
     double2 acc[NJ][NJ];
 #pragma unroll
     for (int i = 0; i < NJ * NJ; i++) (&acc[0][0])[i] = make_double2(0.0, 0.0);
     if (p < npair) {
-      const int e1 = ptr[p + 1];
-      for (int e = ptr[p] + part; e < e1; e += KS) {
-        const int4 h0 = __ldg(reinterpret_cast<const int4*>(pairs + e));          // img_off, na, nb, src_off
-        const int4 h1 = __ldg(reinterpret_cast<const int4*>(pairs + e) + 1);      // src_ld, a_row0, b_row0, pad
-        const int na = h0.y, nb = h0.z;
-        const double* __restrict__ img = pk + h0.x;
-        const double* __restrict__ ra0 = rgl + (size_t)h1.y * 4;
-        const double* __restrict__ rb0 = rgl + (size_t)h1.z * 4;
-        for (int b = 0; b < nb; b++, img += 2 * na) {
-          double2 t[NJ];
-#pragma unroll
-          for (int j = 0; j < NJ; j++) t[j] = make_double2(0.0, 0.0);
-#pragma unroll 4
-          for (int a = 0; a < na; a++) {
-            const double2 v = ldg2(img + 2 * a);
-            const double2 r01 = ldg2(ra0 + a * 4);
-            cfma(t[0], r01.x, v);
-            if (MODE == 0) {
-              cfma(t[1], r01.y, v);
-              cfma(t[2], __ldg(ra0 + a * 4 + 2), v);
-            }
-          }
-          const double2 s01 = ldg2(rb0 + b * 4);
-          const double s2 = MODE == 0 ? __ldg(rb0 + b * 4 + 2) : 0.0;
-#pragma unroll
-          for (int j = 0; j < NJ; j++) {
-            cfma(acc[j][0], s01.x, t[j]);
-            if (MODE == 0) { cfma(acc[j][1], s01.y, t[j]); cfma(acc[j][2], s2, t[j]); }
-          }
+      const int e1 = eptr[p + 1];
+#pragma unroll 2
+      for (int i = eptr[p] + part; i < e1; i += KS) {
+        const double2 v = __ldg(pk + i);
+        const int2 ab = __ldg(el + i);
+        const double2 a01 = ldg2(rgl + (size_t)ab.x * 4), b01 = ldg2(rgl + (size_t)ab.y * 4);
+        if (MODE == 1) {
+          cfma(acc[0][0], a01.x * b01.x, v);
+        } else {
+          const double a2 = __ldg(rgl + (size_t)ab.x * 4 + 2), b2 = __ldg(rgl + (size_t)ab.y * 4 + 2);
+          const double2 u0 = make_double2(a01.x * v.x, a01.x * v.y), u1 = make_double2(a01.y * v.x, a01.y * v.y),
+                        u2 = make_double2(a2 * v.x, a2 * v.y);
+          cfma(acc[0][0], b01.x, u0); cfma(acc[0][1], b01.y, u0); cfma(acc[0][2], b2, u0);
+          cfma(acc[1][0], b01.x, u1); cfma(acc[1][1], b01.y, u1); cfma(acc[1][2], b2, u1);
+          cfma(acc[2][0], b01.x, u2); cfma(acc[2][1], b01.y, u2); cfma(acc[2][2], b2, u2);
         }
       }
     }
@@ -143,6 +121,7 @@ __global__ void __launch_bounds__(256) sf2_density_kernel(HamArgs g) {
       double2& v = (&acc[0][0])[i];
       v.x += __shfl_xor_sync(0xffffffffu, v.x, 1); v.y += __shfl_xor_sync(0xffffffffu, v.y, 1);
       v.x += __shfl_xor_sync(0xffffffffu, v.x, 2); v.y += __shfl_xor_sync(0xffffffffu, v.y, 2);
+      v.x += __shfl_xor_sync(0xffffffffu, v.x, 4); v.y += __shfl_xor_sync(0xffffffffu, v.y, 4);
     }
     if (p < npair && part == 0) {
 #pragma unroll
@@ -201,7 +180,8 @@ void launch_density_sf2(const HamArgs& a, cudaStream_t stream) {
     PNFAM_CUDA_CHECK(cudaFuncSetAttribute(sf2_density_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm0));
     PNFAM_CUDA_CHECK(cudaFuncSetAttribute(sf2_density_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm0));
   }
-  if (a.sf2.npairs_max > 0) sf2_pack_kernel<<<dim3((a.sf2.npairs_max + 127) / 128, 4, a.nactive), 128, 0, stream>>>(a);
+  const int nel = std::max(std::max(a.sf2.nelem[0], a.sf2.nelem[1]), std::max(a.sf2.nelem[2], a.sf2.nelem[3]));
+  if (nel > 0) sf2_pack_kernel<<<dim3((nel + 255) / 256, 4, a.nactive), 256, 0, stream>>>(a);
   const dim3 grid(S.ngl, 8, a.nactive);
   SideStreams& ss = *a.side;
   ss.fork_from(stream, 1);

@@ -155,12 +155,6 @@ struct SfDev {
 constexpr int SF2_NJJ = 11;      // (j, j') combinations of the radial factors in the mean field:
                                  // (0,0) (0,1) (0,2) (0,3) (1,0) (1,1) (1,2) (2,0) (2,1) (2,2) (3,0)
 constexpr int SF2_RUN = 8;       // columns per task of the radial projection (runs of equal n_z are cut at this length)
-struct Sf2Pair {                 // one (rows of one n_z slot) x (columns of one n_z run) sub-block of rho / kappa
-  int img_off, na, nb;           // offset (doubles) of its packed copy [b][a][re,im] (contiguous), rows, columns
-  int src_off, src_ld;           // element offset of the block in the block matrix, leading dimension
-  int a_row0, b_row0;            // padded rows of the first row / column (radial factors, p2l)
-  int pad;
-};
 struct Sf2Task {                 // radial projection: one row a x a run of <= SF2_RUN columns with equal n_z
   int pa, pb0, nb;               // padded row of a, of the first column, columns
   int out_base, ld;              // element offset of the block in the block matrix, leading dimension
@@ -169,15 +163,19 @@ struct Sf2Task {                 // radial projection: one row a x a run of <= S
 struct Sf2Dev {
   int enabled = 0;
   int nzr = 0;
-  const Sf2Pair* pairs[4] = {nullptr, nullptr, nullptr, nullptr};     // rho q0, rho q1, kappa q0, kappa q1
-  const int* pair_ptr[4] = {nullptr, nullptr, nullptr, nullptr};      // [4 sweeps][nzr*nzr + 1]
+  // density: the elements of rho / kappa regrouped by (sweep, zr, zr') -- element i of list k (rho q0, rho q1, kappa q0,
+  // kappa q1) is rsp[..][el_src[k][i]], its row / column have the padded rows el_ab[k][i]; eptr: first element of every
+  // (sweep, zr, zr') group.  The packed copy pk[..][i] = (re, im) is written in this order every iteration.
+  const int2* el_ab[4] = {nullptr, nullptr, nullptr, nullptr};
+  const int* el_src[4] = {nullptr, nullptr, nullptr, nullptr};
+  const int* eptr[4] = {nullptr, nullptr, nullptr, nullptr};          // [4 sweeps][nzr*nzr + 1]
+  int nelem[4] = {0, 0, 0, 0};
   const int2* zrange[4] = {nullptr, nullptr, nullptr, nullptr};       // [4 sweeps][nzr]: zr' range with non-empty pair lists
   const int* order[4] = {nullptr, nullptr, nullptr, nullptr};          // [4 sweeps][1 + nzr*nzr]: count, then the non-empty (zr, zr')
                                                                        // entries by decreasing work (balanced dealing to the lanes)
   const Sf2Task* tasks[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [h / Delta][pass]
   int ntasks[2][2] = {{0, 0}, {0, 0}};
   const unsigned char* need[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [h / Delta][pass]: [4 sasb][nzr*nzr] kt entries in use
-  int npairs_max = 0;                  // longest of the four sub-block lists
   double* kt[2] = {nullptr, nullptr};  // [slot za][2 q][4 sasb][ngl][nzr*nzr][NJJ or 1][2]
 };
 __host__ __device__ inline size_t sf2_kt_elems(int mode, int ngl, int nzr) { return (size_t)4 * ngl * nzr * nzr * (mode == 0 ? SF2_NJJ : 1) * 2; }

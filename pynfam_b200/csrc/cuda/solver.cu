@@ -370,17 +370,20 @@ extern "C" void pnfam_b200_ctx_destroy(pnfam_b200_ctx* c) {
 namespace {
 
 struct Sf2Lists {                 // device lists of the fully factorised path (hamiltonian_sf2.cu)
-  DBuf<Sf2Pair> pairs[4];         // rho q0, rho q1, kappa q0, kappa q1
-  DBuf<int> pair_ptr[4];
+  DBuf<int2> el_ab[4];            // rho q0, rho q1, kappa q0, kappa q1
+  DBuf<int> el_src[4], eptr[4];
+  int nelem[4] = {0, 0, 0, 0};
   DBuf<int2> zrange[4];
   DBuf<int> order[4];
   DBuf<Sf2Task> tasks[2][2];      // [h / Delta][pass]
   int ntasks[2][2] = {{0, 0}, {0, 0}};
   DBuf<unsigned char> need[2][2];
-  int npairs_max = 0;
   void fill(Sf2Dev& F, int nzr) const {
-    F.enabled = 1; F.nzr = nzr; F.npairs_max = npairs_max;
-    for (int k = 0; k < 4; k++) { F.pairs[k] = pairs[k].p; F.pair_ptr[k] = pair_ptr[k].p; F.zrange[k] = zrange[k].p; F.order[k] = order[k].p; }
+    F.enabled = 1; F.nzr = nzr;
+    for (int k = 0; k < 4; k++) {
+      F.el_ab[k] = el_ab[k].p; F.el_src[k] = el_src[k].p; F.eptr[k] = eptr[k].p; F.nelem[k] = nelem[k];
+      F.zrange[k] = zrange[k].p; F.order[k] = order[k].p;
+    }
     for (int m = 0; m < 2; m++)
       for (int q = 0; q < 2; q++) { F.tasks[m][q] = tasks[m][q].p; F.ntasks[m][q] = ntasks[m][q]; F.need[m][q] = need[m][q].p; }
   }
@@ -410,10 +413,15 @@ struct OperatorDev {
 
 // fully factorised path: sub-block lists of the density (one list per input structure, built from the same steps as the
 // packed images) and (row, column-run) tasks of the radial projection (one list per output structure)
-void build_sf2_pairs(const pnfam_b200_ctx& c, const BlockStruct& st, DBuf<Sf2Pair>& d_pairs, DBuf<int>& d_ptr, DBuf<int2>& d_zrange,
-                     DBuf<int>& d_order, int& npairs) {
+struct Sf2Elems {                 // host image of one element list of the fully factorised density
+  std::vector<int2> ab;
+  std::vector<int> src, eptr, order;
+  std::vector<int2> zrange;
+};
+Sf2Elems build_sf2_elems(const pnfam_b200_ctx& c, const BlockStruct& st) {
   const int nzr = c.sf.nzrows, npair = nzr * nzr;
-  std::vector<std::vector<Sf2Pair>> byk((size_t)4 * npair);
+  struct Sub { int na, nb, src_off, src_ld, a_row0, b_row0; };
+  std::vector<std::vector<Sub>> byk((size_t)4 * npair);
   for (int ix = 0; ix < c.nb; ix++) {
     const int iy = st.r2c[ix];
     if (iy < 0) continue;
@@ -430,55 +438,45 @@ void build_sf2_pairs(const pnfam_b200_ctx& c, const BlockStruct& st, DBuf<Sf2Pai
           const int zrb = c.h_zrow[pb + j0];
           int j1 = j0 + 1;
           while (j1 < nbs && c.h_zrow[pb + j1] == zrb) j1++;
-          Sf2Pair p{};
-          p.na = i1 - i0; p.nb = j1 - j0; p.src_off = st.r2m[ix]; p.src_ld = c.db[ix]; p.a_row0 = pa + i0; p.b_row0 = pb + j0;
-          byk[(size_t)sw * npair + (size_t)zra * nzr + zrb].push_back(p);
+          byk[(size_t)sw * npair + (size_t)zra * nzr + zrb].push_back(Sub{i1 - i0, j1 - j0, st.r2m[ix], c.db[ix], pa + i0, pb + j0});
           j0 = j1;
         }
         i0 = i1;
       }
     }
   }
-  std::vector<Sf2Pair> flat;
-  std::vector<int> ptr((size_t)4 * (npair + 1), 0);
-  std::vector<int2> zr((size_t)4 * nzr, make_int2(0, 0));
-  size_t img = 0;
+  Sf2Elems E;
+  E.eptr.assign((size_t)4 * (npair + 1), 0);
+  E.order.assign((size_t)4 * (npair + 1), 0);
+  E.zrange.assign((size_t)4 * nzr, make_int2(0, 0));
   for (int sw = 0; sw < 4; sw++) {
+    std::vector<std::pair<long, int>> w;
     for (int p = 0; p < npair; p++) {
-      ptr[(size_t)sw * (npair + 1) + p] = (int)flat.size();
-      for (Sf2Pair e : byk[(size_t)sw * npair + p]) {
-        e.img_off = (int)img;
-        img += (size_t)2 * e.na * e.nb;
-        flat.push_back(e);
+      E.eptr[(size_t)sw * (npair + 1) + p] = (int)E.ab.size();
+      long work = 0;
+      for (const Sub& e : byk[(size_t)sw * npair + p]) {
+        for (int b = 0; b < e.nb; b++)
+          for (int a = 0; a < e.na; a++) {
+            E.ab.push_back(make_int2(e.a_row0 + a, e.b_row0 + b));
+            E.src.push_back(e.src_off + c.h_p2l[e.a_row0 + a] + c.h_p2l[e.b_row0 + b] * e.src_ld);
+          }
+        work += (long)e.na * e.nb;
       }
-      if (!byk[(size_t)sw * npair + p].empty()) {
-        int2& r = zr[(size_t)sw * nzr + p / nzr];
+      if (work > 0) {
+        w.push_back({-work, p});
+        int2& r = E.zrange[(size_t)sw * nzr + p / nzr];
         const int z2 = p % nzr;
         if (r.x >= r.y) r = make_int2(z2, z2 + 1);
         else { r.x = std::min(r.x, z2); r.y = std::max(r.y, z2 + 1); }
       }
     }
-    ptr[(size_t)sw * (npair + 1) + npair] = (int)flat.size();
-  }
-  if (img > 0x7fffffffull) throw std::runtime_error("density: packed sub-block offsets overflow");
-  // non-empty (zr, zr') entries by decreasing work
-  std::vector<int> order((size_t)4 * (npair + 1), 0);
-  for (int sw = 0; sw < 4; sw++) {
-    std::vector<std::pair<long, int>> w;
-    for (int p = 0; p < npair; p++) {
-      long work = 0;
-      for (const Sf2Pair& e : byk[(size_t)sw * npair + p]) work += (long)e.na * e.nb + e.nb + 4;
-      if (work > 0) w.push_back({-work, p});
-    }
-    std::sort(w.begin(), w.end());
-    int* o = &order[(size_t)sw * (npair + 1)];
+    E.eptr[(size_t)sw * (npair + 1) + npair] = (int)E.ab.size();
+    std::sort(w.begin(), w.end());              // non-empty (zr, zr') entries by decreasing work
+    int* o = &E.order[(size_t)sw * (npair + 1)];
     o[0] = (int)w.size();
     for (size_t k = 0; k < w.size(); k++) o[1 + k] = w[k].second;
   }
-  d_order.upload(order);
-  npairs = (int)flat.size();
-  if (flat.empty()) flat.push_back(Sf2Pair{});
-  d_pairs.upload(flat); d_ptr.upload(ptr); d_zrange.upload(zr);
+  return E;
 }
 
 void build_sf2_tasks(const pnfam_b200_ctx& c, const BlockStruct& st, DBuf<Sf2Task>& d_tasks, int& ntasks, DBuf<unsigned char>& d_need) {
@@ -514,11 +512,11 @@ void build_sf2_tasks(const pnfam_b200_ctx& c, const BlockStruct& st, DBuf<Sf2Tas
 
 // in[k]: input structures (rho q0, rho q1, kappa q0, kappa q1); out[m][q]: output structures
 void build_sf2_lists(const pnfam_b200_ctx& c, const BlockStruct* in[4], const BlockStruct* out[2][2], Sf2Lists& L) {
-  L.npairs_max = 0;
   for (int k = 0; k < 4; k++) {
-    int n = 0;
-    build_sf2_pairs(c, *in[k], L.pairs[k], L.pair_ptr[k], L.zrange[k], L.order[k], n);
-    L.npairs_max = std::max(L.npairs_max, n);
+    Sf2Elems E = build_sf2_elems(c, *in[k]);
+    L.nelem[k] = (int)E.ab.size();
+    if (E.ab.empty()) { E.ab.push_back(make_int2(0, 0)); E.src.push_back(0); }
+    L.el_ab[k].upload(E.ab); L.el_src[k].upload(E.src); L.eptr[k].upload(E.eptr); L.order[k].upload(E.order); L.zrange[k].upload(E.zrange);
   }
   for (int m = 0; m < 2; m++)
     for (int q = 0; q < 2; q++) build_sf2_tasks(c, *out[m][q], L.tasks[m][q], L.ntasks[m][q], L.need[m][q]);
