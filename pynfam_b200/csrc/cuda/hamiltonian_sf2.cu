@@ -79,40 +79,61 @@ __global__ void __launch_bounds__(256) sf2_density_kernel(HamArgs g) {
   }
   for (int i = tid; i < NJ * NJ * npair; i += 256) Pi[i] = make_double2(0.0, 0.0);
   __syncthreads();
-  // ---- radial part: Pi^{jj'}[zr][zr'] = sum over the elements of the group of R^j_a rho_ab R^j'_b at this il.
-  //      KS adjacent lanes own one (zr, zr') entry and stride through its elements (coalesced, independent loads);
-  //      their partial sums are added in a fixed order (shuffles).  The non-empty entries, heaviest first, are dealt to
-  //      the lane groups round by round: the groups of one round carry nearly equal work (the work of an entry falls
-  //      steeply with n_z: the low n_z occur in every block).
-  const int* __restrict__ eptr = F.eptr[list] + (size_t)sweep * (npair + 1);
-  const int2* __restrict__ el = F.el_ab[list];
+  // ---- radial part: Pi^{jj'}[zr][zr'] = sum over the sub-blocks of the group of R^j_a rho_ab R^j'_b at this il, column by
+  //      column: t^j = sum_a R^j_a rho_ab (the column is a contiguous run of the packed copy), then t^j R^j'_b.
+  //      KS adjacent lanes own one (zr, zr') entry and take its columns round robin (adjacent columns are adjacent in
+  //      memory); their partial sums are added in a fixed order (shuffles).  The non-empty entries, heaviest first, are
+  //      dealt to the lane groups round by round in snake order: the groups carry nearly equal work (the work of an
+  //      entry falls steeply with n_z: the low n_z occur in every block).
+  const int* __restrict__ cptr = F.cptr[list] + (size_t)sweep * (npair + 1);
+  const int4* __restrict__ cols = F.cols[list];
   const double2* __restrict__ pk = reinterpret_cast<const double2*>(S.pk[MODE] + ((size_t)za * 2 + q) * S.pk_stride[MODE]);
   const double* __restrict__ rgl = S.rg + (size_t)il * S.dqp_p * 4;
   const int part = tid & (KS - 1);
   const int* __restrict__ order = F.order[list] + (size_t)sweep * (npair + 1);
   const int nwork = order[0];
-  for (int k0 = 0; k0 < nwork; k0 += 256 / KS) {
-    const int k = k0 + (tid >> 3);
+  for (int k0 = 0, round = 0; k0 < nwork; k0 += 256 / KS, round++) {
+    const int k = k0 + ((round & 1) ? 256 / KS - 1 - (tid >> 3) : (tid >> 3));
     const int p = k < nwork ? order[1 + k] : npair;
     double2 acc[NJ][NJ];
 #pragma unroll
     for (int i = 0; i < NJ * NJ; i++) (&acc[0][0])[i] = make_double2(0.0, 0.0);
     if (p < npair) {
-      const int e1 = eptr[p + 1];
-#pragma unroll 2
-      for (int i = eptr[p] + part; i < e1; i += KS) {
-        const double2 v = __ldg(pk + i);
-        const int2 ab = __ldg(el + i);
-        const double2 a01 = ldg2(rgl + (size_t)ab.x * 4), b01 = ldg2(rgl + (size_t)ab.y * 4);
-        if (MODE == 1) {
-          cfma(acc[0][0], a01.x * b01.x, v);
-        } else {
-          const double a2 = __ldg(rgl + (size_t)ab.x * 4 + 2), b2 = __ldg(rgl + (size_t)ab.y * 4 + 2);
-          const double2 u0 = make_double2(a01.x * v.x, a01.x * v.y), u1 = make_double2(a01.y * v.x, a01.y * v.y),
-                        u2 = make_double2(a2 * v.x, a2 * v.y);
-          cfma(acc[0][0], b01.x, u0); cfma(acc[0][1], b01.y, u0); cfma(acc[0][2], b2, u0);
-          cfma(acc[1][0], b01.x, u1); cfma(acc[1][1], b01.y, u1); cfma(acc[1][2], b2, u1);
-          cfma(acc[2][0], b01.x, u2); cfma(acc[2][1], b01.y, u2); cfma(acc[2][2], b2, u2);
+      const int c1 = cptr[p + 1];
+      int c = cptr[p] + part;
+      int4 cn = make_int4(0, 0, 0, 0);
+      if (c < c1) cn = __ldg(cols + c);
+      while (c < c1) {
+        const int4 cd = cn;                                  // first element, rows, row of a_0, row of b
+        c += KS;
+        if (c < c1) cn = __ldg(cols + c);                    // next descriptor one step ahead
+        const double2* __restrict__ vp = pk + cd.x;
+        const double* __restrict__ ra = rgl + (size_t)cd.z * 4;
+        double2 t[NJ];
+#pragma unroll
+        for (int j = 0; j < NJ; j++) t[j] = make_double2(0.0, 0.0);
+        for (int a0 = 0; a0 < cd.y; a0 += 4) {
+          double2 v[4], r01[4];
+          double r2[4];
+#pragma unroll
+          for (int u = 0; u < 4; u++) {                      // all loads of the chunk first (independent)
+            const bool on = a0 + u < cd.y;
+            v[u] = on ? __ldg(vp + a0 + u) : make_double2(0.0, 0.0);
+            r01[u] = on ? ldg2(ra + (a0 + u) * 4) : make_double2(0.0, 0.0);
+            r2[u] = (MODE == 0 && on) ? __ldg(ra + (a0 + u) * 4 + 2) : 0.0;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            cfma(t[0], r01[u].x, v[u]);
+            if (MODE == 0) { cfma(t[1], r01[u].y, v[u]); cfma(t[2], r2[u], v[u]); }
+          }
+        }
+        const double2 b01 = ldg2(rgl + (size_t)cd.w * 4);
+        const double b2 = MODE == 0 ? __ldg(rgl + (size_t)cd.w * 4 + 2) : 0.0;
+#pragma unroll
+        for (int j = 0; j < NJ; j++) {
+          cfma(acc[j][0], b01.x, t[j]);
+          if (MODE == 0) { cfma(acc[j][1], b01.y, t[j]); cfma(acc[j][2], b2, t[j]); }
         }
       }
     }

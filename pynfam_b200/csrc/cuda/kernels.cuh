@@ -164,11 +164,12 @@ struct Sf2Dev {
   int enabled = 0;
   int nzr = 0;
   // density: the elements of rho / kappa regrouped by (sweep, zr, zr') -- element i of list k (rho q0, rho q1, kappa q0,
-  // kappa q1) is rsp[..][el_src[k][i]], its row / column have the padded rows el_ab[k][i]; eptr: first element of every
-  // (sweep, zr, zr') group.  The packed copy pk[..][i] = (re, im) is written in this order every iteration.
-  const int2* el_ab[4] = {nullptr, nullptr, nullptr, nullptr};
+  // kappa q1) is rsp[..][el_src[k][i]]; the packed copy pk[..][i] = (re, im) is written in this order every iteration.
+  // cols[k][c] = (first element, rows, padded row of the first row, padded row of the column): the columns of the
+  // sub-blocks of a group (contiguous runs of the packed copy); cptr: first column of every (sweep, zr, zr') group.
   const int* el_src[4] = {nullptr, nullptr, nullptr, nullptr};
-  const int* eptr[4] = {nullptr, nullptr, nullptr, nullptr};          // [4 sweeps][nzr*nzr + 1]
+  const int4* cols[4] = {nullptr, nullptr, nullptr, nullptr};
+  const int* cptr[4] = {nullptr, nullptr, nullptr, nullptr};          // [4 sweeps][nzr*nzr + 1]
   int nelem[4] = {0, 0, 0, 0};
   const int2* zrange[4] = {nullptr, nullptr, nullptr, nullptr};       // [4 sweeps][nzr]: zr' range with non-empty pair lists
   const int* order[4] = {nullptr, nullptr, nullptr, nullptr};          // [4 sweeps][1 + nzr*nzr]: count, then the non-empty (zr, zr')

@@ -370,8 +370,8 @@ extern "C" void pnfam_b200_ctx_destroy(pnfam_b200_ctx* c) {
 namespace {
 
 struct Sf2Lists {                 // device lists of the fully factorised path (hamiltonian_sf2.cu)
-  DBuf<int2> el_ab[4];            // rho q0, rho q1, kappa q0, kappa q1
-  DBuf<int> el_src[4], eptr[4];
+  DBuf<int4> cols[4];             // rho q0, rho q1, kappa q0, kappa q1
+  DBuf<int> el_src[4], cptr[4];
   int nelem[4] = {0, 0, 0, 0};
   DBuf<int2> zrange[4];
   DBuf<int> order[4];
@@ -381,7 +381,7 @@ struct Sf2Lists {                 // device lists of the fully factorised path (
   void fill(Sf2Dev& F, int nzr) const {
     F.enabled = 1; F.nzr = nzr;
     for (int k = 0; k < 4; k++) {
-      F.el_ab[k] = el_ab[k].p; F.el_src[k] = el_src[k].p; F.eptr[k] = eptr[k].p; F.nelem[k] = nelem[k];
+      F.cols[k] = cols[k].p; F.el_src[k] = el_src[k].p; F.cptr[k] = cptr[k].p; F.nelem[k] = nelem[k];
       F.zrange[k] = zrange[k].p; F.order[k] = order[k].p;
     }
     for (int m = 0; m < 2; m++)
@@ -414,8 +414,8 @@ struct OperatorDev {
 // fully factorised path: sub-block lists of the density (one list per input structure, built from the same steps as the
 // packed images) and (row, column-run) tasks of the radial projection (one list per output structure)
 struct Sf2Elems {                 // host image of one element list of the fully factorised density
-  std::vector<int2> ab;
-  std::vector<int> src, eptr, order;
+  std::vector<int4> cols;
+  std::vector<int> src, cptr, order;
   std::vector<int2> zrange;
 };
 Sf2Elems build_sf2_elems(const pnfam_b200_ctx& c, const BlockStruct& st) {
@@ -446,21 +446,20 @@ Sf2Elems build_sf2_elems(const pnfam_b200_ctx& c, const BlockStruct& st) {
     }
   }
   Sf2Elems E;
-  E.eptr.assign((size_t)4 * (npair + 1), 0);
+  E.cptr.assign((size_t)4 * (npair + 1), 0);
   E.order.assign((size_t)4 * (npair + 1), 0);
   E.zrange.assign((size_t)4 * nzr, make_int2(0, 0));
   for (int sw = 0; sw < 4; sw++) {
     std::vector<std::pair<long, int>> w;
     for (int p = 0; p < npair; p++) {
-      E.eptr[(size_t)sw * (npair + 1) + p] = (int)E.ab.size();
+      E.cptr[(size_t)sw * (npair + 1) + p] = (int)E.cols.size();
       long work = 0;
       for (const Sub& e : byk[(size_t)sw * npair + p]) {
-        for (int b = 0; b < e.nb; b++)
-          for (int a = 0; a < e.na; a++) {
-            E.ab.push_back(make_int2(e.a_row0 + a, e.b_row0 + b));
-            E.src.push_back(e.src_off + c.h_p2l[e.a_row0 + a] + c.h_p2l[e.b_row0 + b] * e.src_ld);
-          }
-        work += (long)e.na * e.nb;
+        for (int b = 0; b < e.nb; b++) {
+          E.cols.push_back(make_int4((int)E.src.size(), e.na, e.a_row0, e.b_row0 + b));
+          for (int a = 0; a < e.na; a++) E.src.push_back(e.src_off + c.h_p2l[e.a_row0 + a] + c.h_p2l[e.b_row0 + b] * e.src_ld);
+        }
+        work += (long)e.na * e.nb + 3 * e.nb;
       }
       if (work > 0) {
         w.push_back({-work, p});
@@ -470,7 +469,7 @@ Sf2Elems build_sf2_elems(const pnfam_b200_ctx& c, const BlockStruct& st) {
         else { r.x = std::min(r.x, z2); r.y = std::max(r.y, z2 + 1); }
       }
     }
-    E.eptr[(size_t)sw * (npair + 1) + npair] = (int)E.ab.size();
+    E.cptr[(size_t)sw * (npair + 1) + npair] = (int)E.cols.size();
     std::sort(w.begin(), w.end());              // non-empty (zr, zr') entries by decreasing work
     int* o = &E.order[(size_t)sw * (npair + 1)];
     o[0] = (int)w.size();
@@ -514,9 +513,9 @@ void build_sf2_tasks(const pnfam_b200_ctx& c, const BlockStruct& st, DBuf<Sf2Tas
 void build_sf2_lists(const pnfam_b200_ctx& c, const BlockStruct* in[4], const BlockStruct* out[2][2], Sf2Lists& L) {
   for (int k = 0; k < 4; k++) {
     Sf2Elems E = build_sf2_elems(c, *in[k]);
-    L.nelem[k] = (int)E.ab.size();
-    if (E.ab.empty()) { E.ab.push_back(make_int2(0, 0)); E.src.push_back(0); }
-    L.el_ab[k].upload(E.ab); L.el_src[k].upload(E.src); L.eptr[k].upload(E.eptr); L.order[k].upload(E.order); L.zrange[k].upload(E.zrange);
+    L.nelem[k] = (int)E.src.size();
+    if (E.src.empty()) { E.cols.push_back(make_int4(0, 0, 0, 0)); E.src.push_back(0); }
+    L.cols[k].upload(E.cols); L.el_src[k].upload(E.src); L.cptr[k].upload(E.cptr); L.order[k].upload(E.order); L.zrange[k].upload(E.zrange);
   }
   for (int m = 0; m < 2; m++)
     for (int q = 0; q < 2; q++) build_sf2_tasks(c, *out[m][q], L.tasks[m][q], L.ntasks[m][q], L.need[m][q]);
