@@ -215,7 +215,7 @@ void launch_density_sf2(const HamArgs& a, cudaStream_t stream) {
 // projection, z part: kt^{jj'}[zr][zr'] of one (il, sa, sb)
 // ================================================================================================
 template <int MODE>
-__global__ void __launch_bounds__(256) sf2_kappa_kernel(HamArgs g) {
+__global__ void __launch_bounds__(256, 3) sf2_kappa_kernel(HamArgs g) {
   constexpr int NP = MODE == 0 ? SF_MFP : 1;       // field-tensor pairs
   constexpr int NJJ = MODE == 0 ? SF2_NJJ : 1;
   extern __shared__ __align__(16) unsigned char smem[];
@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(256) sf2_kappa_kernel(HamArgs g) {
 // projection, radial part: one thread = one row a x a run of <= SF2_RUN columns with equal n_z
 // ================================================================================================
 template <int MODE>
-__global__ void __launch_bounds__(128) sf2_radial_kernel(HamArgs g, int q) {
+__global__ void __launch_bounds__(128, 6) sf2_radial_kernel(HamArgs g, int q) {
   constexpr int NJJ = MODE == 0 ? SF2_NJJ : 1;
   const SfDev& S = g.sf;
   const Sf2Dev& F = g.sf2;
