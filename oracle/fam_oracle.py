@@ -901,7 +901,7 @@ def model_from_problem(p):
         m[k] = p.f64(k)
     for k in ('cdrho', 'ctau', 'ctj0', 'ctj1', 'ctj2', 'crdj', 'cds', 'ct', 'cj', 'cgs', 'cf', 'csdj'):
         m[k] = p.scalar(k)
-    m['blo_active'] = bool(p.iscalar('blo_active'))
+    m['blo_active'] = bool(p.iscalar('statistical'))   # equal filling or finite temperature: P,Q quadrants + T factors
     if m['blo_active']:
         m['qp_fn'], m['qp_fp'] = p.f64('qp_fn'), p.f64('qp_fp')
     return m

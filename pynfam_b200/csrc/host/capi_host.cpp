@@ -61,7 +61,8 @@ int pnfam_problem_scalar(const pnfam_problem* h, const char* name, double* out) 
   std::map<std::string, double> m = {
       {"nb", b.nb}, {"dqp", b.dqp}, {"nghl", b.nghl}, {"ngh", b.ngh}, {"ngl", b.ngl}, {"sep_nzrows", b.sep_nzrows}, {"n_shells", b.n_shells}, {"dmat", (double)b.dmat},
       {"npr_n", b.npr[0]}, {"npr_p", b.npr[1]}, {"nxy", (double)p.f.mat.elem.size()}, {"nxterms", (double)p.g.size()},
-      {"beta_minus", p.f.beta_minus}, {"blo_active", b.blo_active},
+      {"beta_minus", p.f.beta_minus}, {"blo_active", b.blo_active}, {"ft_active", b.ft_active}, {"ft_temp", b.ft_temp},
+      {"statistical", b.statistical()},
       {"blo_qp_n", b.blo_qp[0]}, {"blo_qp_p", b.blo_qp[1]},
       {"skip_residual", x.skip_residual},
       {"cdrho", x.cdrho}, {"ctau", x.ctau}, {"ctj0", x.ctj0}, {"ctj1", x.ctj1}, {"ctj2", x.ctj2}, {"crdj", x.crdj},

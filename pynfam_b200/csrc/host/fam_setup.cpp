@@ -162,6 +162,16 @@ FamBasis FamBasis::build(const HfbSolution& s) {
     M.swap(o);
   };
   reorder_rows(b.Un); reorder_rows(b.Vn); reorder_rows(b.Up); reorder_rows(b.Vp);
+  // finite temperature: Fermi-Dirac occupations re-made from the doubled quasiparticle energies, indexed like E
+  // (hfbtho_solution.f90:364-388); the pairing-window erase below zeroes them with E
+  b.ft_active = s.ft_active; b.ft_temp = s.temper;
+  if (b.ft_active) {
+    b.qp_fn.resize(N); b.qp_fp.resize(N);
+    for (int i = 0; i < N; i++) {
+      b.qp_fn[i] = 0.5 * (1.0 - std::tanh(0.5 * b.En[i] / b.ft_temp));
+      b.qp_fp[i] = 0.5 * (1.0 - std::tanh(0.5 * b.Ep[i] / b.ft_temp));
+    }
+  }
   // pairing window: zero E and the U,V columns of inactive quasiparticles (:402-459)
   for (int it = 0; it < 2; it++) {
     std::vector<char> active(N, 0);
@@ -180,6 +190,7 @@ FamBasis FamBasis::build(const HfbSolution& s) {
       for (int ic = 0; ic < d; ic++, iqp++, im += d) {
         if (!active[iqp]) {
           E[iqp] = 0;
+          if (b.ft_active) (it == 0 ? b.qp_fn : b.qp_fp)[iqp] = 0;
           for (int r = 0; r < d; r++) { U[im + r] = 0; V[im + r] = 0; }
         }
       }
@@ -194,6 +205,8 @@ FamBasis FamBasis::build(const HfbSolution& s) {
       b.blo_ib[it] = s.blo_block[it]; b.blo_is[it] = s.blo_state[it];
     }
   }
+  if (b.blo_active && b.ft_active)       // pnfam_setup.f90:166-169
+    throw std::runtime_error("this code cannot handle T>0 and odd-Z/odd-N simultaneously.");
   if (b.blo_active) {
     b.qp_fn.assign(N, 0.0); b.qp_fp.assign(N, 0.0);
     auto trev = [&](int q) { return q <= N / 2 ? q + N / 2 : q - N / 2; };

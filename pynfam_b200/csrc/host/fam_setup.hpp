@@ -76,7 +76,10 @@ struct FamBasis {
   bool blo_active = false;
   int blo_qp[2] = {0, 0};                // 1-based overall qp index of the blocked level (n, p)
   int blo_ib[2] = {0, 0}, blo_is[2] = {0, 0};
-  std::vector<double> qp_fn, qp_fp;      // equal-filling occupations (only if blo_active)
+  std::vector<double> qp_fn, qp_fp;      // quasiparticle occupations: equal filling (blo_active) or Fermi-Dirac (ft_active)
+  bool ft_active = false;                // finite-temperature HFB solution (pnfam_setup.f90:323-331)
+  double ft_temp = 0;                    // MeV
+  bool statistical() const { return blo_active || ft_active; }   // P,Q quadrants and T factors in the FAM
   // functional data handed over from HFBTHO
   double hfb_cpair[2] = {0, 0}, hfb_alpha_pair[2] = {0, 0}, rho_nm = 0.16, hbzero = 0;
   double hfb_cr0 = 0, hfb_crr = 0, hfb_cdrho = 0, hfb_ctau = 0, hfb_ctj = 0, hfb_crdj = 0;

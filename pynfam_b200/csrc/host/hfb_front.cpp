@@ -487,7 +487,8 @@ static void gamdel(HfbSolution& s, const HelData& h) {
 // ALambda: Fermi level from the BCS-like reference spectrum (erhfb, drhfb)
 // ---------------------------------------------------------------------------------------------
 static void alambda(double& al, int kl, const std::vector<double>& erhfb, std::vector<double>& drhfb, double tz,
-                    double cpv0, int blok1k2d) {
+                    double cpv0, int blok1k2d, double temper, std::vector<double>* f_T) {
+  const bool hot = f_T != nullptr && temper > 1e-12;
   if (cpv0 == 0.0) {
     int ntz = (int)(tz + 0.1); ntz /= 2;
     std::vector<double> d(erhfb.begin(), erhfb.begin() + kl);
@@ -498,18 +499,25 @@ static void alambda(double& al, int kl, const std::vector<double>& erhfb, std::v
   }
   double xinf = -1000.0, xsup = 1000.0;
   for (int lit = 1; lit <= 500; lit++) {
-    double sn = 0, dez = 0;
+    double sn = 0, dez = 0, dfz = 0;
     for (int i = 0; i < kl; i++) {
-      double vh = 0, dvh = 0;
+      double vh = 0, dvh = 0, fT = 0, dfT = 0;
       const double y = erhfb[i] - al, a = y * y + drhfb[i] * drhfb[i], b = std::sqrt(a);
+      if (hot) {
+        fT = 0.5 * (1.0 - std::tanh(0.5 * b / temper));
+        dfT = y / b / temper * fT * (1.0 - fT);
+        (*f_T)[i] = fT;
+      }
       if (b > 0) vh = 0.5 * (1.0 - y / b);
       if (vh < 1e-12) vh = 0;
       if ((vh - 1.0) > 1e-12) vh = 1.0;
       if (b > 0) dvh = 0.5 * drhfb[i] * drhfb[i] / (a * b);
       if (i + 1 == blok1k2d) { vh = 0.5; dvh = 0; }
-      sn += 2.0 * vh;
-      dez += 2.0 * dvh;
+      sn += 2.0 * vh + 2.0 * (1.0 - 2.0 * vh) * fT;
+      dez += 2.0 * (1.0 - 2.0 * fT) * dvh;
+      dfz += 2.0 * (1.0 - 2.0 * vh) * dfT;
     }
+    dez += dfz;
     const double ez = sn - tz, absez = std::fabs(ez) / tz;
     if (ez < 0) xinf = std::max(xinf, al);
     else xsup = std::min(xsup, al);
@@ -542,6 +550,7 @@ static void hfbdiag(HfbSolution& s, const HelData& h, const HfbInput& in, int it
   std::vector<std::vector<double>> evec(nb), eval(nb);
   std::vector<double> erhfb(nt), drhfb(nt);
   const double tz = (double)s.npr[it];
+  const bool hot = s.ft_active && s.temper > 1e-12;
   const double sitest = std::min(0.10, h.si * 0.010);
   bool norm_to_improve = true;
   int inner = -1;
@@ -674,11 +683,12 @@ static void hfbdiag(HfbSolution& s, const HelData& h, const HfbInput& in, int it
         }
         i_uv += nd;
         i_eqp++;
+        const double fT = hot ? 0.5 * (1.0 - std::tanh(0.5 * eqpe / s.temper)) : 0.0;
         if (lpr_pwi) {
           if (k0 == k + 1) blok1k2d = kl + 1;
           erhfb[kl] = enb; drhfb[kl] = ekb; s.occ[it][kl] = pn;
           kl++;
-          sumnz += 2.0 * pn;
+          sumnz += 2.0 * pn + 2.0 * (1.0 - 2.0 * pn) * fT;
         }
       }
       if (!norm_to_improve) { s.ka[it][ib] = kaib; s.kd[it][ib] = kl - kaib; }
@@ -689,7 +699,8 @@ static void hfbdiag(HfbSolution& s, const HelData& h, const HfbInput& in, int it
     s.klmax[it] = kl;
     if (!norm_to_improve) s.ala[it] = al;
     double alnew = al;
-    alambda(alnew, kl, erhfb, drhfb, tz, s.CpV0[it], blok1k2d);
+    if (s.ft_active) s.fT_pwi[it].assign(kl, 0.0);
+    alambda(alnew, kl, erhfb, drhfb, tz, s.CpV0[it], blok1k2d, s.temper, s.ft_active ? &s.fT_pwi[it] : nullptr);
     if (keyblo == 0) ala = alnew;
     else ala = ala + 0.50 * (alnew - ala);
   }
@@ -717,16 +728,23 @@ static void densit_rho(HfbSolution& s) {
       // The reference indexes the ACTIVE list of the block with blo123d (DENSIT: "PNIK=OMPANK(JN+K0)",
       // "If(K.Ne.K0) Cycle"), i.e. it assumes every qp below the blocked one is inside the window.
       const int k0_active = (k0 >= 1 && k0 <= imen) ? k0 : 0;
-      std::vector<double> tfiu(imen), tfid(imen);
+      std::vector<double> tfiu(imen), tfid(imen), pfiu, pfid;
+      if (s.ft_active) { pfiu.resize(imen); pfid.resize(imen); }
       for (int ihil = 0; ihil < nghl; ihil++) {
         std::fill(tfiu.begin(), tfiu.end(), 0.0);
         std::fill(tfid.begin(), tfid.end(), 0.0);
+        std::fill(pfiu.begin(), pfiu.end(), 0.0);
+        std::fill(pfid.begin(), pfid.end(), 0.0);
         double piu = 0, pid = 0;
         for (int i = 0; i < nd; i++) {
           const int ja = im + i;
           const double q = s.qhla[(size_t)ja * nghl + ihil];
           double* dst = s.ns[ja] > 0 ? tfiu.data() : tfid.data();
           for (int k = 0; k < imen; k++) dst[k] += q * s.V[it][(size_t)s.Kpwi[it][k1 + k] + i];
+          if (s.ft_active) {                          // the U component of the quasiparticle (hfbtho_solver.f90:4484-4492)
+            double* dsu = s.ns[ja] > 0 ? pfiu.data() : pfid.data();
+            for (int k = 0; k < imen; k++) dsu[k] -= q * s.U[it][(size_t)s.Kpwi[it][k1 + k] + i];
+          }
           if (k0_active) {
             const double pnik = s.U[it][(size_t)s.Kpwi[it][k1 + k0_active - 1] + i];
             if (s.ns[ja] > 0) piu += pnik * q; else pid += pnik * q;
@@ -734,7 +752,11 @@ static void densit_rho(HfbSolution& s) {
         }
         double t = 0;
         for (int k = 0; k < imen; k++) {
-          const double temp2 = tfiu[k] * tfiu[k] + tfid[k] * tfid[k];
+          double temp2 = tfiu[k] * tfiu[k] + tfid[k] * tfid[k];
+          if (s.ft_active) {                          // TEMP2 of DENSIT, hfbtho_solver.f90:4535-4545
+            const double f1k = s.fT_pwi[it][k1 + k], fk = 1.0 - f1k;
+            temp2 = temp2 * fk + (pfiu[k] * pfiu[k] + pfid[k] * pfid[k]) * f1k;
+          }
           t += temp2;
           if (k + 1 == k0_active) t -= 0.5 * (temp2 - (piu * piu + pid * pid));
         }
@@ -766,7 +788,7 @@ unsigned long long hash_file(const std::string& path, unsigned long long seed) {
 }
 
 namespace {
-constexpr unsigned long long CACHE_MAGIC = 0x42323030484642ull + (2ull << 56);   // "B200HFB", format 2
+constexpr unsigned long long CACHE_MAGIC = 0x42323030484642ull + (3ull << 56);   // "B200HFB", format 3
 struct CacheIO {
   FILE* f;
   bool ok = true, writing;
@@ -794,6 +816,7 @@ void cache_fields(CacheIO& io, HfbSolution& s) {
     io.vec(s.ka[it]); io.vec(s.kd[it]); io.vec(s.Kqp[it]); io.vec(s.Kpwi[it]); io.vec(s.occ[it]); io.vec(s.ro[it]);
     io.pod(s.ala[it]); io.pod(s.ala_out[it]); io.pod(s.inner[it]); io.pod(s.klmax[it]);
     io.pod(s.keyblo[it]); io.pod(s.blo_block[it]); io.pod(s.blo_state[it]); io.pod(s.blok1k2d[it]);
+    io.vec(s.fT_pwi[it]);
   }
 }
 bool cache_load(const std::string& path, unsigned long long key, HfbSolution& s) {
@@ -836,11 +859,13 @@ void cache_save(const std::string& path, unsigned long long key, HfbSolution& s)
 
 HfbSolution HfbSolution::build(const HfbInput& in, const HelData& h, const std::string& cache_file, unsigned long long cache_key) {
   if (in.type_of_calculation < 0) throw std::runtime_error("Lipkin-Nogami (type_of_calculation<0) is not supported");
-  if (in.set_temperature && std::fabs(in.temperature) > 1e-10)
-    throw std::runtime_error("finite-temperature HFB solutions are not supported yet");
   if (h.finite_range) throw std::runtime_error("finite-range (Gogny) functionals are not supported");
   if (h.has_hfb_matrix) throw std::runtime_error(".hel with an HFBmatrX record is not supported");
   HfbSolution s;
+  // finite temperature: switched off below 1e-10 MeV (hfbtho_interface.f90:157-158)
+  s.ft_active = in.set_temperature && std::fabs(in.temperature) > 1e-10;
+  s.temper = in.temperature;
+  if (s.ft_active && in.temperature < 0) throw std::runtime_error("temperature out-of-bounds: T>=0");
   s.nb = h.nb; s.nt = h.nt; s.ngh = h.ngh; s.ngl = h.ngl; s.nghl = h.ngh * h.ngl; s.n_shells = h.n00;
   s.b0 = h.b0; s.bz = h.bz; s.bp = h.bp;
   s.id = h.id; s.nr = h.nr; s.nz = h.nz; s.nl = h.nl; s.ns = h.ns;

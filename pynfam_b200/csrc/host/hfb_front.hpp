@@ -86,6 +86,11 @@ struct HfbSolution {
   int klmax[2] = {0, 0};
   // blocking (odd nuclei, equal-filling approximation)
   int keyblo[2] = {0, 0}, blo_block[2] = {0, 0}, blo_state[2] = {0, 0}, blok1k2d[2] = {0, 0};
+  // finite temperature (hfbtho_solver.f90:1749-1761, 1987-2022): Fermi-Dirac occupations of the quasiparticles inside
+  // the pairing window as the last ALambda call left them (the values DENSIT weighs the densities with)
+  bool ft_active = false;
+  double temper = 0;
+  std::vector<double> fT_pwi[2];
   // densities
   std::vector<double> ro[2];                        // (nghl) normalised rho_n, rho_p
   // functional info carried for the FAM interaction set-up

@@ -2,6 +2,7 @@
 // (exes/pnfam/pnfam_txtoutput.f90:96-253, parsed by pynfam/outputs/pnfam_parser.py:33-132), the device context of a
 // Problem and the batched solve through the C ABI.
 #pragma once
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
@@ -146,7 +147,21 @@ inline void write_dat(const Problem& p, const std::string& namelist, const std::
   log.line(" " + dash);
   log.line(center(" Statistical pnFAM details", w));
   log.line(" " + dash);
-  log.line(" Finite-temperature active: No");
+  log.fmt(" Finite-temperature active: %s", b.ft_active ? "Yes" : "No");
+  if (b.ft_active) {                       // pnfam_txtoutput.f90:179-186 (its first format ends before " MeV")
+    auto f04 = [](double v) {              // Fortran F0.4: no leading zero
+      char t[64]; std::snprintf(t, sizeof t, "%.4f", v);
+      std::string o(t);
+      if (o.rfind("0.", 0) == 0) o.erase(0, 1);
+      else if (o.rfind("-0.", 0) == 0) o.erase(1, 1);
+      return o;
+    };
+    log.fmt("   Temperature .............: %8.4f", b.ft_temp);
+    const size_t ip = std::max_element(b.qp_fp.begin(), b.qp_fp.end()) - b.qp_fp.begin();
+    const size_t in_ = std::max_element(b.qp_fn.begin(), b.qp_fn.end()) - b.qp_fn.begin();
+    log.fmt("   Approx. max. f_p ........: %8.4f (Ep=%sMeV)", b.qp_fp[ip], f04(b.Ep[ip]).c_str());
+    log.fmt("   Approx. max. f_n ........: %8.4f (En=%sMeV)", b.qp_fn[in_], f04(b.En[in_]).c_str());
+  }
   log.fmt(" Odd-nucleus EFA active ..: %s", b.blo_active ? "Yes" : "No");
   if (b.blo_active) {
     const char* nm[2] = {"Neutron", "Proton"};
@@ -206,7 +221,7 @@ inline pnfam_b200_ctx* make_context(const Problem& p, int device, char* err, int
   m.cdrho = x.cdrho; m.ctau = x.ctau; m.ctj0 = x.ctj0; m.ctj1 = x.ctj1; m.ctj2 = x.ctj2; m.crdj = x.crdj; m.cds = x.cds;
   m.ct = x.ct; m.cj = x.cj; m.cgs = x.cgs; m.cf = x.cf; m.csdj = x.csdj;
   m.Ep = b.Ep.data(); m.En = b.En.data(); m.Up = b.Up.data(); m.Vp = b.Vp.data(); m.Un = b.Un.data(); m.Vn = b.Vn.data();
-  m.qp_fp = b.blo_active ? b.qp_fp.data() : nullptr; m.qp_fn = b.blo_active ? b.qp_fn.data() : nullptr;
+  m.qp_fp = b.statistical() ? b.qp_fp.data() : nullptr; m.qp_fn = b.statistical() ? b.qp_fn.data() : nullptr;
   m.ngh = b.ngh; m.ngl = b.ngl; m.sep_nzrows = b.sep_nzrows;
   m.sep_zrow = b.sep_zrow.data(); m.sep_z = b.sep_z.data(); m.sep_r = b.sep_r.data();
   pnfam_b200_ctx* ctx = nullptr;

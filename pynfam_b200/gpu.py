@@ -109,7 +109,7 @@ class Context:
             setattr(m, name, _dp(k[name]))
         for name in ("cdrho", "ctau", "ctj0", "ctj1", "ctj2", "crdj", "cds", "ct", "cj", "cgs", "cf", "csdj"):
             setattr(m, name, p.scalar(name))
-        if p.iscalar("blo_active"):
+        if p.iscalar("statistical"):      # odd-A equal filling or finite temperature: P,Q quadrants, T factors
             k["qp_fp"], k["qp_fn"] = np.ascontiguousarray(p.f64("qp_fp")), np.ascontiguousarray(p.f64("qp_fn"))
             m.qp_fp, m.qp_fn = _dp(k["qp_fp"]), _dp(k["qp_fn"])
         if separable:

@@ -6,7 +6,7 @@ import re
 import numpy as np
 import pytest
 
-from conftest import ROOT, stage_point
+from conftest import GOLDEN, ROOT, stage_point
 from oracle import refrun
 from pynfam_b200 import host
 
@@ -76,6 +76,29 @@ def test_front_end_basis_and_orthonormality(tmp_path):
     # particle number from the normalised coordinate-space densities
     w = 1.0 / p.f64("wdcori")
     assert abs((p.f64("rho_n") * w).sum() - 24) < 1e-9 and abs((p.f64("rho_p") * w).sum() - 16) < 1e-9
+
+
+def test_finite_temperature_setup(tmp_path):
+    """Finite-temperature HFB solution (T = 0.8 MeV fixture made with the reference's executables): thermal occupations
+    re-made from the quasiparticle energies (hfbtho_solution.f90:364-388), zeroed outside the pairing window; the largest
+    ones against the reference's own log header (pnfam_txtoutput.f90:179-186); densities weighted with them integrate
+    to N and Z (DENSIT, hfbtho_solver.f90:4535-4545)."""
+    stage_point("Gd162_finiteT_6sh", "GT-K0", 0, str(tmp_path))
+    p = host.Problem(str(tmp_path), "x.in")
+    assert p.iscalar("ft_active") == 1 and p.iscalar("blo_active") == 0 and p.iscalar("statistical") == 1
+    assert p.scalar("ft_temp") == 0.8
+    fp, fn, Ep, En = p.f64("qp_fp"), p.f64("qp_fn"), p.f64("Ep"), p.f64("En")
+    ref = open(os.path.join(GOLDEN, "Gd162_finiteT_6sh", "reference_stdout.txt")).read()
+    import re
+    mp = re.search(r"max\. f_p \.+:\s+(\S+) \(Ep=(\S+)MeV\)", ref)
+    mn = re.search(r"max\. f_n \.+:\s+(\S+) \(En=(\S+)MeV\)", ref)
+    assert abs(fp.max() - float(mp.group(1))) < 6e-5 and abs(Ep[fp.argmax()] - float(mp.group(2))) < 6e-5
+    assert abs(fn.max() - float(mn.group(1))) < 6e-5 and abs(En[fn.argmax()] - float(mn.group(2))) < 6e-5
+    for f, E in ((fp, Ep), (fn, En)):
+        act = E != 0
+        assert (f[~act] == 0).all() and np.allclose(f[act], 0.5 * (1 - np.tanh(0.5 * E[act] / 0.8)), rtol=0, atol=1e-15)
+    w = 1.0 / p.f64("wdcori")
+    assert abs((p.f64("rho_n") * w).sum() - 98) < 1e-9 and abs((p.f64("rho_p") * w).sum() - 64) < 1e-9
 
 
 def test_couplings_match_reference_header(tmp_path):

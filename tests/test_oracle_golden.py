@@ -20,6 +20,8 @@ CASES = [
     ("Gd162_0-_closed_6sh", "PS0-K0", 8),
     ("S40_All_GT2bc", "GT-K0", 4),       # two-body currents: Yukawa part from GT-K0.tbc + contact + (-1-body)
     ("Gd163_blocked_6sh", "GT-K0", 0),   # odd-A, blocked 5/2-[523] neutron: P,Q quadrants + statistical factors
+    ("Gd162_finiteT_6sh", "GT-K0", 0),   # finite temperature (T = 0.8 MeV): thermal occupations, P,Q quadrants
+    ("Gd162_finiteT_6sh", "RS1-K1", 0),
 ]
 
 
