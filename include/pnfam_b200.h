@@ -153,6 +153,14 @@ int pnfam_b200_calc_hamiltonian(pnfam_b200_ctx* ctx, const pnfam_b200_blockmatri
  * kernels: returns achieved TFLOP/s of a register-resident DMMA loop on all SMs. */
 int pnfam_b200_dmma_peak(int device, double* tflops, char* err, int errlen);
 
+/* Host-only self-check of the transform plan (no device needed): builds the block-task list of
+ * triprod_bbm (pnfam_type_bbm.f90:428-576) for the given block structure, regroups it into the jobs of the
+ * fused transform kernel and evaluates both forms on the CPU with random operands.
+ * out[0..3] = forward {tasks, jobs, products(jobs) / products(tasks), max |difference|}, out[4..7] = backward.
+ * Returns 0, 2 if the structure stays with the two-phase kernels, 1 on error. */
+int pnfam_b200_check_transform_plan(int32_t nb, const int32_t* db, const int32_t* f_ir2c, int32_t use_diag,
+                                    int32_t beta_minus, double* out, char* err, int errlen);
+
 #ifdef __cplusplus
 }
 #endif

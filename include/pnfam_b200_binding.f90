@@ -166,6 +166,17 @@ module pnfam_b200_binding
          character(kind=c_char) :: err(*)
          integer(c_int), value :: errlen
       end function
+
+      ! host-only self-check of the transform plan (no device needed)
+      integer(c_int) function pnfam_b200_check_transform_plan(nb, db, f_ir2c, use_diag, beta_minus, res, err, errlen) &
+            bind(C, name="pnfam_b200_check_transform_plan")
+         import
+         integer(c_int32_t), value :: nb, use_diag, beta_minus
+         integer(c_int32_t), intent(in) :: db(*), f_ir2c(*)
+         real(c_double), intent(out) :: res(8)
+         character(kind=c_char) :: err(*)
+         integer(c_int), value :: errlen
+      end function
    end interface
 
    ! calc_hamiltonian-shaped wrapper (to be placed in the host's own module, after `contains`): point `calc_hamiltonian => calc_dHsp_b200` in setup_hamiltonian

@@ -123,4 +123,25 @@ struct DevTask {
   DevTerm t[4];
 };
 
+
+// fused transform jobs (transform.cu): the terms of one or two output blocks regrouped by associativity,
+//   T_x = sum_{t in group x} alpha_t op(A_t) op(B_t)            (phase 1, the products two outputs share are formed once)
+//   out_o = sum_x beta_{o,x} T_x op(C_{o,x})                    (phase 2, T_x stays in the registers of the warp)
+struct FusedTerm {
+  int a_mat, a_off, a_trans;
+  int b_quad, b_off, b_trans;
+  double alpha_re, alpha_im;
+};
+struct FusedOut {
+  int out_quad, out_off;
+  int c_mat[2], c_off[2], c_trans[2];     // per group
+  double beta_re[2], beta_im[2];
+};
+struct FusedJob {
+  int m, n, ngroups, nout;
+  int nterms[2];
+  FusedTerm t[2][2];                      // [group][term]
+  FusedOut o[2];
+};
+
 }  // namespace pnfam

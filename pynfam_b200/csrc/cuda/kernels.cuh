@@ -36,6 +36,12 @@ struct DevicePlan {
   const int4* tiles2 = nullptr;   // phase 2: (task, 0, first row, first column)
   int ntasks = 0, ntiles1 = 0, ntiles2 = 0, max_dim = 0;
   size_t scratch_elems = 0;       // doubles of scratch per (point, re/im)
+  // fused path (one launch per size class, no scratch): jobs + (job, first m-tile, m-tiles, 0) per CTA, largest first
+  const FusedJob* jobs = nullptr;
+  const int4* fctas[3] = {nullptr, nullptr, nullptr};   // size classes: n <= 88, <= 128, <= 176
+  int nfctas[3] = {0, 0, 0};
+  bool fused = false;
+  int njobs = 0;
 };
 
 struct TransformArgs {
@@ -53,7 +59,8 @@ struct TransformArgs {
   const BatchCtrl* ctrl;          // device-side active count (nullptr: the grid is exact)
 };
 
-void launch_transform(const DevicePlan& plan, const TransformArgs& args, int nactive, cudaStream_t stream);
+// returns the number of kernels launched
+int launch_transform(const DevicePlan& plan, const TransformArgs& args, int nactive, cudaStream_t stream);
 
 // ---- (b)/(c) hamiltonian --------------------------------------------------------------------------
 // Bilinear grid densities D[t][t'][s][s'] = sum_{a in s, b in s'} phi^t_a(r) rho_ab phi^t'_b(r)

@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <mutex>
 #include <numeric>
@@ -389,8 +390,14 @@ struct Sf2Lists {                 // device lists of the fully factorised path (
   }
 };
 
+struct FusedPlanBuf {
+  DBuf<FusedJob> jobs;
+  DBuf<int4> ctas[3];
+};
+
 struct OperatorDev {
   OperatorPlan plan;
+  FusedPlanBuf fwd_fused, bwd_fused;
   DBuf<DevTask> fwd_tasks, bwd_tasks;
   DBuf<int4> fwd_tiles1, fwd_tiles2, bwd_tiles1, bwd_tiles2;
   DevicePlan fwd, bwd;
@@ -641,6 +648,137 @@ void flatten(const TransformPlan& tp, DBuf<DevTask>& dt, DBuf<int4>& d1, DBuf<in
   out.max_dim = maxd; out.scratch_elems = (size_t)toff;
 }
 
+// Jobs of the fused transform kernel (transform.cu).  Per output block the terms are grouped by their C operand,
+// out = sum_x (sum_{t in x} alpha_t A_t B_t) C_x, and two output blocks whose groups are made of the same A_t B_t products
+// (up to one factor per group) share phase 1:  the 8 (16 with P,Q) triple products per block row of the reference's
+// triprod_bbm become 6 (8) products.  Structures the kernel has no shape for (more than 2 groups or 2 terms per group,
+// blocks wider than 176) keep the two-phase kernels.
+bool build_fused_host(const TransformPlan& tp, std::vector<FusedJob>& jobs, std::vector<int4> (&sorted)[3]) {
+  struct Grp { std::vector<int> terms; };
+  jobs.clear();
+  std::map<std::vector<long long>, int> open;            // phase-1 signature -> job with a free output slot
+  auto ab_key = [](const TripleTerm& t) { return (((((long long)t.a_mat * 2 + t.a_trans) * 8 + t.b_quad) * 2 + t.b_trans) << 40) ^ ((long long)t.a_off << 20) ^ t.b_off; };
+  for (const BlockTask& b : tp.tasks) {
+    if (b.n > 176) return false;
+    std::vector<Grp> groups;
+    for (int t = 0; t < b.nterms; t++) {
+      bool found = false;
+      for (Grp& g : groups) {
+        const TripleTerm& r = b.t[g.terms[0]];
+        if (r.c_mat == b.t[t].c_mat && r.c_off == b.t[t].c_off && r.c_trans == b.t[t].c_trans) { g.terms.push_back(t); found = true; break; }
+      }
+      if (!found) groups.push_back(Grp{{t}});
+    }
+    if (groups.size() > 2) return false;
+    for (const Grp& g : groups) if (g.terms.size() > 2) return false;
+    // signature of phase 1: dimensions + the (A, B) products of every group
+    std::vector<long long> sig = {b.m, b.n, (long long)groups.size()};
+    for (const Grp& g : groups) {
+      sig.push_back((long long)g.terms.size());
+      for (int t : g.terms) { sig.push_back(ab_key(b.t[t])); sig.push_back(b.t[t].a_off); sig.push_back(b.t[t].b_off); }
+    }
+    auto fill_out = [&](FusedOut& fo, const double* bre, const double* bim) {
+      fo.out_quad = b.out_quad; fo.out_off = b.out_off;
+      for (size_t x = 0; x < groups.size(); x++) {
+        const TripleTerm& r = b.t[groups[x].terms[0]];
+        fo.c_mat[x] = r.c_mat; fo.c_off[x] = r.c_off; fo.c_trans[x] = r.c_trans;
+        fo.beta_re[x] = bre[x]; fo.beta_im[x] = bim[x];
+      }
+    };
+    auto it = open.find(sig);
+    bool paired = false;
+    if (it != open.end()) {
+      // same products in the same order: this block is beta_x times the phase-1 sums of the job, if the ratio of the
+      // coefficients is one number per group and flavour
+      FusedJob& J = jobs[it->second];
+      double bre[2] = {0, 0}, bim[2] = {0, 0};
+      bool ok = true;
+      for (size_t x = 0; x < groups.size() && ok; x++)
+        for (size_t k = 0; k < groups[x].terms.size() && ok; k++) {
+          const TripleTerm& tt = b.t[groups[x].terms[k]];
+          const FusedTerm& ft = J.t[x][k];
+          if (ft.alpha_re == 0.0 || ft.alpha_im == 0.0) { ok = false; break; }
+          const double rr = tt.alpha_re / ft.alpha_re, ri = tt.alpha_im / ft.alpha_im;
+          if (k == 0) { bre[x] = rr; bim[x] = ri; }
+          else if (rr != bre[x] || ri != bim[x]) ok = false;
+        }
+      if (ok) {
+        fill_out(J.o[1], bre, bim);
+        J.nout = 2;
+        open.erase(it);
+        paired = true;
+      }
+    }
+    if (!paired) {
+      FusedJob J{};
+      J.m = b.m; J.n = b.n; J.ngroups = (int)groups.size(); J.nout = 1;
+      for (size_t x = 0; x < groups.size(); x++) {
+        J.nterms[x] = (int)groups[x].terms.size();
+        for (size_t k = 0; k < groups[x].terms.size(); k++) {
+          const TripleTerm& tt = b.t[groups[x].terms[k]];
+          FusedTerm& ft = J.t[x][k];
+          ft.a_mat = tt.a_mat; ft.a_off = tt.a_off; ft.a_trans = tt.a_trans;
+          ft.b_quad = tt.b_quad; ft.b_off = tt.b_off; ft.b_trans = tt.b_trans;
+          ft.alpha_re = tt.alpha_re; ft.alpha_im = tt.alpha_im;
+        }
+      }
+      const double one[2] = {1.0, 1.0};
+      fill_out(J.o[0], one, one);
+      open[sig] = (int)jobs.size();
+      jobs.push_back(J);
+    }
+  }
+  // CTAs: strips of <= 4 m-tiles, evenly cut; three size classes (register shapes of the kernel); heaviest first
+  std::vector<int4> ctas[3];
+  std::vector<double> work[3];
+  for (size_t j = 0; j < jobs.size(); j++) {
+    const FusedJob& J = jobs[j];
+    const int cls = J.n <= 88 ? 0 : (J.n <= 128 ? 1 : 2);
+    const int m8 = (J.m + 7) / 8, nstrip = (m8 + 3) / 4, per = (m8 + nstrip - 1) / nstrip;
+    double w = 0;
+    for (int x = 0; x < J.ngroups; x++) w += (double)J.nterms[x] * J.m * J.n + (double)J.nout * J.n * J.n;
+    for (int t0 = 0; t0 < m8; t0 += per) {
+      ctas[cls].push_back(make_int4((int)j, t0, std::min(per, m8 - t0), 0));
+      work[cls].push_back(w * std::min(per, m8 - t0));
+    }
+  }
+  for (int k = 0; k < 3; k++) {
+    std::vector<int> idx(ctas[k].size());
+    std::iota(idx.begin(), idx.end(), 0);
+    std::stable_sort(idx.begin(), idx.end(), [&](int a, int b2) { return work[k][a] > work[k][b2]; });
+    sorted[k].clear();
+    for (int i : idx) sorted[k].push_back(ctas[k][i]);
+  }
+  return true;
+}
+
+bool build_fused(const TransformPlan& tp, FusedPlanBuf& fb, DevicePlan& out) {
+  if (getenv("PNFAM_B200_TRANSFORM_2PHASE")) return false;
+  std::vector<FusedJob> jobs;
+  std::vector<int4> sorted[3];
+  if (!build_fused_host(tp, jobs, sorted)) return false;
+  fb.jobs.upload(jobs);
+  out.jobs = fb.jobs.p;
+  for (int k = 0; k < 3; k++) {
+    fb.ctas[k].upload(sorted[k]);
+    out.fctas[k] = fb.ctas[k].p; out.nfctas[k] = (int)sorted[k].size();
+  }
+  out.fused = true;
+  out.njobs = (int)jobs.size();
+  if (getenv("PNFAM_B200_TRANSFORM_DEBUG")) {
+    double p_old = 0, p_new = 0;
+    for (const BlockTask& b : tp.tasks) p_old += (double)b.nterms * ((double)b.m * b.m * b.n + (double)b.m * b.n * b.n);
+    int n2 = 0;
+    for (const FusedJob& J : jobs) {
+      n2 += J.nout == 2;
+      for (int x = 0; x < J.ngroups; x++) p_new += (double)J.nterms[x] * J.m * J.m * J.n + (double)J.nout * J.m * J.n * J.n;
+    }
+    std::fprintf(stderr, "[transform] %zu tasks -> %zu fused jobs (%d with two outputs), CTAs %d/%d/%d, products x%.3f\n", tp.tasks.size(),
+                 jobs.size(), n2, out.nfctas[0], out.nfctas[1], out.nfctas[2], p_new / p_old);
+  }
+  return true;
+}
+
 // 2-quasiparticle tables of matrix_2qp (pnfam_solver.f90:510-544): v[e] = b*f1_i + c*f2_j on a structure
 std::vector<double> table_2qp(const pnfam_b200_ctx& c, const BlockStruct& st, size_t nxy, double b, double cc,
                               const std::vector<double>& f1, const std::vector<double>& f2, double e0) {
@@ -698,6 +836,8 @@ std::unique_ptr<OperatorDev> make_operator(pnfam_b200_ctx& c, const pnfam_b200_o
   od->plan = make_operator_plan(c.db, ir2c, c.use_diag, op.beta_minus != 0);
   flatten(od->plan.forward, od->fwd_tasks, od->fwd_tiles1, od->fwd_tiles2, od->fwd);
   flatten(od->plan.backward, od->bwd_tasks, od->bwd_tiles1, od->bwd_tiles2, od->bwd);
+  build_fused(od->plan.forward, od->fwd_fused, od->fwd);
+  build_fused(od->plan.backward, od->bwd_fused, od->bwd);
   od->scratch_elems = std::max(od->fwd.scratch_elems, od->bwd.scratch_elems);
   for (int k = 0; k < 4; k++) { od->sp[k].upload(od->plan.sp[k]); od->hsp[k].upload(od->plan.hsp[k]); }
   if (c.sf.enabled) {
@@ -929,8 +1069,7 @@ extern "C" int pnfam_b200_solve(pnfam_b200_ctx* c, const pnfam_b200_operator* op
       TransformArgs b = ta;
       b.in = hsp.p; b.in_pstride = 8 * nxy; b.in_pack = 0;
       b.out = hqp.p; b.out_pstride = 8 * nxy; b.out_pack = 0;
-      launch_transform(od->bwd, b, 1, st);
-      launches += 2;
+      launches += launch_transform(od->bwd, b, 1, st);
       PNFAM_CUDA_CHECK(cudaMemcpyAsync(od->gqp.p + (size_t)k * 4 * nxy, hqp.p, 4 * nxy * sizeof(double), cudaMemcpyDeviceToDevice, st));
     }
     PNFAM_CUDA_CHECK(cudaMemsetAsync(hsp.p, 0, 8 * nxy * sizeof(double), st));
@@ -1001,7 +1140,7 @@ extern "C" int pnfam_b200_solve(pnfam_b200_ctx* c, const pnfam_b200_operator* op
         TransformArgs f = ta;
         f.in = vin.p; f.in_pstride = n; f.in_pack = 1;
         f.out = rsp.p; f.out_pstride = 8 * nxy; f.out_pack = 0;
-        launch_transform(od->fwd, f, nact, st);
+        launches += launch_transform(od->fwd, f, nact, st);
         PNFAM_CUDA_CHECK(cudaEventRecord(r.d0.e, st));
         launch_density(ha, st);
         PNFAM_CUDA_CHECK(cudaEventRecord(r.d1.e, st));
@@ -1012,8 +1151,8 @@ extern "C" int pnfam_b200_solve(pnfam_b200_ctx* c, const pnfam_b200_operator* op
         TransformArgs b = ta;
         b.in = hsp.p; b.in_pstride = 8 * nxy; b.in_pack = 0;
         b.out = hqp.p; b.out_pstride = 8 * nxy; b.out_pack = 0;
-        launch_transform(od->bwd, b, nact, st);
-        launches += 2 + 3 + 1 + 5 + 2;   // transform, pack + 2 densities, fields, 4 projections + reduce, transform
+        launches += launch_transform(od->bwd, b, nact, st);
+        launches += 3 + 1 + 5;   // pack + 2 densities, fields, 4 projections + reduce
         n_dens += 2; n_proj += 4;
       }
       launch_greens(ma, st);
@@ -1243,6 +1382,99 @@ __global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters) 
 #pragma unroll
   for (int j = 0; j < 8; j++) s += c[j][0] + c[j][1];
   if (s == 12345.678) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// ---- self-check of the fused transform plan (host only, no device needed) ----------------------------------
+// Builds the operator plan for the given block structure, regroups its tasks into fused jobs and evaluates both forms
+// with random operands on the CPU.  out[0..3] = forward {tasks, jobs, products(jobs)/products(tasks), max |difference|},
+// out[4..7] = the same for the backward transform.  Returns 0, or 2 if the structure is left to the two-phase kernels.
+extern "C" int pnfam_b200_check_transform_plan(int32_t nb, const int32_t* db_, const int32_t* f_ir2c, int32_t use_diag, int32_t beta_minus,
+                                               double* out, char* err, int errlen) {
+  try {
+    std::vector<int> db(db_, db_ + nb), ir2c(f_ir2c, f_ir2c + nb);
+    OperatorPlan op = make_operator_plan(db, ir2c, use_diag != 0, beta_minus != 0);
+    size_t wsize = 0;
+    for (int d : db) wsize += (size_t)d * d;
+    unsigned long long seed = 88172645463325252ull;
+    auto rnd = [&]() { seed ^= seed << 13; seed ^= seed >> 7; seed ^= seed << 17; return (double)(seed >> 11) / 9007199254740992.0 - 0.5; };
+    std::vector<double> W[4];
+    for (auto& w : W) { w.resize(wsize); for (double& v : w) v = rnd(); }
+    const size_t nxy = op.nxy;
+    std::vector<double> in((size_t)2 * 4 * nxy);
+    for (double& v : in) v = rnd();
+    int rc = 0;
+    for (int dir = 0; dir < 2; dir++) {
+      const TransformPlan& tp = dir == 0 ? op.forward : op.backward;
+      std::vector<FusedJob> jobs;
+      std::vector<int4> ctas[3];
+      if (!build_fused_host(tp, jobs, ctas)) { rc = 2; out[4 * dir] = (double)tp.tasks.size(); out[4 * dir + 1] = 0; continue; }
+      auto elemA = [&](int mat, int off, int tr, int m, int i, int k) { return tr ? W[mat][off + k + (size_t)i * m] : W[mat][off + i + (size_t)k * m]; };
+      auto elemB = [&](int c, int quad, int off, int tr, int m, int n, int k, int j) {
+        const double* B = in.data() + ((size_t)c * 4 + quad) * nxy + off;
+        return tr ? B[j + (size_t)k * n] : B[k + (size_t)j * m];
+      };
+      auto elemC = [&](int mat, int off, int tr, int n, int k, int j) { return tr ? W[mat][off + j + (size_t)k * n] : W[mat][off + k + (size_t)j * n]; };
+      std::vector<double> ref((size_t)2 * 4 * nxy, 0.0), got((size_t)2 * 4 * nxy, 0.0);
+      double p_old = 0, p_new = 0;
+      for (const BlockTask& b : tp.tasks) {
+        const int m = b.m, n = b.n;
+        p_old += (double)b.nterms * ((double)m * m * n + (double)m * n * n);
+        for (int c = 0; c < 2; c++)
+          for (int t = 0; t < b.nterms; t++) {
+            const TripleTerm& x = b.t[t];
+            std::vector<double> T((size_t)m * n, 0.0);
+            for (int i = 0; i < m; i++)
+              for (int j = 0; j < n; j++) {
+                double sacc = 0;
+                for (int k = 0; k < m; k++) sacc += elemA(x.a_mat, x.a_off, x.a_trans, m, i, k) * elemB(c, x.b_quad, x.b_off, x.b_trans, m, n, k, j);
+                T[i + (size_t)j * m] = sacc;
+              }
+            const double al = c ? x.alpha_im : x.alpha_re;
+            for (int i = 0; i < m; i++)
+              for (int j = 0; j < n; j++) {
+                double sacc = 0;
+                for (int k = 0; k < n; k++) sacc += T[i + (size_t)k * m] * elemC(x.c_mat, x.c_off, x.c_trans, n, k, j);
+                ref[((size_t)c * 4 + b.out_quad) * nxy + b.out_off + i + (size_t)j * m] += al * sacc;
+              }
+          }
+      }
+      for (const FusedJob& J : jobs) {
+        const int m = J.m, n = J.n;
+        for (int x = 0; x < J.ngroups; x++) p_new += (double)J.nterms[x] * m * m * n + (double)J.nout * m * n * n;
+        for (int c = 0; c < 2; c++)
+          for (int x = 0; x < J.ngroups; x++) {
+            std::vector<double> T((size_t)m * n, 0.0);
+            for (int t = 0; t < J.nterms[x]; t++) {
+              const FusedTerm& f = J.t[x][t];
+              const double al = c ? f.alpha_im : f.alpha_re;
+              for (int i = 0; i < m; i++)
+                for (int j = 0; j < n; j++) {
+                  double sacc = 0;
+                  for (int k = 0; k < m; k++) sacc += elemA(f.a_mat, f.a_off, f.a_trans, m, i, k) * elemB(c, f.b_quad, f.b_off, f.b_trans, m, n, k, j);
+                  T[i + (size_t)j * m] += al * sacc;
+                }
+            }
+            for (int o = 0; o < J.nout; o++) {
+              const FusedOut& fo = J.o[o];
+              const double be = c ? fo.beta_im[x] : fo.beta_re[x];
+              for (int i = 0; i < m; i++)
+                for (int j = 0; j < n; j++) {
+                  double sacc = 0;
+                  for (int k = 0; k < n; k++) sacc += T[i + (size_t)k * m] * elemC(fo.c_mat[x], fo.c_off[x], fo.c_trans[x], n, k, j);
+                  got[((size_t)c * 4 + fo.out_quad) * nxy + fo.out_off + i + (size_t)j * m] += be * sacc;
+                }
+            }
+          }
+      }
+      double worst = 0;
+      for (size_t i = 0; i < ref.size(); i++) worst = std::max(worst, std::fabs(ref[i] - got[i]));
+      out[4 * dir] = (double)tp.tasks.size(); out[4 * dir + 1] = (double)jobs.size(); out[4 * dir + 2] = p_new / p_old; out[4 * dir + 3] = worst;
+    }
+    return rc;
+  } catch (const std::exception& e) {
+    set_err(err, errlen, e.what());
+    return 1;
+  }
 }
 
 extern "C" int pnfam_b200_dmma_peak(int device, double* tflops, char* err, int errlen) {

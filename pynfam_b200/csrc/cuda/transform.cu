@@ -169,8 +169,289 @@ __global__ void __launch_bounds__(256, 3) transform_phase2_kernel(const DevTask*
   store_tile(O, out, M, N, tm0 + m0, tn0 + n0);
 }
 
-void launch_transform(const DevicePlan& plan, const TransformArgs& args, int nactive, cudaStream_t stream) {
-  if (nactive <= 0) return;
+
+// ================================================================================================
+// Fused transform: both products of a triple product in one kernel, the intermediate never leaves the registers.
+//
+// One CTA (256 threads) = (job, strip of <= 4 DMMA m-tiles = 32 rows of the output block(s), omega point).  Warp w works on
+// m-tile (w & 3) of the strip for the real (w < 4) or imaginary (w >= 4) flavour of the middle operand and keeps its
+// 8 x N slice of T_x = sum_t alpha_t op(A_t) op(B_t) in registers as DMMA accumulators.  The accumulator fragment of
+// mma.m8n8k4 (lane l: row l/4, columns 2(l%4), 2(l%4)+1) IS a valid A fragment of the same instruction for the k-steps
+// {0,2,4,6} and {1,3,5,7} of that 8-column tile -- the contraction index may be visited in any order as long as the B
+// operand follows -- so phase 2, out_o += beta T_x op(C_{o,x}), runs straight from those registers: no shared-memory or
+// global round trip of the intermediate, no shuffles.  op(C) is staged with its rows permuted accordingly.
+// op(B) (flavour dependent, k-chunks of 16 rows) and op(C) (shared by the flavours, chunks of 64 rows x 32 columns) stream
+// through a 3-stage cp.async ring, one __syncthreads per chunk; op(A) fragments are read straight from global memory
+// (each warp needs its own 8 rows once; the U, V blocks are L2 resident) one chunk ahead.  Several groups x are
+// accumulated through the output block itself (each thread re-reads only what it wrote).
+// ================================================================================================
+constexpr int TF_KC = 16;        // rows of a phase-1 chunk (per flavour)
+constexpr int TF_K2 = 64;        // contraction rows of a phase-2 chunk
+constexpr int TF_PW = 32;        // output columns of a phase-2 panel
+constexpr int TF_LD2 = 36;       // row stride of a phase-2 chunk
+constexpr int TF_STAGES = 3;
+template <int NT> struct TfShape {
+  static constexpr int LD = NT * 8 + 4;       // row stride of a phase-1 chunk (= 4 or 12 mod 16: conflict-free fragments)
+  static constexpr int CH = (2 * TF_KC * LD > TF_K2 * TF_LD2) ? 2 * TF_KC * LD : TF_K2 * TF_LD2;   // doubles per stage
+  static constexpr size_t SMEM = (size_t)TF_STAGES * CH * sizeof(double);
+};
+
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// DMMA blocks with compile-time tile counts (the tile count of a block is uniform over the CTA: one switch per chunk
+// instead of a predicate per DMMA)
+template <int NJ, int NT, int LD>
+__device__ __forceinline__ void tf_phase1_block(double (&T)[NT][2], const double (&a)[4], const double* __restrict__ bp) {
+#pragma unroll
+  for (int ks = 0; ks < 4; ks++)
+#pragma unroll
+    for (int j = 0; j < NJ; j++) dmma884(T[j][0], T[j][1], a[ks], bp[ks * 4 * LD + 8 * j]);
+}
+template <int NP>
+__device__ __forceinline__ void tf_phase2_block(double (&acc)[4][2], double t0, double t1, const double* __restrict__ cp) {
+#pragma unroll
+  for (int jp = 0; jp < NP; jp++) dmma884(acc[jp][0], acc[jp][1], t0, cp[8 * jp]);
+#pragma unroll
+  for (int jp = 0; jp < NP; jp++) dmma884(acc[jp][0], acc[jp][1], t1, cp[4 * TF_LD2 + 8 * jp]);
+}
+
+template <int NT>
+__global__ void __launch_bounds__(256, NT <= 16 ? 2 : 1) transform_fused_kernel(const FusedJob* __restrict__ jobs, const int4* __restrict__ ctas,
+                                                                                TransformArgs args) {
+  using SH = TfShape<NT>;
+  constexpr int LD = SH::LD, CH = SH::CH;
+  extern __shared__ __align__(16) double tr_smem[];
+  if (args.ctrl && (int)blockIdx.y >= args.ctrl->nactive) return;
+  const int4 e = ctas[blockIdx.x];                      // (job, first m-tile, m-tiles of the strip, -)
+  const FusedJob& J = jobs[e.x];
+  const int M = J.m, N = J.n, K = M;
+  const int za = blockIdx.y, pt = args.active[za];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, lr = lane >> 2, lc = lane & 3;
+  const int c = warp >> 2;                              // flavour of this warp
+  const bool active = (warp & 3) < e.z;
+  const int row = (e.y + (warp & 3)) * 8 + lr;
+  const bool row_ok = active && row < M;
+  const int nk1 = (K + TF_KC - 1) / TF_KC, nk2 = (N + TF_K2 - 1) / TF_K2, npan = (N + TF_PW - 1) / TF_PW;
+  const int n8 = (N + 7) >> 3, ncol = n8 << 3;
+  const int ngroups = J.ngroups, nout = J.nout;
+  const double* __restrict__ in_pt = args.in + (size_t)pt * args.in_pstride;
+  const size_t dflav = quad_offset(args.in_pack, 1, 0, args.nxy) - quad_offset(args.in_pack, 0, 0, args.nxy);   // re -> im
+
+  // ---- staging (all threads).  The issue cursor runs TF_STAGES-1 chunks ahead of the math; its position inside the
+  //      job is (group, phase, term | output, panel, chunk) and the per-thread source pointer of the current operand
+  //      is kept in registers, advanced by a constant per chunk.
+  int sx = 0, sph = 0, st = 0, so = 0, sp = 0, sk = 0;   // group, phase (0/1), term, output, panel, chunk
+  const double* sptr = nullptr;                          // this thread's first source element of chunk sk
+  int strans = 0;
+  auto begin_operand = [&]() {
+    if (sx >= ngroups) return;
+    if (sph == 0) {
+      const FusedTerm& tm = J.t[sx][st];
+      strans = tm.b_trans;
+      const double* B0 = in_pt + quad_offset(args.in_pack, 0, tm.b_quad, args.nxy) + tm.b_off;
+      sptr = strans ? B0 + (tid & 31) + (size_t)(tid >> 5) * N : B0 + (tid & 15) + (size_t)(tid >> 4) * K;
+    } else {
+      const FusedOut& fo = J.o[so];
+      strans = fo.c_trans[sx];
+      const int cm = fo.c_mat[sx];
+      const double* Cm = (cm == 0 ? args.W[0] : cm == 1 ? args.W[1] : cm == 2 ? args.W[2] : args.W[3]) + fo.c_off[sx];
+      const int col0 = sp * TF_PW;
+      sptr = strans ? Cm + col0 + (tid & 31) + (size_t)(tid >> 5) * N : Cm + (tid & 63) + (size_t)(col0 + (tid >> 6)) * N;
+    }
+  };
+  auto stage = [&](double* __restrict__ buf) {
+    if (sph == 0) {                                     // phase 1: rows k0 .. k0+15 of op(B_t), both flavours
+      const int k0 = sk * TF_KC;
+      if (!strans) {                                    // op(B)[k][j] = B[k + j K]: k runs fastest in memory
+        const int kr = tid & 15;
+        double* d = buf + kr * LD + (tid >> 4);
+        int j = tid >> 4;
+        if (k0 + kr < K) {
+          const double* s0 = sptr;
+          for (; j < N; j += 16, d += 16, s0 += 16 * (size_t)K) { cp_async8(d, s0); cp_async8(d + TF_KC * LD, s0 + dflav); }
+        }
+        for (; j < ncol; j += 16, d += 16) { d[0] = 0.0; d[TF_KC * LD] = 0.0; }
+        sptr += TF_KC;
+      } else {                                          // op(B)[k][j] = B[j + k N]: j runs fastest
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const int kr = (tid >> 5) + 8 * h;
+          double* d = buf + kr * LD + (tid & 31);
+          int j = tid & 31;
+          if (k0 + kr < K) {
+            const double* s0 = sptr + (size_t)(8 * h) * N;
+            for (; j < N; j += 32, d += 32, s0 += 32) { cp_async8(d, s0); cp_async8(d + TF_KC * LD, s0 + dflav); }
+          }
+          for (; j < ncol; j += 32, d += 32) { d[0] = 0.0; d[TF_KC * LD] = 0.0; }
+        }
+        sptr += (size_t)TF_KC * N;
+      }
+    } else {                                            // phase 2: 64 rows x 32 columns of op(C_{o,x}), rows permuted
+      const int k0 = sk * TF_K2, col0 = sp * TF_PW;
+      if (!strans) {                                    // op(C)[k][j] = C[k + j N]
+        const int kr = tid & 63, rp = (kr & ~7) | ((kr & 1) << 2) | ((kr & 7) >> 1);
+        double* d = buf + rp * TF_LD2 + (tid >> 6);
+        const double* s0 = sptr;
+        const bool kin = k0 + kr < N;
+#pragma unroll
+        for (int u = 0; u < 8; u++, d += 4, s0 += 4 * (size_t)N) {
+          if (kin && col0 + (tid >> 6) + 4 * u < N) cp_async8(d, s0);
+          else d[0] = 0.0;
+        }
+        sptr += TF_K2;
+      } else {                                          // op(C)[k][j] = C[j + k N]
+        const bool jin = col0 + (tid & 31) < N;
+        const double* s0 = sptr;
+#pragma unroll
+        for (int u = 0; u < 8; u++, s0 += 8 * (size_t)N) {
+          const int kr = (tid >> 5) + 8 * u, rp = (kr & ~7) | ((kr & 1) << 2) | ((kr & 7) >> 1);
+          double* d = buf + rp * TF_LD2 + (tid & 31);
+          if (jin && k0 + kr < N) cp_async8(d, s0);
+          else d[0] = 0.0;
+        }
+        sptr += (size_t)TF_K2 * N;
+      }
+    }
+    // advance the cursor
+    sk++;
+    if (sph == 0) {
+      if (sk == nk1) { sk = 0; if (++st == J.nterms[sx]) { st = 0; sph = 1; so = 0; sp = 0; } begin_operand(); }
+    } else if (sk == nk2) {
+      sk = 0;
+      if (++sp == npan) { sp = 0; if (++so == nout) { so = 0; sph = 0; sx++; } }
+      begin_operand();
+    }
+  };
+  begin_operand();
+  int issued = 0, consumed = 0;
+  auto issue = [&]() {
+    if (sx < ngroups) stage(tr_smem + (size_t)issued * CH);
+    cp_async_commit();
+    if (++issued == TF_STAGES) issued = 0;
+  };
+  // chunk `consumed` has landed for every thread and the buffer of the chunk before it is free again
+  auto acquire = [&]() -> const double* {
+    cp_async_wait_group<TF_STAGES - 2>();
+    __syncthreads();
+    issue();
+    const double* b = tr_smem + (size_t)consumed * CH;
+    if (++consumed == TF_STAGES) consumed = 0;
+    return b;
+  };
+#pragma unroll
+  for (int s = 0; s < TF_STAGES - 1; s++) issue();
+
+  // ---- A fragments of one chunk, scaled by alpha: op(A)[row][k0 + 4 ks + lc] ----------------------------------
+  const double* ap = nullptr;       // this lane's element of chunk 0
+  size_t astep = 0;                 // distance of two k
+  double alpha = 0.0;
+  auto begin_a = [&](const FusedTerm& tm) {
+    const int am = tm.a_mat;
+    const double* Am = (am == 0 ? args.W[0] : am == 1 ? args.W[1] : am == 2 ? args.W[2] : args.W[3]) + tm.a_off;
+    alpha = c ? tm.alpha_im : tm.alpha_re;
+    astep = tm.a_trans ? 1 : (size_t)M;
+    ap = tm.a_trans ? Am + lc + (size_t)row * M : Am + row + (size_t)lc * M;
+  };
+  auto load_a = [&](int k0, double (&a)[4]) {
+#pragma unroll
+    for (int ks = 0; ks < 4; ks++) {
+      const int k = k0 + ks * 4;
+      a[ks] = (row_ok && k + lc < K) ? alpha * __ldg(ap + (size_t)k * astep) : 0.0;
+    }
+  };
+
+  for (int x = 0; x < ngroups; x++) {
+    // ---- phase 1 ----------------------------------------------------------------------------------
+    double T[NT][2];
+#pragma unroll
+    for (int j = 0; j < NT; j++) T[j][0] = T[j][1] = 0.0;
+    const int nt = J.nterms[x];
+    double a_cur[4], a_nxt[4] = {0.0, 0.0, 0.0, 0.0};
+    begin_a(J.t[x][0]);
+    load_a(0, a_cur);
+    for (int t = 0; t < nt; t++) {
+      for (int kc = 0; kc < nk1; kc++) {
+        const double* __restrict__ bp = acquire() + (size_t)c * TF_KC * LD + lc * LD + lr;
+        if (kc + 1 < nk1) load_a((kc + 1) * TF_KC, a_nxt);
+        else if (t + 1 < nt) { begin_a(J.t[x][t + 1]); load_a(0, a_nxt); }
+        if (active) {
+          switch (n8) {
+#define TF_CASE(n) case n: if (n <= NT) tf_phase1_block<(n <= NT ? n : 1), NT, LD>(T, a_cur, bp); break;
+            TF_CASE(1) TF_CASE(2) TF_CASE(3) TF_CASE(4) TF_CASE(5) TF_CASE(6) TF_CASE(7) TF_CASE(8) TF_CASE(9) TF_CASE(10) TF_CASE(11)
+            TF_CASE(12) TF_CASE(13) TF_CASE(14) TF_CASE(15) TF_CASE(16) TF_CASE(17) TF_CASE(18) TF_CASE(19) TF_CASE(20) TF_CASE(21) TF_CASE(22)
+#undef TF_CASE
+            default: break;
+          }
+        }
+#pragma unroll
+        for (int ks = 0; ks < 4; ks++) a_cur[ks] = a_nxt[ks];
+      }
+    }
+    // ---- phase 2 ----------------------------------------------------------------------------------
+    for (int o = 0; o < nout; o++) {
+      const FusedOut& fo = J.o[o];
+      const double beta = c ? fo.beta_im[x] : fo.beta_re[x];
+      double* __restrict__ O = args.out + (size_t)pt * args.out_pstride + quad_offset(args.out_pack, c, fo.out_quad, args.nxy) + fo.out_off;
+      for (int p = 0; p < npan; p++) {
+        const int col0 = p * TF_PW;
+        const int np8 = min(4, n8 - 4 * p);              // n-tiles of this panel
+        double acc[4][2];
+#pragma unroll
+        for (int jp = 0; jp < 4; jp++) acc[jp][0] = acc[jp][1] = 0.0;
+        const double* __restrict__ cp = nullptr;
+#pragma unroll
+        for (int kt = 0; kt < NT; kt++) {
+          if (kt < n8) {                                // uniform over the CTA
+            if ((kt & 7) == 0) cp = acquire() + lc * TF_LD2 + lr;
+            if (active) {
+              const double* __restrict__ q = cp + (kt & 7) * 8 * TF_LD2;
+              if (np8 == 4) tf_phase2_block<4>(acc, T[kt][0], T[kt][1], q);
+              else if (np8 == 3) tf_phase2_block<3>(acc, T[kt][0], T[kt][1], q);
+              else if (np8 == 2) tf_phase2_block<2>(acc, T[kt][0], T[kt][1], q);
+              else tf_phase2_block<1>(acc, T[kt][0], T[kt][1], q);
+            }
+          }
+        }
+        if (row_ok) {
+          double* __restrict__ dst = O + row + (size_t)(col0 + 2 * lc) * M;
+#pragma unroll
+          for (int jp = 0; jp < 4; jp++)
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+              const int col = col0 + 8 * jp + 2 * lc + q;
+              if (col < N) {
+                double* __restrict__ d2 = dst + (size_t)(8 * jp + q) * M;
+                double v = beta * acc[jp][q];
+                if (x > 0) v += *d2;
+                *d2 = v;
+              }
+            }
+        }
+      }
+    }
+  }
+  cp_async_wait_all();
+}
+
+template <int NT>
+static void launch_fused(const DevicePlan& plan, int cls, const TransformArgs& args, int nactive, cudaStream_t stream) {
+  static PerDeviceMax attr;
+  const size_t smem = TfShape<NT>::SMEM;
+  if (attr.raise(smem))
+    PNFAM_CUDA_CHECK(cudaFuncSetAttribute(transform_fused_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  transform_fused_kernel<NT><<<dim3(plan.nfctas[cls], nactive), 256, smem, stream>>>(plan.jobs, plan.fctas[cls], args);
+}
+
+int launch_transform(const DevicePlan& plan, const TransformArgs& args, int nactive, cudaStream_t stream) {
+  if (nactive <= 0) return 0;
+  if (plan.fused) {
+    int n = 0;
+    if (plan.nfctas[2] > 0) { launch_fused<22>(plan, 2, args, nactive, stream); n++; }
+    if (plan.nfctas[1] > 0) { launch_fused<16>(plan, 1, args, nactive, stream); n++; }
+    if (plan.nfctas[0] > 0) { launch_fused<11>(plan, 0, args, nactive, stream); n++; }
+    return n;
+  }
   const int kpad = (plan.max_dim + 3) & ~3;
   const size_t smem = (size_t)3 * kpad * TR_LD * sizeof(double);
   static PerDeviceMax attr;
@@ -181,6 +462,7 @@ void launch_transform(const DevicePlan& plan, const TransformArgs& args, int nac
   dim3 g1(plan.ntiles1, nactive), g2(plan.ntiles2, nactive);
   if (plan.ntiles1 > 0) transform_phase1_kernel<<<g1, 256, smem, stream>>>(plan.tasks, plan.tiles1, args, kpad);
   if (plan.ntiles2 > 0) transform_phase2_kernel<<<g2, 256, smem, stream>>>(plan.tasks, plan.tiles2, args, kpad);
+  return (plan.ntiles1 > 0) + (plan.ntiles2 > 0);
 }
 
 }  // namespace pnfam

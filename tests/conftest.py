@@ -49,3 +49,14 @@ def stage_point(case, op, idx, wd, name="x.in", patch=None):
 
 def gold_rows(pt):
     return {k: complex(float(v[0]), float(v[1])) for k, v in pt["rows"].items()}
+
+
+def terminal_scatter(pt, back=3):
+    """Largest relative change of S between consecutive iterations over the reference's last `back` steps (its own trace
+    prints 10 digits).  Ill-conditioned points (>= 25 Broyden steps) stall near the stopping threshold: round-off differences
+    between two correct implementations are amplified by ~1e7, the rule max|dX| < eps may then trigger a step or two
+    apart, and S is only defined up to this movement."""
+    tr = {t[0]: complex(t[3], t[4]) for t in pt["trace"]}
+    last = max(tr)
+    s = abs(tr[last])
+    return max(abs(tr[k] - tr[k - 1]) / s for k in range(max(2, last - back + 1), last + 1) if k - 1 in tr)

@@ -5,7 +5,7 @@ as stated by BASELINE.json's north_star (observed agreement is ~1e-14)."""
 import numpy as np
 import pytest
 
-from conftest import gold_rows, load_points, stage_point
+from conftest import gold_rows, load_points, stage_point, terminal_scatter
 from oracle import fam_oracle as fo
 from pynfam_b200 import host
 
@@ -408,6 +408,13 @@ def test_contour_driver_with_two_body_currents(gpu, tmp_path):
             gold = gold_rows(pt)
             assert abs(contour.ctr_z[i] - gold["Energy"]) < 1e-12
             loose = abs(contour.ctr_z[i].imag) < 0.5 or pt["iters"] >= 25
+            it_gpu, it_ref = int(fs.iters[i]), pt["iters"]
+            if loose and 1 <= abs(it_gpu - it_ref) <= 2:
+                # the stopping rule triggered a step or two apart on an ill-conditioned point: the result must lie within
+                # the reference's own terminal movement of S (conftest.terminal_scatter)
+                assert _rel(got[i], gold["Strength"]) < LOOSE_TOL + 1.5 * terminal_scatter(pt), (fs.opname, i, it_gpu, it_ref)
+                continue
+            assert it_gpu == it_ref or loose, (fs.opname, i, it_gpu, it_ref)
             assert _rel(got[i], gold["Strength"]) < (LOOSE_TOL if loose else TOL), (fs.opname, i)
 
 

@@ -101,6 +101,30 @@ def test_finite_temperature_setup(tmp_path):
     assert abs((p.f64("rho_n") * w).sum() - 98) < 1e-9 and abs((p.f64("rho_p") * w).sum() - 64) < 1e-9
 
 
+@pytest.mark.parametrize("case,op,idx", [("S40_SKOP_6sh", "GT-K0", 10), ("S40_GT_All", "RS2-K2", 7), ("Gd162_GT_open_6sh", "GT-K1", 40),
+                                         ("Gd163_blocked_6sh", "GT-K1", 0), ("Gd162_finiteT_6sh", "RS1-K1", 0)])
+def test_fused_transform_jobs_equal_the_block_task_list(case, op, idx, tmp_path):
+    """The fused transform kernel works on jobs regrouped by associativity (products shared by two output blocks are
+    formed once).  Host-only self-check of the C ABI library: both forms evaluated on the CPU with random operands
+    give the same block matrices, and the regrouping needs fewer products than triprod_bbm's term list
+    (pnfam_type_bbm.f90:428-552): 8 -> 7 / 6 per block row (forward / backward), 16 -> 10 / 8 with the P,Q quadrants."""
+    from pynfam_b200 import gpu
+    stage_point(case, op, idx, str(tmp_path))
+    p = host.Problem(str(tmp_path), "x.in")
+    L = gpu.lib()
+    ip, dp = ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_double)
+    L.pnfam_b200_check_transform_plan.argtypes = [ctypes.c_int, ip, ip, ctypes.c_int, ctypes.c_int, dp, ctypes.c_char_p, ctypes.c_int]
+    db, r2c = np.ascontiguousarray(p.i32("db")), np.ascontiguousarray(p.i32("f_ir2c"))
+    out, err = (ctypes.c_double * 8)(), ctypes.create_string_buffer(512)
+    stat = int(p.iscalar("statistical"))
+    rc = L.pnfam_b200_check_transform_plan(len(db), db.ctypes.data_as(ip), r2c.ctypes.data_as(ip), stat, int(p.iscalar("beta_minus")), out, err, 512)
+    assert rc == 0, err.value
+    for d in (0, 1):
+        ntasks, njobs, ratio, diff = out[4 * d:4 * d + 4]
+        assert njobs <= ntasks and diff < 1e-13
+        assert ratio <= (0.63 if stat else 0.88)
+
+
 def test_couplings_match_reference_header(tmp_path):
     """The .dat header of the golden point prints the couplings to 9 decimals."""
     stage_point("S40_SKOP_6sh", "GT-K0", 10, str(tmp_path))
