@@ -200,20 +200,46 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 // DMMA blocks with compile-time tile counts (the tile count of a block is uniform over the CTA: one switch per chunk
-// instead of a predicate per DMMA)
+// instead of a predicate per DMMA); nks = k-steps of the chunk that hold data (the last chunk of a block may be short)
 template <int NJ, int NT, int LD>
-__device__ __forceinline__ void tf_phase1_block(double (&T)[NT][2], const double (&a)[4], const double* __restrict__ bp) {
+__device__ __forceinline__ void tf_phase1_block(double (&T)[NT][2], const double (&a)[4], const double* __restrict__ bp, int nks) {
 #pragma unroll
   for (int ks = 0; ks < 4; ks++)
+    if (ks < nks) {
 #pragma unroll
-    for (int j = 0; j < NJ; j++) dmma884(T[j][0], T[j][1], a[ks], bp[ks * 4 * LD + 8 * j]);
+      for (int j = 0; j < NJ; j++) dmma884(T[j][0], T[j][1], a[ks], bp[ks * 4 * LD + 8 * j]);
+    }
 }
+// Rows of a phase-2 chunk are permuted inside every group of 8 contraction indices so that BOTH access patterns hit 4
+// rows that differ modulo 4 (row stride 36 doubles: bank-conflict free): the DMMA fragments -- the accumulator-as-A trick
+// visits k = 2 lc + h, lc = 0..3 -- and the 4-consecutive-k staging patches.  k -> row: 0 2 1 3 6 4 7 5.
+__device__ __forceinline__ int tf_rowperm(int k) { return (0x57463120 >> (4 * k)) & 7; }
 template <int NP>
-__device__ __forceinline__ void tf_phase2_block(double (&acc)[4][2], double t0, double t1, const double* __restrict__ cp) {
+__device__ __forceinline__ void tf_phase2_tile(double (&acc)[4][2], double t0, double t1, const double* __restrict__ c0, const double* __restrict__ c1) {
 #pragma unroll
-  for (int jp = 0; jp < NP; jp++) dmma884(acc[jp][0], acc[jp][1], t0, cp[8 * jp]);
+  for (int jp = 0; jp < NP; jp++) dmma884(acc[jp][0], acc[jp][1], t0, c0[8 * jp]);
 #pragma unroll
-  for (int jp = 0; jp < NP; jp++) dmma884(acc[jp][0], acc[jp][1], t1, cp[4 * TF_LD2 + 8 * jp]);
+  for (int jp = 0; jp < NP; jp++) dmma884(acc[jp][0], acc[jp][1], t1, c1[8 * jp]);
+}
+// the T tiles [KT0, KT0 + 8) of one phase-2 chunk
+template <int KT0, int NT>
+__device__ __forceinline__ void tf_phase2_block(double (&acc)[4][2], const double (&T)[NT][2], int n8, int np8, const double* __restrict__ q0,
+                                                const double* __restrict__ q1) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    constexpr int dummy = 0;
+    (void)dummy;
+    if (KT0 + i < NT && KT0 + i < n8) {
+      constexpr int kt_max = NT - 1;
+      const int kt = KT0 + i < NT ? KT0 + i : kt_max;   // (static) keeps the index inside the array for the dead iterations
+      const double* __restrict__ c0 = q0 + i * 8 * TF_LD2;
+      const double* __restrict__ c1 = q1 + i * 8 * TF_LD2;
+      if (np8 == 4) tf_phase2_tile<4>(acc, T[kt][0], T[kt][1], c0, c1);
+      else if (np8 == 3) tf_phase2_tile<3>(acc, T[kt][0], T[kt][1], c0, c1);
+      else if (np8 == 2) tf_phase2_tile<2>(acc, T[kt][0], T[kt][1], c0, c1);
+      else tf_phase2_tile<1>(acc, T[kt][0], T[kt][1], c0, c1);
+    }
+  }
 }
 
 template <int NT>
@@ -222,13 +248,20 @@ __global__ void __launch_bounds__(256, NT <= 16 ? 2 : 1) transform_fused_kernel(
   using SH = TfShape<NT>;
   constexpr int LD = SH::LD, CH = SH::CH;
   extern __shared__ __align__(16) double tr_smem[];
+  __shared__ FusedJob J;                                // the job descriptor: read many times, from shared memory
   if (args.ctrl && (int)blockIdx.y >= args.ctrl->nactive) return;
   const int4 e = ctas[blockIdx.x];                      // (job, first m-tile, m-tiles of the strip, -)
-  const FusedJob& J = jobs[e.x];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, lr = lane >> 2, lc = lane & 3;
+  {
+    const int* src = reinterpret_cast<const int*>(jobs + e.x);
+    int* dst = reinterpret_cast<int*>(&J);
+    for (int i = tid; i < (int)(sizeof(FusedJob) / 4); i += 256) dst[i] = __ldg(src + i);
+  }
+  __syncthreads();
   const int M = J.m, N = J.n, K = M;
   const int za = blockIdx.y, pt = args.active[za];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, lr = lane >> 2, lc = lane & 3;
   const int c = warp >> 2;                              // flavour of this warp
+  const int row0 = tf_rowperm(2 * lc), row1 = tf_rowperm(2 * lc + 1);   // rows of this lane's phase-2 fragments
   const bool active = (warp & 3) < e.z;
   const int row = (e.y + (warp & 3)) * 8 + lr;
   const bool row_ok = active && row < M;
@@ -237,12 +270,24 @@ __global__ void __launch_bounds__(256, NT <= 16 ? 2 : 1) transform_fused_kernel(
   const int ngroups = J.ngroups, nout = J.nout;
   const double* __restrict__ in_pt = args.in + (size_t)pt * args.in_pstride;
   const size_t dflav = quad_offset(args.in_pack, 1, 0, args.nxy) - quad_offset(args.in_pack, 0, 0, args.nxy);   // re -> im
+  const double* __restrict__ W0 = args.W[0];
+  const double* __restrict__ W1 = args.W[1];
+  const double* __restrict__ W2 = args.W[2];
+  const double* __restrict__ W3 = args.W[3];
+  auto wmat = [&](int m) { return m == 0 ? W0 : (m == 1 ? W1 : (m == 2 ? W2 : W3)); };
 
   // ---- staging (all threads).  The issue cursor runs TF_STAGES-1 chunks ahead of the math; its position inside the
-  //      job is (group, phase, term | output, panel, chunk) and the per-thread source pointer of the current operand
-  //      is kept in registers, advanced by a constant per chunk.
+  //      job is (group, phase, term | output, panel, chunk); the source pointer of the current operand is advanced by
+  //      a constant per chunk.  Thread -> element maps (fixed for the whole kernel):
+  //        k fastest in memory: a warp copies 4 (k) x 8 (j) patches -- full 32-byte sectors on the global side and the
+  //                             bank pattern of the DMMA fragment loads on the shared side (conflict free)
+  //        j fastest in memory: a warp copies 32 consecutive j of one row
+  const int kq = lane & 3, jq = lane >> 2;
+  const int p1_kl = 4 * (warp & 3) + kq, p1_j0 = 8 * (warp >> 2) + jq;           // phase 1, k fastest
+  const int p2_kra = 4 * warp + kq, p2_krb = p2_kra + 32;                          // phase 2, k fastest
+  const int p2_da = ((p2_kra & ~7) + tf_rowperm(p2_kra & 7)) * TF_LD2 + jq, p2_db = ((p2_krb & ~7) + tf_rowperm(p2_krb & 7)) * TF_LD2 + jq;
   int sx = 0, sph = 0, st = 0, so = 0, sp = 0, sk = 0;   // group, phase (0/1), term, output, panel, chunk
-  const double* sptr = nullptr;                          // this thread's first source element of chunk sk
+  const double* sptr = nullptr;
   int strans = 0;
   auto begin_operand = [&]() {
     if (sx >= ngroups) return;
@@ -250,35 +295,33 @@ __global__ void __launch_bounds__(256, NT <= 16 ? 2 : 1) transform_fused_kernel(
       const FusedTerm& tm = J.t[sx][st];
       strans = tm.b_trans;
       const double* B0 = in_pt + quad_offset(args.in_pack, 0, tm.b_quad, args.nxy) + tm.b_off;
-      sptr = strans ? B0 + (tid & 31) + (size_t)(tid >> 5) * N : B0 + (tid & 15) + (size_t)(tid >> 4) * K;
+      sptr = strans ? B0 + lane + (size_t)warp * N : B0 + p1_kl + (size_t)p1_j0 * K;
     } else {
       const FusedOut& fo = J.o[so];
       strans = fo.c_trans[sx];
-      const int cm = fo.c_mat[sx];
-      const double* Cm = (cm == 0 ? args.W[0] : cm == 1 ? args.W[1] : cm == 2 ? args.W[2] : args.W[3]) + fo.c_off[sx];
+      const double* Cm = wmat(fo.c_mat[sx]) + fo.c_off[sx];
       const int col0 = sp * TF_PW;
-      sptr = strans ? Cm + col0 + (tid & 31) + (size_t)(tid >> 5) * N : Cm + (tid & 63) + (size_t)(col0 + (tid >> 6)) * N;
+      sptr = strans ? Cm + col0 + lane + (size_t)warp * N : Cm + (size_t)(col0 + jq) * N;
     }
   };
   auto stage = [&](double* __restrict__ buf) {
     if (sph == 0) {                                     // phase 1: rows k0 .. k0+15 of op(B_t), both flavours
       const int k0 = sk * TF_KC;
-      if (!strans) {                                    // op(B)[k][j] = B[k + j K]: k runs fastest in memory
-        const int kr = tid & 15;
-        double* d = buf + kr * LD + (tid >> 4);
-        int j = tid >> 4;
-        if (k0 + kr < K) {
+      if (!strans) {                                    // op(B)[k][j] = B[k + j K]
+        double* d = buf + p1_kl * LD + p1_j0;
+        int j = p1_j0;
+        if (k0 + p1_kl < K) {
           const double* s0 = sptr;
           for (; j < N; j += 16, d += 16, s0 += 16 * (size_t)K) { cp_async8(d, s0); cp_async8(d + TF_KC * LD, s0 + dflav); }
         }
         for (; j < ncol; j += 16, d += 16) { d[0] = 0.0; d[TF_KC * LD] = 0.0; }
         sptr += TF_KC;
-      } else {                                          // op(B)[k][j] = B[j + k N]: j runs fastest
+      } else {                                          // op(B)[k][j] = B[j + k N]
 #pragma unroll
         for (int h = 0; h < 2; h++) {
-          const int kr = (tid >> 5) + 8 * h;
-          double* d = buf + kr * LD + (tid & 31);
-          int j = tid & 31;
+          const int kr = warp + 8 * h;
+          double* d = buf + kr * LD + lane;
+          int j = lane;
           if (k0 + kr < K) {
             const double* s0 = sptr + (size_t)(8 * h) * N;
             for (; j < N; j += 32, d += 32, s0 += 32) { cp_async8(d, s0); cp_async8(d + TF_KC * LD, s0 + dflav); }
@@ -290,23 +333,22 @@ __global__ void __launch_bounds__(256, NT <= 16 ? 2 : 1) transform_fused_kernel(
     } else {                                            // phase 2: 64 rows x 32 columns of op(C_{o,x}), rows permuted
       const int k0 = sk * TF_K2, col0 = sp * TF_PW;
       if (!strans) {                                    // op(C)[k][j] = C[k + j N]
-        const int kr = tid & 63, rp = (kr & ~7) | ((kr & 1) << 2) | ((kr & 7) >> 1);
-        double* d = buf + rp * TF_LD2 + (tid >> 6);
+        const bool ka = k0 + p2_kra < N, kb = k0 + p2_krb < N;
         const double* s0 = sptr;
-        const bool kin = k0 + kr < N;
 #pragma unroll
-        for (int u = 0; u < 8; u++, d += 4, s0 += 4 * (size_t)N) {
-          if (kin && col0 + (tid >> 6) + 4 * u < N) cp_async8(d, s0);
-          else d[0] = 0.0;
+        for (int u = 0; u < 4; u++, s0 += 8 * (size_t)N) {
+          const bool jin = col0 + 8 * u + jq < N;
+          if (ka && jin) cp_async8(buf + p2_da + 8 * u, s0 + p2_kra); else buf[p2_da + 8 * u] = 0.0;
+          if (kb && jin) cp_async8(buf + p2_db + 8 * u, s0 + p2_krb); else buf[p2_db + 8 * u] = 0.0;
         }
         sptr += TF_K2;
       } else {                                          // op(C)[k][j] = C[j + k N]
-        const bool jin = col0 + (tid & 31) < N;
+        const bool jin = col0 + lane < N;
         const double* s0 = sptr;
 #pragma unroll
         for (int u = 0; u < 8; u++, s0 += 8 * (size_t)N) {
-          const int kr = (tid >> 5) + 8 * u, rp = (kr & ~7) | ((kr & 1) << 2) | ((kr & 7) >> 1);
-          double* d = buf + rp * TF_LD2 + (tid & 31);
+          const int kr = warp + 8 * u;                  // rows 8u + warp: the permutation depends on the warp only
+          double* d = buf + (8 * u + tf_rowperm(warp)) * TF_LD2 + lane;
           if (jin && k0 + kr < N) cp_async8(d, s0);
           else d[0] = 0.0;
         }
@@ -324,32 +366,12 @@ __global__ void __launch_bounds__(256, NT <= 16 ? 2 : 1) transform_fused_kernel(
     }
   };
   begin_operand();
-  int issued = 0, consumed = 0;
-  auto issue = [&]() {
-    if (sx < ngroups) stage(tr_smem + (size_t)issued * CH);
-    cp_async_commit();
-    if (++issued == TF_STAGES) issued = 0;
-  };
-  // chunk `consumed` has landed for every thread and the buffer of the chunk before it is free again
-  auto acquire = [&]() -> const double* {
-    cp_async_wait_group<TF_STAGES - 2>();
-    __syncthreads();
-    issue();
-    const double* b = tr_smem + (size_t)consumed * CH;
-    if (++consumed == TF_STAGES) consumed = 0;
-    return b;
-  };
-#pragma unroll
-  for (int s = 0; s < TF_STAGES - 1; s++) issue();
 
-  // ---- A fragments of one chunk, scaled by alpha: op(A)[row][k0 + 4 ks + lc] ----------------------------------
+  // ---- A fragments of one chunk: op(A)[row][k0 + 4 ks + lc], fetched one chunk ahead, scaled by alpha at hand-over ----
   const double* ap = nullptr;       // this lane's element of chunk 0
   size_t astep = 0;                 // distance of two k
-  double alpha = 0.0;
   auto begin_a = [&](const FusedTerm& tm) {
-    const int am = tm.a_mat;
-    const double* Am = (am == 0 ? args.W[0] : am == 1 ? args.W[1] : am == 2 ? args.W[2] : args.W[3]) + tm.a_off;
-    alpha = c ? tm.alpha_im : tm.alpha_re;
+    const double* Am = wmat(tm.a_mat) + tm.a_off;
     astep = tm.a_trans ? 1 : (size_t)M;
     ap = tm.a_trans ? Am + lc + (size_t)row * M : Am + row + (size_t)lc * M;
   };
@@ -357,76 +379,109 @@ __global__ void __launch_bounds__(256, NT <= 16 ? 2 : 1) transform_fused_kernel(
 #pragma unroll
     for (int ks = 0; ks < 4; ks++) {
       const int k = k0 + ks * 4;
-      a[ks] = (row_ok && k + lc < K) ? alpha * __ldg(ap + (size_t)k * astep) : 0.0;
+      a[ks] = (row_ok && k + lc < K) ? __ldg(ap + (size_t)k * astep) : 0.0;
     }
   };
 
-  for (int x = 0; x < ngroups; x++) {
-    // ---- phase 1 ----------------------------------------------------------------------------------
-    double T[NT][2];
+  // ---- the math walks the same chunk sequence (one call site of the staging code) --------------------------
+  int total = 0;
+  for (int x = 0; x < ngroups; x++) total += J.nterms[x] * nk1 + nout * npan * nk2;
+  int cx = 0, cph = 0, ct = 0, co = 0, cp_ = 0, ck = 0;  // math cursor: group, phase, term, output, panel, chunk
+  double T[NT][2], acc[4][2], a_cur[4], a_nxt[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-    for (int j = 0; j < NT; j++) T[j][0] = T[j][1] = 0.0;
-    const int nt = J.nterms[x];
-    double a_cur[4], a_nxt[4] = {0.0, 0.0, 0.0, 0.0};
-    begin_a(J.t[x][0]);
+  for (int j = 0; j < NT; j++) T[j][0] = T[j][1] = 0.0;
+#pragma unroll
+  for (int jp = 0; jp < 4; jp++) acc[jp][0] = acc[jp][1] = 0.0;
+  double alpha_nxt;
+  {
+    const FusedTerm& tm = J.t[0][0];
+    begin_a(tm);
     load_a(0, a_cur);
-    for (int t = 0; t < nt; t++) {
-      for (int kc = 0; kc < nk1; kc++) {
-        const double* __restrict__ bp = acquire() + (size_t)c * TF_KC * LD + lc * LD + lr;
-        if (kc + 1 < nk1) load_a((kc + 1) * TF_KC, a_nxt);
-        else if (t + 1 < nt) { begin_a(J.t[x][t + 1]); load_a(0, a_nxt); }
-        if (active) {
-          switch (n8) {
-#define TF_CASE(n) case n: if (n <= NT) tf_phase1_block<(n <= NT ? n : 1), NT, LD>(T, a_cur, bp); break;
-            TF_CASE(1) TF_CASE(2) TF_CASE(3) TF_CASE(4) TF_CASE(5) TF_CASE(6) TF_CASE(7) TF_CASE(8) TF_CASE(9) TF_CASE(10) TF_CASE(11)
-            TF_CASE(12) TF_CASE(13) TF_CASE(14) TF_CASE(15) TF_CASE(16) TF_CASE(17) TF_CASE(18) TF_CASE(19) TF_CASE(20) TF_CASE(21) TF_CASE(22)
-#undef TF_CASE
-            default: break;
-          }
-        }
+    const double al = c ? tm.alpha_im : tm.alpha_re;
 #pragma unroll
-        for (int ks = 0; ks < 4; ks++) a_cur[ks] = a_nxt[ks];
-      }
+    for (int ks = 0; ks < 4; ks++) a_cur[ks] *= al;
+    alpha_nxt = al;
+  }
+  int ibuf = 0, cbuf = 0;
+  for (int ch = -(TF_STAGES - 1); ch < total; ch++) {
+    if (ch >= 0) {
+      cp_async_wait_group<TF_STAGES - 2>();             // chunk `ch` has landed for this thread ...
+      __syncthreads();                                  // ... and for all; the buffer of chunk ch-1 is free again
     }
-    // ---- phase 2 ----------------------------------------------------------------------------------
-    for (int o = 0; o < nout; o++) {
-      const FusedOut& fo = J.o[o];
-      const double beta = c ? fo.beta_im[x] : fo.beta_re[x];
-      double* __restrict__ O = args.out + (size_t)pt * args.out_pstride + quad_offset(args.out_pack, c, fo.out_quad, args.nxy) + fo.out_off;
-      for (int p = 0; p < npan; p++) {
-        const int col0 = p * TF_PW;
-        const int np8 = min(4, n8 - 4 * p);              // n-tiles of this panel
-        double acc[4][2];
-#pragma unroll
-        for (int jp = 0; jp < 4; jp++) acc[jp][0] = acc[jp][1] = 0.0;
-        const double* __restrict__ cp = nullptr;
-#pragma unroll
-        for (int kt = 0; kt < NT; kt++) {
-          if (kt < n8) {                                // uniform over the CTA
-            if ((kt & 7) == 0) cp = acquire() + lc * TF_LD2 + lr;
-            if (active) {
-              const double* __restrict__ q = cp + (kt & 7) * 8 * TF_LD2;
-              if (np8 == 4) tf_phase2_block<4>(acc, T[kt][0], T[kt][1], q);
-              else if (np8 == 3) tf_phase2_block<3>(acc, T[kt][0], T[kt][1], q);
-              else if (np8 == 2) tf_phase2_block<2>(acc, T[kt][0], T[kt][1], q);
-              else tf_phase2_block<1>(acc, T[kt][0], T[kt][1], q);
-            }
-          }
+    if (sx < ngroups) stage(tr_smem + (size_t)ibuf * CH);
+    cp_async_commit();
+    if (++ibuf == TF_STAGES) ibuf = 0;
+    if (ch < 0) continue;
+    const double* __restrict__ buf = tr_smem + (size_t)cbuf * CH;
+    if (++cbuf == TF_STAGES) cbuf = 0;
+    if (cph == 0) {
+      // ---- phase 1: T += alpha op(A_t)[rows][k0..] op(B_t)[k0..][:] ------------------------------------------
+      const bool more_k = ck + 1 < nk1, more_t = ct + 1 < J.nterms[cx];
+      if (more_k) load_a((ck + 1) * TF_KC, a_nxt);
+      else if (more_t) { const FusedTerm& tm = J.t[cx][ct + 1]; begin_a(tm); load_a(0, a_nxt); alpha_nxt = c ? tm.alpha_im : tm.alpha_re; }
+      if (active) {
+        const double* __restrict__ bp = buf + (size_t)c * TF_KC * LD + lc * LD + lr;
+        const int nks = min(4, (K - ck * TF_KC + 3) >> 2);
+        switch (n8) {
+#define TF_CASE(n) case n: if (n <= NT) tf_phase1_block<(n <= NT ? n : 1), NT, LD>(T, a_cur, bp, nks); break;
+          TF_CASE(1) TF_CASE(2) TF_CASE(3) TF_CASE(4) TF_CASE(5) TF_CASE(6) TF_CASE(7) TF_CASE(8) TF_CASE(9) TF_CASE(10) TF_CASE(11)
+          TF_CASE(12) TF_CASE(13) TF_CASE(14) TF_CASE(15) TF_CASE(16) TF_CASE(17) TF_CASE(18) TF_CASE(19) TF_CASE(20) TF_CASE(21) TF_CASE(22)
+#undef TF_CASE
+          default: break;
         }
+      }
+#pragma unroll
+      for (int ks = 0; ks < 4; ks++) a_cur[ks] = alpha_nxt * a_nxt[ks];
+      if (++ck == nk1) { ck = 0; if (++ct == J.nterms[cx]) { ct = 0; cph = 1; co = 0; cp_ = 0; } }
+    } else {
+      // ---- phase 2: acc += T[:, k0..] op(C_{o,x})[k0..][panel] ----------------------------------------------
+      const int np8 = min(4, n8 - 4 * cp_);             // n-tiles of this panel
+      if (active) {
+        const double* __restrict__ q0 = buf + row0 * TF_LD2 + lr;
+        const double* __restrict__ q1 = buf + row1 * TF_LD2 + lr;
+        if (ck == 0) tf_phase2_block<0, NT>(acc, T, n8, np8, q0, q1);
+        else if (ck == 1) tf_phase2_block<8, NT>(acc, T, n8, np8, q0, q1);
+        else tf_phase2_block<16, NT>(acc, T, n8, np8, q0, q1);
+      }
+      if (++ck == nk2) {
+        ck = 0;
+        // panel finished: out (+)= beta acc
+        const FusedOut& fo = J.o[co];
         if (row_ok) {
-          double* __restrict__ dst = O + row + (size_t)(col0 + 2 * lc) * M;
+          const double beta = c ? fo.beta_im[cx] : fo.beta_re[cx];
+          const int col0 = cp_ * TF_PW;
+          double* __restrict__ dst = args.out + (size_t)pt * args.out_pstride + quad_offset(args.out_pack, c, fo.out_quad, args.nxy) + fo.out_off +
+                                     row + (size_t)(col0 + 2 * lc) * M;
 #pragma unroll
           for (int jp = 0; jp < 4; jp++)
 #pragma unroll
             for (int q = 0; q < 2; q++) {
-              const int col = col0 + 8 * jp + 2 * lc + q;
-              if (col < N) {
+              if (col0 + 8 * jp + 2 * lc + q < N) {
                 double* __restrict__ d2 = dst + (size_t)(8 * jp + q) * M;
                 double v = beta * acc[jp][q];
-                if (x > 0) v += *d2;
+                if (cx > 0) v += *d2;
                 *d2 = v;
               }
             }
+        }
+#pragma unroll
+        for (int jp = 0; jp < 4; jp++) acc[jp][0] = acc[jp][1] = 0.0;
+        if (++cp_ == npan) {
+          cp_ = 0;
+          if (++co == nout) {                           // group finished: next group starts with a fresh T
+            co = 0; cph = 0; cx++;
+#pragma unroll
+            for (int j = 0; j < NT; j++) T[j][0] = T[j][1] = 0.0;
+            if (cx < ngroups) {
+              const FusedTerm& tm = J.t[cx][0];
+              begin_a(tm);
+              load_a(0, a_cur);
+              const double al = c ? tm.alpha_im : tm.alpha_re;
+#pragma unroll
+              for (int ks = 0; ks < 4; ks++) a_cur[ks] *= al;
+              alpha_nxt = al;
+            }
+          }
         }
       }
     }
