@@ -235,9 +235,15 @@ __global__ void __launch_bounds__(256, 3) sf2_kappa_kernel(HamArgs g) {
     mfs[i] = *reinterpret_cast<const double2*>(src + ((size_t)pr * kih + ih) * 2);
   }
   constexpr int NM = MODE == 0 ? 3 : 1;
+  // two copies of the z tables: [m][zr][ih] for the row index (nearly uniform over a warp) and [m][ih][zr'] for the column
+  // index (consecutive lanes = consecutive zr': conflict-free; the [zr][ih] order would put 32 lanes on two banks)
+  const int nzp = nzr | 1;
+  double* Zt = Zs + (size_t)NM * nzr * ngh;                            // [NM][ngh][nzp]
   for (int i = tid; i < NM * nzr * ngh; i += 256) {
     const int m = i / (nzr * ngh), r = i - m * nzr * ngh, zr = r / ngh, ih = r - zr * ngh;
-    Zs[i] = S.zt[((size_t)m * nzr + zr) * S.zs + ih];
+    const double v = S.zt[((size_t)m * nzr + zr) * S.zs + ih];
+    Zs[i] = v;
+    Zt[((size_t)m * ngh + ih) * nzp + zr] = v;
   }
   __syncthreads();
   const unsigned char* __restrict__ need = F.need[MODE][q] + (size_t)s4 * npair;
@@ -249,15 +255,15 @@ __global__ void __launch_bounds__(256, 3) sf2_kappa_kernel(HamArgs g) {
 #pragma unroll
     for (int i = 0; i < NJJ; i++) acc[i] = make_double2(0.0, 0.0);
     const double* __restrict__ za_ = Zs + (size_t)zr * ngh;
-    const double* __restrict__ zb_ = Zs + (size_t)z2 * ngh;
-    const size_t ms = (size_t)nzr * ngh;
+    const double* __restrict__ zb_ = Zt + z2;
+    const size_t ms = (size_t)nzr * ngh, mt = (size_t)ngh * nzp;
     for (int ih = 0; ih < ngh; ih++) {
-      const double a0 = za_[ih], b0 = zb_[ih];
+      const double a0 = za_[ih], b0 = zb_[(size_t)ih * nzp];
       const double p00 = a0 * b0;
       if (MODE == 1) {
         cfma(acc[0], p00, mfs[ih]);
       } else {
-        const double a1 = za_[ms + ih], a2 = za_[2 * ms + ih], b1 = zb_[ms + ih], b2 = zb_[2 * ms + ih];
+        const double a1 = za_[ms + ih], a2 = za_[2 * ms + ih], b1 = zb_[mt + (size_t)ih * nzp], b2 = zb_[2 * mt + (size_t)ih * nzp];
         const double p01 = a0 * b1, p10 = a1 * b0, p11 = a1 * b1, p02 = a0 * b2, p20 = a2 * b0;
         // (t, t') with t, t' in {phi, d/dr, Lambda/r}: Z0 Z0', radial pair (t, t')
 #pragma unroll
@@ -350,7 +356,7 @@ void launch_projection_sf2(const HamArgs& a, cudaStream_t stream) {
   const SfDev& S = a.sf;
   const Sf2Dev& F = a.sf2;
   const int nzr = F.nzr;
-  const size_t sm0 = (size_t)SF_MFP * S.ngh * 16 + (size_t)3 * nzr * S.ngh * 8, sm1 = (size_t)S.ngh * 16 + (size_t)nzr * S.ngh * 8;
+  const size_t sm0 = (size_t)SF_MFP * S.ngh * 16 + (size_t)3 * (nzr + (nzr | 1)) * S.ngh * 8, sm1 = (size_t)S.ngh * 16 + (size_t)(nzr + (nzr | 1)) * S.ngh * 8;
   static PerDeviceMax attr;
   if (sm0 > 48 * 1024 && attr.raise(sm0))
     PNFAM_CUDA_CHECK(cudaFuncSetAttribute(sf2_kappa_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm0));
