@@ -2,10 +2,13 @@
 """Per-kernel table from the raw CSV of one `ncu --set full` capture (scripts/gpu_evidence.sh exports it on the GPU box):
 time, launch shape, pipe / memory utilisation, DRAM bytes and EXECUTED FP64 flops per launch (2 x DFMA + DADD + DMUL thread
 instructions; DMMA m8n8k4 = 512 flop per warp instruction).  Writes <out>.csv and <out>.json (bench.py reads the JSON for
-roofline.traffic and the executed-flop figures).   Usage: python scripts/ncu_kernels.py <raw.csv> <out prefix> "<command>" """
+roofline.traffic and the executed-flop figures).
+Usage: python scripts/ncu_kernels.py <raw.csv> <out prefix> "<command>" [shells] [omega points per launch] """
 import csv, json, sys
 
 raw, out, cmd = sys.argv[1], sys.argv[2], sys.argv[3]
+shells = int(sys.argv[4]) if len(sys.argv) > 4 else 16
+points = int(sys.argv[5]) if len(sys.argv) > 5 else 8
 rows = list(csv.reader(open(raw)))
 h, units = rows[0], rows[1]
 ix = {k: i for i, k in enumerate(h)}
@@ -55,7 +58,7 @@ with open(out + ".csv", "w") as f:
     w.writerow(keys)
     for r in table:
         w.writerow([("%.4g" % r[k]) if isinstance(r[k], float) else r[k] for k in keys])
-json.dump({"source": "ncu --set full --clock-control none, %s" % cmd, "kernels": table}, open(out + ".json", "w"), indent=1)
+json.dump({"source": "ncu --set full --clock-control none, %s" % cmd, "shells": shells, "points": points, "kernels": table}, open(out + ".json", "w"), indent=1)
 for r in table:
     print("%-28s grid %6d %8.1f us  warps %4.1f%% issue %4.1f%% dmma %4.1f%% fp64 %4.1f%% L1 %4.1f%% L2 %4.1f%% dram %4.1f%% (%6.0f GB/s, %6.1f MB)  fp64 thread flops %.3g (%.2f TF/s)" % (
         r["kernel"][:28], r["grid"], r["us_per_launch"], r["warps_active_pct"], r["issue_active_pct"], r["dmma_pipe_pct"], r["fp64_pipe_pct"],
