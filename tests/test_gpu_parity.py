@@ -557,3 +557,35 @@ def test_empty_and_single_point_batches(gpu, tmp_path):
     rb = ctx.solve(p, omegas=om)
     r1 = ctx.solve(p, omegas=om[1:2])
     assert int(r1["iters"][0]) == int(rb["iters"][1]) and _rel(r1["strength"][0, 0], rb["strength"][1, 0]) < 1e-13
+
+
+def test_two_contexts_on_two_devices_in_one_process(gpu, tmp_path):
+    """One process holding a context on each of two GPUs (per-device attribute / memory-pool caches, device guard): both
+    solve the same points -- 16 shells, so that the kernels need more than 48 KB of dynamic shared memory on BOTH devices --
+    alternately, the results are identical bit for bit and the caller's current device is left alone."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import json
+    import os
+    import re
+    from conftest import GOLDEN
+    pts = json.load(open(os.path.join(GOLDEN, "Gd162_SKOP_16sh", "prod_points.json")))["points"]["GT-K0"][:4]
+    import shutil
+    for f in ("hfbtho_NAMELIST.dat", "hfbtho_output.hel"):
+        shutil.copy(os.path.join(GOLDEN, "Gd162_SKOP_16sh", f), str(tmp_path))
+    (tmp_path / "x.in").write_text(pts[0]["namelist"])
+    p = host.Problem(str(tmp_path), "x.in")
+    om = [complex(float(re.search(r"real_eqrpa\s*=\s*(\S+)", q["namelist"]).group(1)),
+                  float(re.search(r"imag_eqrpa\s*=\s*(\S+)", q["namelist"]).group(1))) for q in pts]
+    torch.cuda.set_device(0)
+    c0, c1 = gpu.Context(p, device=0), gpu.Context(p, device=1)
+    r1 = c1.solve(p, omegas=om)
+    assert torch.cuda.current_device() == 0
+    r0 = c0.solve(p, omegas=om)
+    r1b = c1.solve(p, omegas=om[:2])
+    assert (r0["iters"] == r1["iters"]).all() and (r0["conv"] == 1).all()
+    assert (r0["strength"] == r1["strength"]).all() and (r1b["strength"] == r1["strength"][:2]).all()
+    for i, q in enumerate(pts):
+        g = complex(float(q["rows"]["Strength"][0]), float(q["rows"]["Strength"][1]))
+        assert _rel(r0["strength"][i, 0], g) < LOOSE_TOL
