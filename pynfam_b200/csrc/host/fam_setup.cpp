@@ -545,10 +545,28 @@ ExtField make_external_field(const FamBasis& b, const std::string& beta_type, co
   // base label without the trailing I (same selection rules, I-function folded into dotw)
   std::string B = L;
   if (useI) B = L.substr(0, L.size() - 1);
-  size_t ipt = 0;
-  for (int ibx1 = 0; ibx1 < b.nb; ibx1++) {
+  // every matrix element is an independent grid sum (same order of additions whatever the thread count): block rows in
+  // parallel, largest first
+  std::vector<size_t> ipt0(b.nb, 0);
+  std::vector<int> rows;
+  {
+    size_t acc = 0;
+    for (int ibx1 = 0; ibx1 < b.nb; ibx1++) {
+      ipt0[ibx1] = acc;
+      const int ibx2 = op.mat.ir2c[ibx1] - 1;
+      if (ibx2 < 0) continue;
+      acc += (size_t)b.db[ibx1] * b.db[ibx2];
+      rows.push_back(ibx1);
+    }
+    std::stable_sort(rows.begin(), rows.end(), [&](int x, int y) {
+      return (size_t)b.db[x] * b.db[op.mat.ir2c[x] - 1] > (size_t)b.db[y] * b.db[op.mat.ir2c[y] - 1];
+    });
+  }
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int ir = 0; ir < (int)rows.size(); ir++) {
+    const int ibx1 = rows[ir];
     const int ibx2 = op.mat.ir2c[ibx1] - 1;
-    if (ibx2 < 0) continue;
+    size_t ipt = ipt0[ibx1];
     const int nd1 = b.db[ibx1], nd2 = b.db[ibx2];
     for (int i2 = 0; i2 < nd2; i2++) {
       const int ix2 = i2 + b.isstart[ibx2] - 1;
