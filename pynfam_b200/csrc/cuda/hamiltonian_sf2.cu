@@ -191,15 +191,114 @@ __global__ void __launch_bounds__(256) sf2_density_kernel(HamArgs g) {
   }
 }
 
+// ================================================================================================
+// pairing density, four Gauss-Laguerre nodes per CTA.  kappa -> K needs the plain wave function only (one radial factor
+// R0 per row), so one pass over the packed kappa elements can serve several il at once: the element loads -- the traffic
+// that bounds these gather kernels (every il re-reads the whole packed copy from L2) -- are shared by four nodes and the
+// four R0 of a row come as one 32-byte record (SfDev::r0q).
+// ================================================================================================
+__global__ void __launch_bounds__(256) sf2_kappa_density4_kernel(HamArgs g) {
+  constexpr int KS = 8, NI = 4;
+  extern __shared__ __align__(16) unsigned char smem[];
+  const SfDev& S = g.sf;
+  const Sf2Dev& F = g.sf2;
+  const int iq = blockIdx.x, sweep = blockIdx.y >> 1, q = blockIdx.y & 1, za = blockIdx.z;
+  if (g.ctrl && za >= g.ctrl->nactive) return;
+  const int tid = threadIdx.x;
+  const int nzr = F.nzr, npair = nzr * nzr, ngh = S.ngh, list = 2 + q;
+  double2* Pi = reinterpret_cast<double2*>(smem);                        // [NI][npair]
+  double* Zs = reinterpret_cast<double*>(Pi + (size_t)NI * npair);      // [nzr][ngh]: Z0
+  for (int i = tid; i < nzr * ngh; i += 256) {
+    const int zr = i / ngh, ih = i - zr * ngh;
+    Zs[i] = S.zt[(size_t)zr * S.zs + ih];
+  }
+  for (int i = tid; i < NI * npair; i += 256) Pi[i] = make_double2(0.0, 0.0);
+  __syncthreads();
+  const int* __restrict__ cptr = F.cptr[list] + (size_t)sweep * (npair + 1);
+  const int4* __restrict__ cols = F.cols[list];
+  const double2* __restrict__ pk = reinterpret_cast<const double2*>(S.pk[1] + ((size_t)za * 2 + q) * S.pk_stride[1]);
+  const double* __restrict__ rq = S.r0q + (size_t)iq * S.dqp_p * 4;
+  const int part = tid & (KS - 1);
+  const int* __restrict__ order = F.order[list] + (size_t)sweep * (npair + 1);
+  const int nwork = order[0];
+  for (int k0 = 0, round = 0; k0 < nwork; k0 += 256 / KS, round++) {
+    const int k = k0 + ((round & 1) ? 256 / KS - 1 - (tid >> 3) : (tid >> 3));
+    const int p = k < nwork ? order[1 + k] : npair;
+    double2 acc[NI];
+#pragma unroll
+    for (int i = 0; i < NI; i++) acc[i] = make_double2(0.0, 0.0);
+    if (p < npair) {
+      const int c1 = cptr[p + 1];
+      int c = cptr[p] + part;
+      int4 cn = make_int4(0, 0, 0, 0);
+      if (c < c1) cn = __ldg(cols + c);
+      while (c < c1) {
+        const int4 cd = cn;                                  // first element, rows, row of a_0, row of b
+        c += KS;
+        if (c < c1) cn = __ldg(cols + c);
+        const double2* __restrict__ vp = pk + cd.x;
+        const double* __restrict__ ra = rq + (size_t)cd.z * 4;
+        double2 t[NI];
+#pragma unroll
+        for (int i = 0; i < NI; i++) t[i] = make_double2(0.0, 0.0);
+        for (int a0 = 0; a0 < cd.y; a0 += 4) {
+          double2 v[4], r01[4], r23[4];
+#pragma unroll
+          for (int u = 0; u < 4; u++) {                      // all loads of the chunk first (independent)
+            const bool on = a0 + u < cd.y;
+            v[u] = on ? __ldg(vp + a0 + u) : make_double2(0.0, 0.0);
+            r01[u] = on ? ldg2(ra + (a0 + u) * 4) : make_double2(0.0, 0.0);
+            r23[u] = on ? ldg2(ra + (a0 + u) * 4 + 2) : make_double2(0.0, 0.0);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; u++) { cfma(t[0], r01[u].x, v[u]); cfma(t[1], r01[u].y, v[u]); cfma(t[2], r23[u].x, v[u]); cfma(t[3], r23[u].y, v[u]); }
+        }
+        const double2 b01 = ldg2(rq + (size_t)cd.w * 4), b23 = ldg2(rq + (size_t)cd.w * 4 + 2);
+        cfma(acc[0], b01.x, t[0]); cfma(acc[1], b01.y, t[1]); cfma(acc[2], b23.x, t[2]); cfma(acc[3], b23.y, t[3]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NI; i++) {
+      double2& v = acc[i];
+      v.x += __shfl_xor_sync(0xffffffffu, v.x, 1); v.y += __shfl_xor_sync(0xffffffffu, v.y, 1);
+      v.x += __shfl_xor_sync(0xffffffffu, v.x, 2); v.y += __shfl_xor_sync(0xffffffffu, v.y, 2);
+      v.x += __shfl_xor_sync(0xffffffffu, v.x, 4); v.y += __shfl_xor_sync(0xffffffffu, v.y, 4);
+    }
+    if (p < npair && part == 0) {
+#pragma unroll
+      for (int i = 0; i < NI; i++) Pi[(size_t)i * npair + p] = acc[i];
+    }
+  }
+  __syncthreads();
+  // ---- z part: K(ih, il) = sum_zr Z0(zr,ih) sum_zr' Pi[il][zr][zr'] Z0(zr',ih); task = (il of the group, ih)
+  const int2* __restrict__ zrange = F.zrange[list] + (size_t)sweep * nzr;
+  for (int task = tid; task < ngh * NI; task += 256) {
+    const int i = task / ngh, ih = task - i * ngh, il = iq * NI + i;
+    if (il >= S.ngl) continue;
+    double2 d = make_double2(0.0, 0.0);
+    for (int zr = 0; zr < nzr; zr++) {
+      const int2 rng = zrange[zr];
+      if (rng.x >= rng.y) continue;
+      double2 x = make_double2(0.0, 0.0);
+      const double2* __restrict__ prow = Pi + (size_t)i * npair + (size_t)zr * nzr;
+      for (int z2 = rng.x; z2 < rng.y; z2++) cfma(x, Zs[(size_t)z2 * ngh + ih], prow[z2]);
+      cfma(d, Zs[(size_t)zr * ngh + ih], x);
+    }
+    double* __restrict__ o = g.dd_kap + ((size_t)za * 2 + q) * 8 * g.basis.nghl + (size_t)il * ngh + (size_t)(sweep * 2) * g.basis.nghl + ih;
+    o[0] = d.x;
+    o[g.basis.nghl] = d.y;
+  }
+}
+
 void launch_density_sf2(const HamArgs& a, cudaStream_t stream) {
   if (a.nactive <= 0) return;
   const SfDev& S = a.sf;
   const int nzr = a.sf2.nzr, npair = nzr * nzr;
-  const size_t sm0 = (size_t)9 * npair * 16 + (size_t)2 * nzr * S.ngh * 8, sm1 = (size_t)npair * 16 + (size_t)2 * nzr * S.ngh * 8;
+  const size_t sm0 = (size_t)9 * npair * 16 + (size_t)2 * nzr * S.ngh * 8, sm4 = (size_t)4 * npair * 16 + (size_t)nzr * S.ngh * 8;
   static PerDeviceMax attr;
   if (attr.raise(sm0)) {
     PNFAM_CUDA_CHECK(cudaFuncSetAttribute(sf2_density_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm0));
-    PNFAM_CUDA_CHECK(cudaFuncSetAttribute(sf2_density_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm0));
+    PNFAM_CUDA_CHECK(cudaFuncSetAttribute(sf2_kappa_density4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm0));
   }
   const int nel = std::max(std::max(a.sf2.nelem[0], a.sf2.nelem[1]), std::max(a.sf2.nelem[2], a.sf2.nelem[3]));
   if (nel > 0) sf2_pack_kernel<<<dim3((nel + 255) / 256, 4, a.nactive), 256, 0, stream>>>(a);
@@ -207,7 +306,7 @@ void launch_density_sf2(const HamArgs& a, cudaStream_t stream) {
   SideStreams& ss = *a.side;
   ss.fork_from(stream, 1);
   sf2_density_kernel<0><<<grid, 256, sm0, stream>>>(a);
-  sf2_density_kernel<1><<<grid, 256, sm1, ss.s[0]>>>(a);
+  sf2_kappa_density4_kernel<<<dim3((S.ngl + 3) / 4, 8, a.nactive), 256, sm4, ss.s[0]>>>(a);
   ss.join_to(stream, 1);
 }
 
@@ -293,8 +392,14 @@ __global__ void __launch_bounds__(256, 3) sf2_kappa_kernel(HamArgs g) {
 // ================================================================================================
 // projection, radial part: one thread = one row a x a run of <= SF2_RUN columns with equal n_z
 // ================================================================================================
+#ifndef SF2_RADIAL_UNROLL
+#define SF2_RADIAL_UNROLL 2
+#endif
+#ifndef SF2_RADIAL_CTAS
+#define SF2_RADIAL_CTAS 4
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(128, 6) sf2_radial_kernel(HamArgs g, int q) {
+__global__ void __launch_bounds__(128, SF2_RADIAL_CTAS) sf2_radial_kernel(HamArgs g, int q) {
   constexpr int NJJ = MODE == 0 ? SF2_NJJ : 1;
   const SfDev& S = g.sf;
   const Sf2Dev& F = g.sf2;
@@ -313,6 +418,8 @@ __global__ void __launch_bounds__(128, 6) sf2_radial_kernel(HamArgs g, int q) {
   double2 acc[SF2_RUN];
 #pragma unroll
   for (int c = 0; c < SF2_RUN; c++) acc[c] = make_double2(0.0, 0.0);
+  constexpr int kUnroll = SF2_RADIAL_UNROLL;   // iterations in flight: the loop is bound by the latency of its loads
+#pragma unroll kUnroll
   for (int il = 0; il < ngl; il++, kp += kstride, ra += rstride, rb += rstride) {
     const double2 a01 = ldg2(ra);
     if (MODE == 1) {
