@@ -25,6 +25,7 @@
 //   sf2_radial_kernel   one thread per (row a, run of <= 8 columns with equal n_z) of the output block matrix
 // Sums run in a fixed order (no atomics): results are reproducible run to run.
 #include <algorithm>
+#include <cstdlib>
 
 #include "device_common.cuh"
 #include "kernels.cuh"
@@ -59,25 +60,32 @@ __global__ void __launch_bounds__(256) sf2_pack_kernel(HamArgs g) {
 // ================================================================================================
 // density: radial part + contraction with the z tables
 // ================================================================================================
-template <int MODE>
-__global__ void __launch_bounds__(256) sf2_density_kernel(HamArgs g) {
+// ILS = Gauss-Laguerre nodes per CTA (1 or 2).  With ILS = 2 neighbouring lanes walk the SAME columns for two different
+// il: their element loads hit the same sectors (one fetch from L2 and half the L1 wavefronts per il -- every il has to
+// stream the whole packed copy, which is what bounds this gather kernel) while the register footprint of a lane is that
+// of one il.  The radial factors come from the il-pair table (SfDev::rgp: the two 32-byte records of a row are adjacent).
+template <int MODE, int ILS>
+__global__ void __launch_bounds__(256 * ILS) sf2_density_kernel(HamArgs g) {
+  constexpr int NTHR = 256 * ILS;         // two il: one CTA of 512 threads per SM (its Pi arrays take the room of two CTAs)
   constexpr int NJ = MODE == 0 ? 3 : 1;   // radial factor types of the densities: R0, R1 (d/dr), R2 (Lambda/r)
   constexpr int NT = MODE == 0 ? 4 : 1;   // derivative types: phi, d/dr, Lambda/r, d/dz
   constexpr int KS = 8;                   // lanes sharing one (zr, zr') entry: they stride through its elements
+  constexpr int KC = KS / ILS;            // ... of which KC walk different columns
+  constexpr int RS = 4 * ILS;             // doubles between two rows of the radial-factor table
   extern __shared__ __align__(16) unsigned char smem[];
   const SfDev& S = g.sf;
   const Sf2Dev& F = g.sf2;
-  const int il = blockIdx.x, sweep = blockIdx.y >> 1, q = blockIdx.y & 1, za = blockIdx.z;
+  const int ig = blockIdx.x, sweep = blockIdx.y >> 1, q = blockIdx.y & 1, za = blockIdx.z;
   if (g.ctrl && za >= g.ctrl->nactive) return;
   const int tid = threadIdx.x;
   const int nzr = F.nzr, npair = nzr * nzr, ngh = S.ngh, list = MODE * 2 + q;
-  double2* Pi = reinterpret_cast<double2*>(smem);                        // [NJ*NJ][npair]
-  double* Zs = reinterpret_cast<double*>(Pi + (size_t)NJ * NJ * npair);  // [2][nzr][ngh]: Z0, Z1
-  for (int i = tid; i < 2 * nzr * ngh; i += 256) {
+  double2* Pi = reinterpret_cast<double2*>(smem);                        // [ILS][NJ*NJ][npair]
+  double* Zs = reinterpret_cast<double*>(Pi + (size_t)ILS * NJ * NJ * npair);  // [2][nzr][ngh]: Z0, Z1
+  for (int i = tid; i < 2 * nzr * ngh; i += NTHR) {
     const int m = i / (nzr * ngh), r = i - m * nzr * ngh, zr = r / ngh, ih = r - zr * ngh;
     Zs[i] = S.zt[((size_t)m * nzr + zr) * S.zs + ih];
   }
-  for (int i = tid; i < NJ * NJ * npair; i += 256) Pi[i] = make_double2(0.0, 0.0);
+  for (int i = tid; i < ILS * NJ * NJ * npair; i += NTHR) Pi[i] = make_double2(0.0, 0.0);
   __syncthreads();
   // ---- radial part: Pi^{jj'}[zr][zr'] = sum over the sub-blocks of the group of R^j_a rho_ab R^j'_b at this il, column by
   //      column: t^j = sum_a R^j_a rho_ab (the column is a contiguous run of the packed copy), then t^j R^j'_b.
@@ -88,27 +96,27 @@ __global__ void __launch_bounds__(256) sf2_density_kernel(HamArgs g) {
   const int* __restrict__ cptr = F.cptr[list] + (size_t)sweep * (npair + 1);
   const int4* __restrict__ cols = F.cols[list];
   const double2* __restrict__ pk = reinterpret_cast<const double2*>(S.pk[MODE] + ((size_t)za * 2 + q) * S.pk_stride[MODE]);
-  const double* __restrict__ rgl = S.rg + (size_t)il * S.dqp_p * 4;
-  const int part = tid & (KS - 1);
+  const int part = tid & (KS - 1), isub = part % ILS, cpart = part / ILS;
+  const double* __restrict__ rgl = ILS == 1 ? S.rg + (size_t)ig * S.dqp_p * 4 : S.rgp + (size_t)ig * S.dqp_p * 8 + isub * 4;
   const int* __restrict__ order = F.order[list] + (size_t)sweep * (npair + 1);
   const int nwork = order[0];
-  for (int k0 = 0, round = 0; k0 < nwork; k0 += 256 / KS, round++) {
-    const int k = k0 + ((round & 1) ? 256 / KS - 1 - (tid >> 3) : (tid >> 3));
+  for (int k0 = 0, round = 0; k0 < nwork; k0 += NTHR / KS, round++) {
+    const int k = k0 + ((round & 1) ? NTHR / KS - 1 - (tid >> 3) : (tid >> 3));
     const int p = k < nwork ? order[1 + k] : npair;
     double2 acc[NJ][NJ];
 #pragma unroll
     for (int i = 0; i < NJ * NJ; i++) (&acc[0][0])[i] = make_double2(0.0, 0.0);
     if (p < npair) {
       const int c1 = cptr[p + 1];
-      int c = cptr[p] + part;
+      int c = cptr[p] + cpart;
       int4 cn = make_int4(0, 0, 0, 0);
       if (c < c1) cn = __ldg(cols + c);
       while (c < c1) {
         const int4 cd = cn;                                  // first element, rows, row of a_0, row of b
-        c += KS;
+        c += KC;
         if (c < c1) cn = __ldg(cols + c);                    // next descriptor one step ahead
         const double2* __restrict__ vp = pk + cd.x;
-        const double* __restrict__ ra = rgl + (size_t)cd.z * 4;
+        const double* __restrict__ ra = rgl + (size_t)cd.z * RS;
         double2 t[NJ];
 #pragma unroll
         for (int j = 0; j < NJ; j++) t[j] = make_double2(0.0, 0.0);
@@ -119,8 +127,8 @@ __global__ void __launch_bounds__(256) sf2_density_kernel(HamArgs g) {
           for (int u = 0; u < 4; u++) {                      // all loads of the chunk first (independent)
             const bool on = a0 + u < cd.y;
             v[u] = on ? __ldg(vp + a0 + u) : make_double2(0.0, 0.0);
-            r01[u] = on ? ldg2(ra + (a0 + u) * 4) : make_double2(0.0, 0.0);
-            r2[u] = (MODE == 0 && on) ? __ldg(ra + (a0 + u) * 4 + 2) : 0.0;
+            r01[u] = on ? ldg2(ra + (a0 + u) * RS) : make_double2(0.0, 0.0);
+            r2[u] = (MODE == 0 && on) ? __ldg(ra + (a0 + u) * RS + 2) : 0.0;
           }
 #pragma unroll
           for (int u = 0; u < 4; u++) {
@@ -128,8 +136,8 @@ __global__ void __launch_bounds__(256) sf2_density_kernel(HamArgs g) {
             if (MODE == 0) { cfma(t[1], r01[u].y, v[u]); cfma(t[2], r2[u], v[u]); }
           }
         }
-        const double2 b01 = ldg2(rgl + (size_t)cd.w * 4);
-        const double b2 = MODE == 0 ? __ldg(rgl + (size_t)cd.w * 4 + 2) : 0.0;
+        const double2 b01 = ldg2(rgl + (size_t)cd.w * RS);
+        const double b2 = MODE == 0 ? __ldg(rgl + (size_t)cd.w * RS + 2) : 0.0;
 #pragma unroll
         for (int j = 0; j < NJ; j++) {
           cfma(acc[j][0], b01.x, t[j]);
@@ -138,27 +146,31 @@ __global__ void __launch_bounds__(256) sf2_density_kernel(HamArgs g) {
       }
     }
 #pragma unroll
-    for (int i = 0; i < NJ * NJ; i++) {
+    for (int i = 0; i < NJ * NJ; i++) {                       // sum over the lanes of the same il, fixed order
       double2& v = (&acc[0][0])[i];
-      v.x += __shfl_xor_sync(0xffffffffu, v.x, 1); v.y += __shfl_xor_sync(0xffffffffu, v.y, 1);
+      if (ILS == 1) { v.x += __shfl_xor_sync(0xffffffffu, v.x, 1); v.y += __shfl_xor_sync(0xffffffffu, v.y, 1); }
       v.x += __shfl_xor_sync(0xffffffffu, v.x, 2); v.y += __shfl_xor_sync(0xffffffffu, v.y, 2);
       v.x += __shfl_xor_sync(0xffffffffu, v.x, 4); v.y += __shfl_xor_sync(0xffffffffu, v.y, 4);
     }
-    if (p < npair && part == 0) {
+    if (p < npair && cpart == 0) {
 #pragma unroll
       for (int j = 0; j < NJ; j++)
 #pragma unroll
-        for (int j2 = 0; j2 < NJ; j2++) Pi[(size_t)(j * NJ + j2) * npair + p] = acc[j][j2];
+        for (int j2 = 0; j2 < NJ; j2++) Pi[(size_t)((isub * NJ + j) * NJ + j2) * npair + p] = acc[j][j2];
     }
   }
   __syncthreads();
-  // ---- z part: D^{tt'}(ih) = sum_zr Z^{m_t}(zr,ih) sum_zr' Pi^{j_t j_t'}[zr][zr'] Z^{m_t'}(zr',ih); task = (ih, t')
+  // ---- z part: D^{tt'}(ih) = sum_zr Z^{m_t}(zr,ih) sum_zr' Pi^{j_t j_t'}[zr][zr'] Z^{m_t'}(zr',ih); task = (il, ih, t')
   const int2* __restrict__ zrange = F.zrange[list] + (size_t)sweep * nzr;
   constexpr int ndd = NT * NT * 8;
-  double* __restrict__ out0 = (MODE ? g.dd_kap : g.dd_rho) + ((size_t)za * 2 + q) * ndd * g.basis.nghl + (size_t)il * ngh;
-  for (int task = tid; task < ngh * NT; task += 256) {
-    const int t2 = task / ngh, ih = task - t2 * ngh;
+  for (int task = tid; task < ILS * ngh * NT; task += NTHR) {
+    const int is = task / (ngh * NT), tr = task - is * ngh * NT;
+    const int il = ig * ILS + is;
+    if (il >= S.ngl) continue;
+    const int t2 = tr / ngh, ih = tr - t2 * ngh;
     const int j2 = (MODE == 0 && t2 < 3) ? t2 : 0, m2 = (MODE == 0 && t2 == 3) ? 1 : 0;
+    const double2* __restrict__ Pil = Pi + (size_t)is * NJ * NJ * npair;
+    double* __restrict__ out0 = (MODE ? g.dd_kap : g.dd_rho) + ((size_t)za * 2 + q) * ndd * g.basis.nghl + (size_t)il * ngh;
     double2 d[NT];
 #pragma unroll
     for (int t = 0; t < NT; t++) d[t] = make_double2(0.0, 0.0);
@@ -169,7 +181,7 @@ __global__ void __launch_bounds__(256) sf2_density_kernel(HamArgs g) {
 #pragma unroll
       for (int j = 0; j < NJ; j++) x[j] = make_double2(0.0, 0.0);
       const double* __restrict__ zcol = Zs + (size_t)m2 * nzr * ngh + ih;
-      const double2* __restrict__ prow = Pi + (size_t)j2 * npair + (size_t)zr * nzr;
+      const double2* __restrict__ prow = Pil + (size_t)j2 * npair + (size_t)zr * nzr;
       for (int z2 = rng.x; z2 < rng.y; z2++) {
         const double zz = zcol[(size_t)z2 * ngh];
 #pragma unroll
@@ -294,18 +306,24 @@ void launch_density_sf2(const HamArgs& a, cudaStream_t stream) {
   if (a.nactive <= 0) return;
   const SfDev& S = a.sf;
   const int nzr = a.sf2.nzr, npair = nzr * nzr;
-  const size_t sm0 = (size_t)9 * npair * 16 + (size_t)2 * nzr * S.ngh * 8, sm4 = (size_t)4 * npair * 16 + (size_t)nzr * S.ngh * 8;
+  // PNFAM_B200_DENSITY_ILS=2: two il per CTA (512 threads, one CTA per SM) when its two sets of Pi arrays fit -- measured
+  // slower than one il per CTA on B200 (2.72 against 2.52 ms per launch at 16 shells, 64 points), so it is off by default
+  static const int ils_knob = getenv("PNFAM_B200_DENSITY_ILS") ? atoi(getenv("PNFAM_B200_DENSITY_ILS")) : 1;
+  const size_t zbytes = (size_t)2 * nzr * S.ngh * 8;
+  const int ils = (ils_knob >= 2 && (size_t)18 * npair * 16 + zbytes <= 220 * 1024) ? 2 : 1;
+  const size_t sm0 = (size_t)ils * 9 * npair * 16 + zbytes, sm4 = (size_t)4 * npair * 16 + (size_t)nzr * S.ngh * 8;
   static PerDeviceMax attr;
-  if (attr.raise(sm0)) {
-    PNFAM_CUDA_CHECK(cudaFuncSetAttribute(sf2_density_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm0));
-    PNFAM_CUDA_CHECK(cudaFuncSetAttribute(sf2_kappa_density4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm0));
+  if (attr.raise(std::max(sm0, sm4))) {
+    PNFAM_CUDA_CHECK(cudaFuncSetAttribute(sf2_density_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(sm0, sm4)));
+    PNFAM_CUDA_CHECK(cudaFuncSetAttribute(sf2_density_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(sm0, sm4)));
+    PNFAM_CUDA_CHECK(cudaFuncSetAttribute(sf2_kappa_density4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(sm0, sm4)));
   }
   const int nel = std::max(std::max(a.sf2.nelem[0], a.sf2.nelem[1]), std::max(a.sf2.nelem[2], a.sf2.nelem[3]));
   if (nel > 0) sf2_pack_kernel<<<dim3((nel + 255) / 256, 4, a.nactive), 256, 0, stream>>>(a);
-  const dim3 grid(S.ngl, 8, a.nactive);
   SideStreams& ss = *a.side;
   ss.fork_from(stream, 1);
-  sf2_density_kernel<0><<<grid, 256, sm0, stream>>>(a);
+  if (ils == 2) sf2_density_kernel<0, 2><<<dim3((S.ngl + 1) / 2, 8, a.nactive), 512, sm0, stream>>>(a);
+  else sf2_density_kernel<0, 1><<<dim3(S.ngl, 8, a.nactive), 256, sm0, stream>>>(a);
   sf2_kappa_density4_kernel<<<dim3((S.ngl + 3) / 4, 8, a.nactive), 256, sm4, ss.s[0]>>>(a);
   ss.join_to(stream, 1);
 }
@@ -480,6 +498,6 @@ void launch_projection_sf2(const HamArgs& a, cudaStream_t stream) {
   ss.join_to(stream, 1);
 }
 
-int sf2_smem_bytes(const SfDev& S) { return 9 * S.nzrows * S.nzrows * 16 + 2 * S.nzrows * S.ngh * 8; }
+int sf2_smem_bytes(const SfDev& S) { return 9 * S.nzrows * S.nzrows * 16 + 2 * S.nzrows * S.ngh * 8; }   // one il per CTA
 
 }  // namespace pnfam
