@@ -9,6 +9,7 @@ cp $g/bench_default_$tag.json profiles/${pre}_bench_default.json
 cp $g/bench_reference_$tag.json profiles/${pre}_bench_reference_arm.json
 [ -f $g/pytest_gpu_$tag.log ] && cp $g/pytest_gpu_$tag.log profiles/${pre}_pytest_gpu.log
 cp $g/smoke_$tag.log profiles/${pre}_smoke.log
+for f in bench_2phase bench_12sh bench_20sh bench_24sh level0 fp64_peak; do [ -f $g/${f}_$tag.json ] && cp $g/${f}_$tag.json profiles/${pre}_$f.json; done
 cp $g/smi_$tag.csv profiles/${pre}_smi.csv
 cp $g/launches_$tag.csv profiles/${pre}_launches_16sh_128pts.csv
 python scripts/launch_shares.py $g/launches_$tag.csv > profiles/${pre}_launch_shares.txt
