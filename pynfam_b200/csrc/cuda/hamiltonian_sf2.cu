@@ -107,33 +107,63 @@ __global__ void __launch_bounds__(256 * ILS) sf2_density_kernel(HamArgs g) {
 #pragma unroll
     for (int i = 0; i < NJ * NJ; i++) (&acc[0][0])[i] = make_double2(0.0, 0.0);
     if (p < npair) {
+      // One column per trip.  The loop is bound by the latency of its loads (the packed elements stream from L2, one round
+      // trip per column and lane), so it is software-pipelined by hand: the elements of the NEXT column's first row chunk
+      // are fetched before the current column is worked on, the column descriptors run two trips ahead.
       const int c1 = cptr[p + 1];
       int c = cptr[p] + cpart;
-      int4 cn = make_int4(0, 0, 0, 0);
-      if (c < c1) cn = __ldg(cols + c);
+      int4 cd = make_int4(0, 0, 0, 0), cn = cd;
+      double2 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) v[u] = make_double2(0.0, 0.0);
+      if (c < c1) {
+        cd = __ldg(cols + c);
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+          if (u < cd.y) v[u] = __ldg(pk + cd.x + u);
+      }
+      if (c + KC < c1) cn = __ldg(cols + c + KC);
       while (c < c1) {
-        const int4 cd = cn;                                  // first element, rows, row of a_0, row of b
-        c += KC;
-        if (c < c1) cn = __ldg(cols + c);                    // next descriptor one step ahead
-        const double2* __restrict__ vp = pk + cd.x;
+        const int cnext = c + KC;
+        int4 cnn = make_int4(0, 0, 0, 0);
+        if (cnext + KC < c1) cnn = __ldg(cols + cnext + KC);
+        double2 vn[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) vn[u] = (cnext < c1 && u < cn.y) ? __ldg(pk + cn.x + u) : make_double2(0.0, 0.0);
+        const double2* __restrict__ vp = pk + cd.x;           // first element, rows, row of a_0, row of b
         const double* __restrict__ ra = rgl + (size_t)cd.z * RS;
         double2 t[NJ];
 #pragma unroll
         for (int j = 0; j < NJ; j++) t[j] = make_double2(0.0, 0.0);
-        for (int a0 = 0; a0 < cd.y; a0 += 4) {
-          double2 v[4], r01[4];
+        {
+          double2 r01[4];
           double r2[4];
 #pragma unroll
-          for (int u = 0; u < 4; u++) {                      // all loads of the chunk first (independent)
-            const bool on = a0 + u < cd.y;
-            v[u] = on ? __ldg(vp + a0 + u) : make_double2(0.0, 0.0);
-            r01[u] = on ? ldg2(ra + (a0 + u) * RS) : make_double2(0.0, 0.0);
-            r2[u] = (MODE == 0 && on) ? __ldg(ra + (a0 + u) * RS + 2) : 0.0;
+          for (int u = 0; u < 4; u++) {
+            const bool on = u < cd.y;
+            r01[u] = on ? ldg2(ra + u * RS) : make_double2(0.0, 0.0);
+            r2[u] = (MODE == 0 && on) ? __ldg(ra + u * RS + 2) : 0.0;
           }
 #pragma unroll
           for (int u = 0; u < 4; u++) {
             cfma(t[0], r01[u].x, v[u]);
             if (MODE == 0) { cfma(t[1], r01[u].y, v[u]); cfma(t[2], r2[u], v[u]); }
+          }
+        }
+        for (int a0 = 4; a0 < cd.y; a0 += 4) {               // longer columns: the remaining chunks on demand
+          double2 w[4], r01[4];
+          double r2[4];
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const bool on = a0 + u < cd.y;
+            w[u] = on ? __ldg(vp + a0 + u) : make_double2(0.0, 0.0);
+            r01[u] = on ? ldg2(ra + (a0 + u) * RS) : make_double2(0.0, 0.0);
+            r2[u] = (MODE == 0 && on) ? __ldg(ra + (a0 + u) * RS + 2) : 0.0;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            cfma(t[0], r01[u].x, w[u]);
+            if (MODE == 0) { cfma(t[1], r01[u].y, w[u]); cfma(t[2], r2[u], w[u]); }
           }
         }
         const double2 b01 = ldg2(rgl + (size_t)cd.w * RS);
@@ -143,6 +173,9 @@ __global__ void __launch_bounds__(256 * ILS) sf2_density_kernel(HamArgs g) {
           cfma(acc[j][0], b01.x, t[j]);
           if (MODE == 0) { cfma(acc[j][1], b01.y, t[j]); cfma(acc[j][2], b2, t[j]); }
         }
+        c = cnext; cd = cn; cn = cnn;
+#pragma unroll
+        for (int u = 0; u < 4; u++) v[u] = vn[u];
       }
     }
 #pragma unroll
@@ -240,33 +273,60 @@ __global__ void __launch_bounds__(256) sf2_kappa_density4_kernel(HamArgs g) {
 #pragma unroll
     for (int i = 0; i < NI; i++) acc[i] = make_double2(0.0, 0.0);
     if (p < npair) {
+      // software-pipelined like the rho density: the next column's elements are fetched one trip ahead
       const int c1 = cptr[p + 1];
       int c = cptr[p] + part;
-      int4 cn = make_int4(0, 0, 0, 0);
-      if (c < c1) cn = __ldg(cols + c);
+      int4 cd = make_int4(0, 0, 0, 0), cn = cd;
+      double2 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) v[u] = make_double2(0.0, 0.0);
+      if (c < c1) {
+        cd = __ldg(cols + c);
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+          if (u < cd.y) v[u] = __ldg(pk + cd.x + u);
+      }
+      if (c + KS < c1) cn = __ldg(cols + c + KS);
       while (c < c1) {
-        const int4 cd = cn;                                  // first element, rows, row of a_0, row of b
-        c += KS;
-        if (c < c1) cn = __ldg(cols + c);
+        const int cnext = c + KS;
+        int4 cnn = make_int4(0, 0, 0, 0);
+        if (cnext + KS < c1) cnn = __ldg(cols + cnext + KS);
+        double2 vn[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) vn[u] = (cnext < c1 && u < cn.y) ? __ldg(pk + cn.x + u) : make_double2(0.0, 0.0);
         const double2* __restrict__ vp = pk + cd.x;
         const double* __restrict__ ra = rq + (size_t)cd.z * 4;
         double2 t[NI];
 #pragma unroll
         for (int i = 0; i < NI; i++) t[i] = make_double2(0.0, 0.0);
-        for (int a0 = 0; a0 < cd.y; a0 += 4) {
-          double2 v[4], r01[4], r23[4];
+        {
+          double2 r01[4], r23[4];
 #pragma unroll
-          for (int u = 0; u < 4; u++) {                      // all loads of the chunk first (independent)
-            const bool on = a0 + u < cd.y;
-            v[u] = on ? __ldg(vp + a0 + u) : make_double2(0.0, 0.0);
-            r01[u] = on ? ldg2(ra + (a0 + u) * 4) : make_double2(0.0, 0.0);
-            r23[u] = on ? ldg2(ra + (a0 + u) * 4 + 2) : make_double2(0.0, 0.0);
+          for (int u = 0; u < 4; u++) {
+            const bool on = u < cd.y;
+            r01[u] = on ? ldg2(ra + u * 4) : make_double2(0.0, 0.0);
+            r23[u] = on ? ldg2(ra + u * 4 + 2) : make_double2(0.0, 0.0);
           }
 #pragma unroll
           for (int u = 0; u < 4; u++) { cfma(t[0], r01[u].x, v[u]); cfma(t[1], r01[u].y, v[u]); cfma(t[2], r23[u].x, v[u]); cfma(t[3], r23[u].y, v[u]); }
         }
+        for (int a0 = 4; a0 < cd.y; a0 += 4) {
+          double2 w[4], r01[4], r23[4];
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const bool on = a0 + u < cd.y;
+            w[u] = on ? __ldg(vp + a0 + u) : make_double2(0.0, 0.0);
+            r01[u] = on ? ldg2(ra + (a0 + u) * 4) : make_double2(0.0, 0.0);
+            r23[u] = on ? ldg2(ra + (a0 + u) * 4 + 2) : make_double2(0.0, 0.0);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; u++) { cfma(t[0], r01[u].x, w[u]); cfma(t[1], r01[u].y, w[u]); cfma(t[2], r23[u].x, w[u]); cfma(t[3], r23[u].y, w[u]); }
+        }
         const double2 b01 = ldg2(rq + (size_t)cd.w * 4), b23 = ldg2(rq + (size_t)cd.w * 4 + 2);
         cfma(acc[0], b01.x, t[0]); cfma(acc[1], b01.y, t[1]); cfma(acc[2], b23.x, t[2]); cfma(acc[3], b23.y, t[3]);
+        c = cnext; cd = cn; cn = cnn;
+#pragma unroll
+        for (int u = 0; u < 4; u++) v[u] = vn[u];
       }
     }
 #pragma unroll
