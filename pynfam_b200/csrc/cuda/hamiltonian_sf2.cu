@@ -474,7 +474,7 @@ __global__ void __launch_bounds__(256, 3) sf2_kappa_kernel(HamArgs g) {
 #define SF2_RADIAL_UNROLL 2
 #endif
 #ifndef SF2_RADIAL_CTAS
-#define SF2_RADIAL_CTAS 4
+#define SF2_RADIAL_CTAS 3
 #endif
 template <int MODE>
 __global__ void __launch_bounds__(128, SF2_RADIAL_CTAS) sf2_radial_kernel(HamArgs g, int q) {
@@ -493,33 +493,46 @@ __global__ void __launch_bounds__(128, SF2_RADIAL_CTAS) sf2_radial_kernel(HamArg
                                   ((size_t)zra * nzr + zrb) * NJJ * 2;
   const double* __restrict__ ra = S.rg + (size_t)t.pa * 4;
   const double* __restrict__ rb = S.rg + (size_t)t.pb0 * 4;
-  double2 acc[SF2_RUN];
+  // two rows of equal n_z per thread: the kt entries and the column factors of an il are fetched once for both (the
+  // kernel is bound by L1 throughput); a single-row task runs the second row with zero factors
+  const double f2 = t.na > 1 ? 1.0 : 0.0;
+  const double* __restrict__ ra2 = t.na > 1 ? ra + 4 : ra;
+  double2 acc[SF2_RUN], acd[SF2_RUN];
 #pragma unroll
-  for (int c = 0; c < SF2_RUN; c++) acc[c] = make_double2(0.0, 0.0);
-  constexpr int kUnroll = SF2_RADIAL_UNROLL;   // iterations in flight: the loop is bound by the latency of its loads
-#pragma unroll kUnroll
-  for (int il = 0; il < ngl; il++, kp += kstride, ra += rstride, rb += rstride) {
+  for (int c = 0; c < SF2_RUN; c++) acc[c] = acd[c] = make_double2(0.0, 0.0);
+  for (int il = 0; il < ngl; il++, kp += kstride, ra += rstride, ra2 += rstride, rb += rstride) {
     const double2 a01 = ldg2(ra);
+    double2 c01 = ldg2(ra2);
+    c01.x *= f2; c01.y *= f2;
     if (MODE == 1) {
       const double2 kk = ldg2(kp);
-      const double2 v = make_double2(a01.x * kk.x, a01.x * kk.y);
+      const double2 v = make_double2(a01.x * kk.x, a01.x * kk.y), w = make_double2(c01.x * kk.x, c01.x * kk.y);
 #pragma unroll
       for (int c = 0; c < SF2_RUN; c++)
-        if (c < t.nb) cfma(acc[c], __ldg(rb + c * 4), v);
+        if (c < t.nb) { const double b0 = __ldg(rb + c * 4); cfma(acc[c], b0, v); cfma(acd[c], b0, w); }
     } else {
       const double2 a23 = ldg2(ra + 2);
-      double2 v0 = make_double2(0.0, 0.0), v1 = v0, v2 = v0, v3 = v0;
-      // V^{j'} = sum_j R^j_a kt^{jj'}
-      cfma(v0, a01.x, ldg2(kp + 2 * jj_index(0, 0))); cfma(v0, a01.y, ldg2(kp + 2 * jj_index(1, 0)));
-      cfma(v0, a23.x, ldg2(kp + 2 * jj_index(2, 0))); cfma(v0, a23.y, ldg2(kp + 2 * jj_index(3, 0)));
-      cfma(v1, a01.x, ldg2(kp + 2 * jj_index(0, 1))); cfma(v1, a01.y, ldg2(kp + 2 * jj_index(1, 1))); cfma(v1, a23.x, ldg2(kp + 2 * jj_index(2, 1)));
-      cfma(v2, a01.x, ldg2(kp + 2 * jj_index(0, 2))); cfma(v2, a01.y, ldg2(kp + 2 * jj_index(1, 2))); cfma(v2, a23.x, ldg2(kp + 2 * jj_index(2, 2)));
-      cfma(v3, a01.x, ldg2(kp + 2 * jj_index(0, 3)));
+      double2 c23 = ldg2(ra2 + 2);
+      c23.x *= f2; c23.y *= f2;
+      double2 v0 = make_double2(0.0, 0.0), v1 = v0, v2 = v0, v3 = v0, w0 = v0, w1 = v0, w2 = v0, w3 = v0;
+      // V^{j'} = sum_j R^j_a kt^{jj'} for both rows
+      { const double2 k = ldg2(kp + 2 * jj_index(0, 0)); cfma(v0, a01.x, k); cfma(w0, c01.x, k); }
+      { const double2 k = ldg2(kp + 2 * jj_index(1, 0)); cfma(v0, a01.y, k); cfma(w0, c01.y, k); }
+      { const double2 k = ldg2(kp + 2 * jj_index(2, 0)); cfma(v0, a23.x, k); cfma(w0, c23.x, k); }
+      { const double2 k = ldg2(kp + 2 * jj_index(3, 0)); cfma(v0, a23.y, k); cfma(w0, c23.y, k); }
+      { const double2 k = ldg2(kp + 2 * jj_index(0, 1)); cfma(v1, a01.x, k); cfma(w1, c01.x, k); }
+      { const double2 k = ldg2(kp + 2 * jj_index(1, 1)); cfma(v1, a01.y, k); cfma(w1, c01.y, k); }
+      { const double2 k = ldg2(kp + 2 * jj_index(2, 1)); cfma(v1, a23.x, k); cfma(w1, c23.x, k); }
+      { const double2 k = ldg2(kp + 2 * jj_index(0, 2)); cfma(v2, a01.x, k); cfma(w2, c01.x, k); }
+      { const double2 k = ldg2(kp + 2 * jj_index(1, 2)); cfma(v2, a01.y, k); cfma(w2, c01.y, k); }
+      { const double2 k = ldg2(kp + 2 * jj_index(2, 2)); cfma(v2, a23.x, k); cfma(w2, c23.x, k); }
+      { const double2 k = ldg2(kp + 2 * jj_index(0, 3)); cfma(v3, a01.x, k); cfma(w3, c01.x, k); }
 #pragma unroll
       for (int c = 0; c < SF2_RUN; c++)
         if (c < t.nb) {
           const double2 b01 = ldg2(rb + c * 4), b23 = ldg2(rb + c * 4 + 2);
           cfma(acc[c], b01.x, v0); cfma(acc[c], b01.y, v1); cfma(acc[c], b23.x, v2); cfma(acc[c], b23.y, v3);
+          cfma(acd[c], b01.x, w0); cfma(acd[c], b01.y, w1); cfma(acd[c], b23.x, w2); cfma(acd[c], b23.y, w3);
         }
     }
   }
@@ -527,12 +540,14 @@ __global__ void __launch_bounds__(128, SF2_RADIAL_CTAS) sf2_radial_kernel(HamArg
   const int quad = MODE ? g.kap_quad[q] : g.rho_quad[q];
   double* __restrict__ ore = g.hsp + (((size_t)p * 2 + 0) * 4 + quad) * g.nxy + t.out_base + S.p2l[t.pa];
   double* __restrict__ oim = ore + 4 * g.nxy;
+  const int d2 = t.na > 1 ? S.p2l[t.pa + 1] - S.p2l[t.pa] : 0;
 #pragma unroll
   for (int c = 0; c < SF2_RUN; c++)
     if (c < t.nb) {
       const size_t e = (size_t)S.p2l[t.pb0 + c] * t.ld;
       ore[e] = 2.0 * acc[c].x;
       oim[e] = 2.0 * acc[c].y;
+      if (t.na > 1) { ore[e + d2] = 2.0 * acd[c].x; oim[e + d2] = 2.0 * acd[c].y; }
     }
 }
 

@@ -163,10 +163,12 @@ struct SfDev {
 constexpr int SF2_NJJ = 11;      // (j, j') combinations of the radial factors in the mean field:
                                  // (0,0) (0,1) (0,2) (0,3) (1,0) (1,1) (1,2) (2,0) (2,1) (2,2) (3,0)
 constexpr int SF2_RUN = 8;       // columns per task of the radial projection (runs of equal n_z are cut at this length)
-struct Sf2Task {                 // radial projection: one row a x a run of <= SF2_RUN columns with equal n_z
-  int pa, pb0, nb;               // padded row of a, of the first column, columns
+struct Sf2Task {                 // radial projection: one or two rows a of equal n_z x a run of <= SF2_RUN columns with equal n_z
+  int pa, pb0, nb;               // padded row of (the first) a, of the first column, columns
   int out_base, ld;              // element offset of the block in the block matrix, leading dimension
   int sasb;                      // spin combination 2 sa + sb
+  int na;                        // rows: 1 or 2 (pa, pa + 1: the kt entries of an il are fetched once for both)
+  int pad;
 };
 struct Sf2Dev {
   int enabled = 0;

@@ -508,11 +508,13 @@ void build_sf2_tasks(const pnfam_b200_ctx& c, const BlockStruct& st, DBuf<Sf2Tas
         const int pb0 = c.seg_prow0[sb] + j0, zrb = c.h_zrow[pb0];
         int j1 = j0 + 1;
         while (j1 < nbs && j1 - j0 < SF2_RUN && c.h_zrow[c.seg_prow0[sb] + j1] == zrb) j1++;
-        for (int i = 0; i < na; i++) {
+        for (int i = 0; i < na;) {
           Sf2Task t{};
           t.pa = c.seg_prow0[sa] + i; t.pb0 = pb0; t.nb = j1 - j0; t.out_base = st.r2m[ix]; t.ld = c.db[ix]; t.sasb = s;
+          t.na = (i + 1 < na && c.h_zrow[t.pa + 1] == c.h_zrow[t.pa]) ? 2 : 1;      // rows of equal n_z are neighbours
           tasks.push_back(t);
           need[(size_t)s * npair + (size_t)c.h_zrow[t.pa] * nzr + zrb] = 1;
+          i += t.na;
         }
         j0 = j1;
       }
