@@ -496,13 +496,15 @@ __global__ void __launch_bounds__(128, SF2_RADIAL_CTAS) sf2_radial_kernel(HamArg
   // two rows of equal n_z per thread: the kt entries and the column factors of an il are fetched once for both (the
   // kernel is bound by L1 throughput); a single-row task runs the second row with zero factors
   const double f2 = t.na > 1 ? 1.0 : 0.0;
-  const double* __restrict__ ra2 = t.na > 1 ? ra + 4 : ra;
+  const size_t np = (size_t)S.dqp_p;
+  const double* __restrict__ rt = S.rgt + t.pa;             // component-major radial factors: [il][4][row]
+  const int o2 = t.na > 1 ? 1 : 0;
   double2 acc[SF2_RUN], acd[SF2_RUN];
 #pragma unroll
   for (int c = 0; c < SF2_RUN; c++) acc[c] = acd[c] = make_double2(0.0, 0.0);
-  for (int il = 0; il < ngl; il++, kp += kstride, ra += rstride, ra2 += rstride, rb += rstride) {
-    const double2 a01 = ldg2(ra);
-    double2 c01 = ldg2(ra2);
+  for (int il = 0; il < ngl; il++, kp += kstride, rt += 4 * np, rb += rstride) {
+    const double2 a01 = make_double2(__ldg(rt), __ldg(rt + np));
+    double2 c01 = make_double2(__ldg(rt + o2), __ldg(rt + np + o2));
     c01.x *= f2; c01.y *= f2;
     if (MODE == 1) {
       const double2 kk = ldg2(kp);
@@ -511,8 +513,8 @@ __global__ void __launch_bounds__(128, SF2_RADIAL_CTAS) sf2_radial_kernel(HamArg
       for (int c = 0; c < SF2_RUN; c++)
         if (c < t.nb) { const double b0 = __ldg(rb + c * 4); cfma(acc[c], b0, v); cfma(acd[c], b0, w); }
     } else {
-      const double2 a23 = ldg2(ra + 2);
-      double2 c23 = ldg2(ra2 + 2);
+      const double2 a23 = make_double2(__ldg(rt + 2 * np), __ldg(rt + 3 * np));
+      double2 c23 = make_double2(__ldg(rt + 2 * np + o2), __ldg(rt + 3 * np + o2));
       c23.x *= f2; c23.y *= f2;
       double2 v0 = make_double2(0.0, 0.0), v1 = v0, v2 = v0, v3 = v0, w0 = v0, w1 = v0, w2 = v0, w3 = v0;
       // V^{j'} = sum_j R^j_a kt^{jj'} for both rows

@@ -139,6 +139,8 @@ struct SfDev {
   const double* rg = nullptr;    // [ngl][dqp_p][4]  R0..R3 per padded row (rows of a segment sorted by n_z slot)
   const double* rgp = nullptr;   // [(ngl+1)/2][dqp_p][2][4]  the same for il pairs (density: one copy serves both il)
   const double* r0q = nullptr;   // [(ngl+3)/4][dqp_p][4]  R0 of four consecutive il (pairing density: one pass over kappa serves four il)
+  const double* rgt = nullptr;   // [ngl][4][dqp_p]  component-major copy of rg (radial projection: consecutive lanes = consecutive
+                                 // rows read consecutive doubles)
   const int* zrow = nullptr;     // [dqp_p] z-table row of a padded row (0 for padding)
   const int* p2l = nullptr;      // [dqp_p] index of the state inside its block, -1 for padding
   const int* slot = nullptr;     // [dqp_p] n_z slot of the row inside its spin segment

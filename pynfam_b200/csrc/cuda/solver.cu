@@ -131,7 +131,7 @@ struct pnfam_b200_ctx {
   std::vector<int> seg_prow0, seg_n, seg_nslots;   // per (block, spin) segment: first padded row, states, n_z slots
   std::vector<int> h_zrow, h_p2l;                   // host copies of the per-padded-row tables (list building)
   bool sf2 = false;                                 // fully factorised kernels (hamiltonian_sf2.cu)
-  DBuf<double> d_zt, d_rg, d_rgp, d_r0q;
+  DBuf<double> d_zt, d_rg, d_rgp, d_r0q, d_rgt;
   DBuf<int> d_zrow, d_p2l, d_slot, d_segtab;
   cudaStream_t stream = nullptr;
   std::unique_ptr<SideStreams> side;   // side streams + fork/join events of this context
@@ -233,12 +233,19 @@ static bool setup_separable(pnfam_b200_ctx& c, const pnfam_b200_model& m) {
       for (int k = 0; k < 4; k++)
         if (4 * iq + k < ngl) r0q[((size_t)iq * c.dqp_p + pr) * 4 + k] = rg[((size_t)(4 * iq + k) * c.dqp_p + pr) * 4];
   c.d_r0q.upload(r0q);
+  {
+    std::vector<double> rgt((size_t)ngl * 4 * c.dqp_p, 0.0);
+    for (int il = 0; il < ngl; il++)
+      for (int pr = 0; pr < c.dqp_p; pr++)
+        for (int j = 0; j < 4; j++) rgt[((size_t)il * 4 + j) * c.dqp_p + pr] = rg[((size_t)il * c.dqp_p + pr) * 4 + j];
+    c.d_rgt.upload(rgt);
+  }
   c.h_zrow = zrow; c.h_p2l = p2l;
   c.d_rgp.upload(rgp);
   c.d_zt.upload(zt); c.d_rg.upload(rg); c.d_zrow.upload(zrow); c.d_p2l.upload(p2l); c.d_slot.upload(slot); c.d_segtab.upload(segtab);
   SfDev& S = c.sf;
   S.enabled = 1; S.ngh = ngh; S.ngl = ngl; S.mt = mt; S.kih = kih; S.zs = zs; S.nzrows = nzr; S.dqp_p = c.dqp_p;
-  S.zt = c.d_zt.p; S.rg = c.d_rg.p; S.rgp = c.d_rgp.p; S.r0q = c.d_r0q.p; S.zrow = c.d_zrow.p; S.p2l = c.d_p2l.p; S.slot = c.d_slot.p; S.segtab = c.d_segtab.p;
+  S.zt = c.d_zt.p; S.rg = c.d_rg.p; S.rgp = c.d_rgp.p; S.r0q = c.d_r0q.p; S.rgt = c.d_rgt.p; S.zrow = c.d_zrow.p; S.p2l = c.d_p2l.p; S.slot = c.d_slot.p; S.segtab = c.d_segtab.p;
   S.na_max = 1; S.kpad_max = 4;
   for (int seg = 0; seg < nseg; seg++) { S.na_max = std::max(S.na_max, c.seg_n[seg]); S.kpad_max = std::max(S.kpad_max, pad4(c.seg_nslots[seg])); }
   if (S.na_max > 8 * 12) return S.enabled = 0, false;
@@ -331,7 +338,7 @@ extern "C" int pnfam_b200_ctx_create(const pnfam_b200_model* m, int device, pnfa
         PNFAM_CUDA_CHECK(cudaDeviceSynchronize());
         c->table_h2d_bytes = (int64_t)NTYPE * nraw * 8;
       } else {
-        c->table_h2d_bytes = (int64_t)(c->d_zt.n + c->d_rg.n + c->d_rgp.n + c->d_r0q.n) * 8 + (int64_t)(c->d_zrow.n + c->d_p2l.n + c->d_slot.n + c->d_segtab.n) * 4;
+        c->table_h2d_bytes = (int64_t)(c->d_zt.n + c->d_rg.n + c->d_rgp.n + c->d_r0q.n + c->d_rgt.n) * 8 + (int64_t)(c->d_zrow.n + c->d_p2l.n + c->d_slot.n + c->d_segtab.n) * 4;
       }
     }
     auto up = [&](DBuf<double>& d, const double* p, size_t n) { d.upload(std::vector<double>(p, p + n)); };
