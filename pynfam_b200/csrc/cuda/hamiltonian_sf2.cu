@@ -425,22 +425,25 @@ __global__ void __launch_bounds__(256, 3) sf2_kappa_kernel(HamArgs g) {
   __syncthreads();
   const unsigned char* __restrict__ need = F.need[MODE][q] + (size_t)s4 * npair;
   double* __restrict__ out = F.kt[MODE] + ((size_t)za * 2 + q) * sf2_kt_elems(MODE, S.ngl, nzr) + ((size_t)s4 * S.ngl + il) * npair * NJJ * 2;
-  for (int p = tid; p < npair; p += 256) {
-    if (!need[p]) continue;
-    const int zr = p / nzr, z2 = p - zr * nzr;
+  // kt is stored [jj][zr'][zr] (zr fastest): the radial kernel's lanes are consecutive rows a -- a few neighbouring zr at
+  // one zr' -- so its eleven loads per il touch two or three lines instead of one line per distinct zr.  Consecutive
+  // lanes here therefore differ in zr (the [ih][zr] copy of the z tables), zr' is nearly uniform over a warp.
+  for (int pp = tid; pp < npair; pp += 256) {
+    const int z2 = pp / nzr, zr = pp - z2 * nzr;
+    if (!need[zr * nzr + z2]) continue;
     double2 acc[NJJ];
 #pragma unroll
     for (int i = 0; i < NJJ; i++) acc[i] = make_double2(0.0, 0.0);
-    const double* __restrict__ za_ = Zs + (size_t)zr * ngh;
-    const double* __restrict__ zb_ = Zt + z2;
+    const double* __restrict__ za_ = Zt + zr;
+    const double* __restrict__ zb_ = Zs + (size_t)z2 * ngh;
     const size_t ms = (size_t)nzr * ngh, mt = (size_t)ngh * nzp;
     for (int ih = 0; ih < ngh; ih++) {
-      const double a0 = za_[ih], b0 = zb_[(size_t)ih * nzp];
+      const double a0 = za_[(size_t)ih * nzp], b0 = zb_[ih];
       const double p00 = a0 * b0;
       if (MODE == 1) {
         cfma(acc[0], p00, mfs[ih]);
       } else {
-        const double a1 = za_[ms + ih], a2 = za_[2 * ms + ih], b1 = zb_[mt + (size_t)ih * nzp], b2 = zb_[2 * mt + (size_t)ih * nzp];
+        const double a1 = za_[mt + (size_t)ih * nzp], a2 = za_[2 * mt + (size_t)ih * nzp], b1 = zb_[ms + ih], b2 = zb_[2 * ms + ih];
         const double p01 = a0 * b1, p10 = a1 * b0, p11 = a1 * b1, p02 = a0 * b2, p20 = a2 * b0;
         // (t, t') with t, t' in {phi, d/dr, Lambda/r}: Z0 Z0', radial pair (t, t')
 #pragma unroll
@@ -461,9 +464,9 @@ __global__ void __launch_bounds__(256, 3) sf2_kappa_kernel(HamArgs g) {
         cfma(acc[jj_index(3, 0)], p00, mfs[mfp(4, 0) * ngh + ih]);
       }
     }
-    double2* __restrict__ o = reinterpret_cast<double2*>(out + (size_t)p * NJJ * 2);
+    double2* __restrict__ o = reinterpret_cast<double2*>(out) + pp;
 #pragma unroll
-    for (int i = 0; i < NJJ; i++) o[i] = acc[i];
+    for (int i = 0; i < NJJ; i++) o[(size_t)i * npair] = acc[i];
   }
 }
 
@@ -490,7 +493,8 @@ __global__ void __launch_bounds__(128, SF2_RADIAL_CTAS) sf2_radial_kernel(HamArg
   const int zra = S.zrow[t.pa], zrb = S.zrow[t.pb0];
   const size_t kstride = (size_t)npair * NJJ * 2, rstride = (size_t)S.dqp_p * 4;
   const double* __restrict__ kp = F.kt[MODE] + ((size_t)za * 2 + q) * sf2_kt_elems(MODE, ngl, nzr) + (size_t)t.sasb * ngl * kstride +
-                                  ((size_t)zra * nzr + zrb) * NJJ * 2;
+                                  ((size_t)zrb * nzr + zra) * 2;     // [jj][zr'][zr]
+  const size_t kj = (size_t)npair * 2;                                // doubles between two jj
   const double* __restrict__ ra = S.rg + (size_t)t.pa * 4;
   const double* __restrict__ rb = S.rg + (size_t)t.pb0 * 4;
   // two rows of equal n_z per thread: the kt entries and the column factors of an il are fetched once for both (the
@@ -518,17 +522,17 @@ __global__ void __launch_bounds__(128, SF2_RADIAL_CTAS) sf2_radial_kernel(HamArg
       c23.x *= f2; c23.y *= f2;
       double2 v0 = make_double2(0.0, 0.0), v1 = v0, v2 = v0, v3 = v0, w0 = v0, w1 = v0, w2 = v0, w3 = v0;
       // V^{j'} = sum_j R^j_a kt^{jj'} for both rows
-      { const double2 k = ldg2(kp + 2 * jj_index(0, 0)); cfma(v0, a01.x, k); cfma(w0, c01.x, k); }
-      { const double2 k = ldg2(kp + 2 * jj_index(1, 0)); cfma(v0, a01.y, k); cfma(w0, c01.y, k); }
-      { const double2 k = ldg2(kp + 2 * jj_index(2, 0)); cfma(v0, a23.x, k); cfma(w0, c23.x, k); }
-      { const double2 k = ldg2(kp + 2 * jj_index(3, 0)); cfma(v0, a23.y, k); cfma(w0, c23.y, k); }
-      { const double2 k = ldg2(kp + 2 * jj_index(0, 1)); cfma(v1, a01.x, k); cfma(w1, c01.x, k); }
-      { const double2 k = ldg2(kp + 2 * jj_index(1, 1)); cfma(v1, a01.y, k); cfma(w1, c01.y, k); }
-      { const double2 k = ldg2(kp + 2 * jj_index(2, 1)); cfma(v1, a23.x, k); cfma(w1, c23.x, k); }
-      { const double2 k = ldg2(kp + 2 * jj_index(0, 2)); cfma(v2, a01.x, k); cfma(w2, c01.x, k); }
-      { const double2 k = ldg2(kp + 2 * jj_index(1, 2)); cfma(v2, a01.y, k); cfma(w2, c01.y, k); }
-      { const double2 k = ldg2(kp + 2 * jj_index(2, 2)); cfma(v2, a23.x, k); cfma(w2, c23.x, k); }
-      { const double2 k = ldg2(kp + 2 * jj_index(0, 3)); cfma(v3, a01.x, k); cfma(w3, c01.x, k); }
+      { const double2 k = ldg2(kp + kj * jj_index(0, 0)); cfma(v0, a01.x, k); cfma(w0, c01.x, k); }
+      { const double2 k = ldg2(kp + kj * jj_index(1, 0)); cfma(v0, a01.y, k); cfma(w0, c01.y, k); }
+      { const double2 k = ldg2(kp + kj * jj_index(2, 0)); cfma(v0, a23.x, k); cfma(w0, c23.x, k); }
+      { const double2 k = ldg2(kp + kj * jj_index(3, 0)); cfma(v0, a23.y, k); cfma(w0, c23.y, k); }
+      { const double2 k = ldg2(kp + kj * jj_index(0, 1)); cfma(v1, a01.x, k); cfma(w1, c01.x, k); }
+      { const double2 k = ldg2(kp + kj * jj_index(1, 1)); cfma(v1, a01.y, k); cfma(w1, c01.y, k); }
+      { const double2 k = ldg2(kp + kj * jj_index(2, 1)); cfma(v1, a23.x, k); cfma(w1, c23.x, k); }
+      { const double2 k = ldg2(kp + kj * jj_index(0, 2)); cfma(v2, a01.x, k); cfma(w2, c01.x, k); }
+      { const double2 k = ldg2(kp + kj * jj_index(1, 2)); cfma(v2, a01.y, k); cfma(w2, c01.y, k); }
+      { const double2 k = ldg2(kp + kj * jj_index(2, 2)); cfma(v2, a23.x, k); cfma(w2, c23.x, k); }
+      { const double2 k = ldg2(kp + kj * jj_index(0, 3)); cfma(v3, a01.x, k); cfma(w3, c01.x, k); }
 #pragma unroll
       for (int c = 0; c < SF2_RUN; c++)
         if (c < t.nb) {
