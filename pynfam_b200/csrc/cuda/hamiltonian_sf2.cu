@@ -392,7 +392,7 @@ void launch_density_sf2(const HamArgs& a, cudaStream_t stream) {
 // projection, z part: kt^{jj'}[zr][zr'] of one (il, sa, sb)
 // ================================================================================================
 template <int MODE>
-__global__ void __launch_bounds__(256, 3) sf2_kappa_kernel(HamArgs g) {
+__global__ void __launch_bounds__(256, 2) sf2_kappa_kernel(HamArgs g) {
   constexpr int NP = MODE == 0 ? SF_MFP : 1;       // field-tensor pairs
   constexpr int NJJ = MODE == 0 ? SF2_NJJ : 1;
   extern __shared__ __align__(16) unsigned char smem[];
@@ -428,45 +428,59 @@ __global__ void __launch_bounds__(256, 3) sf2_kappa_kernel(HamArgs g) {
   // kt is stored [jj][zr'][zr] (zr fastest): the radial kernel's lanes are consecutive rows a -- a few neighbouring zr at
   // one zr' -- so its eleven loads per il touch two or three lines instead of one line per distinct zr.  Consecutive
   // lanes here therefore differ in zr (the [ih][zr] copy of the z tables), zr' is nearly uniform over a warp.
-  for (int pp = tid; pp < npair; pp += 256) {
-    const int z2 = pp / nzr, zr = pp - z2 * nzr;
-    if (!need[zr * nzr + z2]) continue;
-    double2 acc[NJJ];
+  // A thread works on TWO columns zr' (2k, 2k+1) of its row zr: the kernel is bound by shared-memory wavefronts, and the
+  // field-tensor broadcasts (18 of the 24 loads per ih) then serve two kt entries.
+  const int nz2 = (nzr + 1) >> 1;
+  for (int pp = tid; pp < nz2 * nzr; pp += 256) {
+    const int zk = pp / nzr, zr = pp - zk * nzr, z2a = 2 * zk, z2b = min(2 * zk + 1, nzr - 1);
+    const bool ona = need[zr * nzr + z2a] != 0, onb = 2 * zk + 1 < nzr && need[zr * nzr + z2b] != 0;
+    if (!ona && !onb) continue;
+    double2 acc[NJJ], acd[NJJ];
 #pragma unroll
-    for (int i = 0; i < NJJ; i++) acc[i] = make_double2(0.0, 0.0);
+    for (int i = 0; i < NJJ; i++) acc[i] = acd[i] = make_double2(0.0, 0.0);
     const double* __restrict__ za_ = Zt + zr;
-    const double* __restrict__ zb_ = Zs + (size_t)z2 * ngh;
+    const double* __restrict__ zb_ = Zs + (size_t)z2a * ngh;
+    const double* __restrict__ zc_ = Zs + (size_t)z2b * ngh;
     const size_t ms = (size_t)nzr * ngh, mt = (size_t)ngh * nzp;
     for (int ih = 0; ih < ngh; ih++) {
-      const double a0 = za_[(size_t)ih * nzp], b0 = zb_[ih];
-      const double p00 = a0 * b0;
+      const double a0 = za_[(size_t)ih * nzp], b0 = zb_[ih], c0 = zc_[ih];
+      const double p00 = a0 * b0, q00 = a0 * c0;
       if (MODE == 1) {
-        cfma(acc[0], p00, mfs[ih]);
+        const double2 m = mfs[ih];
+        cfma(acc[0], p00, m); cfma(acd[0], q00, m);
       } else {
-        const double a1 = za_[mt + (size_t)ih * nzp], a2 = za_[2 * mt + (size_t)ih * nzp], b1 = zb_[ms + ih], b2 = zb_[2 * ms + ih];
+        const double a1 = za_[mt + (size_t)ih * nzp], a2 = za_[2 * mt + (size_t)ih * nzp];
+        const double b1 = zb_[ms + ih], b2 = zb_[2 * ms + ih], c1 = zc_[ms + ih], c2 = zc_[2 * ms + ih];
         const double p01 = a0 * b1, p10 = a1 * b0, p11 = a1 * b1, p02 = a0 * b2, p20 = a2 * b0;
+        const double q01 = a0 * c1, q10 = a1 * c0, q11 = a1 * c1, q02 = a0 * c2, q20 = a2 * c0;
         // (t, t') with t, t' in {phi, d/dr, Lambda/r}: Z0 Z0', radial pair (t, t')
 #pragma unroll
         for (int t = 0; t < 3; t++)
 #pragma unroll
-          for (int t2 = 0; t2 < 3; t2++) cfma(acc[jj_index(t, t2)], p00, mfs[mfp(t, t2) * ngh + ih]);
+          for (int t2 = 0; t2 < 3; t2++) { const double2 m = mfs[mfp(t, t2) * ngh + ih]; cfma(acc[jj_index(t, t2)], p00, m); cfma(acd[jj_index(t, t2)], q00, m); }
         // d/dz on one side: Z1, radial factor R0
 #pragma unroll
         for (int t = 0; t < 3; t++) {
-          cfma(acc[jj_index(t, 0)], p01, mfs[mfp(t, 3) * ngh + ih]);
-          cfma(acc[jj_index(0, t)], p10, mfs[mfp(3, t) * ngh + ih]);
+          { const double2 m = mfs[mfp(t, 3) * ngh + ih]; cfma(acc[jj_index(t, 0)], p01, m); cfma(acd[jj_index(t, 0)], q01, m); }
+          { const double2 m = mfs[mfp(3, t) * ngh + ih]; cfma(acc[jj_index(0, t)], p10, m); cfma(acd[jj_index(0, t)], q10, m); }
         }
-        cfma(acc[jj_index(0, 0)], p11, mfs[mfp(3, 3) * ngh + ih]);
+        { const double2 m = mfs[mfp(3, 3) * ngh + ih]; cfma(acc[jj_index(0, 0)], p11, m); cfma(acd[jj_index(0, 0)], q11, m); }
         // Laplacian = Z2 R0 + Z0 R3, only next to the plain wave function
-        cfma(acc[jj_index(0, 0)], p02, mfs[mfp(0, 4) * ngh + ih]);
-        cfma(acc[jj_index(0, 3)], p00, mfs[mfp(0, 4) * ngh + ih]);
-        cfma(acc[jj_index(0, 0)], p20, mfs[mfp(4, 0) * ngh + ih]);
-        cfma(acc[jj_index(3, 0)], p00, mfs[mfp(4, 0) * ngh + ih]);
+        { const double2 m = mfs[mfp(0, 4) * ngh + ih];
+          cfma(acc[jj_index(0, 0)], p02, m); cfma(acc[jj_index(0, 3)], p00, m); cfma(acd[jj_index(0, 0)], q02, m); cfma(acd[jj_index(0, 3)], q00, m); }
+        { const double2 m = mfs[mfp(4, 0) * ngh + ih];
+          cfma(acc[jj_index(0, 0)], p20, m); cfma(acc[jj_index(3, 0)], p00, m); cfma(acd[jj_index(0, 0)], q20, m); cfma(acd[jj_index(3, 0)], q00, m); }
       }
     }
-    double2* __restrict__ o = reinterpret_cast<double2*>(out) + pp;
+    double2* __restrict__ o = reinterpret_cast<double2*>(out);
+    if (ona) {
 #pragma unroll
-    for (int i = 0; i < NJJ; i++) o[(size_t)i * npair] = acc[i];
+      for (int i = 0; i < NJJ; i++) o[(size_t)i * npair + z2a * nzr + zr] = acc[i];
+    }
+    if (onb) {
+#pragma unroll
+      for (int i = 0; i < NJJ; i++) o[(size_t)i * npair + z2b * nzr + zr] = acd[i];
+    }
   }
 }
 
