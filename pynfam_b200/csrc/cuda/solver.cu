@@ -22,20 +22,34 @@ namespace pnfam {
 // needs tens of GB of work space (Broyden history), and a fresh context / solve then reuses what the previous one
 // returned instead of going back to the driver.  All allocations and frees are ordered on the legacy default
 // stream, with which the (blocking) work stream of a context synchronises implicitly.
-inline void keep_pool_memory() {
+// Two pools per device: the default one holds the large per-solve arrays (Broyden history, amplitudes: always the same
+// sequence of sizes, so a solve finds the blocks the previous one returned), a second one the small allocations (tables of
+// a context, task lists of an operator) -- otherwise those would be carved out of the returned large blocks and the next
+// solve would have to go back to the driver for tens of GB (0.4-0.7 s per solve, seen in the end-to-end timing).
+constexpr size_t SMALL_ALLOC_BYTES = (size_t)32 << 20;
+inline cudaMemPool_t small_pool_of_current_device() {
   static bool done[64] = {};
+  static cudaMemPool_t small[64] = {};
   static std::mutex guard;
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
   std::lock_guard<std::mutex> lock(guard);
-  if (done[dev & 63]) return;
-  cudaMemPool_t pool;
-  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+  if (!done[dev & 63]) {
     unsigned long long keep = ~0ull;
-    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    if (cudaMemPoolCreate(&small[dev & 63], &props) == cudaSuccess) cudaMemPoolSetAttribute(small[dev & 63], cudaMemPoolAttrReleaseThreshold, &keep);
+    else { small[dev & 63] = nullptr; cudaGetLastError(); }
+    done[dev & 63] = true;
   }
-  done[dev & 63] = true;
+  return small[dev & 63];
 }
+inline void keep_pool_memory() { (void)small_pool_of_current_device(); }
 // bytes a solve may still allocate on the current device: free device memory + what the pool holds but does not use
 inline size_t device_bytes_available() {
   size_t fr = 0, tot = 0;
@@ -76,7 +90,11 @@ struct DBuf {
   void alloc(size_t count) {
     release();
     n = count;
-    if (count) { keep_pool_memory(); PNFAM_CUDA_CHECK(cudaMallocAsync(&p, count * sizeof(T), 0)); }
+    if (count) {
+      cudaMemPool_t sp = small_pool_of_current_device();
+      if (sp && count * sizeof(T) < SMALL_ALLOC_BYTES) PNFAM_CUDA_CHECK(cudaMallocFromPoolAsync(&p, count * sizeof(T), sp, 0));
+      else PNFAM_CUDA_CHECK(cudaMallocAsync(&p, count * sizeof(T), 0));
+    }
   }
   void upload(const std::vector<T>& h) {
     alloc(h.size());
