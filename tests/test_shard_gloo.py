@@ -33,9 +33,38 @@ def test_partition_covers_every_point_once_and_balances():
         allidx = np.sort(np.concatenate(parts))
         assert np.array_equal(allidx, np.arange(37))
         assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
-        # the most expensive points (smallest |Im omega|) are spread over different ranks
-        hard = set(np.argsort(np.abs(om.imag))[:world])
+        # the most expensive points (largest expected cost) are spread over different ranks and the estimated loads agree
+        cost = shard.expected_cost(om)
+        hard = set(np.argsort(-cost, kind="stable")[:world].tolist())
         assert all(len(hard & set(p.tolist())) == 1 for p in parts)
+        loads = [cost[p].sum() for p in parts]
+        assert max(loads) - min(loads) <= cost.max() + 1e-9
+
+
+def test_partition_balances_the_measured_iteration_counts_of_the_bench_sweep():
+    """tests/golden/sweep_iters_1024.json: iteration counts of the 1024-point bench sweep (scripts/sweep_iters.py, one B200).
+    Simulated slot scheduler (64 slots, a lock step costs a constant plus the active points): the slowest of 8 ranks stays
+    within 2 % of the mean, the work per rank within 1 %."""
+    import json
+    import os
+    d = np.array(json.load(open(os.path.join(os.path.dirname(__file__), "golden", "sweep_iters_1024.json"))))
+    om, it = d[:, 0] + 1j * d[:, 1], d[:, 2].astype(int)
+    assert np.corrcoef(shard.expected_cost(om), it)[0, 1] > 0.95
+
+    def makespan(idx, slots=64, c0=8.0):
+        queue = sorted(idx, key=lambda i: abs(om[i].imag))
+        live, t = [], 0.0
+        while queue or live:
+            while queue and len(live) < slots:
+                live.append(it[queue.pop(0)])
+            t += c0 + len(live)
+            live = [r - 1 for r in live if r > 1]
+        return t
+    parts = shard.partition(om, 8)
+    assert sorted(set(len(p) for p in parts)) == [128]
+    t = np.array([makespan(p.tolist()) for p in parts])
+    w = np.array([it[p].sum() for p in parts])
+    assert t.max() / t.mean() < 1.02 and w.max() / w.mean() < 1.01
 
 
 def test_two_rank_gloo_gather_reassembles_all_points():
