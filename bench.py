@@ -596,7 +596,7 @@ def ncu_capture(family, shells):
                              "fp64_flops_family_per_point_iteration": fam_flops / d.get("points", 8),
                              "tflops_under_ncu": top["fp64_thread_TFLOPs"], "limiter": lim, "limiter_pct_of_peak": units[lim],
                              "fp64_pipe_pct": top["fp64_pipe_pct"], "l1_throughput_pct": top["l1_throughput_pct"],
-                             "note": "the fully factorised kernels execute ~15x fewer FP64 operations than the reference's GEMM "
+                             "note": "the fully factorised kernels execute ~14x fewer FP64 operations than the reference's GEMM "
                                      "formulation counts (roofline.achieved uses that count, SURVEY 8d); they are FP64-FMA gather "
                                      "kernels bound by L1/shared-memory throughput, not by the FP64 pipe"}}
     except Exception:
