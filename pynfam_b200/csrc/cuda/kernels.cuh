@@ -301,6 +301,7 @@ struct MixArgs {
   double* vout;                   // [P][n]
   double* df;                     // [P][M][n]
   double* dv;                     // [P][M][n]
+  double* du;                     // [P][M][n]  dv + alpha df of the normalised history entries: the update streams ONE array
   double* gram;                   // [P][M][M]
   double* work;                   // [P][M]   df_i . vout
   double* gamma;                  // [P][M]

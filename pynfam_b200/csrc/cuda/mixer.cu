@@ -301,16 +301,23 @@ __global__ void __launch_bounds__(256) bro_update_kernel(MixArgs a) {
   const double vi = a.vin[(size_t)p * a.n + e];
   double* df = a.df + (size_t)p * a.M * a.n + e;
   double* dv = a.dv + (size_t)p * a.M * a.n + e;
+  double* du = a.du + (size_t)p * a.M * a.n + e;
   const double nm = a.normi[p];
   const double* gm = a.gamma + (size_t)p * a.M;
   double curv = alpha * vo;
+  // The combination dv_i + alpha df_i of every normalised history entry is kept as a third array, so this sweep -- the
+  // largest HBM stream of the iteration -- reads one array per entry instead of two; only the newest entry (ipos) is
+  // still raw: it is normalised here and its combination stored (the same expression, hence the same bits as before).
   for (int i = 0; i < iter_used; i++) {
-    double f = df[(size_t)i * a.n], v = dv[(size_t)i * a.n];
+    double t;
     if (i == ipos) {
-      f *= nm; v *= nm;
-      if (ipos != inext) { df[(size_t)i * a.n] = f; dv[(size_t)i * a.n] = v; }
+      const double f = df[(size_t)i * a.n] * nm, v = dv[(size_t)i * a.n] * nm;
+      t = v + alpha * f;
+      if (ipos != inext) { df[(size_t)i * a.n] = f; dv[(size_t)i * a.n] = v; du[(size_t)i * a.n] = t; }
+    } else {
+      t = du[(size_t)i * a.n];
     }
-    curv = curv - gm[i] * (v + alpha * f);
+    curv = curv - gm[i] * t;
   }
   df[(size_t)inext * a.n] = vo;
   dv[(size_t)inext * a.n] = vi;

@@ -976,7 +976,7 @@ extern "C" int pnfam_b200_solve(pnfam_b200_ctx* c, const pnfam_b200_operator* op
     const size_t pf_e = sf ? sf_pf_elems(c->sf.ngl, c->sf.kih) : pf_elems(c->ntiles);
     auto slot_doubles = [&]() {
       size_t d = 2 * n;                                                        // vin, vout
-      if (M > 0) d += 2 * (size_t)Malloc * n;                                  // Broyden history
+      if (M > 0) d += 3 * (size_t)Malloc * n;                                  // Broyden history: df, dv, dv + alpha df
       d += (size_t)Malloc * Malloc + 2 * (size_t)Malloc + (size_t)Malloc * broyden_slices(n) * 2;
       if (M > 64) d += (size_t)Malloc * (Malloc + 2);
       d += (size_t)nred * 2 + 4 + (size_t)nstr * 2 + strength_partial_elems(1, nstr);
@@ -1033,12 +1033,12 @@ extern "C" int pnfam_b200_solve(pnfam_b200_ctx* c, const pnfam_b200_operator* op
     }
 
     // ---- per-slot state -----------------------------------------------------------------------------
-    DBuf<double> vin, vout, df, dv, gram, work, gamma, dotpart, chol, red, d_si, d_normi, d_omega, d_str, d_strpart;
+    DBuf<double> vin, vout, df, dv, du, gram, work, gamma, dotpart, chol, red, d_si, d_normi, d_omega, d_str, d_strpart;
     DBuf<double> rsp, hsp, hqp, scratch, dd_rho, dd_kap, mf, pf, hpart, pk_rho, pk_kap;
     vin.alloc((size_t)S * n); vout.alloc((size_t)S * n);
     vin.zero(); vout.zero();
     // Broyden history: only slots that have been written are ever read (iter_used bounds every loop): no clearing
-    if (M > 0) { df.alloc((size_t)S * Malloc * n); dv.alloc((size_t)S * Malloc * n); }
+    if (M > 0) { df.alloc((size_t)S * Malloc * n); dv.alloc((size_t)S * Malloc * n); du.alloc((size_t)S * Malloc * n); }
     gram.alloc((size_t)S * Malloc * Malloc); work.alloc((size_t)S * Malloc); gamma.alloc((size_t)S * Malloc);
     gram.zero(); work.zero(); gamma.zero();
     dotpart.alloc((size_t)S * Malloc * broyden_slices(n) * 2);
@@ -1120,7 +1120,7 @@ extern "C" int pnfam_b200_solve(pnfam_b200_ctx* c, const pnfam_b200_operator* op
     ma.nvec = nvec; ma.nxy = nxy; ma.n = n; ma.M = Malloc; ma.Mmode = M; ma.alpha = (double)0.7f; ma.w0 = 0.01;
     ma.hqp = hqp.p; ma.fqp = od->gqp.p; ma.esum = od->esum.p; ma.tfac = c->use_diag ? od->tfac.p : nullptr;
     ma.omega = d_omega.p; ma.quench = no_residual ? 0.0 : quench;
-    ma.vin = vin.p; ma.vout = vout.p; ma.df = df.p; ma.dv = dv.p; ma.gram = gram.p; ma.work = work.p; ma.gamma = gamma.p;
+    ma.vin = vin.p; ma.vout = vout.p; ma.df = df.p; ma.dv = dv.p; ma.du = du.p; ma.gram = gram.p; ma.work = work.p; ma.gamma = gamma.p;
     ma.dotpart = dotpart.p; ma.nslices = broyden_slices(n); ma.chol = chol.p;
     ma.red = red.p; ma.nred = nred; ma.si = d_si.p; ma.normi = d_normi.p; ma.gqp = od->gqp.p; ma.nstr = nstr;
     ma.strength = d_str.p; ma.strpart = d_strpart.p; ma.active = d_active.p; ma.ctrl = d_ctrl.p; ma.slot_iter = d_slot_iter.p;
