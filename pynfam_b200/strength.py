@@ -77,14 +77,18 @@ class famContour(object):
         self._generateCtrData()
 
     def setHfbInterval(self, hfb, beta, shift=0.0):
-        """Interval [min(E_gs - buffer, 0), EQRPA_max] (+ shift) from a dict of HFB properties
-        (contour.py:147-205; zero-temperature branch)."""
+        """Interval [min(E_gs - buffer, 0), EQRPA_max] (+ shift) from a dict of HFB properties (contour.py:150-205).
+        Finite temperature: the strength at negative energies matters, the interval starts at -30 MeV, and for electron
+        capture (beta = 'c') it ends at +30 MeV instead of EQRPA_max (contour.py:184-198)."""
         Egs, eqrpamax = hfb["E_gs"], hfb["EQRPA_max"]
-        if hfb.get("ft_active", False):
-            raise NotImplementedError("finite temperature is outside this path")
         emin = min(Egs - self._settings["hfb_emin_buff"], 0.0)
+        emax = eqrpamax
+        if hfb.get("ft_active", False):
+            emin = -30.0
+            if beta == "c":
+                emax = 30.0
         self._settings["energy_min"] = emin + shift
-        self._settings["energy_max"] = eqrpamax + shift
+        self._settings["energy_max"] = emax + shift
         if np.isnan(Egs) or np.isnan(eqrpamax):
             self._settings["energy_min"] = self._settings["energy_max"] = 0.0
         self._generateCtrData()

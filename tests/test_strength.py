@@ -76,6 +76,12 @@ def test_line_contours_and_settings():
     assert c.nr_compute == 5 and abs(c.ctr_z[2].imag) <= 30 + 1e-12     # ellipse capped at max_height
     c.setHfbInterval({"E_gs": 1.2, "EQRPA_max": 7.0}, "-")
     assert (c.energy_min, c.energy_max) == (0.0, 7.0)
+    # finite temperature (contour.py:184-198; checked against the reference module in the build container): the interval
+    # starts at -30 MeV, and ends at +30 MeV for electron capture
+    c.setHfbInterval({"E_gs": 1.2, "EQRPA_max": 7.0, "ft_active": True, "temperature": 0.8}, "-", shift=0.25)
+    assert (c.energy_min, c.energy_max) == (-29.75, 7.25)
+    c.setHfbInterval({"E_gs": 1.2, "EQRPA_max": 7.0, "ft_active": True, "temperature": 0.8}, "c")
+    assert (c.energy_min, c.energy_max) == (-30.0, 30.0)
 
 
 def test_odd_point_count_symmetry_fill():
