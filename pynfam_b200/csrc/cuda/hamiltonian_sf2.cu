@@ -14,15 +14,20 @@
 //
 // (zr = row of the z table, one per distinct n_z of the basis) the work splits into a RADIAL part that touches every
 // matrix element once per Gauss-Laguerre node (O(nxy ngl) instead of the reference's O(nxy ngh ngl)) and a part on
-// (n_z, n_z') pairs that does not depend on the matrix dimension at all.  At 16 shells that is ~10x fewer executed
-// FP64 operations than the one-sided factorisation and ~25x fewer than the GEMM formulation.  All of it is FP64 FMA
-// work on small operands that live in L1/L2 (on B200 the DFMA and DMMA rates are the same 128 flop/clk/SM); the kernels
-// are plain one-thread-one-output loops without hand-over between warps:
-//   sf2_density_kernel  one CTA per (il, sweep ss', pass, omega): eight lanes own one (zr, zr') entry of Pi and stride
-//                       through the elements that feed it (rho is repacked in that order), then the CTA contracts Pi
-//                       with the z tables
-//   sf2_kappa_kernel    one CTA per (il, spin combination, pass, omega): a thread owns one (zr, zr') entry of kt
-//   sf2_radial_kernel   one thread per (row a, run of <= 8 columns with equal n_z) of the output block matrix
+// (n_z, n_z') pairs that does not depend on the matrix dimension at all.  At 16 shells the kernels of this file execute
+// 1.04 GFLOP per omega point and iteration (ncu, profiles/r02_ncu_kernels.csv) where the GEMM formulation counts 14.6.
+// All of it is FP64 FMA work on small operands that live in L1/L2 (on B200 the DFMA and DMMA rates are the same
+// 128 flop/clk/SM); the kernels are gather loops without hand-over between warps, bound by load latency and by L1 /
+// shared-memory wavefronts, not by the FP64 pipe -- what the measurements on B200 led to:
+//   sf2_density_kernel         one CTA per (il, sweep ss', pass, omega): eight lanes own one (zr, zr') entry of Pi and take the
+//                              columns that feed it round robin (rho is repacked in that order), the column loop software-
+//                              pipelined by hand (one L2 round trip per column and lane otherwise); then the CTA contracts
+//                              Pi with the z tables
+//   sf2_kappa_density4_kernel  the pairing density (one radial factor): four il per CTA share the element loads
+//   sf2_kappa_kernel           one CTA per (il, spin combination, pass, omega): a thread owns the kt entries (zr, 2 zr');
+//                              z tables in both index orders (bank conflicts), kt stored [jj][zr'][zr]
+//   sf2_radial_kernel          one thread per (two rows a of equal n_z, run of <= 8 columns with equal n_z) of the output
+//                              block matrix; component-major radial factors (consecutive lanes = consecutive rows)
 // Sums run in a fixed order (no atomics): results are reproducible run to run.
 #include <algorithm>
 #include <cstdlib>
