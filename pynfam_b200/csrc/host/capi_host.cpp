@@ -67,7 +67,7 @@ int pnfam_problem_scalar(const pnfam_problem* h, const char* name, double* out) 
       {"skip_residual", x.skip_residual},
       {"cdrho", x.cdrho}, {"ctau", x.ctau}, {"ctj0", x.ctj0}, {"ctj1", x.ctj1}, {"ctj2", x.ctj2}, {"crdj", x.crdj},
       {"cds", x.cds}, {"ct", x.ct}, {"cj", x.cj}, {"cgs", x.cgs}, {"cf", x.cf}, {"csdj", x.csdj},
-      {"cr0", x.cr0}, {"crr", x.crr}, {"cs0", x.cs0}, {"csr", x.csr}, {"sigma_r", x.sigma_r},
+      {"cr0", x.cr0}, {"crr", x.crr}, {"cs0", x.cs0}, {"csr", x.csr}, {"sigma_r", x.sigma_r}, {"sigma_s", x.sigma_s}, {"sigma_pair", x.sigma_pair},
       {"cpair0", x.cpair0}, {"cpairr", x.cpairr}, {"cspair0", x.cspair0}, {"cspairr", x.cspairr},
       {"real_eqrpa", in.real_eqrpa}, {"imag_eqrpa", in.imag_eqrpa}, {"max_iter", in.max_iter},
       {"broyden_history_size", in.broyden_history_size}, {"convergence_epsilon", in.convergence_epsilon},

@@ -251,7 +251,7 @@ const Skyrme kSkyrme[] = {
 };
 }  // namespace
 
-Interaction Interaction::build(const FamInput& in, const FamBasis& b) {
+Interaction Interaction::build(const FamInput& in, const FamBasis& b, const std::string& rundir) {
   Interaction x;
   const int nghl = b.nghl;
   x.crho.assign(nghl, 0.0); x.cs = x.crho; x.cpair = x.crho; x.cspair = x.crho;
@@ -259,8 +259,34 @@ Interaction Interaction::build(const FamInput& in, const FamBasis& b) {
   while (!nm.empty() && nm.front() == ' ') nm.erase(nm.begin());
   x.name = nm;
   if (nm == "NONE") { x.skip_residual = true; return x; }
-  if (nm.rfind("FILE:", 0) == 0) throw std::runtime_error("custom interaction files (FILE:) are not supported");
+  const bool from_file = nm.rfind("FILE:", 0) == 0;
+  if (from_file) {
+    // custom coupling constants (pnfam_interaction.f90:303-331): namelist &custom_interaction of the named file; none of
+    // the built-in post-processing (J^2 terms, gauge invariance, pairing from vpair_*, overrides) applies (:126-129)
+    std::string file = in.interaction_name;
+    while (!file.empty() && file.front() == ' ') file.erase(file.begin());
+    file = file.substr(5);
+    while (!file.empty() && file.front() == ' ') file.erase(file.begin());
+    while (!file.empty() && file.back() == ' ') file.pop_back();
+    x.name = "FILE:" + file;
+    const std::string path = (!file.empty() && file[0] == '/') ? file : rundir + "/" + file;
+    {
+      std::FILE* probe = std::fopen(path.c_str(), "r");
+      if (!probe) throw std::runtime_error("could not open interaction file \"" + file + "\".");
+      std::fclose(probe);
+    }
+    Namelist nl = Namelist::parse_file(path);
+    if (nl.groups.find("custom_interaction") == nl.groups.end())
+      throw std::runtime_error("could not read interaction file \"" + file + "\".");
+    auto g = [&](const char* k) { return nl.get_double("custom_interaction", k, 0.0); };
+    x.cr0 = g("cr0"); x.crr = g("crr"); x.sigma_r = g("sigma_r"); x.cdrho = g("cdrho"); x.ctau = g("ctau");
+    x.ctj0 = g("ctj0"); x.ctj1 = g("ctj1"); x.ctj2 = g("ctj2"); x.crdj = g("crdj");
+    x.cs0 = g("cs0"); x.csr = g("csr"); x.sigma_s = g("sigma_s"); x.cds = g("cds"); x.ct = g("ct"); x.cj = g("cj");
+    x.csdj = g("csdj"); x.cf = g("cf"); x.cgs = g("cgs");
+    x.cpair0 = g("cpair0"); x.cpairr = g("cpairr"); x.cspair0 = g("cspair0"); x.cspairr = g("cspairr"); x.sigma_pair = g("sigma_pair");
+  }
   const Skyrme* sk = nullptr;
+  if (!from_file) {
   for (const auto& e : kSkyrme) {
     if (nm == e.key || (e.key2[0] && nm == e.key2)) sk = &e;
   }
@@ -318,6 +344,7 @@ Interaction Interaction::build(const FamInput& in, const FamBasis& b) {
       *ovt[i] = in.override_val[i];
       x.notes.push_back(std::string(" [!] Coupling constant ") + ovn[i] + " has been overridden manually");
     }
+  }   // built-in functional
   // self-consistency check against the HFBTHO couplings (:827-941), tolerance 5e-12
   if (in.require_self_consistency) {
     const double tol = 5.0e-12;
@@ -332,6 +359,13 @@ Interaction Interaction::build(const FamInput& in, const FamBasis& b) {
     if (std::fabs(x.cspair0) > 0.0)
       fail = fail || std::fabs(b.hfb_alpha_pair[0] + x.cspairr * std::pow(b.rho_nm, x.sigma_pair) / x.cspair0) > tol;
     if (fail) throw std::runtime_error("FAM couplings are not self-consistent with the HFBTHO functional");
+  }
+  // gauge invariance (check_gauge_invariance :777-822), tolerance 1e-10
+  if (in.require_gauge_invariance) {
+    const double tol = 1.0e-10;
+    if (std::fabs(x.ctau + x.cj) > tol || std::fabs(x.crdj - x.csdj) > tol || std::fabs(3 * x.ctj0 + x.ct + 2 * x.cf) > tol ||
+        std::fabs(4 * x.ctj1 + 2 * x.ct - x.cf) > tol || std::fabs(2 * x.ctj2 + 2 * x.ct + x.cf) > tol)
+      throw std::runtime_error("gauge invariance was requested, but is not fulfilled.");
   }
   for (int r = 0; r < nghl; r++) {
     const double rho = b.rho_n[r] + b.rho_p[r];

@@ -98,7 +98,8 @@ struct Interaction {
   std::vector<double> crho, cs, cpair, cspair;  // (nghl)
   std::vector<std::string> notes;               // "[!] ..." lines for the log
 
-  static Interaction build(const FamInput& in, const FamBasis& b);
+  // rundir: where a `FILE:<name>` interaction file is looked up (the reference opens it relative to its working directory)
+  static Interaction build(const FamInput& in, const FamBasis& b, const std::string& rundir = ".");
 };
 
 struct ExtField {

@@ -69,7 +69,7 @@ std::unique_ptr<Problem> Problem::build(const std::string& rundir, const FamInpu
   p->in = input;
   p->nuc = nuc ? nuc : Nucleus::load(d);
   FamBasis& b = p->nuc->basis;
-  p->inter = Interaction::build(p->in, b);
+  p->inter = Interaction::build(p->in, b, d);
   const FamInput& in = p->in;
   // external field (setup_extfield, pnfam_solver.f90:556-654)
   const int mode = in.two_body_current_mode;

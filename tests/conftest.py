@@ -36,7 +36,7 @@ def stage_point(case, op, idx, wd, name="x.in", patch=None):
         if not os.path.isfile(os.path.join(wd, f)):
             shutil.copy(os.path.join(GOLDEN, case, f), wd)
     for f in os.listdir(os.path.join(GOLDEN, case)):
-        if f.endswith(".tbc") and not os.path.isfile(os.path.join(wd, f)):
+        if (f.endswith(".tbc") or f == "custom_edf.dat") and not os.path.isfile(os.path.join(wd, f)):
             shutil.copy(os.path.join(GOLDEN, case, f), wd)
     pt = load_points(case)[op][idx]
     nml = re.sub(r"two_body_current_mode\s*=\s*114", "two_body_current_mode = 0", pt["namelist"])

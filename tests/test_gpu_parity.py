@@ -63,6 +63,8 @@ CASES = [
     ("Gd162_finiteT_6sh", "RS1-K1", 0),
     ("Gd162_finiteT_6sh", "RS0-K0", 0),
     ("Gd162_finiteT_6sh", "GT-K0", 1),   # interrupted at max_iter = 5
+    ("S40_custom_interaction", "GT-K0", 0),   # couplings from a file (interaction_name = 'FILE:custom_edf.dat')
+    ("S40_custom_interaction", "F-K0", 0),
 ]
 
 

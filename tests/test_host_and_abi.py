@@ -147,6 +147,16 @@ def test_bad_inputs_fail_cleanly(tmp_path):
         host.Problem(str(tmp_path), "x.in")
     with pytest.raises(host.PnfamError):
         host.Problem(str(tmp_path / "nowhere"), "x.in")
+    # couplings from a file (pnfam_interaction.f90:303-331): a missing file and a gauge-invariance violation are errors
+    stage_point("S40_custom_interaction", "GT-K0", 0, str(tmp_path / "c"))
+    os.remove(str(tmp_path / "c" / "custom_edf.dat"))
+    with pytest.raises(host.PnfamError, match="could not open interaction file"):
+        host.Problem(str(tmp_path / "c"), "x.in")
+    stage_point("S40_custom_interaction", "GT-K0", 0, str(tmp_path / "d"))
+    f = tmp_path / "d" / "custom_edf.dat"
+    f.write_text(re.sub(r"cj\s*=\s*\S+", "cj = 1.0", f.read_text()))
+    with pytest.raises(host.PnfamError, match="gauge invariance"):
+        host.Problem(str(tmp_path / "d"), "x.in")
 
 
 def test_drop_in_exe_without_gpu_reports_failure_the_reference_way(tmp_path):

@@ -22,6 +22,8 @@ CASES = [
     ("Gd163_blocked_6sh", "GT-K0", 0),   # odd-A, blocked 5/2-[523] neutron: P,Q quadrants + statistical factors
     ("Gd162_finiteT_6sh", "GT-K0", 0),   # finite temperature (T = 0.8 MeV): thermal occupations, P,Q quadrants
     ("Gd162_finiteT_6sh", "RS1-K1", 0),
+    ("S40_custom_interaction", "GT-K1", 0),   # couplings from a file (interaction_name = 'FILE:custom_edf.dat')
+    ("S40_custom_interaction", "RS1-K0", 0),
 ]
 
 
