@@ -11,6 +11,8 @@ Cases (BASELINE.json configs[2..4]; every point runs to convergence, max_iter = 
                on the 60-node CIRCLE contour of scripts/full_contour.py -> Gd162_SKOP_20sh/prod_points.json
   gd163_16sh   163Gd, 5/2-[523] blocked, 16 shells (configs[2]): hfbtho_main restarted from the even core with
                neutron_blocking = 5,-1,5,2,3, then GT K=0/1 and RS1 points -> Gd163_blocked_16sh/
+  gd162_ft_16sh 162Gd at T = 0.8 MeV, 16 shells (finite-temperature HFB restarted from the zero-temperature solution), GT,
+               F, RS0, RS1 points -> Gd162_finiteT_16sh/
   gd162_12sh / gd162_24sh   HFB ground state at 12 / 24 shells (same recipe as make_gd162_16sh.py) and GT K=0 sweep
                points -> Gd162_SKOP_{12,24}sh/
   loose_6sh    the ill-conditioned points of the reference's 6-shell golden trees (|Im omega| < 0.5 or >= 25
@@ -155,6 +157,36 @@ def gd163_16sh(jobs):
     farm(d, tasks, jobs, "points.json", NOTE % "gd163_16sh")
 
 
+def hfb_finite_temperature(dst, core, jobs, temperature):
+    """162Gd at finite temperature, restarted from the zero-temperature solution in `core`."""
+    os.makedirs(dst, exist_ok=True)
+    if os.path.isfile(os.path.join(dst, "hfbtho_output.hel")):
+        return
+    wd = tempfile.mkdtemp()
+    s = open(os.path.join(core, "hfbtho_NAMELIST.dat")).read()
+    s, n1 = re.subn(r"restart_file\s*=\s*-?\d+", "restart_file = -1", s)
+    s, n2 = re.subn(r"set_temperature\s*=\s*\.false\.", "set_temperature = .true.", s)
+    s, n3 = re.subn(r"temperature\s*=\s*0\.0", "temperature = %r" % temperature, s)
+    assert n1 == 1 and n2 == 1 and n3 == 1
+    open(os.path.join(wd, "hfbtho_NAMELIST.dat"), "w").write(s)
+    shutil.copy(os.path.join(core, "hfbtho_output.hel"), wd)
+    os.chmod(os.path.join(wd, "hfbtho_output.hel"), 0o644)
+    out, t = refrun.run_hfbtho(wd, threads=jobs, timeout=4 * 3600)
+    assert "iteration converged" in out, out[-3000:]
+    print("hfbtho_main T = %g: %.0f s" % (temperature, t), flush=True)
+    for f in ("hfbtho_NAMELIST.dat", "hfbtho_output.hel"):
+        shutil.copy(os.path.join(wd, f), dst)
+
+
+def gd162_finite_temperature_16sh(jobs):
+    """162Gd at T = 0.8 MeV, 16 shells: thermal occupations, P,Q quadrants and T factors at the bench basis size."""
+    d = os.path.join(HERE, "Gd162_finiteT_16sh")
+    hfb_finite_temperature(d, os.path.join(HERE, "Gd162_SKOP_16sh"), jobs, 0.8)
+    tasks = [("GT", 0, 1.0 + 0.5j, 300, {}), ("GT", 1, 3.0 + 1.0j, 300, {}), ("RS1", 1, 4.0 + 1.5j, 300, {}),
+             ("GT", 0, 6.0 + 0.25j, 300, {}), ("F", 0, 2.5 - 2.0j, 300, {}), ("RS0", 0, 5.0 + 3.0j, 300, {})]
+    farm(d, tasks, jobs, "points.json", NOTE % "gd162_ft_16sh")
+
+
 def gd162_small_large(shells, jobs, idx):
     d = os.path.join(HERE, "Gd162_SKOP_%dsh" % shells)
     hfb_ground_state(d, shells, jobs)
@@ -236,6 +268,8 @@ def main():
         gd162_20sh(a.jobs)
     elif a.case == "gd163_16sh":
         gd163_16sh(a.jobs)
+    elif a.case == "gd162_ft_16sh":
+        gd162_finite_temperature_16sh(a.jobs)
     elif a.case == "gd162_12sh":
         gd162_small_large(12, a.jobs, [0, 63, 4, 10, 16, 22, 27, 30, 31, 32])
     elif a.case == "gd162_24sh":

@@ -80,7 +80,10 @@ def check_fixture(gpu, case, fname, wd, separable=True, slots=0, expect_efa=None
                 # The stopping rule max|dX| < eps triggered a step or two apart (only tolerated in the ill-conditioned class).
                 # Stopped one step earlier: the state must equal the reference's OWN state at that iteration (its trace
                 # prints 10 digits).  Otherwise: within the reference's own terminal movement of S (conftest.terminal_scatter).
-                assert loose and abs(it_gpu - it_ref) <= 2, (op, i, it_gpu, it_ref)
+                # (a point within 0.5 MeV of the real axis belongs to that class whatever its iteration count: at
+                # Gd162 T=0.8 GT-K0 w = 6 + 0.25i the reference's residual reads 1.8e-7, 1.9e-7, 6.5e-8 over its last three steps)
+                near_axis = abs(omega_of(pt["namelist"]).imag) < 0.5
+                assert (loose or near_axis) and abs(it_gpu - it_ref) <= 2, (op, i, it_gpu, it_ref)
                 tr = {t[0]: complex(t[3], t[4]) for t in pt["trace"]}
                 err = abs(r["strength"][i, 0] - s_ref) / abs(s_ref)
                 if it_gpu == it_ref - 1 and abs(r["strength"][i, 0] - tr[it_gpu]) / abs(s_ref) < LOOSE_TOL:
@@ -130,6 +133,19 @@ def test_gd163_blocked_16_shells(gpu, tmp_path, separable):
     """configs[2] at its stated size: odd-A equal filling (8 amplitude vectors) on the 40-point-grid kernels."""
     n, _ = check_fixture(gpu, "Gd163_blocked_16sh", "points.json", str(tmp_path), separable=separable, expect_efa=True)
     assert n >= 4
+
+
+def test_gd162_finite_temperature_16_shells(gpu, tmp_path):
+    """Finite temperature (T = 0.8 MeV) at the bench basis size: thermal occupations, 8 amplitude vectors (X, Y, P, Q)
+    and T factors on the factorised kernels; HFB solution and known answers from the reference's executables
+    (tests/golden/make_production.py gd162_ft_16sh)."""
+    path = os.path.join(GOLDEN, "Gd162_finiteT_16sh", "points.json")
+    if not os.path.isfile(path):
+        pytest.skip("fixture Gd162_finiteT_16sh not generated")
+    n, _ = check_fixture(gpu, "Gd162_finiteT_16sh", "points.json", str(tmp_path), expect_efa=False)
+    assert n >= 4
+    stage("Gd162_finiteT_16sh", json.load(open(path))["points"]["GT-K0"][0]["namelist"], str(tmp_path / "p"), "x.in")
+    assert host.Problem(str(tmp_path / "p"), "x.in").iscalar("ft_active") == 1
 
 
 def test_gd162_12_shells(gpu, tmp_path):
