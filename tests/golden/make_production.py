@@ -13,6 +13,7 @@ Cases (BASELINE.json configs[2..4]; every point runs to convergence, max_iter = 
                neutron_blocking = 5,-1,5,2,3, then GT K=0/1 and RS1 points -> Gd163_blocked_16sh/
   gd162_ft_16sh 162Gd at T = 0.8 MeV, 16 shells (finite-temperature HFB restarted from the zero-temperature solution), GT,
                F, RS0, RS1 points -> Gd162_finiteT_16sh/
+  gd162_2bc_16sh closed-form two-body currents (nuclear matter + LDA modes) at 16 shells -> Gd162_SKOP_16sh/tbc_points.json
   gd162_12sh / gd162_24sh   HFB ground state at 12 / 24 shells (same recipe as make_gd162_16sh.py) and GT K=0 sweep
                points -> Gd162_SKOP_{12,24}sh/
   loose_6sh    the ill-conditioned points of the reference's 6-shell golden trees (|Im omega| < 0.5 or >= 25
@@ -102,6 +103,11 @@ def run_point(case_dir, op, k, w, max_iter, extra):
     refrun.stage(wd, case_dir)
     name = "%s-K%d" % (op, k)
     nml = FAM.format(name=name, re=repr(float(w.real)), im=repr(float(w.imag)), op=op, k=k, max_iter=max_iter)
+    extra = dict(extra)
+    mode = extra.pop("two_body_current_mode", 0)
+    if mode:
+        nml = nml.replace("two_body_current_mode = 0", "two_body_current_mode = %d" % mode)
+        extra["mode"] = mode
     open(os.path.join(wd, name + ".in"), "w").write(nml)
     dat, wall, out = refrun.run_pnfam(wd, name + ".in", threads=1, timeout=6 * 3600)
     shutil.rmtree(wd, ignore_errors=True)
@@ -187,6 +193,16 @@ def gd162_finite_temperature_16sh(jobs):
     farm(d, tasks, jobs, "points.json", NOTE % "gd162_ft_16sh")
 
 
+def gd162_2bc_16sh(jobs):
+    """BASELINE configs[1] at the bench basis size: operators with the closed-form (nuclear matter + LDA) two-body
+    currents at 16 shells -- the mode digits of tests/golden/make_2bc_modes.py."""
+    d = os.path.join(HERE, "Gd162_SKOP_16sh")
+    tasks = [("GT", 0, 2.0 + 1.0j, 300, {"two_body_current_mode": 131100}), ("GT", 1, 4.0 + 1.5j, 300, {"two_body_current_mode": 121100}),
+             ("RS0", 0, 5.0 + 2.0j, 300, {"two_body_current_mode": 121211}), ("P", 0, 3.0 + 1.0j, 300, {"two_body_current_mode": 221110}),
+             ("PS0", 0, 6.0 + 2.5j, 300, {"two_body_current_mode": 121101})]
+    farm(d, tasks, jobs, "tbc_points.json", NOTE % "gd162_2bc_16sh")
+
+
 def gd162_small_large(shells, jobs, idx):
     d = os.path.join(HERE, "Gd162_SKOP_%dsh" % shells)
     hfb_ground_state(d, shells, jobs)
@@ -270,6 +286,8 @@ def main():
         gd163_16sh(a.jobs)
     elif a.case == "gd162_ft_16sh":
         gd162_finite_temperature_16sh(a.jobs)
+    elif a.case == "gd162_2bc_16sh":
+        gd162_2bc_16sh(a.jobs)
     elif a.case == "gd162_12sh":
         gd162_small_large(12, a.jobs, [0, 63, 4, 10, 16, 22, 27, 30, 31, 32])
     elif a.case == "gd162_24sh":

@@ -148,6 +148,13 @@ def test_gd162_finite_temperature_16_shells(gpu, tmp_path):
     assert host.Problem(str(tmp_path / "p"), "x.in").iscalar("ft_active") == 1
 
 
+def test_gd162_16_shells_two_body_currents(gpu, tmp_path):
+    """BASELINE configs[1] at the bench basis size: GT, RS0, P, PS0 with the closed-form (nuclear matter + LDA) two-body
+    currents at 16 shells, known answers from the reference binary (tests/golden/make_production.py gd162_2bc_16sh)."""
+    n, _ = check_fixture(gpu, "Gd162_SKOP_16sh", "tbc_points.json", str(tmp_path))
+    assert n >= 5
+
+
 def test_gd162_12_shells(gpu, tmp_path):
     check_fixture(gpu, "Gd162_SKOP_12sh", "points.json", str(tmp_path))
 
