@@ -83,7 +83,7 @@ def parity_sample(all_strength, conv):
     for the same sweep points (tests/golden/Gd162_SKOP_<n>sh/prod_points.json or points.json, made by
     tests/golden/make_production.py).  Returns (max relative error on S and the cross-terms, points compared)."""
     import numpy as np
-    for fn in ("prod_points.json", "points.json"):
+    for fn in ("prod_points.json", "sweep_points.json", "points.json"):
         path = os.path.join(case_dir(), fn)
         if not os.path.isfile(path):
             continue

@@ -13,6 +13,7 @@ Cases (BASELINE.json configs[2..4]; every point runs to convergence, max_iter = 
                neutron_blocking = 5,-1,5,2,3, then GT K=0/1 and RS1 points -> Gd163_blocked_16sh/
   gd162_ft_16sh 162Gd at T = 0.8 MeV, 16 shells (finite-temperature HFB restarted from the zero-temperature solution), GT,
                F, RS0, RS1 points -> Gd162_finiteT_16sh/
+  gd162_20sh_sweep six points of bench.py's contour sweep at 20 shells -> Gd162_SKOP_20sh/sweep_points.json
   gd162_2bc_16sh closed-form two-body currents (nuclear matter + LDA modes) at 16 shells -> Gd162_SKOP_16sh/tbc_points.json
   gd162_12sh / gd162_24sh   HFB ground state at 12 / 24 shells (same recipe as make_gd162_16sh.py) and GT K=0 sweep
                points -> Gd162_SKOP_{12,24}sh/
@@ -193,6 +194,15 @@ def gd162_finite_temperature_16sh(jobs):
     farm(d, tasks, jobs, "points.json", NOTE % "gd162_ft_16sh")
 
 
+def gd162_20sh_sweep(jobs):
+    """Points of bench.py's contour sweep at 20 shells (bench.py --shells 20 compares its strengths with them outside the
+    timed region) -> Gd162_SKOP_20sh/sweep_points.json"""
+    d = os.path.join(HERE, "Gd162_SKOP_20sh")
+    om = sweep(64)
+    tasks = [("GT", 0, om[i], 300, {"sweep_index": i}) for i in (2, 11, 20, 26, 29, 31)]
+    farm(d, tasks, jobs, "sweep_points.json", NOTE % "gd162_20sh_sweep")
+
+
 def gd162_2bc_16sh(jobs):
     """BASELINE configs[1] at the bench basis size: operators with the closed-form (nuclear matter + LDA) two-body
     currents at 16 shells -- the mode digits of tests/golden/make_2bc_modes.py."""
@@ -286,6 +296,8 @@ def main():
         gd163_16sh(a.jobs)
     elif a.case == "gd162_ft_16sh":
         gd162_finite_temperature_16sh(a.jobs)
+    elif a.case == "gd162_20sh_sweep":
+        gd162_20sh_sweep(a.jobs)
     elif a.case == "gd162_2bc_16sh":
         gd162_2bc_16sh(a.jobs)
     elif a.case == "gd162_12sh":

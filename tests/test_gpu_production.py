@@ -155,6 +155,13 @@ def test_gd162_16_shells_two_body_currents(gpu, tmp_path):
     assert n >= 5
 
 
+def test_gd162_20_shells_sweep_points(gpu, tmp_path):
+    """Six converged points of bench.py's contour sweep at 20 shells (18 to 54 iterations), the ones `bench.py --shells 20`
+    checks its strengths against."""
+    n, _ = check_fixture(gpu, "Gd162_SKOP_20sh", "sweep_points.json", str(tmp_path))
+    assert n >= 6
+
+
 def test_gd162_12_shells(gpu, tmp_path):
     check_fixture(gpu, "Gd162_SKOP_12sh", "points.json", str(tmp_path))
 
