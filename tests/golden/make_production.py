@@ -15,6 +15,7 @@ Cases (BASELINE.json configs[2..4]; every point runs to convergence, max_iter = 
                F, RS0, RS1 points -> Gd162_finiteT_16sh/
   gd162_20sh_sweep six points of bench.py's contour sweep at 20 shells -> Gd162_SKOP_20sh/sweep_points.json
   gd162_2bc_16sh closed-form two-body currents (nuclear matter + LDA modes) at 16 shells -> Gd162_SKOP_16sh/tbc_points.json
+  gd162_ft_20sh the same at 20 shells -> Gd162_finiteT_20sh/
   gd162_12sh / gd162_24sh   HFB ground state at 12 / 24 shells (same recipe as make_gd162_16sh.py) and GT K=0 sweep
                points -> Gd162_SKOP_{12,24}sh/
   loose_6sh    the ill-conditioned points of the reference's 6-shell golden trees (|Im omega| < 0.5 or >= 25
@@ -213,6 +214,14 @@ def gd162_2bc_16sh(jobs):
     farm(d, tasks, jobs, "tbc_points.json", NOTE % "gd162_2bc_16sh")
 
 
+def gd162_finite_temperature_20sh(jobs):
+    """162Gd at T = 0.8 MeV, 20 shells (the basis of the north-star run)."""
+    d = os.path.join(HERE, "Gd162_finiteT_20sh")
+    hfb_finite_temperature(d, os.path.join(HERE, "Gd162_SKOP_20sh"), jobs, 0.8)
+    tasks = [("GT", 0, 1.0 + 0.5j, 300, {}), ("GT", 1, 3.0 + 1.0j, 300, {}), ("RS1", 1, 4.0 + 1.5j, 300, {}), ("RS0", 0, 5.0 + 3.0j, 300, {})]
+    farm(d, tasks, jobs, "points.json", NOTE % "gd162_ft_20sh")
+
+
 def gd162_small_large(shells, jobs, idx):
     d = os.path.join(HERE, "Gd162_SKOP_%dsh" % shells)
     hfb_ground_state(d, shells, jobs)
@@ -300,6 +309,8 @@ def main():
         gd162_20sh_sweep(a.jobs)
     elif a.case == "gd162_2bc_16sh":
         gd162_2bc_16sh(a.jobs)
+    elif a.case == "gd162_ft_20sh":
+        gd162_finite_temperature_20sh(a.jobs)
     elif a.case == "gd162_12sh":
         gd162_small_large(12, a.jobs, [0, 63, 4, 10, 16, 22, 27, 30, 31, 32])
     elif a.case == "gd162_24sh":

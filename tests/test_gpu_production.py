@@ -135,16 +135,18 @@ def test_gd163_blocked_16_shells(gpu, tmp_path, separable):
     assert n >= 4
 
 
-def test_gd162_finite_temperature_16_shells(gpu, tmp_path):
-    """Finite temperature (T = 0.8 MeV) at the bench basis size: thermal occupations, 8 amplitude vectors (X, Y, P, Q)
-    and T factors on the factorised kernels; HFB solution and known answers from the reference's executables
-    (tests/golden/make_production.py gd162_ft_16sh)."""
-    path = os.path.join(GOLDEN, "Gd162_finiteT_16sh", "points.json")
+@pytest.mark.parametrize("shells", [16, 20])
+def test_gd162_finite_temperature_production_sizes(gpu, tmp_path, shells):
+    """Finite temperature (T = 0.8 MeV) at the bench and north-star basis sizes: thermal occupations, 8 amplitude vectors
+    (X, Y, P, Q) and T factors on the factorised kernels; HFB solutions and known answers from the reference's
+    executables (tests/golden/make_production.py gd162_ft_16sh / gd162_ft_20sh)."""
+    case = "Gd162_finiteT_%dsh" % shells
+    path = os.path.join(GOLDEN, case, "points.json")
     if not os.path.isfile(path):
-        pytest.skip("fixture Gd162_finiteT_16sh not generated")
-    n, _ = check_fixture(gpu, "Gd162_finiteT_16sh", "points.json", str(tmp_path), expect_efa=False)
+        pytest.skip("fixture %s not generated" % case)
+    n, _ = check_fixture(gpu, case, "points.json", str(tmp_path), expect_efa=False)
     assert n >= 4
-    stage("Gd162_finiteT_16sh", json.load(open(path))["points"]["GT-K0"][0]["namelist"], str(tmp_path / "p"), "x.in")
+    stage(case, json.load(open(path))["points"]["GT-K0"][0]["namelist"], str(tmp_path / "p"), "x.in")
     assert host.Problem(str(tmp_path / "p"), "x.in").iscalar("ft_active") == 1
 
 
