@@ -371,9 +371,10 @@ void launch_density_sf2(const HamArgs& a, cudaStream_t stream) {
   if (a.nactive <= 0) return;
   const SfDev& S = a.sf;
   const int nzr = a.sf2.nzr, npair = nzr * nzr;
-  // PNFAM_B200_DENSITY_ILS=2: two il per CTA (512 threads, one CTA per SM) when its two sets of Pi arrays fit -- measured
-  // slower than one il per CTA on B200 (2.72 against 2.52 ms per launch at 16 shells, 64 points), so it is off by default
-  static const int ils_knob = getenv("PNFAM_B200_DENSITY_ILS") ? atoi(getenv("PNFAM_B200_DENSITY_ILS")) : 1;
+  // two il per CTA (512 threads, one CTA per SM) when its two sets of Pi arrays fit: with the column loop software-
+  // pipelined the shared element fetches pay (1.93 against 2.18 ms per launch at 16 shells, 64 points; before the
+  // pipelining the variant was slower).  PNFAM_B200_DENSITY_ILS=1 keeps one il per CTA.
+  static const int ils_knob = getenv("PNFAM_B200_DENSITY_ILS") ? atoi(getenv("PNFAM_B200_DENSITY_ILS")) : 2;
   const size_t zbytes = (size_t)2 * nzr * S.ngh * 8;
   const int ils = (ils_knob >= 2 && (size_t)18 * npair * 16 + zbytes <= 220 * 1024) ? 2 : 1;
   const size_t sm0 = (size_t)ils * 9 * npair * 16 + zbytes, sm4 = (size_t)4 * npair * 16 + (size_t)nzr * S.ngh * 8;
