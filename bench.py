@@ -570,7 +570,7 @@ def run_full_contour(args):
         dist.destroy_process_group()
 
 
-NCU_FAMILY = {"density": ["sf2_density_kernel<0, 1>", "sf2_kappa_density4_kernel", "sf2_pack_kernel"],
+NCU_FAMILY = {"density": ["sf2_density_kernel<0, 2>", "sf2_density_kernel<0, 1>", "sf2_kappa_density4_kernel", "sf2_pack_kernel"],
               "projection": ["sf2_kappa_kernel<0>", "sf2_kappa_kernel<1>", "sf2_radial_kernel<0>", "sf2_radial_kernel<1>"]}
 
 
@@ -584,7 +584,7 @@ def ncu_capture(family, shells):
         if shells != d.get("shells", 16):
             return None
         ks = {k["kernel"]: k for k in d["kernels"]}
-        top = ks[NCU_FAMILY[family][0]]
+        top = ks[[n for n in NCU_FAMILY[family] if n in ks][0]]       # the rho density runs as <0, 2> (two il per CTA) or <0, 1>
         launches = {"density": 1.0, "projection": 2.0}      # radial kernels launch once per pass, the others once for both
         fam_flops = sum(ks[n]["fp64_thread_flops_per_launch"] * (launches[family] if "radial" in n else 1.0) for n in NCU_FAMILY[family] if n in ks)
         units = {"l1": top["l1_throughput_pct"], "fp64_pipe": top["fp64_pipe_pct"], "l2": top["l2_throughput_pct"], "dram": top["dram_throughput_pct"],
