@@ -23,13 +23,17 @@ extern "C" {
  *              get_raw_hfb_solution           exes/pnfam/hfbtho_solution.f90:137-395,
  *              HFBTHO_program (0 iterations)  exes/pnfam/hfbtho_interface.f90:20-226,
  *              init_interaction               exes/pnfam/pnfam_interaction.f90:90-260,
- *              init_external_field            exes/pnfam/pnfam_extfield.f90:37-108.
+ *              init_external_field            exes/pnfam/pnfam_extfield.f90:37-108,
+ *              effective_2bc_extfield         exes/pnfam/pnfam_extfield_2bc.f90:26-465 (+ write_tbc / read_tbc,
+ *                                             exes/pnfam/pnfam_storage.f90:488-727).
  * ---------------------------------------------------------------------------------------------- */
 typedef struct pnfam_problem pnfam_problem;
 
 /* rundir holds hfbtho_NAMELIST.dat + hfbtho_output.hel (+ <name>.tbc); namelist_file is the pnFAM
  * namelist (relative to rundir unless absolute) -- the argv[1] of pnfam_main.x
- * (exes/pnfam/pnfam_setup.f90:214-250). */
+ * (exes/pnfam/pnfam_setup.f90:214-250).  Full-FAM two-body currents (two_body_current_mode = x1x1xx): <name>.tbc is read
+ * when it fits the calculation, otherwise the field is computed and the file (re)written in the reference's record
+ * layout, as the reference does (PNFAM_B200_NO_TBC_GENERATOR=1: fail instead). */
 int pnfam_problem_create(const char* rundir, const char* namelist_file, pnfam_problem** out, char* err, int errlen);
 /* Same, but reuses the HFB reconstruction of an existing problem (same rundir / nucleus). */
 int pnfam_problem_create_shared(const pnfam_problem* nucleus_of, const char* rundir, const char* namelist_file,

@@ -690,7 +690,7 @@ std::vector<ExtField> make_crossterms(const ExtField& op, const FieldProvider& f
 
 bool read_tbc(const std::string& path, const FamBasis& b, const FamInput& in, ExtField& f, std::string& why) {
   std::ifstream probe(path, std::ios::binary);
-  if (!probe) { why = "cannot open " + path + " (computing the two-body-current field from scratch is not supported)"; return false; }
+  if (!probe) { why = "cannot open " + path; return false; }
   probe.close();
   FortUnformatted fu(path);
   FortRecord r;
@@ -736,7 +736,8 @@ bool read_tbc(const std::string& path, const FamBasis& b, const FamInput& in, Ex
   return found;
 }
 
-void apply_two_body_current_gt(const std::string& tbc_path, const FamBasis& b, const FamInput& in, const TwoBody& tb, ExtField& f) {
+void apply_two_body_current_gt(const std::string& tbc_path, const FamBasis& b, const FamInput& in, const TwoBody& tb, ExtField& f,
+                               const HfbSolution* hfb) {
   // setup_extfield (pnfam_solver.f90:586-646): F = [-GT_1body if 1BC+2BC] + GT[rho_fac] (+ Yukawa part from <name>.tbc
   // for the full-FAM mode).  rho_fac: contact term, plus the nuclear-matter exchange term in the LDA modes.
   if (tb.u[2] == 4 || tb.u[2] == 5)
@@ -751,9 +752,18 @@ void apply_two_body_current_gt(const std::string& tbc_path, const FamBasis& b, c
     return;
   }
   std::string why;
-  if (!read_tbc(tbc_path, b, in, f, why))
-    throw std::runtime_error(why + " (the full-FAM two-body-current field generator, pnfam_extfield_2bc.f90, is not part of this "
-                                   "library: provide the .tbc file the reference caches)");
+  if (!read_tbc(tbc_path, b, in, f, why)) {
+    // "Starting calculation from scratch..." (fam_io(-1) failed, pnfam_solver.f90:622-640): compute and cache
+    if (!hfb || getenv("PNFAM_B200_NO_TBC_GENERATOR"))
+      throw std::runtime_error(why + " (the two-body-current field generator is switched off: provide the .tbc file)");
+    const TbcField fld = generate_two_body_current_field(*hfb, b, f, in.two_body_current_usep);
+    const double c3 = in.two_body_current_lecs[0], c4 = in.two_body_current_lecs[1] + 0.25;
+    const double fac[6] = {c3, c3, c4, c4, 1.0, 1.0};            // summed like read_tbc does: the next set-up, which reads
+    std::fill(f.mat.elem.begin(), f.mat.elem.end(), 0.0);        // the cached file, gets bit-identical elements
+    for (int a = 0; a < (in.two_body_current_usep ? 6 : 4); a++)
+      for (size_t i = 0; i < tmp.size(); i++) f.mat.elem[i] += fld.c[a][i] * fac[a];
+    try { write_tbc(tbc_path, b, in, f, tb, fld); } catch (const std::exception&) { /* a read-only run directory: keep going */ }
+  }
   for (size_t i = 0; i < tmp.size(); i++) f.mat.elem[i] += tmp[i];
 }
 

@@ -137,6 +137,18 @@ std::vector<ExtField> make_crossterms(const ExtField& op, const FieldProvider& f
 bool read_tbc(const std::string& path, const FamBasis& b, const FamInput& in, ExtField& f, std::string& why);
 // Full two-body-current GT field of mode i1 i2=1 i3=1 i4>0 (pnfam_solver.f90:596-652):
 //   F = [-GT_1body if i1==1] + GT[contact rho_fac] + Yukawa part from <name>.tbc
-void apply_two_body_current_gt(const std::string& tbc_path, const FamBasis& b, const FamInput& in, const TwoBody& tb, ExtField& f);
+//   hfb: the undoubled HFB solution; when the file is absent or does not fit the calculation the Yukawa part is computed
+//   (generate_two_body_current_field) and cached in <name>.tbc like the reference does; nullptr = read only
+void apply_two_body_current_gt(const std::string& tbc_path, const FamBasis& b, const FamInput& in, const TwoBody& tb, ExtField& f,
+                               const HfbSolution* hfb = nullptr);
+
+// The Yukawa part of the full-FAM two-body-current GT field (effective_2bc_extfield, pnfam_extfield_2bc.f90:26-465;
+// csrc/host/tbc_generator.cpp), low-energy constants stripped as in the .tbc file: c[0..5] = c3 direct, c3 exchange,
+// c4 direct, c4 exchange, momentum direct, momentum exchange (the last two zero without use_p), each of the size and
+// element order of f.mat.elem.  Gamma part, even nuclei at T = 0.
+struct TbcField { std::vector<double> c[6]; };
+TbcField generate_two_body_current_field(const HfbSolution& s, const FamBasis& b, const ExtField& f, bool use_p);
+// <name>.tbc in the reference's record layout (write_tbc, pnfam_storage.f90:488-559; written atomically)
+void write_tbc(const std::string& path, const FamBasis& b, const FamInput& in, const ExtField& f, const TwoBody& tb, const TbcField& fld);
 
 }  // namespace pnfam

@@ -92,7 +92,8 @@ def test_closed_form_two_body_current_fields(key, tmp_path):
 
 
 def test_unsupported_two_body_current_modes_fail_loudly(tmp_path):
-    """The density-matrix-expansion variants and the full-FAM field without its .tbc file are refused with a message."""
+    """The density-matrix-expansion variants are refused with a message (the full-FAM field without its .tbc file is
+    computed: tests/test_tbc_generator.py)."""
     import json
     import shutil
     from conftest import GOLDEN
@@ -103,7 +104,6 @@ def test_unsupported_two_body_current_modes_fail_loudly(tmp_path):
         shutil.copy(os.path.join(g, f), str(tmp_path))
     for key, old, new, msg in (("GT-K0-121100", "121100", "141100", "density-matrix-expansion"),
                                ("P-K0-221110", "221110", "121120", "density-matrix-expansion"),
-                               ("GT-K0-121100", "121100", "111100", "tbc"),
                                ("GT-K0-121100", "121100", "161100", "Invalid value")):
         (tmp_path / "x.in").write_text(pts[key][0]["namelist"].replace(old, new))
         with pytest.raises(host.PnfamError, match=msg):

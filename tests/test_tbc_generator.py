@@ -1,0 +1,203 @@
+"""CPU tests of the full-FAM two-body-current field generator (csrc/host/tbc_generator.cpp; the reference's
+effective_2bc_extfield, exes/pnfam/pnfam_extfield_2bc.f90:26-465) -- SURVEY.md section 8f row 3.
+
+Known answers: the <OP>.tbc files the reference itself wrote,
+  * tests/golden/S40_All_GT2bc/GT-K{0,1}.tbc: from the reference's own golden tree tests/S40_All_GT2bc/hfb_soln,
+  * tests/golden/tbc_generator/*: the reference's prebuilt pnfam_main.x started here without a .tbc file
+    (tests/golden/make_tbc_generator.py): momentum-dependent terms, beta+, a deformed nucleus.
+A run directory WITHOUT the .tbc file makes the library compute the field and cache it in the reference's record layout;
+the file is compared record by record, the field element by element, and the strengths of the complete FAM solve
+(CPU oracle) with the reference's.  Bound: 1e-12 of the largest element of a component (measured: 7e-15)."""
+import json
+import os
+import shutil
+import struct
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, gold_rows, load_points
+from oracle import fam_oracle as fo
+from pynfam_b200 import host
+
+GEN = os.path.join(GOLDEN, "tbc_generator")
+GEN_CASES = ["S40_usep_K0", "S40_usep_K1", "S40_betaplus_K1", "S40_betaplus_usep_K0", "Gd162_6sh_usep_K1", "Gd162_6sh_K0"]
+
+
+def records(path):
+    d = open(path, "rb").read()
+    pos, out = 0, []
+    while pos < len(d):
+        n = struct.unpack("<i", d[pos:pos + 4])[0]
+        out.append(d[pos + 4:pos + 4 + n])
+        assert struct.unpack("<i", d[pos + 4 + n:pos + 8 + n])[0] == n
+        pos += n + 8
+    return out
+
+
+def compare_files(mine, ref):
+    a, b = records(mine), records(ref)
+    assert [len(r) for r in a] == [len(r) for r in b]
+    worst = 0.0
+    for i, (x, y) in enumerate(zip(a, b)):
+        if len(x) < 1000:
+            assert x == y, ("header record", i)        # version, key, flags, LECs, dimensions, label, K, ...
+            continue
+        x, y = np.frombuffer(x, "<f8"), np.frombuffer(y, "<f8")
+        scale = np.abs(y).max()
+        if scale < 1e-14:                              # the c4 direct and momentum direct parts vanish identically
+            assert np.abs(x).max() < 1e-14
+            continue
+        worst = max(worst, np.abs(x - y).max() / scale)
+    return worst
+
+
+def stage(src_dir, wd, namelist_text, name):
+    for f in ("hfbtho_NAMELIST.dat", "hfbtho_output.hel"):
+        shutil.copy(os.path.join(src_dir, f), wd)
+    with open(os.path.join(wd, name + ".in"), "w") as f:
+        f.write(namelist_text)
+
+
+@pytest.mark.parametrize("op", ["GT-K0", "GT-K1"])
+def test_generated_file_equals_the_golden_tree_file(op, tmp_path):
+    wd = str(tmp_path)
+    src = os.path.join(GOLDEN, "S40_All_GT2bc")
+    stage(src, wd, load_points("S40_All_GT2bc")[op][3]["namelist"], op)
+    p = host.Problem(wd, op + ".in")
+    assert os.path.isfile(os.path.join(wd, op + ".tbc"))
+    worst = compare_files(os.path.join(wd, op + ".tbc"), os.path.join(src, op + ".tbc"))
+    print("worst relative difference of a component: %.2e" % worst)
+    assert worst < 1e-12
+    # the field set up from the generated elements equals the one set up from the reference's file
+    wd2 = str(tmp_path / "from_file")
+    os.makedirs(wd2)
+    stage(src, wd2, load_points("S40_All_GT2bc")[op][3]["namelist"], op)
+    shutil.copy(os.path.join(src, op + ".tbc"), wd2)
+    q = host.Problem(wd2, op + ".in")
+    f1, f2 = p.f64("f_elem"), q.f64("f_elem")
+    assert np.abs(f1 - f2).max() < 1e-12 * np.abs(f2).max()
+
+
+@pytest.mark.parametrize("case", GEN_CASES)
+def test_generated_file_equals_the_reference_binary_file(case, tmp_path):
+    wd = str(tmp_path)
+    src = os.path.join(GEN, case)
+    info = json.load(open(os.path.join(GEN, "strengths.json")))["cases"][case]
+    name = info["name"]
+    stage(src, wd, open(os.path.join(src, name + ".in")).read(), name)
+    host.Problem(wd, name + ".in")
+    worst = compare_files(os.path.join(wd, name + ".tbc"), os.path.join(src, name + ".tbc"))
+    print(case, "worst relative difference of a component: %.2e" % worst)
+    assert worst < 1e-12
+
+
+def test_second_set_up_reads_the_cached_file(tmp_path):
+    """The generated file is what the next process reads (as the reference does): same field, no recomputation."""
+    wd = str(tmp_path)
+    src = os.path.join(GOLDEN, "S40_All_GT2bc")
+    nml = load_points("S40_All_GT2bc")["GT-K1"][0]["namelist"]
+    stage(src, wd, nml, "GT-K1")
+    f1 = host.Problem(wd, "GT-K1.in").f64("f_elem")
+    stamp = os.path.getmtime(os.path.join(wd, "GT-K1.tbc"))
+    os.environ["PNFAM_B200_NO_TBC_GENERATOR"] = "1"      # a second set-up must not need the generator
+    try:
+        f2 = host.Problem(wd, "GT-K1.in").f64("f_elem")
+    finally:
+        del os.environ["PNFAM_B200_NO_TBC_GENERATOR"]
+    assert os.path.getmtime(os.path.join(wd, "GT-K1.tbc")) == stamp
+    assert np.array_equal(f1, f2)
+
+
+@pytest.mark.parametrize("op,idx", [("GT-K0", 4), ("GT-K1", 12)])
+def test_fam_solve_with_generated_field_matches_golden_point(op, idx, tmp_path):
+    """Complete chain without any reference-made file: generated field -> FAM solve (CPU oracle) -> the golden strength,
+    cross-terms and iteration count of tests/S40_All_GT2bc (1e-9)."""
+    wd = str(tmp_path)
+    pt = load_points("S40_All_GT2bc")[op][idx]
+    stage(os.path.join(GOLDEN, "S40_All_GT2bc"), wd, pt["namelist"], "x")
+    p = host.Problem(wd, "x.in")
+    it, si, st = fo.solver_from_problem(p).solve(p.iscalar("max_iter"), p.scalar("convergence_epsilon"))
+    assert it == pt["iters"]
+    gold = gold_rows(pt)
+    labels = ["Strength"] + [p.label(i) for i in range(1, 1 + p.iscalar("nxterms"))]
+    for k, lab in enumerate(labels):
+        if lab in gold:
+            assert abs(st[k] - gold[lab]) <= 1e-9 * abs(gold[lab]), (lab, st[k], gold[lab])
+
+
+@pytest.mark.parametrize("case", ["S40_usep_K0", "S40_betaplus_K1", "Gd162_6sh_usep_K1"])
+def test_fam_solve_with_generated_field_matches_reference_binary(case, tmp_path):
+    """The same for the momentum-dependent terms, beta+ and the deformed nucleus: strengths of the reference binary that
+    computed its own field (tests/golden/tbc_generator/strengths.json)."""
+    wd = str(tmp_path)
+    src = os.path.join(GEN, case)
+    info = json.load(open(os.path.join(GEN, "strengths.json")))["cases"][case]
+    name = info["name"]
+    stage(src, wd, open(os.path.join(src, name + ".in")).read(), name)
+    p = host.Problem(wd, name + ".in")
+    it, si, st = fo.solver_from_problem(p).solve(p.iscalar("max_iter"), p.scalar("convergence_epsilon"))
+    assert it == info["iters"]
+    labels = ["Strength"] + [p.label(i) for i in range(1, 1 + p.iscalar("nxterms"))]
+    for k, lab in enumerate(labels):
+        g = complex(float(info["rows"][lab][0]), float(info["rows"][lab][1]))
+        assert abs(st[k] - g) <= 1e-9 * abs(g), (case, lab, st[k], g)
+
+
+def test_generator_can_be_switched_off_and_refuses_unsupported_solutions(tmp_path):
+    wd = str(tmp_path)
+    stage(os.path.join(GOLDEN, "S40_All_GT2bc"), wd, load_points("S40_All_GT2bc")["GT-K0"][0]["namelist"], "x")
+    os.environ["PNFAM_B200_NO_TBC_GENERATOR"] = "1"
+    try:
+        with pytest.raises(host.PnfamError, match="tbc"):
+            host.Problem(wd, "x.in")
+    finally:
+        del os.environ["PNFAM_B200_NO_TBC_GENERATOR"]
+    # finite temperature: the density matrix of the generator has no thermal terms -> loud refusal
+    wd2 = str(tmp_path / "hot")
+    os.makedirs(wd2)
+    nml = load_points("Gd162_finiteT_6sh")["GT-K0"][0]["namelist"].replace("two_body_current_mode = 0", "two_body_current_mode = 111100")
+    assert "111100" in nml
+    stage(os.path.join(GOLDEN, "Gd162_finiteT_6sh"), wd2, nml, "x")
+    with pytest.raises(host.PnfamError, match="finite temperature"):
+        host.Problem(wd2, "x.in")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["golden:GT-K1", "S40_usep_K1", "Gd162_6sh_usep_K1"])
+def test_gpu_solve_with_generated_field(case, tmp_path):
+    """The product path end to end: no .tbc in the run directory -> host generator -> batched GPU solve -> the reference's
+    strengths (golden tree: all 30 computed points of GT-K1; reference binary: momentum terms, deformed nucleus), 1e-9."""
+    import re
+    from pynfam_b200 import gpu
+    wd = str(tmp_path)
+    if case.startswith("golden:"):
+        op = case.split(":")[1]
+        pts = load_points("S40_All_GT2bc")[op]
+        stage(os.path.join(GOLDEN, "S40_All_GT2bc"), wd, pts[0]["namelist"], "x")
+        om = [complex(float(re.search(r"real_eqrpa\s*=\s*(\S+)", pt["namelist"]).group(1)),
+                      float(re.search(r"imag_eqrpa\s*=\s*(\S+)", pt["namelist"]).group(1))) for pt in pts]
+        golds = [(gold_rows(pt), pt["iters"]) for pt in pts]
+    else:
+        src = os.path.join(GEN, case)
+        info = json.load(open(os.path.join(GEN, "strengths.json")))["cases"][case]
+        nml = open(os.path.join(src, info["name"] + ".in")).read()
+        stage(src, wd, nml, "x")
+        om = [complex(float(re.search(r"real_eqrpa\s*=\s*(\S+)", nml).group(1)), float(re.search(r"imag_eqrpa\s*=\s*(\S+)", nml).group(1)))]
+        golds = [({k: complex(float(v[0]), float(v[1])) for k, v in info["rows"].items()}, info["iters"])]
+    p = host.Problem(wd, "x.in")
+    assert os.path.isfile(os.path.join(wd, p.label(-2) + ".tbc"))
+    ctx = gpu.Context(p)
+    r = ctx.solve(p, omegas=om)
+    worst = 0.0
+    for i, (gold, iters) in enumerate(golds):
+        loose = abs(om[i].imag) < 0.5 or iters >= 25         # ill-conditioned points: see tests/test_gpu_parity.py
+        if not loose:
+            assert int(r["iters"][i]) == iters, i
+        for k, lab in enumerate(["Strength"] + r["labels"][1:]):
+            if lab in gold:
+                rel = abs(r["strength"][i, k] - gold[lab]) / abs(gold[lab])
+                assert rel < (5e-8 if loose else 1e-9), (i, lab, rel)
+                if not loose:
+                    worst = max(worst, rel)
+    print(case, "worst relative difference on well-conditioned points: %.2e" % worst)
