@@ -31,6 +31,8 @@
 #include <map>
 #include <stdexcept>
 
+#include <omp.h>
+
 #include "fam_setup.hpp"
 
 namespace pnfam {
@@ -89,6 +91,7 @@ struct Tables {
   std::vector<double> mez, mer;        // [g][i][j][k][l] over 0..nbig: z (with the fit prefactor) and perpendicular
   std::vector<double> zk[NKIND];       // [g][i][j][k][l] over 0..nzx
   std::vector<double> rk[NKIND];       // [g][i][j][k][l] over 0..nsm
+  std::vector<double> rkT[NKIND];      // the same with the last two indices exchanged (exchange elements)
 
   size_t ibig(int g, int i, int j, int k, int l) const {
     const size_t n = nbig + 1;
@@ -277,29 +280,49 @@ Tables build_tables(const HfbSolution& s, bool use_p) {
           for (int nk = 0; nk <= n; nk++)
             for (int nl = 0; nl <= n; nl++)
               for (int g = 0; g < NG; g++) t.rk[kd][t.ir(g, ni, nj, nk, nl)] = me1d(t, false, g, ni, nj, nk, nl, KIND_D[kd], KIND_P[kd]);
+      t.rkT[kd].assign(t.rk[kd].size(), 0.0);
+      for (int g = 0; g < NG; g++)
+        for (int ni = 0; ni <= n; ni++)
+          for (int nj = 0; nj <= n; nj++)
+            for (int nk = 0; nk <= n; nk++)
+              for (int nl = 0; nl <= n; nl++) t.rkT[kd][t.ir(g, ni, nj, nl, nk)] = t.rk[kd][t.ir(g, ni, nj, nk, nl)];
     }
   }
   return t;
 }
 
-// MatrixElement_radx (pnfam_spatial_mtxels.f90:387-450): derivative kind `kx` along x, plain Gaussian along y
+// MatrixElement_radx (pnfam_spatial_mtxels.f90:387-450): derivative kind `kx` along x, plain Gaussian along y.
+// Same terms in the same order; offsets and coefficient products hoisted, the sign alternates along the innermost index.
 double radx(const Tables& t, int g, int kx, int ni, int li, int nj, int lj, int nk, int lk, int nl, int ll) {
-  const std::vector<double>& mx = t.rk[kx];
-  const std::vector<double>& my = t.rk[G00];
+  const size_t n1 = t.nsm + 1, n2 = n1 * n1, n3 = n2 * n1, slab = n3 * n1;
+  const double* mx = t.rk[kx].data() + (size_t)g * slab;
+  const double* my = t.rk[G00].data() + (size_t)g * slab;
   const int Ni = 2 * ni + std::abs(li), Nj = 2 * nj + std::abs(lj), Nk = 2 * nk + std::abs(lk), Nl = 2 * nl + std::abs(ll);
+  // the x element vanishes unless (sum of the x quantum numbers + d + [p != 0]) is even; the y sum is even by construction
+  if ((Ni + Nj + Nk + Nl + KIND_D[kx] + (KIND_P[kx] ? 1 : 0)) % 2 != 0) return 0.0;
+  const double* Ci = &t.cp2c[((size_t)ni * (4 * t.nsh + 1) + (li + 2 * t.nsh)) * (2 * t.nsh + 1)];
+  const double* Cj = &t.cp2c[((size_t)nj * (4 * t.nsh + 1) + (lj + 2 * t.nsh)) * (2 * t.nsh + 1)];
+  const double* Ck = &t.cp2c[((size_t)nk * (4 * t.nsh + 1) + (lk + 2 * t.nsh)) * (2 * t.nsh + 1)];
+  const double* Cl = &t.cp2c[((size_t)nl * (4 * t.nsh + 1) + (ll + 2 * t.nsh)) * (2 * t.nsh + 1)];
   double v = 0.0;
   for (int yi = 0; yi <= Ni; yi++) {
-    const double ci = t.C(ni, li, yi);
+    const double ci = Ci[yi];
+    const size_t xi_ = (size_t)(Ni - yi) * n3, yi_ = (size_t)yi * n3;
     for (int yj = 0; yj <= Nj; yj++) {
-      const double cj = t.C(nj, lj, yj);
+      const double cij = ci * Cj[yj];
+      const size_t xj_ = xi_ + (size_t)(Nj - yj) * n2, yj_ = yi_ + (size_t)yj * n2;
       for (int yk = 0; yk <= Nk; yk++) {
-        const double ck = t.C(nk, lk, yk);
-        for (int yl = (yi + yj + yk) % 2; yl <= Nl; yl += 2) {
-          const double cl = t.C(nl, ll, yl);
-          const int e = yi + yj + (yi + yj + yk + yl) / 2;
-          v += ((e % 2) ? -1.0 : 1.0) * ci * cj * ck * cl * mx[t.ir(g, Ni - yi, Nj - yj, Nk - yk, Nl - yl)] *
-               my[t.ir(g, yi, yj, yk, yl)];
+        const double cijk = cij * Ck[yk];
+        const double* px = mx + xj_ + (size_t)(Nk - yk) * n1 + Nl;
+        const double* py = my + yj_ + (size_t)yk * n1;
+        const int y0 = (yi + yj + yk) % 2;
+        double sg = ((yi + yj + (yi + yj + yk + y0) / 2) % 2) ? -1.0 : 1.0;
+        double acc = 0.0;
+        for (int yl = y0; yl <= Nl; yl += 2) {
+          acc += sg * Cl[yl] * px[-yl] * py[yl];
+          sg = -sg;
         }
+        v += cijk * acc;
       }
     }
   }
@@ -308,51 +331,123 @@ double radx(const Tables& t, int g, int kx, int ni, int li, int nj, int lj, int 
 
 // imaginary part of MatrixElement_rad_cmplx (pnfam_spatial_mtxels.f90:609-688) for kinds (kx along x, ky along y)
 double rad_cmplx_imag(const Tables& t, int g, int kx, int ky, int ni, int li, int nj, int lj, int nk, int lk, int nl, int ll) {
-  const std::vector<double>& mx = t.rk[kx];
-  const std::vector<double>& my = t.rk[ky];
+  const size_t n1 = t.nsm + 1, n2 = n1 * n1, n3 = n2 * n1, slab = n3 * n1;
+  const double* mx = t.rk[kx].data() + (size_t)g * slab;
+  const double* my = t.rk[ky].data() + (size_t)g * slab;
   const int Ni = 2 * ni + std::abs(li), Nj = 2 * nj + std::abs(lj), Nk = 2 * nk + std::abs(lk), Nl = 2 * nl + std::abs(ll);
+  const double* Ci = &t.cp2c[((size_t)ni * (4 * t.nsh + 1) + (li + 2 * t.nsh)) * (2 * t.nsh + 1)];
+  const double* Cj = &t.cp2c[((size_t)nj * (4 * t.nsh + 1) + (lj + 2 * t.nsh)) * (2 * t.nsh + 1)];
+  const double* Ck = &t.cp2c[((size_t)nk * (4 * t.nsh + 1) + (lk + 2 * t.nsh)) * (2 * t.nsh + 1)];
+  const double* Cl = &t.cp2c[((size_t)nl * (4 * t.nsh + 1) + (ll + 2 * t.nsh)) * (2 * t.nsh + 1)];
   double v = 0.0;
   for (int yi = 0; yi <= Ni; yi++) {
-    const double ci = t.C(ni, li, yi);
+    const size_t xi_ = (size_t)(Ni - yi) * n3, yi_ = (size_t)yi * n3;
     for (int yj = 0; yj <= Nj; yj++) {
-      const double cj = t.C(nj, lj, yj);
+      const double cij = Ci[yi] * Cj[yj];
+      const size_t xj_ = xi_ + (size_t)(Nj - yj) * n2, yj_ = yi_ + (size_t)yj * n2;
       for (int yk = 0; yk <= Nk; yk++) {
-        const double ck = t.C(nk, lk, yk);
-        for (int yl = 0; yl <= Nl; yl++) {
-          const int e = ((yi + yj - yk - yl) % 4 + 4) % 4;   // i^e: imaginary part +1 (e = 1), -1 (e = 3)
-          if (e % 2 == 0) continue;
-          const double cl = t.C(nl, ll, yl);
-          v += (e == 1 ? 1.0 : -1.0) * ci * cj * ck * cl * mx[t.ir(g, Ni - yi, Nj - yj, Nk - yk, Nl - yl)] *
-               my[t.ir(g, yi, yj, yk, yl)];
+        const double cijk = cij * Ck[yk];
+        const double* px = mx + xj_ + (size_t)(Nk - yk) * n1 + Nl;
+        const double* py = my + yj_ + (size_t)yk * n1;
+        // i^(yi+yj-yk-yl) has an imaginary part only for an odd exponent: +1 for 1 (mod 4), -1 for 3 (mod 4)
+        const int y0 = (yi + yj + yk + 1) % 2;
+        int e = (((yi + yj - yk - y0) % 4) + 4) % 4;
+        double sg = e == 1 ? 1.0 : -1.0;
+        double acc = 0.0;
+        for (int yl = y0; yl <= Nl; yl += 2) {
+          acc += sg * Cl[yl] * px[-yl] * py[yl];
+          sg = -sg;
         }
+        v += cijk * acc;
       }
     }
   }
   return v;
 }
 
-// MatrixElement_ddGr (pnfam_spatial_mtxels.f90:292-371)
-double ddgr(const Tables& t, int g, int ni, int li, int nj, int lj, int nk, int lk, int nl, int ll, int di, int dj, int dip) {
-  if (-li - lj + lk + ll + di + dj != 0) return 0.0;
+// The four-fold Cartesian sum of MatrixElement_radx with the quantum numbers of two of the four states fixed:
+//   radx(A, B, C, D) = sum_{yB, yD} cB(yB) cD(yD) (-1)^(yB + ceil((yB + yD) / 2)) Q[yB][yD][N_B - yB][N_D - yD],
+//   Q[YB][YD][XB][XD] = sum_{yA, yC} cA(yA) cC(yC) (-1)^(yA + floor((yA + yC) / 2)) My[yA, YB, yC, YD] Mx[N_A - yA, XB, N_C - yC, XD]
+// (the reference's sign (-1)^(yA + yB + (yA + yB + yC + yD) / 2) factorises like this on the even sums, the only ones
+// with a non-zero y element).  One Q per (A, C, derivative kind, Gaussian) serves every pair (B, D), both orientations of
+// their Lambda, and -- built from the tables with the last two indices exchanged -- the exchange elements
+// radx(A, B, D, C).  O(N^4) per element becomes O(N^2).
+void build_q(const Tables& t, int kind, bool exc, int nA, int lA, int nC, int lC, std::vector<double>& Q) {
+  const size_t n1 = t.nsm + 1, n2 = n1 * n1, n3 = n2 * n1, slab = n3 * n1;
+  const int nmax = t.nrlx;
+  Q.assign((size_t)NG * slab, 0.0);
+  const std::vector<double>& MX = exc ? t.rkT[kind] : t.rk[kind];
+  const std::vector<double>& MY = exc ? t.rkT[G00] : t.rk[G00];
+  const int NA = 2 * nA + std::abs(lA), NC = 2 * nC + std::abs(lC);
+  const int xpar = KIND_D[kind] + (KIND_P[kind] ? 1 : 0);
+  const double* CA = &t.cp2c[((size_t)nA * (4 * t.nsh + 1) + (lA + 2 * t.nsh)) * (2 * t.nsh + 1)];
+  const double* CC = &t.cp2c[((size_t)nC * (4 * t.nsh + 1) + (lC + 2 * t.nsh)) * (2 * t.nsh + 1)];
+  for (int g = 0; g < NG; g++) {
+    const double* mx = MX.data() + (size_t)g * slab;
+    const double* my = MY.data() + (size_t)g * slab;
+    double* q = Q.data() + (size_t)g * slab;
+    for (int yA = 0; yA <= NA; yA++)
+      for (int yC = 0; yC <= NC; yC++) {
+        const double w = CA[yA] * CC[yC] * (((yA + (yA + yC) / 2) % 2) ? -1.0 : 1.0);
+        if (w == 0.0) continue;
+        for (int YB = 0; YB <= nmax; YB++)
+          for (int YD = (yA + YB + yC) % 2; YD <= nmax; YD += 2) {
+            const double l = w * my[(size_t)yA * n3 + (size_t)YB * n2 + (size_t)yC * n1 + YD];
+            if (l == 0.0) continue;
+            double* qrow = q + ((size_t)YB * n1 + YD) * n2;
+            const double* mrow = mx + (size_t)(NA - yA) * n3 + (size_t)(NC - yC) * n1;
+            for (int XB = 0; XB <= nmax - YB; XB++) {     // the x element vanishes for an odd (sum + d + [p != 0])
+              double* qq = qrow + (size_t)XB * n1;
+              const double* mm = mrow + (size_t)XB * n2;
+              for (int XD = (NA - yA + NC - yC + XB + xpar) % 2; XD <= nmax - YD; XD += 2) qq[XD] += l * mm[XD];
+            }
+          }
+      }
+  }
+}
+
+inline double radx_q(const Tables& t, const double* qg, int nB, int lB, int nD, int lD) {
+  const size_t n1 = t.nsm + 1, n2 = n1 * n1;
+  const int NB = 2 * nB + std::abs(lB), ND = 2 * nD + std::abs(lD);
+  const double* CB = &t.cp2c[((size_t)nB * (4 * t.nsh + 1) + (lB + 2 * t.nsh)) * (2 * t.nsh + 1)];
+  const double* CD = &t.cp2c[((size_t)nD * (4 * t.nsh + 1) + (lD + 2 * t.nsh)) * (2 * t.nsh + 1)];
+  double v = 0.0;
+  for (int yB = 0; yB <= NB; yB++) {
+    double acc = 0.0;
+    for (int yD = 0; yD <= ND; yD++) {
+      const double sg = ((yB + (yB + yD + 1) / 2) % 2) ? -1.0 : 1.0;
+      acc += sg * CD[yD] * qg[((size_t)yB * n1 + yD) * n2 + (size_t)(NB - yB) * n1 + (ND - yD)];
+    }
+    v += CB[yB] * acc;
+  }
+  return v;
+}
+
+inline int kind_of(int d, int pp) {
+  for (int k = 0; k < NKIND; k++) if (KIND_D[k] == d && KIND_P[k] == pp) return k;
+  throw std::runtime_error("two-body currents: invalid derivative kind");
+}
+
+// MatrixElement_ddGr (pnfam_spatial_mtxels.f90:292-371); msum = -li - lj + lk + ll of the four states,
+// X(kind) = MatrixElement_radx for that derivative kind, XC(kind) = Im MatrixElement_rad_cmplx(dx = 1, py = kind)
+template <class RX, class RC>
+double ddgr(int msum, RX&& X, RC&& XC, int di, int dj, int dip) {
+  if (msum + di + dj != 0) return 0.0;
   const int p = dip != 0 ? 1 : 0;
-  auto kind = [](int d, int pp) {
-    for (int k = 0; k < NKIND; k++) if (KIND_D[k] == d && KIND_P[k] == pp) return k;
-    throw std::runtime_error("two-body currents: invalid derivative kind");
-  };
-  auto X = [&](int d, int pp) { return radx(t, g, kind(d, pp), ni, li, nj, lj, nk, lk, nl, ll); };
   const double cr2 = std::sqrt(2.0);
-  if (di == 0 && dj == 0) return X(0, 0);
-  if (std::abs(di + dj) == 2) return X(2 - p, dip) * 2.0;
-  if (std::abs(di + dj) == 1) return dj == 0 ? X(1 - p, dip) * (-(di + dj) * cr2) : X(1, 0) * (-(di + dj) * cr2);
-  double v = X(2 - p, dip) * (-1.0);
-  if (dip != 0) v += rad_cmplx_imag(t, g, G10, kind(0, dip), ni, li, nj, lj, nk, lk, nl, ll);
+  if (di == 0 && dj == 0) return X(kind_of(0, 0));
+  if (std::abs(di + dj) == 2) return X(kind_of(2 - p, dip)) * 2.0;
+  if (std::abs(di + dj) == 1) return dj == 0 ? X(kind_of(1 - p, dip)) * (-(di + dj) * cr2) : X(kind_of(1, 0)) * (-(di + dj) * cr2);
+  double v = X(kind_of(2 - p, dip)) * (-1.0);
+  if (dip != 0) v += XC(kind_of(0, dip));
   return v;
 }
 
 // calc_Jr_opt (pnfam_type_extfield_2bc.f90:294-398): radial components, no prefactors
-void calc_jr(const Tables& t, int K, bool use_p, int g, int ni, int li, int nj, int lj, int nk, int lk, int nl, int ll, double* J) {
+template <class RX, class RC>
+void calc_jr(int K, bool use_p, int msum, RX&& X, RC&& XC, double* J) {
   for (int c = 0; c < NCOMP; c++) J[c] = 0.0;
-  auto dd = [&](int di, int dj, int dip) { return ddgr(t, g, ni, li, nj, lj, nk, lk, nl, ll, di, dj, dip); };
+  auto dd = [&](int di, int dj, int dip) { return ddgr(msum, X, XC, di, dj, dip); };
   if (use_p) {
     J[R0P] = dd(K, -1, 1); J[R0Z] = dd(K, 0, 1); J[R0M] = dd(K, +1, 1);
     J[RP0] = dd(K, -1, 2); J[RZ0] = dd(K, 0, 2); J[RM0] = dd(K, +1, 2);
@@ -505,7 +600,13 @@ TbcField generate_two_body_current_field(const HfbSolution& s, const FamBasis& b
   if (K < -1 || K > 1) throw std::runtime_error("ERROR, invalid K for extfield 2bc");
   const int nt = s.nt, nbx = s.nb;
   const size_t nxy = f.mat.elem.size();
+  const bool timing = getenv("PNFAM_B200_SETUP_TIMING") != nullptr;
+  double t_phase = omp_get_wtime(), t_jr = 0.0, t_con = 0.0;
+  auto lap = [&](const char* what) {
+    if (timing) { const double now = omp_get_wtime(); std::fprintf(stderr, "[setup]   2BC %-18s %.3f s\n", what, now - t_phase); t_phase = now; }
+  };
   const Tables t = build_tables(s, use_p);
+  lap("1D tables");
   const int ncomp = use_p ? (int)NCOMP : (int)R0P;
 
   // prefactors with unit LECs
@@ -568,8 +669,8 @@ TbcField generate_two_body_current_field(const HfbSolution& s, const FamBasis& b
     for (int B = 0; B < ncls; B++)
       if (cls[D].np == cls[B].np) { pair_id[(size_t)D * ncls + B] = (int)pairs.size(); pairs.push_back({D, B}); }
   const int npairs = (int)pairs.size();
-  const size_t wrec = (size_t)NG * ncomp;             // one (pair) record: [g][comp]
-  const size_t wsz = (size_t)4 * npairs * wrec;       // [src = x*2+q ... see below][pair][g][comp]
+  const size_t wrec = (size_t)NG * ncomp;             // one (pair) record: [comp][g]
+  const size_t wsz = (size_t)4 * npairs * wrec;       // [src = x*2+q ... see below][pair][comp][g]
 
   // doubled states (time-reversed partners after the originals), grouped by (n_r, Lambda)
   struct Dst { int z, r, l, sp, sign, blk, pos; };
@@ -603,6 +704,14 @@ TbcField generate_two_body_current_field(const HfbSolution& s, const FamBasis& b
       for (int sd = -1; sd <= 1; sd += 2)
         for (int sb = -1; sb <= 1; sb += 2) sc_tab[sidx(sa, sc, sd, sb)] = spin_coef(sa, sc, sd, sb, f.beta_minus);
 
+  struct SpinTerm { int out, src, comp; double coef; };
+  std::vector<std::vector<SpinTerm>> sc_list(16);
+  for (int i = 0; i < 16; i++)
+    for (int o = 0; o < 6; o++)
+      for (int src = 0; src < 4; src++)
+        for (int c = 0; c < ncomp; c++)
+          if (sc_tab[i].c[o][src][c] != 0.0) sc_list[i].push_back({o, src, c, sc_tab[i].c[o][src][c]});
+
   // unsorted result: index ir2m(block of a) - 1 + pos_a + pos_c * d_a in the reference's original in-block order
   std::vector<double> raw[6];
   for (auto& v : raw) v.assign(nxy, 0.0);
@@ -633,24 +742,32 @@ TbcField generate_two_body_current_field(const HfbSolution& s, const FamBasis& b
               for (int g = 0; g < NG; g++) {
                 calc_jz(t, q, K, use_p, g, za, zb, zc, zd, Jd);
                 calc_jz(t, q, K, use_p, g, za, zb, zd, zc, Je);
-                double* w0 = w + ((size_t)0 * npairs + pid) * wrec + (size_t)g * ncomp;
-                double* w1 = w + ((size_t)1 * npairs + pid) * wrec + (size_t)g * ncomp;
-                double* w2 = w + ((size_t)2 * npairs + pid) * wrec + (size_t)g * ncomp;
-                double* w3 = w + ((size_t)3 * npairs + pid) * wrec + (size_t)g * ncomp;
-                for (int c = 0; c < ncomp; c++) { w0[c] += Jd[c] * rn; w1[c] += Jd[c] * rp; w2[c] += Je[c] * rn; w3[c] += Je[c] * rp; }
+                double* w0 = w + ((size_t)0 * npairs + pid) * wrec + g;
+                double* w1 = w + ((size_t)1 * npairs + pid) * wrec + g;
+                double* w2 = w + ((size_t)2 * npairs + pid) * wrec + g;
+                double* w3 = w + ((size_t)3 * npairs + pid) * wrec + g;
+                for (int c = 0; c < ncomp; c++) { w0[c * NG] += Jd[c] * rn; w1[c * NG] += Jd[c] * rp; w2[c * NG] += Je[c] * rn; w3[c * NG] += Je[c] * rp; }
               }
             }
         }
       }
 
+    lap("z contraction");
     // radial elements per (A, C) and the contraction
-#pragma omp parallel for schedule(dynamic)
+#pragma omp parallel for schedule(dynamic) reduction(+ : t_jr, t_con)
     for (int ic = 0; ic < (int)combos.size(); ic++) {
+      const double tt0 = omp_get_wtime();
       const std::array<int, 2> kA = gkeys[combos[ic].A], kC = gkeys[combos[ic].C];
       const int ra = kA[0], la = kA[1], rc = kC[0], lc = kC[1];
       // JR[pair][v][g][comp], v = 0: dir, 1: exc, 2: dir with time-reversed (d, b), 3: exc with time-reversed (d, b)
       std::vector<double> JR((size_t)npairs * 4 * wrec, 0.0);
       std::vector<char> use_n(npairs, 0), use_t(npairs, 0);
+      std::vector<double> Q[NKIND][2];
+      const size_t qslab = (size_t)(t.nsm + 1) * (t.nsm + 1) * (t.nsm + 1) * (t.nsm + 1);
+      auto q_of = [&](int kind, int exc, int g) -> const double* {
+        if (Q[kind][exc].empty()) build_q(t, kind, exc != 0, ra, la, rc, lc, Q[kind][exc]);
+        return Q[kind][exc].data() + (size_t)g * qslab;
+      };
       for (int p = 0; p < npairs; p++) {
         const RadClass& D = cls[pairs[p][0]];
         const RadClass& B = cls[pairs[p][1]];
@@ -659,26 +776,28 @@ TbcField generate_two_body_current_field(const HfbSolution& s, const FamBasis& b
         use_n[p] = dn >= K - 1 && dn <= K + 1;
         use_t[p] = dt >= K - 1 && dt <= K + 1;
         for (int g = 0; g < NG; g++) {
-          double* j = JR.data() + ((size_t)p * 4) * wrec + (size_t)g * ncomp;
+          double* j = JR.data() + ((size_t)p * 4) * wrec + g;
           double tmp[NCOMP];
-          if (use_n[p]) {
-            calc_jr(t, K, use_p, g, ra, la, rb, lb, rc, lc, rd, ld, tmp);
-            std::copy(tmp, tmp + ncomp, j);
-            calc_jr(t, K, use_p, g, ra, la, rb, lb, rd, ld, rc, lc, tmp);
-            std::copy(tmp, tmp + ncomp, j + wrec);
-          }
-          if (use_t[p]) {
-            calc_jr(t, K, use_p, g, ra, la, rb, -lb, rc, lc, rd, -ld, tmp);
-            std::copy(tmp, tmp + ncomp, j + 2 * wrec);
-            calc_jr(t, K, use_p, g, ra, la, rb, -lb, rd, -ld, rc, lc, tmp);
-            std::copy(tmp, tmp + ncomp, j + 3 * wrec);
+          for (int v = 0; v < 4; v++) {
+            if (v < 2 ? !use_n[p] : !use_t[p]) continue;
+            const int exc = v & 1, sl = v < 2 ? 1 : -1;              // orientation of Lambda_b, Lambda_d
+            const int msum = -la - sl * lb + lc + sl * ld;
+            auto X = [&](int kind) { return radx_q(t, q_of(kind, exc, g), rb, sl * lb, rd, sl * ld); };
+            auto XC = [&](int kind) {
+              return exc ? rad_cmplx_imag(t, g, G10, kind, ra, la, rb, sl * lb, rd, sl * ld, rc, lc)
+                         : rad_cmplx_imag(t, g, G10, kind, ra, la, rb, sl * lb, rc, lc, rd, sl * ld);
+            };
+            calc_jr(K, use_p, msum, X, XC, tmp);
+            for (int c = 0; c < ncomp; c++) j[(size_t)v * wrec + (size_t)c * NG] = tmp[c];
           }
         }
       }
-      for (int a : group[kA]) {
+      const double tt1 = omp_get_wtime();
+      t_jr += tt1 - tt0;
+      for (int a : group.at(kA)) {
         const Dst& sa_ = dst[a];
         if (sa_.z < za0 || sa_.z >= za1) continue;
-        for (int c : group[kC]) {
+        for (int c : group.at(kC)) {
           const Dst& sc_ = dst[c];
           if (f.mat.ir2c[sa_.blk] - 1 != sc_.blk) continue;
           const double* w = W.data() + ((size_t)(sa_.z - za0) * nz1 + sc_.z) * wsz;
@@ -691,18 +810,14 @@ TbcField generate_two_body_current_field(const HfbSolution& s, const FamBasis& b
             const double sign_db = (sd + sb == 0) ? -1.0 : 1.0;
             for (int tr = 0; tr < 2; tr++) {
               if (tr == 0 ? !use_n[p] : !use_t[p]) continue;
-              const SpinCoef& co = tr == 0 ? sc_tab[sidx(sa_.sp, sc_.sp, sd, sb)] : sc_tab[sidx(sa_.sp, sc_.sp, -sd, -sb)];
+              const std::vector<SpinTerm>& terms = tr == 0 ? sc_list[sidx(sa_.sp, sc_.sp, sd, sb)] : sc_list[sidx(sa_.sp, sc_.sp, -sd, -sb)];
               const double fac = tr == 0 ? 1.0 : sign_db;
-              for (int src = 0; src < 4; src++) {
-                const double* ws = w + ((size_t)src * npairs + p) * wrec;
-                const double* js = JR.data() + ((size_t)p * 4 + (src / 2) + 2 * tr) * wrec;
-                for (int o = (src < 2 ? 0 : 1); o < 6; o += 2) {
-                  const double* cf = co.c[o][src];
-                  double acc = 0.0;
-                  for (int g = 0; g < NG; g++)
-                    for (int cc = 0; cc < ncomp; cc++) acc += cf[cc] * ws[(size_t)g * ncomp + cc] * js[(size_t)g * ncomp + cc];
-                  gam[o] += fac * acc;
-                }
+              for (const SpinTerm& tm : terms) {
+                const double* ws = w + ((size_t)tm.src * npairs + p) * wrec + (size_t)tm.comp * NG;
+                const double* js = JR.data() + ((size_t)p * 4 + (tm.src / 2) + 2 * tr) * wrec + (size_t)tm.comp * NG;
+                double acc = 0.0;
+                for (int g = 0; g < NG; g++) acc += ws[g] * js[g];
+                gam[tm.out] += fac * tm.coef * acc;
               }
             }
           }
@@ -712,8 +827,12 @@ TbcField generate_two_body_current_field(const HfbSolution& s, const FamBasis& b
           for (int o = 0; o < 6; o++) raw[o][at] = gam[o] * sg;
         }
       }
+      t_con += omp_get_wtime() - tt1;
     }
+    lap("radial + spin");
   }
+  if (timing) std::fprintf(stderr, "[setup]   2BC thread-seconds: radial elements %.2f, contraction %.2f (%d classes, %d pairs, %d (A,C))\n",
+                           t_jr, t_con, ncls, npairs, (int)combos.size());
 
   // spin sort of rows and columns (reorder_blockmatrix_basis 'a' with new_order, pnfam_extfield_2bc.f90:903-913)
   TbcField out;
