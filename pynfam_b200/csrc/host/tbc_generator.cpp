@@ -601,6 +601,8 @@ TbcField generate_two_body_current_field(const HfbSolution& s, const FamBasis& b
   const int nt = s.nt, nbx = s.nb;
   const size_t nxy = f.mat.elem.size();
   const bool timing = getenv("PNFAM_B200_SETUP_TIMING") != nullptr;
+  // self-check switch: the reference's own four-fold Cartesian sum for every radial element instead of the intermediate
+  const bool literal = getenv("PNFAM_B200_TBC_LITERAL_RADIAL") != nullptr;
   double t_phase = omp_get_wtime(), t_jr = 0.0, t_con = 0.0;
   auto lap = [&](const char* what) {
     if (timing) { const double now = omp_get_wtime(); std::fprintf(stderr, "[setup]   2BC %-18s %.3f s\n", what, now - t_phase); t_phase = now; }
@@ -782,7 +784,10 @@ TbcField generate_two_body_current_field(const HfbSolution& s, const FamBasis& b
             if (v < 2 ? !use_n[p] : !use_t[p]) continue;
             const int exc = v & 1, sl = v < 2 ? 1 : -1;              // orientation of Lambda_b, Lambda_d
             const int msum = -la - sl * lb + lc + sl * ld;
-            auto X = [&](int kind) { return radx_q(t, q_of(kind, exc, g), rb, sl * lb, rd, sl * ld); };
+            auto X = [&](int kind) {
+              if (literal) return exc ? radx(t, g, kind, ra, la, rb, sl * lb, rd, sl * ld, rc, lc) : radx(t, g, kind, ra, la, rb, sl * lb, rc, lc, rd, sl * ld);
+              return radx_q(t, q_of(kind, exc, g), rb, sl * lb, rd, sl * ld);
+            };
             auto XC = [&](int kind) {
               return exc ? rad_cmplx_imag(t, g, G10, kind, ra, la, rb, sl * lb, rd, sl * ld, rc, lc)
                          : rad_cmplx_imag(t, g, G10, kind, ra, la, rb, sl * lb, rc, lc, rd, sl * ld);

@@ -201,3 +201,27 @@ def test_gpu_solve_with_generated_field(case, tmp_path):
                 if not loose:
                     worst = max(worst, rel)
     print(case, "worst relative difference on well-conditioned points: %.2e" % worst)
+
+
+def test_factorised_radial_elements_equal_the_literal_sum_at_12_shells(tmp_path):
+    """Beyond the sizes the reference binary can be run at here: the per-(A, C) intermediate of the radial elements against
+    the reference's literal four-fold Cartesian sum (PNFAM_B200_TBC_LITERAL_RADIAL=1), 12-shell 162Gd, K = 0; the two
+    .tbc files agree to 1e-12 of the largest element."""
+    src = os.path.join(GOLDEN, "Gd162_SKOP_12sh")
+    info = json.load(open(os.path.join(GEN, "strengths.json")))["cases"]["Gd162_6sh_K0"]
+    nml = open(os.path.join(GEN, "Gd162_6sh_K0", info["name"] + ".in")).read()
+    files = []
+    for sub, env in (("fast", None), ("literal", "1")):
+        wd = str(tmp_path / sub)
+        os.makedirs(wd)
+        stage(src, wd, nml, info["name"])
+        if env:
+            os.environ["PNFAM_B200_TBC_LITERAL_RADIAL"] = env
+        try:
+            host.Problem(wd, info["name"] + ".in")
+        finally:
+            os.environ.pop("PNFAM_B200_TBC_LITERAL_RADIAL", None)
+        files.append(os.path.join(wd, info["name"] + ".tbc"))
+    worst = compare_files(files[0], files[1])
+    print("12 shells, factorised vs literal radial sum: %.2e" % worst)
+    assert worst < 1e-12
