@@ -372,14 +372,19 @@ double rad_cmplx_imag(const Tables& t, int g, int kx, int ky, int ni, int li, in
 // with a non-zero y element).  One Q per (A, C, derivative kind, Gaussian) serves every pair (B, D), both orientations of
 // their Lambda, and -- built from the tables with the last two indices exchanged -- the exchange elements
 // radx(A, B, D, C).  O(N^4) per element becomes O(N^2).
-void build_q(const Tables& t, int kind, bool exc, int nA, int lA, int nC, int lC, std::vector<double>& Q) {
+// mode 0: the real sum above (y kind = plain Gaussian); modes 1, 2: the real / imaginary part of i^(yA - yC) instead of
+// the sign, for MatrixElement_rad_cmplx (x kind `kind`, y kind `ky`):  Im sum i^(yA + yB - yC - yD) ... =
+//   sum_{yB, yD} cB cD [ Im i^(yB - yD) Q_re + Re i^(yB - yD) Q_im ][yB][yD][N_B - yB][N_D - yD]
+inline int ipow_re(int n) { n = ((n % 4) + 4) % 4; return n == 0 ? 1 : n == 2 ? -1 : 0; }
+inline int ipow_im(int n) { n = ((n % 4) + 4) % 4; return n == 1 ? 1 : n == 3 ? -1 : 0; }
+void build_q(const Tables& t, int kind, bool exc, int nA, int lA, int nC, int lC, std::vector<double>& Q, int mode = 0, int ky = G00) {
   const size_t n1 = t.nsm + 1, n2 = n1 * n1, n3 = n2 * n1, slab = n3 * n1;
   const int nmax = t.nrlx;
   Q.assign((size_t)NG * slab, 0.0);
   const std::vector<double>& MX = exc ? t.rkT[kind] : t.rk[kind];
-  const std::vector<double>& MY = exc ? t.rkT[G00] : t.rk[G00];
+  const std::vector<double>& MY = exc ? t.rkT[ky] : t.rk[ky];
   const int NA = 2 * nA + std::abs(lA), NC = 2 * nC + std::abs(lC);
-  const int xpar = KIND_D[kind] + (KIND_P[kind] ? 1 : 0);
+  const int xpar = KIND_D[kind] + (KIND_P[kind] ? 1 : 0), ypar = KIND_D[ky] + (KIND_P[ky] ? 1 : 0);
   const double* CA = &t.cp2c[((size_t)nA * (4 * t.nsh + 1) + (lA + 2 * t.nsh)) * (2 * t.nsh + 1)];
   const double* CC = &t.cp2c[((size_t)nC * (4 * t.nsh + 1) + (lC + 2 * t.nsh)) * (2 * t.nsh + 1)];
   for (int g = 0; g < NG; g++) {
@@ -388,10 +393,11 @@ void build_q(const Tables& t, int kind, bool exc, int nA, int lA, int nC, int lC
     double* q = Q.data() + (size_t)g * slab;
     for (int yA = 0; yA <= NA; yA++)
       for (int yC = 0; yC <= NC; yC++) {
-        const double w = CA[yA] * CC[yC] * (((yA + (yA + yC) / 2) % 2) ? -1.0 : 1.0);
+        const double sgn = mode == 0 ? ((((yA + (yA + yC) / 2) % 2) ? -1.0 : 1.0)) : mode == 1 ? (double)ipow_re(yA - yC) : (double)ipow_im(yA - yC);
+        const double w = CA[yA] * CC[yC] * sgn;
         if (w == 0.0) continue;
         for (int YB = 0; YB <= nmax; YB++)
-          for (int YD = (yA + YB + yC) % 2; YD <= nmax; YD += 2) {
+          for (int YD = (yA + YB + yC + ypar) % 2; YD <= nmax; YD += 2) {
             const double l = w * my[(size_t)yA * n3 + (size_t)YB * n2 + (size_t)yC * n1 + YD];
             if (l == 0.0) continue;
             double* qrow = q + ((size_t)YB * n1 + YD) * n2;
@@ -417,6 +423,23 @@ inline double radx_q(const Tables& t, const double* qg, int nB, int lB, int nD, 
     for (int yD = 0; yD <= ND; yD++) {
       const double sg = ((yB + (yB + yD + 1) / 2) % 2) ? -1.0 : 1.0;
       acc += sg * CD[yD] * qg[((size_t)yB * n1 + yD) * n2 + (size_t)(NB - yB) * n1 + (ND - yD)];
+    }
+    v += CB[yB] * acc;
+  }
+  return v;
+}
+
+inline double rad_q_imag(const Tables& t, const double* qre, const double* qim, int nB, int lB, int nD, int lD) {
+  const size_t n1 = t.nsm + 1, n2 = n1 * n1;
+  const int NB = 2 * nB + std::abs(lB), ND = 2 * nD + std::abs(lD);
+  const double* CB = &t.cp2c[((size_t)nB * (4 * t.nsh + 1) + (lB + 2 * t.nsh)) * (2 * t.nsh + 1)];
+  const double* CD = &t.cp2c[((size_t)nD * (4 * t.nsh + 1) + (lD + 2 * t.nsh)) * (2 * t.nsh + 1)];
+  double v = 0.0;
+  for (int yB = 0; yB <= NB; yB++) {
+    double acc = 0.0;
+    for (int yD = 0; yD <= ND; yD++) {
+      const size_t at = ((size_t)yB * n1 + yD) * n2 + (size_t)(NB - yB) * n1 + (ND - yD);
+      acc += CD[yD] * (ipow_im(yB - yD) * qre[at] + ipow_re(yB - yD) * qim[at]);
     }
     v += CB[yB] * acc;
   }
@@ -770,6 +793,11 @@ TbcField generate_two_body_current_field(const HfbSolution& s, const FamBasis& b
         if (Q[kind][exc].empty()) build_q(t, kind, exc != 0, ra, la, rc, lc, Q[kind][exc]);
         return Q[kind][exc].data() + (size_t)g * qslab;
       };
+      std::vector<double> QC[NKIND][2][2];      // rad_cmplx intermediates: [y kind][exc][re | im]
+      auto qc_of = [&](int ky, int exc, int part, int g) -> const double* {
+        if (QC[ky][exc][part].empty()) build_q(t, G10, exc != 0, ra, la, rc, lc, QC[ky][exc][part], 1 + part, ky);
+        return QC[ky][exc][part].data() + (size_t)g * qslab;
+      };
       for (int p = 0; p < npairs; p++) {
         const RadClass& D = cls[pairs[p][0]];
         const RadClass& B = cls[pairs[p][1]];
@@ -789,6 +817,7 @@ TbcField generate_two_body_current_field(const HfbSolution& s, const FamBasis& b
               return radx_q(t, q_of(kind, exc, g), rb, sl * lb, rd, sl * ld);
             };
             auto XC = [&](int kind) {
+              if (!literal) return rad_q_imag(t, qc_of(kind, exc, 0, g), qc_of(kind, exc, 1, g), rb, sl * lb, rd, sl * ld);
               return exc ? rad_cmplx_imag(t, g, G10, kind, ra, la, rb, sl * lb, rd, sl * ld, rc, lc)
                          : rad_cmplx_imag(t, g, G10, kind, ra, la, rb, sl * lb, rc, lc, rd, sl * ld);
             };
