@@ -5,6 +5,7 @@
 #include <cctype>
 #include <cmath>
 #include <fstream>
+#include <mutex>
 #include <stdexcept>
 
 namespace pnfam {
@@ -197,6 +198,7 @@ FamBasis FamBasis::build(const HfbSolution& s) {
     }
   }
   b.rho_n = s.ro[0]; b.rho_p = s.ro[1];
+  b.src = &s;
   // equal-filling blocking data (pnfam_setup.f90:323-362)
   for (int it = 0; it < 2; it++) {
     if (s.keyblo[it] != 0) {
@@ -465,6 +467,9 @@ std::vector<double> tbc_gt_rho_fac(const FamBasis& b, const TwoBody& tb) {
       }
     }
     for (int r = 0; r < b.nghl; r++) rf[r] = rf[r] + da1[r];
+  } else if (tb.u[2] == 4 || tb.u[2] == 5) {
+    const std::vector<double> ex = tbc_dme_exc(b, tb);
+    for (int r = 0; r < b.nghl; r++) rf[r] = rf[r] + ex[r];
   }
   return rf;
 }
@@ -515,6 +520,109 @@ std::vector<double> tbc_ps0_correction(const FamBasis& b) {
   return rf;
 }
 
+void FamBasis::need_tau_d2rho() const {
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lk(mu);
+  if (!tau0.empty()) return;
+  if (!src) throw std::runtime_error("density-matrix-expansion currents: no HFB solution attached to the basis");
+  std::vector<double> tau[2], dro[2];
+  src->kinetic_and_laplacian(tau, dro);
+  d2rho0.resize(nghl);
+  for (int i = 0; i < nghl; i++) d2rho0[i] = dro[0][i] + dro[1][i];
+  std::vector<double> t(nghl);
+  for (int i = 0; i < nghl; i++) t[i] = tau[0][i] + tau[1][i];
+  tau0.swap(t);
+}
+
+// ---- density-matrix expansion (pnfam_extfield.f90:1195-1330, 1380-1545): the U integrals, with the reference's cut-offs
+namespace {
+struct DmeU {
+  double m;
+  DmeU() : m(TB_MPI / TB_HBARC) {}
+  double lg(double kf) const { return std::log(1.0 + 4.0 * kf * kf / (m * m)); }
+  double u00(double kf) const {
+    if (kf < 0.001) return 1.0 / (m * m);
+    return 1.5 / (kf * kf) * (1 - m / kf * std::atan(2 * kf / m) + m * m / (4.0 * kf * kf) * lg(kf));
+  }
+  double u02(double kf) const {
+    if (kf < 0.00005) return 0.0;
+    return 0.75 / (kf * kf) * (lg(kf) - 4.0 * kf * kf / (4.0 * kf * kf + m * m));
+  }
+  double u02_kf2(double kf) const {
+    if (kf < 0.001) return 6.0 / (m * m * m * m);
+    return 0.75 / (kf * kf * kf * kf) * (lg(kf) - 4.0 * kf * kf / (4.0 * kf * kf + m * m));
+  }
+  double u22(double kf) const {
+    return -1.0 * kf / (3.0 * TB_PI * TB_PI) * (1.0 + 8.0 * kf * kf / (4.0 * kf * kf + m * m) - m * m / (4.0 * kf * kf) * lg(kf));
+  }
+  double u10(double kf) const {
+    if (kf < 0.001) return 3.0 / (m * m);
+    return 1.5 / (kf * kf) * (1.0 - m * m / (4.0 * kf * kf) * lg(kf));
+  }
+  double u12(double kf) const {
+    if (kf < 0.0001) return 0.0;
+    const double d = 4.0 * kf * kf + m * m;
+    return 3.0 / d * ((4.0 * kf * kf - m * m) / d + (1.0 + m * m / (4.0 * kf * kf)) * lg(kf));
+  }
+  double u12_kf2(double kf) const {
+    if (kf < 0.001) return 30.0 / (m * m * m * m) + (-224.0 / std::pow(m, 6)) * kf * kf;
+    const double d = 4.0 * kf * kf + m * m;
+    return 3.0 / (kf * kf * d) * ((4.0 * kf * kf - m * m) / d + (1.0 + m * m / (4.0 * kf * kf)) * lg(kf));
+  }
+  double u24(double kf) const {
+    const double d = 4.0 * kf * kf + m * m;
+    return kf * kf * (80.0 * std::pow(kf, 4) + 40.0 * kf * kf * m * m - 3.0 * std::pow(m, 4)) / (d * d * d) + 0.75 * lg(kf);
+  }
+  double u24_kf4(double kf) const {
+    if (kf < 0.001) return 35.0 / (3.0 * std::pow(m, 4)) + (-112.0 / std::pow(m, 6)) * kf * kf;
+    return 1.0 / (6.0 * kf * kf * kf * kf) * u24(kf);
+  }
+};
+}  // namespace
+
+// dme_exc (pnfam_extfield.f90:1271-1307)
+std::vector<double> tbc_dme_exc(const FamBasis& b, const TwoBody& tb) {
+  b.need_tau_d2rho();
+  const DmeU U;
+  const double m = U.m, c3 = tb.lecs[0], c4 = tb.lecs[1], cd = tb.lecs[2] * (-0.25), d1 = cd * 0.50, d2 = cd * 0.25;
+  const double ca = 2 * tb_caux(), ch = 1.0 / 3.0 * (2 * c4 - c3 + 0.5), cc = -d1 + 2 * d2;
+  std::vector<double> rf(b.nghl);
+  for (int r = 0; r < b.nghl; r++) {
+    const double rho = b.rho_n[r] + b.rho_p[r], kf = kf_snm(rho);
+    const double rf1 = ca * (ch * (1 - m * m * U.u00(kf) - m * m * U.u02(kf) * 0.1) + cc) * rho;
+    const double rf2 = ca * ch * m * m / 6 * U.u02_kf2(kf) * (0.25 * b.d2rho0[r] - b.tau0[r]);
+    rf[r] = rf1 - rf2;
+  }
+  return rf;
+}
+
+// dme_vector (pnfam_extfield.f90:1621-1662)
+std::vector<double> tbc_dme_vector(const FamBasis& b) {
+  b.need_tau_d2rho();
+  const DmeU U;
+  std::vector<double> rf(b.nghl);
+  for (int r = 0; r < b.nghl; r++) {
+    const double rho = b.rho_n[r] + b.rho_p[r], kf = kf_snm(rho);
+    rf[r] = TB_GA * TB_GA * TB_MN * TB_HBARC / (4.0 * TB_FPI * TB_FPI) *
+            ((U.u10(kf) + 0.1 * U.u12(kf)) * rho + U.u22(kf) - U.u24(kf) * kf / (15.0 * TB_PI * TB_PI) +
+             (U.u12_kf2(kf) / 6.0 - U.u24_kf4(kf)) * (0.25 * b.d2rho0[r] - b.tau0[r]));
+  }
+  return rf;
+}
+
+// dme_axial_2 (pnfam_extfield.f90:1573-1602)
+std::vector<double> tbc_dme_axial(const FamBasis& b) {
+  b.need_tau_d2rho();
+  const DmeU U;
+  std::vector<double> rf(b.nghl);
+  for (int r = 0; r < b.nghl; r++) {
+    const double rho = b.rho_n[r] + b.rho_p[r], kf = kf_snm(rho);
+    rf[r] = TB_HBARC * TB_MN / (6.0 * TB_FPI * TB_FPI) *
+            ((U.u10(kf) + 0.1 * U.u12(kf)) * rho + U.u12_kf2(kf) / 6.0 * (0.25 * b.d2rho0[r] - b.tau0[r]));
+  }
+  return rf;
+}
+
 ExtField make_external_field(const FamBasis& b, const std::string& beta_type, const std::string& label_in, int K,
                              const std::vector<double>* rho_fac, const TwoBody* tb) {
   ExtField op;
@@ -542,8 +650,7 @@ ExtField make_external_field(const FamBasis& b, const std::string& beta_type, co
   if (useI) ifun = i1111(b);
   // two-body-current weight on wf_1 (pnfam_extfield.f90:189-197, 349-366, 383-557, 562-607): RS* fields carry
   // (1 - correction) when the 4th mode digit is >= 2 (3: asymmetric nuclear matter); P and PS0 carry 1 + correction
-  // (1BC + 2BC) or the correction alone (2BC only) when their digit is 1.  The density-matrix-expansion variants
-  // (digit 2) are not restated.
+  // (1BC + 2BC) or the correction alone (2BC only): digit 1 = nuclear matter, 2 = density-matrix expansion.
   std::vector<double> w1;
   if (tb && tb->active()) {
     const bool rs = (L == "RS0" || L == "RS1" || L == "RS2" || L == "RS0I" || L == "RS1I");
@@ -552,9 +659,9 @@ ExtField make_external_field(const FamBasis& b, const std::string& beta_type, co
       for (auto& x : w1) x = 1.0 - x;
     } else if ((L == "P" && tb->u[5] != 0) || (L == "PS0" && tb->u[6] != 0)) {
       const int dg = L == "P" ? tb->u[5] : tb->u[6];
-      if (dg == 2) throw std::runtime_error("two_body_current_mode: the density-matrix-expansion current of " + L + " is not supported");
-      if (dg == 1) {
-        w1 = L == "P" ? tbc_p_correction(b) : tbc_ps0_correction(b);
+      if (dg == 1 || dg == 2) {
+        if (dg == 1) w1 = L == "P" ? tbc_p_correction(b) : tbc_ps0_correction(b);
+        else w1 = L == "P" ? tbc_dme_vector(b) : tbc_dme_axial(b);
         if (tb->u[1] == 1) for (auto& x : w1) x = 1 + x;
       }
     }
@@ -688,7 +795,7 @@ std::vector<ExtField> make_crossterms(const ExtField& op, const FieldProvider& f
   return out;
 }
 
-bool read_tbc(const std::string& path, const FamBasis& b, const FamInput& in, ExtField& f, std::string& why) {
+bool read_tbc(const std::string& path, const FamBasis& b, const FamInput& in, ExtField& f, std::string& why, bool direct_only) {
   std::ifstream probe(path, std::ios::binary);
   if (!probe) { why = "cannot open " + path; return false; }
   probe.close();
@@ -726,6 +833,7 @@ bool read_tbc(const std::string& path, const FamBasis& b, const FamInput& in, Ex
       if (r.size() != nxy * 8) throw std::runtime_error(".tbc: unexpected record size");
       std::vector<double> v = r.get_vec<double>(nxy);
       const double s = a < 4 ? fac[a] : 1.0;
+      if (direct_only && (a & 1)) continue;                    // c3e, c4e, cpe: exchange parts
       for (size_t i = 0; i < nxy; i++) tot[i] += v[i] * s;
     }
     f.mat.elem = tot;
@@ -740,19 +848,18 @@ void apply_two_body_current_gt(const std::string& tbc_path, const FamBasis& b, c
                                const HfbSolution* hfb) {
   // setup_extfield (pnfam_solver.f90:586-646): F = [-GT_1body if 1BC+2BC] + GT[rho_fac] (+ Yukawa part from <name>.tbc
   // for the full-FAM mode).  rho_fac: contact term, plus the nuclear-matter exchange term in the LDA modes.
-  if (tb.u[2] == 4 || tb.u[2] == 5)
-    throw std::runtime_error("two_body_current_mode: the density-matrix-expansion modes (2nd digit 4, 5) are not supported");
   std::vector<double> tmp(f.mat.elem.size(), 0.0);
   if (tb.u[1] == 1) for (size_t i = 0; i < tmp.size(); i++) tmp[i] = -f.mat.elem[i];   // Park sign convention: -sigma tau + 2BC
   const std::vector<double> rho_fac = tbc_gt_rho_fac(b, tb);
   ExtField contact = make_external_field(b, f.beta_minus ? "-" : "+", f.label, f.k, &rho_fac);
   for (size_t i = 0; i < tmp.size(); i++) tmp[i] += contact.mat.elem[i];
-  if (tb.u[2] != 1) {                       // no FAM part: F = -sigma tau + sigma tau f(rho)
+  const bool direct_only = tb.u[2] == 5;    // DME exchange term + the direct part of the FAM field
+  if (tb.u[2] != 1 && tb.u[2] != 5) {       // no FAM part: F = -sigma tau + sigma tau f(rho)
     f.mat.elem = tmp;
     return;
   }
   std::string why;
-  if (!read_tbc(tbc_path, b, in, f, why)) {
+  if (!read_tbc(tbc_path, b, in, f, why, direct_only)) {
     // "Starting calculation from scratch..." (fam_io(-1) failed, pnfam_solver.f90:622-640): compute and cache
     if (!hfb || getenv("PNFAM_B200_NO_TBC_GENERATOR"))
       throw std::runtime_error(why + " (the two-body-current field generator is switched off: provide the .tbc file)");
@@ -760,8 +867,10 @@ void apply_two_body_current_gt(const std::string& tbc_path, const FamBasis& b, c
     const double c3 = in.two_body_current_lecs[0], c4 = in.two_body_current_lecs[1] + 0.25;
     const double fac[6] = {c3, c3, c4, c4, 1.0, 1.0};            // summed like read_tbc does: the next set-up, which reads
     std::fill(f.mat.elem.begin(), f.mat.elem.end(), 0.0);        // the cached file, gets bit-identical elements
-    for (int a = 0; a < (in.two_body_current_usep ? 6 : 4); a++)
+    for (int a = 0; a < (in.two_body_current_usep ? 6 : 4); a++) {
+      if (direct_only && (a & 1)) continue;
       for (size_t i = 0; i < tmp.size(); i++) f.mat.elem[i] += fld.c[a][i] * fac[a];
+    }
     try { write_tbc(tbc_path, b, in, f, tb, fld); } catch (const std::exception&) { /* a read-only run directory: keep going */ }
   }
   for (size_t i = 0; i < tmp.size(); i++) f.mat.elem[i] += tmp[i];

@@ -73,6 +73,11 @@ struct FamBasis {
   std::vector<double> sep_r;             // [4][dqp][ngl]
   std::vector<double> Ep, En, Up, Vp, Un, Vn;
   std::vector<double> rho_n, rho_p;      // coordinate-space densities (normalised)
+  // isoscalar kinetic density and Laplacian of the density (tau_n + tau_p, Delta rho_n + Delta rho_p) for the
+  // density-matrix-expansion two-body currents; computed from `src` on first use
+  const HfbSolution* src = nullptr;
+  mutable std::vector<double> tau0, d2rho0;
+  void need_tau_d2rho() const;
   bool blo_active = false;
   int blo_qp[2] = {0, 0};                // 1-based overall qp index of the blocked level (n, p)
   int blo_ib[2] = {0, 0}, blo_is[2] = {0, 0};
@@ -125,6 +130,11 @@ std::vector<double> tbc_gt_rho_fac(const FamBasis& b, const TwoBody& tb);   // G
 std::vector<double> tbc_rsl_correction(const FamBasis& b, const TwoBody& tb, bool snm);
 std::vector<double> tbc_p_correction(const FamBasis& b);
 std::vector<double> tbc_ps0_correction(const FamBasis& b);
+// density-matrix-expansion variants (pnfam_extfield.f90:1195-1330, 1380-1545, 1573-1662): exchange term of the GT current
+// (2nd mode digit 4, 5), vector current of P (5th digit 2), axial charge of PS0 (6th digit 2)
+std::vector<double> tbc_dme_exc(const FamBasis& b, const TwoBody& tb);
+std::vector<double> tbc_dme_vector(const FamBasis& b);
+std::vector<double> tbc_dme_axial(const FamBasis& b);
 ExtField make_external_field(const FamBasis& b, const std::string& beta_type, const std::string& label, int k,
                              const std::vector<double>* rho_fac = nullptr, const TwoBody* tb = nullptr);
 std::vector<ExtField> make_crossterms(const FamBasis& b, const ExtField& op, const TwoBody* tb = nullptr);
@@ -134,7 +144,8 @@ using FieldProvider = std::function<ExtField(const std::string&, const std::stri
 std::vector<ExtField> make_crossterms(const ExtField& op, const FieldProvider& field);
 // Read the Yukawa part of a two-body-current field from <name>.tbc (pnfam_storage.f90:562-727).
 // On success f.mat.elem holds c3/c4-weighted gamma (direct + exchange) exactly as read_tbc leaves it.
-bool read_tbc(const std::string& path, const FamBasis& b, const FamInput& in, ExtField& f, std::string& why);
+// direct_only: the direct (Hartree) part alone, calc_totgamdel(..., 'd') -- mode digit 2 = 5 (DME exchange + FAM direct)
+bool read_tbc(const std::string& path, const FamBasis& b, const FamInput& in, ExtField& f, std::string& why, bool direct_only = false);
 // Full two-body-current GT field of mode i1 i2=1 i3=1 i4>0 (pnfam_solver.f90:596-652):
 //   F = [-GT_1body if i1==1] + GT[contact rho_fac] + Yukawa part from <name>.tbc
 //   hfb: the undoubled HFB solution; when the file is absent or does not fit the calculation the Yukawa part is computed

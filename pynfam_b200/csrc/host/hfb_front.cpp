@@ -772,6 +772,65 @@ static void densit_rho(HfbSolution& s) {
   }
 }
 
+// DENSIT restricted to tau(r) and Delta rho(r): TEMP4 / TEMP5 of the zero-temperature branch (hfbtho_solver.f90:4559-4566)
+// with the weights and the particle-number rescaling of the end of the routine (:4697-4716).
+void HfbSolution::kinetic_and_laplacian(std::vector<double> tau[2], std::vector<double> dro[2]) const {
+  const HfbSolution& s = *this;
+  if (s.ft_active) throw std::runtime_error("tau and Delta rho at finite temperature are not computed");
+  if (s.keyblo[0] || s.keyblo[1]) throw std::runtime_error("tau and Delta rho of blocked (odd) nuclei are not computed");
+  const int nghl = s.nghl;
+  for (int it = 0; it < 2; it++) {
+    std::vector<double> ro(nghl, 0.0), ta(nghl, 0.0), dr(nghl, 0.0);
+    for (int ib = 0; ib < s.nb; ib++) {
+      const int nd = s.id[ib], im = s.ia[ib];
+      const int k1 = s.ka[it][ib], imen = s.kd[it][ib];
+      if (imen <= 0) continue;
+      // LAPLUS = Omega + 1/2 of the block; Lambda of the spin-down (xlap) and spin-up (xlam) components
+      const double xlap = (double)(s.nl[im] + (s.ns[im] + 1) / 2), xlam = xlap - 1.0;
+      const double xlap2 = xlap * xlap, xlam2 = xlam * xlam;
+#pragma omp parallel
+      {
+        std::vector<double> fu(imen), fd(imen), fur(imen), fdr(imen), fuz(imen), fdz(imen), fu2(imen), fd2(imen);
+#pragma omp for schedule(static)
+        for (int ihil = 0; ihil < nghl; ihil++) {
+          for (auto* v : {&fu, &fd, &fur, &fdr, &fuz, &fdz, &fu2, &fd2}) std::fill(v->begin(), v->end(), 0.0);
+          for (int i = 0; i < nd; i++) {
+            const int ja = im + i;
+            const double q = s.qhla[(size_t)ja * nghl + ihil], r1 = s.fi1r[(size_t)ja * nghl + ihil];
+            const double z1 = s.fi1z[(size_t)ja * nghl + ihil], d2 = s.fi2d[(size_t)ja * nghl + ihil];
+            const bool up = s.ns[ja] > 0;
+            double* a0 = up ? fu.data() : fd.data();
+            double* a1 = up ? fur.data() : fdr.data();
+            double* a2 = up ? fuz.data() : fdz.data();
+            double* a3 = up ? fu2.data() : fd2.data();
+            for (int k = 0; k < imen; k++) {
+              const double v = s.V[it][(size_t)s.Kpwi[it][k1 + k] + i];
+              a0[k] += q * v; a1[k] += r1 * v; a2[k] += z1 * v; a3[k] += d2 * v;
+            }
+          }
+          const double y = s.y[ihil], y2 = y * y;
+          double t2 = 0, t4 = 0, t5 = 0;
+          for (int k = 0; k < imen; k++) {
+            const double tw = fur[k] * fur[k] + fdr[k] * fdr[k] + fuz[k] * fuz[k] + fdz[k] * fdz[k];
+            t2 += fu[k] * fu[k] + fd[k] * fd[k];
+            t4 += xlam2 * y2 * fu[k] * fu[k] + xlap2 * y2 * fd[k] * fd[k] + tw;
+            t5 += fu[k] * fu2[k] + fd[k] * fd2[k] + tw;
+          }
+          ro[ihil] += t2; ta[ihil] += t4; dr[ihil] += t5;
+        }
+      }
+    }
+    double ssum = 0;
+    for (int i = 0; i < nghl; i++) ssum += ro[i];
+    const double piu = 2.0 * (double)s.npr[it] / (2.0 * ssum);
+    tau[it].resize(nghl); dro[it].resize(nghl);
+    for (int i = 0; i < nghl; i++) {
+      tau[it][i] = ta[i] * (s.wdcori[i] * piu);
+      dro[it][i] = dr[i] * (s.wdcori[i] * piu * 2.0);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Cache of the expensive stages.  Not part of the reference (which repeats the whole zero-iteration HFBTHO run in every
 // pnfam_main.x launch, 4-18 s at 16 shells); SURVEY.md section 8f row 4.

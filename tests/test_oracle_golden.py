@@ -91,9 +91,40 @@ def test_closed_form_two_body_current_fields(key, tmp_path):
         assert abs(st[k] - gold) / abs(gold) < 1e-9, (key, lab)
 
 
+DME_KEYS = [("S40_2bc_dme", k) for k in ("GT-K0-141100", "GT-K1-141100", "GT-K0-241100", "GT-K0-151100", "GT-K1-151100", "P-K0-121120",
+                                        "P-K1-121120", "P-K0-221120", "PS0-K0-121102", "PS0-K0-221102", "RS0-K0-141222")] + \
+           [("Gd162_2bc_dme", k) for k in ("GT-K1-141100", "GT-K0-151100", "P-K1-121120", "PS0-K0-121102")]
+
+
+@pytest.mark.parametrize("case,key", DME_KEYS)
+def test_density_matrix_expansion_two_body_currents(case, key, tmp_path):
+    """The DME variants (csrc/host/fam_setup.cpp: tbc_dme_exc, tbc_dme_vector, tbc_dme_axial; tau and Delta rho from
+    csrc/host/hfb_front.cpp: kinetic_and_laplacian) through the CPU oracle against the reference binary
+    (tests/golden/make_2bc_dme.py): GT with the DME exchange term alone (141100, 241100) and plus the DIRECT part of the
+    full-FAM field, which the generator computes here because no .tbc file is staged (151100); P / PS0 with the DME vector
+    current / axial charge; spherical 40S and deformed 162Gd.  Strength, every cross-term, iteration count; 1e-9."""
+    import json
+    import shutil
+    from conftest import GOLDEN
+    g = os.path.join(GOLDEN, case)
+    pt = json.load(open(os.path.join(g, "points.json")))["points"][key][0]
+    for f in ("hfbtho_NAMELIST.dat", "hfbtho_output.hel"):
+        shutil.copy(os.path.join(g, f), str(tmp_path))
+    (tmp_path / "x.in").write_text(pt["namelist"])
+    p = host.Problem(str(tmp_path), "x.in")
+    it, si, st = fo.solver_from_problem(p).solve(300, 1e-7)
+    assert it == pt["iters"]
+    labels = ["Strength"] + [p.label(i) for i in range(1, 1 + p.iscalar("nxterms"))]
+    worst = 0.0
+    for k, lab in enumerate(labels):
+        gold = complex(float(pt["rows"][lab][0]), float(pt["rows"][lab][1]))
+        worst = max(worst, abs(st[k] - gold) / abs(gold))
+        assert abs(st[k] - gold) / abs(gold) < 1e-9, (key, lab, st[k], gold)
+    print(case, key, "worst relative difference %.2e" % worst)
+
+
 def test_unsupported_two_body_current_modes_fail_loudly(tmp_path):
-    """The density-matrix-expansion variants are refused with a message (the full-FAM field without its .tbc file is
-    computed: tests/test_tbc_generator.py)."""
+    """Invalid mode digits and the pairing (Delta) part are refused with the reference's messages."""
     import json
     import shutil
     from conftest import GOLDEN
@@ -102,9 +133,9 @@ def test_unsupported_two_body_current_modes_fail_loudly(tmp_path):
     pts = json.load(open(os.path.join(g, "points.json")))["points"]
     for f in ("hfbtho_NAMELIST.dat", "hfbtho_output.hel"):
         shutil.copy(os.path.join(g, f), str(tmp_path))
-    for key, old, new, msg in (("GT-K0-121100", "121100", "141100", "density-matrix-expansion"),
-                               ("P-K0-221110", "221110", "121120", "density-matrix-expansion"),
-                               ("GT-K0-121100", "121100", "161100", "Invalid value")):
+    for key, old, new, msg in (("GT-K0-121100", "121100", "161100", "Invalid value"),
+                               ("GT-K0-121100", "121100", "213100", "Invalid value"),
+                               ("GT-K0-121100", "121100", "112100", "not yet operational")):
         (tmp_path / "x.in").write_text(pts[key][0]["namelist"].replace(old, new))
         with pytest.raises(host.PnfamError, match=msg):
             host.Problem(str(tmp_path), "x.in")
