@@ -156,7 +156,7 @@ void apply_two_body_current_gt(const std::string& tbc_path, const FamBasis& b, c
 // The Yukawa part of the full-FAM two-body-current GT field (effective_2bc_extfield, pnfam_extfield_2bc.f90:26-465;
 // csrc/host/tbc_generator.cpp), low-energy constants stripped as in the .tbc file: c[0..5] = c3 direct, c3 exchange,
 // c4 direct, c4 exchange, momentum direct, momentum exchange (the last two zero without use_p), each of the size and
-// element order of f.mat.elem.  Gamma part, even nuclei at T = 0.
+// element order of f.mat.elem.  Gamma part; even and blocked nuclei, zero and finite temperature.
 struct TbcField { std::vector<double> c[6]; };
 TbcField generate_two_body_current_field(const HfbSolution& s, const FamBasis& b, const ExtField& f, bool use_p);
 // <name>.tbc in the reference's record layout (write_tbc, pnfam_storage.f90:488-559; written atomically)

@@ -20,8 +20,8 @@
 //      coefficients probed from the literal spin functions.
 // Work per nucleus drops by about (N_z+1)^2; OpenMP over the (A, C) pairs.
 //
-// Scope: gamma (particle-hole) part, T = 0, no blocking -- the pairing part (3rd digit of the mode 2, 3) is refused
-// upstream exactly where the reference says "not yet operational".
+// Scope: gamma (particle-hole) part -- the pairing part (3rd digit of the mode 2, 3) is refused upstream exactly where the
+// reference says "not yet operational"; even and blocked (odd, equal filling) nuclei, zero and finite temperature.
 #include <algorithm>
 #include <array>
 #include <cmath>
@@ -617,8 +617,6 @@ struct RadClass {            // one (Omega, n_r, Lambda, s) class of the undoubl
 }  // namespace
 
 TbcField generate_two_body_current_field(const HfbSolution& s, const FamBasis& b, const ExtField& f, bool use_p) {
-  if (s.ft_active) throw std::runtime_error("two-body-current field generator: finite temperature is not supported");
-  if (s.keyblo[0] || s.keyblo[1]) throw std::runtime_error("two-body-current field generator: blocked (odd) nuclei are not supported");
   const int K = f.k;
   if (K < -1 || K > 1) throw std::runtime_error("ERROR, invalid K for extfield 2bc");
   const int nt = s.nt, nbx = s.nb;
@@ -641,18 +639,31 @@ TbcField generate_two_body_current_field(const HfbSolution& s, const FamBasis& b
   const double cy = caux * 4.0;
   q.y_c2r2 = cy * 2.0 * cr2; q.y_2 = cy * 2.0; q.y_4 = cy * 4.0; q.cr2 = caux * cr2; q.two = caux * 2.0;
 
-  // HO-basis density matrices rho_db = rk / 2 = sum_k V_dk V_bk over the pairing window (hfbtho_solver.f90:1822-1856)
+  // HO-basis density matrices rho_db = rk / 2 (hfbtho_solver.f90:1822-1856): sum_k V_dk V_bk over the pairing window;
+  // finite temperature: V (1 - f_k) V + U f_k U with the Fermi-Dirac factor of the quasiparticle energy (:1749-1761);
+  // blocked level (equal filling): - (V V - U U) / 2 of the blocked quasiparticle
   std::vector<size_t> boff(nbx + 1, 0);
   for (int ib = 0; ib < nbx; ib++) boff[ib + 1] = boff[ib] + (size_t)s.id[ib] * s.id[ib];
   std::vector<double> rho[2];
+  const bool hot = s.ft_active && s.temper > 1e-12;
   for (int it = 0; it < 2; it++) {
     rho[it].assign(boff[nbx], 0.0);
     for (int ib = 0; ib < nbx; ib++) {
       const int nd = s.id[ib];
+      double* R = rho[it].data() + boff[ib];
       for (int kk = s.ka[it][ib]; kk < s.ka[it][ib] + s.kd[it][ib]; kk++) {
         const double* V = s.V[it].data() + s.Kpwi[it][kk];
+        const double* U = s.U[it].data() + s.Kpwi[it][kk];
+        const double fT = hot ? 0.5 * (1.0 - std::tanh(0.5 * s.E[it][s.Kqp[it][kk] - 1] / s.temper)) : 0.0;
         for (int n2 = 0; n2 < nd; n2++)
-          for (int n1 = 0; n1 < nd; n1++) rho[it][boff[ib] + n1 + (size_t)n2 * nd] += V[n1] * V[n2];
+          for (int n1 = 0; n1 < nd; n1++) R[n1 + (size_t)n2 * nd] += V[n1] * (1.0 - fT) * V[n2] + U[n1] * fT * U[n2];
+      }
+      if (s.keyblo[it] && s.blo_block[it] == ib + 1 && s.kd[it][ib] > 0) {
+        if (s.blok1k2d[it] <= 0) throw std::runtime_error("two-body-current field generator: no blocking candidate found");
+        const double* V = s.V[it].data() + s.Kpwi[it][s.blok1k2d[it] - 1];
+        const double* U = s.U[it].data() + s.Kpwi[it][s.blok1k2d[it] - 1];
+        for (int n2 = 0; n2 < nd; n2++)
+          for (int n1 = 0; n1 < nd; n1++) R[n1 + (size_t)n2 * nd] += 0.5 * (-V[n1] * V[n2] + U[n1] * U[n2]);
       }
     }
   }

@@ -23,14 +23,20 @@ CASES = [  # (case, source tree, operator K, beta, usep, omega)
     ("S40_betaplus_usep_K0", "S40_All_GT2bc", 0, "+", True, 3.0 + 0.5j),
     ("Gd162_6sh_usep_K1", "Gd162_GT_open_6sh", 1, "-", True, 1.5 + 0.75j),
     ("Gd162_6sh_K0", "Gd162_GT_open_6sh", 0, "-", False, 1.5 + 0.75j),
+    ("Gd163_blocked_K0", "Gd163_blocked_6sh", 0, "-", False, 1.5 + 0.75j),      # odd-A, equal-filling blocking
+    ("Gd163_blocked_usep_K0", "Gd163_blocked_6sh", 0, "-", True, 1.5 + 0.75j),
+    ("Gd162_finiteT_K1", "Gd162_finiteT_6sh", 1, "-", False, 1.5 + 0.75j),      # T = 0.8 MeV
 ]
 
 
 def main():
     out = os.path.join(HERE, "tbc_generator")
     os.makedirs(out, exist_ok=True)
-    strengths = {}
+    spath = os.path.join(out, "strengths.json")
+    strengths = json.load(open(spath))["cases"] if os.path.isfile(spath) else {}
     for case, tree, k, beta, usep, w in CASES:
+        if len(sys.argv) > 1 and case not in sys.argv[1:]:      # usage: make_tbc_generator.py [case ...]
+            continue
         dst = os.path.join(out, case)
         os.makedirs(dst, exist_ok=True)
         tmp = tempfile.mkdtemp()

@@ -4,7 +4,8 @@ effective_2bc_extfield, exes/pnfam/pnfam_extfield_2bc.f90:26-465) -- SURVEY.md s
 Known answers: the <OP>.tbc files the reference itself wrote,
   * tests/golden/S40_All_GT2bc/GT-K{0,1}.tbc: from the reference's own golden tree tests/S40_All_GT2bc/hfb_soln,
   * tests/golden/tbc_generator/*: the reference's prebuilt pnfam_main.x started here without a .tbc file
-    (tests/golden/make_tbc_generator.py): momentum-dependent terms, beta+, a deformed nucleus.
+    (tests/golden/make_tbc_generator.py): momentum-dependent terms, beta+, a deformed nucleus, a blocked odd-A nucleus,
+    finite temperature.
 A run directory WITHOUT the .tbc file makes the library compute the field and cache it in the reference's record layout;
 the file is compared record by record, the field element by element, and the strengths of the complete FAM solve
 (CPU oracle) with the reference's.  Bound: 1e-12 of the largest element of a component (measured: 7e-15)."""
@@ -21,7 +22,8 @@ from oracle import fam_oracle as fo
 from pynfam_b200 import host
 
 GEN = os.path.join(GOLDEN, "tbc_generator")
-GEN_CASES = ["S40_usep_K0", "S40_usep_K1", "S40_betaplus_K1", "S40_betaplus_usep_K0", "Gd162_6sh_usep_K1", "Gd162_6sh_K0"]
+GEN_CASES = ["S40_usep_K0", "S40_usep_K1", "S40_betaplus_K1", "S40_betaplus_usep_K0", "Gd162_6sh_usep_K1", "Gd162_6sh_K0",
+             "Gd163_blocked_K0", "Gd163_blocked_usep_K0", "Gd162_finiteT_K1"]
 
 
 def records(path):
@@ -126,9 +128,10 @@ def test_fam_solve_with_generated_field_matches_golden_point(op, idx, tmp_path):
             assert abs(st[k] - gold[lab]) <= 1e-9 * abs(gold[lab]), (lab, st[k], gold[lab])
 
 
-@pytest.mark.parametrize("case", ["S40_usep_K0", "S40_betaplus_K1", "Gd162_6sh_usep_K1"])
+@pytest.mark.parametrize("case", ["S40_usep_K0", "S40_betaplus_K1", "Gd162_6sh_usep_K1", "Gd163_blocked_usep_K0", "Gd162_finiteT_K1"])
 def test_fam_solve_with_generated_field_matches_reference_binary(case, tmp_path):
-    """The same for the momentum-dependent terms, beta+ and the deformed nucleus: strengths of the reference binary that
+    """The same for the momentum-dependent terms, beta+, the deformed nucleus, the blocked odd-A nucleus (density matrix with
+    the equal-filling term) and finite temperature (thermal density matrix): strengths of the reference binary that
     computed its own field (tests/golden/tbc_generator/strengths.json)."""
     wd = str(tmp_path)
     src = os.path.join(GEN, case)
@@ -144,7 +147,7 @@ def test_fam_solve_with_generated_field_matches_reference_binary(case, tmp_path)
         assert abs(st[k] - g) <= 1e-9 * abs(g), (case, lab, st[k], g)
 
 
-def test_generator_can_be_switched_off_and_refuses_unsupported_solutions(tmp_path):
+def test_generator_can_be_switched_off(tmp_path):
     wd = str(tmp_path)
     stage(os.path.join(GOLDEN, "S40_All_GT2bc"), wd, load_points("S40_All_GT2bc")["GT-K0"][0]["namelist"], "x")
     os.environ["PNFAM_B200_NO_TBC_GENERATOR"] = "1"
@@ -153,18 +156,10 @@ def test_generator_can_be_switched_off_and_refuses_unsupported_solutions(tmp_pat
             host.Problem(wd, "x.in")
     finally:
         del os.environ["PNFAM_B200_NO_TBC_GENERATOR"]
-    # finite temperature: the density matrix of the generator has no thermal terms -> loud refusal
-    wd2 = str(tmp_path / "hot")
-    os.makedirs(wd2)
-    nml = load_points("Gd162_finiteT_6sh")["GT-K0"][0]["namelist"].replace("two_body_current_mode = 0", "two_body_current_mode = 111100")
-    assert "111100" in nml
-    stage(os.path.join(GOLDEN, "Gd162_finiteT_6sh"), wd2, nml, "x")
-    with pytest.raises(host.PnfamError, match="finite temperature"):
-        host.Problem(wd2, "x.in")
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("case", ["golden:GT-K1", "S40_usep_K1", "Gd162_6sh_usep_K1"])
+@pytest.mark.parametrize("case", ["golden:GT-K1", "S40_usep_K1", "Gd162_6sh_usep_K1", "Gd163_blocked_usep_K0", "Gd162_finiteT_K1"])
 def test_gpu_solve_with_generated_field(case, tmp_path):
     """The product path end to end: no .tbc in the run directory -> host generator -> batched GPU solve -> the reference's
     strengths (golden tree: all 30 computed points of GT-K1; reference binary: momentum terms, deformed nucleus), 1e-9."""
