@@ -377,10 +377,15 @@ double rad_cmplx_imag(const Tables& t, int g, int kx, int ky, int ni, int li, in
 //   sum_{yB, yD} cB cD [ Im i^(yB - yD) Q_re + Re i^(yB - yD) Q_im ][yB][yD][N_B - yB][N_D - yD]
 inline int ipow_re(int n) { n = ((n % 4) + 4) % 4; return n == 0 ? 1 : n == 2 ? -1 : 0; }
 inline int ipow_im(int n) { n = ((n % 4) + 4) % 4; return n == 1 ? 1 : n == 3 ? -1 : 0; }
+// Storage: Q is only needed where XB + YB = N_B and XD + YD = N_D are total Cartesian quanta of a basis state, so it is
+// kept as Q[g][tri(N_B, yB)][tri(N_D, yD)], tri(N, y) = N (N + 1) / 2 + y: 1.1 MB per (kind, orientation) at 16 shells,
+// and the sum of one element walks rows of it.
+inline int tri(int N, int y) { return N * (N + 1) / 2 + y; }
 void build_q(const Tables& t, int kind, bool exc, int nA, int lA, int nC, int lC, std::vector<double>& Q, int mode = 0, int ky = G00) {
   const size_t n1 = t.nsm + 1, n2 = n1 * n1, n3 = n2 * n1, slab = n3 * n1;
   const int nmax = t.nrlx;
-  Q.assign((size_t)NG * slab, 0.0);
+  const size_t M = (size_t)(nmax + 1) * (nmax + 2) / 2, qslab = M * M;
+  Q.assign((size_t)NG * qslab, 0.0);
   const std::vector<double>& MX = exc ? t.rkT[kind] : t.rk[kind];
   const std::vector<double>& MY = exc ? t.rkT[ky] : t.rk[ky];
   const int NA = 2 * nA + std::abs(lA), NC = 2 * nC + std::abs(lC);
@@ -390,7 +395,7 @@ void build_q(const Tables& t, int kind, bool exc, int nA, int lA, int nC, int lC
   for (int g = 0; g < NG; g++) {
     const double* mx = MX.data() + (size_t)g * slab;
     const double* my = MY.data() + (size_t)g * slab;
-    double* q = Q.data() + (size_t)g * slab;
+    double* q = Q.data() + (size_t)g * qslab;
     for (int yA = 0; yA <= NA; yA++)
       for (int yC = 0; yC <= NC; yC++) {
         const double sgn = mode == 0 ? ((((yA + (yA + yC) / 2) % 2) ? -1.0 : 1.0)) : mode == 1 ? (double)ipow_re(yA - yC) : (double)ipow_im(yA - yC);
@@ -400,12 +405,11 @@ void build_q(const Tables& t, int kind, bool exc, int nA, int lA, int nC, int lC
           for (int YD = (yA + YB + yC + ypar) % 2; YD <= nmax; YD += 2) {
             const double l = w * my[(size_t)yA * n3 + (size_t)YB * n2 + (size_t)yC * n1 + YD];
             if (l == 0.0) continue;
-            double* qrow = q + ((size_t)YB * n1 + YD) * n2;
             const double* mrow = mx + (size_t)(NA - yA) * n3 + (size_t)(NC - yC) * n1;
             for (int XB = 0; XB <= nmax - YB; XB++) {     // the x element vanishes for an odd (sum + d + [p != 0])
-              double* qq = qrow + (size_t)XB * n1;
+              double* qq = q + (size_t)tri(XB + YB, YB) * M;
               const double* mm = mrow + (size_t)XB * n2;
-              for (int XD = (NA - yA + NC - yC + XB + xpar) % 2; XD <= nmax - YD; XD += 2) qq[XD] += l * mm[XD];
+              for (int XD = (NA - yA + NC - yC + XB + xpar) % 2; XD <= nmax - YD; XD += 2) qq[tri(XD + YD, YD)] += l * mm[XD];
             }
           }
       }
@@ -413,16 +417,17 @@ void build_q(const Tables& t, int kind, bool exc, int nA, int lA, int nC, int lC
 }
 
 inline double radx_q(const Tables& t, const double* qg, int nB, int lB, int nD, int lD) {
-  const size_t n1 = t.nsm + 1, n2 = n1 * n1;
   const int NB = 2 * nB + std::abs(lB), ND = 2 * nD + std::abs(lD);
+  const size_t M = (size_t)(t.nrlx + 1) * (t.nrlx + 2) / 2;
   const double* CB = &t.cp2c[((size_t)nB * (4 * t.nsh + 1) + (lB + 2 * t.nsh)) * (2 * t.nsh + 1)];
   const double* CD = &t.cp2c[((size_t)nD * (4 * t.nsh + 1) + (lD + 2 * t.nsh)) * (2 * t.nsh + 1)];
   double v = 0.0;
   for (int yB = 0; yB <= NB; yB++) {
+    const double* row = qg + (size_t)tri(NB, yB) * M + tri(ND, 0);
     double acc = 0.0;
     for (int yD = 0; yD <= ND; yD++) {
       const double sg = ((yB + (yB + yD + 1) / 2) % 2) ? -1.0 : 1.0;
-      acc += sg * CD[yD] * qg[((size_t)yB * n1 + yD) * n2 + (size_t)(NB - yB) * n1 + (ND - yD)];
+      acc += sg * CD[yD] * row[yD];
     }
     v += CB[yB] * acc;
   }
@@ -430,17 +435,15 @@ inline double radx_q(const Tables& t, const double* qg, int nB, int lB, int nD, 
 }
 
 inline double rad_q_imag(const Tables& t, const double* qre, const double* qim, int nB, int lB, int nD, int lD) {
-  const size_t n1 = t.nsm + 1, n2 = n1 * n1;
   const int NB = 2 * nB + std::abs(lB), ND = 2 * nD + std::abs(lD);
+  const size_t M = (size_t)(t.nrlx + 1) * (t.nrlx + 2) / 2;
   const double* CB = &t.cp2c[((size_t)nB * (4 * t.nsh + 1) + (lB + 2 * t.nsh)) * (2 * t.nsh + 1)];
   const double* CD = &t.cp2c[((size_t)nD * (4 * t.nsh + 1) + (lD + 2 * t.nsh)) * (2 * t.nsh + 1)];
   double v = 0.0;
   for (int yB = 0; yB <= NB; yB++) {
+    const size_t at = (size_t)tri(NB, yB) * M + tri(ND, 0);
     double acc = 0.0;
-    for (int yD = 0; yD <= ND; yD++) {
-      const size_t at = ((size_t)yB * n1 + yD) * n2 + (size_t)(NB - yB) * n1 + (ND - yD);
-      acc += CD[yD] * (ipow_im(yB - yD) * qre[at] + ipow_re(yB - yD) * qim[at]);
-    }
+    for (int yD = 0; yD <= ND; yD++) acc += CD[yD] * (ipow_im(yB - yD) * qre[at + yD] + ipow_re(yB - yD) * qim[at + yD]);
     v += CB[yB] * acc;
   }
   return v;
@@ -624,7 +627,7 @@ TbcField generate_two_body_current_field(const HfbSolution& s, const FamBasis& b
   const bool timing = getenv("PNFAM_B200_SETUP_TIMING") != nullptr;
   // self-check switch: the reference's own four-fold Cartesian sum for every radial element instead of the intermediate
   const bool literal = getenv("PNFAM_B200_TBC_LITERAL_RADIAL") != nullptr;
-  double t_phase = omp_get_wtime(), t_jr = 0.0, t_con = 0.0;
+  double t_phase = omp_get_wtime(), t_jr = 0.0, t_con = 0.0, t_q = 0.0;
   auto lap = [&](const char* what) {
     if (timing) { const double now = omp_get_wtime(); std::fprintf(stderr, "[setup]   2BC %-18s %.3f s\n", what, now - t_phase); t_phase = now; }
   };
@@ -792,7 +795,7 @@ TbcField generate_two_body_current_field(const HfbSolution& s, const FamBasis& b
 
     lap("z contraction");
     // radial elements per (A, C) and the contraction
-#pragma omp parallel for schedule(dynamic) reduction(+ : t_jr, t_con)
+#pragma omp parallel for schedule(dynamic) reduction(+ : t_jr, t_con, t_q)
     for (int ic = 0; ic < (int)combos.size(); ic++) {
       const double tt0 = omp_get_wtime();
       const std::array<int, 2> kA = gkeys[combos[ic].A], kC = gkeys[combos[ic].C];
@@ -801,9 +804,9 @@ TbcField generate_two_body_current_field(const HfbSolution& s, const FamBasis& b
       std::vector<double> JR((size_t)npairs * 4 * wrec, 0.0);
       std::vector<char> use_n(npairs, 0), use_t(npairs, 0);
       std::vector<double> Q[NKIND][2];
-      const size_t qslab = (size_t)(t.nsm + 1) * (t.nsm + 1) * (t.nsm + 1) * (t.nsm + 1);
+      const size_t qM = (size_t)(t.nrlx + 1) * (t.nrlx + 2) / 2, qslab = qM * qM;
       auto q_of = [&](int kind, int exc, int g) -> const double* {
-        if (Q[kind][exc].empty()) build_q(t, kind, exc != 0, ra, la, rc, lc, Q[kind][exc]);
+        if (Q[kind][exc].empty()) { const double q0 = omp_get_wtime(); build_q(t, kind, exc != 0, ra, la, rc, lc, Q[kind][exc]); t_q += omp_get_wtime() - q0; }
         return Q[kind][exc].data() + (size_t)g * qslab;
       };
       std::vector<double> QC[NKIND][2][2];      // rad_cmplx intermediates: [y kind][exc][re | im]
@@ -878,8 +881,8 @@ TbcField generate_two_body_current_field(const HfbSolution& s, const FamBasis& b
     }
     lap("radial + spin");
   }
-  if (timing) std::fprintf(stderr, "[setup]   2BC thread-seconds: radial elements %.2f, contraction %.2f (%d classes, %d pairs, %d (A,C))\n",
-                           t_jr, t_con, ncls, npairs, (int)combos.size());
+  if (timing) std::fprintf(stderr, "[setup]   2BC thread-seconds: radial elements %.2f (intermediates %.2f), contraction %.2f (%d classes, %d pairs, %d (A,C))\n",
+                           t_jr, t_q, t_con, ncls, npairs, (int)combos.size());
 
   // spin sort of rows and columns (reorder_blockmatrix_basis 'a' with new_order, pnfam_extfield_2bc.f90:903-913)
   TbcField out;

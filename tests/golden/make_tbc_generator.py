@@ -26,6 +26,8 @@ CASES = [  # (case, source tree, operator K, beta, usep, omega)
     ("Gd163_blocked_K0", "Gd163_blocked_6sh", 0, "-", False, 1.5 + 0.75j),      # odd-A, equal-filling blocking
     ("Gd163_blocked_usep_K0", "Gd163_blocked_6sh", 0, "-", True, 1.5 + 0.75j),
     ("Gd162_finiteT_K1", "Gd162_finiteT_6sh", 1, "-", False, 1.5 + 0.75j),      # T = 0.8 MeV
+    # a basis size of BASELINE.json configs[4]: about an hour of the reference on 6 threads (the .tbc is 0.9 MB)
+    ("Gd162_12sh_K0", "Gd162_SKOP_12sh", 0, "-", False, 2.0 + 1.0j),
 ]
 
 
@@ -54,7 +56,7 @@ def main():
         assert "beta_type = '%s'" % beta in nml
         open(os.path.join(wd, name + ".in"), "w").write(nml)
         assert not os.path.exists(os.path.join(wd, name + ".tbc"))
-        dat, wall, log = refrun.run_pnfam(wd, name + ".in", threads=4)
+        dat, wall, log = refrun.run_pnfam(wd, name + ".in", threads=int(os.environ.get("REF_THREADS", "4")), timeout=4 * 3600)
         assert "Calculating 2BC matrix elements" in log, log[-2000:]
         shutil.copy(os.path.join(wd, name + ".tbc"), dst)
         open(os.path.join(dst, name + ".in"), "w").write(nml)
