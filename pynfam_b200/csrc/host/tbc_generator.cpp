@@ -406,10 +406,14 @@ void build_q(const Tables& t, int kind, bool exc, int nA, int lA, int nC, int lC
             const double l = w * my[(size_t)yA * n3 + (size_t)YB * n2 + (size_t)yC * n1 + YD];
             if (l == 0.0) continue;
             const double* mrow = mx + (size_t)(NA - yA) * n3 + (size_t)(NC - yC) * n1;
-            for (int XB = 0; XB <= nmax - YB; XB++) {     // the x element vanishes for an odd (sum + d + [p != 0])
+            // target column tri(XD + YD, YD) = tri0[XD]: hoisted, the x element vanishes for an odd (sum + d + [p != 0])
+            int tri0[64];
+            for (int XD = 0; XD <= nmax - YD; XD++) tri0[XD] = tri(XD + YD, YD);
+            const int xd_par = (NA - yA + NC - yC + xpar) % 2;
+            for (int XB = 0; XB <= nmax - YB; XB++) {
               double* qq = q + (size_t)tri(XB + YB, YB) * M;
               const double* mm = mrow + (size_t)XB * n2;
-              for (int XD = (NA - yA + NC - yC + XB + xpar) % 2; XD <= nmax - YD; XD += 2) qq[tri(XD + YD, YD)] += l * mm[XD];
+              for (int XD = (xd_par + XB) % 2; XD <= nmax - YD; XD += 2) qq[tri0[XD]] += l * mm[XD];
             }
           }
       }
