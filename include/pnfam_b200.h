@@ -45,6 +45,25 @@ int pnfam_problem_array_f64(pnfam_problem* p, const char* name, const double** p
 int pnfam_problem_array_i32(pnfam_problem* p, const char* name, const int32_t** ptr, int64_t* n);
 /* which: 0 operator label, 1..nxterms cross-term labels, -1 interaction name, -2 output base name */
 int pnfam_problem_label(const pnfam_problem* p, int which, char* out, int outlen);
+/* The Yukawa part of the full-FAM two-body-current Gamow-Teller field from the arrays the reference's own routine works on:
+ * replaces  effective_2bc_extfield(op)  exes/pnfam/pnfam_extfield_2bc.f90:26-465, called by setup_extfield
+ * (exes/pnfam/pnfam_solver.f90:622-640) when <name>.tbc cannot be read.  Inputs are what that routine takes from the modules
+ * hfb_solution / hfbtho / type_blockmatrix (exes/pnfam/hfbtho_solution.f90:40-58):
+ *   ntx, nbx        states and blocks of the HFBTHO basis (Omega > 0 only);  id[nbx] = states per block
+ *   hnz, hnr, hnl, hns [ntx]   n_z, n_r, Lambda, 2 s of every state (hfbtho's nz, nr, nl, ns)
+ *   bz, bp          oscillator lengths
+ *   rmat            HO-basis density matrix rk: column-major (ld_rmat, 2 nbx); column ib holds the id(ib)^2 elements of the
+ *                   neutron block ib, column nbx + ib of the proton block (rho_db = rmat / 2)
+ *   ir2c, ir2m [2 nbx]   1-based block structure of op%mat in the doubled basis (type_blockmatrix);  nxy = size(op%mat%elem)
+ *   k, beta_minus   operator K (-1, 0, +1) and beta type;  use_p = two_body_current_usep
+ *   spin_sorted     1: rows / columns of every block in the spin-sorted order of the USE_HBLAS = 1 build, 0: original order
+ * Outputs (each [nxy], may be NULL): the six parts of op%gam with the low-energy constants stripped, exactly the records
+ * write_tbc stores (exes/pnfam/pnfam_storage.f90:526-534):  op%mat%elem = c3 (c3d + c3e) + (c4 + 1/4) (c4d + c4e) + cpd + cpe. */
+int pnfam_host_effective_2bc_extfield(int32_t ntx, int32_t nbx, const int32_t* id, const int32_t* hnz, const int32_t* hnr,
+                                      const int32_t* hnl, const int32_t* hns, double bz, double bp, const double* rmat,
+                                      int64_t ld_rmat, const int32_t* ir2c, const int32_t* ir2m, int64_t nxy, int32_t k,
+                                      int32_t beta_minus, int32_t use_p, int32_t spin_sorted, double* c3d, double* c3e,
+                                      double* c4d, double* c4e, double* cpd, double* cpe, char* err, int errlen);
 /* OpenMP threads of the host set-up (n <= 0: unchanged); returns the previous setting.  The reconstructed HFB solution
  * is kept in <rundir>/.pnfam_b200_hfb_<hash of the two input files>.cache (PNFAM_B200_CACHE_DIR: another directory,
  * PNFAM_B200_NO_CACHE: off): later launches in directories holding the same two files load it instead of repeating

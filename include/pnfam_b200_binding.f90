@@ -177,6 +177,29 @@ module pnfam_b200_binding
          character(kind=c_char) :: err(*)
          integer(c_int), value :: errlen
       end function
+
+      ! libpnfam_host.so: the Yukawa part of the full-FAM two-body-current GT field, replaces the call
+      !    call effective_2bc_extfield(f)            (pnfam_solver.f90:629, pnfam_extfield_2bc.f90:26-465)
+      ! with the arrays that routine takes from hfb_solution / hfbtho / type_blockmatrix:
+      !    ierr = pnfam_host_effective_2bc_extfield(ntx, nbx, hdb_half, hnz, hnr, hnl, hns, bz, bp, rmat, &
+      !              int(size(rmat,1),c_int64_t), f%mat%ir2c, f%mat%ir2m, int(size(f%mat%elem),c_int64_t), f%k, &
+      !              merge(1,0,f%beta_minus), merge(1,0,two_body_current_usep), 1, &
+      !              f%gam%c3d, f%gam%c3e, f%gam%c4d, f%gam%c4e, f%gam%cpd, f%gam%cpe, err, len(err))
+      ! (hdb_half = id(1:nbx), the block sizes of the undoubled HFBTHO basis); then mult_gamdel_lecs + calc_totgamdel as
+      ! read_tbc does (pnfam_storage.f90:654-661).
+      integer(c_int) function pnfam_host_effective_2bc_extfield(ntx, nbx, id, hnz, hnr, hnl, hns, bz, bp, rmat, ld_rmat, &
+            ir2c, ir2m, nxy, k, beta_minus, use_p, spin_sorted, c3d, c3e, c4d, c4e, cpd, cpe, err, errlen) &
+            bind(C, name="pnfam_host_effective_2bc_extfield")
+         import
+         integer(c_int32_t), value :: ntx, nbx, k, beta_minus, use_p, spin_sorted
+         integer(c_int32_t), intent(in) :: id(*), hnz(*), hnr(*), hnl(*), hns(*), ir2c(*), ir2m(*)
+         real(c_double), value :: bz, bp
+         real(c_double), intent(in) :: rmat(*)
+         integer(c_int64_t), value :: ld_rmat, nxy
+         real(c_double), intent(out) :: c3d(*), c3e(*), c4d(*), c4e(*), cpd(*), cpe(*)
+         character(kind=c_char) :: err(*)
+         integer(c_int), value :: errlen
+      end function
    end interface
 
    ! calc_hamiltonian-shaped wrapper (to be placed in the host's own module, after `contains`): point `calc_hamiltonian => calc_dHsp_b200` in setup_hamiltonian

@@ -1,4 +1,5 @@
 // C ABI of the host set-up library (libpnfam_host.so): declared in include/pnfam_b200.h.
+#include <algorithm>
 #include <cstring>
 #include <map>
 #include <string>
@@ -75,7 +76,7 @@ int pnfam_problem_scalar(const pnfam_problem* h, const char* name, double* out) 
       {"energy_shift_prot", in.energy_shift_prot}, {"energy_shift_neut", in.energy_shift_neut},
       {"ala_n", p.nuc->hfb.ala[0]}, {"ala_p", p.nuc->hfb.ala[1]},
       {"inner_n", p.nuc->hfb.inner[0]}, {"inner_p", p.nuc->hfb.inner[1]},
-      {"setup_seconds", p.setup_seconds},
+      {"setup_seconds", p.setup_seconds}, {"hfb_bz", p.nuc->hfb.bz}, {"hfb_bp", p.nuc->hfb.bp}, {"hfb_nt", p.nuc->hfb.nt}, {"hfb_nb", p.nuc->hfb.nb},
   };
   auto it = m.find(n);
   if (it == m.end()) return 1;
@@ -103,6 +104,26 @@ int pnfam_problem_array_f64(pnfam_problem* h, const char* name, const double** p
   };
   auto it = m.find(nm);
   if (it != m.end()) v = it->second;
+  if (!v && nm == "hfb_rk") {
+    // HFBTHO's HO-basis density matrix rk(nqx, 2 nbx) = pnFAM's rmat (hfbtho_solution.f90:57): column ib = block ib of the
+    // neutrons, column nbx + ib = of the protons, id(ib)^2 elements each, column-major; nqx = the largest id^2
+    auto& c = h->f64_cache["hfb_rk"];
+    if (c.empty()) {
+      const TbcProblem pr = tbc_problem_from(s, p.f, false);
+      size_t nqx = 0;
+      for (int d : s.id) nqx = std::max(nqx, (size_t)d * d);
+      c.assign(nqx * 2 * s.nb, 0.0);
+      for (int it = 0; it < 2; it++) {
+        size_t off = 0;
+        for (int ib = 0; ib < s.nb; ib++) {
+          const size_t d2 = (size_t)s.id[ib] * s.id[ib];
+          for (size_t i = 0; i < d2; i++) c[(size_t)(it * s.nb + ib) * nqx + i] = 2.0 * pr.rho[it][off + i];
+          off += d2;
+        }
+      }
+    }
+    v = &c;
+  }
   if (!v && nm.rfind("g_elem_", 0) == 0) {
     size_t i = (size_t)std::stoi(nm.substr(7));
     if (i < p.g.size()) v = &p.g[i].mat.elem;
@@ -122,7 +143,8 @@ int pnfam_problem_array_i32(pnfam_problem* h, const char* name, const int32_t** 
       {"db", &b.db}, {"isstart", &b.isstart}, {"nr", &b.nr}, {"nz", &b.nz}, {"nl", &b.nl}, {"ns", &b.ns},
       {"npar", &b.npar}, {"num_spin_up", &b.num_spin_up}, {"sep_zrow", &b.sep_zrow},
       {"f_ir2c", &p.f.mat.ir2c}, {"f_ic2r", &p.f.mat.ic2r}, {"f_ir2m", &p.f.mat.ir2m}, {"f_ic2m", &p.f.mat.ic2m},
-      {"hfb_id", &p.nuc->hfb.id},
+      {"hfb_id", &p.nuc->hfb.id}, {"hfb_nz", &p.nuc->hfb.nz}, {"hfb_nr", &p.nuc->hfb.nr}, {"hfb_nl", &p.nuc->hfb.nl},
+      {"hfb_ns", &p.nuc->hfb.ns},
   };
   auto it = m.find(nm);
   if (it != m.end()) v = it->second;
@@ -147,6 +169,44 @@ int pnfam_problem_label(const pnfam_problem* h, int which, char* out, int outlen
   else return 1;
   set_err(out, outlen, s);
   return 0;
+}
+
+// effective_2bc_extfield with plain arrays (see include/pnfam_b200.h)
+int pnfam_host_effective_2bc_extfield(int32_t ntx, int32_t nbx, const int32_t* id, const int32_t* hnz, const int32_t* hnr,
+                                      const int32_t* hnl, const int32_t* hns, double bz, double bp, const double* rmat,
+                                      int64_t ld_rmat, const int32_t* ir2c, const int32_t* ir2m, int64_t nxy, int32_t k,
+                                      int32_t beta_minus, int32_t use_p, int32_t spin_sorted, double* c3d, double* c3e,
+                                      double* c4d, double* c4e, double* cpd, double* cpe, char* err, int errlen) {
+  try {
+    if (ntx <= 0 || nbx <= 0 || !id || !hnz || !hnr || !hnl || !hns || !rmat || !ir2c || !ir2m || nxy <= 0)
+      throw std::runtime_error("pnfam_host_effective_2bc_extfield: missing argument");
+    TbcProblem pr;
+    pr.nt = ntx; pr.nb = nbx;
+    pr.id.assign(id, id + nbx);
+    pr.nz.assign(hnz, hnz + ntx); pr.nr.assign(hnr, hnr + ntx); pr.nl.assign(hnl, hnl + ntx); pr.ns.assign(hns, hns + ntx);
+    pr.bz = bz; pr.bp = bp;
+    int tot = 0;
+    for (int ib = 0; ib < nbx; ib++) {
+      if (id[ib] <= 0 || (int64_t)id[ib] * id[ib] > ld_rmat) throw std::runtime_error("pnfam_host_effective_2bc_extfield: block larger than ld_rmat");
+      tot += id[ib];
+    }
+    if (tot != ntx) throw std::runtime_error("pnfam_host_effective_2bc_extfield: sum of id differs from ntx");
+    for (int it = 0; it < 2; it++)
+      for (int ib = 0; ib < nbx; ib++) {
+        const double* col = rmat + (size_t)(it * nbx + ib) * ld_rmat;
+        for (int64_t i = 0; i < (int64_t)id[ib] * id[ib]; i++) pr.rho[it].push_back(0.5 * col[i]);      // rho_db = rmat / 2
+      }
+    pr.ir2c.assign(ir2c, ir2c + 2 * nbx); pr.ir2m.assign(ir2m, ir2m + 2 * nbx);
+    pr.nxy = (size_t)nxy; pr.K = k; pr.beta_minus = beta_minus != 0; pr.use_p = use_p != 0; pr.spin_sorted = spin_sorted != 0;
+    const TbcField f = generate_two_body_current_field(pr);
+    double* out[6] = {c3d, c3e, c4d, c4e, cpd, cpe};
+    for (int o = 0; o < 6; o++)
+      if (out[o]) std::memcpy(out[o], f.c[o].data(), (size_t)nxy * sizeof(double));
+    return 0;
+  } catch (const std::exception& e) {
+    set_err(err, errlen, e.what());
+    return 1;
+  }
 }
 
 // number of OpenMP threads of the host set-up (HFB reconstruction, tables, external fields); n <= 0: leave unchanged.

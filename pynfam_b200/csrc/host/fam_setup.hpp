@@ -158,6 +158,23 @@ void apply_two_body_current_gt(const std::string& tbc_path, const FamBasis& b, c
 // c4 direct, c4 exchange, momentum direct, momentum exchange (the last two zero without use_p), each of the size and
 // element order of f.mat.elem.  Gamma part; even and blocked nuclei, zero and finite temperature.
 struct TbcField { std::vector<double> c[6]; };
+// The contraction described by plain arrays -- what effective_2bc_extfield takes from the modules hfb_solution, hfbtho and
+// type_blockmatrix: the undoubled HFBTHO basis (blocks id, quantum numbers of every state, oscillator lengths), the
+// HO-basis density matrices rho = rmat / 2 of neutrons and protons (packed block by block, column-major id x id), the block
+// structure of the operator in the doubled basis (1-based ir2c, ir2m), K, beta type.  spin_sorted: rows and columns of
+// every block in the spin-sorted order of the USE_HBLAS = 1 build (the shipped one), else the original order.
+struct TbcProblem {
+  int nt = 0, nb = 0;
+  std::vector<int> id, nz, nr, nl, ns;
+  double bz = 0, bp = 0;
+  std::vector<double> rho[2];
+  std::vector<int> ir2c, ir2m;
+  size_t nxy = 0;
+  int K = 0;
+  bool beta_minus = true, use_p = false, spin_sorted = true;
+};
+TbcField generate_two_body_current_field(const TbcProblem& pr);
+TbcProblem tbc_problem_from(const HfbSolution& s, const ExtField& f, bool use_p);
 TbcField generate_two_body_current_field(const HfbSolution& s, const FamBasis& b, const ExtField& f, bool use_p);
 // <name>.tbc in the reference's record layout (write_tbc, pnfam_storage.f90:488-559; written atomically)
 void write_tbc(const std::string& path, const FamBasis& b, const FamInput& in, const ExtField& f, const TwoBody& tb, const TbcField& fld);

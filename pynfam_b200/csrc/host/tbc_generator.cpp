@@ -32,6 +32,7 @@
 #include <stdexcept>
 
 #include <omp.h>
+#include <unistd.h>
 
 #include "fam_setup.hpp"
 
@@ -187,7 +188,7 @@ double me1d(const Tables& t, bool z, int g, int ni, int nj, int nk, int nl, int 
   throw std::runtime_error("two-body currents: derivative combination not implemented");
 }
 
-Tables build_tables(const HfbSolution& s, bool use_p) {
+Tables build_tables(const TbcProblem& s, bool use_p) {
   Tables t;
   t.bz = s.bz; t.bp = s.bp;
   for (int i = 0; i < s.nt; i++) {
@@ -623,11 +624,14 @@ struct RadClass {            // one (Omega, n_r, Lambda, s) class of the undoubl
 
 }  // namespace
 
-TbcField generate_two_body_current_field(const HfbSolution& s, const FamBasis& b, const ExtField& f, bool use_p) {
-  const int K = f.k;
+TbcField generate_two_body_current_field(const TbcProblem& s) {
+  const int K = s.K;
   if (K < -1 || K > 1) throw std::runtime_error("ERROR, invalid K for extfield 2bc");
+  const bool use_p = s.use_p;
   const int nt = s.nt, nbx = s.nb;
-  const size_t nxy = f.mat.elem.size();
+  const size_t nxy = s.nxy;
+  if ((int)s.id.size() != nbx || (int)s.nz.size() != nt || (int)s.ir2c.size() != 2 * nbx || (int)s.ir2m.size() != 2 * nbx)
+    throw std::runtime_error("two-body-current field generator: inconsistent array sizes");
   const bool timing = getenv("PNFAM_B200_SETUP_TIMING") != nullptr;
   // self-check switch: the reference's own four-fold Cartesian sum for every radial element instead of the intermediate
   const bool literal = getenv("PNFAM_B200_TBC_LITERAL_RADIAL") != nullptr;
@@ -646,37 +650,16 @@ TbcField generate_two_body_current_field(const HfbSolution& s, const FamBasis& b
   const double cy = caux * 4.0;
   q.y_c2r2 = cy * 2.0 * cr2; q.y_2 = cy * 2.0; q.y_4 = cy * 4.0; q.cr2 = caux * cr2; q.two = caux * 2.0;
 
-  // HO-basis density matrices rho_db = rk / 2 (hfbtho_solver.f90:1822-1856): sum_k V_dk V_bk over the pairing window;
-  // finite temperature: V (1 - f_k) V + U f_k U with the Fermi-Dirac factor of the quasiparticle energy (:1749-1761);
-  // blocked level (equal filling): - (V V - U U) / 2 of the blocked quasiparticle
   std::vector<size_t> boff(nbx + 1, 0);
   for (int ib = 0; ib < nbx; ib++) boff[ib + 1] = boff[ib] + (size_t)s.id[ib] * s.id[ib];
-  std::vector<double> rho[2];
-  const bool hot = s.ft_active && s.temper > 1e-12;
-  for (int it = 0; it < 2; it++) {
-    rho[it].assign(boff[nbx], 0.0);
-    for (int ib = 0; ib < nbx; ib++) {
-      const int nd = s.id[ib];
-      double* R = rho[it].data() + boff[ib];
-      for (int kk = s.ka[it][ib]; kk < s.ka[it][ib] + s.kd[it][ib]; kk++) {
-        const double* V = s.V[it].data() + s.Kpwi[it][kk];
-        const double* U = s.U[it].data() + s.Kpwi[it][kk];
-        const double fT = hot ? 0.5 * (1.0 - std::tanh(0.5 * s.E[it][s.Kqp[it][kk] - 1] / s.temper)) : 0.0;
-        for (int n2 = 0; n2 < nd; n2++)
-          for (int n1 = 0; n1 < nd; n1++) R[n1 + (size_t)n2 * nd] += V[n1] * (1.0 - fT) * V[n2] + U[n1] * fT * U[n2];
-      }
-      if (s.keyblo[it] && s.blo_block[it] == ib + 1 && s.kd[it][ib] > 0) {
-        if (s.blok1k2d[it] <= 0) throw std::runtime_error("two-body-current field generator: no blocking candidate found");
-        const double* V = s.V[it].data() + s.Kpwi[it][s.blok1k2d[it] - 1];
-        const double* U = s.U[it].data() + s.Kpwi[it][s.blok1k2d[it] - 1];
-        for (int n2 = 0; n2 < nd; n2++)
-          for (int n1 = 0; n1 < nd; n1++) R[n1 + (size_t)n2 * nd] += 0.5 * (-V[n1] * V[n2] + U[n1] * U[n2]);
-      }
-    }
-  }
+  if (s.rho[0].size() != boff[nbx] || s.rho[1].size() != boff[nbx])
+    throw std::runtime_error("two-body-current field generator: density matrices of the wrong size");
+  const std::vector<double>* rho = s.rho;
+  std::vector<int> ia(nbx, 0);
+  for (int ib = 1; ib < nbx; ib++) ia[ib] = ia[ib - 1] + s.id[ib - 1];
   std::vector<int> blk(nt), pos(nt);
   for (int ib = 0; ib < nbx; ib++)
-    for (int i = 0; i < s.id[ib]; i++) { blk[s.ia[ib] + i] = ib; pos[s.ia[ib] + i] = i; }
+    for (int i = 0; i < s.id[ib]; i++) { blk[ia[ib] + i] = ib; pos[ia[ib] + i] = i; }
 
   // radial classes in the reference's order (Omega, n_r, Lambda, s), members by n_z
   std::vector<RadClass> cls;
@@ -733,7 +716,7 @@ TbcField generate_two_body_current_field(const HfbSolution& s, const FamBasis& b
       bool any = false;
       for (int a : group[gkeys[A]]) {
         for (int c : group[gkeys[C]])
-          if (f.mat.ir2c[dst[a].blk] - 1 == dst[c].blk) { any = true; break; }
+          if (s.ir2c[dst[a].blk] - 1 == dst[c].blk) { any = true; break; }
         if (any) break;
       }
       if (any) combos.push_back({A, C});
@@ -745,7 +728,7 @@ TbcField generate_two_body_current_field(const HfbSolution& s, const FamBasis& b
   for (int sa = -1; sa <= 1; sa += 2)
     for (int sc = -1; sc <= 1; sc += 2)
       for (int sd = -1; sd <= 1; sd += 2)
-        for (int sb = -1; sb <= 1; sb += 2) sc_tab[sidx(sa, sc, sd, sb)] = spin_coef(sa, sc, sd, sb, f.beta_minus);
+        for (int sb = -1; sb <= 1; sb += 2) sc_tab[sidx(sa, sc, sd, sb)] = spin_coef(sa, sc, sd, sb, s.beta_minus);
 
   struct SpinTerm { int out, src, comp; double coef; };
   std::vector<std::vector<SpinTerm>> sc_list(16);
@@ -776,7 +759,7 @@ TbcField generate_two_body_current_field(const HfbSolution& s, const FamBasis& b
         double* w = W.data() + ((size_t)(za - za0) * nz1 + zc) * wsz;
         double Jd[NCOMP], Je[NCOMP];
         for (int ib = 0; ib < nbx; ib++) {
-          const int nd = s.id[ib], i0 = s.ia[ib];
+          const int nd = s.id[ib], i0 = ia[ib];
           for (int jb = 0; jb < nd; jb++)
             for (int jd = 0; jd < nd; jd++) {
               const int sb_ = i0 + jb, sd_ = i0 + jd;
@@ -853,7 +836,7 @@ TbcField generate_two_body_current_field(const HfbSolution& s, const FamBasis& b
         if (sa_.z < za0 || sa_.z >= za1) continue;
         for (int c : group.at(kC)) {
           const Dst& sc_ = dst[c];
-          if (f.mat.ir2c[sa_.blk] - 1 != sc_.blk) continue;
+          if (s.ir2c[sa_.blk] - 1 != sc_.blk) continue;
           const double* w = W.data() + ((size_t)(sa_.z - za0) * nz1 + sc_.z) * wsz;
           double gam[6] = {0, 0, 0, 0, 0, 0};
           for (int p = 0; p < npairs; p++) {
@@ -875,8 +858,8 @@ TbcField generate_two_body_current_field(const HfbSolution& s, const FamBasis& b
               }
             }
           }
-          const int da = b.db[sa_.blk];
-          const size_t at = (size_t)f.mat.ir2m[sa_.blk] - 1 + sa_.pos + (size_t)sc_.pos * da;
+          const int da = s.id[sa_.blk % nbx];
+          const size_t at = (size_t)s.ir2m[sa_.blk] - 1 + sa_.pos + (size_t)sc_.pos * da;
           const double sg = (double)(sa_.sign * sc_.sign);
           for (int o = 0; o < 6; o++) raw[o][at] = gam[o] * sg;
         }
@@ -890,30 +873,71 @@ TbcField generate_two_body_current_field(const HfbSolution& s, const FamBasis& b
 
   // spin sort of rows and columns (reorder_blockmatrix_basis 'a' with new_order, pnfam_extfield_2bc.f90:903-913)
   TbcField out;
-  std::vector<std::vector<int>> order(b.nb);
-  for (int ib = 0; ib < b.nb; ib++) {
+  std::vector<std::vector<int>> order(2 * nbx);
+  for (int ib = 0; ib < 2 * nbx; ib++) {
     const int h0 = ib < nbx ? ib : ib - nbx;
     const int flip = ib < nbx ? 1 : -1;
-    for (int i = 0; i < s.id[h0]; i++) if (flip * s.ns[s.ia[h0] + i] > 0) order[ib].push_back(i);
-    for (int i = 0; i < s.id[h0]; i++) if (flip * s.ns[s.ia[h0] + i] < 0) order[ib].push_back(i);
+    for (int i = 0; i < s.id[h0]; i++) if (flip * s.ns[ia[h0] + i] > 0) order[ib].push_back(i);
+    for (int i = 0; i < s.id[h0]; i++) if (flip * s.ns[ia[h0] + i] < 0) order[ib].push_back(i);
   }
   for (int o = 0; o < 6; o++) {
     out.c[o].assign(nxy, 0.0);
-    for (int ibr = 0; ibr < b.nb; ibr++) {
-      const int ibc = f.mat.ir2c[ibr] - 1;
+    for (int ibr = 0; ibr < 2 * nbx; ibr++) {
+      const int ibc = s.ir2c[ibr] - 1;
       if (ibc < 0) continue;
-      const int dr = b.db[ibr], dc = b.db[ibc];
-      const size_t im = (size_t)f.mat.ir2m[ibr] - 1;
+      const int dr = s.id[ibr % nbx], dc = s.id[ibc % nbx];
+      const size_t im = (size_t)s.ir2m[ibr] - 1;
       for (int c = 0; c < dc; c++)
-        for (int r = 0; r < dr; r++) out.c[o][im + r + (size_t)c * dr] = raw[o][im + order[ibr][r] + (size_t)order[ibc][c] * dr];
+        for (int r = 0; r < dr; r++) out.c[o][im + r + (size_t)c * dr] = s.spin_sorted ? raw[o][im + order[ibr][r] + (size_t)order[ibc][c] * dr] : raw[o][im + r + (size_t)c * dr];
     }
   }
   return out;
 }
 
+// Front door of the set-up: density matrices rho_db = rk / 2 (hfbtho_solver.f90:1822-1856) from the HFB solution:
+// sum_k V_dk V_bk over the pairing window; finite temperature: V (1 - f_k) V + U f_k U with the Fermi-Dirac factor of the
+// quasiparticle energy (:1749-1761); blocked level (equal filling): - (V V - U U) / 2 of the blocked quasiparticle.
+TbcProblem tbc_problem_from(const HfbSolution& s, const ExtField& f, bool use_p) {
+  TbcProblem pr;
+  pr.nt = s.nt; pr.nb = s.nb; pr.id = s.id; pr.nz = s.nz; pr.nr = s.nr; pr.nl = s.nl; pr.ns = s.ns; pr.bz = s.bz; pr.bp = s.bp;
+  pr.ir2c = f.mat.ir2c; pr.ir2m = f.mat.ir2m; pr.nxy = f.mat.elem.size(); pr.K = f.k; pr.beta_minus = f.beta_minus; pr.use_p = use_p;
+  const int nbx = s.nb;
+  std::vector<size_t> boff(nbx + 1, 0);
+  for (int ib = 0; ib < nbx; ib++) boff[ib + 1] = boff[ib] + (size_t)s.id[ib] * s.id[ib];
+  const bool hot = s.ft_active && s.temper > 1e-12;
+  for (int it = 0; it < 2; it++) {
+    pr.rho[it].assign(boff[nbx], 0.0);
+    for (int ib = 0; ib < nbx; ib++) {
+      const int nd = s.id[ib];
+      double* R = pr.rho[it].data() + boff[ib];
+      for (int kk = s.ka[it][ib]; kk < s.ka[it][ib] + s.kd[it][ib]; kk++) {
+        const double* V = s.V[it].data() + s.Kpwi[it][kk];
+        const double* U = s.U[it].data() + s.Kpwi[it][kk];
+        const double fT = hot ? 0.5 * (1.0 - std::tanh(0.5 * s.E[it][s.Kqp[it][kk] - 1] / s.temper)) : 0.0;
+        for (int n2 = 0; n2 < nd; n2++)
+          for (int n1 = 0; n1 < nd; n1++) R[n1 + (size_t)n2 * nd] += V[n1] * (1.0 - fT) * V[n2] + U[n1] * fT * U[n2];
+      }
+      if (s.keyblo[it] && s.blo_block[it] == ib + 1 && s.kd[it][ib] > 0) {
+        if (s.blok1k2d[it] <= 0) throw std::runtime_error("two-body-current field generator: no blocking candidate found");
+        const double* V = s.V[it].data() + s.Kpwi[it][s.blok1k2d[it] - 1];
+        const double* U = s.U[it].data() + s.Kpwi[it][s.blok1k2d[it] - 1];
+        for (int n2 = 0; n2 < nd; n2++)
+          for (int n1 = 0; n1 < nd; n1++) R[n1 + (size_t)n2 * nd] += 0.5 * (-V[n1] * V[n2] + U[n1] * U[n2]);
+      }
+    }
+  }
+  return pr;
+}
+
+TbcField generate_two_body_current_field(const HfbSolution& s, const FamBasis& b, const ExtField& f, bool use_p) {
+  if (b.nb != 2 * s.nb) throw std::runtime_error("two-body-current field generator: basis and HFB solution do not match");
+  return generate_two_body_current_field(tbc_problem_from(s, f, use_p));
+}
+
 // write_tbc (pnfam_storage.f90:488-559): same records, so that the reference and this library read each other's files
 void write_tbc(const std::string& path, const FamBasis& b, const FamInput& in, const ExtField& f, const TwoBody& tb, const TbcField& fld) {
-  const std::string tmp = path + ".tmp";
+  // unique temporary name: the ranks of a sharded run that own points of the same operator may generate the same file
+  const std::string tmp = path + ".tmp." + std::to_string((long)getpid()) + "." + std::to_string((unsigned long)omp_get_thread_num());
   {
     std::ofstream os(tmp, std::ios::binary | std::ios::trunc);
     if (!os) throw std::runtime_error("cannot write " + tmp);

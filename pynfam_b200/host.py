@@ -29,6 +29,10 @@ def lib():
                                               ctypes.POINTER(ctypes.c_int64)]
         L.pnfam_problem_label.argtypes = [vp, ci, cp, ci]
         L.pnfam_host_set_threads.argtypes = [ci]
+        i32, i64, dbl = ctypes.c_int32, ctypes.c_int64, ctypes.c_double
+        pi32, pdbl = ctypes.POINTER(i32), ctypes.POINTER(dbl)
+        L.pnfam_host_effective_2bc_extfield.argtypes = [i32, i32, pi32, pi32, pi32, pi32, pi32, dbl, dbl, pdbl, i64, pi32, pi32, i64,
+                                                        i32, i32, i32, i32, pdbl, pdbl, pdbl, pdbl, pdbl, pdbl, cp, ci]
         _LIB = L
     return _LIB
 
@@ -40,6 +44,26 @@ class PnfamError(RuntimeError):
 def set_threads(n):
     """OpenMP threads of the host set-up (n <= 0: unchanged); returns the previous setting."""
     return int(lib().pnfam_host_set_threads(int(n)))
+
+
+def effective_2bc_extfield(id_, nz, nr, nl, ns, bz, bp, rmat, ir2c, ir2m, nxy, k, beta_minus=True, use_p=False, spin_sorted=True):
+    """The reference's effective_2bc_extfield (pnfam_extfield_2bc.f90:26-465) on plain arrays, through the C ABI
+    (include/pnfam_b200.h: pnfam_host_effective_2bc_extfield).  rmat: HFBTHO's rk as a Fortran-ordered (nqx, 2 nbx) array.
+    Returns the six LEC-stripped parts (c3d, c3e, c4d, c4e, cpd, cpe) as an array of shape (6, nxy)."""
+    i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+    id_, nz, nr, nl, ns, ir2c, ir2m = map(i32, (id_, nz, nr, nl, ns, ir2c, ir2m))
+    rmat = np.asfortranarray(rmat, dtype=np.float64)
+    out = np.zeros((6, int(nxy)))
+    err = ctypes.create_string_buffer(1024)
+    pi = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
+    pd = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+    rc = lib().pnfam_host_effective_2bc_extfield(len(nz), len(id_), pi(id_), pi(nz), pi(nr), pi(nl), pi(ns), float(bz), float(bp),
+                                                 pd(rmat), rmat.shape[0], pi(ir2c), pi(ir2m), int(nxy), int(k), int(bool(beta_minus)),
+                                                 int(bool(use_p)), int(bool(spin_sorted)), pd(out[0]), pd(out[1]), pd(out[2]),
+                                                 pd(out[3]), pd(out[4]), pd(out[5]), err, 1024)
+    if rc != 0:
+        raise PnfamError(err.value.decode(errors="replace"))
+    return out
 
 
 class Problem:

@@ -26,6 +26,8 @@ CASES = [  # (case, source tree, operator K, beta, usep, omega)
     ("Gd163_blocked_K0", "Gd163_blocked_6sh", 0, "-", False, 1.5 + 0.75j),      # odd-A, equal-filling blocking
     ("Gd163_blocked_usep_K0", "Gd163_blocked_6sh", 0, "-", True, 1.5 + 0.75j),
     ("Gd162_finiteT_K1", "Gd162_finiteT_6sh", 1, "-", False, 1.5 + 0.75j),      # T = 0.8 MeV
+    ("S40_Kminus1", "S40_All_GT2bc", -1, "-", False, 2.0 + 1.0j),                # K = -1 branch of the spatial components
+    ("Gd162_6sh_usep_Kminus1", "Gd162_GT_open_6sh", -1, "+", True, 1.5 + 0.75j),
     # a basis size of BASELINE.json configs[4]: about an hour of the reference on 6 threads (the .tbc is 0.9 MB)
     ("Gd162_12sh_K0", "Gd162_SKOP_12sh", 0, "-", False, 2.0 + 1.0j),
 ]
@@ -47,7 +49,7 @@ def main():
             shutil.copy(os.path.join(HERE, tree, f), dst)
         wd = tempfile.mkdtemp()
         refrun.stage(wd, tmp)
-        name = "GT-K%d" % k
+        name = "GT-K%d" % k if k >= 0 else "GT-Km%d" % -k
         nml = FAM.format(name=name, re=repr(w.real), im=repr(w.imag), op="GT", k=k, max_iter=300)
         nml = nml.replace("two_body_current_mode = 0", "two_body_current_mode = 111100")
         nml = nml.replace("beta_type = '-'", "beta_type = '%s'" % beta)
@@ -63,9 +65,11 @@ def main():
         strengths[case] = {"name": name, "rows": {kk: [repr(v.real), repr(v.imag)] for kk, v in dat["rows"].items()},
                            "iters": dat["iters"], "conv": dat["conv"], "wall_s": wall}
         print(case, dat["rows"]["Strength"], dat["iters"], "%.1f s" % wall, flush=True)
-    json.dump({"source": "reference's prebuilt pnfam_main.x (oracle/_ref), started without a .tbc file, by "
-                         "tests/golden/make_tbc_generator.py", "cases": strengths},
-              open(os.path.join(out, "strengths.json"), "w"), indent=0)
+        # merge into the file as it is NOW (several of these scripts may run side by side)
+        merged = json.load(open(spath))["cases"] if os.path.isfile(spath) else {}
+        merged[case] = strengths[case]
+        json.dump({"source": "reference's prebuilt pnfam_main.x (oracle/_ref), started without a .tbc file, by "
+                             "tests/golden/make_tbc_generator.py", "cases": merged}, open(spath, "w"), indent=0)
 
 
 if __name__ == "__main__":

@@ -5,12 +5,13 @@ Known answers: the <OP>.tbc files the reference itself wrote,
   * tests/golden/S40_All_GT2bc/GT-K{0,1}.tbc: from the reference's own golden tree tests/S40_All_GT2bc/hfb_soln,
   * tests/golden/tbc_generator/*: the reference's prebuilt pnfam_main.x started here without a .tbc file
     (tests/golden/make_tbc_generator.py): momentum-dependent terms, beta+, a deformed nucleus, a blocked odd-A nucleus,
-    finite temperature.
+    finite temperature, K = -1, and 162Gd at 12 shells.
 A run directory WITHOUT the .tbc file makes the library compute the field and cache it in the reference's record layout;
 the file is compared record by record, the field element by element, and the strengths of the complete FAM solve
 (CPU oracle) with the reference's.  Bound: 1e-12 of the largest element of a component (measured: 7e-15)."""
 import json
 import os
+import re
 import shutil
 import struct
 
@@ -23,7 +24,8 @@ from pynfam_b200 import host
 
 GEN = os.path.join(GOLDEN, "tbc_generator")
 GEN_CASES = ["S40_usep_K0", "S40_usep_K1", "S40_betaplus_K1", "S40_betaplus_usep_K0", "Gd162_6sh_usep_K1", "Gd162_6sh_K0",
-             "Gd163_blocked_K0", "Gd163_blocked_usep_K0", "Gd162_finiteT_K1"]
+             "Gd163_blocked_K0", "Gd163_blocked_usep_K0", "Gd162_finiteT_K1", "S40_Kminus1", "Gd162_6sh_usep_Kminus1",
+             "Gd162_12sh_K0"]    # 12 shells: a basis size of BASELINE.json configs[4]; 13 minutes of the reference on 5 threads
 
 
 def records(path):
@@ -94,6 +96,44 @@ def test_generated_file_equals_the_reference_binary_file(case, tmp_path):
     assert worst < 1e-12
 
 
+@pytest.mark.parametrize("case", ["S40_usep_K1", "Gd162_6sh_K0", "Gd163_blocked_K0"])
+def test_plain_array_entry_point_equals_the_reference_file(case, tmp_path):
+    """pnfam_host_effective_2bc_extfield (include/pnfam_b200.h): the entry a Fortran maintainer calls in place of
+    effective_2bc_extfield, fed with the arrays that routine takes from its modules (HFBTHO quantum numbers, oscillator
+    lengths, rk, the block structure of the operator) -- against the .tbc the reference binary wrote."""
+    wd = str(tmp_path)
+    src = os.path.join(GEN, case)
+    info = json.load(open(os.path.join(GEN, "strengths.json")))["cases"][case]
+    name = info["name"]
+    nml = open(os.path.join(src, name + ".in")).read()
+    stage(src, wd, nml, name)
+    shutil.copy(os.path.join(src, name + ".tbc"), wd)          # the set-up itself reads the reference's file: no generation
+    os.environ["PNFAM_B200_NO_TBC_GENERATOR"] = "1"
+    try:
+        p = host.Problem(wd, name + ".in")
+    finally:
+        del os.environ["PNFAM_B200_NO_TBC_GENERATOR"]
+    nb = p.iscalar("hfb_nb")
+    rk = p.f64("hfb_rk").reshape(2 * nb, -1).T                  # Fortran (nqx, 2 nbx)
+    out = host.effective_2bc_extfield(p.i32("hfb_id"), p.i32("hfb_nz"), p.i32("hfb_nr"), p.i32("hfb_nl"), p.i32("hfb_ns"),
+                                      p.scalar("hfb_bz"), p.scalar("hfb_bp"), rk, p.i32("f_ir2c"), p.i32("f_ir2m"), p.iscalar("nxy"),
+                                      k=int(re.search(r"operator_k\s*=\s*(-?\d+)", nml).group(1)), beta_minus=bool(p.iscalar("beta_minus")),
+                                      use_p=".true." in nml.split("two_body_current_usep")[1].split("\n")[0])
+    ref = [np.frombuffer(r, "<f8") for r in records(os.path.join(src, name + ".tbc")) if len(r) > 1000]
+    for a, b in zip(out, ref):
+        scale = np.abs(b).max()
+        assert np.abs(a - b).max() <= 1e-12 * max(scale, 1e-2)
+    # unsorted variant: the same numbers in the original in-block order (a permutation of every block)
+    raw = host.effective_2bc_extfield(p.i32("hfb_id"), p.i32("hfb_nz"), p.i32("hfb_nr"), p.i32("hfb_nl"), p.i32("hfb_ns"),
+                                      p.scalar("hfb_bz"), p.scalar("hfb_bp"), rk, p.i32("f_ir2c"), p.i32("f_ir2m"), p.iscalar("nxy"),
+                                      k=int(re.search(r"operator_k\s*=\s*(-?\d+)", nml).group(1)), beta_minus=bool(p.iscalar("beta_minus")),
+                                      use_p=False, spin_sorted=False)
+    assert abs(np.sort(np.abs(raw[0])) - np.sort(np.abs(out[0]))).max() < 1e-14
+    with pytest.raises(host.PnfamError, match="invalid K"):
+        host.effective_2bc_extfield(p.i32("hfb_id"), p.i32("hfb_nz"), p.i32("hfb_nr"), p.i32("hfb_nl"), p.i32("hfb_ns"),
+                                    p.scalar("hfb_bz"), p.scalar("hfb_bp"), rk, p.i32("f_ir2c"), p.i32("f_ir2m"), p.iscalar("nxy"), k=2)
+
+
 def test_second_set_up_reads_the_cached_file(tmp_path):
     """The generated file is what the next process reads (as the reference does): same field, no recomputation."""
     wd = str(tmp_path)
@@ -159,7 +199,7 @@ def test_generator_can_be_switched_off(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("case", ["golden:GT-K1", "S40_usep_K1", "Gd162_6sh_usep_K1", "Gd163_blocked_usep_K0", "Gd162_finiteT_K1"])
+@pytest.mark.parametrize("case", ["golden:GT-K1", "S40_usep_K1", "Gd162_6sh_usep_K1", "Gd163_blocked_usep_K0", "Gd162_finiteT_K1", "Gd162_12sh_K0"])
 def test_gpu_solve_with_generated_field(case, tmp_path):
     """The product path end to end: no .tbc in the run directory -> host generator -> batched GPU solve -> the reference's
     strengths (golden tree: all 30 computed points of GT-K1; reference binary: momentum terms, deformed nucleus), 1e-9."""
