@@ -772,12 +772,12 @@ static void densit_rho(HfbSolution& s) {
   }
 }
 
-// DENSIT restricted to tau(r) and Delta rho(r): TEMP4 / TEMP5 of the zero-temperature branch (hfbtho_solver.f90:4559-4566)
-// with the weights and the particle-number rescaling of the end of the routine (:4697-4716).
+// DENSIT restricted to tau(r) and Delta rho(r): TEMP4 / TEMP5 (hfbtho_solver.f90:4535-4566) -- zero temperature, the
+// finite-temperature branch (V part weighted with 1 - f_k, U part with f_k) and the equal-filling correction of the
+// blocked quasiparticle (:4586-4596) -- with the weights and the particle-number rescaling of the end of the routine
+// (:4697-4716).
 void HfbSolution::kinetic_and_laplacian(std::vector<double> tau[2], std::vector<double> dro[2]) const {
   const HfbSolution& s = *this;
-  if (s.ft_active) throw std::runtime_error("tau and Delta rho at finite temperature are not computed");
-  if (s.keyblo[0] || s.keyblo[1]) throw std::runtime_error("tau and Delta rho of blocked (odd) nuclei are not computed");
   const int nghl = s.nghl;
   for (int it = 0; it < 2; it++) {
     std::vector<double> ro(nghl, 0.0), ta(nghl, 0.0), dr(nghl, 0.0);
@@ -785,36 +785,65 @@ void HfbSolution::kinetic_and_laplacian(std::vector<double> tau[2], std::vector<
       const int nd = s.id[ib], im = s.ia[ib];
       const int k1 = s.ka[it][ib], imen = s.kd[it][ib];
       if (imen <= 0) continue;
+      const int k0 = (s.keyblo[it] && s.blo_block[it] == ib + 1) ? s.blo_state[it] : 0;
+      const int k0_active = (k0 >= 1 && k0 <= imen) ? k0 : 0;      // as in densit_rho above
       // LAPLUS = Omega + 1/2 of the block; Lambda of the spin-down (xlap) and spin-up (xlam) components
       const double xlap = (double)(s.nl[im] + (s.ns[im] + 1) / 2), xlam = xlap - 1.0;
       const double xlap2 = xlap * xlap, xlam2 = xlam * xlam;
+      const bool hot = s.ft_active;
 #pragma omp parallel
       {
-        std::vector<double> fu(imen), fd(imen), fur(imen), fdr(imen), fuz(imen), fdz(imen), fu2(imen), fd2(imen);
+        // V part: [0] phi, [1] d/dr, [2] d/dz, [3] second derivatives; u = spin up, d = spin down; p*: the U part (T > 0)
+        std::vector<double> fu[4], fd[4], pu[4], pd[4];
+        for (int c = 0; c < 4; c++) { fu[c].resize(imen); fd[c].resize(imen); if (hot) { pu[c].resize(imen); pd[c].resize(imen); } }
 #pragma omp for schedule(static)
         for (int ihil = 0; ihil < nghl; ihil++) {
-          for (auto* v : {&fu, &fd, &fur, &fdr, &fuz, &fdz, &fu2, &fd2}) std::fill(v->begin(), v->end(), 0.0);
+          for (int c = 0; c < 4; c++) {
+            std::fill(fu[c].begin(), fu[c].end(), 0.0); std::fill(fd[c].begin(), fd[c].end(), 0.0);
+            if (hot) { std::fill(pu[c].begin(), pu[c].end(), 0.0); std::fill(pd[c].begin(), pd[c].end(), 0.0); }
+          }
+          double bu[4] = {0, 0, 0, 0}, bd[4] = {0, 0, 0, 0};        // blocked level: PIU, PIUR, PIUZ, PIUD2 / PID...
           for (int i = 0; i < nd; i++) {
             const int ja = im + i;
-            const double q = s.qhla[(size_t)ja * nghl + ihil], r1 = s.fi1r[(size_t)ja * nghl + ihil];
-            const double z1 = s.fi1z[(size_t)ja * nghl + ihil], d2 = s.fi2d[(size_t)ja * nghl + ihil];
+            const double w[4] = {s.qhla[(size_t)ja * nghl + ihil], s.fi1r[(size_t)ja * nghl + ihil],
+                                 s.fi1z[(size_t)ja * nghl + ihil], s.fi2d[(size_t)ja * nghl + ihil]};
             const bool up = s.ns[ja] > 0;
-            double* a0 = up ? fu.data() : fd.data();
-            double* a1 = up ? fur.data() : fdr.data();
-            double* a2 = up ? fuz.data() : fdz.data();
-            double* a3 = up ? fu2.data() : fd2.data();
             for (int k = 0; k < imen; k++) {
               const double v = s.V[it][(size_t)s.Kpwi[it][k1 + k] + i];
-              a0[k] += q * v; a1[k] += r1 * v; a2[k] += z1 * v; a3[k] += d2 * v;
+              for (int c = 0; c < 4; c++) (up ? fu : fd)[c][k] += w[c] * v;
+              if (hot) {
+                const double u = s.U[it][(size_t)s.Kpwi[it][k1 + k] + i];
+                for (int c = 0; c < 4; c++) (up ? pu : pd)[c][k] -= w[c] * u;
+              }
+            }
+            if (k0_active) {
+              const double pnik = s.U[it][(size_t)s.Kpwi[it][k1 + k0_active - 1] + i];
+              for (int c = 0; c < 4; c++) (up ? bu : bd)[c] += pnik * w[c];
             }
           }
           const double y = s.y[ihil], y2 = y * y;
           double t2 = 0, t4 = 0, t5 = 0;
           for (int k = 0; k < imen; k++) {
-            const double tw = fur[k] * fur[k] + fdr[k] * fdr[k] + fuz[k] * fuz[k] + fdz[k] * fdz[k];
-            t2 += fu[k] * fu[k] + fd[k] * fd[k];
-            t4 += xlam2 * y2 * fu[k] * fu[k] + xlap2 * y2 * fd[k] * fd[k] + tw;
-            t5 += fu[k] * fu2[k] + fd[k] * fd2[k] + tw;
+            const double tw = fu[1][k] * fu[1][k] + fd[1][k] * fd[1][k] + fu[2][k] * fu[2][k] + fd[2][k] * fd[2][k];
+            double e2 = fu[0][k] * fu[0][k] + fd[0][k] * fd[0][k];
+            double e4 = xlam2 * y2 * fu[0][k] * fu[0][k] + xlap2 * y2 * fd[0][k] * fd[0][k] + tw;
+            double e5 = fu[0][k] * fu[3][k] + fd[0][k] * fd[3][k] + tw;
+            if (hot) {
+              const double f1k = s.fT_pwi[it][k1 + k], fk = 1.0 - f1k;
+              const double twp = pu[1][k] * pu[1][k] + pd[1][k] * pd[1][k] + pu[2][k] * pu[2][k] + pd[2][k] * pd[2][k];
+              const double tw_t = tw * fk + twp * f1k;
+              e2 = e2 * fk + (pu[0][k] * pu[0][k] + pd[0][k] * pd[0][k]) * f1k;
+              e4 = (xlam2 * y2 * fu[0][k] * fu[0][k] + xlap2 * y2 * fd[0][k] * fd[0][k]) * fk +
+                   (xlam2 * y2 * pu[0][k] * pu[0][k] + xlap2 * y2 * pd[0][k] * pd[0][k]) * f1k + tw_t;
+              e5 = (fu[0][k] * fu[3][k] + fd[0][k] * fd[3][k]) * fk + (pu[0][k] * pu[3][k] + pd[0][k] * pd[3][k]) * f1k + tw_t;
+            }
+            t2 += e2; t4 += e4; t5 += e5;
+            if (k + 1 == k0_active) {
+              const double pw = bu[1] * bu[1] + bd[1] * bd[1] + bu[2] * bu[2] + bd[2] * bd[2];
+              t2 -= 0.5 * (e2 - (bu[0] * bu[0] + bd[0] * bd[0]));
+              t4 -= 0.5 * (e4 - (pw + xlam2 * y2 * bu[0] * bu[0] + xlap2 * y2 * bd[0] * bd[0]));
+              t5 -= 0.5 * (e5 - (pw + bu[0] * bu[3] + bd[0] * bd[3]));
+            }
           }
           ro[ihil] += t2; ta[ihil] += t4; dr[ihil] += t5;
         }

@@ -94,7 +94,7 @@ struct HfbSolution {
   // densities
   std::vector<double> ro[2];                        // (nghl) normalised rho_n, rho_p
   // kinetic density tau and Laplacian of rho, same normalisation as DENSIT leaves them (hfbtho_solver.f90:4545-4549,
-  // 4697-4716); only the density-matrix-expansion two-body currents need them: computed on demand, T = 0, no blocking
+  // 4697-4716); only the density-matrix-expansion two-body currents need them: computed on demand
   void kinetic_and_laplacian(std::vector<double> tau[2], std::vector<double> dro[2]) const;
   // functional info carried for the FAM interaction set-up
   double CpV0[2], CpV1[2], rho_nm = 0.16, hbzero = 0;

@@ -11,14 +11,19 @@
 //            classes with their n_z lists).
 //
 // Same sums, different organisation.  The reference loops (n_z^a, n_z^c) outermost and re-evaluates the radial
-// two-body elements for every one of the (N_z+1)^2 combinations; here
+// two-body elements -- each a four-fold sum over Cartesian quanta -- for every one of the (N_z+1)^2 combinations; here
 //   1. all 1D tables (seven derivative kinds x six Gaussians) are built once,
-//   2. the z contraction  W[q][dir|exc][(D,B)][g][comp](z_a, z_c) = sum_{z_b z_d} J^z_comp(g; z_a z_b z_c z_d) rho^q_db
-//      is made once per (z_a, z_c) for every pair of radial classes D, B,
+//   2. the z contraction  W[q][dir|exc][(D,B)][comp][g](z_a, z_c) = sum_{z_b z_d} J^z_comp(g; z_a z_b z_c z_d) rho^q_db
+//      is made once per (z_a, z_c) for every pair of radial classes D, B (chunked over z_a under a memory bound),
 //   3. the radial elements J^r(g; A B C D) are made once per pair of radial classes (A, C) = (n_r, Lambda) of the bra and
-//      the ket and serve every (z_a, z_c, s_a, s_c) of that pair; the spin-isospin contraction is a table of linear
-//      coefficients probed from the literal spin functions.
-// Work per nucleus drops by about (N_z+1)^2; OpenMP over the (A, C) pairs.
+//      the ket and serve every (z_a, z_c, s_a, s_c) of that pair,
+//   4. each radial element is an O(N^2) sum over an intermediate built once per (A, C, derivative kind, Gaussian)
+//      (build_q below) instead of the O(N^4) Cartesian sum; exchange elements use tables with the last two indices
+//      exchanged; the complex element of the momentum terms splits the same way,
+//   5. the spin-isospin contraction is a sparse list of linear coefficients probed from the literal spin functions.
+// OpenMP over the (A, C) pairs.  PNFAM_B200_TBC_LITERAL_RADIAL=1 evaluates step 4 with the reference's literal sums
+// (self-check).  Entry points: generate_two_body_current_field(TbcProblem) on plain arrays (C ABI:
+// pnfam_host_effective_2bc_extfield) and the set-up's front door that takes the density matrices from the HFB solution.
 //
 // Scope: gamma (particle-hole) part -- the pairing part (3rd digit of the mode 2, 3) is refused upstream exactly where the
 // reference says "not yet operational"; even and blocked (odd, equal filling) nuclei, zero and finite temperature.

@@ -3,7 +3,8 @@
 1195-1330, 1380-1662; tau and Delta rho from HFBTHO's DENSIT), produced with the reference's own prebuilt pnfam_main.x
 (oracle/_ref): GT with the DME exchange term alone (2nd digit 4) and with the direct part of the full-FAM field on top
 (2nd digit 5: the reference computes its .tbc from scratch), P with the DME vector current (5th digit 2), PS0 with the DME
-axial charge (6th digit 2); 1BC+2BC and 2BC only, cross-terms on; spherical 40S and deformed 162Gd at 6 shells.
+axial charge (6th digit 2); 1BC+2BC and 2BC only, cross-terms on; spherical 40S and deformed 162Gd at 6 shells,
+blocked 163Gd and 162Gd at T = 0.8 MeV.
 -> tests/golden/S40_2bc_dme/points.json, tests/golden/Gd162_2bc_dme/points.json
 """
 import json
@@ -25,11 +26,16 @@ CASES = {
         ("PS0", 0, 121102, 4.0 - 2.0j), ("PS0", 0, 221102, 4.0 - 2.0j), ("RS0", 0, 141222, 4.0 + 2.0j)]),
     "Gd162_2bc_dme": ("Gd162_GT_open_6sh", [
         ("GT", 1, 141100, 1.5 + 0.75j), ("GT", 0, 151100, 1.5 + 0.75j), ("P", 1, 121120, 5.0 + 1.0j), ("PS0", 0, 121102, 4.0 + 1.0j)]),
+    # tau and Delta rho with the equal-filling term of the blocked level / the thermal occupations
+    "Gd163_2bc_dme": ("Gd163_blocked_6sh", [("GT", 0, 141100, 1.5 + 0.75j), ("GT", 1, 151100, 1.5 + 0.75j), ("PS0", 0, 121102, 4.0 + 1.0j)]),
+    "Gd162T_2bc_dme": ("Gd162_finiteT_6sh", [("GT", 1, 141100, 1.5 + 0.75j), ("P", 0, 121120, 5.0 + 1.0j)]),
 }
 
 
 def main():
     for out, (tree, cases) in CASES.items():
+        if len(sys.argv) > 1 and out not in sys.argv[1:]:      # usage: make_2bc_dme.py [group ...]
+            continue
         dst = os.path.join(HERE, out)
         os.makedirs(dst, exist_ok=True)
         for f in ("hfbtho_NAMELIST.dat", "hfbtho_output.hel"):

@@ -227,7 +227,7 @@ def test_closed_form_two_body_current_modes(gpu, tmp_path):
     assert n == 11
 
 
-@pytest.mark.parametrize("case,npts", [("S40_2bc_dme", 11), ("Gd162_2bc_dme", 4)])
+@pytest.mark.parametrize("case,npts", [("S40_2bc_dme", 11), ("Gd162_2bc_dme", 4), ("Gd163_2bc_dme", 3), ("Gd162T_2bc_dme", 2)])
 def test_density_matrix_expansion_two_body_current_modes(gpu, case, npts, tmp_path):
     """The remaining values of two_body_current_mode: DME exchange term of the GT current alone and with the direct part
     of the full-FAM field (computed by the host generator: no .tbc is staged), DME vector current of P, DME axial charge of

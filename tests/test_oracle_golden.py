@@ -93,7 +93,9 @@ def test_closed_form_two_body_current_fields(key, tmp_path):
 
 DME_KEYS = [("S40_2bc_dme", k) for k in ("GT-K0-141100", "GT-K1-141100", "GT-K0-241100", "GT-K0-151100", "GT-K1-151100", "P-K0-121120",
                                         "P-K1-121120", "P-K0-221120", "PS0-K0-121102", "PS0-K0-221102", "RS0-K0-141222")] + \
-           [("Gd162_2bc_dme", k) for k in ("GT-K1-141100", "GT-K0-151100", "P-K1-121120", "PS0-K0-121102")]
+           [("Gd162_2bc_dme", k) for k in ("GT-K1-141100", "GT-K0-151100", "P-K1-121120", "PS0-K0-121102")] + \
+           [("Gd163_2bc_dme", k) for k in ("GT-K0-141100", "GT-K1-151100", "PS0-K0-121102")] + \
+           [("Gd162T_2bc_dme", k) for k in ("GT-K1-141100", "P-K0-121120")]   # blocked 163Gd; 162Gd at T = 0.8 MeV
 
 
 @pytest.mark.parametrize("case,key", DME_KEYS)
