@@ -94,13 +94,20 @@ Namelist Namelist::parse_file(const std::string& path) {
       group.clear();
       continue;
     }
-    if (!t.empty() && t.back() == '/' && t.find('\'') == std::string::npos) {
-      end_group = true;
-      t = trim(t.substr(0, t.size() - 1));
+    if (!t.empty() && t.back() == '/') {      // a terminating slash outside quotes
+      char q = 0;
+      for (size_t i = 0; i + 1 < t.size(); i++) {
+        if (q) { if (t[i] == q) q = 0; }
+        else if (t[i] == '\'' || t[i] == '"') q = t[i];
+      }
+      if (!q) {
+        end_group = true;
+        t = trim(t.substr(0, t.size() - 1));
+      }
     }
-    // possibly several "key = value" on one line is rare in these files; handle one per line,
-    // plus continuation lines (no '=') that extend the previous key's list.
-    size_t eq = std::string::npos;
+    // Several "key = value" assignments may share a line (the namelists shipped with HFBTHO and the reference's own
+    // test inputs do); lines without '=' continue the value list of the previous key.
+    std::vector<size_t> eqs;                 // positions of '=' outside quotes
     {
       char q = 0;
       for (size_t i = 0; i < t.size(); i++) {
@@ -110,24 +117,51 @@ Namelist Namelist::parse_file(const std::string& path) {
         } else if (c == '\'' || c == '"') {
           q = c;
         } else if (c == '=') {
-          eq = i;
-          break;
+          eqs.push_back(i);
         }
       }
     }
-    if (eq == std::string::npos) {
+    if (eqs.empty()) {
       if (!lastkey.empty()) {
         auto more = split_values(t);
         auto& dst = nl.groups[group][lastkey];
         dst.insert(dst.end(), more.begin(), more.end());
       }
     } else {
-      std::string key = lower(trim(t.substr(0, eq)));
-      // drop array-section syntax like key(1:3)
-      size_t par = key.find('(');
-      if (par != std::string::npos) key = trim(key.substr(0, par));
-      nl.groups[group][key] = split_values(t.substr(eq + 1));
-      lastkey = key;
+      // start of the name in front of every '=': skip blanks, an optional (section), then the identifier
+      std::vector<size_t> starts;
+      for (size_t eq : eqs) {
+        size_t i = eq;
+        while (i > 0 && std::isspace((unsigned char)t[i - 1])) i--;
+        if (i > 0 && t[i - 1] == ')') {
+          while (i > 0 && t[i - 1] != '(') i--;
+          if (i > 0) i--;
+          while (i > 0 && std::isspace((unsigned char)t[i - 1])) i--;
+        }
+        while (i > 0 && (std::isalnum((unsigned char)t[i - 1]) || t[i - 1] == '_' || t[i - 1] == '%')) i--;
+        starts.push_back(i);
+      }
+      // text in front of the first name continues the previous key
+      if (starts[0] > 0 && !lastkey.empty()) {
+        std::string head = trim(t.substr(0, starts[0]));
+        if (!head.empty() && head != ",") {
+          auto more = split_values(head);
+          auto& dst = nl.groups[group][lastkey];
+          dst.insert(dst.end(), more.begin(), more.end());
+        }
+      }
+      for (size_t k = 0; k < eqs.size(); k++) {
+        std::string key = lower(trim(t.substr(starts[k], eqs[k] - starts[k])));
+        // drop array-section syntax like key(1:3)
+        size_t par = key.find('(');
+        if (par != std::string::npos) key = trim(key.substr(0, par));
+        const size_t vend = k + 1 < eqs.size() ? starts[k + 1] : t.size();
+        std::string val = trim(t.substr(eqs[k] + 1, vend - eqs[k] - 1));
+        // the comma that separates this assignment from the next one is not a (null) value
+        if (k + 1 < eqs.size() && !val.empty() && val.back() == ',') val = trim(val.substr(0, val.size() - 1));
+        nl.groups[group][key] = split_values(val);
+        lastkey = key;
+      }
     }
     if (end_group) group.clear();
   }

@@ -6,7 +6,7 @@ import re
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, ROOT, stage_point
+from conftest import GOLDEN, ROOT, load_points, stage_point
 from oracle import refrun
 from pynfam_b200 import host
 
@@ -43,6 +43,51 @@ def test_namelist_roundtrip(tmp_path):
     assert back["general"]["fam_output_filename"] == "GT-K0"
     assert back["general"]["imag_eqrpa"] == -2.25
     assert back["interaction"]["vpair_t1"] is None
+
+
+def test_namelists_with_several_assignments_per_line(tmp_path):
+    """The namelists shipped with HFBTHO and the reference's own install test (exes/pnfam/tests/pnfam2_serial) put several
+    `key = value` pairs on a line and close the group on the same line; pynfam writes one per line.  Both layouts of the
+    same content must set up the same problem (neutron number, shells, functional, pairing ...)."""
+    import shutil
+    g = os.path.join(GOLDEN, "Cr50_SLY4_6sh")
+    pt = load_points("Cr50_SLY4_6sh")["GT-K1"][0]
+    text = open(os.path.join(g, "hfbtho_NAMELIST.dat")).read()
+    assert "proton_number = 24, neutron_number = 26, type_of_calculation = 1 /" in text      # the multi-key layout
+    one, multi = tmp_path / "one", tmp_path / "multi"
+    for d in (one, multi):
+        d.mkdir()
+        shutil.copy(os.path.join(g, "hfbtho_output.hel"), d)
+        (d / "x.in").write_text(pt["namelist"])
+    (multi / "hfbtho_NAMELIST.dat").write_text(text)
+    # one assignment per line, '/' on its own line
+    out = []
+    for line in text.splitlines():
+        line = line.strip()
+        if line.startswith("&"):
+            head, _, rest = line.partition(" ")
+            out.append(head)
+            line = rest.strip()
+        closing = line.endswith("/")
+        line = line[:-1].strip() if closing else line
+        parts, cur, depth = [], "", 0
+        for tok in line.split(","):
+            if "=" in tok and cur:
+                parts.append(cur)
+                cur = tok
+            else:
+                cur = cur + "," + tok if cur else tok
+        if cur.strip():
+            parts.append(cur)
+        out += ["    " + q.strip() for q in parts if q.strip()]
+        if closing:
+            out.append("/")
+    (one / "hfbtho_NAMELIST.dat").write_text("\n".join(out) + "\n")
+    a, b = host.Problem(str(one), "x.in"), host.Problem(str(multi), "x.in")
+    assert a.iscalar("npr_n") == b.iscalar("npr_n") == 26 and a.iscalar("npr_p") == b.iscalar("npr_p") == 24
+    assert a.iscalar("n_shells") == b.iscalar("n_shells") == 6
+    assert np.array_equal(a.f64("En"), b.f64("En")) and np.array_equal(a.f64("f_elem"), b.f64("f_elem"))
+    assert abs(a.scalar("ala_n") - -12.116887) < 1e-5      # thoout.dat of the reference's hfbtho_main run
 
 
 def test_front_end_basis_and_orthonormality(tmp_path):

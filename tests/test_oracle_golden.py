@@ -24,6 +24,9 @@ CASES = [
     ("Gd162_finiteT_6sh", "RS1-K1", 0),
     ("S40_custom_interaction", "GT-K1", 0),   # couplings from a file (interaction_name = 'FILE:custom_edf.dat')
     ("S40_custom_interaction", "RS1-K0", 0),
+    ("Cr50_SLY4_6sh", "GT-K1", 0),            # the reference's own install test (50Cr, SLy4): omega = 2, 6, 10 + 2i MeV
+    ("Cr50_SLY4_6sh", "GT-K1", 1),
+    ("Cr50_SLY4_6sh", "GT-K1", 2),
 ]
 
 
@@ -49,6 +52,24 @@ def test_oracle_reproduces_golden_point(case, op, idx, tmp_path):
     for (i, lab, si_g, re_g, im_g), (i2, _, si_o, s_o) in zip(pt["trace"], s.trace):
         assert i == i2
         assert abs(si_g - si_o) < 6e-11 and abs(re_g - s_o.real) < 6e-11 and abs(im_g - s_o.imag) < 6e-11
+
+
+def test_reference_install_test_published_values(tmp_path):
+    """exes/pnfam/tests/pnfam2_serial/test_nompi.sh:139-156: the three GT- K=1 strength-function values of 50Cr (SLy4, 6
+    shells; HFB solution made by the reference's hfbtho_main from the test's own namelist,
+    tests/golden/make_cr50_install_test.py) that the reference checks to 0.1 % after installation.  The published numbers
+    are the imaginary parts of S; measured here: 1e-9 (the reference binary run here agrees with them to the same 1e-9)."""
+    from conftest import load_points
+    worst = 0.0
+    for idx, pt in enumerate(load_points("Cr50_SLY4_6sh")["GT-K1"]):
+        stage_point("Cr50_SLY4_6sh", "GT-K1", idx, str(tmp_path))
+        p = host.Problem(str(tmp_path), "x.in")
+        it, si, st = fo.solver_from_problem(p).solve(p.iscalar("max_iter"), p.scalar("convergence_epsilon"))
+        rel = abs(st[0].imag / pt["published_im_strength"] - 1)
+        worst = max(worst, rel)
+        assert rel < 1e-3                      # the reference's own bound
+        assert rel < 1e-8                      # what it actually is
+    print("50Cr install test: worst deviation from the published values %.2e" % worst)
 
 
 def test_no_residual_interaction_two_steps(tmp_path):
