@@ -65,8 +65,6 @@ CASES = [
     ("Gd162_finiteT_6sh", "GT-K0", 1),   # interrupted at max_iter = 5
     ("S40_custom_interaction", "GT-K0", 0),   # couplings from a file (interaction_name = 'FILE:custom_edf.dat')
     ("S40_custom_interaction", "F-K0", 0),
-    ("Cr50_SLY4_6sh", "GT-K1", 0),            # the reference's own install test (test_nompi.sh): 50Cr, SLy4
-    ("Cr50_SLY4_6sh", "GT-K1", 2),
 ]
 
 

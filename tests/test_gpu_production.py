@@ -225,12 +225,3 @@ def test_closed_form_two_body_current_modes(gpu, tmp_path):
     the corrected cross-term fields -- against the reference binary (tests/golden/make_2bc_modes.py)."""
     n, worst = check_fixture(gpu, "S40_2bc_modes", "points.json", str(tmp_path))
     assert n == 11
-
-
-@pytest.mark.parametrize("case,npts", [("S40_2bc_dme", 11), ("Gd162_2bc_dme", 4), ("Gd163_2bc_dme", 3), ("Gd162T_2bc_dme", 2)])
-def test_density_matrix_expansion_two_body_current_modes(gpu, case, npts, tmp_path):
-    """The remaining values of two_body_current_mode: DME exchange term of the GT current alone and with the direct part
-    of the full-FAM field (computed by the host generator: no .tbc is staged), DME vector current of P, DME axial charge of
-    PS0 -- against the reference binary (tests/golden/make_2bc_dme.py)."""
-    n, worst = check_fixture(gpu, case, "points.json", str(tmp_path))
-    assert n == npts

@@ -198,46 +198,6 @@ def test_generator_can_be_switched_off(tmp_path):
         del os.environ["PNFAM_B200_NO_TBC_GENERATOR"]
 
 
-@pytest.mark.gpu
-@pytest.mark.parametrize("case", ["golden:GT-K1", "S40_usep_K1", "Gd162_6sh_usep_K1", "Gd163_blocked_usep_K0", "Gd162_finiteT_K1", "Gd162_12sh_K0"])
-def test_gpu_solve_with_generated_field(case, tmp_path):
-    """The product path end to end: no .tbc in the run directory -> host generator -> batched GPU solve -> the reference's
-    strengths (golden tree: all 30 computed points of GT-K1; reference binary: momentum terms, deformed nucleus), 1e-9."""
-    import re
-    from pynfam_b200 import gpu
-    wd = str(tmp_path)
-    if case.startswith("golden:"):
-        op = case.split(":")[1]
-        pts = load_points("S40_All_GT2bc")[op]
-        stage(os.path.join(GOLDEN, "S40_All_GT2bc"), wd, pts[0]["namelist"], "x")
-        om = [complex(float(re.search(r"real_eqrpa\s*=\s*(\S+)", pt["namelist"]).group(1)),
-                      float(re.search(r"imag_eqrpa\s*=\s*(\S+)", pt["namelist"]).group(1))) for pt in pts]
-        golds = [(gold_rows(pt), pt["iters"]) for pt in pts]
-    else:
-        src = os.path.join(GEN, case)
-        info = json.load(open(os.path.join(GEN, "strengths.json")))["cases"][case]
-        nml = open(os.path.join(src, info["name"] + ".in")).read()
-        stage(src, wd, nml, "x")
-        om = [complex(float(re.search(r"real_eqrpa\s*=\s*(\S+)", nml).group(1)), float(re.search(r"imag_eqrpa\s*=\s*(\S+)", nml).group(1)))]
-        golds = [({k: complex(float(v[0]), float(v[1])) for k, v in info["rows"].items()}, info["iters"])]
-    p = host.Problem(wd, "x.in")
-    assert os.path.isfile(os.path.join(wd, p.label(-2) + ".tbc"))
-    ctx = gpu.Context(p)
-    r = ctx.solve(p, omegas=om)
-    worst = 0.0
-    for i, (gold, iters) in enumerate(golds):
-        loose = abs(om[i].imag) < 0.5 or iters >= 25         # ill-conditioned points: see tests/test_gpu_parity.py
-        if not loose:
-            assert int(r["iters"][i]) == iters, i
-        for k, lab in enumerate(["Strength"] + r["labels"][1:]):
-            if lab in gold:
-                rel = abs(r["strength"][i, k] - gold[lab]) / abs(gold[lab])
-                assert rel < (5e-8 if loose else 1e-9), (i, lab, rel)
-                if not loose:
-                    worst = max(worst, rel)
-    print(case, "worst relative difference on well-conditioned points: %.2e" % worst)
-
-
 def test_factorised_radial_elements_equal_the_literal_sum_at_12_shells(tmp_path):
     """Beyond the sizes the reference binary can be run at here: the per-(A, C) intermediate of the radial elements against
     the reference's literal four-fold Cartesian sum (PNFAM_B200_TBC_LITERAL_RADIAL=1), 12-shell 162Gd, K = 0; the two
