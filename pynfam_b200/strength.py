@@ -618,6 +618,17 @@ def run_contours(rundir, namelist, operators, contour, dest=None, device=0, **so
     return out
 
 
+def _missing_tbc_files(rundir, namelist, fss):
+    """Indices of the operators whose full-FAM two-body-current field has to be computed: GT with
+    two_body_current_mode = x1x1xx or x5x1xx (pnfam_solver.f90:596-640) and no <OP>.tbc in rundir."""
+    text = open(os.path.join(rundir, namelist)).read()
+    m = re.search(r"(?im)^\s*two_body_current_mode\s*=\s*(\d+)", text)
+    mode = int(m.group(1)) if m else 0
+    if mode == 0 or (mode // 10000) % 10 not in (1, 5) or (mode // 100) % 10 == 0:
+        return []
+    return [o for o, fs in enumerate(fss) if fs.bareop.upper() == "GT" and not os.path.isfile(os.path.join(rundir, fs.opname + ".tbc"))]
+
+
 def run_contours_sharded(rundir, namelist, operators, contour, dest=None, dist=None, device=0, solve_points=None,
                          concurrent_solves=None, **solve_kw):
     """run_contours over the ranks of a torch.distributed job (one process per GPU): the (operator, contour point) tasks
@@ -642,16 +653,29 @@ def run_contours_sharded(rundir, namelist, operators, contour, dest=None, dist=N
     fss = [famStrength(op, k, contour) for op, k in operators]
     probs, first = {}, None
     if multi:
+        # Full-FAM two-body currents: a missing <OP>.tbc is computed by the set-up (csrc/host/tbc_generator.cpp, seconds to
+        # minutes per operator).  Every missing file is generated by ONE rank, the files dealt round robin, before the
+        # ranks that own points of those operators set them up and read the cached file.  The list is taken before any
+        # rank starts writing.
+        todo = _missing_tbc_files(rundir, namelist, fss)
+        dist.barrier()
         # The HFB reconstruction is the same on every rank: rank 0 does it once with all host threads and leaves the
         # solution in the set-up cache of the run directory (csrc/host/hfb_front.cpp), the other ranks load it.
         if rank == 0:
             from . import host
             prev = host.set_threads(os.cpu_count() or 1)
-            o0 = next((o for o, idx in mine if len(idx)), 0)
+            owned = [o for o, idx in mine if len(idx)]
+            o0 = next((o for o in owned if o not in todo), todo[0] if todo else (owned[0] if owned else 0))
             probs[o0] = fss[o0].setup(rundir, namelist)
             first = probs[o0]
             host.set_threads(prev)
         dist.barrier()
+        for j, o in enumerate(todo):
+            if j % world == rank and o not in probs:
+                probs[o] = fss[o].setup(rundir, namelist, share_nucleus_with=first)
+                first = first or probs[o]
+        if todo:
+            dist.barrier()
     for o, idx in mine:
         if len(idx) and o not in probs:
             probs[o] = fss[o].setup(rundir, namelist, share_nucleus_with=first)

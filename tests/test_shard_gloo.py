@@ -168,3 +168,52 @@ def test_two_rank_contour_driver_writes_the_same_files_as_one_rank(tmp_path):
         a = open(os.path.join(d1, op + ".out.ctr"), "rb").read()
         assert a == open(os.path.join(d2, op + ".out.ctr"), "rb").read() and len(a) > 500
         assert os.path.isfile(os.path.join(d2, op + ".out"))
+
+
+def _tbc_worker(rank, world, port, wd, dest):
+    from pynfam_b200.strength import famContour, run_contours_sharded
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    os.environ["PNFAM_B200_SETUP_TIMING"] = "1"          # the generator reports on stderr when it runs
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    c = famContour("CIRCLE", {"energy_min": 0.0, "energy_max": 10.476036, "nr_points": 14})
+    import contextlib
+    import io
+    import sys
+    log = os.path.join(dest, "stderr.%d" % rank)
+    fd = os.open(log, os.O_WRONLY | os.O_CREAT | os.O_TRUNC)
+    os.dup2(fd, 2)
+    fss = run_contours_sharded(wd, "x.in", [("GT-", 0), ("GT-", 1)], c, dest=dest, dist=dist, solve_points=_stub_solve)
+    assert [f.opname for f in fss] == ["GT-K0", "GT-K1"]
+    dist.destroy_process_group()
+
+
+def test_two_ranks_generate_each_missing_two_body_current_file_once(tmp_path):
+    """Full-FAM two-body currents in a sharded run whose run directory has no .tbc files: the operators' points are split
+    over both ranks, yet each file is computed by exactly one rank (round robin) and read by the other; the files equal the
+    reference's (tests/golden/S40_All_GT2bc)."""
+    import shutil
+    from conftest import GOLDEN, load_points
+    from test_tbc_generator import compare_files
+    wd, dest = str(tmp_path / "w"), str(tmp_path / "o")
+    os.makedirs(wd)
+    os.makedirs(dest)
+    src = os.path.join(GOLDEN, "S40_All_GT2bc")
+    for f in ("hfbtho_NAMELIST.dat", "hfbtho_output.hel"):
+        shutil.copy(os.path.join(src, f), wd)
+    open(os.path.join(wd, "x.in"), "w").write(load_points("S40_All_GT2bc")["GT-K0"][0]["namelist"])
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    procs = [ctx.Process(target=_tbc_worker, args=(r, 2, port, wd, dest)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=300)
+        assert p.exitcode == 0
+    runs = [open(os.path.join(dest, "stderr.%d" % r)).read().count("2BC 1D tables") for r in range(2)]
+    assert runs == [1, 1], runs                         # two files, one generation on each rank, none repeated
+    for op in ("GT-K0", "GT-K1"):
+        assert compare_files(os.path.join(wd, op + ".tbc"), os.path.join(src, op + ".tbc")) < 1e-12
+        assert os.path.isfile(os.path.join(dest, op + ".out.ctr"))
