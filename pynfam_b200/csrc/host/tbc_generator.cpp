@@ -98,6 +98,7 @@ struct Tables {
   std::vector<double> zk[NKIND];       // [g][i][j][k][l] over 0..nzx
   std::vector<double> rk[NKIND];       // [g][i][j][k][l] over 0..nsm
   std::vector<double> rkT[NKIND];      // the same with the last two indices exchanged (exchange elements)
+  std::vector<double> rkg[NKIND], rkgT[NKIND];   // [i][j][k][l][g] copies of rk / rkT (Gaussian index fastest) for build_q
 
   size_t ibig(int g, int i, int j, int k, int l) const {
     const size_t n = nbig + 1;
@@ -292,6 +293,15 @@ Tables build_tables(const TbcProblem& s, bool use_p) {
           for (int nj = 0; nj <= n; nj++)
             for (int nk = 0; nk <= n; nk++)
               for (int nl = 0; nl <= n; nl++) t.rkT[kd][t.ir(g, ni, nj, nl, nk)] = t.rk[kd][t.ir(g, ni, nj, nk, nl)];
+      t.rkg[kd].assign(t.rk[kd].size(), 0.0); t.rkgT[kd].assign(t.rk[kd].size(), 0.0);
+      for (int g = 0; g < NG; g++)
+        for (int ni = 0; ni <= n; ni++)
+          for (int nj = 0; nj <= n; nj++)
+            for (int nk = 0; nk <= n; nk++)
+              for (int nl = 0; nl <= n; nl++) {
+                t.rkg[kd][(t.ir(0, ni, nj, nk, nl)) * NG + g] = t.rk[kd][t.ir(g, ni, nj, nk, nl)];
+                t.rkgT[kd][(t.ir(0, ni, nj, nk, nl)) * NG + g] = t.rkT[kd][t.ir(g, ni, nj, nk, nl)];
+              }
     }
   }
   return t;
@@ -384,79 +394,83 @@ double rad_cmplx_imag(const Tables& t, int g, int kx, int ky, int ni, int li, in
 inline int ipow_re(int n) { n = ((n % 4) + 4) % 4; return n == 0 ? 1 : n == 2 ? -1 : 0; }
 inline int ipow_im(int n) { n = ((n % 4) + 4) % 4; return n == 1 ? 1 : n == 3 ? -1 : 0; }
 // Storage: Q is only needed where XB + YB = N_B and XD + YD = N_D are total Cartesian quanta of a basis state, so it is
-// kept as Q[g][tri(N_B, yB)][tri(N_D, yD)], tri(N, y) = N (N + 1) / 2 + y: 1.1 MB per (kind, orientation) at 16 shells,
-// and the sum of one element walks rows of it.
+// kept as Q[tri(N_B, yB)][tri(N_D, yD)][g], tri(N, y) = N (N + 1) / 2 + y, the six Gaussians innermost: 1.1 MB per
+// (kind, orientation) at 16 shells; the sum of one element walks rows of it for all Gaussians at once, and the build
+// shares its index arithmetic between them.
 inline int tri(int N, int y) { return N * (N + 1) / 2 + y; }
 void build_q(const Tables& t, int kind, bool exc, int nA, int lA, int nC, int lC, std::vector<double>& Q, int mode = 0, int ky = G00) {
-  const size_t n1 = t.nsm + 1, n2 = n1 * n1, n3 = n2 * n1, slab = n3 * n1;
+  const size_t n1 = t.nsm + 1, n2 = n1 * n1, n3 = n2 * n1;
   const int nmax = t.nrlx;
-  const size_t M = (size_t)(nmax + 1) * (nmax + 2) / 2, qslab = M * M;
-  Q.assign((size_t)NG * qslab, 0.0);
-  const std::vector<double>& MX = exc ? t.rkT[kind] : t.rk[kind];
-  const std::vector<double>& MY = exc ? t.rkT[ky] : t.rk[ky];
+  const size_t M = (size_t)(nmax + 1) * (nmax + 2) / 2;
+  Q.assign(M * M * NG, 0.0);
+  const double* mx = (exc ? t.rkgT[kind] : t.rkg[kind]).data();
+  const double* my = (exc ? t.rkgT[ky] : t.rkg[ky]).data();
   const int NA = 2 * nA + std::abs(lA), NC = 2 * nC + std::abs(lC);
   const int xpar = KIND_D[kind] + (KIND_P[kind] ? 1 : 0), ypar = KIND_D[ky] + (KIND_P[ky] ? 1 : 0);
   const double* CA = &t.cp2c[((size_t)nA * (4 * t.nsh + 1) + (lA + 2 * t.nsh)) * (2 * t.nsh + 1)];
   const double* CC = &t.cp2c[((size_t)nC * (4 * t.nsh + 1) + (lC + 2 * t.nsh)) * (2 * t.nsh + 1)];
-  for (int g = 0; g < NG; g++) {
-    const double* mx = MX.data() + (size_t)g * slab;
-    const double* my = MY.data() + (size_t)g * slab;
-    double* q = Q.data() + (size_t)g * qslab;
-    for (int yA = 0; yA <= NA; yA++)
-      for (int yC = 0; yC <= NC; yC++) {
-        const double sgn = mode == 0 ? ((((yA + (yA + yC) / 2) % 2) ? -1.0 : 1.0)) : mode == 1 ? (double)ipow_re(yA - yC) : (double)ipow_im(yA - yC);
-        const double w = CA[yA] * CC[yC] * sgn;
-        if (w == 0.0) continue;
-        for (int YB = 0; YB <= nmax; YB++)
-          for (int YD = (yA + YB + yC + ypar) % 2; YD <= nmax; YD += 2) {
-            const double l = w * my[(size_t)yA * n3 + (size_t)YB * n2 + (size_t)yC * n1 + YD];
-            if (l == 0.0) continue;
-            const double* mrow = mx + (size_t)(NA - yA) * n3 + (size_t)(NC - yC) * n1;
-            // target column tri(XD + YD, YD) = tri0[XD]: hoisted, the x element vanishes for an odd (sum + d + [p != 0])
-            int tri0[64];
-            for (int XD = 0; XD <= nmax - YD; XD++) tri0[XD] = tri(XD + YD, YD);
-            const int xd_par = (NA - yA + NC - yC + xpar) % 2;
-            for (int XB = 0; XB <= nmax - YB; XB++) {
-              double* qq = q + (size_t)tri(XB + YB, YB) * M;
-              const double* mm = mrow + (size_t)XB * n2;
-              for (int XD = (xd_par + XB) % 2; XD <= nmax - YD; XD += 2) qq[tri0[XD]] += l * mm[XD];
+  double* q = Q.data();
+  for (int yA = 0; yA <= NA; yA++)
+    for (int yC = 0; yC <= NC; yC++) {
+      const double sgn = mode == 0 ? ((((yA + (yA + yC) / 2) % 2) ? -1.0 : 1.0)) : mode == 1 ? (double)ipow_re(yA - yC) : (double)ipow_im(yA - yC);
+      const double w = CA[yA] * CC[yC] * sgn;
+      if (w == 0.0) continue;
+      const double* mrow = mx + ((size_t)(NA - yA) * n3 + (size_t)(NC - yC) * n1) * NG;
+      const int xd_par = (NA - yA + NC - yC + xpar) % 2;
+      for (int YB = 0; YB <= nmax; YB++)
+        for (int YD = (yA + YB + yC + ypar) % 2; YD <= nmax; YD += 2) {
+          const double* myp = my + ((size_t)yA * n3 + (size_t)YB * n2 + (size_t)yC * n1 + YD) * NG;
+          double l[NG];
+          for (int g = 0; g < NG; g++) l[g] = w * myp[g];
+          // target column tri(XD + YD, YD) = tri0[XD]: hoisted; the x element vanishes for an odd (sum + d + [p != 0])
+          int tri0[64];
+          for (int XD = 0; XD <= nmax - YD; XD++) tri0[XD] = tri(XD + YD, YD) * NG;
+          for (int XB = 0; XB <= nmax - YB; XB++) {
+            double* qq = q + (size_t)tri(XB + YB, YB) * M * NG;
+            const double* mm = mrow + (size_t)XB * n2 * NG;
+            for (int XD = (xd_par + XB) % 2; XD <= nmax - YD; XD += 2) {
+              double* dst = qq + tri0[XD];
+              const double* src = mm + (size_t)XD * NG;
+              for (int g = 0; g < NG; g++) dst[g] += l[g] * src[g];
             }
           }
-      }
-  }
-}
-
-inline double radx_q(const Tables& t, const double* qg, int nB, int lB, int nD, int lD) {
-  const int NB = 2 * nB + std::abs(lB), ND = 2 * nD + std::abs(lD);
-  const size_t M = (size_t)(t.nrlx + 1) * (t.nrlx + 2) / 2;
-  const double* CB = &t.cp2c[((size_t)nB * (4 * t.nsh + 1) + (lB + 2 * t.nsh)) * (2 * t.nsh + 1)];
-  const double* CD = &t.cp2c[((size_t)nD * (4 * t.nsh + 1) + (lD + 2 * t.nsh)) * (2 * t.nsh + 1)];
-  double v = 0.0;
-  for (int yB = 0; yB <= NB; yB++) {
-    const double* row = qg + (size_t)tri(NB, yB) * M + tri(ND, 0);
-    double acc = 0.0;
-    for (int yD = 0; yD <= ND; yD++) {
-      const double sg = ((yB + (yB + yD + 1) / 2) % 2) ? -1.0 : 1.0;
-      acc += sg * CD[yD] * row[yD];
+        }
     }
-    v += CB[yB] * acc;
-  }
-  return v;
 }
 
-inline double rad_q_imag(const Tables& t, const double* qre, const double* qim, int nB, int lB, int nD, int lD) {
+// all six Gaussians of one element
+inline void radx_q(const Tables& t, const double* q, int nB, int lB, int nD, int lD, double* v) {
   const int NB = 2 * nB + std::abs(lB), ND = 2 * nD + std::abs(lD);
   const size_t M = (size_t)(t.nrlx + 1) * (t.nrlx + 2) / 2;
   const double* CB = &t.cp2c[((size_t)nB * (4 * t.nsh + 1) + (lB + 2 * t.nsh)) * (2 * t.nsh + 1)];
   const double* CD = &t.cp2c[((size_t)nD * (4 * t.nsh + 1) + (lD + 2 * t.nsh)) * (2 * t.nsh + 1)];
-  double v = 0.0;
+  for (int g = 0; g < NG; g++) v[g] = 0.0;
   for (int yB = 0; yB <= NB; yB++) {
-    const size_t at = (size_t)tri(NB, yB) * M + tri(ND, 0);
-    double acc = 0.0;
-    for (int yD = 0; yD <= ND; yD++) acc += CD[yD] * (ipow_im(yB - yD) * qre[at + yD] + ipow_re(yB - yD) * qim[at + yD]);
-    v += CB[yB] * acc;
+    const double* row = q + ((size_t)tri(NB, yB) * M + tri(ND, 0)) * NG;
+    double acc[NG] = {0, 0, 0, 0, 0, 0};
+    for (int yD = 0; yD <= ND; yD++) {
+      const double c = (((yB + (yB + yD + 1) / 2) % 2) ? -1.0 : 1.0) * CD[yD];
+      for (int g = 0; g < NG; g++) acc[g] += c * row[(size_t)yD * NG + g];
+    }
+    for (int g = 0; g < NG; g++) v[g] += CB[yB] * acc[g];
   }
-  return v;
+}
+
+inline void rad_q_imag(const Tables& t, const double* qre, const double* qim, int nB, int lB, int nD, int lD, double* v) {
+  const int NB = 2 * nB + std::abs(lB), ND = 2 * nD + std::abs(lD);
+  const size_t M = (size_t)(t.nrlx + 1) * (t.nrlx + 2) / 2;
+  const double* CB = &t.cp2c[((size_t)nB * (4 * t.nsh + 1) + (lB + 2 * t.nsh)) * (2 * t.nsh + 1)];
+  const double* CD = &t.cp2c[((size_t)nD * (4 * t.nsh + 1) + (lD + 2 * t.nsh)) * (2 * t.nsh + 1)];
+  for (int g = 0; g < NG; g++) v[g] = 0.0;
+  for (int yB = 0; yB <= NB; yB++) {
+    const size_t at = ((size_t)tri(NB, yB) * M + tri(ND, 0)) * NG;
+    double acc[NG] = {0, 0, 0, 0, 0, 0};
+    for (int yD = 0; yD <= ND; yD++) {
+      const double ci = CD[yD] * ipow_im(yB - yD), cr = CD[yD] * ipow_re(yB - yD);
+      for (int g = 0; g < NG; g++) acc[g] += ci * qre[at + (size_t)yD * NG + g] + cr * qim[at + (size_t)yD * NG + g];
+    }
+    for (int g = 0; g < NG; g++) v[g] += CB[yB] * acc[g];
+  }
 }
 
 inline int kind_of(int d, int pp) {
@@ -796,15 +810,14 @@ TbcField generate_two_body_current_field(const TbcProblem& s) {
       std::vector<double> JR((size_t)npairs * 4 * wrec, 0.0);
       std::vector<char> use_n(npairs, 0), use_t(npairs, 0);
       std::vector<double> Q[NKIND][2];
-      const size_t qM = (size_t)(t.nrlx + 1) * (t.nrlx + 2) / 2, qslab = qM * qM;
-      auto q_of = [&](int kind, int exc, int g) -> const double* {
+      auto q_of = [&](int kind, int exc) -> const double* {
         if (Q[kind][exc].empty()) { const double q0 = omp_get_wtime(); build_q(t, kind, exc != 0, ra, la, rc, lc, Q[kind][exc]); t_q += omp_get_wtime() - q0; }
-        return Q[kind][exc].data() + (size_t)g * qslab;
+        return Q[kind][exc].data();
       };
       std::vector<double> QC[NKIND][2][2];      // rad_cmplx intermediates: [y kind][exc][re | im]
-      auto qc_of = [&](int ky, int exc, int part, int g) -> const double* {
-        if (QC[ky][exc][part].empty()) build_q(t, G10, exc != 0, ra, la, rc, lc, QC[ky][exc][part], 1 + part, ky);
-        return QC[ky][exc][part].data() + (size_t)g * qslab;
+      auto qc_of = [&](int ky, int exc, int part) -> const double* {
+        if (QC[ky][exc][part].empty()) { const double q0 = omp_get_wtime(); build_q(t, G10, exc != 0, ra, la, rc, lc, QC[ky][exc][part], 1 + part, ky); t_q += omp_get_wtime() - q0; }
+        return QC[ky][exc][part].data();
       };
       for (int p = 0; p < npairs; p++) {
         const RadClass& D = cls[pairs[p][0]];
@@ -813,21 +826,26 @@ TbcField generate_two_body_current_field(const TbcProblem& s) {
         const int dn = la + lb - lc - ld, dt = la - lb - lc + ld;
         use_n[p] = dn >= K - 1 && dn <= K + 1;
         use_t[p] = dt >= K - 1 && dt <= K + 1;
-        for (int g = 0; g < NG; g++) {
-          double* j = JR.data() + ((size_t)p * 4) * wrec + g;
-          double tmp[NCOMP];
-          for (int v = 0; v < 4; v++) {
-            if (v < 2 ? !use_n[p] : !use_t[p]) continue;
-            const int exc = v & 1, sl = v < 2 ? 1 : -1;              // orientation of Lambda_b, Lambda_d
-            const int msum = -la - sl * lb + lc + sl * ld;
+        for (int v = 0; v < 4; v++) {
+          if (v < 2 ? !use_n[p] : !use_t[p]) continue;
+          const int exc = v & 1, sl = v < 2 ? 1 : -1;              // orientation of Lambda_b, Lambda_d
+          const int msum = -la - sl * lb + lc + sl * ld;
+          // the elements of all six Gaussians per derivative kind, made on first use
+          double xv[NKIND][NG], xcv[NKIND][NG];
+          bool have_x[NKIND] = {false, false, false, false, false, false, false}, have_xc[NKIND] = {false, false, false, false, false, false, false};
+          for (int g = 0; g < NG; g++) {
+            double* j = JR.data() + ((size_t)p * 4) * wrec + g;
+            double tmp[NCOMP];
             auto X = [&](int kind) {
               if (literal) return exc ? radx(t, g, kind, ra, la, rb, sl * lb, rd, sl * ld, rc, lc) : radx(t, g, kind, ra, la, rb, sl * lb, rc, lc, rd, sl * ld);
-              return radx_q(t, q_of(kind, exc, g), rb, sl * lb, rd, sl * ld);
+              if (!have_x[kind]) { radx_q(t, q_of(kind, exc), rb, sl * lb, rd, sl * ld, xv[kind]); have_x[kind] = true; }
+              return xv[kind][g];
             };
             auto XC = [&](int kind) {
-              if (!literal) return rad_q_imag(t, qc_of(kind, exc, 0, g), qc_of(kind, exc, 1, g), rb, sl * lb, rd, sl * ld);
-              return exc ? rad_cmplx_imag(t, g, G10, kind, ra, la, rb, sl * lb, rd, sl * ld, rc, lc)
-                         : rad_cmplx_imag(t, g, G10, kind, ra, la, rb, sl * lb, rc, lc, rd, sl * ld);
+              if (literal) return exc ? rad_cmplx_imag(t, g, G10, kind, ra, la, rb, sl * lb, rd, sl * ld, rc, lc)
+                                      : rad_cmplx_imag(t, g, G10, kind, ra, la, rb, sl * lb, rc, lc, rd, sl * ld);
+              if (!have_xc[kind]) { rad_q_imag(t, qc_of(kind, exc, 0), qc_of(kind, exc, 1), rb, sl * lb, rd, sl * ld, xcv[kind]); have_xc[kind] = true; }
+              return xcv[kind][g];
             };
             calc_jr(K, use_p, msum, X, XC, tmp);
             for (int c = 0; c < ncomp; c++) j[(size_t)v * wrec + (size_t)c * NG] = tmp[c];
