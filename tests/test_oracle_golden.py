@@ -72,6 +72,35 @@ def test_reference_install_test_published_values(tmp_path):
     print("50Cr install test: worst deviation from the published values %.2e" % worst)
 
 
+def test_triprod_known_answers_of_the_reference_unit_test():
+    """exes/pnfam/tests/modules/blockmatrix_type_test.f90: the reference's own unit test of `triprod` -- hand-built
+    block matrices on the block grid db = [3, 2, 1], three products with hand-computed answers (its tolerance: 1e-5; the
+    numbers are small integers, so they are met exactly) and the block structure of the results."""
+    import numpy as np
+    db = [3, 2, 1]
+
+    def bm(ir2c, ic2r, ir2m, ic2m, elem):
+        m = fo.BlockMatrix(3, len(elem))
+        m.ir2c[:], m.ic2r[:], m.ir2m[:], m.ic2m[:] = ir2c, ic2r, ir2m, ic2m
+        m.elem = np.array(elem, float)
+        return m
+    A = bm([1, 2, 3], [1, 2, 3], [1, 10, 14], [1, 10, 14], [1, 1, -1, 2, 0, 2, 2, 3, 1, 5, 6, 1, 2, 20])
+    B = bm([3, 1, 0], [2, 0, 1], [1, 4, 0], [4, 0, 1], [6, 2, -1, 3, -1, 2, -2, 1, 0])
+    C = bm([1, 2, 3], [1, 2, 3], [1, 10, 14], [1, 10, 14], [2, 1, 0, 3, -1, 0, 1, 0, 2, 1, -1, 0, 1, 3])
+    U = bm([1, 2, 3], [1, 2, 3], [1, 10, 14], [1, 10, 14], [1, 0, 0, 0, 1, 0, 0, 0, 1, 1, 0, 0, 1, 1])
+    same = lambda x, y: all(np.array_equal(getattr(x, k), getattr(y, k)) for k in ("ir2c", "ic2r", "ir2m", "ic2m"))
+    M = fo.BlockMatrix(3, 14)
+    fo.triprod(db, 'n', A, 'n', B, 'n', C, 1.0, 0.0, M)                  # test 1: A B C
+    assert np.array_equal(M.elem[:9], [24, 9, -9, 36, 40, 34, 40, 24, 28]) and same(B, M)
+    M = fo.BlockMatrix(3, 14)
+    fo.triprod(db, 'n', U, 't', B, 'n', U, 1.0, 0.0, M)                  # test 2: B^T, structure transposed
+    assert np.array_equal(M.elem[:9], [3, 2, 1, -1, -2, 0, 6, 2, -1]) and not same(B, M)
+    assert list(M.ir2c) == [2, 0, 1] and list(M.ic2r) == [3, 1, 0]
+    M = fo.BlockMatrix(3, 14)
+    fo.triprod(db, 't', A, 'n', B, 't', C, 1.0, 0.0, M)                  # test 3: A^T B C^T
+    assert np.array_equal(M.elem[:9], [27, 30, 51, 17, -3, 11, 3, 10, 2]) and same(B, M)
+
+
 def test_no_residual_interaction_two_steps(tmp_path):
     """interaction_name='NONE' => dH = 0, no mixing, converged after 2 steps with si = 0
     (pnfam_solver.f90:138-141, 262-264); known answer from the live reference binary."""

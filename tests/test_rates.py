@@ -173,3 +173,22 @@ def test_phase_space_functions_against_the_reference_module():
         # the 20-point continued fraction amplifies last-bit differences of its inputs (the real-axis integrals above
         # agree to 1e-12) where f_n is small: compare on the scale of the function (worst case 3e-9, beta+ Z = 63)
         assert np.max(np.abs(got - want)) < 1e-8 * np.max(np.abs(want)), (r["beta"], r["Z"], r["n"])
+
+
+def test_fermi_function_against_the_landolt_boernstein_table_of_the_reference_unit_test():
+    """exes/pnfam/tests/modules/fermi_test.f90 (f0_us_test, lambda2_us_test): the reference's own unit test compares the
+    unscreened Fermi function F0 and lambda_2 with the Landolt-Boernstein tables for Z = 32 (A = 72) and Z = 84 (A = 210) at
+    eleven momenta p / m_e, with cut-offs of 0.1 % and 35 %.  Same table, same cut-offs (measured: 0.018 % and 25 %)."""
+    import numpy as np
+    from pynfam_b200 import rates
+    p = np.array([0.1, 0.5, 1.0, 2.0, 3.0, 4.0, 5.0, 10.0, 20.0, 25.0, 30.0])
+    table = {   # (Z, A): (F0, lambda_2), fermi_test.f90:365-388
+        (32, 72): ([2.1611e1, 4.8821, 3.2982, 2.7288, 2.5778, 2.5051, 2.4594, 2.3476, 2.2546, 2.2266, 2.2039],
+                   [5.5523, 1.0796, 0.9524, 0.9344, 0.9396, 0.9464, 0.9531, 0.9801, 1.0199, 1.0367, 1.0525]),
+        (84, 210): ([3.8164e2, 8.0476e1, 4.5386e1, 2.9197e1, 2.3706e1, 2.0707e1, 1.8726e1, 1.3865e1, 1.0340e1, 9.4135, 8.7180],
+                    [15.6186, 1.1168, 0.6928, 0.6440, 0.6798, 0.7222, 0.7637, 0.9429, 1.2198, 1.3340, 1.4352]),
+    }
+    w = np.sqrt(p * p + 1.0)
+    for (Z, A), (f0, l2) in table.items():
+        assert np.max(np.abs(rates.Fermi(0, Z, A, w.copy(), False) / np.array(f0) - 1.0)) < 1e-3
+        assert np.max(np.abs(rates.lambda_ke(2, Z, A, w.copy(), False) / np.array(l2) - 1.0)) < 0.35
