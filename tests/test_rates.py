@@ -192,3 +192,17 @@ def test_fermi_function_against_the_landolt_boernstein_table_of_the_reference_un
     for (Z, A), (f0, l2) in table.items():
         assert np.max(np.abs(rates.Fermi(0, Z, A, w.copy(), False) / np.array(f0) - 1.0)) < 1e-3
         assert np.max(np.abs(rates.lambda_ke(2, Z, A, w.copy(), False) / np.array(l2) - 1.0)) < 0.35
+
+
+def test_phase_space_integrals_against_the_mathematica_values_of_the_reference_unit_test():
+    """exes/pnfam/tests/modules/phasespace_test.f90 (real_psi_test): f_1 .. f_6 for Z_final = 57, A = 174,
+    W_max = 27.766732 against Mathematica, cut-off 5e-4 there (measured here: <= 4.8e-6)."""
+    import numpy as np
+    from pynfam_b200 import rates
+    mathematica = [2.209608199614178e5, 2.577925271039772e6, 3.470883516733893e7, 5.398097056657456e8,
+                   5.998661241258061e8, 5.178321508233396e8]
+    ps = rates.phaseSpace("-")
+    for n, ref in enumerate(mathematica, start=1):
+        val = float(np.ravel(ps.calcPsi(n, 57, 174, np.array([27.766732])))[0])
+        assert abs(val / ref - 1.0) < 5e-4
+        assert abs(val / ref - 1.0) < 1e-5
