@@ -3,7 +3,9 @@
 
 #include <algorithm>
 #include <cctype>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <fstream>
 #include <mutex>
 #include <stdexcept>
@@ -845,7 +847,7 @@ bool read_tbc(const std::string& path, const FamBasis& b, const FamInput& in, Ex
 }
 
 void apply_two_body_current_gt(const std::string& tbc_path, const FamBasis& b, const FamInput& in, const TwoBody& tb, ExtField& f,
-                               const HfbSolution* hfb) {
+                               const HfbSolution* hfb, std::vector<std::string>* notes) {
   // setup_extfield (pnfam_solver.f90:586-646): F = [-GT_1body if 1BC+2BC] + GT[rho_fac] (+ Yukawa part from <name>.tbc
   // for the full-FAM mode).  rho_fac: contact term, plus the nuclear-matter exchange term in the LDA modes.
   std::vector<double> tmp(f.mat.elem.size(), 0.0);
@@ -863,7 +865,19 @@ void apply_two_body_current_gt(const std::string& tbc_path, const FamBasis& b, c
     // "Starting calculation from scratch..." (fam_io(-1) failed, pnfam_solver.f90:622-640): compute and cache
     if (!hfb || getenv("PNFAM_B200_NO_TBC_GENERATOR"))
       throw std::runtime_error(why + " (the two-body-current field generator is switched off: provide the .tbc file)");
+    // the reference's log lines (pnfam_storage.f90:690-702, pnfam_solver.f90:623-632)
+    if (notes) {
+      notes->push_back("  * " + why + ": starting calculation from scratch...");
+      notes->push_back("  * Calculating 2BC matrix elements...");
+    }
+    const auto t_gen = std::chrono::steady_clock::now();
     const TbcField fld = generate_two_body_current_field(*hfb, b, f, in.two_body_current_usep);
+    if (notes) {
+      char buf[96];
+      std::snprintf(buf, sizeof buf, "  * Two-body current wall time (min): %12.3E",
+                    std::chrono::duration<double>(std::chrono::steady_clock::now() - t_gen).count() / 60.0);
+      notes->push_back(buf);
+    }
     const double c3 = in.two_body_current_lecs[0], c4 = in.two_body_current_lecs[1] + 0.25;
     const double fac[6] = {c3, c3, c4, c4, 1.0, 1.0};            // summed like read_tbc does: the next set-up, which reads
     std::fill(f.mat.elem.begin(), f.mat.elem.end(), 0.0);        // the cached file, gets bit-identical elements
@@ -873,6 +887,7 @@ void apply_two_body_current_gt(const std::string& tbc_path, const FamBasis& b, c
     }
     try { write_tbc(tbc_path, b, in, f, tb, fld); } catch (const std::exception&) { /* a read-only run directory: keep going */ }
   }
+  else if (notes) notes->push_back("  * Reading from extfield file: " + tbc_path.substr(tbc_path.find_last_of('/') + 1));
   for (size_t i = 0; i < tmp.size(); i++) f.mat.elem[i] += tmp[i];
 }
 

@@ -151,7 +151,7 @@ bool read_tbc(const std::string& path, const FamBasis& b, const FamInput& in, Ex
 //   hfb: the undoubled HFB solution; when the file is absent or does not fit the calculation the Yukawa part is computed
 //   (generate_two_body_current_field) and cached in <name>.tbc like the reference does; nullptr = read only
 void apply_two_body_current_gt(const std::string& tbc_path, const FamBasis& b, const FamInput& in, const TwoBody& tb, ExtField& f,
-                               const HfbSolution* hfb = nullptr);
+                               const HfbSolution* hfb = nullptr, std::vector<std::string>* notes = nullptr);
 
 // The Yukawa part of the full-FAM two-body-current GT field (effective_2bc_extfield, pnfam_extfield_2bc.f90:26-465;
 // csrc/host/tbc_generator.cpp), low-energy constants stripped as in the .tbc file: c[0..5] = c3 direct, c3 exchange,

@@ -101,7 +101,7 @@ std::unique_ptr<Problem> Problem::build(const std::string& rundir, const FamInpu
   if (in.compute_crossterms)
     p->g = make_crossterms(p->f, [&](const std::string& beta, const std::string& l, int k) { return field_of(beta, l, k, l != "R"); });
   if (mode != 0 && p->f.label == "GT" && tb.u[4] != 0)
-    apply_two_body_current_gt(d + "/" + in.fam_output_filename + ".tbc", b, in, tb, p->f, &p->nuc->hfb);
+    apply_two_body_current_gt(d + "/" + in.fam_output_filename + ".tbc", b, in, tb, p->f, &p->nuc->hfb, &p->notes);
   p->setup_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   return p;
 }

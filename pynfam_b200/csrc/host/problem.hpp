@@ -28,6 +28,7 @@ struct Problem {
   ExtField f;
   std::vector<ExtField> g;
   double setup_seconds = 0;
+  std::vector<std::string> notes;       // set-up messages of the reference's log (two-body-current file read / computed)
   static std::unique_ptr<Problem> load(const std::string& rundir, const std::string& namelist,
                                        std::shared_ptr<Nucleus> nuc = nullptr);
   // the same from an already parsed (and possibly overridden) namelist -- what the contour driver does per task

@@ -120,6 +120,8 @@ inline void write_dat(const Problem& p, const std::string& namelist, const std::
   log.fmt(" Broyden mixing factor:           %4.2f", (double)0.7f);
   log.fmt(" Convergence limit:               %8.1E", in.convergence_epsilon);
   log.line("");
+  for (const auto& n : p.notes) log.line(n);
+  if (!p.notes.empty()) log.line("");
   log.line(" " + dash);
   log.line(center(" pnFAM Interaction", w));
   log.line(" " + dash);
