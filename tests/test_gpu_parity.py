@@ -349,14 +349,21 @@ def test_contour_executable_against_oracle(gpu, tmp_path):
             assert _rel(s, dat["rows"]["Strength"]) < 1e-15
             so = fo.solver_from_problem(prob, model=model, omega=w)
             it, _, st = so.solve(300, 1e-7)
-            if it >= 25:
-                # ill-conditioned class (27 Broyden steps at w = 6 + 0.75i, residual 9e-8 at the stop): the stopping rule
-                # may trigger a step or two apart; the result must lie within the oracle's own terminal movement of S
-                tr = [t[-1] for t in so.trace]
-                scatter = max(abs(tr[j] - tr[j - 1]) for j in range(len(tr) - 3, len(tr))) / abs(st[0])
-                assert abs(it - dat["iters"]) <= 2 and _rel(s, st[0]) < LOOSE_TOL + 1.5 * scatter, (k, i, it, dat["iters"])
+            tr = [t[-1] for t in so.trace]
+            scatter = max(abs(tr[j] - tr[j - 1]) for j in range(len(tr) - 3, len(tr))) / abs(st[0])
+            if dat["iters"] == it:
+                # ill-conditioned class (>= 25 Broyden steps; 27 at w = 6 + 0.75i): within the oracle's own terminal movement of S
+                assert _rel(s, st[0]) < (TOL if it < 25 else LOOSE_TOL + 1.5 * scatter), (k, i)
             else:
-                assert it == dat["iters"] and _rel(s, st[0]) < TOL, (k, i)
+                # The stopping rule max|dX| < eps triggered a step or two apart.  Only legitimate when the oracle's residual at
+                # the deciding iteration is borderline (within 15 % of eps: 1.04e-7 at step 21 of K = 1, w = 3.5 + 0.75i;
+                # 9.2e-8 at step 27 of K = 0, w = 6 + 0.75i) or in the ill-conditioned class; the state is then compared at
+                # EQUAL iteration numbers: the oracle is run for exactly the executable's count.
+                res = {t[0]: t[2] for t in so.trace}
+                first = min(it, dat["iters"])
+                assert abs(it - dat["iters"]) <= 2 and (it >= 25 or abs(res[first] / 1e-7 - 1.0) < 0.15), (k, i, it, dat["iters"])
+                _, _, st_eq = fo.solver_from_problem(prob, model=model, omega=w).solve(dat["iters"], 0.0)
+                assert _rel(s, st_eq[0]) < LOOSE_TOL + 1.5 * scatter, (k, i, it, dat["iters"])
 
 
 def _sharded_worker(rank, world, port, wd, dest):
