@@ -765,7 +765,7 @@ TbcField generate_two_body_current_field(const TbcProblem& s) {
   const int nz1 = t.nzx + 1;
   const size_t per_za = (size_t)nz1 * wsz * sizeof(double);
   double mem_gb = 4.0;                                // PNFAM_B200_TBC_MEM_GB: bound on the z-contracted densities kept at once
-  if (const char* e = getenv("PNFAM_B200_TBC_MEM_GB")) mem_gb = std::max(0.01, atof(e));
+  if (const char* e = getenv("PNFAM_B200_TBC_MEM_GB")) mem_gb = std::max(1e-4, atof(e));
   const int za_chunk = (int)std::max<size_t>(1, std::min<size_t>(nz1, (size_t)(mem_gb * 1073741824.0) / std::max<size_t>(1, per_za)));
   std::vector<double> W;
   for (int za0 = 0; za0 < nz1; za0 += za_chunk) {

@@ -220,3 +220,25 @@ def test_factorised_radial_elements_equal_the_literal_sum_at_12_shells(tmp_path)
     worst = compare_files(files[0], files[1])
     print("12 shells, factorised vs literal radial sum: %.2e" % worst)
     assert worst < 1e-12
+
+
+def test_chunked_z_contraction_gives_the_same_field(tmp_path):
+    """PNFAM_B200_TBC_MEM_GB bounds the z-contracted densities kept at once (large bases: 24 shells needs two chunks under
+    the default 4 GB); with a bound that forces several chunks at 6 shells the file still equals the reference's."""
+    wd = str(tmp_path)
+    src = os.path.join(GOLDEN, "S40_All_GT2bc")
+    stage(src, wd, load_points("S40_All_GT2bc")["GT-K1"][0]["namelist"], "GT-K1")
+    os.environ["PNFAM_B200_TBC_MEM_GB"] = "0.003"
+    os.environ["PNFAM_B200_SETUP_TIMING"] = "1"
+    fd_saved = os.dup(2)
+    log = str(tmp_path / "stderr.txt")
+    fd = os.open(log, os.O_WRONLY | os.O_CREAT | os.O_TRUNC)
+    os.dup2(fd, 2)
+    try:
+        host.Problem(wd, "GT-K1.in")
+    finally:
+        os.dup2(fd_saved, 2)
+        os.close(fd)
+        del os.environ["PNFAM_B200_TBC_MEM_GB"], os.environ["PNFAM_B200_SETUP_TIMING"]
+    assert open(log).read().count("2BC z contraction") >= 2          # really chunked
+    assert compare_files(os.path.join(wd, "GT-K1.tbc"), os.path.join(src, "GT-K1.tbc")) < 1e-12
