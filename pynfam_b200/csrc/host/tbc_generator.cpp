@@ -761,10 +761,16 @@ TbcField generate_two_body_current_field(const TbcProblem& s) {
   std::vector<double> raw[6];
   for (auto& v : raw) v.assign(nxy, 0.0);
 
-  // z contraction for all (z_a, z_c) of a chunk of z_a values (memory bound: 4 GB by default)
+  // z contraction for all (z_a, z_c) of a chunk of z_a values (memory bound: a quarter of the RAM by default)
   const int nz1 = t.nzx + 1;
   const size_t per_za = (size_t)nz1 * wsz * sizeof(double);
-  double mem_gb = 4.0;                                // PNFAM_B200_TBC_MEM_GB: bound on the z-contracted densities kept at once
+  // bound on the z-contracted densities kept at once: a quarter of the physical memory, at least 4 GB (PNFAM_B200_TBC_MEM_GB);
+  // with several chunks the radial elements are recomputed per chunk
+  double mem_gb = 4.0;
+  {
+    const long pages = sysconf(_SC_PHYS_PAGES), psize = sysconf(_SC_PAGE_SIZE);
+    if (pages > 0 && psize > 0) mem_gb = std::max(4.0, 0.25 * (double)pages * (double)psize / 1073741824.0);
+  }
   if (const char* e = getenv("PNFAM_B200_TBC_MEM_GB")) mem_gb = std::max(1e-4, atof(e));
   const int za_chunk = (int)std::max<size_t>(1, std::min<size_t>(nz1, (size_t)(mem_gb * 1073741824.0) / std::max<size_t>(1, per_za)));
   std::vector<double> W;
