@@ -30,6 +30,8 @@ CASES = [  # (case, source tree, operator K, beta, usep, omega)
     ("Gd162_6sh_usep_Kminus1", "Gd162_GT_open_6sh", -1, "+", True, 1.5 + 0.75j),
     # a basis size of BASELINE.json configs[4]: about an hour of the reference on 6 threads (the .tbc is 0.9 MB)
     ("Gd162_12sh_K0", "Gd162_SKOP_12sh", 0, "-", False, 2.0 + 1.0j),
+    ("Gd162_12sh_K1", "Gd162_SKOP_12sh", 1, "-", False, 2.0 + 1.0j),
+    ("Gd162_12sh_usep_K0", "Gd162_SKOP_12sh", 0, "-", True, 2.0 + 1.0j),
 ]
 
 
