@@ -25,7 +25,7 @@ from pynfam_b200 import host
 GEN = os.path.join(GOLDEN, "tbc_generator")
 GEN_CASES = ["S40_usep_K0", "S40_usep_K1", "S40_betaplus_K1", "S40_betaplus_usep_K0", "Gd162_6sh_usep_K1", "Gd162_6sh_K0",
              "Gd163_blocked_K0", "Gd163_blocked_usep_K0", "Gd162_finiteT_K1", "S40_Kminus1", "Gd162_6sh_usep_Kminus1",
-             "Gd162_12sh_K0", "Gd162_12sh_K1"]    # 12 shells: a basis size of BASELINE.json configs[4]; 9-13 minutes of the reference each
+             "Gd162_12sh_K0", "Gd162_12sh_K1", "Gd162_12sh_usep_K0"]    # 12 shells: a basis size of BASELINE.json configs[4]; 9-22 minutes of the reference each
 
 
 def records(path):
